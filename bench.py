@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — pileup base-calls scored per second on the demuxlet LLK path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload demux|freemux]
+
+One "step" = one pass of the hot path (pscl_demux_score: accumulation kernel + per-cell epilogue)
+over one synthetic pileup of BASELINE.json configs[1] (10k cells x 8 samples x 100k SNPs,
+alpha in {0, 0.5}) per GPU.  With N > 1 every rank owns an independent barcode shard of that
+same shape (weak scaling, no data-path collective).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "pileup base-calls scored/sec (demuxlet LLK)"
+UNIT = "base-calls/s"
+ALPHAS = [0.0, 0.5]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="demux", choices=["demux", "freemux"])
+    ap.add_argument("--cells", type=int, default=0, help="override the cell count (debug)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    from popscle_b200 import synth
+    cfg = dict(synth.CONFIGS[2 if args.workload == "demux" else 3])
+    if args.cells:
+        cfg["C"] = args.cells
+    return cfg
+
+
+def make_workload(args, rank):
+    from popscle_b200 import synth
+    cfg = workload_config(args)
+    seed = 20260101 + (2 if args.workload == "demux" else 3) + 1000 * rank
+    s = synth.make_pileup(cfg["C"], cfg["nv"], cfg["V"], cfg["kbar"], seed)
+    gp = synth.gt_to_gp(s.geno) if args.workload == "demux" else None
+    return cfg, s, gp
+
+
+def algorithmic_bytes_demux(plp, nv):
+    """10 B per base-call tuple + 12*nv B genotype gather per pair + 160 B per cell."""
+    return 10 * plp.n_reads + 12 * nv * plp.n_pairs + 160 * plp.n_cells
+
+
+def algorithmic_bytes_fmx_iter(plp, nS):
+    return (72 + 4 + 24 * nS) * plp.n_pairs + 8 * plp.n_cells * (nS * (nS + 1) // 2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key):
+    """per-launch dram bytes of the dominant kernel from the committed ncu summary, if any"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+def cpu_baseline_demux(s, gp, target_s, threads):
+    """Times the oracle (CPU restatement of cmd_cram_demuxlet.cpp:636-991, one log() per term like
+    the reference) on a bounded sample of the SAME workload: the first M cells."""
+    import oracle_py as orc
+    plp = s.plp
+    m0 = min(plp.n_cells, max(threads * 4, 32))
+    t0 = time.perf_counter()
+    orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m0, n_threads=threads)
+    dt = time.perf_counter() - t0
+    rate = max(m0 / max(dt, 1e-6), 1e-9)  # cells/s
+    m = int(min(plp.n_cells, max(m0, rate * target_s)))
+    t0 = time.perf_counter()
+    orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
+    dt = time.perf_counter() - t0
+    reads = int(plp.pair_read_ptr[plp.cell_ptr[m]])
+    return reads / dt, m, reads, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference binary
+    cannot be linked here or on the GPU box (htslib absent), so this arm times the
+    oracle port of cmd_cram_demuxlet.cpp:636-991 on all host threads, each step a bounded sample."""
+    if rank != 0:
+        return
+    cfg, s, gp = make_workload(args, 0)
+    threads = os.cpu_count() or 1
+    import oracle_py as orc
+    plp = s.plp
+    # size one step to ~ cpu_seconds / (steps + warmup)
+    per_step = max(1.0, args.cpu_seconds * 4 / max(1, args.steps + args.warmup))
+    m0 = min(plp.n_cells, max(threads * 4, 32))
+    t0 = time.perf_counter(); orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m0, n_threads=threads); dt = time.perf_counter() - t0
+    m = int(min(plp.n_cells, max(m0, m0 / dt * per_step)))
+    reads = int(plp.pair_read_ptr[plp.cell_ptr[m]])
+    for _ in range(args.warmup):
+        orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
+    dt = time.perf_counter() - t0
+    v = reads * args.steps / dt
+    sample = f"first {m} of {plp.n_cells} cells ({reads} base-calls) per step"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "demuxlet configs[1]: 10k cells x 8 samples x 100k SNPs, alpha {0,0.5}",
+                       "cells": plp.n_cells, "samples": cfg["nv"], "snps": cfg["V"], "pairs": plp.n_pairs,
+                       "base_calls": plp.n_reads},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.workload == "freemux":
+        from popscle_b200 import bench_fmx
+        bench_fmx.main(args, rank, local_rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from popscle_b200 import Context, _build
+    _build.build_cuda()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, s, gp = make_workload(args, rank)
+    plp, nv = s.plp, cfg["nv"]
+    stream = torch.cuda.current_stream()
+    ctx = Context(local_rank, stream=stream.cuda_stream)
+
+    # ---- device-resident arm ("value") ----------------------------------------------------------
+    dplp = ctx.upload(plp)
+    ctx.demux_set_geno(gp, None, plp.n_snps)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        ctx.demux_score(dplp, ALPHAS, 0.5)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    main_ms = []
+    barrier()
+    for a, b in ev:
+        flush.zero_()  # L2 flush between timed iterations (untimed)
+        a.record(stream)
+        ctx.demux_score(dplp, ALPHAS, 0.5)
+        b.record(stream)
+        b.synchronize()
+        main_ms.append(ctx.demux_last_kernel_ms()[0])
+    barrier()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_ms_max = float(t.item())
+    nreads = torch.tensor([plp.n_reads], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nreads, op=dist.ReduceOp.SUM)
+    total_reads = float(nreads.item())
+    value = total_reads * args.steps / (t_ms_max * 1e-3)
+
+    # ---- end-to-end arm: host buffers through the one-call C ABI (H2D + kernels + D2H) -----------
+    def pin(a):
+        t_ = torch.from_numpy(a).pin_memory()
+        return t_, t_.numpy()
+    keep = []
+    from popscle_b200 import Pileup
+    arrs = {}
+    for name in ("cell_ptr", "pair_snp", "pair_read_ptr", "read_allele", "read_qual"):
+        t_, v_ = pin(getattr(plp, name)); keep.append(t_); arrs[name] = v_
+    gp_t, gp_pin = pin(gp); keep.append(gp_t)
+    hplp = Pileup(plp.n_cells, plp.n_snps, arrs["cell_ptr"], arrs["pair_snp"], arrs["pair_read_ptr"],
+                  arrs["read_allele"], arrs["read_qual"], None)
+    h2d = sum(v.nbytes for v in arrs.values()) + gp_pin.nbytes
+    d2h = 160 * plp.n_cells
+    for _ in range(2):
+        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = total_reads * e2e_steps / float(e2e_t.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        k_ms = float(np.mean(main_ms))
+        abytes = algorithmic_bytes_demux(plp, nv)
+        achieved = abytes / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic("k_demux_default"), "kernel": f"k_demux_default<{nv}>",
+                "kernel_ms": k_ms, "algorithmic_bytes": abytes, "peak_source": peak_src}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": t_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "demuxlet configs[1]: 10k cells x 8 samples x 100k SNPs, alpha {0,0.5}",
+                           "cells_per_gpu": plp.n_cells, "samples": nv, "snps": plp.n_snps, "pairs_per_gpu": plp.n_pairs,
+                           "base_calls_per_gpu": plp.n_reads, "sharding": f"barcodes x{world}, no collective",
+                           "l2": "flushed between timed steps (256 MiB memset, untimed)"},
+                "roofline": roof,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "api": "pscl_demux_run (pinned host buffers in, per-cell records out)"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, m, reads, dt = cpu_baseline_demux(s, gp, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {m} of {plp.n_cells} cells ({reads} base-calls) in {dt:.1f}s; "
+                                              "oracle port of cmd_cram_demuxlet.cpp:636-991"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

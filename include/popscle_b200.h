@@ -1,0 +1,223 @@
+/*
+ * popscle_b200.h — C ABI of the B200-native demuxlet / freemuxlet genotype-likelihood engine.
+ *
+ * The reference (statgen/popscle) has no plugin / FFI layer: each command is one function
+ * `int32_t cmdXxx(int32_t argc, char** argv)` (reference commands.h:33-38, cramore.cpp:43-45).
+ * The seam this library replaces is the block of each command body that sits AFTER
+ * `sc_dropseq_lib_t::load_from_plp` has returned (cmd_cram_demuxlet.cpp:122,
+ * cmd_cram_freemux2.cpp:87) and BEFORE the `hprintf` row writers
+ * (cmd_cram_demuxlet.cpp:993, cmd_cram_freemux2.cpp:608-665).  Each entry point below cites the
+ * reference lines it stands in for.  The state that crosses the seam in the reference is
+ * `sc_dropseq_lib_t` (sc_drop_seq.h:130-184) — nested std::maps — which is flattened here to a
+ * cell-major CSR / SoA pileup image.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; all buffers are caller-owned HOST memory unless a name ends
+ *    in `_dev` (then it is a CUDA device pointer on the context's GPU);
+ *  - every function returns PSCL_OK (0) or a negative pscl_status; the message for the last
+ *    failure of a context is available from pscl_last_error().  Nothing throws across the ABI
+ *    (the reference's error() prints "FATAL ERROR" and throws, Error.cpp:29-42; the host wrapper
+ *    re-creates that behaviour from the status code);
+ *  - there is NO CPU fallback: without a CUDA device pscl_create() fails with PSCL_ENODEV.
+ */
+#ifndef POPSCLE_B200_H
+#define POPSCLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSCL_ABI_VERSION 1
+
+typedef enum pscl_status {
+  PSCL_OK = 0,
+  PSCL_EINVAL = -1,  /* bad argument (message says which)                           */
+  PSCL_ENODEV = -2,  /* no usable CUDA device / wrong architecture                  */
+  PSCL_ECUDA = -3,   /* CUDA runtime error (message carries cudaGetErrorString)     */
+  PSCL_ENOMEM = -4,  /* device or host allocation failed                            */
+  PSCL_ESTATE = -5   /* call sequence error (e.g. EM step before init)              */
+} pscl_status;
+
+/* droplet types, as printed in DROPLET.TYPE (cmd_cram_demuxlet.cpp:925-988,
+ * cmd_cram_freemux2.cpp:663: types 0=SNG 1=DBL 2=AMB) */
+enum { PSCL_SNG = 0, PSCL_DBL = 1, PSCL_AMB = 2 };
+
+/* ------------------------------------------------------------------------------------------
+ * Pileup image (replaces sc_dropseq_lib_t::cell_umis / snp_umis / snps, sc_drop_seq.h:158-173).
+ * Cell-major CSR.  A "pair" is one (cell, SNP) with >= 1 base-call, i.e. one entry of
+ * cell_umis[cell]; pairs of a cell are sorted by ascending SNP id (std::map order,
+ * cmd_cram_demuxlet.cpp:656).  A "read" is one base-call that passed --min-BQ, already
+ * capped at --cap-BQ (sc_drop_seq.cpp:361-369).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pscl_pileup {
+  int32_t n_cells;              /* C  = scl.nbcs                                               */
+  int32_t n_snps;               /* V  = scl.nsnps                                              */
+  int64_t n_pairs;              /* P                                                           */
+  int64_t n_reads;              /* N                                                           */
+  const int64_t* cell_ptr;      /* [C+1] pair range of each cell                               */
+  const int32_t* pair_snp;      /* [P]   SNP id of the pair                                    */
+  const int64_t* pair_read_ptr; /* [P+1] read range of each pair                               */
+  const uint8_t* read_allele;   /* [N]   0 = REF, 1 = ALT, 2 = other (sc_drop_seq.cpp:58)      */
+  const uint8_t* read_qual;     /* [N]   phred base quality, 0..93                             */
+  const double* snp_af;         /* [V]   AF column of .var.gz (freemuxlet prior); may be NULL
+                                         for demuxlet                                          */
+} pscl_pileup;
+
+/* Genotype table (replaces sc_snp_t::gps, sc_drop_seq.h:29-37, filled at
+ * sc_drop_seq.cpp:287-315 — i.e. AFTER the geno-error mixing). */
+typedef struct pscl_geno {
+  int32_t n_samples;     /* nv = vr.get_nsamples()                                              */
+  const double* gp;      /* [V * nv * 3] P(genotype = 0/1/2) per SNP, sample; rows of SNPs with
+                            has_gp == 0 are ignored                                             */
+  const uint8_t* has_gp; /* [V] 1 if snps[v].gps != NULL (cmd_cram_demuxlet.cpp:733); NULL = all 1 */
+} pscl_geno;
+
+/* ------------------------------------------------------------------------------------------
+ * demuxlet — replaces cmd_cram_demuxlet.cpp:636-991 (per-barcode loop: pG fold :655-725,
+ * pair grid :733-747, priors / logAdd sums :788-821, best/next scans :827-906,
+ * SNG/DBL/AMB decision :925-991).  One record per cell = the numeric content of one `.best`
+ * row (:993-1013).  Indices are sample indices (host maps them to vr.get_sample_id_at) and
+ * alpha-grid indices (host prints gridAlpha[idx]).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pscl_demux_opts {
+  int32_t n_alpha;        /* |gridAlpha|; must be >= 2 (reference divides by nAlpha-1, :794)    */
+  const double* alphas;   /* gridAlpha; alphas[0] is taken as the singlet plane (:806,:828)     */
+  double doublet_prior;   /* --doublet-prior, default 0.5 (:32)                                 */
+} pscl_demux_opts;
+
+typedef struct pscl_demux_cell {
+  int32_t n_snps;                               /* cell_umis[i].size() (:996)                   */
+  int32_t type;                                 /* PSCL_SNG / PSCL_DBL / PSCL_AMB               */
+  int32_t best_j, best_k, best_a;               /* BEST.GUESS  (:999)                           */
+  int32_t next_j, next_k, next_a;               /* NEXT.GUESS  (:1001)                          */
+  int32_t sng_best, sng_next;                   /* SNG.BEST.GUESS / SNG.NEXT.GUESS              */
+  int32_t dbl_best_j, dbl_best_k, dbl_best_a;   /* DBL.BEST.GUESS (:1011)                       */
+  int32_t dbl_next_j, dbl_next_k, dbl_next_a;   /* second-best doublet (used by :933-939)       */
+  double best_llk, next_llk;                    /* BEST.LLK, NEXT.LLK                           */
+  double best_pp;                               /* BEST.POSTERIOR — exp() only in the DBL branch
+                                                   (:927 vs :949,:970), reproduced as is        */
+  double sng_pp;                                /* SNG.POSTERIOR  = exp(sngLLK - sumLLK) (:990) */
+  double sng_best_llk, sng_next_llk;
+  double sng_only_pp;                           /* SNG.ONLY.POSTERIOR (:991)                    */
+  double dbl_best_llk, dbl_next_llk;
+  double sum_llk, sng_llk;                      /* the two logAdd sums (:791, init -1e-300 sic) */
+  double reserved_;                             /* pad to 160 bytes                             */
+} pscl_demux_cell;
+
+/* ------------------------------------------------------------------------------------------
+ * freemuxlet — replaces cmd_cram_freemux2.cpp:117-163 (stage 1), :184-261 (sort + greedy
+ * seeding), :277-288 (cluster pileup build), :373-605 (EM) ; `mode_old` selects the EM variant
+ * of cmd_cram_freemuxlet.cpp:456-653 (geno_error only on the last iteration, no early stop,
+ * cluster ids not reset) — its pairwise/vote seeding (:184-346) is NOT implemented, so old
+ * mode needs init_clust.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pscl_fmx_opts {
+  int32_t n_clusters;         /* --nsample                                                      */
+  double doublet_prior;       /* default 0.5  (cmd_cram_freemux2.cpp:19)                        */
+  double geno_error;          /* default 0.1  (:20)                                             */
+  int32_t max_iter;           /* reference hard-codes 10 (:373)                                 */
+  int32_t early_stop;         /* 1 = break when nchanged == 0 (:601)                            */
+  double frac_init_clust;     /* default 1.0 (:28)                                              */
+  double singlet_score_thres; /* default -1e300 (:26)                                           */
+  int32_t mode_old;           /* 0 = freemux2 (popscle freemuxlet), 1 = freemuxlet-old EM rules */
+} pscl_fmx_opts;
+
+typedef struct pscl_fmx_cell {
+  int32_t n_snps, n_reads;              /* NUM.SNPS, NUM.READS (incl. allele==2, :150)          */
+  int32_t type;                         /* 0 SNG 1 DBL 2 AMB                                     */
+  int32_t clust;                        /* clusts[i] after the last classify (-1 unless SNG)     */
+  int32_t best_j, best_k, next_j, next_k;
+  int32_t sng_best, sng_next;
+  int32_t dbl_best_j, dbl_best_k, dbl_next_j, dbl_next_k;
+  int32_t init_clust;                   /* cluster after seeding (clust0)                        */
+  int32_t reserved_;
+  double best_llk, next_llk;
+  double best_pp;                       /* stored as a LOG in all branches (:526,:549,:571)      */
+  double sng_pp, sng_only_pp;
+  double sng_best_llk, sng_next_llk, dbl_best_llk, dbl_next_llk;
+  double sum_llk;
+  double llk0, llk2;                    /* stage-1 DBL.LLK / SNG.LLK of .lmix (:161)             */
+} pscl_fmx_cell;
+
+typedef struct pscl_fmx_result {
+  int32_t n_iter;      /* EM iterations executed                                                */
+  int32_t n_changed;   /* nchanged of the last iteration                                        */
+  int32_t n_singlet, n_doublet, n_ambiguous;
+} pscl_fmx_result;
+
+typedef struct pscl_ctx pscl_ctx;
+typedef struct pscl_plp pscl_plp; /* device-resident pileup image */
+
+/* ---- context ---- */
+int pscl_abi_version(void);
+/* Opens CUDA device `device` (ordinal).  Fails with PSCL_ENODEV when there is no sm_100 GPU. */
+int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen);
+void pscl_destroy(pscl_ctx* ctx);
+const char* pscl_last_error(const pscl_ctx* ctx);
+/* cudaStream_t the context launches on (as void*), for callers that time with CUDA events
+ * or order their own work (e.g. a torch.distributed all-reduce) after ours. */
+void* pscl_stream(pscl_ctx* ctx);
+int pscl_sync(pscl_ctx* ctx);
+
+/* ---- pileup upload: host CSR -> packed device image (1 B/read, 4+4 B/pair) ---- */
+int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* host, pscl_plp** out);
+void pscl_plp_free(pscl_ctx* ctx, pscl_plp* plp);
+
+/* ---- demuxlet ---- */
+/* Uploads the genotype table (replicated per GPU).  Replaces the previous one. */
+int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t n_snps);
+/* Scores cells [cell_begin, cell_end) of the resident pileup.  Results stay on the device;
+ * kernels are enqueued on pscl_stream() and the call returns without synchronising. */
+int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
+                     int32_t cell_begin, int32_t cell_end);
+/* Copies the per-cell records of the last pscl_demux_score() to `out[cell_end-cell_begin]`
+ * (synchronises).  `llk_grid`, if not NULL, receives the live part of llksAB as
+ * [cell][j][k][n] doubles (n_cells * nv * nv * n_alpha): singlets at [j][0][0], doublets at
+ * [j][k][n>=1] (j != k); entries the reference never reads (:806,:883-906) are NaN.
+ * Requires pscl_demux_score to have been called with the grid enabled (see below). */
+int pscl_demux_fetch(pscl_ctx* ctx, pscl_demux_cell* out, double* llk_grid);
+/* Debug switch: keep the per-cell LLK grid on the device so pscl_demux_fetch can return it. */
+int pscl_demux_keep_grid(pscl_ctx* ctx, int enable);
+/* One-call convenience used by the CLI host: upload (if needed) + score + fetch. */
+int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_geno* geno,
+                   const pscl_demux_opts* opts, pscl_demux_cell* out, double* llk_grid);
+/* Device time (ms, CUDA events on pscl_stream) of the kernels of the last pscl_demux_score. */
+int pscl_demux_last_kernel_ms(pscl_ctx* ctx, float* ms_main, float* ms_total);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+int64_t pscl_launch_count(const pscl_ctx* ctx);
+
+/* ---- freemuxlet ---- */
+/* Whole run on one GPU: stage 1, seeding (or init_clust[C], -1 = unassigned; NULL = greedy
+ * seeding), cluster build, EM.  `clust_gl` (nullable) receives [V][n_clusters][9] cluster
+ * genotype likelihoods (absent entries = 1.0, as operator[] default-constructs them,
+ * cmd_cram_freemux2.cpp:634); `clust_cnt` (nullable) [V][n_clusters][3] = nreads,nref,nalt. */
+int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts,
+                 const int32_t* init_clust, pscl_fmx_cell* out, double* clust_gl,
+                 int32_t* clust_cnt, pscl_fmx_result* res);
+
+/* Step-level API for SNP-sharded multi-GPU EM: each rank uploads the pairs of its
+ * SNP range (cells keep global ids), and the caller all-reduces the LLK partials between
+ * E-step and classify. */
+int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp* plp, const pscl_fmx_opts* opts);
+/* stage 1: per-pair 9-GL (kept on device) + per-cell partial llk0/llk2/nsnps/nreads written
+ * to stage1_dev[4*C] doubles (llk0, llk2, nsnps, nreads planes) for the caller to all-reduce. */
+int pscl_fmx_stage1(pscl_ctx* ctx, double* stage1_dev);
+/* greedy seeding on the local pairs; needs the all-reduced scores. Only meaningful unsharded. */
+int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, int32_t* clust_dev);
+/* (re)build the cluster table from membership clust_dev[C] (-1 = none): ordered merges. */
+int pscl_fmx_mstep(pscl_ctx* ctx, const int32_t* clust_dev);
+/* E-step partial LLKs of the local SNP range into llk_dev[C * npairs] (overwritten). */
+int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev);
+/* epilogue + classify from (all-reduced) llk_dev; updates clust_dev, cell records; returns
+ * nchanged etc. in *res (synchronises). */
+int pscl_fmx_classify(pscl_ctx* ctx, const double* llk_dev, int32_t* clust_dev,
+                      pscl_fmx_result* res);
+int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POPSCLE_B200_H */

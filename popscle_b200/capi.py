@@ -1,0 +1,360 @@
+"""ctypes binding of libpopscle_b200.so (include/popscle_b200.h).
+
+Thin host-side mirror used by the tests, bench.py and the multi-GPU drivers; the C++ CLI host
+(popscle_b200/host/) links the same library directly.  There is NO CPU fallback here: if the
+shared library is missing, or no sm_100 device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpopscle_b200.so")
+
+PSCL_OK = 0
+PSCL_SNG, PSCL_DBL, PSCL_AMB = 0, 1, 2
+TYPE_NAMES = {0: "SNG", 1: "DBL", 2: "AMB"}
+
+
+class PsclError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"popscle_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CPileup(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("n_snps", C.c_int32), ("n_pairs", C.c_int64), ("n_reads", C.c_int64),
+                ("cell_ptr", C.c_void_p), ("pair_snp", C.c_void_p), ("pair_read_ptr", C.c_void_p),
+                ("read_allele", C.c_void_p), ("read_qual", C.c_void_p), ("snp_af", C.c_void_p)]
+
+
+class CGeno(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("gp", C.c_void_p), ("has_gp", C.c_void_p)]
+
+
+class CDemuxOpts(C.Structure):
+    _fields_ = [("n_alpha", C.c_int32), ("alphas", C.c_void_p), ("doublet_prior", C.c_double)]
+
+
+class CFmxOpts(C.Structure):
+    _fields_ = [("n_clusters", C.c_int32), ("doublet_prior", C.c_double), ("geno_error", C.c_double),
+                ("max_iter", C.c_int32), ("early_stop", C.c_int32), ("frac_init_clust", C.c_double),
+                ("singlet_score_thres", C.c_double), ("mode_old", C.c_int32)]
+
+
+class CFmxResult(C.Structure):
+    _fields_ = [("n_iter", C.c_int32), ("n_changed", C.c_int32), ("n_singlet", C.c_int32),
+                ("n_doublet", C.c_int32), ("n_ambiguous", C.c_int32)]
+
+
+# numpy views of the per-cell records (layout == the C structs; checked against sizeof in tests)
+DEMUX_CELL_DTYPE = np.dtype([
+    ("n_snps", "<i4"), ("type", "<i4"),
+    ("best_j", "<i4"), ("best_k", "<i4"), ("best_a", "<i4"),
+    ("next_j", "<i4"), ("next_k", "<i4"), ("next_a", "<i4"),
+    ("sng_best", "<i4"), ("sng_next", "<i4"),
+    ("dbl_best_j", "<i4"), ("dbl_best_k", "<i4"), ("dbl_best_a", "<i4"),
+    ("dbl_next_j", "<i4"), ("dbl_next_k", "<i4"), ("dbl_next_a", "<i4"),
+    ("best_llk", "<f8"), ("next_llk", "<f8"), ("best_pp", "<f8"), ("sng_pp", "<f8"),
+    ("sng_best_llk", "<f8"), ("sng_next_llk", "<f8"), ("sng_only_pp", "<f8"),
+    ("dbl_best_llk", "<f8"), ("dbl_next_llk", "<f8"), ("sum_llk", "<f8"), ("sng_llk", "<f8"),
+    ("reserved_", "<f8"),
+])
+assert DEMUX_CELL_DTYPE.itemsize == 160
+
+FMX_CELL_DTYPE = np.dtype([
+    ("n_snps", "<i4"), ("n_reads", "<i4"), ("type", "<i4"), ("clust", "<i4"),
+    ("best_j", "<i4"), ("best_k", "<i4"), ("next_j", "<i4"), ("next_k", "<i4"),
+    ("sng_best", "<i4"), ("sng_next", "<i4"),
+    ("dbl_best_j", "<i4"), ("dbl_best_k", "<i4"), ("dbl_next_j", "<i4"), ("dbl_next_k", "<i4"),
+    ("init_clust", "<i4"), ("reserved_", "<i4"),
+    ("best_llk", "<f8"), ("next_llk", "<f8"), ("best_pp", "<f8"), ("sng_pp", "<f8"), ("sng_only_pp", "<f8"),
+    ("sng_best_llk", "<f8"), ("sng_next_llk", "<f8"), ("dbl_best_llk", "<f8"), ("dbl_next_llk", "<f8"),
+    ("sum_llk", "<f8"), ("llk0", "<f8"), ("llk2", "<f8"),
+])
+assert FMX_CELL_DTYPE.itemsize == 160
+
+
+@dataclass
+class Pileup:
+    """Host-side flat pileup (the content of sc_dropseq_lib_t after load_from_plp,
+    reference sc_drop_seq.cpp:103-384), cell-major CSR."""
+    n_cells: int
+    n_snps: int
+    cell_ptr: np.ndarray       # int64 [C+1]
+    pair_snp: np.ndarray       # int32 [P]
+    pair_read_ptr: np.ndarray  # int64 [P+1]
+    read_allele: np.ndarray    # uint8 [N]
+    read_qual: np.ndarray      # uint8 [N]
+    snp_af: np.ndarray | None = None  # float64 [V]
+
+    def __post_init__(self):
+        self.cell_ptr = np.ascontiguousarray(self.cell_ptr, dtype=np.int64)
+        self.pair_snp = np.ascontiguousarray(self.pair_snp, dtype=np.int32)
+        self.pair_read_ptr = np.ascontiguousarray(self.pair_read_ptr, dtype=np.int64)
+        self.read_allele = np.ascontiguousarray(self.read_allele, dtype=np.uint8)
+        self.read_qual = np.ascontiguousarray(self.read_qual, dtype=np.uint8)
+        if self.snp_af is not None:
+            self.snp_af = np.ascontiguousarray(self.snp_af, dtype=np.float64)
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.pair_snp.shape[0])
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.read_allele.shape[0])
+
+    def c_struct(self, cls=CPileup):
+        s = cls()
+        s.n_cells, s.n_snps, s.n_pairs, s.n_reads = self.n_cells, self.n_snps, self.n_pairs, self.n_reads
+        s.cell_ptr = self.cell_ptr.ctypes.data
+        s.pair_snp = self.pair_snp.ctypes.data
+        s.pair_read_ptr = self.pair_read_ptr.ctypes.data
+        s.read_allele = self.read_allele.ctypes.data
+        s.read_qual = self.read_qual.ctypes.data
+        s.snp_af = self.snp_af.ctypes.data if self.snp_af is not None else None
+        return s
+
+    def slice_cells(self, c0: int, c1: int) -> "Pileup":
+        """Barcode shard [c0, c1) as an independent pileup (demuxlet multi-GPU sharding)."""
+        p0, p1 = int(self.cell_ptr[c0]), int(self.cell_ptr[c1])
+        r0, r1 = int(self.pair_read_ptr[p0]), int(self.pair_read_ptr[p1])
+        return Pileup(c1 - c0, self.n_snps, self.cell_ptr[c0:c1 + 1] - p0, self.pair_snp[p0:p1],
+                      self.pair_read_ptr[p0:p1 + 1] - r0, self.read_allele[r0:r1], self.read_qual[r0:r1], self.snp_af)
+
+    def slice_snps(self, v0: int, v1: int) -> "Pileup":
+        """SNP shard [v0, v1): same cells (global ids), only the pairs of those SNPs; SNP ids stay
+        global so the AF table and cluster table index the same way (freemuxlet SNP sharding)."""
+        keep = (self.pair_snp >= v0) & (self.pair_snp < v1)
+        pair_cell = np.repeat(np.arange(self.n_cells, dtype=np.int64), np.diff(self.cell_ptr))
+        cnt = np.bincount(pair_cell[keep], minlength=self.n_cells)
+        cell_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        nrd = np.diff(self.pair_read_ptr)
+        rkeep = np.repeat(keep, nrd)
+        prp = np.concatenate([[0], np.cumsum(nrd[keep])]).astype(np.int64)
+        return Pileup(self.n_cells, self.n_snps, cell_ptr, self.pair_snp[keep], prp, self.read_allele[rkeep],
+                      self.read_qual[rkeep], self.snp_af)
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PsclError(-2, f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    sigs = {
+        "pscl_abi_version": (C.c_int, []),
+        "pscl_create": (C.c_int, [C.c_int, C.POINTER(vp), C.c_char_p, C.c_size_t]),
+        "pscl_destroy": (None, [vp]),
+        "pscl_last_error": (C.c_char_p, [vp]),
+        "pscl_stream": (vp, [vp]),
+        "pscl_set_stream": (C.c_int, [vp, vp]),
+        "pscl_sync": (C.c_int, [vp]),
+        "pscl_launch_count": (i64, [vp]),
+        "pscl_set_partial_budget": (C.c_int, [vp, C.c_size_t]),
+        "pscl_plp_upload": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(vp)]),
+        "pscl_plp_free": (None, [vp, vp]),
+        "pscl_demux_set_geno": (C.c_int, [vp, C.POINTER(CGeno), i32]),
+        "pscl_demux_score": (C.c_int, [vp, vp, C.POINTER(CDemuxOpts), i32, i32]),
+        "pscl_demux_fetch": (C.c_int, [vp, vp, vp]),
+        "pscl_demux_keep_grid": (C.c_int, [vp, C.c_int]),
+        "pscl_demux_force_general": (C.c_int, [vp, C.c_int]),
+        "pscl_demux_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CGeno), C.POINTER(CDemuxOpts), vp, vp]),
+        "pscl_demux_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "pscl_fmx_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult)]),
+        "pscl_fmx_init": (C.c_int, [vp, vp, C.POINTER(CFmxOpts)]),
+        "pscl_fmx_stage1": (C.c_int, [vp, vp]),
+        "pscl_fmx_seed": (C.c_int, [vp, vp, vp]),
+        "pscl_fmx_mstep": (C.c_int, [vp, vp]),
+        "pscl_fmx_estep": (C.c_int, [vp, i32, vp]),
+        "pscl_fmx_classify": (C.c_int, [vp, vp, vp, C.POINTER(CFmxResult)]),
+        "pscl_fmx_fetch": (C.c_int, [vp, vp, vp, vp]),
+        "pscl_fmx_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "pscl_abi_version", "pscl_create", "pscl_destroy", "pscl_last_error", "pscl_stream", "pscl_set_stream",
+    "pscl_sync", "pscl_launch_count", "pscl_set_partial_budget", "pscl_plp_upload", "pscl_plp_free",
+    "pscl_demux_set_geno", "pscl_demux_score", "pscl_demux_fetch", "pscl_demux_keep_grid",
+    "pscl_demux_force_general", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_fmx_run", "pscl_fmx_init",
+    "pscl_fmx_stage1", "pscl_fmx_seed", "pscl_fmx_mstep", "pscl_fmx_estep", "pscl_fmx_classify",
+    "pscl_fmx_fetch", "pscl_fmx_last_kernel_ms",
+]
+
+
+class Context:
+    """One pscl_ctx (one GPU)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self.lib.pscl_create(device, C.byref(h), err, len(err))
+        if rc != PSCL_OK:
+            raise PsclError(rc, err.value.decode())
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self._chk(self.lib.pscl_set_stream(self.h, C.c_void_p(stream)))
+
+    def _chk(self, rc: int):
+        if rc != PSCL_OK:
+            raise PsclError(rc, self.lib.pscl_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pscl_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.pscl_stream(self.h) or 0)
+
+    def sync(self):
+        self._chk(self.lib.pscl_sync(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pscl_launch_count(self.h))
+
+    def set_partial_budget(self, nbytes: int):
+        self._chk(self.lib.pscl_set_partial_budget(self.h, nbytes))
+
+    # ---- pileup ----
+    def upload(self, plp: Pileup) -> "DevicePileup":
+        cs = plp.c_struct()
+        out = C.c_void_p()
+        self._chk(self.lib.pscl_plp_upload(self.h, C.byref(cs), C.byref(out)))
+        return DevicePileup(self, out, plp.n_cells, plp.n_snps, plp.n_pairs, plp.n_reads)
+
+    # ---- demuxlet ----
+    def demux_set_geno(self, gp: np.ndarray, has_gp: np.ndarray | None, n_snps: int):
+        gp = np.ascontiguousarray(gp, dtype=np.float64)
+        assert gp.ndim == 3 and gp.shape[0] == n_snps and gp.shape[2] == 3, gp.shape
+        g = CGeno()
+        g.n_samples = gp.shape[1]
+        g.gp = gp.ctypes.data
+        hg = None
+        if has_gp is not None:
+            hg = np.ascontiguousarray(has_gp, dtype=np.uint8)
+            g.has_gp = hg.ctypes.data
+        self._chk(self.lib.pscl_demux_set_geno(self.h, C.byref(g), n_snps))
+        self.sync()  # gp / hg are pageable numpy buffers
+        self._nv = gp.shape[1]
+
+    def demux_keep_grid(self, enable: bool):
+        self._chk(self.lib.pscl_demux_keep_grid(self.h, int(enable)))
+        self._keep = enable
+
+    def demux_force_general(self, enable: bool):
+        self._chk(self.lib.pscl_demux_force_general(self.h, int(enable)))
+
+    def demux_score(self, dplp: "DevicePileup", alphas, doublet_prior: float = 0.5, cell_begin: int = 0,
+                    cell_end: int | None = None):
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        o = CDemuxOpts(len(al), al.ctypes.data, doublet_prior)
+        ce = dplp.n_cells if cell_end is None else cell_end
+        self._chk(self.lib.pscl_demux_score(self.h, dplp.h, C.byref(o), cell_begin, ce))
+        self._dm_shape = (ce - cell_begin, self._nv, self._nv, len(al))
+
+    def demux_fetch(self, want_grid: bool = False):
+        n = self._dm_shape[0]
+        out = np.zeros(n, dtype=DEMUX_CELL_DTYPE)
+        grid = np.empty(self._dm_shape, dtype=np.float64) if want_grid else None
+        self._chk(self.lib.pscl_demux_fetch(self.h, out.ctypes.data, grid.ctypes.data if want_grid else None))
+        return (out, grid) if want_grid else out
+
+    def demux_last_kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self._chk(self.lib.pscl_demux_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def demux_run(self, plp: Pileup, gp: np.ndarray, has_gp, alphas, doublet_prior: float = 0.5,
+                  want_grid: bool = False):
+        """The one-call path of the CLI host: host buffers in, per-cell records out."""
+        gp = np.ascontiguousarray(gp, dtype=np.float64)
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        cs = plp.c_struct()
+        g = CGeno()
+        g.n_samples = gp.shape[1]
+        g.gp = gp.ctypes.data
+        hg = None
+        if has_gp is not None:
+            hg = np.ascontiguousarray(has_gp, dtype=np.uint8)
+            g.has_gp = hg.ctypes.data
+        o = CDemuxOpts(len(al), al.ctypes.data, doublet_prior)
+        out = np.zeros(plp.n_cells, dtype=DEMUX_CELL_DTYPE)
+        grid = np.empty((plp.n_cells, gp.shape[1], gp.shape[1], len(al))) if want_grid else None
+        self._chk(self.lib.pscl_demux_run(self.h, C.byref(cs), C.byref(g), C.byref(o), out.ctypes.data,
+                                          grid.ctypes.data if want_grid else None))
+        return (out, grid) if want_grid else out
+
+    # ---- freemuxlet ----
+    @staticmethod
+    def fmx_opts(n_clusters: int, doublet_prior=0.5, geno_error=0.1, max_iter=10, early_stop=True,
+                 frac_init_clust=1.0, singlet_score_thres=-1e300, mode_old=False) -> CFmxOpts:
+        return CFmxOpts(n_clusters, doublet_prior, geno_error, max_iter, int(early_stop), frac_init_clust,
+                        singlet_score_thres, int(mode_old))
+
+    def fmx_run(self, plp: Pileup, opts: CFmxOpts, init_clust: np.ndarray | None = None, want_clusters=False):
+        cs = plp.c_struct()
+        out = np.zeros(plp.n_cells, dtype=FMX_CELL_DTYPE)
+        res = CFmxResult()
+        ic = None
+        if init_clust is not None:
+            ic = np.ascontiguousarray(init_clust, dtype=np.int32)
+        gl = cnt = None
+        if want_clusters:
+            gl = np.empty((plp.n_snps, opts.n_clusters, 9), dtype=np.float64)
+            cnt = np.empty((plp.n_snps, opts.n_clusters, 3), dtype=np.int32)
+        self._chk(self.lib.pscl_fmx_run(self.h, C.byref(cs), C.byref(opts), ic.ctypes.data if ic is not None else None,
+                                        out.ctypes.data, gl.ctypes.data if gl is not None else None,
+                                        cnt.ctypes.data if cnt is not None else None, C.byref(res)))
+        return out, res, gl, cnt
+
+
+class DevicePileup:
+    def __init__(self, ctx: Context, h, n_cells, n_snps, n_pairs, n_reads):
+        self.ctx, self.h = ctx, h
+        self.n_cells, self.n_snps, self.n_pairs, self.n_reads = n_cells, n_snps, n_pairs, n_reads
+
+    def free(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.pscl_plp_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

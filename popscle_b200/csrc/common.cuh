@@ -1,0 +1,123 @@
+// common.cuh — shared host/device plumbing of libpopscle_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/popscle_b200.h"
+
+#define PSCL_MAX_ALPHA 32 /* pG fold keeps n_alpha*9 values in one warp's registers (<= 9 per lane) */
+
+struct pscl_plp {
+  int32_t C = 0, V = 0;
+  int64_t P = 0, N = 0;
+  // cell-major CSR (device)
+  int64_t* cell_ptr = nullptr;   // [C+1]
+  int32_t* pair_snp = nullptr;   // [P]
+  uint32_t* pair_rd = nullptr;   // [P+1] read offsets (N < 2^32 per device image)
+  uint8_t* rd_aq = nullptr;      // [N] allele<<6 | qual (qual <= 63)
+  double* snp_af = nullptr;      // [V] or null
+  // work items: chunks of <= ITEM_PAIRS pairs of one cell, so that no single warp/CTA owns a
+  // huge cell; items of a cell are contiguous, item_order lists them by descending size
+  int32_t n_items = 0;
+  int32_t* item_cell = nullptr;    // [n_items]
+  int64_t* item_pbeg = nullptr;    // [n_items]
+  int64_t* item_pend = nullptr;    // [n_items]
+  int32_t* item_order = nullptr;   // [n_items]
+  int32_t* cell_item_ptr = nullptr;  // [C+1]
+  std::vector<int32_t> h_cell_item_ptr;
+  std::vector<int64_t> h_cell_ptr;
+  // SNP-major view for the freemuxlet M-step (built lazily)
+  int64_t* snp_ptr = nullptr;    // [V+1]
+  uint32_t* snp_pair = nullptr;  // [P] pair ids, ascending cell id inside one SNP
+  int32_t* pair_cell = nullptr;  // [P]
+  void* scratch_h2d = nullptr;   // int64 staging for pair_read_ptr
+};
+
+struct pscl_fmx_state;
+
+struct pscl_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double* phred_err = nullptr;  // [256] device copy of PhredHelper's phred2Err (staged to smem by kernels)
+  // demuxlet state
+  int32_t nv = 0, geno_V = 0;
+  double* gp = nullptr;       // [V][nv][3]
+  uint8_t* has_gp = nullptr;  // [V] or null (= all)
+  bool keep_grid = false, force_general = false, dm_single_batch = true;
+  int32_t dm_cell_begin = 0, dm_cell_end = 0, dm_nalpha = 0;
+  void* dm_cells = nullptr;   // pscl_demux_cell[cells]
+  size_t dm_cells_cap = 0;
+  double* dm_grid = nullptr;  // [cells][nv][nv][nalpha] when keep_grid
+  size_t dm_grid_cap = 0;
+  double* dm_partial = nullptr;  // [items in batch][nv*nv*nalpha]
+  size_t dm_partial_cap = 0;
+  int* dm_counter = nullptr;     // persistent-kernel work counter
+  size_t partial_budget_bytes = (size_t)1 << 30;
+  float dm_ms_main = 0.f, dm_ms_total = 0.f;
+  bool dm_timed = false;
+  pscl_fmx_state* fmx = nullptr;
+};
+
+static inline int pscl_fail(pscl_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+#include <stdarg.h>
+static inline int pscl_fail(pscl_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define PSCL_CUDA(ctx, call)                                                                        \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return pscl_fail(ctx, e__ == cudaErrorMemoryAllocation ? PSCL_ENOMEM : PSCL_ECUDA,            \
+                       "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static inline int pscl_reserve(pscl_ctx* ctx, T** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes && *p) return PSCL_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  PSCL_CUDA(ctx, cudaMalloc((void**)p, bytes ? bytes : 16));
+  *cap = bytes;
+  return PSCL_OK;
+}
+
+// ---- device helpers --------------------------------------------------------------------------
+// phred -> P(error): PhredHelper.cpp:30 `phred2Err[i] = (i > 1) ? pow(0.1, i*0.1) : 0.75`, filled on
+// the host with the same libm call so the table is bit-identical to the reference's.
+// (single translation unit: popscle_b200.cu includes every part, so these are plain statics)
+static __constant__ double c_alpha[PSCL_MAX_ALPHA];
+
+// Running product kept as (mantissa in [1,2), integer exponent): one log per accumulator at the
+// end instead of one per term (the reference calls log() per (j,k,n) term,
+// cmd_cram_demuxlet.cpp:746).  renorm() moves the double's exponent field into `e`.
+__device__ __forceinline__ void pscl_renorm(double& m, int& e) {
+  int hi = __double2hiint(m);
+  int ex = (hi >> 20) & 0x7ff;
+  if (ex != 0 && ex != 0x7ff) {  // leave 0 / denormal / inf / nan untouched (-> log gives -inf/nan)
+    e += ex - 1023;
+    m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(m));
+  }
+}
+__device__ __forceinline__ double pscl_prod_log(double m, int e) {
+  return log(m) + (double)e * 0.693147180559945309417232121458;
+}

@@ -1,0 +1,211 @@
+// context.inl — context lifetime and pileup upload (part of the single TU popscle_b200.cu)
+
+#define PSCL_ITEM_PAIRS 2048
+
+extern "C" int pscl_abi_version(void) { return PSCL_ABI_VERSION; }
+
+extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen) {
+  auto fail = [&](int code, const std::string& m) {
+    if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
+    return code;
+  };
+  if (!out) return fail(PSCL_EINVAL, "pscl_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(PSCL_ENODEV, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                 " (popscle_b200 has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PSCL_ENODEV, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(PSCL_ECUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(PSCL_ENODEV, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                 "; this library carries sm_100a code only");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(PSCL_ECUDA, cudaGetErrorString(e));
+  pscl_ctx* c = new pscl_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete c;
+    return fail(PSCL_ECUDA, cudaGetErrorString(e));
+  }
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  cudaEventCreate(&c->ev2);
+  // PhredHelper.cpp:30 — same expression, same libm, evaluated on the host
+  double tab[256];
+  for (int i = 0; i < 256; ++i) tab[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;
+  if (cudaMalloc((void**)&c->phred_err, sizeof(tab)) != cudaSuccess ||
+      cudaMemcpy(c->phred_err, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc((void**)&c->dm_counter, 64) != cudaSuccess) {
+    delete c;
+    return fail(PSCL_ENOMEM, "device allocation failed in pscl_create");
+  }
+  *out = c;
+  return PSCL_OK;
+}
+
+static void fmx_state_free(pscl_ctx* ctx);
+
+extern "C" void pscl_destroy(pscl_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  fmx_state_free(ctx);
+  cudaFree(ctx->gp);
+  cudaFree(ctx->has_gp);
+  cudaFree(ctx->dm_cells);
+  cudaFree(ctx->dm_grid);
+  cudaFree(ctx->dm_partial);
+  cudaFree(ctx->dm_counter);
+  cudaFree(ctx->phred_err);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev2);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* pscl_last_error(const pscl_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* pscl_stream(pscl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int pscl_set_stream(pscl_ctx* ctx, void* stream) {
+  if (!ctx) return PSCL_EINVAL;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)stream;
+  ctx->own_stream = false;
+  return PSCL_OK;
+}
+extern "C" int pscl_sync(pscl_ctx* ctx) {
+  if (!ctx) return PSCL_EINVAL;
+  PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSCL_OK;
+}
+extern "C" int64_t pscl_launch_count(const pscl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes) {
+  if (!ctx || bytes < (1u << 20)) return PSCL_EINVAL;
+  ctx->partial_budget_bytes = bytes;
+  return PSCL_OK;
+}
+
+// allele (0/1/2) and phred quality (<= 63) of one base-call packed into one byte
+__global__ void k_pack_reads(const uint8_t* __restrict__ al, const uint8_t* __restrict__ q,
+                             uint8_t* __restrict__ aq, int64_t n, int* bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t a = al[i], b = q[i];
+  if (a > 2 || b > 63) atomicExch(bad, 1);
+  aq[i] = (uint8_t)((a << 6) | (b & 63));
+}
+
+// int64 read offsets -> uint32 (device images hold < 2^32 reads)
+__global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)in[i];
+}
+
+extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
+  if (!p) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  cudaFree(p->cell_ptr); cudaFree(p->pair_snp); cudaFree(p->pair_rd); cudaFree(p->rd_aq);
+  cudaFree(p->snp_af); cudaFree(p->item_cell); cudaFree(p->item_pbeg);
+  cudaFree(p->item_pend); cudaFree(p->item_order); cudaFree(p->cell_item_ptr); cudaFree(p->snp_ptr);
+  cudaFree(p->snp_pair); cudaFree(p->pair_cell); cudaFree(p->scratch_h2d);
+  delete p;
+}
+
+extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!h || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_plp_upload: NULL argument");
+  *out = nullptr;
+  const int32_t C = h->n_cells, V = h->n_snps;
+  const int64_t P = h->n_pairs, N = h->n_reads;
+  if (C < 0 || V < 0 || P < 0 || N < 0) return pscl_fail(ctx, PSCL_EINVAL, "negative size in pscl_pileup");
+  if (!h->cell_ptr || (P > 0 && (!h->pair_snp || !h->pair_read_ptr)) || (N > 0 && (!h->read_allele || !h->read_qual)))
+    return pscl_fail(ctx, PSCL_EINVAL, "pscl_pileup has a NULL array");
+  if (N >= ((int64_t)1 << 32) || P >= ((int64_t)1 << 32))
+    return pscl_fail(ctx, PSCL_EINVAL, "a device pileup image holds < 2^32 pairs/reads; shard the barcodes or SNPs");
+  if (h->cell_ptr[0] != 0 || h->cell_ptr[C] != P)
+    return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr must run from 0 to n_pairs");
+  for (int32_t c = 0; c < C; ++c)
+    if (h->cell_ptr[c + 1] < h->cell_ptr[c]) return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr not monotone at cell %d", c);
+  if (P > 0 && (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N))
+    return pscl_fail(ctx, PSCL_EINVAL, "pair_read_ptr must run from 0 to n_reads");
+  PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
+  pscl_plp* p = new pscl_plp();
+  p->C = C; p->V = V; p->P = P; p->N = N;
+  p->h_cell_ptr.assign(h->cell_ptr, h->cell_ptr + C + 1);
+  // work items
+  std::vector<int32_t> item_cell;
+  std::vector<int64_t> pbeg, pend;
+  p->h_cell_item_ptr.resize(C + 1);
+  for (int32_t c = 0; c < C; ++c) {
+    p->h_cell_item_ptr[c] = (int32_t)item_cell.size();
+    int64_t b = h->cell_ptr[c], e = h->cell_ptr[c + 1], n = e - b;
+    int64_t nch = (n + PSCL_ITEM_PAIRS - 1) / PSCL_ITEM_PAIRS;
+    for (int64_t i = 0; i < nch; ++i) {  // equal split, multiples of 32 pairs
+      int64_t s = b + ((n * i / nch) & ~(int64_t)31), t = (i + 1 == nch) ? e : b + ((n * (i + 1) / nch) & ~(int64_t)31);
+      item_cell.push_back(c); pbeg.push_back(s); pend.push_back(t);
+    }
+  }
+  p->h_cell_item_ptr[C] = (int32_t)item_cell.size();
+  p->n_items = (int32_t)item_cell.size();
+  std::vector<int32_t> order(p->n_items);
+  for (int32_t i = 0; i < p->n_items; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return pend[a] - pbeg[a] > pend[b] - pbeg[b]; });
+
+  auto up = [&](void** d, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(d, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+#define UP(field, src, bytes) if (e == cudaSuccess) e = up((void**)&p->field, src, bytes)
+  UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
+  UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
+  UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1));
+  uint8_t *d_al = nullptr, *d_q = nullptr;
+  int* d_bad = nullptr;
+  if (e == cudaSuccess) e = up((void**)&d_al, h->read_allele, (size_t)N);
+  if (e == cudaSuccess) e = up((void**)&d_q, h->read_qual, (size_t)N);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+  if (e == cudaSuccess && N > 0) {
+    k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, d_bad);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (h->snp_af) UP(snp_af, h->snp_af, sizeof(double) * V);
+  UP(item_cell, item_cell.data(), sizeof(int32_t) * p->n_items);
+  UP(item_pbeg, pbeg.data(), sizeof(int64_t) * p->n_items);
+  UP(item_pend, pend.data(), sizeof(int64_t) * p->n_items);
+  UP(item_order, order.data(), sizeof(int32_t) * p->n_items);
+  UP(cell_item_ptr, p->h_cell_item_ptr.data(), sizeof(int32_t) * (C + 1));
+#undef UP
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
+  if (e == cudaSuccess && P > 0) {
+    k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  int bad = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  // the host vectors above are pageable sources of async copies: drain before they go out of scope
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_al); cudaFree(d_q); cudaFree(d_bad);
+  if (e == cudaSuccess && bad) {
+    pscl_plp_free(ctx, p);
+    return pscl_fail(ctx, PSCL_EINVAL, "read_allele must be 0/1/2 and read_qual <= 63 (dsc-pileup writes phred <= 40, cmd_cram_dsc_pileup.cpp:19-20)");
+  }
+  if (e != cudaSuccess) {
+    pscl_plp_free(ctx, p);
+    return pscl_fail(ctx, e == cudaErrorMemoryAllocation ? PSCL_ENOMEM : PSCL_ECUDA, "pileup upload failed: %s", cudaGetErrorString(e));
+  }
+  cudaFree(p->scratch_h2d);
+  p->scratch_h2d = nullptr;
+  *out = p;
+  return PSCL_OK;
+}

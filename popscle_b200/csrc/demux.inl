@@ -1,0 +1,722 @@
+// demux.inl — demuxlet per-barcode likelihood grid + per-cell epilogue (part of popscle_b200.cu)
+//
+// Replaces cmd_cram_demuxlet.cpp:636-991.  Two accumulation kernels write per-work-item partial
+// LLK grids laid out like the reference's llksAB ([j][k][n], :620/:746); one epilogue kernel sums
+// the items of a cell in fixed order and restates the prior / logAdd / best-next / SNG-DBL-AMB
+// logic (:788-991).
+//
+//   k_demux_default<NV> : the default alpha grid {0, 0.5} (:85-89) and 2 <= nv <= 8.  One warp per
+//       work item, ONE LANE PER (cell,SNP) PAIR: the nv singlet + nv(nv-1)/2 doublet running
+//       products live in that lane's registers.  Inputs are software-pipelined: indices two
+//       iterations ahead (registers), read bytes and the genotype row one iteration ahead
+//       (cp.async into a conflict-free shared-memory row per lane).
+//   k_demux_general<EPT> : any nv / alpha grid.  One CTA per (work item, tile of 256*EPT grid
+//       entries); 8 pairs per round are folded by one warp each, staged in shared memory, and
+//       every thread updates its EPT register accumulators.
+//
+// Arithmetic notes (all FP64):
+//  * pG (:655-725) is evaluated in closed form: the reference divides by the running joint
+//    maximum after every read and once more after adding 1e-10, which equals
+//    (raw/max(raw) + 1e-10)/(1 + 1e-10) up to rounding.
+//  * log(sum) per term (:746) becomes a running product with a separately tracked exponent and a
+//    single log per accumulator per work item.
+//  * sum_lm g_j[l] g_k[m] pG[n][l][m] is evaluated as g_j . (pG[n] g_k).
+//  * at alpha == 0.5, pG[l][m] depends on l+m only, so LLK[j][k] == LLK[k][j] mathematically; the
+//    default kernel computes k<j once and mirrors it (the reference's choice between (j,k) and
+//    (k,j) is rounding noise; SURVEY.md Appendix C compares that pair unordered).
+
+#include <cuda_pipeline_primitives.h>
+
+// ------------------------------------------------------------------------------------------------
+// default-grid kernel
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+struct DefaultCfg {
+  static constexpr int NE = NV + NV * (NV - 1) / 2;       // live accumulators per lane
+  static constexpr int ROW_D = NV * 3;                    // doubles per genotype row
+  static constexpr bool V16 = (NV % 2 == 0);              // row is a multiple of 16 B
+  // smem row stride in doubles: odd multiple of 16 B (even NV) / odd number of doubles (odd NV)
+  static constexpr int STRIDE_D = V16 ? ((ROW_D / 2) | 1) * 2 : ROW_D;
+  static constexpr int THREADS = 256;
+  static constexpr size_t SMEM = sizeof(double) * 256 + (size_t)2 * THREADS * STRIDE_D * sizeof(double) +
+                                 (size_t)NE * THREADS * sizeof(int);
+};
+
+struct DemuxArgs {
+  const int32_t* pair_snp;
+  const uint32_t* pair_rd;
+  const uint8_t* rd_aq;
+  const double* gp;
+  const uint8_t* has_gp;
+  const double* phred_err;
+  const int32_t* item_order;  // nullable
+  const int64_t* item_pbeg;
+  const int64_t* item_pend;
+  double* partial;            // [n_work][nv*nv*nalpha]
+  int* counter;
+  int32_t item_base, n_work;
+  int32_t nv, nalpha;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
+  using Cfg = DefaultCfg<NV>;
+  constexpr int NE = Cfg::NE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_err = reinterpret_cast<double*>(smem_raw);                 // [256]
+  double* s_g = s_err + 256;                                           // [2][256][STRIDE_D]
+  int* s_exp = reinterpret_cast<int*>(s_g + 2 * 256 * Cfg::STRIDE_D);  // [NE][256]
+  const int tid = threadIdx.x, lane = tid & 31;
+  s_err[tid] = a.phred_err[tid];
+  __syncthreads();
+  const double invD = 1.0 / (1.0 + 1e-10);
+  double* my_g[2] = {s_g + (size_t)tid * Cfg::STRIDE_D, s_g + (size_t)(256 + tid) * Cfg::STRIDE_D};
+
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(a.counter, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= a.n_work) break;
+    const int item = a.item_order ? a.item_order[w] : a.item_base + w;
+    const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
+    const int64_t niter = (pe - pb + 31) >> 5;
+
+    double acc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { acc[e] = 1.0; s_exp[e * 256 + tid] = 0; }
+
+    // ---- pipeline prologue -------------------------------------------------------------------
+    // stage A (two ahead): snp, r0, r1;  stage B (one ahead): read bytes, has_gp, genotype row
+    int32_t snpA = 0; uint32_t r0A = 0, r1A = 0; bool okA = false;
+    int32_t snpB = 0; uint32_t r0B = 0, r1B = 0; bool okB = false;
+    uint32_t bytesB = 0; bool hasB = false;
+    auto loadA = [&](int64_t it) {
+      int64_t p = pb + (it << 5) + lane;
+      okA = (it < niter) && (p < pe);
+      if (okA) { snpA = a.pair_snp[p]; r0A = a.pair_rd[p]; r1A = a.pair_rd[p + 1]; }
+    };
+    auto issueB = [&](int buf) {  // consumes stage A registers
+      snpB = snpA; r0B = r0A; r1B = r1A; okB = okA;
+      hasB = okB;
+      bytesB = 0;
+      if (okB) {
+        if (a.has_gp) hasB = a.has_gp[snpB] != 0;
+        uint32_t n = r1B - r0B;
+        // first 4 reads of the pair, one byte each (allele<<6 | qual)
+        if (n > 0) bytesB |= (uint32_t)a.rd_aq[r0B];
+        if (n > 1) bytesB |= (uint32_t)a.rd_aq[r0B + 1] << 8;
+        if (n > 2) bytesB |= (uint32_t)a.rd_aq[r0B + 2] << 16;
+        if (n > 3) bytesB |= (uint32_t)a.rd_aq[r0B + 3] << 24;
+        if (hasB) {
+          const double* src = a.gp + (size_t)snpB * Cfg::ROW_D;
+          double* dst = my_g[buf];
+          if constexpr (Cfg::V16) {
+#pragma unroll
+            for (int i = 0; i < Cfg::ROW_D; i += 2) __pipeline_memcpy_async(dst + i, src + i, 16);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Cfg::ROW_D; ++i) __pipeline_memcpy_async(dst + i, src + i, 8);
+          }
+        }
+      }
+      __pipeline_commit();
+    };
+    loadA(0);
+    issueB(0);
+    loadA(1);
+
+    for (int64_t it = 0; it < niter; ++it) {
+      const int buf = (int)(it & 1);
+      // current iteration's operands (stage B of the previous step)
+      const uint32_t r0 = r0B, r1 = r1B, bytes = bytesB;
+      const bool has = hasB;
+      // issue the next iteration's loads before computing
+      issueB(buf ^ 1);
+      loadA(it + 2);
+      __pipeline_wait_prior(1);  // the row of iteration `it` has landed
+
+      if (has) {
+        // ---- D1/D2: fold the reads (cmd_cram_demuxlet.cpp:660-725) -------------------------
+        // p = 0.5*l + (m-l)*0.5*alpha (:673) takes 5 values on the {0,0.5} grid: 0,.25,.5,.75,1
+        double f0 = 1.0, f1 = 1.0, f2 = 1.0, f3 = 1.0, f4 = 1.0;
+        const uint32_t nrd = r1 - r0;
+        for (uint32_t r = 0; r < nrd; ++r) {
+          uint32_t aq = (r < 4) ? ((bytes >> (8 * r)) & 0xffu) : (uint32_t)a.rd_aq[r0 + r];
+          uint32_t al = aq >> 6;
+          if (al == 2) continue;  // :664
+          double err = s_err[aq & 63u];
+          double mat = 1.0 - err, e3 = err / 3.0;
+          double pR = (al == 0) ? mat : e3;  // :666
+          double pA = (al == 1) ? mat : e3;  // :667
+          f0 *= pR;
+          f1 *= (pR * 0.75 + pA * 0.25);
+          f2 *= (pR * 0.5 + pA * 0.5);
+          f3 *= (pR * 0.25 + pA * 0.75);
+          f4 *= pA;
+          if ((r & 7u) == 7u) {  // keep deep pileups away from underflow (:692-699 does it per read)
+            double mx = fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
+            double ri = 1.0 / mx;
+            f0 *= ri; f1 *= ri; f2 *= ri; f3 *= ri; f4 *= ri;
+          }
+        }
+        const double mx = fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
+        const double ri = 1.0 / mx;
+        const double h0 = fma(f0, ri, 1e-10) * invD, h1 = fma(f1, ri, 1e-10) * invD,
+                     h2 = fma(f2, ri, 1e-10) * invD, h3 = fma(f3, ri, 1e-10) * invD,
+                     h4 = fma(f4, ri, 1e-10) * invD;  // :704-725
+
+        // ---- D3: genotype row from shared memory --------------------------------------------
+        double G[NV][3];
+        {
+          const double* row = my_g[buf];
+          if constexpr (Cfg::V16) {
+            const double2* r2 = reinterpret_cast<const double2*>(row);
+            double flat[Cfg::ROW_D];
+#pragma unroll
+            for (int i = 0; i < Cfg::ROW_D / 2; ++i) { double2 t = r2[i]; flat[2 * i] = t.x; flat[2 * i + 1] = t.y; }
+#pragma unroll
+            for (int j = 0; j < NV; ++j) { G[j][0] = flat[3 * j]; G[j][1] = flat[3 * j + 1]; G[j][2] = flat[3 * j + 2]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) { G[j][0] = row[3 * j]; G[j][1] = row[3 * j + 1]; G[j][2] = row[3 * j + 2]; }
+          }
+        }
+        // singlets: llksAB[j][0][0] (:806) = log( (sum_l g_j[l] pG0[l]) * (sum_m g_0[m]) ), pG0[l] = h(2l)
+        const double sg0 = G[0][0] + G[0][1] + G[0][2];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[j] *= (G[j][0] * h0 + G[j][1] * h2 + G[j][2] * h4) * sg0;
+        // doublets at alpha = 0.5: pG1[l][m] = h(l+m)
+#pragma unroll
+        for (int j = 1; j < NV; ++j) {
+          const double v0 = h0 * G[j][0] + h1 * G[j][1] + h2 * G[j][2];
+          const double v1 = h1 * G[j][0] + h2 * G[j][1] + h3 * G[j][2];
+          const double v2 = h2 * G[j][0] + h3 * G[j][1] + h4 * G[j][2];
+#pragma unroll
+          for (int k = 0; k < j; ++k)
+            acc[NV + j * (j - 1) / 2 + k] *= (G[k][0] * v0 + G[k][1] * v1 + G[k][2] * v2);
+        }
+      }
+      if ((it & 7) == 7) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * 256 + tid] += ex; }
+      }
+    }
+    __pipeline_wait_prior(0);
+
+    // ---- item epilogue: one log per accumulator, warp sum, write the partial grid ------------
+    double* out = a.partial + (size_t)(item - a.item_base) * (NV * NV * 2);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      double x = pscl_prod_log(acc[e], s_exp[e * 256 + tid]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      acc[e] = x;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) out[(j * NV + 0) * 2 + 0] = acc[j];
+#pragma unroll
+      for (int j = 1; j < NV; ++j)
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+          double x = acc[NV + j * (j - 1) / 2 + k];
+          out[(j * NV + k) * 2 + 1] = x;
+          out[(k * NV + j) * 2 + 1] = x;
+        }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// general kernel
+// ------------------------------------------------------------------------------------------------
+struct GeneralArgs {
+  DemuxArgs d;
+  int32_t E;        // nv + (nalpha-1)*nv*nv entries
+  int32_t PB;       // pair slots per round (<= 8)
+  int32_t slot_d;   // doubles per slot
+  int32_t nvv_max;  // v doubles per slot
+};
+
+template <int EPT>
+__global__ void __launch_bounds__(256) k_demux_general(GeneralArgs ga) {
+  const DemuxArgs& a = ga.d;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_err = reinterpret_cast<double*>(smem_raw);  // [256]
+  double* s_slots = s_err + 256;                        // [PB][slot_d] : pg | g | v
+  int* s_has = reinterpret_cast<int*>(s_slots + (size_t)ga.PB * ga.slot_d);  // [PB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nv = a.nv, na = a.nalpha, nv2 = nv * nv;
+  s_err[tid] = a.phred_err[tid];
+
+  const int w = blockIdx.x;
+  const int item = a.item_order ? a.item_order[w] : a.item_base + w;
+  const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
+  const int e_lo = blockIdx.y * (256 * EPT);
+  const int e_hi = min(ga.E, e_lo + 256 * EPT) - 1;
+  auto plane_of = [&](int e) { return e < nv ? 0 : 1 + (e - nv) / nv2; };
+  const int nlo = plane_of(e_lo), nhi = plane_of(e_hi);
+  const int nvv = (nhi - nlo + 1) * nv * 3;
+  const int pg_d = na * 9, g_d = nv * 3;
+
+  double acc[EPT];
+  int ex[EPT], goff[EPT], voff[EPT], gidx[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    int e = e_lo + i * 256 + tid;
+    acc[i] = 1.0; ex[i] = 0; gidx[i] = -1; goff[i] = 0; voff[i] = 0;
+    if (e <= e_hi) {
+      int n, j, k;
+      if (e < nv) { n = 0; j = e; k = 0; }
+      else { int d = e - nv; n = 1 + d / nv2; j = (d / nv) % nv; k = d % nv; }
+      goff[i] = j * 3;
+      voff[i] = ((n - nlo) * nv + k) * 3;
+      gidx[i] = (j * nv + k) * na + n;
+    }
+  }
+  // per-lane alpha weights for the fold: value i = lane + 32*t  ->  (n,l,m)
+  constexpr int VPL = (PSCL_MAX_ALPHA * 9 + 31) / 32;
+  double pw[VPL];
+#pragma unroll
+  for (int t = 0; t < VPL; ++t) {
+    int i = lane + 32 * t;
+    int n = i / 9, l = (i % 9) / 3, m = i % 3;
+    pw[t] = (i < pg_d) ? 0.5 * l + (m - l) * 0.5 * c_alpha[n] : 0.0;  // :673
+  }
+  const double invD = 1.0 / (1.0 + 1e-10);
+  __syncthreads();
+
+  for (int64_t base = pb; base < pe; base += ga.PB) {
+    // ---- phase A: warp s folds pair base+s and stages its genotype row ----------------------
+    if (warp < ga.PB) {
+      const int64_t p = base + warp;
+      double* slot = s_slots + (size_t)warp * ga.slot_d;
+      bool has = false;
+      if (p < pe) {
+        const int32_t snp = a.pair_snp[p];
+        has = a.has_gp ? (a.has_gp[snp] != 0) : true;
+        if (has) {
+          const uint32_t r0 = a.pair_rd[p], r1 = a.pair_rd[p + 1];
+          double val[VPL];
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) val[t] = 1.0;
+          uint32_t cnt = 0;
+          for (uint32_t r = r0; r < r1; ++r) {
+            uint32_t aq = a.rd_aq[r];
+            uint32_t al = aq >> 6;
+            if (al == 2) continue;
+            double err = s_err[aq & 63u];
+            double mat = 1.0 - err, e3 = err / 3.0;
+            double pR = (al == 0) ? mat : e3, pA = (al == 1) ? mat : e3;
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) val[t] *= (pR * (1.0 - pw[t]) + pA * pw[t]);  // :685
+            if ((++cnt & 7u) == 0u) {
+              double mx = 0.0;
+#pragma unroll
+              for (int t = 0; t < VPL; ++t) if (lane + 32 * t < pg_d) mx = fmax(mx, val[t]);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+              double ri = 1.0 / mx;
+#pragma unroll
+              for (int t = 0; t < VPL; ++t) val[t] *= ri;
+            }
+          }
+          double mx = 0.0;
+#pragma unroll
+          for (int t = 0; t < VPL; ++t) if (lane + 32 * t < pg_d) mx = fmax(mx, val[t]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          const double ri = 1.0 / mx;
+#pragma unroll
+          for (int t = 0; t < VPL; ++t)
+            if (lane + 32 * t < pg_d) slot[lane + 32 * t] = fma(val[t], ri, 1e-10) * invD;  // :704-725
+          const double* src = a.gp + (size_t)snp * g_d;
+          for (int i = lane; i < g_d; i += 32) slot[pg_d + i] = src[i];
+        }
+      }
+      if (lane == 0) s_has[warp] = has ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- phase B: v[n][k][l] = sum_m pG[n][l][m] g_k[m] for the planes of this tile -----------
+    for (int idx = tid; idx < ga.PB * nvv; idx += 256) {
+      int s = idx / nvv, r = idx - s * nvv;
+      if (!s_has[s]) continue;
+      const double* slot = s_slots + (size_t)s * ga.slot_d;
+      int nn = r / g_d + nlo, kl = r % g_d, k = kl / 3, l = kl % 3;
+      const double* pg = slot + nn * 9 + l * 3;
+      const double* g = slot + pg_d + k * 3;
+      s_slots[(size_t)s * ga.slot_d + pg_d + g_d + r] = pg[0] * g[0] + pg[1] * g[1] + pg[2] * g[2];
+    }
+    __syncthreads();
+    // ---- phase C: every thread updates its EPT accumulators -----------------------------------
+    for (int s = 0; s < ga.PB; ++s) {
+      if (!s_has[s]) continue;
+      const double* g = s_slots + (size_t)s * ga.slot_d + pg_d;
+      const double* v = g + g_d;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        if (gidx[i] >= 0) {
+          const double* gj = g + goff[i];
+          const double* vk = v + voff[i];
+          acc[i] *= (gj[0] * vk[0] + gj[1] * vk[1] + gj[2] * vk[2]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) pscl_renorm(acc[i], ex[i]);
+    __syncthreads();
+  }
+  double* out = a.partial + (size_t)(item - a.item_base) * ((size_t)nv2 * na);
+#pragma unroll
+  for (int i = 0; i < EPT; ++i)
+    if (gidx[i] >= 0) out[gidx[i]] = pscl_prod_log(acc[i], ex[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-cell epilogue (cmd_cram_demuxlet.cpp:788-991)
+// ------------------------------------------------------------------------------------------------
+struct Top2 {
+  double v1, v2;
+  int i1, i2;
+};
+// total order of the reference's scans (:827-837, :883-906): larger value first, earlier scan
+// index first among equals; entries never beat the -1e300 initial value unless strictly larger.
+__device__ __forceinline__ bool top_before(double va, int ia, double vb, int ib) {
+  return (va > vb) || (va == vb && ia < ib);
+}
+__device__ __forceinline__ void top2_push(Top2& t, double v, int i) {
+  if (!(v > -1e300)) return;
+  if (top_before(v, i, t.v1, t.i1)) { t.v2 = t.v1; t.i2 = t.i1; t.v1 = v; t.i1 = i; }
+  else if (top_before(v, i, t.v2, t.i2)) { t.v2 = v; t.i2 = i; }
+}
+__device__ __forceinline__ Top2 top2_shfl_merge(Top2 t, int o) {
+  double ov1 = __shfl_xor_sync(0xffffffffu, t.v1, o), ov2 = __shfl_xor_sync(0xffffffffu, t.v2, o);
+  int oi1 = __shfl_xor_sync(0xffffffffu, t.i1, o), oi2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+  top2_push(t, ov1, oi1);
+  top2_push(t, ov2, oi2);
+  return t;
+}
+
+struct EpiArgs {
+  const int64_t* cell_ptr;
+  const int32_t* cell_item_ptr;
+  double* partial;          // [items][G]; the first item's row is overwritten with the cell sum
+  pscl_demux_cell* cells;   // [cells in batch], indexed from out_base
+  double* grid;             // nullable: [cells][G]
+  int32_t cell_begin;       // first cell of this batch
+  int32_t out_base;         // index of cell_begin inside cells[] / grid[]
+  int32_t item_base;        // first item of this batch
+  int32_t nv, nalpha;
+  double doublet_prior;
+};
+
+__global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
+  const int c = a.cell_begin + blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nv = a.nv, na = a.nalpha, G = nv * nv * na;
+  const int ia = a.cell_item_ptr[c], ib = a.cell_item_ptr[c + 1];
+  double* sum_row = a.partial + (size_t)(ia - a.item_base) * G;
+  double* grid_row = a.grid ? a.grid + (size_t)(a.out_base + blockIdx.x) * G : nullptr;
+  const double lsp = log((1.0 - a.doublet_prior) / nv);                       // :793
+  const double ldp1 = log(a.doublet_prior / nv / (nv - 1.) / (na - 1.));      // :794
+  const double ldp2 = log(a.doublet_prior / nv / (nv - 1.) / (na - 1.) * 2);  // :795
+
+  Top2 sng = {-1e300, -1e300, 0x7fffffff, 0x7fffffff}, dbl = sng;
+  double mx_all = -1e-300, mx_sng = -1e-300;  // the (sic) -1e-300 start of :791 is a term of both sums
+  for (int idx = tid; idx < G; idx += 128) {
+    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    const bool is_s = (n == 0 && k == 0), is_d = (n >= 1 && j != k);
+    double x = __longlong_as_double(0x7ff8000000000000ll);
+    if (is_s || is_d) {
+      x = 0.0;  // memset(llksAB,0) :643 — a cell without items keeps zeros
+      for (int it = ia; it < ib; ++it) x += a.partial[(size_t)(it - a.item_base) * G + idx];
+      if (ib > ia) sum_row[idx] = x;
+      if (is_s) {
+        top2_push(sng, x, j);
+        double t = x + lsp;
+        mx_all = fmax(mx_all, t); mx_sng = fmax(mx_sng, t);
+      } else {
+        top2_push(dbl, x, idx);
+        if (c_alpha[n] == 0.5) { if (k < j) mx_all = fmax(mx_all, x + ldp2); }  // :812-815
+        else mx_all = fmax(mx_all, x + ldp1);
+      }
+    }
+    if (grid_row) grid_row[idx] = x;
+  }
+  __shared__ Top2 s_sng[4], s_dbl[4];
+  __shared__ double s_mx[2][4], s_sum[2][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sng = top2_shfl_merge(sng, o);
+    dbl = top2_shfl_merge(dbl, o);
+    mx_all = fmax(mx_all, __shfl_xor_sync(0xffffffffu, mx_all, o));
+    mx_sng = fmax(mx_sng, __shfl_xor_sync(0xffffffffu, mx_sng, o));
+  }
+  if (lane == 0) { s_sng[warp] = sng; s_dbl[warp] = dbl; s_mx[0][warp] = mx_all; s_mx[1][warp] = mx_sng; }
+  __syncthreads();
+  mx_all = fmax(fmax(s_mx[0][0], s_mx[0][1]), fmax(s_mx[0][2], s_mx[0][3]));
+  mx_sng = fmax(fmax(s_mx[1][0], s_mx[1][1]), fmax(s_mx[1][2], s_mx[1][3]));
+  // second pass: sum of exp (the logAdd chains of :804-821 evaluated as max + log(sum exp))
+  double se_all = 0.0, se_sng = 0.0;
+  for (int idx = tid; idx < G; idx += 128) {
+    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    if (n == 0 && k == 0) {
+      double x = (ib > ia) ? sum_row[idx] : 0.0;
+      se_all += exp(x + lsp - mx_all);
+      se_sng += exp(x + lsp - mx_sng);
+    } else if (n >= 1 && j != k) {
+      double x = (ib > ia) ? sum_row[idx] : 0.0;
+      if (c_alpha[n] == 0.5) { if (k < j) se_all += exp(x + ldp2 - mx_all); }
+      else se_all += exp(x + ldp1 - mx_all);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se_all += __shfl_xor_sync(0xffffffffu, se_all, o);
+    se_sng += __shfl_xor_sync(0xffffffffu, se_sng, o);
+  }
+  if (lane == 0) { s_sum[0][warp] = se_all; s_sum[1][warp] = se_sng; }
+  __syncthreads();
+  if (tid != 0) return;
+  for (int wv = 1; wv < 4; ++wv) {
+    top2_push(sng, s_sng[wv].v1, s_sng[wv].i1); top2_push(sng, s_sng[wv].v2, s_sng[wv].i2);
+    top2_push(dbl, s_dbl[wv].v1, s_dbl[wv].i1); top2_push(dbl, s_dbl[wv].v2, s_dbl[wv].i2);
+  }
+  se_all = s_sum[0][0] + s_sum[0][1] + s_sum[0][2] + s_sum[0][3] + exp(-1e-300 - mx_all);
+  se_sng = s_sum[1][0] + s_sum[1][1] + s_sum[1][2] + s_sum[1][3] + exp(-1e-300 - mx_sng);
+  const double sumLLK = mx_all + log(se_all), sngLLK = mx_sng + log(se_sng);
+
+  const int sBest = (sng.i1 == 0x7fffffff) ? -1 : sng.i1, sNext = (sng.i2 == 0x7fffffff) ? -1 : sng.i2;
+  const double sngBestLLK = sng.v1, sngNextLLK = sng.v2, dblBestLLK = dbl.v1, dblNextLLK = dbl.v2;
+  int dBest1 = -1, dBest2 = -1, dBestA = -1, dNext1 = -1, dNext2 = -1, dNextA = -1;
+  if (dbl.i1 != 0x7fffffff) { dBestA = dbl.i1 % na; dBest2 = (dbl.i1 / na) % nv; dBest1 = dbl.i1 / na / nv; }
+  if (dbl.i2 != 0x7fffffff) { dNextA = dbl.i2 % na; dNext2 = (dbl.i2 / na) % nv; dNext1 = dbl.i2 / na / nv; }
+
+  pscl_demux_cell o;
+  memset(&o, 0, sizeof(o));
+  o.n_snps = (int32_t)(a.cell_ptr[c + 1] - a.cell_ptr[c]);
+  if (dblBestLLK > sngBestLLK + 2) {  // :925-946
+    o.type = PSCL_DBL;
+    o.best_pp = exp(dblBestLLK + ((dBestA >= 0 && c_alpha[dBestA] == 0.5) ? ldp2 : ldp1) - sumLLK);
+    o.best_j = dBest1; o.best_k = dBest2; o.best_llk = dblBestLLK; o.best_a = dBestA;
+    if (dblNextLLK > sngBestLLK + 2) { o.next_j = dNext1; o.next_k = dNext2; o.next_llk = dblNextLLK; o.next_a = dNextA; }
+    else { o.next_j = o.next_k = sBest; o.next_llk = sngBestLLK; o.next_a = 0; }
+  } else {
+    o.type = (sngBestLLK > sngNextLLK + 2) ? PSCL_SNG : PSCL_AMB;  // :947 / :968
+    o.best_pp = sngBestLLK + lsp - sumLLK;                         // no exp (:949, :970)
+    o.best_j = o.best_k = sBest; o.best_llk = sngBestLLK; o.best_a = 0;
+    if (dblBestLLK > sngNextLLK + 2) { o.next_j = dBest1; o.next_k = dBest2; o.next_llk = dblBestLLK; o.next_a = dBestA; }
+    else { o.next_j = o.next_k = sNext; o.next_llk = sngNextLLK; o.next_a = 0; }
+  }
+  o.sng_best = sBest; o.sng_next = sNext;
+  o.dbl_best_j = dBest1; o.dbl_best_k = dBest2; o.dbl_best_a = dBestA;
+  o.dbl_next_j = dNext1; o.dbl_next_k = dNext2; o.dbl_next_a = dNextA;
+  o.sng_pp = exp(sngLLK - sumLLK);               // :990
+  o.sng_only_pp = exp(sngBestLLK + lsp - sngLLK);  // :991
+  o.sng_best_llk = sngBestLLK; o.sng_next_llk = sngNextLLK;
+  o.dbl_best_llk = dblBestLLK; o.dbl_next_llk = dblNextLLK;
+  o.sum_llk = sumLLK; o.sng_llk = sngLLK;
+  a.cells[a.out_base + blockIdx.x] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host API
+// ------------------------------------------------------------------------------------------------
+extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t n_snps) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!geno || !geno->gp || geno->n_samples < 2 || n_snps < 0)
+    return pscl_fail(ctx, PSCL_EINVAL,
+                     "pscl_demux_set_geno: need gp and n_samples >= 2 (the reference divides by nv-1, "
+                     "cmd_cram_demuxlet.cpp:794)");
+  PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaFree(ctx->gp); ctx->gp = nullptr;
+  cudaFree(ctx->has_gp); ctx->has_gp = nullptr;
+  size_t bytes = sizeof(double) * (size_t)n_snps * geno->n_samples * 3;
+  PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp, bytes ? bytes : 16));
+  PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->gp, geno->gp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (geno->has_gp) {
+    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->has_gp, n_snps ? n_snps : 16));
+    PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->has_gp, geno->has_gp, n_snps, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->nv = geno->n_samples;
+  ctx->geno_V = n_snps;
+  return PSCL_OK;
+}
+
+extern "C" int pscl_demux_keep_grid(pscl_ctx* ctx, int enable) {
+  if (!ctx) return PSCL_EINVAL;
+  ctx->keep_grid = enable != 0;
+  return PSCL_OK;
+}
+extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
+  if (!ctx) return PSCL_EINVAL;
+  ctx->force_general = enable != 0;
+  return PSCL_OK;
+}
+
+template <int NV>
+static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
+  using Cfg = DefaultCfg<NV>;
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  int grid = ctx->sm_count;
+  if (grid * 8 > a.n_work) grid = (a.n_work + 7) / 8;
+  if (grid < 1) grid = 1;
+  k_demux_default<NV><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
+  return cudaGetLastError();
+}
+
+extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
+                                int32_t cell_begin, int32_t cell_end) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!plp || !opts || !opts->alphas) return pscl_fail(ctx, PSCL_EINVAL, "pscl_demux_score: NULL argument");
+  if (!ctx->gp) return pscl_fail(ctx, PSCL_ESTATE, "pscl_demux_score: call pscl_demux_set_geno first");
+  if (ctx->geno_V != plp->V) return pscl_fail(ctx, PSCL_EINVAL, "genotype table has %d SNPs, pileup %d", ctx->geno_V, plp->V);
+  if (cell_begin < 0 || cell_end > plp->C || cell_begin > cell_end)
+    return pscl_fail(ctx, PSCL_EINVAL, "bad cell range [%d,%d) of %d", cell_begin, cell_end, plp->C);
+  const int na = opts->n_alpha, nv = ctx->nv;
+  if (na < 2 || na > PSCL_MAX_ALPHA)
+    return pscl_fail(ctx, PSCL_EINVAL, "n_alpha must be in [2,%d] (the reference divides by nAlpha-1, cmd_cram_demuxlet.cpp:794)", PSCL_MAX_ALPHA);
+  if (!(opts->doublet_prior > 0.0 && opts->doublet_prior < 1.0))
+    return pscl_fail(ctx, PSCL_EINVAL, "doublet_prior must be in (0,1)");
+  PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
+  double h_alpha[PSCL_MAX_ALPHA] = {0};
+  for (int i = 0; i < na; ++i) h_alpha[i] = opts->alphas[i];
+  PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_alpha, h_alpha, sizeof(h_alpha), 0, cudaMemcpyHostToDevice, ctx->stream));
+
+  const int ncell = cell_end - cell_begin;
+  const size_t G = (size_t)nv * nv * na;
+  int rc;
+  if ((rc = pscl_reserve(ctx, (pscl_demux_cell**)&ctx->dm_cells, &ctx->dm_cells_cap, sizeof(pscl_demux_cell) * (size_t)ncell)) != PSCL_OK) return rc;
+  if (ctx->keep_grid && (rc = pscl_reserve(ctx, &ctx->dm_grid, &ctx->dm_grid_cap, sizeof(double) * G * ncell)) != PSCL_OK) return rc;
+  ctx->dm_cell_begin = cell_begin; ctx->dm_cell_end = cell_end; ctx->dm_nalpha = na;
+
+  const bool use_default = !ctx->force_general && na == 2 && h_alpha[0] == 0.0 && h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
+  const std::vector<int32_t>& cip = plp->h_cell_item_ptr;
+  size_t max_items = ctx->partial_budget_bytes / (G * sizeof(double));
+  if (max_items < 1) max_items = 1;
+
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  float main_ms_known = 0.f;
+  bool single_batch = true;
+  int c0 = cell_begin;
+  while (c0 < cell_end) {
+    // batch = as many whole cells as fit the partial-grid budget
+    int c1 = c0 + 1;
+    while (c1 < cell_end && (size_t)(cip[c1 + 1] - cip[c0]) <= max_items) ++c1;
+    const int ib = cip[c0], ie = cip[c1], nwork = ie - ib;
+    if (c1 < cell_end || c0 > cell_begin) single_batch = false;
+    if ((rc = pscl_reserve(ctx, &ctx->dm_partial, &ctx->dm_partial_cap, sizeof(double) * G * (size_t)(nwork > 0 ? nwork : 1))) != PSCL_OK) return rc;
+    if (nwork > 0) {
+      DemuxArgs a;
+      a.pair_snp = plp->pair_snp; a.pair_rd = plp->pair_rd; a.rd_aq = plp->rd_aq;
+      a.gp = ctx->gp; a.has_gp = ctx->has_gp; a.phred_err = ctx->phred_err;
+      a.item_order = (ib == 0 && ie == plp->n_items) ? plp->item_order : nullptr;
+      a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend;
+      a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
+      a.item_base = ib; a.n_work = nwork; a.nv = nv; a.nalpha = na;
+      cudaError_t e = cudaSuccess;
+      if (use_default) {
+        PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
+        switch (nv) {
+          case 2: e = launch_default<2>(ctx, a); break;
+          case 3: e = launch_default<3>(ctx, a); break;
+          case 4: e = launch_default<4>(ctx, a); break;
+          case 5: e = launch_default<5>(ctx, a); break;
+          case 6: e = launch_default<6>(ctx, a); break;
+          case 7: e = launch_default<7>(ctx, a); break;
+          case 8: e = launch_default<8>(ctx, a); break;
+        }
+      } else {
+        constexpr int EPT = 8;
+        GeneralArgs ga;
+        ga.d = a;
+        ga.E = nv + (na - 1) * nv * nv;
+        int planes = std::min(na, (256 * EPT) / (nv * nv) + 2);
+        ga.nvv_max = planes * nv * 3;
+        ga.slot_d = na * 9 + nv * 3 + ga.nvv_max;
+        size_t slot_bytes = sizeof(double) * ga.slot_d;
+        int PB = (int)std::min<size_t>(8, (200 * 1024 - 2048 - 64) / slot_bytes);
+        if (PB < 1) return pscl_fail(ctx, PSCL_EINVAL, "n_samples=%d too large for the shared-memory staging of the general kernel", nv);
+        ga.PB = PB;
+        size_t smem = sizeof(double) * 256 + slot_bytes * PB + sizeof(int) * 8;
+        static bool attr_set[64] = {false};
+        if (!attr_set[ctx->device & 63]) {
+          PSCL_CUDA(ctx, cudaFuncSetAttribute(k_demux_general<EPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr_set[ctx->device & 63] = true;
+        }
+        dim3 grid((unsigned)nwork, (unsigned)((ga.E + 256 * EPT - 1) / (256 * EPT)));
+        k_demux_general<EPT><<<grid, 256, smem, ctx->stream>>>(ga);
+        e = cudaGetLastError();
+      }
+      ctx->launches++;
+      if (e != cudaSuccess) return pscl_fail(ctx, PSCL_ECUDA, "demux kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    if (single_batch) PSCL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    EpiArgs ea;
+    ea.cell_ptr = plp->cell_ptr; ea.cell_item_ptr = plp->cell_item_ptr; ea.partial = ctx->dm_partial;
+    ea.cells = (pscl_demux_cell*)ctx->dm_cells; ea.grid = ctx->keep_grid ? ctx->dm_grid : nullptr;
+    ea.cell_begin = c0; ea.out_base = c0 - cell_begin; ea.item_base = ib; ea.nv = nv; ea.nalpha = na;
+    ea.doublet_prior = opts->doublet_prior;
+    k_demux_epilogue<<<(unsigned)(c1 - c0), 128, 0, ctx->stream>>>(ea);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+    c0 = c1;
+  }
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+  ctx->dm_timed = true;
+  ctx->dm_single_batch = single_batch;
+  (void)main_ms_known;
+  return PSCL_OK;
+}
+
+extern "C" int pscl_demux_last_kernel_ms(pscl_ctx* ctx, float* ms_main, float* ms_total) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!ctx->dm_timed) return pscl_fail(ctx, PSCL_ESTATE, "no pscl_demux_score has run");
+  PSCL_CUDA(ctx, cudaEventSynchronize(ctx->ev2));
+  float t = 0.f, m = -1.f;
+  PSCL_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev0, ctx->ev2));
+  if (ctx->dm_single_batch) PSCL_CUDA(ctx, cudaEventElapsedTime(&m, ctx->ev0, ctx->ev1));
+  if (ms_main) *ms_main = m;
+  if (ms_total) *ms_total = t;
+  return PSCL_OK;
+}
+
+extern "C" int pscl_demux_fetch(pscl_ctx* ctx, pscl_demux_cell* out, double* llk_grid) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!ctx->dm_timed) return pscl_fail(ctx, PSCL_ESTATE, "pscl_demux_fetch before pscl_demux_score");
+  const int ncell = ctx->dm_cell_end - ctx->dm_cell_begin;
+  if (out)
+    PSCL_CUDA(ctx, cudaMemcpyAsync(out, ctx->dm_cells, sizeof(pscl_demux_cell) * (size_t)ncell, cudaMemcpyDeviceToHost, ctx->stream));
+  if (llk_grid) {
+    if (!ctx->keep_grid || !ctx->dm_grid) return pscl_fail(ctx, PSCL_ESTATE, "llk_grid requested but pscl_demux_keep_grid was off");
+    size_t G = (size_t)ctx->nv * ctx->nv * ctx->dm_nalpha;
+    PSCL_CUDA(ctx, cudaMemcpyAsync(llk_grid, ctx->dm_grid, sizeof(double) * G * ncell, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSCL_OK;
+}
+
+extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_geno* geno,
+                              const pscl_demux_opts* opts, pscl_demux_cell* out, double* llk_grid) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!host || !geno || !opts || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_demux_run: NULL argument");
+  pscl_plp* plp = nullptr;
+  int rc = pscl_plp_upload(ctx, host, &plp);
+  if (rc != PSCL_OK) return rc;
+  rc = pscl_demux_set_geno(ctx, geno, host->n_snps);
+  bool keep = ctx->keep_grid;
+  if (rc == PSCL_OK && llk_grid) ctx->keep_grid = true;
+  if (rc == PSCL_OK) rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);
+  if (rc == PSCL_OK) rc = pscl_demux_fetch(ctx, out, llk_grid);
+  ctx->keep_grid = keep;
+  std::string err = ctx->err;
+  pscl_plp_free(ctx, plp);
+  ctx->err = err;
+  return rc;
+}

@@ -1,0 +1,95 @@
+"""Parity rules between the CUDA path and the oracle.
+
+LLKs: |x_gpu - x_ref| <= 1e-4 * max(1, |x_ref|) (north_star tolerance).  Ids / droplet types exact,
+except that (a) an alpha == 0.5 doublet (j,k) is compared as an unordered pair — the reference's
+own choice between (j,k) and (k,j) is FP rounding noise — and (b) cells whose deciding margin is
+within 1e-9*|LLK| of a threshold in the oracle are counted as numerically tied and skipped.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+RTOL = 1e-4
+
+
+def close(a, b, rtol=RTOL):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    both_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    return both_inf | (np.abs(a - b) <= rtol * np.maximum(1.0, np.abs(b)))
+
+
+def assert_close(a, b, what, rtol=RTOL):
+    ok = close(a, b, rtol)
+    if not np.all(ok):
+        i = int(np.argmin(ok.ravel()))
+        raise AssertionError(f"{what}: {np.count_nonzero(~ok)} of {ok.size} differ; first at {i}: "
+                             f"{np.ravel(a)[i]!r} vs {np.ravel(b)[i]!r}")
+
+
+def _tied(ref, eps=1e-9):
+    """cells whose classification or argmax sits on a numerical tie in the oracle"""
+    scale = eps * np.maximum(1.0, np.abs(ref["sng_best_llk"]))
+    t = np.abs(ref["dbl_best_llk"] - ref["sng_best_llk"] - 2) <= scale
+    t |= np.abs(ref["sng_best_llk"] - ref["sng_next_llk"] - 2) <= scale
+    t |= np.abs(ref["dbl_best_llk"] - ref["sng_next_llk"] - 2) <= scale
+    t |= np.abs(ref["dbl_next_llk"] - ref["sng_best_llk"] - 2) <= scale
+    t |= np.abs(ref["sng_best_llk"] - ref["sng_next_llk"]) <= scale
+    return t
+
+
+def _pair_key(j, k, a, alphas):
+    """(j,k,alpha) with the alpha==0.5 pair unordered"""
+    j = np.asarray(j).copy(); k = np.asarray(k).copy(); a = np.asarray(a)
+    half = np.array([alphas[x] == 0.5 if x >= 0 else False for x in a])
+    lo, hi = np.minimum(j, k), np.maximum(j, k)
+    j = np.where(half, lo, j); k = np.where(half, hi, k)
+    return j, k, a
+
+
+def check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.02):
+    """out/ref: DEMUX_CELL_DTYPE arrays; grid/rgrid: [cell][j][k][n] (either may be None)."""
+    assert len(out) == len(ref)
+    nz = ref["n_snps"] > 0
+    assert np.array_equal(out["n_snps"], ref["n_snps"])
+    if grid is not None and rgrid is not None:
+        nv, na = rgrid.shape[1], rgrid.shape[3]
+        live = np.zeros((nv, nv, na), dtype=bool)
+        live[:, 0, 0] = True
+        for n in range(1, na):
+            live[:, :, n] = ~np.eye(nv, dtype=bool)
+        assert_close(grid[:, live], rgrid[:, live], "llksAB live entries")
+        assert np.all(np.isnan(grid[:, ~live])), "dead grid entries must be NaN"
+    for f in ("best_llk", "next_llk", "sng_best_llk", "sng_next_llk", "dbl_best_llk", "sum_llk", "sng_llk",
+              "sng_pp", "sng_only_pp", "best_pp"):
+        assert_close(out[f][nz], ref[f][nz], f)
+    tied = _tied(ref) | ~nz
+    assert tied.mean() <= allow_tied_frac, f"too many numerically tied cells: {tied.mean()}"
+    ok = ~tied
+    for f in ("type", "sng_best", "sng_next", "best_a", "dbl_best_a"):
+        bad = np.flatnonzero(ok & (out[f] != ref[f]))
+        assert bad.size == 0, f"{f} differs for cells {bad[:10]}: {out[f][bad[:10]]} vs {ref[f][bad[:10]]}"
+    for pre, af in (("best", "best_a"), ("dbl_best", "dbl_best_a")):
+        oj, ok_, _ = _pair_key(out[pre + "_j"], out[pre + "_k"], out[af], alphas)
+        rj, rk, _ = _pair_key(ref[pre + "_j"], ref[pre + "_k"], ref[af], alphas)
+        bad = np.flatnonzero(ok & ((oj != rj) | (ok_ != rk)))
+        assert bad.size == 0, f"{pre} pair differs for cells {bad[:10]}"
+    # NEXT: the second-best doublet is usually the mirror of the best at alpha 0.5; compare its LLK
+    # (checked above) and its ids as an unordered pair where the oracle has no near-tie for 2nd place
+    return int(ok.sum())
+
+
+def check_fmx_parity(out, ref, allow_tied_frac=0.02):
+    assert len(out) == len(ref)
+    for f in ("n_snps", "n_reads", "init_clust"):
+        assert np.array_equal(out[f], ref[f]), f
+    for f in ("llk0", "llk2", "best_llk", "next_llk", "sng_best_llk", "sng_next_llk", "dbl_best_llk", "dbl_next_llk",
+              "sum_llk", "sng_pp", "sng_only_pp", "best_pp"):
+        assert_close(out[f], ref[f], f)
+    tied = _tied(ref)
+    assert tied.mean() <= allow_tied_frac
+    ok = ~tied
+    for f in ("type", "clust", "sng_best", "sng_next", "best_j", "best_k", "dbl_best_j", "dbl_best_k"):
+        bad = np.flatnonzero(ok & (out[f] != ref[f]))
+        assert bad.size == 0, f"{f} differs for cells {bad[:10]}: {out[f][bad[:10]]} vs {ref[f][bad[:10]]}"
+    return int(ok.sum())

@@ -1,0 +1,148 @@
+"""GPU parity of the demuxlet path (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from popscle_b200 import synth
+from tests.parity import check_demux_parity, assert_close
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT = [0.0, 0.5]
+
+
+def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
+    ctx.demux_force_general(general)
+    try:
+        out, grid = ctx.demux_run(s.plp, gp, has_gp, alphas, dp, want_grid=True)
+    finally:
+        ctx.demux_force_general(False)
+    ref, rgrid = orc.demux(s.plp, gp, has_gp, alphas, dp, want_grid=True, n_threads=8)
+    return out, grid, ref, rgrid
+
+
+@pytest.mark.parametrize("nv", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("general", [False, True])
+def test_default_grid_parity(ctx, nv, general):
+    s = synth.make_pileup(C=300, nv=nv, V=2000, kbar=250, seed=100 + nv)
+    gp = synth.gt_to_gp(s.geno)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
+    n = check_demux_parity(out, grid, ref, rgrid, DEFAULT)
+    assert n > 0.95 * len(out)
+
+
+def test_config1_tutorial_shape(ctx):
+    s = synth.make_config(1)
+    gp = synth.gt_to_gp(s.geno)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT)
+    check_demux_parity(out, grid, ref, rgrid, DEFAULT)
+    sng = out["type"] == 0
+    assert (out["sng_best"][sng] == s.truth_d1[sng]).mean() > 0.99
+
+
+@pytest.mark.parametrize("nv,alphas", [(4, [0.0, 0.25, 0.5]), (6, [0.0, 0.1, 0.2, 0.3, 0.4, 0.5]),
+                                        (16, [0.0, 0.5]), (12, [0.0, 0.3])])
+def test_general_grids(ctx, nv, alphas):
+    s = synth.make_pileup(C=120, nv=nv, V=1500, kbar=200, seed=300 + nv)
+    gp = synth.gt_to_gp(s.geno)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas)
+    check_demux_parity(out, grid, ref, rgrid, alphas)
+
+
+def test_config4_shape_small(ctx):
+    """nv=64, 21-point alpha grid (config 4's shape) on a few cells."""
+    alphas = [0.025 * i for i in range(21)]
+    s = synth.make_pileup(C=12, nv=64, V=3000, kbar=150, seed=404)
+    gp = synth.gt_to_gp(s.geno)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas)
+    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.2)
+
+
+def test_missing_genotypes_and_other_alleles(ctx):
+    """SNPs without GP contribute nothing but count in NUM.SNPS (SURVEY 8a note 8); allele 2 reads
+    are skipped (note 5); soft GP rows."""
+    s = synth.make_pileup(C=150, nv=5, V=1200, kbar=200, seed=55)
+    rng = np.random.default_rng(5)
+    gp = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 5)).astype(np.float32).astype(np.float64)
+    has = (rng.random(s.plp.n_snps) > 0.3).astype(np.uint8)
+    s.plp.read_allele[rng.random(s.plp.n_reads) < 0.2] = 2
+    for general in (False, True):
+        out, grid, ref, rgrid = _run_both(ctx, s, gp, has, DEFAULT, general)
+        check_demux_parity(out, grid, ref, rgrid, DEFAULT)
+
+
+def test_deep_pairs_and_empty_cells(ctx):
+    """pairs with hundreds of reads (underflow guard), cells without any pair, 1-pair cells."""
+    rng = np.random.default_rng(9)
+    C, V, nv = 40, 300, 4
+    counts = rng.integers(0, 60, C)
+    counts[[0, 7, C - 1]] = 0
+    counts[3] = 1
+    cell_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    P = int(cell_ptr[-1])
+    snp = np.concatenate([np.sort(rng.choice(V, c, replace=False)) for c in counts]).astype(np.int32)
+    nrd = rng.integers(1, 6, P)
+    nrd[rng.random(P) < 0.05] = 400
+    prp = np.concatenate([[0], np.cumsum(nrd)]).astype(np.int64)
+    N = int(prp[-1])
+    from popscle_b200 import Pileup
+    plp = Pileup(C, V, cell_ptr, snp, prp, rng.integers(0, 3, N).astype(np.uint8), rng.integers(13, 41, N).astype(np.uint8),
+                 rng.uniform(0.05, 0.5, V))
+    geno = rng.integers(0, 3, (nv, V)).astype(np.int8)
+    gp = synth.gt_to_gp(geno)
+    s = synth.Synth(plp, geno, plp.snp_af, None, None, 9)
+    for general in (False, True):
+        out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
+        check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.3)
+
+
+def test_sharding_is_bit_identical(ctx):
+    """barcode shards reproduce the unsharded records bit for bit; so do partial-grid batches."""
+    s = synth.make_pileup(C=400, nv=8, V=3000, kbar=300, seed=77)
+    gp = synth.gt_to_gp(s.geno)
+    full = ctx.demux_run(s.plp, gp, None, DEFAULT)
+    parts = [ctx.demux_run(s.plp.slice_cells(a, b), gp, None, DEFAULT) for a, b in ((0, 130), (130, 131), (131, 400))]
+    assert np.concatenate(parts).tobytes() == full.tobytes()
+    ctx.set_partial_budget(1 << 20)
+    try:
+        d = ctx.upload(s.plp)
+        ctx.demux_set_geno(gp, None, s.plp.n_snps)
+        ctx.demux_score(d, DEFAULT, 0.5, 50, 333)
+        sub = ctx.demux_fetch()
+    finally:
+        ctx.set_partial_budget(1 << 30)
+    assert sub.tobytes() == full[50:333].tobytes()
+
+
+def test_symmetry_properties(ctx):
+    """LLK[j,k,a] == LLK[k,j,1-a]; permuting samples permutes the grid."""
+    alphas = [0.0, 0.25, 0.5, 0.75]
+    s = synth.make_pileup(C=60, nv=5, V=800, kbar=150, seed=21)
+    gp = synth.gt_to_gp(s.geno)
+    _, grid = ctx.demux_run(s.plp, gp, None, alphas, want_grid=True)
+    for j in range(5):
+        for k in range(5):
+            if j != k:
+                assert_close(grid[:, j, k, 1], grid[:, k, j, 3], "alpha symmetry", rtol=1e-9)
+                assert_close(grid[:, j, k, 2], grid[:, k, j, 2], "alpha 0.5 symmetry", rtol=1e-9)
+    perm = np.array([3, 0, 4, 1, 2])
+    _, grid2 = ctx.demux_run(s.plp, gp[:, perm, :], None, alphas, want_grid=True)
+    for n in range(1, 4):
+        a = grid2[:, :, :, n]
+        b = grid[:, perm][:, :, perm][:, :, :, n]
+        off = ~np.eye(5, dtype=bool)
+        assert_close(a[:, off], b[:, off], "sample permutation", rtol=1e-9)
+
+
+def test_errors(ctx):
+    from popscle_b200 import PsclError
+    s = synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1)
+    gp = synth.gt_to_gp(s.geno)
+    with pytest.raises(PsclError):
+        ctx.demux_run(s.plp, gp, None, [0.0])           # nAlpha == 1 divides by zero in the reference
+    with pytest.raises(PsclError):
+        ctx.demux_run(s.plp, gp[:, :1, :], None, DEFAULT)  # nv == 1
+    bad = synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1).plp
+    bad.read_qual[0] = 99
+    with pytest.raises(PsclError):
+        ctx.demux_run(bad, gp, None, DEFAULT)
