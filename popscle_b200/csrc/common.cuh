@@ -50,6 +50,7 @@ struct pscl_ctx {
   std::string err;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double* fold_tab = nullptr;   // [3][64][6] per-read factors of the default alpha grid (demux.inl)
   double* phred_err = nullptr;  // [256] device copy of PhredHelper's phred2Err (staged to smem by kernels)
   // demuxlet state
   int32_t nv = 0, geno_V = 0;

@@ -36,7 +36,22 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
   // PhredHelper.cpp:30 — same expression, same libm, evaluated on the host
   double tab[256];
   for (int i = 0; i < 256; ++i) tab[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;
-  if (cudaMalloc((void**)&c->phred_err, sizeof(tab)) != cudaSuccess ||
+  // per-read fold factors for the default alpha grid {0, 0.5}: cmd_cram_demuxlet.cpp:666-667,:673,:685
+  static double ftab[3 * 64 * 6];
+  for (int al = 0; al < 3; ++al)
+    for (int q = 0; q < 64; ++q) {
+      double* t = ftab + (al * 64 + q) * 6;
+      double err = tab[q], mat = 1. - err;
+      double pR = (al == 0) ? mat : err / 3.0, pA = (al == 1) ? mat : err / 3.0;
+      for (int i = 0; i < 5; ++i) {
+        double p = 0.25 * i;
+        t[i] = (al == 2) ? 1.0 : (pR * (1.0 - p) + pA * p);
+      }
+      t[5] = 1.0;
+    }
+  if (cudaMalloc((void**)&c->fold_tab, sizeof(ftab)) != cudaSuccess ||
+      cudaMemcpy(c->fold_tab, ftab, sizeof(ftab), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc((void**)&c->phred_err, sizeof(tab)) != cudaSuccess ||
       cudaMemcpy(c->phred_err, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMalloc((void**)&c->dm_counter, 64) != cudaSuccess) {
     delete c;
@@ -60,6 +75,7 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   cudaFree(ctx->dm_partial);
   cudaFree(ctx->dm_counter);
   cudaFree(ctx->phred_err);
+  cudaFree(ctx->fold_tab);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev2);

@@ -30,16 +30,30 @@
 // ------------------------------------------------------------------------------------------------
 // default-grid kernel
 // ------------------------------------------------------------------------------------------------
+// Per-read factors of the 5 distinct mixing fractions p = 0, .25, .5, .75, 1 that the {0, 0.5} grid
+// produces (p = 0.5*l + (m-l)*0.5*alpha, :673): fold_tab[allele][qual][i] = pR*(1-p_i) + pA*p_i with
+// pR/pA from :666-667.  Row allele==2 (skipped read, :664) and the "no read" row are all ones, so
+// the fold is branch-free.  Filled on the host in the reference's own expression order.
+#define PSCL_FOLD_ROW 6  /* 5 factors padded to 48 B */
+#define PSCL_FOLD_ONES (2 * 64)
+
 template <int NV>
 struct DefaultCfg {
-  static constexpr int NE = NV + NV * (NV - 1) / 2;       // live accumulators per lane
+  static constexpr int ND = NV * (NV - 1) / 2;            // doublet accumulators (k < j)
+  static constexpr int NE = NV + ND + 2;                  // + singlet column scale + pair normaliser
   static constexpr int ROW_D = NV * 3;                    // doubles per genotype row
   static constexpr bool V16 = (NV % 2 == 0);              // row is a multiple of 16 B
   // smem row stride in doubles: odd multiple of 16 B (even NV) / odd number of doubles (odd NV)
   static constexpr int STRIDE_D = V16 ? ((ROW_D / 2) | 1) * 2 : ROW_D;
+  // cooperative gather geometry: CH-byte pieces, LPR (power of two) lanes per row, RPI rows per instruction
+  static constexpr int CH = V16 ? 16 : 8;
+  static constexpr int NCH = ROW_D * 8 / CH;
+  static constexpr int LPR = NCH <= 1 ? 1 : NCH <= 2 ? 2 : NCH <= 4 ? 4 : NCH <= 8 ? 8 : NCH <= 16 ? 16 : 32;
+  static constexpr int RPI = 32 / LPR;
+  static_assert(NCH <= 32, "genotype row too long for the cooperative gather");
   static constexpr int THREADS = 256;
-  static constexpr size_t SMEM = sizeof(double) * 256 + (size_t)2 * THREADS * STRIDE_D * sizeof(double) +
-                                 (size_t)NE * THREADS * sizeof(int);
+  static constexpr size_t SMEM = sizeof(double) * 3 * 64 * PSCL_FOLD_ROW +
+                                 (size_t)2 * THREADS * STRIDE_D * sizeof(double) + (size_t)NE * THREADS * sizeof(int);
 };
 
 struct DemuxArgs {
@@ -49,6 +63,7 @@ struct DemuxArgs {
   const double* gp;
   const uint8_t* has_gp;
   const double* phred_err;
+  const double* fold_tab;     // [3][64][PSCL_FOLD_ROW]
   const int32_t* item_order;  // nullable
   const int64_t* item_pbeg;
   const int64_t* item_pend;
@@ -61,16 +76,16 @@ struct DemuxArgs {
 template <int NV>
 __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
-  constexpr int NE = Cfg::NE;
+  constexpr int NE = Cfg::NE, ND = Cfg::ND, SD = Cfg::STRIDE_D;
+  constexpr int E_SG0 = NV + ND, E_MX = NV + ND + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_err = reinterpret_cast<double*>(smem_raw);                 // [256]
-  double* s_g = s_err + 256;                                           // [2][256][STRIDE_D]
-  int* s_exp = reinterpret_cast<int*>(s_g + 2 * 256 * Cfg::STRIDE_D);  // [NE][256]
+  double* s_tab = reinterpret_cast<double*>(smem_raw);        // [3*64][PSCL_FOLD_ROW]
+  double* s_g = s_tab + 3 * 64 * PSCL_FOLD_ROW;               // [2][256][SD]
+  int* s_exp = reinterpret_cast<int*>(s_g + 2 * 256 * SD);    // [NE][256]
   const int tid = threadIdx.x, lane = tid & 31;
-  s_err[tid] = a.phred_err[tid];
+  for (int i = tid; i < 3 * 64 * PSCL_FOLD_ROW; i += 256) s_tab[i] = a.fold_tab[i];
   __syncthreads();
-  const double invD = 1.0 / (1.0 + 1e-10);
-  double* my_g[2] = {s_g + (size_t)tid * Cfg::STRIDE_D, s_g + (size_t)(256 + tid) * Cfg::STRIDE_D};
+  double* const g_row0 = s_g + (size_t)tid * SD;              // buffer 1 is 256*SD doubles further
 
   for (;;) {
     int w = 0;
@@ -79,44 +94,47 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     if (w >= a.n_work) break;
     const int item = a.item_order ? a.item_order[w] : a.item_base + w;
     const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
-    const int64_t niter = (pe - pb + 31) >> 5;
+    const int niter = (int)((pe - pb + 31) >> 5);
 
     double acc[NE];
 #pragma unroll
     for (int e = 0; e < NE; ++e) { acc[e] = 1.0; s_exp[e * 256 + tid] = 0; }
+    int n_has = 0;
 
-    // ---- pipeline prologue -------------------------------------------------------------------
-    // stage A (two ahead): snp, r0, r1;  stage B (one ahead): read bytes, has_gp, genotype row
+    // ---- software pipeline --------------------------------------------------------------------
+    // stage A (two iterations ahead): snp, r0, r1
+    // stage B (one ahead): first 3 read bytes (kept in separate registers so nothing waits on them
+    //                      before use), has_gp, genotype row via cp.async into this lane's smem row
     int32_t snpA = 0; uint32_t r0A = 0, r1A = 0; bool okA = false;
-    int32_t snpB = 0; uint32_t r0B = 0, r1B = 0; bool okB = false;
-    uint32_t bytesB = 0; bool hasB = false;
-    auto loadA = [&](int64_t it) {
-      int64_t p = pb + (it << 5) + lane;
+    uint32_t r0B = 0, r1B = 0, b0B = 0, b1B = 0, b2B = 0, hasB = 0;
+    auto loadA = [&](int it) {
+      int64_t p = pb + ((int64_t)it << 5) + lane;
       okA = (it < niter) && (p < pe);
       if (okA) { snpA = a.pair_snp[p]; r0A = a.pair_rd[p]; r1A = a.pair_rd[p + 1]; }
     };
-    auto issueB = [&](int buf) {  // consumes stage A registers
-      snpB = snpA; r0B = r0A; r1B = r1A; okB = okA;
-      hasB = okB;
-      bytesB = 0;
-      if (okB) {
-        if (a.has_gp) hasB = a.has_gp[snpB] != 0;
-        uint32_t n = r1B - r0B;
-        // first 4 reads of the pair, one byte each (allele<<6 | qual)
-        if (n > 0) bytesB |= (uint32_t)a.rd_aq[r0B];
-        if (n > 1) bytesB |= (uint32_t)a.rd_aq[r0B + 1] << 8;
-        if (n > 2) bytesB |= (uint32_t)a.rd_aq[r0B + 2] << 16;
-        if (n > 3) bytesB |= (uint32_t)a.rd_aq[r0B + 3] << 24;
-        if (hasB) {
-          const double* src = a.gp + (size_t)snpB * Cfg::ROW_D;
-          double* dst = my_g[buf];
-          if constexpr (Cfg::V16) {
+    auto issueB = [&](int buf) {  // consumes stage A
+      r0B = r0A; r1B = r1A; hasB = 0; b0B = b1B = b2B = PSCL_FOLD_ONES << 6;  // placeholder: "no read"
+      if (okA) {
+        hasB = 1;
+        if (a.has_gp) hasB = a.has_gp[snpA];
+        const uint32_t n = r1B - r0B;
+        if (n > 0) b0B = a.rd_aq[r0B];
+        if (n > 1) b1B = a.rd_aq[r0B + 1];
+        if (n > 2) b2B = a.rd_aq[r0B + 2];
+      }
+      // Cooperative row gather: the warp's 32 genotype rows are fetched LPR lanes per row, so one
+      // LDGSTS instruction touches 32/LPR whole rows (a few 128-B lines) instead of 32 scattered
+      // 16-B pieces of 32 different rows (one L1 tag lookup each).
+      const unsigned okmask = __ballot_sync(0xffffffffu, okA);
+      double* dst_base = s_g + ((size_t)buf * 256 + (tid & ~31)) * SD;
 #pragma unroll
-            for (int i = 0; i < Cfg::ROW_D; i += 2) __pipeline_memcpy_async(dst + i, src + i, 16);
-          } else {
-#pragma unroll
-            for (int i = 0; i < Cfg::ROW_D; ++i) __pipeline_memcpy_async(dst + i, src + i, 8);
-          }
+      for (int i = 0; i < Cfg::LPR; ++i) {
+        const int row = i * Cfg::RPI + (lane / Cfg::LPR), piece = lane % Cfg::LPR;
+        const int snp_r = __shfl_sync(0xffffffffu, snpA, row);
+        if (((okmask >> row) & 1u) && piece < Cfg::NCH) {
+          const char* src = reinterpret_cast<const char*>(a.gp + (size_t)snp_r * Cfg::ROW_D) + piece * Cfg::CH;
+          char* dst = reinterpret_cast<char*>(dst_base + (size_t)row * SD) + piece * Cfg::CH;
+          __pipeline_memcpy_async(dst, src, Cfg::CH);
         }
       }
       __pipeline_commit();
@@ -125,50 +143,46 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     issueB(0);
     loadA(1);
 
-    for (int64_t it = 0; it < niter; ++it) {
-      const int buf = (int)(it & 1);
-      // current iteration's operands (stage B of the previous step)
-      const uint32_t r0 = r0B, r1 = r1B, bytes = bytesB;
-      const bool has = hasB;
-      // issue the next iteration's loads before computing
+    for (int it = 0; it < niter; ++it) {
+      const int buf = it & 1;
+      const uint32_t r0 = r0B, r1 = r1B, b0 = b0B, b1 = b1B, b2 = b2B;
+      const bool has = hasB != 0;
+      __syncwarp();  // every lane is done reading buffer buf^1 (iteration it-1) before it is refilled
       issueB(buf ^ 1);
       loadA(it + 2);
-      __pipeline_wait_prior(1);  // the row of iteration `it` has landed
+      __pipeline_wait_prior(1);  // this lane's pieces of iteration `it` have landed ...
+      __syncwarp();              // ... and so have the other lanes' pieces of this lane's row
 
       if (has) {
-        // ---- D1/D2: fold the reads (cmd_cram_demuxlet.cpp:660-725) -------------------------
-        // p = 0.5*l + (m-l)*0.5*alpha (:673) takes 5 values on the {0,0.5} grid: 0,.25,.5,.75,1
-        double f0 = 1.0, f1 = 1.0, f2 = 1.0, f3 = 1.0, f4 = 1.0;
+        ++n_has;
+        // ---- D1: fold the reads (cmd_cram_demuxlet.cpp:660-700), branch-free for the first 3 ----
+        // byte = allele<<6 | qual -> table row allele*64+qual; the placeholder maps to the ones row
+        const double* t0 = s_tab + (b0 < 256u ? b0 : (uint32_t)PSCL_FOLD_ONES) * PSCL_FOLD_ROW;
+        const double* t1 = s_tab + (b1 < 256u ? b1 : (uint32_t)PSCL_FOLD_ONES) * PSCL_FOLD_ROW;
+        const double* t2 = s_tab + (b2 < 256u ? b2 : (uint32_t)PSCL_FOLD_ONES) * PSCL_FOLD_ROW;
+        double f0 = t0[0] * t1[0] * t2[0], f1 = t0[1] * t1[1] * t2[1], f2 = t0[2] * t1[2] * t2[2],
+               f3 = t0[3] * t1[3] * t2[3], f4 = t0[4] * t1[4] * t2[4];
         const uint32_t nrd = r1 - r0;
-        for (uint32_t r = 0; r < nrd; ++r) {
-          uint32_t aq = (r < 4) ? ((bytes >> (8 * r)) & 0xffu) : (uint32_t)a.rd_aq[r0 + r];
-          uint32_t al = aq >> 6;
-          if (al == 2) continue;  // :664
-          double err = s_err[aq & 63u];
-          double mat = 1.0 - err, e3 = err / 3.0;
-          double pR = (al == 0) ? mat : e3;  // :666
-          double pA = (al == 1) ? mat : e3;  // :667
-          f0 *= pR;
-          f1 *= (pR * 0.75 + pA * 0.25);
-          f2 *= (pR * 0.5 + pA * 0.5);
-          f3 *= (pR * 0.25 + pA * 0.75);
-          f4 *= pA;
-          if ((r & 7u) == 7u) {  // keep deep pileups away from underflow (:692-699 does it per read)
-            double mx = fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
-            double ri = 1.0 / mx;
+        for (uint32_t r = 3; r < nrd; ++r) {  // rare: > 3 base-calls on one (cell,SNP)
+          const double* t = s_tab + (uint32_t)a.rd_aq[r0 + r] * PSCL_FOLD_ROW;
+          f0 *= t[0]; f1 *= t[1]; f2 *= t[2]; f3 *= t[3]; f4 *= t[4];
+          if ((r & 7u) == 7u) {  // deep pileups: rescale by the running max like :692-699
+            const double ri = 1.0 / fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
             f0 *= ri; f1 *= ri; f2 *= ri; f3 *= ri; f4 *= ri;
           }
         }
+        // ---- D2 (:704-725) without the division: pG = (f/mx + 1e-10)/(1+1e-10) = h/(mx*(1+1e-10))
+        // with h = f + 1e-10*mx; the common factor mx is accumulated once per pair (acc[E_MX]) and
+        // (1+1e-10)^n_has is applied at the end.
         const double mx = fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
-        const double ri = 1.0 / mx;
-        const double h0 = fma(f0, ri, 1e-10) * invD, h1 = fma(f1, ri, 1e-10) * invD,
-                     h2 = fma(f2, ri, 1e-10) * invD, h3 = fma(f3, ri, 1e-10) * invD,
-                     h4 = fma(f4, ri, 1e-10) * invD;  // :704-725
+        const double h0 = fma(1e-10, mx, f0), h1 = fma(1e-10, mx, f1), h2 = fma(1e-10, mx, f2),
+                     h3 = fma(1e-10, mx, f3), h4 = fma(1e-10, mx, f4);
+        acc[E_MX] *= mx;
 
-        // ---- D3: genotype row from shared memory --------------------------------------------
+        // ---- D3: genotype row from this lane's shared-memory row ------------------------------
         double G[NV][3];
         {
-          const double* row = my_g[buf];
+          const double* row = g_row0 + (size_t)buf * 256 * SD;
           if constexpr (Cfg::V16) {
             const double2* r2 = reinterpret_cast<const double2*>(row);
             double flat[Cfg::ROW_D];
@@ -181,10 +195,11 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
             for (int j = 0; j < NV; ++j) { G[j][0] = row[3 * j]; G[j][1] = row[3 * j + 1]; G[j][2] = row[3 * j + 2]; }
           }
         }
-        // singlets: llksAB[j][0][0] (:806) = log( (sum_l g_j[l] pG0[l]) * (sum_m g_0[m]) ), pG0[l] = h(2l)
-        const double sg0 = G[0][0] + G[0][1] + G[0][2];
+        // singlets: llksAB[j][0][0] (:806) = log((sum_l g_j[l] pG0[l]) * (sum_m g_0[m])), pG0[l] = h(2l);
+        // the (sum_m g_0[m]) column factor is common to all j and accumulated once
+        acc[E_SG0] *= (G[0][0] + G[0][1] + G[0][2]);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) acc[j] *= (G[j][0] * h0 + G[j][1] * h2 + G[j][2] * h4) * sg0;
+        for (int j = 0; j < NV; ++j) acc[j] *= (G[j][0] * h0 + G[j][1] * h2 + G[j][2] * h4);
         // doublets at alpha = 0.5: pG1[l][m] = h(l+m)
 #pragma unroll
         for (int j = 1; j < NV; ++j) {
@@ -203,26 +218,54 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     }
     __pipeline_wait_prior(0);
 
-    // ---- item epilogue: one log per accumulator, warp sum, write the partial grid ------------
+    // ---- item epilogue ---------------------------------------------------------------------------
+    // Lane products are multiplied across the warp first (mantissas in [1,2) after renorm, so 32 of
+    // them cannot overflow), then ONE log per accumulator per item, taken by lane e%32.  Rolled
+    // through this lane's (now free) genotype rows so it does not bloat the hot loop's I-footprint.
+    {
+      double* st0 = g_row0;
+      double* st1 = g_row0 + (size_t)256 * SD;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) { if (e < SD) st0[e] = acc[e]; else st1[e - SD] = acc[e]; }
+    }
+    double corr = 0.0, sg0_log = 0.0, keep_m0 = 1.0, keep_m1 = 1.0;
+    int keep_e0 = 0, keep_e1 = 0;
+#pragma unroll 1
+    for (int e = 0; e < NE; ++e) {
+      double m = (e < SD) ? g_row0[e] : g_row0[(size_t)256 * SD + (e - SD)];
+      int ex = s_exp[e * 256 + tid];
+      pscl_renorm(m, ex);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m *= __shfl_xor_sync(0xffffffffu, m, o);
+        ex += __shfl_xor_sync(0xffffffffu, ex, o);
+      }
+      if (e == E_MX) {  // every lane: log(prod mx * (1+1e-10)^n_has), the pair normaliser of :704-725
+        int nh = n_has;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, o);
+        corr = pscl_prod_log(m, ex) + (double)nh * log1p(1e-10);
+      } else if (e == E_SG0) {  // every lane: log prod (sum_m g_0[m]), the k=0 column factor of :806
+        sg0_log = pscl_prod_log(m, ex);
+      } else if ((e & 31) == lane) {
+        if (e < 32) { keep_m0 = m; keep_e0 = ex; } else { keep_m1 = m; keep_e1 = ex; }
+      }
+    }
     double* out = a.partial + (size_t)(item - a.item_base) * (NV * NV * 2);
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      double x = pscl_prod_log(acc[e], s_exp[e * 256 + tid]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      acc[e] = x;
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) out[(j * NV + 0) * 2 + 0] = acc[j];
-#pragma unroll
-      for (int j = 1; j < NV; ++j)
-#pragma unroll
-        for (int k = 0; k < j; ++k) {
-          double x = acc[NV + j * (j - 1) / 2 + k];
+    for (int half = 0; half < 2; ++half) {
+      const int e = lane + 32 * half;
+      if (e < NV + ND) {
+        double x = pscl_prod_log(half ? keep_m1 : keep_m0, half ? keep_e1 : keep_e0) - corr;
+        if (e < NV) out[(e * NV + 0) * 2 + 0] = x + sg0_log;
+        else {
+          int dd = e - NV, j = 1;
+          while ((j + 1) * j / 2 <= dd) ++j;  // dd = j(j-1)/2 + k
+          const int k = dd - j * (j - 1) / 2;
           out[(j * NV + k) * 2 + 1] = x;
           out[(k * NV + j) * 2 + 1] = x;
         }
+      }
     }
     __syncwarp();
   }
@@ -615,7 +658,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     if (nwork > 0) {
       DemuxArgs a;
       a.pair_snp = plp->pair_snp; a.pair_rd = plp->pair_rd; a.rd_aq = plp->rd_aq;
-      a.gp = ctx->gp; a.has_gp = ctx->has_gp; a.phred_err = ctx->phred_err;
+      a.gp = ctx->gp; a.has_gp = ctx->has_gp; a.phred_err = ctx->phred_err; a.fold_tab = ctx->fold_tab;
       a.item_order = (ib == 0 && ie == plp->n_items) ? plp->item_order : nullptr;
       a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend;
       a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
