@@ -43,6 +43,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
 
 def host_sources():
     d = os.path.join(HERE, "host")
+    if not os.path.isdir(d):
+        return []
     return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cpp", ".h"))]
 
 
