@@ -199,23 +199,47 @@ int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* op
                  int32_t* clust_cnt, pscl_fmx_result* res);
 
 /* Step-level API for SNP-sharded multi-GPU EM: each rank uploads the pairs of its
- * SNP range (cells keep global ids), and the caller all-reduces the LLK partials between
- * E-step and classify. */
+ * SNP range (cells keep global ids), and the caller all-reduces the per-cell partial sums between
+ * the steps.  All `_dev` pointers are device memory on the context's GPU; kernels are enqueued on
+ * pscl_stream().  Sequence:
+ *   init -> stage1 -> [all-reduce stage1_dev] -> seed -> mstep(clust_dev) ->
+ *   repeat { estep -> [all-reduce llk_dev] -> classify -> mstep(NULL) } -> fetch            */
 int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp* plp, const pscl_fmx_opts* opts);
-/* stage 1: per-pair 9-GL (kept on device) + per-cell partial llk0/llk2/nsnps/nreads written
- * to stage1_dev[4*C] doubles (llk0, llk2, nsnps, nreads planes) for the caller to all-reduce. */
+/* Stage 1 (cmd_cram_freemux2.cpp:117-159): per-pair 9-GL (kept on the device) and the per-cell
+ * partial sums of the local pairs, written to stage1_dev[4*C] doubles as four planes
+ * llk0 | llk2 | nsnps | nreads. */
 int pscl_fmx_stage1(pscl_ctx* ctx, double* stage1_dev);
-/* greedy seeding on the local pairs; needs the all-reduced scores. Only meaningful unsharded. */
-int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, int32_t* clust_dev);
-/* (re)build the cluster table from membership clust_dev[C] (-1 = none): ordered merges. */
+/* Consumes the (all-reduced) stage-1 planes: fills the per-cell records, then either takes the
+ * initial clusters from init_clust_dev[C] (-1 = unassigned; --init-cluster, :198-216) or, when
+ * it is NULL, runs the greedy seeding (:184-189, :223-260) on the local pairs — only meaningful
+ * when this rank holds all pairs.  clust_dev[C] receives the initial cluster of every cell. */
+int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int32_t* init_clust_dev,
+                  int32_t* clust_dev);
+/* (Re)builds the cluster pileups of the local SNPs by ordered merges (:277-288, :590-596).
+ * clust_dev[C] = cluster each cell is merged into (-1 = none); NULL = the singlet membership the
+ * last pscl_fmx_classify produced. */
 int pscl_fmx_mstep(pscl_ctx* ctx, const int32_t* clust_dev);
-/* E-step partial LLKs of the local SNP range into llk_dev[C * npairs] (overwritten). */
+/* E-step partial LLKs of the local SNPs (:383-456) into llk_dev[C * npairs] (overwritten),
+ * pair (j,k<=j) at index j(j+1)/2+k as in the reference. */
 int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev);
-/* epilogue + classify from (all-reduced) llk_dev; updates clust_dev, cell records; returns
- * nchanged etc. in *res (synchronises). */
+/* Per-cell epilogue + classification from the (all-reduced) llk_dev (:458-584); updates the
+ * cell records, clust_dev and the membership of the next M-step; *res (nullable) receives
+ * nchanged etc.  Synchronises. */
 int pscl_fmx_classify(pscl_ctx* ctx, const double* llk_dev, int32_t* clust_dev,
                       pscl_fmx_result* res);
+/* Per-cell records (nullable) and, when requested, the full cluster pileups of the current
+ * membership (layout as in pscl_fmx_run).  Synchronises. */
 int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt);
+/* Device time (ms) of the last pscl_fmx_estep or pscl_fmx_mstep (CUDA events on pscl_stream). */
+int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float* ms);
+
+/* ---- knobs used by tests and the benchmark harness ---- */
+/* Launch on a caller-owned stream (e.g. torch's current stream) instead of the context's own. */
+int pscl_set_stream(pscl_ctx* ctx, void* cuda_stream);
+/* Upper bound of the per-batch partial-grid scratch of pscl_demux_score (default 1 GiB). */
+int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes);
+/* Route every alpha grid through the general demuxlet kernel (parity tests of that kernel). */
+int pscl_demux_force_general(pscl_ctx* ctx, int enable);
 
 #ifdef __cplusplus
 }

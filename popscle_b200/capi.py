@@ -175,12 +175,12 @@ def load_library() -> C.CDLL:
         "pscl_fmx_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult)]),
         "pscl_fmx_init": (C.c_int, [vp, vp, C.POINTER(CFmxOpts)]),
         "pscl_fmx_stage1": (C.c_int, [vp, vp]),
-        "pscl_fmx_seed": (C.c_int, [vp, vp, vp]),
+        "pscl_fmx_seed": (C.c_int, [vp, vp, vp, vp]),
         "pscl_fmx_mstep": (C.c_int, [vp, vp]),
         "pscl_fmx_estep": (C.c_int, [vp, i32, vp]),
         "pscl_fmx_classify": (C.c_int, [vp, vp, vp, C.POINTER(CFmxResult)]),
         "pscl_fmx_fetch": (C.c_int, [vp, vp, vp, vp]),
-        "pscl_fmx_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "pscl_fmx_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError = the library does not export what the header declares
@@ -341,6 +341,43 @@ class Context:
                                         out.ctypes.data, gl.ctypes.data if gl is not None else None,
                                         cnt.ctypes.data if cnt is not None else None, C.byref(res)))
         return out, res, gl, cnt
+
+    # step-level freemuxlet API (SNP-sharded EM): *_dev arguments are raw device pointers (ints)
+    def fmx_init(self, dplp: "DevicePileup", opts: CFmxOpts):
+        self._chk(self.lib.pscl_fmx_init(self.h, dplp.h, C.byref(opts)))
+        self._fmx_shape = (dplp.n_cells, dplp.n_snps, opts.n_clusters)
+
+    def fmx_stage1(self, stage1_dev: int):
+        self._chk(self.lib.pscl_fmx_stage1(self.h, C.c_void_p(stage1_dev)))
+
+    def fmx_seed(self, stage1_dev: int, init_clust_dev: int | None, clust_dev: int):
+        self._chk(self.lib.pscl_fmx_seed(self.h, C.c_void_p(stage1_dev),
+                                         C.c_void_p(init_clust_dev) if init_clust_dev else None, C.c_void_p(clust_dev)))
+
+    def fmx_mstep(self, clust_dev: int | None):
+        self._chk(self.lib.pscl_fmx_mstep(self.h, C.c_void_p(clust_dev) if clust_dev else None))
+
+    def fmx_estep(self, it: int, llk_dev: int):
+        self._chk(self.lib.pscl_fmx_estep(self.h, it, C.c_void_p(llk_dev)))
+
+    def fmx_classify(self, llk_dev: int, clust_dev: int) -> CFmxResult:
+        res = CFmxResult()
+        self._chk(self.lib.pscl_fmx_classify(self.h, C.c_void_p(llk_dev), C.c_void_p(clust_dev), C.byref(res)))
+        return res
+
+    def fmx_fetch(self, want_clusters: bool = False):
+        nc, nv, ns = self._fmx_shape
+        out = np.zeros(nc, dtype=FMX_CELL_DTYPE)
+        gl = np.empty((nv, ns, 9), dtype=np.float64) if want_clusters else None
+        cnt = np.empty((nv, ns, 3), dtype=np.int32) if want_clusters else None
+        self._chk(self.lib.pscl_fmx_fetch(self.h, out.ctypes.data, gl.ctypes.data if want_clusters else None,
+                                          cnt.ctypes.data if want_clusters else None))
+        return out, gl, cnt
+
+    def fmx_last_kernel_ms(self) -> float:
+        a = C.c_float()
+        self._chk(self.lib.pscl_fmx_last_kernel_ms(self.h, C.byref(a)))
+        return a.value
 
 
 class DevicePileup:

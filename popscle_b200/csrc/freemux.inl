@@ -1,12 +1,1031 @@
-// freemux.inl — freemuxlet kernels (stage 1, seeding, E-step, classify, M-step)
-static void fmx_state_free(pscl_ctx* ctx) { (void)ctx; }
-#define FMX_TODO(ctx) (ctx ? pscl_fail(ctx, PSCL_ESTATE, "freemuxlet path not built yet") : PSCL_EINVAL)
-extern "C" int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup*, const pscl_fmx_opts*, const int32_t*, pscl_fmx_cell*, double*, int32_t*, pscl_fmx_result*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp*, const pscl_fmx_opts*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_stage1(pscl_ctx* ctx, double*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double*, int32_t*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_mstep(pscl_ctx* ctx, const int32_t*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_estep(pscl_ctx* ctx, int32_t, double*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_classify(pscl_ctx* ctx, const double*, int32_t*, pscl_fmx_result*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell*, double*, int32_t*) { return FMX_TODO(ctx); }
-extern "C" int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float*, float*, float*) { return FMX_TODO(ctx); }
+// freemux.inl — freemuxlet on the device (part of the single TU popscle_b200.cu)
+//
+// Replaces cmd_cram_freemux2.cpp:117-605 (`popscle freemuxlet`) and the EM rules of
+// cmd_cram_freemuxlet.cpp:456-653 (`freemuxlet-old`, opts.mode_old):
+//
+//   k_fmx_stage1      per (cell,SNP) pair 9-genotype likelihoods (sc_drop_seq.cpp:452-509) and the
+//                     per-cell singlet score sums (cmd_cram_freemux2.cpp:138-159)
+//   k_fmx_seed        greedy sequential cluster seeding (:223-260, sc_drop_seq.cpp:544-578), one
+//                     persistent CTA walking the cells in score order
+//   k_fmx_mstep       cluster pileups rebuilt by ordered merges (:277-288, :590-596,
+//                     sc_drop_seq.h:77-101); one thread per (SNP, cluster) replays the merges of the
+//                     SNP-major pair list in ascending cell id — the clamp makes merge order matter
+//   k_fmx_posterior   per (SNP, cluster) genotype posterior u = (1-e) norm(h * gl_diag) + e h (:402-415):
+//                     it does not depend on the cell, so it is built once per iteration, not per pair
+//   k_fmx_estep       cell x cluster-pair LLK partials (:383-456); one lane per (cell,SNP) pair, running
+//                     products in registers, posterior rows gathered into shared memory (cp.async)
+//   k_fmx_classify    best/next scans, logAdd sums, SNG/DBL/AMB decision, nchanged (:458-584)
+//
+// Data layout: stage 1 keeps the pair GLs twice — plane-major [9][P] in cell-major pair order (lane
+// per pair kernels read 9 coalesced streams) and record-major [P][9] in SNP-major order (the M-step
+// walks one SNP's cells as one contiguous block).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#define PSCL_FMX_MAX_CLUSTERS 24
+#define PSCL_MIN_NORM_GL 1e-6 /* sc_drop_seq.h:14 */
+
+struct pscl_fmx_state {
+  const pscl_plp* plp = nullptr;
+  pscl_fmx_opts o{};
+  int nS = 0, npairs = 0, US = 0, SD = 0;  // US: posterior row stride (doubles, even); SD: smem row stride
+  int32_t C = 0, V = 0;
+  int64_t P = 0;
+  // SNP-major view of the pair list (ascending cell id inside one SNP)
+  int64_t* snp_ptr = nullptr;    // [V+1]
+  uint32_t* snp_pair = nullptr;  // [P] cell-major pair id of each SNP-major entry
+  int32_t* snp_cell = nullptr;   // [P] cell of each SNP-major entry
+  uint32_t* csc_pos = nullptr;   // [P] SNP-major position of each cell-major pair
+  double* gl_soa = nullptr;      // [9][P]  cell-major
+  double* gl_csc = nullptr;      // [P][9]  SNP-major
+  double* clust_diag = nullptr;  // [V][nS][3]  diagonal GLs of the cluster pileups (all the E-step reads)
+  double* u_tab = nullptr;       // [V][US]     per (SNP, cluster) posterior
+  double* clust_gl = nullptr;    // [V][nS][9]  full cluster pileups (seeding, final output)
+  int32_t* clust_cnt = nullptr;  // [V][nS][3]
+  uint8_t* present = nullptr;    // [V][nS]     map membership during seeding (sc_drop_seq.cpp:551-552)
+  pscl_fmx_cell* cells = nullptr;  // [C]
+  int32_t* member = nullptr;       // [C] cluster the next M-step merges the cell into (-1 = none)
+  double* item_s1 = nullptr;       // [n_items][2] stage-1 partial llk0 / llk2
+  int32_t* item_nrd = nullptr;     // [n_items]    stage-1 partial read count
+  double* item_llk = nullptr;      // [n_items][npairs]
+  int32_t* counters = nullptr;     // [4] nchanged, nsingle, namb
+  int32_t* order = nullptr;        // [C] seeding order
+  int* work_counter = nullptr;
+  double* own_stage1 = nullptr;    // buffers of the one-call path
+  double* own_llk = nullptr;
+  int32_t* own_clust = nullptr;
+  bool stage1_done = false, begun = false, final_tab = false;
+  int iters = 0;
+  pscl_fmx_result last{};
+  float ms_estep = 0.f, ms_mstep = 0.f, ms_classify = 0.f;
+};
+
+static void fmx_state_free(pscl_ctx* ctx) {
+  pscl_fmx_state* s = ctx->fmx;
+  if (!s) return;
+  cudaFree(s->snp_ptr); cudaFree(s->snp_pair); cudaFree(s->snp_cell); cudaFree(s->csc_pos);
+  cudaFree(s->gl_soa); cudaFree(s->gl_csc); cudaFree(s->clust_diag); cudaFree(s->u_tab);
+  cudaFree(s->clust_gl); cudaFree(s->clust_cnt); cudaFree(s->present); cudaFree(s->cells);
+  cudaFree(s->member); cudaFree(s->item_s1); cudaFree(s->item_nrd); cudaFree(s->item_llk);
+  cudaFree(s->counters); cudaFree(s->order); cudaFree(s->work_counter);
+  cudaFree(s->own_stage1); cudaFree(s->own_llk); cudaFree(s->own_clust);
+  delete s;
+  ctx->fmx = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SNP-major view
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fmx_iota(uint32_t* v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+
+// after the stable sort by SNP: segment starts, owning cell of each entry, inverse permutation
+__global__ void k_fmx_csc_fill(const int32_t* __restrict__ key, const uint32_t* __restrict__ val,
+                               const int64_t* __restrict__ cell_ptr, int32_t C, int32_t V, int64_t P,
+                               int64_t* __restrict__ snp_ptr, int32_t* __restrict__ snp_cell,
+                               uint32_t* __restrict__ csc_pos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int32_t k = key[i];
+  const int32_t prev = (i == 0) ? -1 : key[i - 1];
+  for (int32_t v = prev + 1; v <= k; ++v) snp_ptr[v] = i;
+  if (i == P - 1)
+    for (int32_t v = k + 1; v <= V; ++v) snp_ptr[v] = P;
+  const uint32_t p = val[i];
+  csc_pos[p] = (uint32_t)i;
+  int lo = 0, hi = C;  // largest c with cell_ptr[c] <= p
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (cell_ptr[mid] <= (int64_t)p) lo = mid; else hi = mid;
+  }
+  snp_cell[i] = lo;
+}
+
+__global__ void k_fmx_fill_i64(int64_t* v, int64_t n, int64_t x) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1 (sc_drop_seq.cpp:452-509 + cmd_cram_freemux2.cpp:138-159)
+// ------------------------------------------------------------------------------------------------
+struct S1Args {
+  const int32_t* pair_snp;
+  const uint32_t* pair_rd;
+  const uint8_t* rd_aq;
+  const double* snp_af;
+  const double* phred_err;
+  const uint32_t* csc_pos;
+  const int64_t* item_pbeg;
+  const int64_t* item_pend;
+  double* gl_soa;
+  double* gl_csc;
+  double* item_s1;
+  int32_t* item_nrd;
+  int64_t P;
+  int32_t n_items;
+};
+
+__global__ void __launch_bounds__(256) k_fmx_stage1(S1Args a) {
+  __shared__ double s_err[64];
+  if (threadIdx.x < 64) s_err[threadIdx.x] = a.phred_err[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  // the 9 mixing weights of a REF base at alpha = 0.5 (:482-490); ALT is the mirror image
+  const double wref[9] = {1.0, 0.75, 0.5, 0.75, 0.5, 0.25, 0.5, 0.25, 0.0};
+  for (int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < a.n_items; item += warps) {
+    const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
+    double l0 = 0.0, l2 = 0.0;
+    int nrd_all = 0;
+    for (int64_t p = pb + lane; p < pe; p += 32) {
+      const uint32_t r0 = a.pair_rd[p], r1 = a.pair_rd[p + 1];
+      double gl[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) gl[i] = 1.0;
+      for (uint32_t r = r0; r < r1; ++r) {
+        const uint32_t aq = a.rd_aq[r], al = aq >> 6;
+        if (al > 1) continue;  // :467 (still counted in nreads, :465)
+        const double err = s_err[aq & 63u];
+        const double mat = 1.0 - err, e4 = err / 4.;  // PhredHelper.cpp:32
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {  // no FMA contraction: the reference multiplies, then adds
+          gl[i] = __dmul_rn(gl[i], __dadd_rn(__dmul_rn(mat, al == 0 ? wref[i] : wref[8 - i]), e4));
+          t = __dadd_rn(t, gl[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gl[i] /= t;  // :493-494
+      }
+      nrd_all += (int)(r1 - r0);
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { gl[i] = (gl[i] < PSCL_MIN_NORM_GL) ? PSCL_MIN_NORM_GL : gl[i]; t = __dadd_rn(t, gl[i]); }  // :498-503
+#pragma unroll
+      for (int i = 0; i < 9; ++i) gl[i] /= t;
+      const uint32_t q = a.csc_pos[p];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { a.gl_soa[(size_t)i * a.P + p] = gl[i]; a.gl_csc[(size_t)q * 9 + i] = gl[i]; }
+      const double af = a.snp_af[a.pair_snp[p]];
+      double h[3];
+      h[0] = __dmul_rn(1.0 - af, 1.0 - af); h[1] = __dmul_rn(__dmul_rn(2.0, af), 1.0 - af); h[2] = __dmul_rn(af, af);
+      double lk0 = 0.0, lk2 = 0.0;
+#pragma unroll
+      for (int gi = 0; gi < 3; ++gi) {  // cmd_cram_freemux2.cpp:143-148
+        lk2 = __dadd_rn(lk2, __dmul_rn(gl[gi * 3 + gi], h[gi]));
+#pragma unroll
+        for (int gj = 0; gj < 3; ++gj) lk0 = __dadd_rn(lk0, __dmul_rn(__dmul_rn(gl[gi * 3 + gj], h[gi]), h[gj]));
+      }
+      l0 += log(lk0);
+      l2 += log(lk2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+      l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+      nrd_all += __shfl_xor_sync(0xffffffffu, nrd_all, o);
+    }
+    if (lane == 0) { a.item_s1[2 * item] = l0; a.item_s1[2 * item + 1] = l2; a.item_nrd[item] = nrd_all; }
+  }
+}
+
+// per-cell sums of the item partials in item order -> planes llk0 | llk2 | nsnps | nreads of stage1[4*C]
+__global__ void k_fmx_stage1_cells(const int32_t* __restrict__ cell_item_ptr, const int64_t* __restrict__ cell_ptr,
+                                   const double* __restrict__ item_s1, const int32_t* __restrict__ item_nrd,
+                                   int32_t C, double* __restrict__ stage1) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double l0 = 0.0, l2 = 0.0;
+  int64_t nr = 0;
+  for (int it = cell_item_ptr[c]; it < cell_item_ptr[c + 1]; ++it) { l0 += item_s1[2 * it]; l2 += item_s1[2 * it + 1]; nr += item_nrd[it]; }
+  stage1[c] = l0;
+  stage1[(size_t)C + c] = l2;
+  stage1[(size_t)2 * C + c] = (double)(cell_ptr[c + 1] - cell_ptr[c]);
+  stage1[(size_t)3 * C + c] = (double)nr;
+}
+
+// cell records from the (all-reduced) stage-1 planes; initial membership (cmd_cram_freemux2.cpp:192-216, :350-370)
+__global__ void k_fmx_begin(const double* __restrict__ stage1, const int32_t* __restrict__ init_clust, int32_t C,
+                            pscl_fmx_cell* __restrict__ cells, int32_t* __restrict__ clust, double* __restrict__ score) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  pscl_fmx_cell r;
+  memset(&r, 0, sizeof(r));
+  r.llk0 = stage1[c];
+  r.llk2 = stage1[(size_t)C + c];
+  r.n_snps = (int32_t)stage1[(size_t)2 * C + c];
+  r.n_reads = (int32_t)stage1[(size_t)3 * C + c];
+  score[c] = r.llk2 - r.llk0;  // :159
+  const int ic = (init_clust && init_clust[c] >= 0) ? init_clust[c] : -1;
+  r.type = (ic >= 0) ? 0 : -1;
+  r.clust = r.init_clust = ic;
+  r.best_j = r.best_k = r.next_j = r.next_k = -1;
+  r.sng_best = r.sng_next = r.dbl_best_j = r.dbl_best_k = r.dbl_next_j = r.dbl_next_k = -1;
+  r.best_llk = r.next_llk = r.sng_best_llk = r.sng_next_llk = r.dbl_best_llk = r.dbl_next_llk = -1e300;
+  r.best_pp = r.sng_pp = r.sng_only_pp = r.sum_llk = -1e300;
+  cells[c] = r;
+  clust[c] = ic;
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge (sc_drop_seq.h:77-101); the reference divides by the sum, here one reciprocal per
+// normalisation (<= 1 ulp apart; bit parity with glibc log() is out of reach anyway)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fmx_merge(double (&gl)[9], const double (&o)[9]) {
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { gl[i] *= o[i]; t += gl[i]; }
+  double r = 1.0 / t;
+  t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { gl[i] *= r; gl[i] = (gl[i] < PSCL_MIN_NORM_GL) ? PSCL_MIN_NORM_GL : gl[i]; t += gl[i]; }
+  r = 1.0 / t;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gl[i] *= r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy seeding (cmd_cram_freemux2.cpp:223-260): one CTA, cells strictly in score order
+// ------------------------------------------------------------------------------------------------
+struct SeedArgs {
+  const int32_t* order;
+  const double* score;
+  const int64_t* cell_ptr;
+  const int32_t* pair_snp;
+  const double* gl_soa;
+  const double* snp_af;
+  double* clust_gl;   // [V][nS][9], initialised to 1.0
+  uint8_t* present;   // [V][nS], initialised to 0
+  int32_t* clust;     // [C] out
+  pscl_fmx_cell* cells;
+  int64_t P;
+  int32_t C, nS;
+  double frac, thres;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_fmx_seed(SeedArgs a) {
+  __shared__ double s_d2[32], s_d0[32], s_sc[PSCL_FMX_MAX_CLUSTERS];
+  __shared__ int s_choice;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nS = a.nS;
+  const int wpc = 32 / nS;            // warps per cluster (nS <= 24 < 32)
+  const int my_j = warp / wpc, my_w = warp % wpc;
+  const bool active = my_j < nS;
+  for (int i = 0; i < a.C; ++i) {
+    const int si = a.order[i];
+    if ((double)i > (double)a.C * a.frac) continue;  // :225
+    if (a.score[si] < a.thres) continue;             // :226
+    const int64_t pb = a.cell_ptr[si], pe = a.cell_ptr[si + 1];
+    // ---- distance to every cluster over the SNPs present in both (sc_drop_seq.cpp:544-578) ----
+    double d2 = 0.0, d0 = 0.0;
+    if (active) {
+      for (int64_t p = pb + my_w * 32 + lane; p < pe; p += (int64_t)wpc * 32) {
+        const int32_t s = a.pair_snp[p];
+        const size_t e = (size_t)s * nS + my_j;
+        if (!a.present[e]) continue;
+        const double af = a.snp_af[s];
+        const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
+        const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
+        const double* cj = a.clust_gl + e * 9;
+        const double cj0 = cj[0], cj1 = cj[4], cj2 = cj[8];
+        const double lk2 = ci0 * cj0 * h0 + ci1 * cj1 * h1 + ci2 * cj2 * h2;
+        const double a0 = ci0 * h0, a1 = ci1 * h1, a2 = ci2 * h2, b0 = cj0 * h0, b1 = cj1 * h1, b2 = cj2 * h2;
+        const double lk0 = (a0 + a1 + a2) * (b0 + b1 + b2);  // sum_g sum_h ci[g] cj[h] h[g] h[h]
+        d2 += log(lk2);
+        d0 += log(lk0);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+    }
+    if (lane == 0) { s_d2[warp] = d2; s_d0[warp] = d0; }
+    __syncthreads();
+    if (tid < nS) {
+      double t2 = 0.0, t0 = 0.0;
+      for (int w = 0; w < wpc; ++w) { t2 += s_d2[tid * wpc + w]; t0 += s_d0[tid * wpc + w]; }
+      s_sc[tid] = t2 - t0;  // dropDs[j].llk2 - dropDs[j].llk0
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = 0;
+      double bs = s_sc[0];
+      for (int j = 1; j < nS; ++j)
+        if (s_sc[j] > bs) { best = j; bs = s_sc[j]; }  // :238-241, first wins
+      s_choice = best;
+      a.clust[si] = best;
+      a.cells[si].clust = a.cells[si].init_clust = best;
+      a.cells[si].type = 0;
+    }
+    __syncthreads();
+    const int jstar = s_choice;
+    // ---- merge the cell into the chosen cluster (:248-251) ----
+    for (int64_t p = pb + tid; p < pe; p += 1024) {
+      const size_t e = (size_t)a.pair_snp[p] * nS + jstar;
+      double gl[9], o[9];
+      double* cg = a.clust_gl + e * 9;
+#pragma unroll
+      for (int g = 0; g < 9; ++g) { gl[g] = cg[g]; o[g] = a.gl_soa[(size_t)g * a.P + p]; }
+      fmx_merge(gl, o);
+#pragma unroll
+      for (int g = 0; g < 9; ++g) cg[g] = gl[g];
+      a.present[e] = 1;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_fmx_fill_f64(double* v, size_t n, double x) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// M-step: cluster pileups from scratch (cmd_cram_freemux2.cpp:277-288, :516-517 + :590-596)
+// ------------------------------------------------------------------------------------------------
+struct MArgs {
+  const int64_t* snp_ptr;
+  const int32_t* snp_cell;
+  const uint32_t* snp_pair;
+  const double* gl_csc;
+  const int32_t* member;
+  const uint32_t* pair_rd;
+  const uint8_t* rd_aq;
+  double* clust_diag;
+  double* clust_gl;    // written when final
+  int32_t* clust_cnt;  // written when final
+  int32_t V, nS, final_;
+};
+
+__global__ void __launch_bounds__(256) k_fmx_mstep(MArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)a.V * a.nS) return;
+  const int v = (int)(t / a.nS), j = (int)(t - (int64_t)v * a.nS);
+  double gl[9];
+#pragma unroll
+  for (int g = 0; g < 9; ++g) gl[g] = 1.0;  // default-constructed pileup (sc_drop_seq.h:72-75)
+  int nreads = 0, nref = 0, nalt = 0;
+  const int64_t b = a.snp_ptr[v], e = a.snp_ptr[v + 1];
+  for (int64_t i = b; i < e; ++i) {  // ascending cell id: the clamp makes the merge order matter
+    if (a.member[a.snp_cell[i]] != j) continue;
+    double o[9];
+    const double* src = a.gl_csc + (size_t)i * 9;
+#pragma unroll
+    for (int g = 0; g < 9; ++g) o[g] = src[g];
+    fmx_merge(gl, o);
+    if (a.final_) {
+      const uint32_t p = a.snp_pair[i];
+      for (uint32_t r = a.pair_rd[p]; r < a.pair_rd[p + 1]; ++r) {
+        const uint32_t al = a.rd_aq[r] >> 6;
+        ++nreads;
+        if (al == 0) ++nref; else if (al == 1) ++nalt;
+      }
+    }
+  }
+  double* d = a.clust_diag + (size_t)t * 3;
+  d[0] = gl[0]; d[1] = gl[4]; d[2] = gl[8];
+  if (a.final_) {
+    double* cg = a.clust_gl + (size_t)t * 9;
+#pragma unroll
+    for (int g = 0; g < 9; ++g) cg[g] = gl[g];
+    int32_t* cc = a.clust_cnt + (size_t)t * 3;
+    cc[0] = nreads; cc[1] = nref; cc[2] = nalt;
+  }
+}
+
+// posterior of each (SNP, cluster) (cmd_cram_freemux2.cpp:388-390, :402-415)
+__global__ void k_fmx_posterior(const double* __restrict__ clust_diag, const double* __restrict__ snp_af, int32_t V,
+                                int32_t nS, int32_t US, double geno_error, int apply_err, double* __restrict__ u_tab) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)V * nS) return;
+  const int v = (int)(t / nS), j = (int)(t - (int64_t)v * nS);
+  const double af = snp_af[v];
+  const double h0 = (1.0 - af) * (1.0 - af), h1 = 2 * af * (1.0 - af), h2 = af * af;
+  const double* d = clust_diag + (size_t)t * 3;
+  double u0 = h0 * d[0], u1 = h1 * d[1], u2 = h2 * d[2];
+  const double s = u0 + u1 + u2;
+  u0 /= s; u1 /= s; u2 /= s;
+  if (apply_err) {
+    u0 = (1 - geno_error) * u0 + geno_error * h0;
+    u1 = (1 - geno_error) * u1 + geno_error * h1;
+    u2 = (1 - geno_error) * u2 + geno_error * h2;
+  }
+  double* u = u_tab + (size_t)v * US + j * 3;
+  u[0] = u0; u[1] = u1; u[2] = u2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// E-step (cmd_cram_freemux2.cpp:383-456)
+// ------------------------------------------------------------------------------------------------
+// One warp per work item (<= 2048 pairs of one cell), one lane per (cell,SNP) pair.  A kernel
+// instance owns the cluster rows j in [J0, J1) (all k <= j): NA running products per lane, kept as
+// mantissa (register) + exponent (shared memory), one log per accumulator per item.
+//   lk[j][k] = sum_{a,b} gl[a][b] u_j[a] u_k[b] = u_j . (GL u_k)      (:443, k < j)
+//   lk[j][j] = sum_a gl[a][a] u_j[a]                                    (:450)
+// NS > 0: the cluster count is a compile-time constant (J0 = 0, J1 = NS); NS == 0: runtime a.nS.
+struct EArgs {
+  const int32_t* pair_snp;
+  const double* gl_soa;
+  const double* u_tab;
+  const int32_t* item_order;
+  const int64_t* item_pbeg;
+  const int64_t* item_pend;
+  double* item_llk;   // [n_items][npairs]
+  int* counter;
+  int64_t P;
+  int32_t n_items, npairs;
+  int32_t nS, US, SD;  // SD: shared-memory row stride in doubles (16-byte units odd -> conflict-free)
+};
+
+template <int NS, int J0, int J1, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fmx_estep(EArgs a) {
+  constexpr int NR = J1 - J0;
+  constexpr int NA = J1 * (J1 + 1) / 2 - J0 * (J0 + 1) / 2;
+  constexpr int EBASE = J0 * (J0 + 1) / 2;
+  const int nS = NS > 0 ? NS : a.nS;
+  const int US = NS > 0 ? ((NS * 3 + 1) & ~1) : a.US;
+  const int SD = NS > 0 ? ((((US / 2) & 1) == 0) ? US + 2 : US) : a.SD;
+  const int NCH = US / 2;                       // 16-byte pieces per posterior row
+  int lg = 0;
+  while ((1 << lg) < NCH && lg < 5) ++lg;       // lanes per row (power of two, <= 32)
+  const int LPR = 1 << lg, RPI = 32 >> lg;
+  const int PPL = (NCH + LPR - 1) >> lg;        // pieces per lane (1, or 2 when NCH > 32)
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_u = reinterpret_cast<double*>(smem_raw);                         // [2][THREADS][SD]
+  int* s_exp = reinterpret_cast<int*>(s_u + (size_t)2 * THREADS * SD);       // [NA][THREADS]
+  const int tid = threadIdx.x, lane = tid & 31;
+  double* const row0 = s_u + (size_t)tid * SD;
+  const size_t buf_d = (size_t)THREADS * SD;
+
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(a.counter, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= a.n_items) break;
+    const int item = a.item_order[w];
+    const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
+    const int niter = (int)((pe - pb + 31) >> 5);
+
+    double acc[NA];
+#pragma unroll
+    for (int e = 0; e < NA; ++e) { acc[e] = 1.0; s_exp[e * THREADS + tid] = 0; }
+
+    // software pipeline: SNP id two iterations ahead; posterior row (cp.async) and the pair's 9 GLs
+    // (registers) one iteration ahead
+    int32_t snpA = 0; bool okA = false;
+    double glB[9]; bool okB = false;
+    auto loadA = [&](int it) {
+      const int64_t p = pb + ((int64_t)it << 5) + lane;
+      okA = (it < niter) && (p < pe);
+      if (okA) snpA = a.pair_snp[p];
+    };
+    auto issueB = [&](int it, int buf) {  // consumes stage A (iteration `it`)
+      okB = okA;
+      if (okA) {
+        const int64_t p = pb + ((int64_t)it << 5) + lane;
+#pragma unroll
+        for (int g = 0; g < 9; ++g) glB[g] = a.gl_soa[(size_t)g * a.P + p];
+      }
+      const unsigned okmask = __ballot_sync(0xffffffffu, okA);
+      double* dst_base = s_u + (size_t)buf * buf_d + (size_t)(tid & ~31) * SD;
+      for (int i = 0; i < LPR; ++i) {
+        const int row = i * RPI + (lane >> lg), piece = lane & (LPR - 1);
+        const int snp_r = __shfl_sync(0xffffffffu, snpA, row);
+        if ((okmask >> row) & 1u) {
+          for (int pp = 0; pp < PPL; ++pp) {
+            const int pc = piece + (pp << lg);
+            if (pc < NCH)
+              __pipeline_memcpy_async(reinterpret_cast<char*>(dst_base + (size_t)row * SD) + pc * 16,
+                                      reinterpret_cast<const char*>(a.u_tab + (size_t)snp_r * US) + pc * 16, 16);
+          }
+        }
+      }
+      __pipeline_commit();
+    };
+    loadA(0);
+    issueB(0, 0);
+    loadA(1);
+
+    for (int it = 0; it < niter; ++it) {
+      const int buf = it & 1;
+      const bool ok = okB;
+      double gl[9];
+#pragma unroll
+      for (int g = 0; g < 9; ++g) gl[g] = glB[g];
+      __syncwarp();  // all lanes are done with buffer buf^1 before it is refilled
+      issueB(it + 1, buf ^ 1);
+      loadA(it + 2);
+      __pipeline_wait_prior(1);
+      __syncwarp();
+
+      if (ok) {
+        const double* row = row0 + (size_t)buf * buf_d;
+        double uj[NR][3];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (J0 + r < nS) { uj[r][0] = row[(J0 + r) * 3]; uj[r][1] = row[(J0 + r) * 3 + 1]; uj[r][2] = row[(J0 + r) * 3 + 2]; }
+          else { uj[r][0] = uj[r][1] = uj[r][2] = 0.0; }
+        }
+#pragma unroll
+        for (int k = 0; k < J1; ++k) {
+          if (k < nS) {
+            double k0, k1, k2;
+            if (k >= J0) { k0 = uj[k - J0 < 0 ? 0 : k - J0][0]; k1 = uj[k - J0 < 0 ? 0 : k - J0][1]; k2 = uj[k - J0 < 0 ? 0 : k - J0][2]; }
+            else { k0 = row[k * 3]; k1 = row[k * 3 + 1]; k2 = row[k * 3 + 2]; }
+            const double v0 = gl[0] * k0 + gl[1] * k1 + gl[2] * k2;
+            const double v1 = gl[3] * k0 + gl[4] * k1 + gl[5] * k2;
+            const double v2 = gl[6] * k0 + gl[7] * k1 + gl[8] * k2;
+#pragma unroll
+            for (int j = (k + 1 > J0 ? k + 1 : J0); j < J1; ++j)
+              if (j < nS) acc[j * (j + 1) / 2 + k - EBASE] *= (uj[j - J0][0] * v0 + uj[j - J0][1] * v1 + uj[j - J0][2] * v2);
+            if (k >= J0) acc[k * (k + 1) / 2 + k - EBASE] *= (gl[0] * k0 + gl[4] * k1 + gl[8] * k2);
+          }
+        }
+      }
+      if ((it & 31) == 31) {  // every factor is >= ~1e-6 (clamped GLs), so 32 of them stay far above underflow
+#pragma unroll
+        for (int e = 0; e < NA; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * THREADS + tid] += ex; }
+      }
+    }
+    __pipeline_wait_prior(0);
+    __syncwarp();
+
+    // ---- item epilogue: product across the warp, one log per accumulator, taken by lane e % 32 ----
+    // (rolled through this lane's now idle posterior rows: 2*SD >= NA doubles, checked on the host)
+#pragma unroll
+    for (int e = 0; e < NA; ++e) { if (e < SD) row0[e] = acc[e]; else row0[buf_d + (e - SD)] = acc[e]; }
+    double keep_m0 = 1.0, keep_m1 = 1.0;
+    int keep_e0 = 0, keep_e1 = 0;
+#pragma unroll 1
+    for (int e = 0; e < NA; ++e) {
+      double m = (e < SD) ? row0[e] : row0[buf_d + (e - SD)];
+      int ex = s_exp[e * THREADS + tid];
+      pscl_renorm(m, ex);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m *= __shfl_xor_sync(0xffffffffu, m, o);
+        ex += __shfl_xor_sync(0xffffffffu, ex, o);
+      }
+      if ((e & 31) == lane) {
+        if (e < 32) { keep_m0 = m; keep_e0 = ex; } else { keep_m1 = m; keep_e1 = ex; }
+      }
+    }
+    double* out = a.item_llk + (size_t)item * a.npairs;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int e = lane + 32 * half;
+      if (e < NA && e + EBASE < a.npairs) out[e + EBASE] = pscl_prod_log(half ? keep_m1 : keep_m0, half ? keep_e1 : keep_e0);
+    }
+    __syncwarp();
+  }
+}
+
+// llk[c][pair] = sum over the cell's items, in item order (a cell without pairs keeps 0, :385 init)
+__global__ void k_fmx_llk_reduce(const int32_t* __restrict__ cell_item_ptr, const double* __restrict__ item_llk,
+                                 int32_t C, int32_t npairs, double* __restrict__ llk) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)C * npairs) return;
+  const int c = (int)(t / npairs), q = (int)(t - (int64_t)c * npairs);
+  double x = 0.0;
+  for (int it = cell_item_ptr[c]; it < cell_item_ptr[c + 1]; ++it) x += item_llk[(size_t)it * npairs + q];
+  llk[t] = x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-cell epilogue + classify (cmd_cram_freemux2.cpp:458-584; old mode cmd_cram_freemuxlet.cpp:524-648)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fmx_log_add(double la, double lb) {  // sc_drop_seq.cpp:5-8
+  return (la > lb) ? la + log(1.0 + exp(lb - la)) : lb + log(1.0 + exp(la - lb));
+}
+
+__global__ void __launch_bounds__(128) k_fmx_classify(const double* __restrict__ llk, int32_t C, int32_t nS,
+                                                      double doublet_prior, int mode_old, pscl_fmx_cell* __restrict__ cells,
+                                                      int32_t* __restrict__ clust, int32_t* __restrict__ member,
+                                                      int32_t* __restrict__ counters) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int npairs = nS * (nS + 1) / 2;
+  const double* llks = llk + (size_t)c * npairs;
+  const double lsp = log((1.0 - doublet_prior) / nS);            // :379
+  const double ldp = log(doublet_prior / nS / (nS - 1) * 2.0);   // :380
+  int sBest = -1, sNext = -1, dBest1 = -1, dBest2 = -1, dNext1 = -1, dNext2 = -1;
+  double sngBestLLK = -1e300, sngNextLLK = -1e300, dblBestLLK = -1e300, dblNextLLK = -1e300;
+  double sumLLK = -1e300, sngLLK = -1e300;
+  for (int j = 0; j < nS; ++j) {  // :468-497, same scan order
+    for (int k = 0; k < j; ++k) {
+      const double x = llks[j * (j + 1) / 2 + k];
+      if (x > dblBestLLK) { dNext1 = dBest1; dNext2 = dBest2; dblNextLLK = dblBestLLK; dBest1 = j; dBest2 = k; dblBestLLK = x; }
+      else if (x > dblNextLLK) { dNext1 = j; dNext2 = k; dblNextLLK = x; }
+      sumLLK = fmx_log_add(sumLLK, x + ldp);
+    }
+    const double x = llks[j * (j + 1) / 2 + j];
+    if (x > sngBestLLK) { sNext = sBest; sngNextLLK = sngBestLLK; sBest = j; sngBestLLK = x; }
+    else if (x > sngNextLLK) { sNext = j; sngNextLLK = x; }
+    sumLLK = fmx_log_add(sumLLK, x + lsp);
+    sngLLK = fmx_log_add(sngLLK, x + lsp);
+  }
+  pscl_fmx_cell r = cells[c];
+  const int prev_type = r.type;
+  r.sng_best = sBest; r.sng_best_llk = sngBestLLK; r.sng_next = sNext; r.sng_next_llk = sngNextLLK;
+  r.dbl_best_j = dBest1; r.dbl_best_k = dBest2; r.dbl_best_llk = dblBestLLK;
+  r.dbl_next_j = dNext1; r.dbl_next_k = dNext2; r.dbl_next_llk = dblNextLLK;
+  r.sng_pp = exp(sngLLK - sumLLK);            // :510
+  r.sng_only_pp = exp(sngBestLLK + lsp - sngLLK);  // :511
+  r.sum_llk = sumLLK;
+  int cl = mode_old ? r.clust : -1;  // :520 resets clusts; freemuxlet-old never touches it
+  bool changed;
+  if (dblBestLLK > sngBestLLK + 2) {  // :521-543
+    changed = prev_type != 1;
+    r.type = 1;
+    r.best_pp = dblBestLLK + ldp - sumLLK;  // kept as a log (:526)
+    r.best_j = dBest1; r.best_k = dBest2; r.best_llk = dblBestLLK;
+    if (dblNextLLK > sngBestLLK + 2) { r.next_j = dNext1; r.next_k = dNext2; r.next_llk = dblNextLLK; }
+    else { r.next_j = r.next_k = sBest; r.next_llk = sngBestLLK; }
+  } else if (sngBestLLK > sngNextLLK + 2) {  // :544-565
+    changed = (prev_type != 0) || (r.best_j != sBest) || (r.best_k != sBest);
+    r.type = 0;
+    atomicAdd(&counters[1], 1);
+    r.best_pp = sngBestLLK + lsp - sumLLK;
+    r.best_j = r.best_k = sBest; r.best_llk = sngBestLLK;
+    if (!mode_old) cl = sBest;  // :553
+    if (dblBestLLK > sngNextLLK + 2) { r.next_j = dBest1; r.next_k = dBest2; r.next_llk = dblBestLLK; }
+    else { r.next_j = r.next_k = sNext; r.next_llk = sngNextLLK; }
+  } else {  // :566-584
+    changed = prev_type != 2;
+    r.type = 2;
+    atomicAdd(&counters[2], 1);
+    r.best_pp = sngBestLLK + lsp - sumLLK;
+    r.best_j = r.best_k = sBest; r.best_llk = sngBestLLK;
+    if (dblBestLLK > sngNextLLK + 2) { r.next_j = dBest1; r.next_k = dBest2; r.next_llk = dblNextLLK; /* sic :578 */ }
+    else { r.next_j = r.next_k = sNext; r.next_llk = sngNextLLK; }
+  }
+  if (changed) atomicAdd(&counters[0], 1);
+  r.clust = cl;
+  cells[c] = r;
+  clust[c] = cl;
+  member[c] = (r.type == 0 && r.best_j == r.best_k) ? r.best_j : -1;  // who the M-step merges (:592-594)
+}
+
+// ------------------------------------------------------------------------------------------------
+// host API
+// ------------------------------------------------------------------------------------------------
+#define FMX_GRID(n, b) (unsigned)(((n) + (b)-1) / (b))
+
+static int fmx_build_csc(pscl_ctx* ctx, pscl_fmx_state* s) {
+  const pscl_plp* plp = s->plp;
+  const int64_t P = s->P;
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->snp_ptr, sizeof(int64_t) * ((size_t)s->V + 1)));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->snp_pair, sizeof(uint32_t) * (size_t)(P ? P : 1)));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->snp_cell, sizeof(int32_t) * (size_t)(P ? P : 1)));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->csc_pos, sizeof(uint32_t) * (size_t)(P ? P : 1)));
+  if (P == 0) {
+    k_fmx_fill_i64<<<FMX_GRID(s->V + 1, 256), 256, 0, ctx->stream>>>(s->snp_ptr, (int64_t)s->V + 1, 0);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+    return PSCL_OK;
+  }
+  int32_t* key_out = nullptr;
+  uint32_t* val_in = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  PSCL_CUDA(ctx, cudaMalloc((void**)&key_out, sizeof(int32_t) * (size_t)P));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&val_in, sizeof(uint32_t) * (size_t)P));
+  k_fmx_iota<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(val_in, P);
+  ctx->launches++;
+  int end_bit = 1;
+  while (end_bit < 31 && ((int64_t)1 << end_bit) < (int64_t)s->V) ++end_bit;
+  // stable LSD radix sort: equal SNP ids keep their cell-major order = ascending cell id
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int)P, 0, end_bit, ctx->stream);
+  PSCL_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int)P, 0, end_bit, ctx->stream);
+  ctx->launches += 4;
+  if (e == cudaSuccess) {
+    k_fmx_csc_fill<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(key_out, s->snp_pair, plp->cell_ptr, s->C, s->V, P, s->snp_ptr, s->snp_cell, s->csc_pos);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(key_out); cudaFree(val_in); cudaFree(tmp);
+  if (e != cudaSuccess) return pscl_fail(ctx, PSCL_ECUDA, "SNP-major view build failed: %s", cudaGetErrorString(e));
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp* plp, const pscl_fmx_opts* o) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!plp || !o) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_init: NULL argument");
+  if (o->n_clusters < 2 || o->n_clusters > PSCL_FMX_MAX_CLUSTERS)
+    return pscl_fail(ctx, PSCL_EINVAL, "n_clusters must be in [2,%d] (the reference divides by nSamples-1, cmd_cram_freemux2.cpp:380)", PSCL_FMX_MAX_CLUSTERS);
+  if (!plp->snp_af) return pscl_fail(ctx, PSCL_EINVAL, "freemuxlet needs the AF column of .var.gz (pscl_pileup.snp_af)");
+  if (!(o->doublet_prior > 0.0 && o->doublet_prior < 1.0)) return pscl_fail(ctx, PSCL_EINVAL, "doublet_prior must be in (0,1)");
+  if (!(o->geno_error >= 0.0 && o->geno_error <= 1.0)) return pscl_fail(ctx, PSCL_EINVAL, "geno_error must be in [0,1]");
+  if (o->max_iter < 0) return pscl_fail(ctx, PSCL_EINVAL, "max_iter must be >= 0");
+  PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
+  fmx_state_free(ctx);
+  pscl_fmx_state* s = new pscl_fmx_state();
+  ctx->fmx = s;
+  s->plp = plp; s->o = *o;
+  s->nS = o->n_clusters; s->npairs = s->nS * (s->nS + 1) / 2;
+  s->US = (s->nS * 3 + 1) & ~1;
+  s->SD = (((s->US / 2) & 1) == 0) ? s->US + 2 : s->US;
+  s->C = plp->C; s->V = plp->V; s->P = plp->P;
+  const size_t P1 = (size_t)(s->P ? s->P : 1), VS = (size_t)(s->V ? s->V : 1) * s->nS, C1 = (size_t)(s->C ? s->C : 1);
+  const size_t NI = (size_t)(plp->n_items ? plp->n_items : 1);
+  int rc = fmx_build_csc(ctx, s);
+  if (rc != PSCL_OK) return rc;
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->gl_soa, sizeof(double) * 9 * P1));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->gl_csc, sizeof(double) * 9 * P1));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->clust_diag, sizeof(double) * 3 * VS));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->u_tab, sizeof(double) * (size_t)(s->V ? s->V : 1) * s->US));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->clust_gl, sizeof(double) * 9 * VS));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->clust_cnt, sizeof(int32_t) * 3 * VS));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->present, VS));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->cells, sizeof(pscl_fmx_cell) * C1));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->member, sizeof(int32_t) * C1));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->item_s1, sizeof(double) * 2 * NI));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->item_nrd, sizeof(int32_t) * NI));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->item_llk, sizeof(double) * NI * s->npairs));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->counters, sizeof(int32_t) * 4));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->order, sizeof(int32_t) * C1));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->work_counter, 64));
+  PSCL_CUDA(ctx, cudaMemsetAsync(s->u_tab, 0, sizeof(double) * (size_t)(s->V ? s->V : 1) * s->US, ctx->stream));
+  return PSCL_OK;
+}
+
+#define FMX_STATE(ctx, s)                                                        \
+  if (!ctx) return PSCL_EINVAL;                                                  \
+  pscl_fmx_state* s = ctx->fmx;                                                  \
+  if (!s) return pscl_fail(ctx, PSCL_ESTATE, "call pscl_fmx_init first");        \
+  PSCL_CUDA(ctx, cudaSetDevice(ctx->device))
+
+extern "C" int pscl_fmx_stage1(pscl_ctx* ctx, double* stage1_dev) {
+  FMX_STATE(ctx, s);
+  if (!stage1_dev) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_stage1: NULL output");
+  const pscl_plp* plp = s->plp;
+  if (plp->n_items > 0) {
+    S1Args a;
+    a.pair_snp = plp->pair_snp; a.pair_rd = plp->pair_rd; a.rd_aq = plp->rd_aq; a.snp_af = plp->snp_af;
+    a.phred_err = ctx->phred_err; a.csc_pos = s->csc_pos; a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend;
+    a.gl_soa = s->gl_soa; a.gl_csc = s->gl_csc; a.item_s1 = s->item_s1; a.item_nrd = s->item_nrd;
+    a.P = s->P; a.n_items = plp->n_items;
+    int grid = std::min((plp->n_items + 7) / 8, ctx->sm_count * 8);
+    k_fmx_stage1<<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+  }
+  if (s->C > 0) {
+    k_fmx_stage1_cells<<<FMX_GRID(s->C, 128), 128, 0, ctx->stream>>>(plp->cell_item_ptr, plp->cell_ptr, s->item_s1, s->item_nrd, s->C, stage1_dev);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+  }
+  cudaFree(s->csc_pos);  // only stage 1 scatters through it
+  s->csc_pos = nullptr;
+  s->stage1_done = true;
+  return PSCL_OK;
+}
+
+// sc_drop_comp_t (sc_drop_seq.h:190-198): score descending, ties by larger id first
+static void fmx_sort_order(const std::vector<double>& score, std::vector<int32_t>& order) {
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+  std::sort(order.begin(), order.end(), [&](int32_t l, int32_t r) {
+    double cmp = score[l] - score[r];
+    if (cmp != 0) return cmp > 0;
+    return l > r;
+  });
+}
+
+extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int32_t* init_clust_dev, int32_t* clust_dev) {
+  FMX_STATE(ctx, s);
+  if (!s->stage1_done) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_seed before pscl_fmx_stage1");
+  if (!stage1_dev || !clust_dev) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_seed: NULL argument");
+  const pscl_plp* plp = s->plp;
+  double* score = nullptr;
+  PSCL_CUDA(ctx, cudaMalloc((void**)&score, sizeof(double) * (size_t)(s->C ? s->C : 1)));
+  if (s->C > 0) {
+    k_fmx_begin<<<FMX_GRID(s->C, 128), 128, 0, ctx->stream>>>(stage1_dev, init_clust_dev, s->C, s->cells, clust_dev, score);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && !init_clust_dev && s->C > 0) {
+    std::vector<double> h_score(s->C);
+    std::vector<int32_t> h_order(s->C);
+    e = cudaMemcpyAsync(h_score.data(), score, sizeof(double) * s->C, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+      fmx_sort_order(h_score, h_order);
+      e = cudaMemcpyAsync(s->order, h_order.data(), sizeof(int32_t) * s->C, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    const size_t VS = (size_t)s->V * s->nS;
+    if (e == cudaSuccess && VS > 0) {
+      k_fmx_fill_f64<<<FMX_GRID(VS * 9, 256), 256, 0, ctx->stream>>>(s->clust_gl, VS * 9, 1.0);
+      ctx->launches++;
+      e = cudaMemsetAsync(s->present, 0, VS, ctx->stream);
+    }
+    if (e == cudaSuccess) {
+      SeedArgs a;
+      a.order = s->order; a.score = score; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa;
+      a.snp_af = plp->snp_af; a.clust_gl = s->clust_gl; a.present = s->present; a.clust = clust_dev; a.cells = s->cells;
+      a.P = s->P; a.C = s->C; a.nS = s->nS; a.frac = s->o.frac_init_clust; a.thres = s->o.singlet_score_thres;
+      k_fmx_seed<<<1, 1024, 0, ctx->stream>>>(a);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h_order is a pageable source
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(score);
+  if (e != cudaSuccess) return pscl_fail(ctx, PSCL_ECUDA, "freemuxlet seeding failed: %s", cudaGetErrorString(e));
+  s->begun = true;
+  s->iters = 0;
+  return PSCL_OK;
+}
+
+static int fmx_mstep_launch(pscl_ctx* ctx, pscl_fmx_state* s, const int32_t* member, int final_) {
+  const int64_t n = (int64_t)s->V * s->nS;
+  if (n == 0) return PSCL_OK;
+  MArgs a;
+  a.snp_ptr = s->snp_ptr; a.snp_cell = s->snp_cell; a.snp_pair = s->snp_pair; a.gl_csc = s->gl_csc; a.member = member;
+  a.pair_rd = s->plp->pair_rd; a.rd_aq = s->plp->rd_aq; a.clust_diag = s->clust_diag; a.clust_gl = s->clust_gl;
+  a.clust_cnt = s->clust_cnt; a.V = s->V; a.nS = s->nS; a.final_ = final_;
+  k_fmx_mstep<<<FMX_GRID(n, 256), 256, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  PSCL_CUDA(ctx, cudaGetLastError());
+  s->final_tab = final_ != 0;
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_mstep(pscl_ctx* ctx, const int32_t* clust_dev) {
+  FMX_STATE(ctx, s);
+  if (!s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_mstep before pscl_fmx_seed");
+  if (clust_dev) PSCL_CUDA(ctx, cudaMemcpyAsync(s->member, clust_dev, sizeof(int32_t) * (size_t)s->C, cudaMemcpyDeviceToDevice, ctx->stream));
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = fmx_mstep_launch(ctx, s, s->member, 0);
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  return rc;
+}
+
+template <int NS, int J0, int J1, int THREADS>
+static int fmx_estep_launch(pscl_ctx* ctx, pscl_fmx_state* s, const EArgs& a) {
+  constexpr int NA = J1 * (J1 + 1) / 2 - J0 * (J0 + 1) / 2;
+  if (2 * s->SD < NA) return pscl_fail(ctx, PSCL_EINVAL, "internal: E-step staging rows too short (SD=%d, NA=%d)", s->SD, NA);
+  const size_t smem = sizeof(double) * 2 * THREADS * (size_t)s->SD + sizeof(int) * (size_t)NA * THREADS;
+  auto kern = k_fmx_estep<NS, J0, J1, THREADS>;
+  PSCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  PSCL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+  if (per_sm < 1) return pscl_fail(ctx, PSCL_EINVAL, "E-step kernel does not fit one SM (smem %zu B)", smem);
+  int grid = ctx->sm_count * per_sm;
+  const int need = (a.n_items + THREADS / 32 - 1) / (THREADS / 32);
+  if (grid > need) grid = need;
+  PSCL_CUDA(ctx, cudaMemsetAsync(s->work_counter, 0, sizeof(int), ctx->stream));
+  kern<<<grid, THREADS, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  PSCL_CUDA(ctx, cudaGetLastError());
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev) {
+  FMX_STATE(ctx, s);
+  if (!s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_estep before pscl_fmx_seed / pscl_fmx_mstep");
+  if (!llk_dev) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_estep: NULL output");
+  const pscl_plp* plp = s->plp;
+  // geno_error is mixed in every iteration by freemux2 (:410), only in the last one by freemuxlet-old (:485)
+  const int apply_err = s->o.mode_old ? (s->o.geno_error > 0 && iter + 1 == s->o.max_iter) : (s->o.geno_error > 0);
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  const int64_t n = (int64_t)s->V * s->nS;
+  if (n > 0) {
+    k_fmx_posterior<<<FMX_GRID(n, 256), 256, 0, ctx->stream>>>(s->clust_diag, plp->snp_af, s->V, s->nS, s->US, s->o.geno_error, apply_err, s->u_tab);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+  }
+  if (plp->n_items > 0) {
+    EArgs a;
+    a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.u_tab = s->u_tab; a.item_order = plp->item_order;
+    a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend; a.item_llk = s->item_llk; a.counter = s->work_counter;
+    a.P = s->P; a.n_items = plp->n_items; a.npairs = s->npairs; a.nS = s->nS; a.US = s->US; a.SD = s->SD;
+    int rc = PSCL_OK;
+    const int nS = s->nS;
+    switch (nS) {
+      case 2: rc = fmx_estep_launch<2, 0, 2, 128>(ctx, s, a); break;
+      case 3: rc = fmx_estep_launch<3, 0, 3, 128>(ctx, s, a); break;
+      case 4: rc = fmx_estep_launch<4, 0, 4, 128>(ctx, s, a); break;
+      case 5: rc = fmx_estep_launch<5, 0, 5, 128>(ctx, s, a); break;
+      case 6: rc = fmx_estep_launch<6, 0, 6, 128>(ctx, s, a); break;
+      case 7: rc = fmx_estep_launch<7, 0, 7, 128>(ctx, s, a); break;
+      case 8: rc = fmx_estep_launch<8, 0, 8, 128>(ctx, s, a); break;
+      default:
+        rc = fmx_estep_launch<0, 0, 8, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 8) rc = fmx_estep_launch<0, 8, 11, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 11) rc = fmx_estep_launch<0, 11, 14, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 14) rc = fmx_estep_launch<0, 14, 16, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 16) rc = fmx_estep_launch<0, 16, 18, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 18) rc = fmx_estep_launch<0, 18, 20, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 20) rc = fmx_estep_launch<0, 20, 22, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 22) rc = fmx_estep_launch<0, 22, 24, 64>(ctx, s, a);
+    }
+    if (rc != PSCL_OK) return rc;
+  }
+  if ((int64_t)s->C * s->npairs > 0) {
+    k_fmx_llk_reduce<<<FMX_GRID((int64_t)s->C * s->npairs, 256), 256, 0, ctx->stream>>>(plp->cell_item_ptr, s->item_llk, s->C, s->npairs, llk_dev);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+  }
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_classify(pscl_ctx* ctx, const double* llk_dev, int32_t* clust_dev, pscl_fmx_result* res) {
+  FMX_STATE(ctx, s);
+  if (!s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_classify before pscl_fmx_seed");
+  if (!llk_dev || !clust_dev) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_classify: NULL argument");
+  PSCL_CUDA(ctx, cudaMemsetAsync(s->counters, 0, sizeof(int32_t) * 4, ctx->stream));
+  if (s->C > 0) {
+    k_fmx_classify<<<FMX_GRID(s->C, 128), 128, 0, ctx->stream>>>(llk_dev, s->C, s->nS, s->o.doublet_prior, s->o.mode_old, s->cells, clust_dev, s->member, s->counters);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+  }
+  int32_t h[4] = {0, 0, 0, 0};
+  PSCL_CUDA(ctx, cudaMemcpyAsync(h, s->counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  s->iters++;
+  s->last.n_iter = s->iters; s->last.n_changed = h[0]; s->last.n_singlet = h[1]; s->last.n_ambiguous = h[2];
+  s->last.n_doublet = s->C - h[1] - h[2];
+  if (res) *res = s->last;
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt) {
+  FMX_STATE(ctx, s);
+  if (!s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_fetch before pscl_fmx_seed");
+  if (out && s->C > 0)
+    PSCL_CUDA(ctx, cudaMemcpyAsync(out, s->cells, sizeof(pscl_fmx_cell) * (size_t)s->C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (clust_gl || clust_cnt) {
+    // full 9-GL pileups and read counts of the current membership (what clustPileup holds when the
+    // reference writes .clust1.vcf.gz, cmd_cram_freemux2.cpp:608-658)
+    int rc = fmx_mstep_launch(ctx, s, s->member, 1);
+    if (rc != PSCL_OK) return rc;
+    const size_t VS = (size_t)s->V * s->nS;
+    if (clust_gl && VS) PSCL_CUDA(ctx, cudaMemcpyAsync(clust_gl, s->clust_gl, sizeof(double) * 9 * VS, cudaMemcpyDeviceToHost, ctx->stream));
+    if (clust_cnt && VS) PSCL_CUDA(ctx, cudaMemcpyAsync(clust_cnt, s->clust_cnt, sizeof(int32_t) * 3 * VS, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float* ms) {
+  FMX_STATE(ctx, s);
+  (void)s;
+  PSCL_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  float t = 0.f;
+  PSCL_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+  if (ms) *ms = t;
+  return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts, const int32_t* init_clust,
+                            pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, pscl_fmx_result* res) {
+  if (!ctx) return PSCL_EINVAL;
+  if (!host || !opts || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_run: NULL argument");
+  pscl_plp* plp = nullptr;
+  int rc = pscl_plp_upload(ctx, host, &plp);
+  if (rc != PSCL_OK) return rc;
+  int32_t* d_init = nullptr;
+  auto body = [&]() -> int {
+    int r = pscl_fmx_init(ctx, plp, opts);
+    if (r != PSCL_OK) return r;
+    pscl_fmx_state* s = ctx->fmx;
+    const size_t C1 = (size_t)(s->C ? s->C : 1);
+    PSCL_CUDA(ctx, cudaMalloc((void**)&s->own_stage1, sizeof(double) * 4 * C1));
+    PSCL_CUDA(ctx, cudaMalloc((void**)&s->own_llk, sizeof(double) * C1 * s->npairs));
+    PSCL_CUDA(ctx, cudaMalloc((void**)&s->own_clust, sizeof(int32_t) * C1));
+    if (init_clust) {
+      for (int32_t c = 0; c < s->C; ++c)
+        if (init_clust[c] >= s->nS) return pscl_fail(ctx, PSCL_EINVAL, "init_clust[%d] = %d is not below n_clusters = %d", c, init_clust[c], s->nS);
+      PSCL_CUDA(ctx, cudaMalloc((void**)&d_init, sizeof(int32_t) * C1));
+      PSCL_CUDA(ctx, cudaMemcpyAsync(d_init, init_clust, sizeof(int32_t) * (size_t)s->C, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((r = pscl_fmx_stage1(ctx, s->own_stage1)) != PSCL_OK) return r;
+    if ((r = pscl_fmx_seed(ctx, s->own_stage1, d_init, s->own_clust)) != PSCL_OK) return r;
+    if ((r = pscl_fmx_mstep(ctx, s->own_clust)) != PSCL_OK) return r;  // :277-288
+    pscl_fmx_result rr;
+    memset(&rr, 0, sizeof(rr));
+    for (int iter = 0; iter < s->o.max_iter; ++iter) {
+      if ((r = pscl_fmx_estep(ctx, iter, s->own_llk)) != PSCL_OK) return r;
+      if ((r = pscl_fmx_classify(ctx, s->own_llk, s->own_clust, &rr)) != PSCL_OK) return r;
+      if ((r = pscl_fmx_mstep(ctx, nullptr)) != PSCL_OK) return r;
+      if (!s->o.mode_old && s->o.early_stop && rr.n_changed == 0) break;  // :601-604
+    }
+    if (res) *res = rr;
+    return pscl_fmx_fetch(ctx, out, clust_gl, clust_cnt);
+  };
+  rc = body();
+  std::string err = ctx->err;
+  cudaFree(d_init);
+  fmx_state_free(ctx);
+  pscl_plp_free(ctx, plp);
+  ctx->err = err;
+  return rc;
+}
