@@ -1,0 +1,130 @@
+"""Golden vectors written by the reference itself (oracle/_ref/popscle_ref = the reference's own
+demuxlet / freemuxlet translation units, see tests/golden/make_golden.py): the same argv is replayed
+through popscle_b200.cli with the CPU oracle (must reproduce the files byte for byte) and with the
+CUDA library (ids exact, LLK columns within 1e-4 relative — BASELINE.json's tolerance)."""
+import gzip
+import json
+import os
+import shutil
+
+import pytest
+
+from popscle_b200 import cli
+from tests.engines import OracleEngine
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(d for d in os.listdir(GOLD) if os.path.isdir(os.path.join(GOLD, d)))
+LLK_RTOL = 1e-4       # north_star tolerance on LLK columns
+PRINT_ATOL = 0.0101   # two %.2lf roundings
+
+
+def _replay(case, tmp_path, engine):
+    src = os.path.join(GOLD, case)
+    work = tmp_path / case
+    shutil.copytree(src, work)
+    argv = json.load(open(work / "cmd.json"))["argv"]
+    argv = [("out" if a == "ref" and argv[i - 1] == "--out" else a) for i, a in enumerate(argv)]
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        rc = cli.COMMANDS[argv[0]](argv[1:], engine=engine)
+    finally:
+        os.chdir(cwd)
+    assert rc == 0
+    pairs = []
+    for fn in sorted(os.listdir(work)):
+        if fn.startswith("ref."):
+            ours = work / ("out." + fn[4:])
+            if not ours.exists():
+                ours = work / ("out." + fn[4:] + ".gz")
+            assert ours.exists(), f"{case}: output {fn[4:]} was not written"
+            txt = gzip.open(ours, "rt").read() if str(ours).endswith(".gz") else open(ours).read()
+            txt = "".join(l for l in txt.splitlines(True) if not l.startswith("##fileDate="))
+            pairs.append((fn, open(work / fn).read(), txt))
+    assert pairs
+    return pairs
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_reproduces_reference_files(case, tmp_path, built):
+    for fn, ref, ours in _replay(case, tmp_path, OracleEngine()):
+        if ref != ours:
+            a, b = ref.split("\n"), ours.split("\n")
+            bad = [i for i, (x, y) in enumerate(zip(a, b)) if x != y]
+            raise AssertionError(f"{case}/{fn}: {len(bad)} of {len(a)} lines differ (lengths {len(a)}/{len(b)}); first:\nREF {a[bad[0]][:300]}\nOUR {b[bad[0]][:300]}")
+
+
+def _num(s):
+    try:
+        return float(s)
+    except ValueError:
+        return None
+
+
+def _close(a, b, rtol, atol):
+    if a == b or (a != a and b != b):
+        return True
+    return abs(a - b) <= rtol * max(1.0, abs(b)) + atol
+
+
+def _cmp_guess(x, y):
+    """'j,k,alpha' (demuxlet) or 'j,k' (freemuxlet): unordered pair at alpha 0.5 / for cluster pairs"""
+    fx, fy = x.split(","), y.split(",")
+    if len(fx) != len(fy):
+        return False
+    if len(fx) == 3:
+        if fx[2] != fy[2]:
+            return False
+        return (fx[:2] == fy[:2]) or (fx[2] == "0.50" and sorted(fx[:2]) == sorted(fy[:2]))
+    return fx == fy
+
+
+def _compare_table(ref, ours, what):
+    a, b = ref.rstrip("\n").split("\n"), ours.rstrip("\n").split("\n")
+    assert len(a) == len(b), f"{what}: {len(a)} vs {len(b)} lines"
+    hdr = a[0].split("\t")
+    assert a[0] == b[0]
+    for ln, (x, y) in enumerate(zip(a[1:], b[1:]), 2):
+        fx, fy = x.split("\t"), y.split("\t")
+        assert len(fx) == len(fy), f"{what}:{ln}"
+        for h, u, v in zip(hdr, fx, fy):
+            if h.endswith(".GUESS") and "," in u:
+                assert _cmp_guess(u, v), f"{what}:{ln} {h}: {u} vs {v}"
+                continue
+            nu, nv = _num(u), _num(v)
+            if nu is None or nv is None or h in ("INT_ID", "NUM.SNPS", "NUM.READS", "NSNPs", "NREADs", "SNG.BEST.GUESS", "SNG.NEXT.GUESS"):
+                assert u == v, f"{what}:{ln} {h}: {u} vs {v}"
+            elif "POSTERIOR" in h:
+                # %.2lg / %.5lf of probabilities (or of a log, cmd_cram_demuxlet.cpp:949): 2 significant digits
+                assert _close(nu, nv, 0.06, 1e-5), f"{what}:{ln} {h}: {u} vs {v}"
+            else:
+                assert _close(nu, nv, LLK_RTOL, PRINT_ATOL), f"{what}:{ln} {h}: {u} vs {v}"
+
+
+def _compare_vcf(ref, ours, what):
+    a, b = ref.rstrip("\n").split("\n"), ours.rstrip("\n").split("\n")
+    assert len(a) == len(b), f"{what}: {len(a)} vs {len(b)} lines"
+    for ln, (x, y) in enumerate(zip(a, b), 1):
+        if x == y:
+            continue
+        assert not x.startswith("#"), f"{what}:{ln} header differs"
+        fx, fy = x.split("\t"), y.split("\t")
+        assert fx[:9] == fy[:9], f"{what}:{ln} site columns differ"
+        for u, v in zip(fx[9:], fy[9:]):
+            pu, pv = u.split(":"), v.split(":")
+            assert pu[0] == pv[0] and pu[2] == pv[2] and pu[3] == pv[3], f"{what}:{ln} GT/DP/AD: {u} vs {v}"
+            assert abs(int(pu[1]) - int(pv[1])) <= 1, f"{what}:{ln} GQ: {u} vs {v}"   # int() truncation of -10 log10
+            for s, t in zip(pu[4].split(","), pv[4].split(",")):
+                assert abs(int(s) - int(t)) <= 1, f"{what}:{ln} PL: {u} vs {v}"
+            for s, t in zip(pu[5].split(","), pv[5].split(",")):
+                assert _close(float(s), float(t), 1e-2, 1e-12), f"{what}:{ln} GP: {u} vs {v}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_matches_reference_files(case, tmp_path, ctx):
+    for fn, ref, ours in _replay(case, tmp_path, ctx):
+        if fn.endswith(".vcf"):
+            _compare_vcf(ref, ours, f"{case}/{fn}")
+        else:
+            _compare_table(ref, ours, f"{case}/{fn}")
