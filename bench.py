@@ -69,6 +69,48 @@ def algorithmic_bytes_fmx_iter(plp, nS):
     return (72 + 4 + 24 * nS) * plp.n_pairs + 8 * plp.n_cells * (nS * (nS + 1) // 2)
 
 
+class NvmlSampler:
+    """SM clock and clock-event reasons polled through NVML every few ms DURING the timed region (the timed
+    region of this benchmark lasts milliseconds: `nvidia-smi -lms` would return one or two samples)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index=0):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        self.sm, self.bits, self.stop_flag = [], 0, False
+        self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+
+    def start(self):
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(1.0)
+        reasons = sorted(v for k, v in self.REASONS.items() if self.bits & k)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(self.max),
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
+
+
+def make_sampler(gpu_index=0):
+    try:
+        return NvmlSampler(gpu_index)
+    except Exception:
+        return ClockSampler(gpu_index)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -137,57 +179,116 @@ def ncu_traffic(kernel_key):
         return None
 
 
-def cpu_baseline_demux(s, gp, target_s, threads):
-    """Times the oracle (CPU restatement of cmd_cram_demuxlet.cpp:636-991, one log() per term like
-    the reference) on a bounded sample of the SAME workload: the first M cells."""
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "popscle_ref")
+
+
+def write_reference_sample(s, nv, n_cells, workdir):
+    """dsc-pileup files + GT VCF of the first n_cells cells of the workload, for the reference binary."""
+    from popscle_b200 import plpio
+    os.makedirs(workdir, exist_ok=True)
+    sub = s.plp.slice_cells(0, n_cells)
+    sites = plpio.default_sites(sub.n_snps, s.af, seed=1)
+    plpio.write_plp(os.path.join(workdir, "p"), sub, sites)
+    plpio.write_vcf(os.path.join(workdir, "g.vcf.gz"), sites, [f"S{j}" for j in range(nv)], geno=s.geno)
+    return sub
+
+
+def time_reference_binary(workdir):
+    """Runs the reference's own `demuxlet` (oracle/_ref/popscle_ref: unmodified cmd_cram_demuxlet.cpp) once and
+    returns the wall time of its likelihood stage only — from its "Starting to identify best matching individual
+    IDs" notice (cmd_cram_demuxlet.cpp:588, after load_from_plp) to process exit — plus the load time."""
+    t0 = time.perf_counter()
+    p = subprocess.Popen([REF_BIN, "demuxlet", "--plp", "p", "--vcf", "g.vcf.gz", "--field", "GT", "--out", "ref"], cwd=workdir,
+                         stderr=subprocess.PIPE, stdout=subprocess.DEVNULL, text=True, bufsize=1)
+    t_start = None
+    for ln in p.stderr:
+        if t_start is None and "Starting to identify best matching" in ln:
+            t_start = time.perf_counter()
+    p.wait()
+    t1 = time.perf_counter()
+    if p.returncode != 0 or t_start is None:
+        raise RuntimeError("reference binary failed")
+    return t1 - t_start, t_start - t0
+
+
+def cpu_baseline_demux(s, gp, nv, target_s, threads):
+    """CPU baseline of the ours arm: the reference's own demuxlet (single-threaded, as the reference is) on a bounded
+    sample of the same workload; the OpenMP oracle port on all cores is reported beside it."""
     import oracle_py as orc
     plp = s.plp
+    out = {}
     m0 = min(plp.n_cells, max(threads * 4, 32))
     t0 = time.perf_counter()
     orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m0, n_threads=threads)
-    dt = time.perf_counter() - t0
-    rate = max(m0 / max(dt, 1e-6), 1e-9)  # cells/s
-    m = int(min(plp.n_cells, max(m0, rate * target_s)))
+    rate = m0 / max(time.perf_counter() - t0, 1e-6)
+    m = int(min(plp.n_cells, max(m0, rate * min(target_s, 5.0))))
     t0 = time.perf_counter()
     orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
     dt = time.perf_counter() - t0
     reads = int(plp.pair_read_ptr[plp.cell_ptr[m]])
-    return reads / dt, m, reads, dt
+    port = {"value": reads / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {m} of {plp.n_cells} cells ({reads} base-calls) in {dt:.1f}s; OpenMP oracle port of cmd_cram_demuxlet.cpp:636-991"}
+    if not os.path.exists(REF_BIN):
+        return port
+    import tempfile
+    with tempfile.TemporaryDirectory() as wd:
+        n = int(min(plp.n_cells, max(50, 0.45 * rate / max(threads, 1) * target_s)))  # one thread, std::map walks: ~0.45x the port's per-core rate
+        sub = write_reference_sample(s, nv, n, wd)
+        llk_s, load_s = time_reference_binary(wd)
+    return {"value": sub.n_reads / llk_s, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"first {n} of {plp.n_cells} cells ({sub.n_reads} base-calls): likelihood stage {llk_s:.1f}s (+{load_s:.1f}s file loading, not counted) "
+                      "of oracle/_ref/popscle_ref demuxlet = the reference's own cmd_cram_demuxlet.cpp, single-threaded as the reference is",
+            "port_all_cores": port}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference binary
-    cannot be linked here or on the GPU box (htslib absent), so this arm times the
-    oracle port of cmd_cram_demuxlet.cpp:636-991 on all host threads, each step a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path — oracle/_ref/popscle_ref (the reference's
+    unmodified translation units, oracle/build_ref.sh) when it is there, else the oracle port.  The reference is
+    single-threaded, so one host core is all it can use.  Each step = one run of its likelihood
+    stage on a bounded sample (the first cells of configs[1]); file loading is not counted."""
     if rank != 0:
         return
     cfg, s, gp = make_workload(args, 0)
-    threads = os.cpu_count() or 1
-    import oracle_py as orc
     plp = s.plp
-    # size one step to ~ cpu_seconds / (steps + warmup)
-    per_step = max(1.0, args.cpu_seconds * 4 / max(1, args.steps + args.warmup))
-    m0 = min(plp.n_cells, max(threads * 4, 32))
-    t0 = time.perf_counter(); orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m0, n_threads=threads); dt = time.perf_counter() - t0
-    m = int(min(plp.n_cells, max(m0, m0 / dt * per_step)))
-    reads = int(plp.pair_read_ptr[plp.cell_ptr[m]])
-    for _ in range(args.warmup):
-        orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
-    dt = time.perf_counter() - t0
-    v = reads * args.steps / dt
-    sample = f"first {m} of {plp.n_cells} cells ({reads} base-calls) per step"
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    threads = os.cpu_count() or 1
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "demuxlet configs[1]: 10k cells x 8 samples x 100k SNPs, alpha {0,0.5}",
-                       "cells": plp.n_cells, "samples": cfg["nv"], "snps": cfg["V"], "pairs": plp.n_pairs,
-                       "base_calls": plp.n_reads},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "cells": plp.n_cells, "samples": cfg["nv"], "snps": cfg["V"], "pairs": plp.n_pairs, "base_calls": plp.n_reads},
             "gpu_launches": 0}
+    if os.path.exists(REF_BIN):
+        import tempfile
+        total_runs = max(1, args.steps + args.warmup)
+        n = int(min(plp.n_cells, max(40, 150 * 65 // total_runs)))  # ~150 s of likelihood work in total at ~65 cells/s
+        with tempfile.TemporaryDirectory() as wd:
+            sub = write_reference_sample(s, cfg["nv"], n, wd)
+            for _ in range(args.warmup):
+                time_reference_binary(wd)
+            ts = [time_reference_binary(wd)[0] for _ in range(args.steps)]
+        dt = float(sum(ts))
+        v = sub.n_reads * args.steps / dt
+        kind, cores = "reference", 1
+        sample = (f"first {n} of {plp.n_cells} cells ({sub.n_reads} base-calls) per step; likelihood stage of oracle/_ref/popscle_ref "
+                  "demuxlet (the reference's own cmd_cram_demuxlet.cpp), file loading excluded")
+    else:
+        import oracle_py as orc
+        per_step = max(1.0, args.cpu_seconds * 4 / max(1, args.steps + args.warmup))
+        m0 = min(plp.n_cells, max(threads * 4, 32))
+        t0 = time.perf_counter(); orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m0, n_threads=threads); dt = time.perf_counter() - t0
+        m = int(min(plp.n_cells, max(m0, m0 / dt * per_step)))
+        reads = int(plp.pair_read_ptr[plp.cell_ptr[m]])
+        for _ in range(args.warmup):
+            orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.demux(plp, gp, None, ALPHAS, 0.5, 0, m, n_threads=threads)
+        dt = time.perf_counter() - t0
+        v = reads * args.steps / dt
+        kind, cores = "port", threads
+        sample = f"first {m} of {plp.n_cells} cells ({reads} base-calls) per step; OpenMP oracle port (oracle/_ref not built)"
+    line = dict(base, value=v, ms_per_step=1e3 * dt / args.steps,
+                cpu_baseline={"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                e2e={"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     print(json.dumps(line), flush=True)
 
 
@@ -231,7 +332,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         ctx.demux_score(dplp, ALPHAS, 0.5)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = make_sampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count
@@ -306,11 +407,7 @@ def main():
                         "steps": e2e_steps, "api": "pscl_demux_run (pinned host buffers in, per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            v, m, reads, dt = cpu_baseline_demux(s, gp, args.cpu_seconds, threads)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"first {m} of {plp.n_cells} cells ({reads} base-calls) in {dt:.1f}s; "
-                                              "oracle port of cmd_cram_demuxlet.cpp:636-991"}
+            line["cpu_baseline"] = cpu_baseline_demux(s, gp, nv, args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

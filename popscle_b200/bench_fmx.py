@@ -70,7 +70,7 @@ def main(args, rank, local_rank, world):
     for it in range(W):
         em_iter(it)
     barrier()
-    sampler = B.ClockSampler(local_rank)
+    sampler = B.make_sampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count

@@ -1,0 +1,81 @@
+"""The C-ABI library builds without a GPU, exports every symbol include/*.h declares, and refuses
+to run without a device (no CPU fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from popscle_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "popscle_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pscl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported(built):
+    names = _declared()
+    assert len(names) >= 25
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/popscle_b200.h but not exported: {missing}"
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (pscl_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert exported <= set(names), f"exported but not declared in the header: {sorted(exported - set(names))}"
+    assert sorted(capi.EXPORTED_SYMBOLS) == names
+
+
+def test_library_is_sm100a_only(built):
+    out = subprocess.run(["cuobjdump", "--list-elf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "popscle_b200.h"\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    assert subprocess.call([str(exe)]) == 0
+    assert capi.DEMUX_CELL_DTYPE.itemsize == 160 and capi.FMX_CELL_DTYPE.itemsize == 160
+
+
+def test_no_cpu_fallback(built):
+    """Without a GPU pscl_create must fail with PSCL_ENODEV and the Python host must raise."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = capi.load_library()
+    assert lib.pscl_abi_version() == 1
+    h = ctypes.c_void_p()
+    err = ctypes.create_string_buffer(256)
+    rc = lib.pscl_create(0, ctypes.byref(h), err, len(err))
+    assert rc == -2 and not h.value and b"no CPU fallback" in err.value
+    with pytest.raises(capi.PsclError):
+        capi.Context(0)
+    from popscle_b200 import cli
+    with pytest.raises(capi.PsclError):
+        gold = os.path.join(ROOT, "tests", "golden", "demux_gt")
+        cwd = os.getcwd()
+        os.chdir(gold)
+        try:
+            cli.demuxlet(["--plp", "p", "--vcf", "g.vcf.gz", "--field", "GT", "--out", "/tmp/never_written"])
+        finally:
+            os.chdir(cwd)
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "popscle_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".cpp", ".h")):
+                t = open(os.path.join(dp, f)).read()
+                if re.search(r"oracle_py|popscle_oracle|liboracle|oracle/_ref", t):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,216 @@
+"""Host logic on CPU: file round trips, loader semantics, CLI errors, partitioning, and the N>1
+paths over gloo (world_size 2) with the oracle standing in for the device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from popscle_b200 import cli, dist, plpio, synth
+from tests.engines import OracleEngine
+from tests.parity import assert_close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plp_round_trip_and_bq_window(tmp_path):
+    s = synth.make_pileup(C=40, nv=3, V=300, kbar=80, seed=5, cap_bq=40)
+    sites = plpio.default_sites(300, s.af, seed=5)
+    bcs = plpio.write_plp(str(tmp_path / "p"), s.plp, sites)
+    L = plpio.load_plp(str(tmp_path / "p"))  # library defaults minBQ=1 capBQ=60
+    assert L.barcodes == bcs
+    for f in ("cell_ptr", "pair_snp", "pair_read_ptr", "read_allele", "read_qual"):
+        assert np.array_equal(getattr(L.plp, f), getattr(s.plp, f)), f
+    assert_close(L.plp.snp_af, s.af, "af", rtol=1e-12)
+    L2 = plpio.load_plp(str(tmp_path / "p"), min_bq=20, cap_bq=30)  # sc_drop_seq.cpp:361-369
+    keep = s.plp.read_qual >= 20
+    assert L2.plp.n_reads == int(keep.sum())
+    assert L2.plp.read_qual.max() == 30 and L2.plp.read_qual.min() == 20
+    assert L2.plp.n_pairs <= s.plp.n_pairs  # pairs whose reads are all filtered vanish
+
+
+def test_cel_filters_and_header_errors(tmp_path):
+    s = synth.make_pileup(C=30, nv=3, V=200, kbar=60, seed=6, cap_bq=40)
+    sites = plpio.default_sites(200, s.af, seed=6)
+    bcs = plpio.write_plp(str(tmp_path / "p"), s.plp, sites)
+    npair = np.diff(s.plp.cell_ptr)
+    thr = int(np.median(npair))
+    L = plpio.load_plp(str(tmp_path / "p"), min_snp=thr)
+    assert L.barcodes == [b for b, n in zip(bcs, npair) if n >= thr]
+    L = plpio.load_plp(str(tmp_path / "p"), group_list=bcs[5:12])
+    assert L.barcodes == bcs[5:12]
+    import gzip
+    with gzip.open(tmp_path / "bad.cel.gz", "wt") as f:
+        f.write("#DROPLET_ID\tBARCODE\tNUM.READ\tNUM.UMI\tNUM.SNP\n")
+    for ext in ("var.gz", "plp.gz"):
+        os.link(tmp_path / f"p.{ext}", tmp_path / f"bad.{ext}")
+    with pytest.raises(ValueError, match="malformed or outdated"):
+        plpio.load_plp(str(tmp_path / "bad"))
+
+
+def test_cli_usage_errors(tmp_path):
+    with pytest.raises(cli.UsageError, match="Missing required"):
+        cli.demuxlet(["--plp", "x"], engine=OracleEngine())
+    with pytest.raises(cli.UsageError, match="Missing required"):
+        cli.freemuxlet(["--plp", "x", "--out", "y"], engine=OracleEngine())
+    with pytest.raises(cli.UsageError, match="more than once"):
+        cli.demuxlet(["--plp", "x", "--plp", "y"], engine=OracleEngine())
+    with pytest.raises(cli.UsageError, match="Cannot recognize"):
+        cli.freemuxlet(["--nope"], engine=OracleEngine())
+    assert cli.main(["demuxlet", "--sam", "a.bam", "--vcf", "v", "--out", "o"]) == 134
+    assert cli.main(["frobnicate"]) == 2
+
+
+def test_balanced_partitions():
+    s = synth.make_pileup(C=500, nv=3, V=4000, kbar=300, seed=7)
+    for n in (1, 2, 3, 8):
+        r = dist.balanced_cell_ranges(s.plp.cell_ptr, n)
+        assert r[0][0] == 0 and r[-1][1] == 500 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        pairs = [int(s.plp.cell_ptr[b] - s.plp.cell_ptr[a]) for a, b in r]
+        assert max(pairs) - min(pairs) <= 2 * int(np.diff(s.plp.cell_ptr).max())
+        v = dist.balanced_snp_ranges(s.plp.pair_snp, 4000, n)
+        assert v[0][0] == 0 and v[-1][1] == 4000 and all(a[1] == b[0] for a, b in zip(v, v[1:]))
+        cnt = np.bincount(s.plp.pair_snp, minlength=4000)
+        ps = [int(cnt[a:b].sum()) for a, b in v]
+        assert sum(ps) == s.plp.n_pairs and max(ps) - min(ps) <= 2 * int(cnt.max())
+    tiny = dist.balanced_cell_ranges(np.array([0, 5], dtype=np.int64), 4)  # more ranks than cells
+    assert sum(b - a for a, b in tiny) == 1
+
+
+def test_slices_are_consistent():
+    s = synth.make_pileup(C=60, nv=3, V=500, kbar=100, seed=8)
+    parts = [s.plp.slice_cells(a, b) for a, b in dist.balanced_cell_ranges(s.plp.cell_ptr, 3)]
+    assert sum(p.n_pairs for p in parts) == s.plp.n_pairs and sum(p.n_reads for p in parts) == s.plp.n_reads
+    sh = [s.plp.slice_snps(a, b) for a, b in dist.balanced_snp_ranges(s.plp.pair_snp, 500, 3)]
+    assert sum(p.n_pairs for p in sh) == s.plp.n_pairs and all(p.n_cells == 60 for p in sh)
+
+
+# ---- world_size 2 over gloo -------------------------------------------------------------------
+def _worker_demux(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    import torch.distributed as td
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    s = synth.make_pileup(C=90, nv=4, V=600, kbar=120, seed=31)
+    gp = synth.gt_to_gp(s.geno)
+
+    def gather(rec):
+        out = [None] * world
+        td.all_gather_object(out, rec)
+        return out
+    got = dist.demux_sharded(OracleEngine(1), s.plp, gp, None, [0.0, 0.5], 0.5, rank, world, gather)
+    if rank == 0:
+        full = orc.demux(s.plp, gp, None, [0.0, 0.5])
+        q.put(got.tobytes() == full.tobytes())
+    td.destroy_process_group()
+
+
+class _OracleStep:
+    """step-level freemuxlet surface over the oracle's pieces (host-logic test only)"""
+    def __init__(self):
+        self.new_f64 = lambda n: np.zeros(n)
+        self.new_i32 = lambda n: np.zeros(n, dtype=np.int32)
+
+    def init(self, plp, opts):
+        self.plp, self.o = plp, opts
+        self.nS = opts.n_clusters
+        self.pair_gl = np.array([orc.fmx_pair_pileup(plp.read_allele[a:b], plp.read_qual[a:b])[0]
+                                 for a, b in zip(plp.pair_read_ptr[:-1], plp.pair_read_ptr[1:])]).reshape(-1, 9)
+        self.pair_cell = np.repeat(np.arange(plp.n_cells), np.diff(plp.cell_ptr))
+
+    def stage1(self, st):
+        C = self.plp.n_cells
+        st[:] = 0
+        st[2 * C:3 * C] = np.diff(self.plp.cell_ptr)
+
+    def seed(self, st, init, cl):
+        cl[:] = init
+        self.types = np.where(init >= 0, 0, -1)
+        self.cells = np.zeros(self.plp.n_cells, dtype=orc.FMX_CELL_DTYPE)
+        for f in ("best_j", "best_k"):
+            self.cells[f] = -1
+
+    def mstep(self, cl):
+        if cl is not None:
+            self.member = np.array(cl)
+        V, nS = self.plp.n_snps, self.nS
+        gl = np.ones((V, nS, 9))
+        for p in range(self.plp.n_pairs):  # ascending cell id inside every SNP
+            j = self.member[self.pair_cell[p]]
+            if j >= 0:
+                v = self.plp.pair_snp[p]
+                gl[v, j], _, _ = orc.fmx_merge(gl[v, j], [0, 0, 0], 0.0, self.pair_gl[p], [0, 0, 0], 0.0)
+        self.clust_gl = gl
+
+    def estep(self, it, llk):
+        llk[:] = orc.fmx_estep(self.plp, self.pair_gl, self.clust_gl, self.nS, self.o.geno_error).ravel()
+
+    def classify(self, llk, cl):
+        nS = self.nS
+        L = llk.reshape(self.plp.n_cells, -1)
+        diag = [j * (j + 1) // 2 + j for j in range(nS)]
+        sng = L[:, diag]
+        off = np.ones(L.shape[1], bool); off[diag] = False
+        best = sng.argmax(1)
+        srt = np.sort(sng, 1)
+        is_dbl = L[:, off].max(1) > srt[:, -1] + 2
+        is_sng = ~is_dbl & (srt[:, -1] > srt[:, -2] + 2)
+        new_types = np.where(is_dbl, 1, np.where(is_sng, 0, 2))
+        changed = int(((new_types != self.types) | (is_sng & (self.cells["best_j"] != best))).sum())
+        self.types = new_types
+        self.cells["best_j"] = self.cells["best_k"] = best
+        self.member = np.where(is_sng, best, -1)
+        cl[:] = self.member
+
+        class R: pass
+        r = R(); r.n_changed = changed
+        return r
+
+    def fetch(self):
+        return self.types.copy(), self.member.copy()
+
+
+def _worker_fmx(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    import torch
+    import torch.distributed as td
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    s = synth.make_pileup(C=50, nv=3, V=400, kbar=120, seed=32)
+    v0, v1 = dist.balanced_snp_ranges(s.plp.pair_snp, 400, world)[rank]
+
+    def allreduce(buf):
+        t = torch.from_numpy(buf)
+        td.all_reduce(t)
+    o = orc.fmx_opts(3, max_iter=4)
+    init = s.truth_d1.astype(np.int32)
+    (types, member), res = dist.fmx_em_sharded(_OracleStep(), s.plp.slice_snps(v0, v1), o, init, allreduce, 50)
+    if rank == 0:
+        (t1, m1), r1 = dist.fmx_em_sharded(_OracleStep(), s.plp, o, init, lambda b: None, 50)
+        ref = orc.fmx_run(s.plp, o, init)["cells"]
+        q.put(bool(np.array_equal(types, t1) and np.array_equal(member, m1) and np.array_equal(types, ref["type"])
+                   and np.array_equal(member, np.where(ref["type"] == 0, ref["best_j"], -1))))
+    td.destroy_process_group()
+
+
+def _spawn(fn, port):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=fn, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in ps:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in ps)
+    return ok
+
+
+def test_gloo_barcode_sharded_demuxlet(built):
+    assert _spawn(_worker_demux, 29611)
+
+
+def test_gloo_snp_sharded_freemuxlet(built):
+    assert _spawn(_worker_fmx, 29612)

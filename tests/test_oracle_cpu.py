@@ -1,0 +1,155 @@
+"""CPU checks of the oracle itself: analytic spot values, properties, and the
+regression vectors that do not need the reference binary."""
+import math
+
+import numpy as np
+
+import oracle_py as orc
+from popscle_b200 import synth
+from tests.parity import assert_close
+
+
+def test_phred_table(built):
+    L = orc.lib()
+    assert L.orc_phred2err(0) == 0.75 and L.orc_phred2err(1) == 0.75  # PhredHelper.cpp:30
+    for q in (2, 13, 20, 40, 60):
+        assert L.orc_phred2err(q) == math.pow(0.1, q * 0.1)
+        assert L.orc_phred2mat(q) == 1.0 - math.pow(0.1, q * 0.1)
+
+
+def test_log_add(built):
+    L = orc.lib()
+    assert_close(L.orc_log_add(-1.0, -2.0), math.log(math.exp(-1) + math.exp(-2)), "logAdd", rtol=1e-14)
+    assert L.orc_log_add(-1e300, -5.0) == -5.0
+    assert L.orc_log_add(-1e-300, -800.0) == -1e-300  # the (sic) start value of cmd_cram_demuxlet.cpp:791 swallows real LLKs
+
+
+def test_demux_single_read_pg(built):
+    """one REF read, q=20, alpha grid {0, 0.5}: pR=0.99, pA=0.01/3 (cmd_cram_demuxlet.cpp:666-667)"""
+    pg = orc.demux_pair_pg([0], [20], [0.0, 0.5])
+    pR, pA = 0.99, 0.01 / 3
+    raw = np.array([[[pR * (1 - p) + pA * p for p in (0.5 * l + (m - l) * 0.5 * a for m in range(3))] for l in range(3)] for a in (0.0, 0.5)])
+    assert_close(raw[0, :, 0], [0.99, 0.4966666667, 0.0033333333], "alpha=0 rows", rtol=1e-9)
+    want = (raw / raw.max() + 1e-10) / (1 + 1e-10)  # closed form of :692-725
+    assert_close(pg, want, "pG closed form", rtol=1e-14)
+    # allele 2 reads are skipped (:664): pG stays flat
+    flat = orc.demux_pair_pg([2, 2], [30, 30], [0.0, 0.5])
+    assert_close(flat, np.ones((2, 3, 3)), "skipped reads", rtol=1e-15)
+
+
+def test_demux_pg_closed_form_many_reads(built):
+    rng = np.random.default_rng(0)
+    al = rng.integers(0, 3, 40)
+    q = rng.integers(13, 41, 40)
+    alphas = [0.0, 0.1, 0.25, 0.5]
+    pg = orc.demux_pair_pg(al, q, alphas)
+    raw = np.ones((4, 3, 3))
+    for a, b in zip(al, q):
+        if a == 2:
+            continue
+        e = 10 ** (-b / 10)
+        pR, pA = (1 - e if a == 0 else e / 3), (1 - e if a == 1 else e / 3)
+        for n, alpha in enumerate(alphas):
+            for l in range(3):
+                for m in range(3):
+                    p = 0.5 * l + (m - l) * 0.5 * alpha
+                    raw[n, l, m] *= pR * (1 - p) + pA * p
+    assert_close(pg, (raw / raw.max() + 1e-10) / (1 + 1e-10), "pG closed form", rtol=1e-12)
+
+
+def test_demux_symmetry_and_permutation(built):
+    """LLK[j,k,a] == LLK[k,j,1-a]; permuting samples permutes the grid."""
+    alphas = [0.0, 0.25, 0.5, 0.75]
+    s = synth.make_pileup(C=30, nv=4, V=500, kbar=120, seed=21)
+    gp = synth.gt_to_gp(s.geno)
+    _, grid = orc.demux(s.plp, gp, None, alphas, want_grid=True)
+    for j in range(4):
+        for k in range(4):
+            if j != k:
+                assert_close(grid[:, j, k, 1], grid[:, k, j, 3], "alpha symmetry", rtol=1e-10)
+                assert_close(grid[:, j, k, 2], grid[:, k, j, 2], "alpha 0.5 symmetry", rtol=1e-10)
+    perm = np.array([2, 0, 3, 1])
+    _, g2 = orc.demux(s.plp, gp[:, perm, :], None, alphas, want_grid=True)
+    off = ~np.eye(4, dtype=bool)
+    for n in range(1, 4):
+        assert_close(g2[:, :, :, n][:, off], grid[:, perm][:, :, perm][:, :, :, n][:, off], "permutation", rtol=1e-10)
+    # alpha = 0 plane does not depend on k up to the row-sum factor (§8a note 3)
+    assert_close(grid[:, :, 1, 0], grid[:, :, 0, 0], "alpha 0 independent of k", rtol=1e-6)
+
+
+def test_demux_recovers_truth_and_quirks(built):
+    s = synth.make_config(1)
+    gp = synth.gt_to_gp(s.geno)
+    out = orc.demux(s.plp, gp, None, [0.0, 0.5], n_threads=8)
+    sng = out["type"] == 0
+    assert sng.mean() > 0.8
+    assert (out["sng_best"][sng] == s.truth_d1[sng]).mean() > 0.99
+    dbl = out["type"] == 1
+    truth_dbl = s.truth_d1 != s.truth_d2
+    assert (truth_dbl[dbl]).mean() > 0.95
+    # quirk 1: sumLLK starts at -1e-300, so SNG.POSTERIOR is exp(0) = 1 for every realistic cell
+    assert np.mean(out["sng_pp"] == 1.0) > 0.9 and np.all(out["sng_pp"] <= 1.0)
+    # quirk 2: SNG/AMB BEST.POSTERIOR is a log (negative), DBL is exp() (in [0,1])
+    assert np.all(out["best_pp"][sng] < 0) and np.all((out["best_pp"][dbl] >= 0) & (out["best_pp"][dbl] <= 1))
+
+
+def test_fmx_pair_pileup_values(built):
+    """one REF read q=20 at alpha=0.5 (sc_drop_seq.cpp:482-490): weights {1,.75,.5,.75,.5,.25,.5,.25,0}"""
+    gls, cnt, ld = orc.fmx_pair_pileup([0], [20])
+    w = np.array([1, .75, .5, .75, .5, .25, .5, .25, 0])
+    raw = 0.99 * w + 0.01 / 4
+    want = raw / raw.sum()
+    want = np.maximum(want, 1e-6)
+    want /= want.sum()
+    assert_close(gls, want, "9-GL", rtol=1e-14)
+    assert list(cnt) == [1, 1, 0]
+    g2, c2, _ = orc.fmx_pair_pileup([2, 1], [20, 30])
+    assert list(c2) == [2, 0, 1]  # allele 2 counts in nreads only (:465-467)
+
+
+def test_merge_is_order_dependent(built):
+    """H3 regression vector: the 1e-6 clamp after every merge makes merge order matter
+    (sc_drop_seq.h:77-101) — 12 REF cells then 12 ALT cells vs interleaved."""
+    ref, _, _ = orc.fmx_pair_pileup([0], [30])
+    alt, _, _ = orc.fmx_pair_pileup([1], [30])
+
+    def run(seq):
+        g, c, ld = np.ones(9), np.zeros(3, dtype=np.int32), 0.0
+        for x in seq:
+            g, c, ld = orc.fmx_merge(g, c, ld, x, [1, 0, 0], 0.0)
+        return g
+
+    blocked = run([ref] * 12 + [alt] * 12)
+    inter = run([ref, alt] * 12)
+    assert_close(blocked[[0, 4, 8]], [1.0e-6, 0.0460, 0.8130], "blocked", rtol=2e-2)
+    assert abs(inter[4] - 0.32) < 0.02 and inter[0] < 1e-5 and inter[8] < 1e-5
+    assert abs(blocked[4] - inter[4]) > 0.2
+
+
+def test_fmx_recovers_donors(built):
+    s = synth.make_pileup(C=300, nv=4, V=2500, kbar=300, seed=504)
+    r = orc.fmx_run(s.plp, orc.fmx_opts(4), want_clusters=True, n_threads=8)
+    c = r["cells"]
+    sng = c["type"] == 0
+    tab = np.zeros((4, 4), dtype=int)
+    np.add.at(tab, (c["clust"][sng], s.truth_d1[sng]), 1)
+    assert tab.max(axis=1).sum() > 0.97 * sng.sum()
+    assert r["res"].n_changed == 0 and r["res"].n_iter <= 10
+    # cluster read counts add up to the reads of the singlets' pairs
+    nrd = np.diff(s.plp.pair_read_ptr)
+    pair_cell = np.repeat(np.arange(s.plp.n_cells), np.diff(s.plp.cell_ptr))
+    assert r["clust_cnt"][:, :, 0].sum() == nrd[sng[pair_cell]].sum()
+
+
+def test_fmx_snp_shard_sum_equals_full(built):
+    """E-step partial LLKs of SNP shards add up to the unsharded E-step."""
+    s = synth.make_pileup(C=80, nv=3, V=900, kbar=200, seed=9)
+    r = orc.fmx_run(s.plp, orc.fmx_opts(3, max_iter=1), want_clusters=True, want_pair_gl=True, want_llk=True)
+    full = orc.fmx_estep(s.plp, r["pair_gl"], r["clust_gl"], 3, 0.1)
+    tot = np.zeros_like(full)
+    pair_cell = np.repeat(np.arange(s.plp.n_cells), np.diff(s.plp.cell_ptr))
+    for v0, v1 in ((0, 300), (300, 650), (650, 900)):
+        sh = s.plp.slice_snps(v0, v1)
+        keep = (s.plp.pair_snp >= v0) & (s.plp.pair_snp < v1)
+        tot += orc.fmx_estep(sh, r["pair_gl"][keep], r["clust_gl"], 3, 0.1)
+    assert_close(tot, full, "sharded E-step", rtol=1e-12)
