@@ -9,7 +9,8 @@
  * (SURVEY.md §4, §8c).  The restatement is pinned against the reference's own translation
  * units compiled from /root/reference by oracle/build_ref.sh into oracle/_ref/ (the real
  * cmdCramDemuxlet / cmdCramFreemux2 / sc_drop_seq.cpp / PhredHelper.cpp code, linked against a
- * small htslib stand-in); see oracle/README.md and tests/golden/.
+ * small htslib stand-in, oracle/htslib_standin/): tests/golden/ holds the files that binary wrote and
+ * tests/test_golden.py requires this restatement to reproduce them byte for byte.
  *
  * Every function cites the reference file:line it follows.  All arithmetic is FP64 in the
  * reference's operation order (compile WITHOUT -ffast-math and with -ffp-contract=off).
