@@ -1,0 +1,324 @@
+// loader.cpp — see loader.h
+#include "loader.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <set>
+
+#include "tsv.h"
+
+namespace pscl_host {
+
+std::vector<std::string> read_first_column(const std::string& path) {
+  LineReader r(path);
+  std::string line;
+  std::vector<char*> f;
+  std::vector<std::string> out;
+  while (next_row(r, line, f)) out.emplace_back(f[0]);
+  return out;
+}
+
+namespace {
+
+// ---- text VCF cursor: records that pass the demuxlet site filters, with float posteriors ----------
+struct VcfCursor {
+  LineReader rd;
+  const LoadOptions& o;
+  std::map<std::string, int> contig;  // header order, then first appearance
+  std::vector<std::string> samples;   // selected sample names, in reference order
+  std::vector<int> cols;              // their VCF columns
+  bool eof = false;
+  int rid = -1, pos = 0;
+  char ref = 0, alt = 0;
+  std::vector<float> gps;             // [nv*3] of the current record
+  std::string line;
+  std::vector<std::string> c, alleles, fmt, cell, parts, vals;
+
+  VcfCursor(const std::string& path, const LoadOptions& opt) : rd(path), o(opt) {
+    bool saw = false;
+    while (rd.next(line)) {
+      if (line.compare(0, 2, "##") == 0) {
+        if (line.compare(0, 13, "##contig=<ID=") == 0) {
+          size_t e = line.find_first_of(",>", 13);
+          std::string id = line.substr(13, e == std::string::npos ? std::string::npos : e - 13);
+          if (!contig.count(id)) { int k = (int)contig.size(); contig[id] = k; }
+        }
+        continue;
+      }
+      if (line.compare(0, 6, "#CHROM") == 0) {
+        split_char(line, '\t', c);
+        std::vector<std::string> all(c.begin() + std::min<size_t>(9, c.size()), c.end());
+        if (!o.sm.empty()) {  // std::set iteration = sorted, duplicates dropped (bcf_filtered_reader.cpp:107-125)
+          std::set<std::string> want(o.sm.begin(), o.sm.end());
+          for (const auto& s : want) {
+            auto it = std::find(all.begin(), all.end(), s);
+            if (it == all.end()) throw host_error("Cannot find sample ID " + s + " from the BCF file");
+            samples.push_back(s);
+            cols.push_back((int)(it - all.begin()));
+          }
+        } else {
+          samples = all;
+          cols.resize(all.size());
+          std::iota(cols.begin(), cols.end(), 0);
+        }
+        saw = true;
+        break;
+      }
+      break;
+    }
+    if (!saw) throw host_error("Failed reading the BCF/VCF header from " + path + " (text VCF, plain or gzip, is supported)");
+  }
+
+  // advance to the next record passing the site filters (bcf_filtered_reader.cpp:505-581, :748-762)
+  bool read() {
+    const int nv = (int)cols.size();
+    while (rd.next(line)) {
+      if (line.empty()) continue;
+      split_char(line, '\t', c);
+      if (c.size() < 10) throw host_error("VCF data line with fewer than 10 columns in " + rd.path());
+      auto it = contig.find(c[0]);
+      if (it == contig.end()) { int k = (int)contig.size(); it = contig.emplace(c[0], k).first; }
+      alleles.clear();
+      alleles.push_back(c[3]);
+      if (c[4] != ".") { split_char(c[4], ',', parts); alleles.insert(alleles.end(), parts.begin(), parts.end()); }
+      const int nal = (int)alleles.size();
+      if (nal > o.max_alleles) continue;
+      split_char(c[8], ':', fmt);
+      int gi = -1, fi = -1;
+      for (size_t i = 0; i < fmt.size(); ++i) {
+        if (fmt[i] == "GT") gi = (int)i;
+        if (fmt[i] == o.field) fi = (int)i;
+      }
+      if (gi < 0) throw host_error("Cannot find the field GT from the VCF file at position " + c[0] + ":" + c[1]);
+      // minMAC / minCallRate force GT parsing (bcf_filter_arg.h:110-113)
+      std::vector<int> g1(nv), g2(nv), acs(nal, 0);
+      int an = 0;
+      std::vector<std::vector<std::string>> smp(nv);
+      for (int i = 0; i < nv; ++i) {
+        split_char(c[9 + cols[i]], ':', smp[i]);
+        const std::string& gt = gi < (int)smp[i].size() ? smp[i][gi] : std::string(".");
+        size_t sep = gt.find_first_of("/|");
+        std::string a = gt.substr(0, sep), b = sep == std::string::npos ? std::string(".") : gt.substr(sep + 1);
+        g1[i] = (a == "." || a.empty()) ? -1 : atoi(a.c_str());
+        g2[i] = (b == "." || b.empty()) ? -1 : atoi(b.c_str());
+        if (g1[i] >= 0) { ++an; ++acs[g1[i]]; }
+        if (g2[i] >= 0) { ++an; ++acs[g2[i]]; }
+      }
+      if (nv > 0 && o.min_callrate > (double)an / (2.0 * nv)) continue;
+      const int ac = an - acs[0];
+      if (ac < o.min_mac || an - ac < o.min_mac) continue;
+      // ---- posteriors with gt_error = 0 (load_from_plp passes 0, sc_drop_seq.cpp:113,285) ----
+      const int ngen = nal * (nal + 1) / 2;
+      gps.assign((size_t)nv * ngen, 0.f);
+      if (o.field == "GT") {  // :379-412
+        for (int i = 0; i < nv; ++i) {
+          if (g1[i] < 0 || g2[i] < 0) {
+            int l = 0;
+            for (int j = 0; j < nal; ++j)
+              for (int k = 0; k <= j; ++k, ++l)
+                gps[(size_t)i * ngen + l] = (float)((j == k ? 1.0 : 2.0) * (acs[j] + 1.0 / nal) / (an + 1.0) * (acs[k] + 1.0 / nal) / (an + 1.0));
+          } else {
+            const int a = std::max(g1[i], g2[i]), b = std::min(g1[i], g2[i]);
+            gps[(size_t)i * ngen + a * (a + 1) / 2 + b] = 1.0f;
+          }
+        }
+      } else if (o.field == "PL") {  // :250-327, ploidy 2
+        if (fi < 0) throw host_error("Cannot parse posterior probability at " + c[0] + ":" + c[1]);
+        std::vector<double> pls((size_t)nv * ngen), af(nal, 1.0 / nal), gp(ngen), post((size_t)nv * ngen);
+        for (int i = 0; i < nv; ++i) {
+          split_char(fi < (int)smp[i].size() ? smp[i][fi] : std::string("."), ',', vals);
+          for (int l = 0; l < ngen; ++l) pls[(size_t)i * ngen + l] = l < (int)vals.size() ? atoi(vals[l].c_str()) : 0;
+        }
+        for (int iter = 0; iter < 10; ++iter) {
+          std::vector<double> nw(nal, 0.0);
+          for (int i = 0; i < nv; ++i) {
+            double sum = 0;
+            int l = 0;
+            for (int j = 0; j < nal; ++j)
+              for (int k = 0; k <= j; ++k, ++l) sum += (gp[l] = (j == k ? 1 : 2) * af[j] * af[k] * std::pow(0.1, pls[(size_t)i * ngen + l] / 10.0));
+            l = 0;
+            for (int j = 0; j < nal; ++j)
+              for (int k = 0; k <= j; ++k, ++l) { gp[l] /= sum; nw[j] += gp[l]; nw[k] += gp[l]; post[(size_t)i * ngen + l] = gp[l]; }
+          }
+          for (int j = 0; j < nal; ++j) af[j] = nw[j] / (2.0 * nv);
+        }
+        for (size_t i = 0; i < post.size(); ++i) gps[i] = (float)post[i];
+      } else {  // GP-like float field, :434-458 with gt_error = 0
+        if (fi < 0) throw host_error("Cannot parse posterior probability at " + c[0] + ":" + c[1]);
+        for (int i = 0; i < nv; ++i) {
+          split_char(fi < (int)smp[i].size() ? smp[i][fi] : std::string("."), ',', vals);
+          float sum = 0.f;
+          for (int l = 0; l < ngen; ++l) { float x = l < (int)vals.size() ? (float)atof(vals[l].c_str()) : 0.f; gps[(size_t)i * ngen + l] = x; sum += x; }
+          for (int l = 0; l < ngen; ++l) gps[(size_t)i * ngen + l] /= sum;
+        }
+      }
+      rid = it->second;
+      pos = atoi(c[1].c_str());
+      ref = alleles[0][0];
+      alt = nal > 1 ? alleles[1][0] : '.';
+      if (nal != 2) gps.resize((size_t)nv * 3, 0.f);
+      return true;
+    }
+    eof = true;
+    return false;
+  }
+};
+
+void expect_header(LineReader& r, const char* const* names, int n, const std::string& what, const char* expecting) {
+  std::string line;
+  std::vector<char*> f;
+  if (!next_row(r, line, f)) throw host_error("Cannot read the first line of " + what);
+  bool ok = (int)f.size() == n;
+  for (int i = 0; ok && i < n; ++i) ok = strcmp(f[i], names[i]) == 0;
+  if (!ok) throw host_error("The header line of " + what + " is malformed or outdated. Expecting " + expecting);
+}
+
+}  // namespace
+
+void load_plp(const LoadOptions& o, Loaded& L) {
+  std::string line;
+  std::vector<char*> f;
+  // ---- CEL (sc_drop_seq.cpp:124-203) ----
+  std::vector<int32_t> index_bcs;
+  std::vector<int64_t> tmp_totl, tmp_uniq, tmp_nsnp;
+  {
+    LineReader r(o.plp_prefix + ".cel.gz");
+    static const char* H[] = {"#DROPLET_ID", "BARCODE", "NUM.READ", "NUM.UMI", "NUM.UMIwSNP", "NUM.SNP"};
+    expect_header(r, H, 6, o.plp_prefix + ".cel.gz", "#DROPLET_ID BARCODE NUM.READ NUM.UMI NUM.UMIwSNP NUM.SNP");
+    std::set<std::string> valid(o.group_list.begin(), o.group_list.end());
+    int nskip = 0;
+    while (next_row(r, line, f)) {
+      if (f.size() < 6) throw host_error("Cannot access field at 5 >= " + std::to_string(f.size()));
+      if (o.has_group_list && !valid.count(f[1])) { ++nskip; index_bcs.push_back(-1); continue; }
+      const int n_reads = atoi(f[2]), n_umis = atoi(f[3]), n_uws = atoi(f[4]), n_snps = atoi(f[5]);
+      if (n_reads < o.min_read || n_umis < o.min_umi || n_snps < o.min_snp) { index_bcs.push_back(-1); ++nskip; continue; }
+      const int new_id = (int)L.barcodes.size();
+      if (new_id + nskip != atoi(f[0]))
+        throw host_error("Observed DROPLET_ID " + std::string(f[0]) + " is different from expected DROPLET_ID. Did you modify the digital pileup files by yourself?");
+      L.barcodes.emplace_back(f[1]);
+      index_bcs.push_back(new_id);
+      tmp_totl.push_back(n_reads); tmp_uniq.push_back(n_uws); tmp_nsnp.push_back(n_snps);
+    }
+  }
+  const int32_t C = (int32_t)L.barcodes.size();
+  // ---- VAR, merge-joined with the VCF cursor (:206-330) ----
+  {
+    LineReader r(o.plp_prefix + ".var.gz");
+    static const char* H[] = {"#SNP_ID", "CHROM", "POS", "REF", "ALT", "AF"};
+    expect_header(r, H, 6, o.plp_prefix + ".var.gz", "#SNP_ID CHROM POS REF ALT AF");
+    std::unique_ptr<VcfCursor> vc;
+    int nv = 0;
+    if (!o.vcf.empty()) {
+      vc.reset(new VcfCursor(o.vcf, o));
+      if (!vc->read()) throw host_error("Cannot read any single variant from " + o.vcf);
+      L.samples = vc->samples;
+      nv = (int)L.samples.size();
+    }
+    std::map<std::string, int> chr2rid;
+    while (next_row(r, line, f)) {
+      if (f.size() < 6) throw host_error("Cannot access field at 5 >= " + std::to_string(f.size()));
+      auto it = chr2rid.find(f[1]);
+      if (it == chr2rid.end()) { int k = (int)chr2rid.size(); it = chr2rid.emplace(f[1], k).first; L.rid2chr.emplace_back(f[1]); }
+      const int rid = it->second, pos = atoi(f[2]);
+      const char ref = f[3][0], alt = f[4][0];
+      L.chrom.emplace_back(f[1]); L.pos.push_back(pos); L.ref.push_back(ref); L.alt.push_back(alt); L.af.push_back(atof(f[5]));
+      if (!vc) continue;
+      bool found = false;
+      for (;;) {  // VCF header rids are compared NUMERICALLY with the VAR first-appearance rids (:262-264)
+        if (vc->eof || vc->rid > rid) break;
+        if (vc->rid == rid) {
+          if (vc->pos > pos) break;
+          if (vc->pos == pos) { found = (vc->ref == ref && vc->alt == alt); break; }
+        }
+        vc->read();
+      }
+      const size_t base = L.gp.size();
+      L.gp.resize(base + (size_t)nv * 3, 0.0);
+      L.has_gp.push_back(found ? 1 : 0);
+      if (!found) continue;
+      double avg[3] = {1e-10, 1e-10, 1e-10};  // :288-292
+      for (int i = 0; i < nv * 3; ++i) avg[i % 3] += (L.gp[base + i] = (double)vc->gps[i]);
+      const double sum = avg[0] + avg[1] + avg[2];
+      avg[0] /= sum; avg[1] /= sum; avg[2] /= sum;
+      double err = o.geno_error_offset;
+      if (err > 0.999) err = 0.999;
+      if (err < 0) err = 0;
+      if (err > 0)
+        for (int i = 0; i < nv * 3; ++i) L.gp[base + i] = (1 - err) * L.gp[base + i] + err * avg[i % 3];
+    }
+  }
+  const int32_t V = (int32_t)L.chrom.size();
+  // ---- PLP (:335-372): rows -> (cell, snp, reads); then cell-major, SNP ascending ----
+  std::vector<int32_t> row_cell, row_snp;
+  std::vector<int64_t> row_beg;  // into al / bq
+  std::vector<uint8_t> al, bq;
+  {
+    LineReader r(o.plp_prefix + ".plp.gz");
+    static const char* H[] = {"#DROPLET_ID", "SNP_ID", "ALLELES", "BASEQS"};
+    expect_header(r, H, 4, o.plp_prefix + ".plp.gz", "#DROPLET_ID SNP_ID ALLELES BASEQS");
+    while (next_row(r, line, f)) {
+      if (f.size() < 4) throw host_error("Cannot access field at 3 >= " + std::to_string(f.size()));
+      const int drop = atoi(f[0]);
+      if (drop < 0 || drop >= (int)index_bcs.size()) throw host_error("DROPLET_ID " + std::string(f[0]) + " of .plp.gz is not in .cel.gz");
+      const int ibc = index_bcs[drop];
+      if (ibc < 0) continue;
+      const int snp = atoi(f[1]);
+      if (snp < 0 || snp >= V) throw host_error("SNP_ID " + std::string(f[1]) + " of .plp.gz is not in .var.gz");
+      const char *pa = f[2], *pq = f[3];
+      const size_t l = strlen(pq), la = strlen(pa);
+      const int64_t b0 = (int64_t)al.size();
+      for (size_t i = 0; i < l && i < la; ++i) {
+        int q = (int)(signed char)(pq[i] - 33);
+        if (q >= o.min_bq) {
+          if (q > o.cap_bq) q = o.cap_bq;
+          al.push_back((uint8_t)(pa[i] - '0'));
+          bq.push_back((uint8_t)q);
+        }
+      }
+      if ((int64_t)al.size() == b0) continue;
+      row_cell.push_back(ibc); row_snp.push_back(snp); row_beg.push_back(b0);
+    }
+    row_beg.push_back((int64_t)al.size());
+  }
+  const size_t R = row_cell.size();
+  std::vector<uint32_t> order(R);
+  std::iota(order.begin(), order.end(), 0u);
+  bool sorted = true;
+  for (size_t i = 1; i < R && sorted; ++i)
+    sorted = row_cell[i - 1] < row_cell[i] || (row_cell[i - 1] == row_cell[i] && row_snp[i - 1] <= row_snp[i]);
+  if (!sorted)  // dsc-pileup writes SNP-major; the std::map of the reference makes it cell-major, SNP ascending
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return row_cell[a] != row_cell[b] ? row_cell[a] < row_cell[b] : row_snp[a] < row_snp[b];
+    });
+  L.n_cells = C; L.n_snps = V;
+  L.cell_ptr.assign((size_t)C + 1, 0);
+  L.pair_read_ptr.assign(1, 0);
+  L.read_allele.reserve(al.size()); L.read_qual.reserve(bq.size());
+  L.cell_uniq_reads.assign(C, 0);
+  int prev_c = -1, prev_s = -1;
+  for (size_t k = 0; k < R; ++k) {
+    const uint32_t i = order[k];
+    const bool same = row_cell[i] == prev_c && row_snp[i] == prev_s;  // a (cell,SNP) listed on several rows is one pair
+    L.read_allele.insert(L.read_allele.end(), al.begin() + row_beg[i], al.begin() + row_beg[i + 1]);
+    L.read_qual.insert(L.read_qual.end(), bq.begin() + row_beg[i], bq.begin() + row_beg[i + 1]);
+    if (same) L.pair_read_ptr.back() = (int64_t)L.read_allele.size();
+    else {
+      L.pair_snp.push_back(row_snp[i]);
+      L.pair_read_ptr.push_back((int64_t)L.read_allele.size());
+      ++L.cell_ptr[(size_t)row_cell[i] + 1];
+    }
+    L.cell_uniq_reads[row_cell[i]] += row_beg[i + 1] - row_beg[i];
+    prev_c = row_cell[i]; prev_s = row_snp[i];
+  }
+  for (int32_t c = 0; c < C; ++c) L.cell_ptr[c + 1] += L.cell_ptr[c];
+  // sanity check on the observed counts (:375-381): NUM.READ replaces the pass count where the rest agrees
+  L.cell_totl_reads = L.cell_uniq_reads;
+  for (int32_t c = 0; c < C; ++c)
+    if (L.cell_uniq_reads[c] == tmp_uniq[c] && tmp_nsnp[c] == L.cell_ptr[c + 1] - L.cell_ptr[c]) L.cell_totl_reads[c] = tmp_totl[c];
+}
+
+}  // namespace pscl_host

@@ -1,0 +1,59 @@
+// loader.h — dsc-pileup CEL/VAR/PLP (+ text VCF) -> flat cell-major pileup for the C ABI.
+// Reproduces sc_dropseq_lib_t::load_from_plp (reference sc_drop_seq.cpp:103-384) and the genotype
+// preparation of BCFFilteredReader (bcf_filtered_reader.cpp:367-461, :505-581) for text VCF.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/popscle_b200.h"
+
+namespace pscl_host {
+
+struct LoadOptions {
+  std::string plp_prefix, vcf;           // vcf empty = no genotypes (freemuxlet)
+  std::string field = "GP";
+  double geno_error_offset = 0.1;
+  std::vector<std::string> sm;           // --sm / --sm-list (held in a std::set by the reference: sorted)
+  int min_bq = 1, cap_bq = 60;           // library defaults (sc_drop_seq.h:181); the commands pass 13 / 20
+  int min_read = 0, min_umi = 0, min_snp = 0;
+  std::vector<std::string> group_list;   // empty = all barcodes
+  bool has_group_list = false;
+  int min_mac = 1;
+  double min_callrate = 0.5;
+  int max_alleles = 2;
+};
+
+struct Loaded {
+  // pileup (cell-major CSR)
+  int32_t n_cells = 0, n_snps = 0;
+  std::vector<int64_t> cell_ptr, pair_read_ptr;
+  std::vector<int32_t> pair_snp;
+  std::vector<uint8_t> read_allele, read_qual;
+  // sites
+  std::vector<std::string> chrom, rid2chr;
+  std::vector<int32_t> pos;
+  std::vector<char> ref, alt;
+  std::vector<double> af;
+  // droplets
+  std::vector<std::string> barcodes;
+  std::vector<int64_t> cell_uniq_reads, cell_totl_reads;
+  // genotypes (when a VCF was given)
+  std::vector<std::string> samples;
+  std::vector<double> gp;       // [V][nv][3]
+  std::vector<uint8_t> has_gp;  // [V]
+
+  pscl_pileup view() const {
+    pscl_pileup p;
+    p.n_cells = n_cells; p.n_snps = n_snps;
+    p.n_pairs = (int64_t)pair_snp.size(); p.n_reads = (int64_t)read_allele.size();
+    p.cell_ptr = cell_ptr.data(); p.pair_snp = pair_snp.data(); p.pair_read_ptr = pair_read_ptr.data();
+    p.read_allele = read_allele.data(); p.read_qual = read_qual.data(); p.snp_af = af.data();
+    return p;
+  }
+};
+
+void load_plp(const LoadOptions& o, Loaded& out);
+std::vector<std::string> read_first_column(const std::string& path);
+
+}  // namespace pscl_host

@@ -128,3 +128,95 @@ def test_cuda_matches_reference_files(case, tmp_path, ctx):
             _compare_vcf(ref, ours, f"{case}/{fn}")
         else:
             _compare_table(ref, ours, f"{case}/{fn}")
+
+
+# ---- the C++ CLI host (popscle_b200/host -> popscle_b200/popscle) -----------------------------------
+def _fnv1a(*arrays):
+    h = 1469598103934665603
+    for a in arrays:
+        for b in a.tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+def _host_argv(case, work):
+    argv = json.load(open(os.path.join(GOLD, case, "cmd.json")))["argv"]
+    return [("out" if a == "ref" and argv[i - 1] == "--out" else a) for i, a in enumerate(argv)]
+
+
+@pytest.fixture(scope="session")
+def host_exe(built):
+    from popscle_b200 import _build
+    exe = _build.build_host()
+    assert exe and os.path.exists(exe)
+    return exe
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cpp_host_loader_matches_python_loader(case, tmp_path, host_exe):
+    """`--dry-run` (test hook): the C++ loader's flat image has the same checksum as plpio.load_plp's."""
+    import subprocess
+    import numpy as np
+    from popscle_b200 import plpio
+    work = tmp_path / case
+    shutil.copytree(os.path.join(GOLD, case), work)
+    argv = _host_argv(case, work)
+    r = subprocess.run([host_exe] + argv + ["--dry-run"], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    o = cli._parse(argv[1:], {"demuxlet": cli.DEMUXLET_SPEC, "freemuxlet": cli.FREEMUXLET_SPEC, "freemuxlet-old": cli.FREEMUXLET_OLD_SPEC}[argv[0]])
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        if argv[0] == "demuxlet":
+            L = plpio.load_plp(o["plp"], o["vcf"], field=o["field"], geno_error_offset=o["geno-error-offset"], sm_list=o["sm"] or None,
+                               min_bq=o["min-BQ"], cap_bq=o["cap-BQ"], min_read=o["min-total"], min_umi=o["min-umi"], min_snp=o["min-snp"],
+                               group_list=cli._read_list(o["group-list"]) if o["group-list"] else None)
+        elif argv[0] == "freemuxlet":
+            L = plpio.load_plp(o["plp"], None, min_bq=o["min-BQ"], cap_bq=o["cap-BQ"])
+        else:
+            L = plpio.load_plp(o["plp"], None)
+    finally:
+        os.chdir(cwd)
+    p = L.plp
+    assert (got["cells"], got["snps"], got["pairs"], got["reads"]) == (p.n_cells, p.n_snps, p.n_pairs, p.n_reads)
+    assert got["pileup_fnv1a"] == _fnv1a(p.cell_ptr, p.pair_snp, p.pair_read_ptr, p.read_allele, p.read_qual, p.snp_af)
+    if L.geno is not None:
+        assert got["samples"] == len(L.geno.samples) and got["has_gp"] == int(L.geno.has_gp.sum())
+        assert got["geno_fnv1a"] == _fnv1a(np.ascontiguousarray(L.geno.gp), L.geno.has_gp)
+
+
+def test_cpp_host_errors(host_exe, tmp_path):
+    import subprocess
+    r = subprocess.run([host_exe, "demuxlet", "--plp", "x"], capture_output=True, text=True)
+    assert r.returncode == 134 and "FATAL ERROR" in r.stderr and "Missing required option(s)" in r.stderr
+    r = subprocess.run([host_exe, "freemuxlet", "--plp", "x", "--out", "y"], capture_output=True, text=True)
+    assert r.returncode == 134 and "--nsample" in r.stderr
+    r = subprocess.run([host_exe, "demuxlet", "--nope", "1"], capture_output=True, text=True)
+    assert r.returncode == 134 and "Cannot recognize" in r.stderr
+    assert subprocess.run([host_exe, "dsc-pileup"], capture_output=True).returncode == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cpp_host_matches_reference_files(case, tmp_path, host_exe):
+    """the drop-in binary end to end: files in, CUDA likelihoods, reference-format files out"""
+    import subprocess
+    work = tmp_path / case
+    shutil.copytree(os.path.join(GOLD, case), work)
+    r = subprocess.run([host_exe] + _host_argv(case, work), cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n = 0
+    for fn in sorted(os.listdir(work)):
+        if not fn.startswith("ref."):
+            continue
+        ours = work / ("out." + fn[4:])
+        if not ours.exists():
+            ours = work / ("out." + fn[4:] + ".gz")
+        assert ours.exists(), fn
+        txt = gzip.open(ours, "rt").read() if str(ours).endswith(".gz") else open(ours).read()
+        txt = "".join(l for l in txt.splitlines(True) if not l.startswith("##fileDate="))
+        ref = open(work / fn).read()
+        (_compare_vcf if fn.endswith(".vcf") else _compare_table)(ref, txt, f"{case}/{fn} (C++ host)")
+        n += 1
+    assert n > 0
