@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", default="ws", choices=["ws", "lane", "general"],
+                    help="demuxlet accumulation kernel: k_demux_ws (default), k_demux_default, k_demux_general")
     return ap.parse_args()
 
 
@@ -318,6 +320,8 @@ def main():
     plp, nv = s.plp, cfg["nv"]
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
+    ctx.demux_select_kernel({"ws": 0, "lane": 1, "general": 2}[args.kernel])
+    kname = {"ws": "k_demux_ws", "lane": "k_demux_default", "general": "k_demux_general"}[args.kernel]
 
     # ---- device-resident arm ("value") ----------------------------------------------------------
     dplp = ctx.upload(plp)
@@ -393,7 +397,7 @@ def main():
         abytes = algorithmic_bytes_demux(plp, nv)
         achieved = abytes / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("k_demux_default"), "kernel": f"k_demux_default<{nv}>",
+                "traffic": ncu_traffic(kname), "kernel": f"{kname}<{nv}>",
                 "kernel_ms": k_ms, "algorithmic_bytes": abytes, "peak_source": peak_src}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": t_ms_max / args.steps, "higher_is_better": True,

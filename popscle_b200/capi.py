@@ -170,6 +170,7 @@ def load_library() -> C.CDLL:
         "pscl_demux_fetch": (C.c_int, [vp, vp, vp]),
         "pscl_demux_keep_grid": (C.c_int, [vp, C.c_int]),
         "pscl_demux_force_general": (C.c_int, [vp, C.c_int]),
+        "pscl_demux_select_kernel": (C.c_int, [vp, C.c_int]),
         "pscl_demux_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CGeno), C.POINTER(CDemuxOpts), vp, vp]),
         "pscl_demux_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "pscl_fmx_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult)]),
@@ -194,7 +195,7 @@ EXPORTED_SYMBOLS = [
     "pscl_abi_version", "pscl_create", "pscl_destroy", "pscl_last_error", "pscl_stream", "pscl_set_stream",
     "pscl_sync", "pscl_launch_count", "pscl_set_partial_budget", "pscl_plp_upload", "pscl_plp_free",
     "pscl_demux_set_geno", "pscl_demux_score", "pscl_demux_fetch", "pscl_demux_keep_grid",
-    "pscl_demux_force_general", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_fmx_run", "pscl_fmx_init",
+    "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_fmx_run", "pscl_fmx_init",
     "pscl_fmx_stage1", "pscl_fmx_seed", "pscl_fmx_mstep", "pscl_fmx_estep", "pscl_fmx_classify",
     "pscl_fmx_fetch", "pscl_fmx_last_kernel_ms",
 ]
@@ -278,6 +279,10 @@ class Context:
 
     def demux_force_general(self, enable: bool):
         self._chk(self.lib.pscl_demux_force_general(self.h, int(enable)))
+
+    def demux_select_kernel(self, which: int):
+        """0 = auto (k_demux_ws), 1 = k_demux_default, 2 = k_demux_general (default alpha grid only)."""
+        self._chk(self.lib.pscl_demux_select_kernel(self.h, int(which)))
 
     def demux_score(self, dplp: "DevicePileup", alphas, doublet_prior: float = 0.5, cell_begin: int = 0,
                     cell_end: int | None = None):

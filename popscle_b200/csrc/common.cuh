@@ -38,6 +38,12 @@ struct pscl_plp {
   uint32_t* snp_pair = nullptr;  // [P] pair ids, ascending cell id inside one SNP
   int32_t* pair_cell = nullptr;  // [P]
   void* scratch_h2d = nullptr;   // int64 staging for pair_read_ptr
+  // demuxlet class streams for k_demux_ws (built lazily, demux_ws.inl): 8-byte records, class S
+  // (<= 1 usable base-call) first, then M (2-3), then D (> 3), inside each cell's pair range
+  uint2* dmx_rec = nullptr;          // [P]
+  double* dmx_deep = nullptr;        // [n_deep][6] folded factors of the pairs with > 3 usable base-calls
+  uint4* dmx_desc_nat = nullptr;     // [n_items] {begin, end, first M, first D}, natural item order
+  uint4* dmx_desc_sorted = nullptr;  // [n_items] the same in item_order
 };
 
 struct pscl_fmx_state;
@@ -56,6 +62,9 @@ struct pscl_ctx {
   int32_t nv = 0, geno_V = 0;
   double* gp = nullptr;       // [V][nv][3]
   uint8_t* has_gp = nullptr;  // [V] or null (= all)
+  double* gpM = nullptr;      // [V][(3nv+1)&~1] 16-B padded genotype rows (k_demux_ws, built lazily)
+  double* gpS = nullptr;      // [V][nv][2] (S_j, M_j) moments of the rows
+  int demux_kernel = 0;       // 0 auto (k_demux_ws), 1 k_demux_default, 2 k_demux_general
   bool keep_grid = false, force_general = false, dm_single_batch = true;
   int32_t dm_cell_begin = 0, dm_cell_end = 0, dm_nalpha = 0;
   void* dm_cells = nullptr;   // pscl_demux_cell[cells]

@@ -563,6 +563,8 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
   a.cells[a.out_base + blockIdx.x] = o;
 }
 
+#include "demux_ws.inl"
+
 // ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
@@ -575,6 +577,8 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaFree(ctx->gp); ctx->gp = nullptr;
   cudaFree(ctx->has_gp); ctx->has_gp = nullptr;
+  cudaFree(ctx->gpM); ctx->gpM = nullptr;
+  cudaFree(ctx->gpS); ctx->gpS = nullptr;
   size_t bytes = sizeof(double) * (size_t)n_snps * geno->n_samples * 3;
   PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp, bytes ? bytes : 16));
   PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->gp, geno->gp, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -595,6 +599,11 @@ extern "C" int pscl_demux_keep_grid(pscl_ctx* ctx, int enable) {
 extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
   if (!ctx) return PSCL_EINVAL;
   ctx->force_general = enable != 0;
+  return PSCL_OK;
+}
+extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 2) return PSCL_EINVAL;
+  ctx->demux_kernel = which;
   return PSCL_OK;
 }
 
@@ -639,7 +648,13 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
   if (ctx->keep_grid && (rc = pscl_reserve(ctx, &ctx->dm_grid, &ctx->dm_grid_cap, sizeof(double) * G * ncell)) != PSCL_OK) return rc;
   ctx->dm_cell_begin = cell_begin; ctx->dm_cell_end = cell_end; ctx->dm_nalpha = na;
 
-  const bool use_default = !ctx->force_general && na == 2 && h_alpha[0] == 0.0 && h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
+  const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && na == 2 && h_alpha[0] == 0.0 &&
+                           h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
+  const bool use_ws = use_default && ctx->demux_kernel == 0;
+  if (use_ws) {
+    if ((rc = dmx_build_classes(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
+    if ((rc = dmx_build_geno_tables(ctx)) != PSCL_OK) return rc;
+  }
   const std::vector<int32_t>& cip = plp->h_cell_item_ptr;
   size_t max_items = ctx->partial_budget_bytes / (G * sizeof(double));
   if (max_items < 1) max_items = 1;
@@ -664,7 +679,26 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
       a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
       a.item_base = ib; a.n_work = nwork; a.nv = nv; a.nalpha = na;
       cudaError_t e = cudaSuccess;
-      if (use_default) {
+      if (use_ws) {
+        PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
+        WsArgs wa;
+        wa.rec = plp->dmx_rec; wa.deep = plp->dmx_deep;
+        wa.gpM = ctx->gpM; wa.gpS = ctx->gpS; wa.fold_tab = ctx->fold_tab;
+        const bool whole = (ib == 0 && ie == plp->n_items);
+        wa.desc = whole ? plp->dmx_desc_sorted : plp->dmx_desc_nat + ib;
+        wa.desc_item = whole ? plp->item_order : nullptr;
+        wa.partial = ctx->dm_partial; wa.counter = ctx->dm_counter;
+        wa.item_base = ib; wa.n_work = nwork;
+        switch (nv) {
+          case 2: e = launch_ws<2>(ctx, wa); break;
+          case 3: e = launch_ws<3>(ctx, wa); break;
+          case 4: e = launch_ws<4>(ctx, wa); break;
+          case 5: e = launch_ws<5>(ctx, wa); break;
+          case 6: e = launch_ws<6>(ctx, wa); break;
+          case 7: e = launch_ws<7>(ctx, wa); break;
+          case 8: e = launch_ws<8>(ctx, wa); break;
+        }
+      } else if (use_default) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
         switch (nv) {
           case 2: e = launch_default<2>(ctx, a); break;

@@ -11,18 +11,23 @@ pytestmark = pytest.mark.gpu
 DEFAULT = [0.0, 0.5]
 
 
+KERNELS = {"ws": 0, "lane": 1, "general": 2}
+
+
 def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
-    ctx.demux_force_general(general)
+    """general: False/True (legacy switch) or one of KERNELS' names."""
+    which = KERNELS[general] if isinstance(general, str) else (2 if general else 0)
+    ctx.demux_select_kernel(which)
     try:
         out, grid = ctx.demux_run(s.plp, gp, has_gp, alphas, dp, want_grid=True)
     finally:
-        ctx.demux_force_general(False)
+        ctx.demux_select_kernel(0)
     ref, rgrid = orc.demux(s.plp, gp, has_gp, alphas, dp, want_grid=True, n_threads=8)
     return out, grid, ref, rgrid
 
 
-@pytest.mark.parametrize("nv", [2, 3, 4, 5, 8])
-@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("nv", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("general", ["ws", "lane", "general"])
 def test_default_grid_parity(ctx, nv, general):
     s = synth.make_pileup(C=300, nv=nv, V=2000, kbar=250, seed=100 + nv)
     gp = synth.gt_to_gp(s.geno)
@@ -66,7 +71,7 @@ def test_missing_genotypes_and_other_alleles(ctx):
     gp = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 5)).astype(np.float32).astype(np.float64)
     has = (rng.random(s.plp.n_snps) > 0.3).astype(np.uint8)
     s.plp.read_allele[rng.random(s.plp.n_reads) < 0.2] = 2
-    for general in (False, True):
+    for general in ("ws", "lane", "general"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, has, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT)
 
@@ -91,15 +96,17 @@ def test_deep_pairs_and_empty_cells(ctx):
     geno = rng.integers(0, 3, (nv, V)).astype(np.int8)
     gp = synth.gt_to_gp(geno)
     s = synth.Synth(plp, geno, plp.snp_af, None, None, 9)
-    for general in (False, True):
+    for general in ("ws", "lane", "general"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.3)
 
 
-def test_sharding_is_bit_identical(ctx):
+@pytest.mark.parametrize("kernel", ["ws", "lane"])
+def test_sharding_is_bit_identical(ctx, kernel):
     """barcode shards reproduce the unsharded records bit for bit; so do partial-grid batches."""
     s = synth.make_pileup(C=400, nv=8, V=3000, kbar=300, seed=77)
     gp = synth.gt_to_gp(s.geno)
+    ctx.demux_select_kernel(KERNELS[kernel])
     full = ctx.demux_run(s.plp, gp, None, DEFAULT)
     parts = [ctx.demux_run(s.plp.slice_cells(a, b), gp, None, DEFAULT) for a, b in ((0, 130), (130, 131), (131, 400))]
     assert np.concatenate(parts).tobytes() == full.tobytes()
@@ -111,6 +118,7 @@ def test_sharding_is_bit_identical(ctx):
         sub = ctx.demux_fetch()
     finally:
         ctx.set_partial_budget(1 << 30)
+        ctx.demux_select_kernel(0)
     assert sub.tobytes() == full[50:333].tobytes()
 
 
@@ -146,3 +154,13 @@ def test_errors(ctx):
     bad.read_qual[0] = 99
     with pytest.raises(PsclError):
         ctx.demux_run(bad, gp, None, DEFAULT)
+
+
+@pytest.mark.parametrize("kernel", ["ws", "lane"])
+def test_cells_larger_than_one_work_item(ctx, kernel):
+    """cells with > 2048 pairs are cut into several work items whose partial grids are summed in item order."""
+    s = synth.make_pileup(C=24, nv=8, V=30000, kbar=5000, seed=88)
+    assert np.diff(s.plp.cell_ptr).max() > 4096
+    gp = synth.gt_to_gp(s.geno)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, kernel)
+    check_demux_parity(out, grid, ref, rgrid, DEFAULT)
