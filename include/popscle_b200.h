@@ -240,9 +240,9 @@ int pscl_set_stream(pscl_ctx* ctx, void* cuda_stream);
 int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes);
 /* Route every alpha grid through the general demuxlet kernel (parity tests of that kernel). */
 int pscl_demux_force_general(pscl_ctx* ctx, int enable);
-/* Kernel used for the default alpha grid {0, 0.5} with <= 8 samples: 0 = automatic (the
- * warp-specialised k_demux_ws), 1 = k_demux_default (lane-per-pair baseline), 2 = k_demux_general.
- * All three are parity-tested against the same oracle. */
+/* Kernel used for the default alpha grid {0, 0.5} with <= 8 samples: 0 = automatic (currently 1),
+ * 1 = k_demux_default (lane per pair), 2 = k_demux_general, 3 = k_demux_cls (class-split records,
+ * TMA packet ring).  All are parity-tested against the same oracle. */
 int pscl_demux_select_kernel(pscl_ctx* ctx, int which);
 
 #ifdef __cplusplus

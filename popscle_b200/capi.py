@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpopscle_b200.so")
+LIB_PATH = os.environ.get("PSCL_LIB_PATH") or os.path.join(_HERE, "libpopscle_b200.so")  # override: A/B builds of the same sources
 
 PSCL_OK = 0
 PSCL_SNG, PSCL_DBL, PSCL_AMB = 0, 1, 2
@@ -281,7 +281,7 @@ class Context:
         self._chk(self.lib.pscl_demux_force_general(self.h, int(enable)))
 
     def demux_select_kernel(self, which: int):
-        """0 = auto (k_demux_ws), 1 = k_demux_default, 2 = k_demux_general (default alpha grid only)."""
+        """0 = auto, 1 = k_demux_default, 2 = k_demux_general, 3 = k_demux_cls (default alpha grid only)."""
         self._chk(self.lib.pscl_demux_select_kernel(self.h, int(which)))
 
     def demux_score(self, dplp: "DevicePileup", alphas, doublet_prior: float = 0.5, cell_begin: int = 0,

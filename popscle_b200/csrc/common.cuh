@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -38,11 +39,11 @@ struct pscl_plp {
   uint32_t* snp_pair = nullptr;  // [P] pair ids, ascending cell id inside one SNP
   int32_t* pair_cell = nullptr;  // [P]
   void* scratch_h2d = nullptr;   // int64 staging for pair_read_ptr
-  // demuxlet class streams for k_demux_ws (built lazily, demux_ws.inl): 8-byte records, class S
+  // demuxlet class streams for k_demux_cls (built lazily, demux_cls.inl): 8-byte records, class S
   // (<= 1 usable base-call) first, then M (2-3), then D (> 3), inside each cell's pair range
-  uint2* dmx_rec = nullptr;          // [P]
+  unsigned char* dmx_pkt = nullptr;  // [n_pkt][272] batch packets: 16-byte header + 32 records (k_dmx_pack)
   double* dmx_deep = nullptr;        // [n_deep][6] folded factors of the pairs with > 3 usable base-calls
-  uint4* dmx_desc_nat = nullptr;     // [n_items] {begin, end, first M, first D}, natural item order
+  uint4* dmx_desc_nat = nullptr;     // [n_items] {first packet, end packet, item, -}, natural item order
   uint4* dmx_desc_sorted = nullptr;  // [n_items] the same in item_order
 };
 
@@ -62,9 +63,9 @@ struct pscl_ctx {
   int32_t nv = 0, geno_V = 0;
   double* gp = nullptr;       // [V][nv][3]
   uint8_t* has_gp = nullptr;  // [V] or null (= all)
-  double* gpM = nullptr;      // [V][(3nv+1)&~1] 16-B padded genotype rows (k_demux_ws, built lazily)
+  double* gpM = nullptr;      // [V][(3nv+1)&~1] 16-B padded genotype rows (k_demux_cls, built lazily)
   double* gpS = nullptr;      // [V][nv][2] (S_j, M_j) moments of the rows
-  int demux_kernel = 0;       // 0 auto (k_demux_ws), 1 k_demux_default, 2 k_demux_general
+  int demux_kernel = 0;       // 0 auto (= 1), 1 k_demux_default, 2 k_demux_general, 3 k_demux_cls
   bool keep_grid = false, force_general = false, dm_single_batch = true;
   int32_t dm_cell_begin = 0, dm_cell_end = 0, dm_nalpha = 0;
   void* dm_cells = nullptr;   // pscl_demux_cell[cells]

@@ -37,6 +37,9 @@
 #define PSCL_FOLD_ROW 6  /* 5 factors padded to 48 B */
 #define PSCL_FOLD_ONES (2 * 64)
 
+// max of positive, non-NaN doubles: DSETP + 2 SEL instead of fmax()'s NaN-aware sequence
+__device__ __forceinline__ double dmx_pmax(double x, double y) { return x > y ? x : y; }
+
 template <int NV>
 struct DefaultCfg {
   static constexpr int ND = NV * (NV - 1) / 2;            // doublet accumulators (k < j)
@@ -167,14 +170,14 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
           const double* t = s_tab + (uint32_t)a.rd_aq[r0 + r] * PSCL_FOLD_ROW;
           f0 *= t[0]; f1 *= t[1]; f2 *= t[2]; f3 *= t[3]; f4 *= t[4];
           if ((r & 7u) == 7u) {  // deep pileups: rescale by the running max like :692-699
-            const double ri = 1.0 / fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
+            const double ri = 1.0 / dmx_pmax(dmx_pmax(dmx_pmax(f0, f1), dmx_pmax(f2, f3)), f4);
             f0 *= ri; f1 *= ri; f2 *= ri; f3 *= ri; f4 *= ri;
           }
         }
         // ---- D2 (:704-725) without the division: pG = (f/mx + 1e-10)/(1+1e-10) = h/(mx*(1+1e-10))
         // with h = f + 1e-10*mx; the common factor mx is accumulated once per pair (acc[E_MX]) and
         // (1+1e-10)^n_has is applied at the end.
-        const double mx = fmax(fmax(fmax(f0, f1), fmax(f2, f3)), f4);
+        const double mx = dmx_pmax(dmx_pmax(dmx_pmax(f0, f1), dmx_pmax(f2, f3)), f4);
         const double h0 = fma(1e-10, mx, f0), h1 = fma(1e-10, mx, f1), h2 = fma(1e-10, mx, f2),
                      h3 = fma(1e-10, mx, f3), h4 = fma(1e-10, mx, f4);
         acc[E_MX] *= mx;
@@ -563,7 +566,7 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
   a.cells[a.out_base + blockIdx.x] = o;
 }
 
-#include "demux_ws.inl"
+#include "demux_cls.inl"
 
 // ------------------------------------------------------------------------------------------------
 // host API
@@ -602,7 +605,7 @@ extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
   return PSCL_OK;
 }
 extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 2) return PSCL_EINVAL;
+  if (!ctx || which < 0 || which > 3) return PSCL_EINVAL;
   ctx->demux_kernel = which;
   return PSCL_OK;
 }
@@ -650,7 +653,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
 
   const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && na == 2 && h_alpha[0] == 0.0 &&
                            h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
-  const bool use_ws = use_default && ctx->demux_kernel == 0;
+  const bool use_ws = use_default && ctx->demux_kernel == 3;
   if (use_ws) {
     if ((rc = dmx_build_classes(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
     if ((rc = dmx_build_geno_tables(ctx)) != PSCL_OK) return rc;
@@ -681,22 +684,21 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
       cudaError_t e = cudaSuccess;
       if (use_ws) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
-        WsArgs wa;
-        wa.rec = plp->dmx_rec; wa.deep = plp->dmx_deep;
+        ClsArgs wa;
+        wa.pkt = plp->dmx_pkt; wa.deep = plp->dmx_deep;
         wa.gpM = ctx->gpM; wa.gpS = ctx->gpS; wa.fold_tab = ctx->fold_tab;
         const bool whole = (ib == 0 && ie == plp->n_items);
         wa.desc = whole ? plp->dmx_desc_sorted : plp->dmx_desc_nat + ib;
-        wa.desc_item = whole ? plp->item_order : nullptr;
         wa.partial = ctx->dm_partial; wa.counter = ctx->dm_counter;
-        wa.item_base = ib; wa.n_work = nwork;
+        wa.item_base = ib; wa.n_work = nwork; wa.n_snps = ctx->geno_V;
         switch (nv) {
-          case 2: e = launch_ws<2>(ctx, wa); break;
-          case 3: e = launch_ws<3>(ctx, wa); break;
-          case 4: e = launch_ws<4>(ctx, wa); break;
-          case 5: e = launch_ws<5>(ctx, wa); break;
-          case 6: e = launch_ws<6>(ctx, wa); break;
-          case 7: e = launch_ws<7>(ctx, wa); break;
-          case 8: e = launch_ws<8>(ctx, wa); break;
+          case 2: e = launch_cls<2>(ctx, wa); break;
+          case 3: e = launch_cls<3>(ctx, wa); break;
+          case 4: e = launch_cls<4>(ctx, wa); break;
+          case 5: e = launch_cls<5>(ctx, wa); break;
+          case 6: e = launch_cls<6>(ctx, wa); break;
+          case 7: e = launch_cls<7>(ctx, wa); break;
+          case 8: e = launch_cls<8>(ctx, wa); break;
         }
       } else if (use_default) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
