@@ -8,8 +8,12 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/popscle_b200.h"
 
@@ -79,6 +83,22 @@ struct pscl_ctx {
   float dm_ms_main = 0.f, dm_ms_total = 0.f;
   bool dm_timed = false;
   pscl_fmx_state* fmx = nullptr;
+};
+
+// ---- device memory: stream-ordered allocation out of the device's default memory pool -------------
+// pscl_demux_run / pscl_fmx_run build and drop a device image per call; with plain cudaMalloc/cudaFree
+// that cost 15-750 ms per call on the GPU box (traced with PSCL_TRACE=1), an order of magnitude more
+// than the copies and kernels together.  Every allocation of this library therefore goes through
+// cudaMallocAsync / cudaFreeAsync on the calling context's stream; pscl_create raises the pool's
+// release threshold so freed blocks stay mapped for the next call.  The two macros below route the
+// (many) existing call sites; PsclScope publishes the current context's stream to them.
+static thread_local cudaStream_t t_pscl_stream = nullptr;
+static inline cudaError_t pscl_pool_alloc(void** p, size_t n) { return cudaMallocAsync(p, n ? n : 16, t_pscl_stream); }
+static inline cudaError_t pscl_pool_free(void* p) { return p ? cudaFreeAsync(p, t_pscl_stream) : cudaSuccess; }
+#define cudaMalloc(p, n) pscl_pool_alloc((void**)(p), (n))
+#define cudaFree(p) pscl_pool_free((void*)(p))
+struct PsclScope {
+  explicit PsclScope(const pscl_ctx* c) { t_pscl_stream = c->stream; }
 };
 
 static inline int pscl_fail(pscl_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));

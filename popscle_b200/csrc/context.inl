@@ -33,6 +33,14 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   cudaEventCreate(&c->ev2);
+  {  // keep freed blocks mapped in the device's default pool (see common.cuh: device memory)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  PsclScope scope__(c);
   // PhredHelper.cpp:30 — same expression, same libm, evaluated on the host
   double tab[256];
   for (int i = 0; i < 256; ++i) tab[i] = (i > 1) ? pow(0.1, i * 0.1) : 0.75;
@@ -50,10 +58,10 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
       t[5] = 1.0;
     }
   if (cudaMalloc((void**)&c->fold_tab, sizeof(ftab)) != cudaSuccess ||
-      cudaMemcpy(c->fold_tab, ftab, sizeof(ftab), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpyAsync(c->fold_tab, ftab, sizeof(ftab), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
       cudaMalloc((void**)&c->phred_err, sizeof(tab)) != cudaSuccess ||
-      cudaMemcpy(c->phred_err, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMalloc((void**)&c->dm_counter, 64) != cudaSuccess) {
+      cudaMemcpyAsync(c->phred_err, tab, sizeof(tab), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+      cudaMalloc((void**)&c->dm_counter, 64) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
     delete c;
     return fail(PSCL_ENOMEM, "device allocation failed in pscl_create");
   }
@@ -65,6 +73,7 @@ static void fmx_state_free(pscl_ctx* ctx);
 
 extern "C" void pscl_destroy(pscl_ctx* ctx) {
   if (!ctx) return;
+  PsclScope scope__(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   fmx_state_free(ctx);
@@ -81,6 +90,11 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev2);
+  cudaStreamSynchronize(ctx->stream);
+  {  // hand the cached blocks back to the driver
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -89,6 +103,7 @@ extern "C" const char* pscl_last_error(const pscl_ctx* ctx) { return ctx ? ctx->
 extern "C" void* pscl_stream(pscl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int pscl_set_stream(pscl_ctx* ctx, void* stream) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t)stream;
@@ -97,6 +112,7 @@ extern "C" int pscl_set_stream(pscl_ctx* ctx, void* stream) {
 }
 extern "C" int pscl_sync(pscl_ctx* ctx) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PSCL_OK;
 }
@@ -125,7 +141,7 @@ __global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restric
 
 extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
   if (!p) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ctx) { t_pscl_stream = ctx->stream; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
   cudaFree(p->cell_ptr); cudaFree(p->pair_snp); cudaFree(p->pair_rd); cudaFree(p->rd_aq);
   cudaFree(p->snp_af); cudaFree(p->item_cell); cudaFree(p->item_pbeg);
   cudaFree(p->item_pend); cudaFree(p->item_order); cudaFree(p->cell_item_ptr); cudaFree(p->snp_ptr);
@@ -136,6 +152,7 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
 
 extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!h || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_plp_upload: NULL argument");
   *out = nullptr;
   const int32_t C = h->n_cells, V = h->n_snps;

@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t n_snps) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!geno || !geno->gp || geno->n_samples < 2 || n_snps < 0)
     return pscl_fail(ctx, PSCL_EINVAL,
                      "pscl_demux_set_geno: need gp and n_samples >= 2 (the reference divides by nv-1, "
@@ -596,11 +597,13 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
 
 extern "C" int pscl_demux_keep_grid(pscl_ctx* ctx, int enable) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   ctx->keep_grid = enable != 0;
   return PSCL_OK;
 }
 extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   ctx->force_general = enable != 0;
   return PSCL_OK;
 }
@@ -629,6 +632,7 @@ static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
 extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
                                 int32_t cell_begin, int32_t cell_end) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!plp || !opts || !opts->alphas) return pscl_fail(ctx, PSCL_EINVAL, "pscl_demux_score: NULL argument");
   if (!ctx->gp) return pscl_fail(ctx, PSCL_ESTATE, "pscl_demux_score: call pscl_demux_set_geno first");
   if (ctx->geno_V != plp->V) return pscl_fail(ctx, PSCL_EINVAL, "genotype table has %d SNPs, pileup %d", ctx->geno_V, plp->V);
@@ -756,6 +760,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
 
 extern "C" int pscl_demux_last_kernel_ms(pscl_ctx* ctx, float* ms_main, float* ms_total) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!ctx->dm_timed) return pscl_fail(ctx, PSCL_ESTATE, "no pscl_demux_score has run");
   PSCL_CUDA(ctx, cudaEventSynchronize(ctx->ev2));
   float t = 0.f, m = -1.f;
@@ -768,6 +773,7 @@ extern "C" int pscl_demux_last_kernel_ms(pscl_ctx* ctx, float* ms_main, float* m
 
 extern "C" int pscl_demux_fetch(pscl_ctx* ctx, pscl_demux_cell* out, double* llk_grid) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!ctx->dm_timed) return pscl_fail(ctx, PSCL_ESTATE, "pscl_demux_fetch before pscl_demux_score");
   const int ncell = ctx->dm_cell_end - ctx->dm_cell_begin;
   if (out)
@@ -784,18 +790,31 @@ extern "C" int pscl_demux_fetch(pscl_ctx* ctx, pscl_demux_cell* out, double* llk
 extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_geno* geno,
                               const pscl_demux_opts* opts, pscl_demux_cell* out, double* llk_grid) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!host || !geno || !opts || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_demux_run: NULL argument");
+  // PSCL_TRACE=1: wall-clock of every phase on stderr (each phase is drained first, so the sum is an upper bound)
+  static const bool trace = getenv("PSCL_TRACE") != nullptr;
+  auto now = [&]() { if (trace) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   pscl_plp* plp = nullptr;
   int rc = pscl_plp_upload(ctx, host, &plp);
   if (rc != PSCL_OK) return rc;
+  const auto t1 = now();
   rc = pscl_demux_set_geno(ctx, geno, host->n_snps);
+  const auto t2 = now();
   bool keep = ctx->keep_grid;
   if (rc == PSCL_OK && llk_grid) ctx->keep_grid = true;
   if (rc == PSCL_OK) rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);
+  const auto t3 = now();
   if (rc == PSCL_OK) rc = pscl_demux_fetch(ctx, out, llk_grid);
+  const auto t4 = now();
   ctx->keep_grid = keep;
   std::string err = ctx->err;
   pscl_plp_free(ctx, plp);
   ctx->err = err;
+  if (trace)
+    fprintf(stderr, "[pscl_demux_run] upload %.3f ms | set_geno %.3f | score %.3f | fetch %.3f | free %.3f\n", ms(t0, t1), ms(t1, t2),
+            ms(t2, t3), ms(t3, t4), ms(t4, now()));
   return rc;
 }

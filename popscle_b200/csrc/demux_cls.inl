@@ -38,7 +38,6 @@
 // pipeline, profiles/r02d_*) measured 0.80 ms.  k_demux_default therefore stays the default; this kernel
 // is selectable (pscl_demux_select_kernel(ctx, 3)) and parity-tested, and is the base for the next round.
 
-#include <cub/device/device_scan.cuh>
 
 #ifndef CLS_THREADS
 #define CLS_THREADS 256

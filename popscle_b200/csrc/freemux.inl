@@ -19,8 +19,6 @@
 // Data layout: stage 1 keeps the pair GLs twice — plane-major [9][P] in cell-major pair order (lane
 // per pair kernels read 9 coalesced streams) and record-major [P][9] in SNP-major order (the M-step
 // walks one SNP's cells as one contiguous block).
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #define PSCL_FMX_MAX_CLUSTERS 24
 #define PSCL_MIN_NORM_GL 1e-6 /* sc_drop_seq.h:14 */
@@ -716,6 +714,7 @@ static int fmx_build_csc(pscl_ctx* ctx, pscl_fmx_state* s) {
 
 extern "C" int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp* plp, const pscl_fmx_opts* o) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!plp || !o) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_init: NULL argument");
   if (o->n_clusters < 2 || o->n_clusters > PSCL_FMX_MAX_CLUSTERS)
     return pscl_fail(ctx, PSCL_EINVAL, "n_clusters must be in [2,%d] (the reference divides by nSamples-1, cmd_cram_freemux2.cpp:380)", PSCL_FMX_MAX_CLUSTERS);
@@ -757,6 +756,7 @@ extern "C" int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp* plp, const pscl_fmx_
 
 #define FMX_STATE(ctx, s)                                                        \
   if (!ctx) return PSCL_EINVAL;                                                  \
+  PsclScope scope__(ctx);                                                        \
   pscl_fmx_state* s = ctx->fmx;                                                  \
   if (!s) return pscl_fail(ctx, PSCL_ESTATE, "call pscl_fmx_init first");        \
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device))
@@ -988,6 +988,7 @@ extern "C" int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float* ms) {
 extern "C" int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts, const int32_t* init_clust,
                             pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, pscl_fmx_result* res) {
   if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
   if (!host || !opts || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_run: NULL argument");
   pscl_plp* plp = nullptr;
   int rc = pscl_plp_upload(ctx, host, &plp);
