@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSCL_ABI_VERSION 1
+#define PSCL_ABI_VERSION 2
 
 typedef enum pscl_status {
   PSCL_OK = 0,
@@ -64,6 +64,11 @@ typedef struct pscl_pileup {
   const uint8_t* read_qual;     /* [N]   phred base quality, 0..93                             */
   const double* snp_af;         /* [V]   AF column of .var.gz (freemuxlet prior); may be NULL
                                          for demuxlet                                          */
+  /* Compact alternatives (ABI 2; NULL = not given).  A host that builds them halves the bytes that
+   * cross PCIe per pileup (13 -> 5.3 B per pair + 2 -> 1 B per base-call); when one is given the
+   * wide array it replaces may be NULL. */
+  const uint32_t* pair_read_ptr32; /* [P+1] the same offsets as pair_read_ptr (n_reads < 2^32)  */
+  const uint8_t* read_aq;          /* [N]   allele << 6 | qual, qual <= 63                      */
 } pscl_pileup;
 
 /* Genotype table (replaces sc_snp_t::gps, sc_drop_seq.h:29-37, filled at
@@ -162,7 +167,8 @@ const char* pscl_last_error(const pscl_ctx* ctx);
 void* pscl_stream(pscl_ctx* ctx);
 int pscl_sync(pscl_ctx* ctx);
 
-/* ---- pileup upload: host CSR -> packed device image (1 B/read, 4+4 B/pair) ---- */
+/* ---- pileup upload: host CSR -> packed device image (1 B/read, 4+4 B/pair) ----
+ * Uses the compact arrays of pscl_pileup when present (no repacking kernels, fewer H2D bytes). */
 int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* host, pscl_plp** out);
 void pscl_plp_free(pscl_ctx* ctx, pscl_plp* plp);
 

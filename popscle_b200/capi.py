@@ -29,7 +29,8 @@ class PsclError(RuntimeError):
 class CPileup(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("n_snps", C.c_int32), ("n_pairs", C.c_int64), ("n_reads", C.c_int64),
                 ("cell_ptr", C.c_void_p), ("pair_snp", C.c_void_p), ("pair_read_ptr", C.c_void_p),
-                ("read_allele", C.c_void_p), ("read_qual", C.c_void_p), ("snp_af", C.c_void_p)]
+                ("read_allele", C.c_void_p), ("read_qual", C.c_void_p), ("snp_af", C.c_void_p),
+                ("pair_read_ptr32", C.c_void_p), ("read_aq", C.c_void_p)]
 
 
 class CGeno(C.Structure):
@@ -109,7 +110,18 @@ class Pileup:
     def n_reads(self) -> int:
         return int(self.read_allele.shape[0])
 
-    def c_struct(self, cls=CPileup):
+    def compact(self):
+        """(pair_read_ptr32, read_aq): the compact arrays of ABI 2 (uint32 offsets, allele<<6|qual), cached."""
+        c = getattr(self, "_compact", None)
+        if c is None:
+            if self.n_reads >= 1 << 32 or (self.read_qual > 63).any() or (self.read_allele > 2).any():
+                raise PsclError(-1, "compact pileup needs n_reads < 2^32, qual <= 63, allele <= 2")
+            c = (np.ascontiguousarray(self.pair_read_ptr, dtype=np.uint32),
+                 np.ascontiguousarray((self.read_allele << 6) | self.read_qual, dtype=np.uint8))
+            self._compact = c
+        return c
+
+    def c_struct(self, cls=CPileup, compact=False):
         s = cls()
         s.n_cells, s.n_snps, s.n_pairs, s.n_reads = self.n_cells, self.n_snps, self.n_pairs, self.n_reads
         s.cell_ptr = self.cell_ptr.ctypes.data
@@ -118,6 +130,10 @@ class Pileup:
         s.read_allele = self.read_allele.ctypes.data
         s.read_qual = self.read_qual.ctypes.data
         s.snp_af = self.snp_af.ctypes.data if self.snp_af is not None else None
+        if compact:  # only the compact arrays cross the ABI
+            p32, aq = self.compact()
+            s.pair_read_ptr32, s.read_aq = p32.ctypes.data, aq.ctypes.data
+            s.pair_read_ptr = s.read_allele = s.read_qual = None
         return s
 
     def slice_cells(self, c0: int, c1: int) -> "Pileup":
@@ -252,8 +268,8 @@ class Context:
         self._chk(self.lib.pscl_set_partial_budget(self.h, nbytes))
 
     # ---- pileup ----
-    def upload(self, plp: Pileup) -> "DevicePileup":
-        cs = plp.c_struct()
+    def upload(self, plp: Pileup, compact: bool = False) -> "DevicePileup":
+        cs = plp.c_struct(compact=compact)
         out = C.c_void_p()
         self._chk(self.lib.pscl_plp_upload(self.h, C.byref(cs), C.byref(out)))
         return DevicePileup(self, out, plp.n_cells, plp.n_snps, plp.n_pairs, plp.n_reads)
@@ -305,11 +321,11 @@ class Context:
         return a.value, b.value
 
     def demux_run(self, plp: Pileup, gp: np.ndarray, has_gp, alphas, doublet_prior: float = 0.5,
-                  want_grid: bool = False):
+                  want_grid: bool = False, compact: bool = False):
         """The one-call path of the CLI host: host buffers in, per-cell records out."""
         gp = np.ascontiguousarray(gp, dtype=np.float64)
         al = np.ascontiguousarray(alphas, dtype=np.float64)
-        cs = plp.c_struct()
+        cs = plp.c_struct(compact=compact)
         g = CGeno()
         g.n_samples = gp.shape[1]
         g.gp = gp.ctypes.data
@@ -331,8 +347,9 @@ class Context:
         return CFmxOpts(n_clusters, doublet_prior, geno_error, max_iter, int(early_stop), frac_init_clust,
                         singlet_score_thres, int(mode_old))
 
-    def fmx_run(self, plp: Pileup, opts: CFmxOpts, init_clust: np.ndarray | None = None, want_clusters=False):
-        cs = plp.c_struct()
+    def fmx_run(self, plp: Pileup, opts: CFmxOpts, init_clust: np.ndarray | None = None, want_clusters=False,
+                compact: bool = False):
+        cs = plp.c_struct(compact=compact)
         out = np.zeros(plp.n_cells, dtype=FMX_CELL_DTYPE)
         res = CFmxResult()
         ic = None

@@ -133,6 +133,22 @@ __global__ void k_pack_reads(const uint8_t* __restrict__ al, const uint8_t* __re
   aq[i] = (uint8_t)((a << 6) | (b & 63));
 }
 
+// already packed reads: only the validity check (allele code 3 does not exist)
+__global__ void k_check_reads(const uint8_t* __restrict__ aq, int64_t n, int* bad) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i >= n) return;
+  bool b = false;
+  if (i + 16 <= n && (reinterpret_cast<uintptr_t>(aq + i) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(aq + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b |= ((w[k] & (w[k] >> 1)) & 0x40404040u) != 0u;  // bits 7 and 6 both set
+  } else {
+    for (int64_t k = i; k < n && k < i + 16; ++k) b |= (aq[k] >> 6) == 3;
+  }
+  if (b) atomicExch(bad, 1);
+}
+
 // int64 read offsets -> uint32 (device images hold < 2^32 reads)
 __global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,7 +174,8 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   const int32_t C = h->n_cells, V = h->n_snps;
   const int64_t P = h->n_pairs, N = h->n_reads;
   if (C < 0 || V < 0 || P < 0 || N < 0) return pscl_fail(ctx, PSCL_EINVAL, "negative size in pscl_pileup");
-  if (!h->cell_ptr || (P > 0 && (!h->pair_snp || !h->pair_read_ptr)) || (N > 0 && (!h->read_allele || !h->read_qual)))
+  const bool ptr32 = h->pair_read_ptr32 != nullptr, packed = h->read_aq != nullptr;
+  if (!h->cell_ptr || (P > 0 && (!h->pair_snp || (!h->pair_read_ptr && !ptr32))) || (N > 0 && !packed && (!h->read_allele || !h->read_qual)))
     return pscl_fail(ctx, PSCL_EINVAL, "pscl_pileup has a NULL array");
   if (N >= ((int64_t)1 << 32) || P >= ((int64_t)1 << 32))
     return pscl_fail(ctx, PSCL_EINVAL, "a device pileup image holds < 2^32 pairs/reads; shard the barcodes or SNPs");
@@ -166,7 +183,7 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
     return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr must run from 0 to n_pairs");
   for (int32_t c = 0; c < C; ++c)
     if (h->cell_ptr[c + 1] < h->cell_ptr[c]) return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr not monotone at cell %d", c);
-  if (P > 0 && (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N))
+  if (P > 0 && (ptr32 ? (h->pair_read_ptr32[0] != 0 || (int64_t)h->pair_read_ptr32[P] != N) : (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N)))
     return pscl_fail(ctx, PSCL_EINVAL, "pair_read_ptr must run from 0 to n_reads");
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
   pscl_plp* p = new pscl_plp();
@@ -198,19 +215,25 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
     return e;
   };
   cudaError_t e = cudaSuccess;
-#define UP(field, src, bytes) if (e == cudaSuccess) e = up((void**)&p->field, src, bytes)
+#define UP(field, src, bytes) do { if (e == cudaSuccess) e = up((void**)&p->field, src, bytes); } while (0)
   UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
   UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
-  UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1));
+  if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
+  else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
   uint8_t *d_al = nullptr, *d_q = nullptr;
   int* d_bad = nullptr;
-  if (e == cudaSuccess) e = up((void**)&d_al, h->read_allele, (size_t)N);
-  if (e == cudaSuccess) e = up((void**)&d_q, h->read_qual, (size_t)N);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
+  if (packed) {
+    UP(rd_aq, h->read_aq, (size_t)N);
+  } else {
+    if (e == cudaSuccess) e = up((void**)&d_al, h->read_allele, (size_t)N);
+    if (e == cudaSuccess) e = up((void**)&d_q, h->read_qual, (size_t)N);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
+  }
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
   if (e == cudaSuccess && N > 0) {
-    k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, d_bad);
+    if (packed) k_check_reads<<<(unsigned)((N + 4095) / 4096), 256, 0, ctx->stream>>>(p->rd_aq, N, d_bad);
+    else k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, d_bad);
     ctx->launches++;
     e = cudaGetLastError();
   }
@@ -221,8 +244,8 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   UP(item_order, order.data(), sizeof(int32_t) * p->n_items);
   UP(cell_item_ptr, p->h_cell_item_ptr.data(), sizeof(int32_t) * (C + 1));
 #undef UP
-  if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
-  if (e == cudaSuccess && P > 0) {
+  if (e == cudaSuccess && !ptr32) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
+  if (e == cudaSuccess && P > 0 && !ptr32) {
     k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1);
     ctx->launches++;
     e = cudaGetLastError();

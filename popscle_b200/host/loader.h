@@ -43,8 +43,25 @@ struct Loaded {
   std::vector<double> gp;       // [V][nv][3]
   std::vector<uint8_t> has_gp;  // [V]
 
+  // compact arrays of ABI 2 (filled by view() on first use): 32-bit read offsets, allele<<6|qual
+  mutable std::vector<uint32_t> pair_read_ptr32;
+  mutable std::vector<uint8_t> read_aq;
+
   pscl_pileup view() const {
     pscl_pileup p;
+    p.pair_read_ptr32 = nullptr; p.read_aq = nullptr;
+    if (read_allele.size() < (1ull << 32)) {  // halves the bytes pscl_plp_upload sends over PCIe
+      if (pair_read_ptr32.size() != pair_read_ptr.size()) pair_read_ptr32.assign(pair_read_ptr.begin(), pair_read_ptr.end());
+      bool ok = true;
+      if (read_aq.size() != read_allele.size()) {
+        read_aq.resize(read_allele.size());
+        for (size_t i = 0; i < read_aq.size(); ++i) {
+          ok = ok && read_allele[i] <= 2 && read_qual[i] <= 63;
+          read_aq[i] = (uint8_t)((read_allele[i] << 6) | (read_qual[i] & 63));
+        }
+      }
+      if (ok) { p.pair_read_ptr32 = pair_read_ptr32.data(); p.read_aq = read_aq.data(); }
+    }
     p.n_cells = n_cells; p.n_snps = n_snps;
     p.n_pairs = (int64_t)pair_snp.size(); p.n_reads = (int64_t)read_allele.size();
     p.cell_ptr = cell_ptr.data(); p.pair_snp = pair_snp.data(); p.pair_read_ptr = pair_read_ptr.data();

@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 from popscle_b200 import capi
@@ -39,7 +40,7 @@ def test_library_is_sm100a_only(built):
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "popscle_b200.h"\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 ? 0 : 1; }\n')
+    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==88 && offsetof(pscl_pileup, read_aq)==80 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
@@ -52,7 +53,7 @@ def test_no_cpu_fallback(built):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = capi.load_library()
-    assert lib.pscl_abi_version() == 1
+    assert lib.pscl_abi_version() == 2
     h = ctypes.c_void_p()
     err = ctypes.create_string_buffer(256)
     rc = lib.pscl_create(0, ctypes.byref(h), err, len(err))
@@ -79,3 +80,18 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"oracle_py|popscle_oracle|liboracle|oracle/_ref", t):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_pileup_struct_matches_the_ctypes_mirror():
+    """ABI 2: the compact arrays sit behind the wide ones; the ctypes mirror has the same layout."""
+    import ctypes as C
+    from popscle_b200 import capi
+    assert C.sizeof(capi.CPileup) == 88
+    assert capi.CPileup.pair_read_ptr32.offset == 72 and capi.CPileup.read_aq.offset == 80
+    from popscle_b200 import synth
+    s = synth.make_pileup(C=5, nv=2, V=50, kbar=50, seed=3)
+    p32, aq = s.plp.compact()
+    assert p32.dtype == np.uint32 and (p32 == s.plp.pair_read_ptr).all()
+    assert ((aq >> 6) == s.plp.read_allele).all() and ((aq & 63) == s.plp.read_qual).all()
+    cs = s.plp.c_struct(compact=True)
+    assert cs.pair_read_ptr is None and cs.read_allele is None and cs.read_aq == aq.ctypes.data

@@ -164,3 +164,21 @@ def test_cells_larger_than_one_work_item(ctx, kernel):
     gp = synth.gt_to_gp(s.geno)
     out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, kernel)
     check_demux_parity(out, grid, ref, rgrid, DEFAULT)
+
+
+def test_compact_pileup_inputs_are_equivalent(ctx):
+    """ABI 2 compact host arrays (u32 read offsets, allele<<6|qual) give bit-identical records, for demuxlet and
+    freemuxlet; a byte with allele code 3 is rejected."""
+    from popscle_b200 import PsclError
+    s = synth.make_pileup(C=150, nv=6, V=1500, kbar=200, seed=4242)
+    gp = synth.gt_to_gp(s.geno)
+    a = ctx.demux_run(s.plp, gp, None, DEFAULT)
+    b = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=True)
+    assert a.tobytes() == b.tobytes()
+    fa = ctx.fmx_run(s.plp, ctx.fmx_opts(3))[0]
+    fb = ctx.fmx_run(s.plp, ctx.fmx_opts(3), compact=True)[0]
+    assert fa.tobytes() == fb.tobytes()
+    bad = synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1).plp
+    bad.compact()[1][5] |= 0xC0
+    with pytest.raises(PsclError):
+        ctx.demux_run(bad, synth.gt_to_gp(synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1).geno), None, DEFAULT, compact=True)
