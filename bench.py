@@ -36,7 +36,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="demux", choices=["demux", "freemux"])
+    ap.add_argument("--workload", default="demux", choices=["demux", "freemux", "demux64"],
+                    help="demux = configs[1] (the metric's config); freemux = configs[2]; demux64 = configs[3]'s shape "
+                         "(64 samples, 21-point alpha grid, 1M SNPs) on --cells cells per GPU (default 256)")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,6 +296,82 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_demux64(args, rank, local_rank, world):
+    """configs[3]'s shape (50k cells x 64 samples x 1M SNPs, 21-point alpha grid, barcodes sharded over the GPUs) on
+    `--cells` cells per GPU: the general kernel is FP64-bound here (~626 kflop per pair against ~800 B),
+    so the line carries an `fp64` object beside the (tiny) HBM roofline fraction."""
+    import torch
+    import torch.distributed as dist
+    from popscle_b200 import Context, _build, synth
+    _build.build_cuda()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    c4 = synth.CONFIGS[4]
+    cells = args.cells or 256
+    s = synth.make_pileup(cells, c4["nv"], c4["V"], c4["kbar"], 20260105 + 1000 * rank)
+    gp = synth.gt_to_gp(s.geno)
+    alphas = list(c4["alphas"])
+    plp, nv, na = s.plp, c4["nv"], len(alphas)
+    stream = torch.cuda.current_stream()
+    ctx = Context(local_rank, stream=stream.cuda_stream)
+    dplp = ctx.upload(plp, compact=True)
+    ctx.demux_set_geno(gp, None, plp.n_snps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        ctx.demux_score(dplp, alphas, 0.5)
+    barrier()
+    sampler = make_sampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    barrier()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        ctx.demux_score(dplp, alphas, 0.5)
+        b.record(stream)
+        b.synchronize()
+    barrier()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    n = torch.tensor([plp.n_reads, plp.n_pairs], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n)
+    t_ms = float(t.item())
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        step_s = t_ms * 1e-3 / args.steps
+        abytes = algorithmic_bytes_demux(plp, nv)
+        nrd_mean = plp.n_reads / max(plp.n_pairs, 1)
+        flops = plp.n_pairs * (18.0 * nv * na + 7.0 * nv * nv * na + 36.0 * nrd_mean * na)  # SURVEY.md 8(d), minimal formulation
+        line = {"metric": METRIC, "value": float(n[0].item()) / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "demuxlet configs[3] shape: 64 samples x 1M SNPs, 21-point alpha grid, barcodes sharded",
+                           "cells_per_gpu": plp.n_cells, "samples": nv, "snps": plp.n_snps, "alphas": na, "pairs_per_gpu": plp.n_pairs,
+                           "base_calls_per_gpu": plp.n_reads, "l2": "flushed between timed steps (256 MiB memset, untimed)"},
+                "roofline": {"bound": "hbm", "achieved": abytes / step_s / 1e9, "peak": peak, "unit": "GB/s", "frac": abytes / step_s / 1e9 / peak,
+                             "traffic": None, "kernel": "k_demux_general / k_demux_poly", "algorithmic_bytes": abytes, "peak_source": peak_src},
+                "fp64": {"algorithmic_flops": flops, "achieved_tflops": flops / step_s / 1e12, "peak_tflops": 37.2,
+                         "frac": flops / step_s / 1e12 / 37.2, "peak_source": "148 SMs x 64 FP64 FMA lanes x 2 x 1.965 GHz"},
+                "pairs_per_s": float(n[1].item()) / step_s, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -305,6 +383,9 @@ def main():
     if args.workload == "freemux":
         from popscle_b200 import bench_fmx
         bench_fmx.main(args, rank, local_rank, world)
+        return
+    if args.workload == "demux64":
+        run_demux64(args, rank, local_rank, world)
         return
 
     import torch

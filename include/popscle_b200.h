@@ -246,9 +246,11 @@ int pscl_set_stream(pscl_ctx* ctx, void* cuda_stream);
 int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes);
 /* Route every alpha grid through the general demuxlet kernel (parity tests of that kernel). */
 int pscl_demux_force_general(pscl_ctx* ctx, int enable);
-/* Kernel used for the default alpha grid {0, 0.5} with <= 8 samples: 0 = automatic (currently 1),
- * 1 = k_demux_default (lane per pair), 2 = k_demux_general, 3 = k_demux_cls (class-split records,
- * TMA packet ring).  All are parity-tested against the same oracle. */
+/* Accumulation kernel: 0 = automatic (k_demux_default for the alpha grid {0, 0.5} with <= 8 samples,
+ * k_demux_poly otherwise), 1 = k_demux_default (lane per pair; needs that default shape),
+ * 2 = k_demux_general (9-FMA baseline, any shape), 3 = k_demux_cls (class-split records, TMA packet
+ * ring; default shape), 4 = k_demux_poly (polynomial in alpha, any shape).  All are parity-tested
+ * against the same oracle. */
 int pscl_demux_select_kernel(pscl_ctx* ctx, int which);
 
 #ifdef __cplusplus

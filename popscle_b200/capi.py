@@ -297,7 +297,7 @@ class Context:
         self._chk(self.lib.pscl_demux_force_general(self.h, int(enable)))
 
     def demux_select_kernel(self, which: int):
-        """0 = auto, 1 = k_demux_default, 2 = k_demux_general, 3 = k_demux_cls (default alpha grid only)."""
+        """0 = auto, 1 = k_demux_default, 2 = k_demux_general, 3 = k_demux_cls, 4 = k_demux_poly (see popscle_b200.h)."""
         self._chk(self.lib.pscl_demux_select_kernel(self.h, int(which)))
 
     def demux_score(self, dplp: "DevicePileup", alphas, doublet_prior: float = 0.5, cell_begin: int = 0,

@@ -43,6 +43,9 @@ struct pscl_plp {
   uint32_t* snp_pair = nullptr;  // [P] pair ids, ascending cell id inside one SNP
   int32_t* pair_cell = nullptr;  // [P]
   void* scratch_h2d = nullptr;   // int64 staging for pair_read_ptr
+  // class-ordered record stream of k_demux_poly (built lazily, demux_poly.inl)
+  uint2* ply_rec = nullptr;      // [P]
+  uint4* ply_rng = nullptr;      // [n_items] {begin, first M, first D, end}
   // demuxlet class streams for k_demux_cls (built lazily, demux_cls.inl): 8-byte records, class S
   // (<= 1 usable base-call) first, then M (2-3), then D (> 3), inside each cell's pair range
   unsigned char* dmx_pkt = nullptr;  // [n_pkt][272] batch packets: 16-byte header + 32 records (k_dmx_pack)
@@ -69,7 +72,7 @@ struct pscl_ctx {
   uint8_t* has_gp = nullptr;  // [V] or null (= all)
   double* gpM = nullptr;      // [V][(3nv+1)&~1] 16-B padded genotype rows (k_demux_cls, built lazily)
   double* gpS = nullptr;      // [V][nv][2] (S_j, M_j) moments of the rows
-  int demux_kernel = 0;       // 0 auto (= 1), 1 k_demux_default, 2 k_demux_general, 3 k_demux_cls
+  int demux_kernel = 0;       // 0 auto, 1 k_demux_default, 2 k_demux_general, 3 k_demux_cls, 4 k_demux_poly
   bool keep_grid = false, force_general = false, dm_single_batch = true;
   int32_t dm_cell_begin = 0, dm_cell_end = 0, dm_nalpha = 0;
   void* dm_cells = nullptr;   // pscl_demux_cell[cells]

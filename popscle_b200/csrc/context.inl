@@ -162,6 +162,7 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
   cudaFree(p->snp_af); cudaFree(p->item_cell); cudaFree(p->item_pbeg);
   cudaFree(p->item_pend); cudaFree(p->item_order); cudaFree(p->cell_item_ptr); cudaFree(p->snp_ptr);
   cudaFree(p->snp_pair); cudaFree(p->pair_cell); cudaFree(p->scratch_h2d);
+  cudaFree(p->ply_rec); cudaFree(p->ply_rng);
   cudaFree(p->dmx_pkt); cudaFree(p->dmx_deep); cudaFree(p->dmx_desc_nat); cudaFree(p->dmx_desc_sorted);
   delete p;
 }

@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
 }
 
 #include "demux_cls.inl"
+#include "demux_poly.inl"
 
 // ------------------------------------------------------------------------------------------------
 // host API
@@ -608,7 +609,7 @@ extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
   return PSCL_OK;
 }
 extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 3) return PSCL_EINVAL;
+  if (!ctx || which < 0 || which > 4) return PSCL_EINVAL;
   ctx->demux_kernel = which;
   return PSCL_OK;
 }
@@ -655,8 +656,16 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
   if (ctx->keep_grid && (rc = pscl_reserve(ctx, &ctx->dm_grid, &ctx->dm_grid_cap, sizeof(double) * G * ncell)) != PSCL_OK) return rc;
   ctx->dm_cell_begin = cell_begin; ctx->dm_cell_end = cell_end; ctx->dm_nalpha = na;
 
-  const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && na == 2 && h_alpha[0] == 0.0 &&
+  const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && ctx->demux_kernel != 4 && na == 2 && h_alpha[0] == 0.0 &&
                            h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
+  // every other shape: the polynomial kernel unless k_demux_general was asked for
+  const bool use_poly = !use_default && !ctx->force_general && ctx->demux_kernel != 2;
+  if (use_poly) {
+    if ((rc = ply_build_stream(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
+    double h_gamma[PSCL_MAX_ALPHA] = {0};
+    for (int i = 0; i < na; ++i) h_gamma[i] = 0.5 * h_alpha[i];
+    PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gamma, h_gamma, sizeof(h_gamma), 0, cudaMemcpyHostToDevice, ctx->stream));
+  }
   const bool use_ws = use_default && ctx->demux_kernel == 3;
   if (use_ws) {
     if ((rc = dmx_build_classes(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
@@ -715,6 +724,13 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
           case 7: e = launch_default<7>(ctx, a); break;
           case 8: e = launch_default<8>(ctx, a); break;
         }
+      } else if (use_poly) {
+        PolyArgs pa;
+        pa.rec = plp->ply_rec; pa.rng = plp->ply_rng;
+        pa.order = (ib == 0 && ie == plp->n_items) ? plp->item_order : nullptr;
+        pa.gp = ctx->gp; pa.has_gp = ctx->has_gp; pa.pair_rd = plp->pair_rd; pa.rd_aq = plp->rd_aq; pa.phred_err = ctx->phred_err;
+        pa.partial = ctx->dm_partial; pa.item_base = ib; pa.nv = nv; pa.na = na; pa.tiles = (nv + PLY_T - 1) / PLY_T;
+        e = launch_poly(ctx, pa, nwork);
       } else {
         constexpr int EPT = 8;
         GeneralArgs ga;

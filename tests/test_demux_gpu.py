@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 DEFAULT = [0.0, 0.5]
 
 
-KERNELS = {"auto": 0, "lane": 1, "general": 2, "cls": 3}
+KERNELS = {"auto": 0, "lane": 1, "general": 2, "cls": 3, "poly": 4}
 
 
 def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
@@ -27,7 +27,7 @@ def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
 
 
 @pytest.mark.parametrize("nv", [2, 3, 4, 5, 6, 7, 8])
-@pytest.mark.parametrize("general", ["cls", "lane", "general"])
+@pytest.mark.parametrize("general", ["cls", "lane", "general", "poly"])
 def test_default_grid_parity(ctx, nv, general):
     s = synth.make_pileup(C=300, nv=nv, V=2000, kbar=250, seed=100 + nv)
     gp = synth.gt_to_gp(s.geno)
@@ -47,11 +47,37 @@ def test_config1_tutorial_shape(ctx):
 
 @pytest.mark.parametrize("nv,alphas", [(4, [0.0, 0.25, 0.5]), (6, [0.0, 0.1, 0.2, 0.3, 0.4, 0.5]),
                                         (16, [0.0, 0.5]), (12, [0.0, 0.3])])
-def test_general_grids(ctx, nv, alphas):
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+def test_general_grids(ctx, nv, alphas, kernel):
+    """auto = k_demux_poly for these shapes; k_demux_general is the 9-FMA baseline"""
     s = synth.make_pileup(C=120, nv=nv, V=1500, kbar=200, seed=300 + nv)
     gp = synth.gt_to_gp(s.geno)
-    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas, kernel)
     check_demux_parity(out, grid, ref, rgrid, alphas)
+
+
+def test_poly_soft_genotypes_deep_pairs_and_big_cells(ctx):
+    """k_demux_poly on soft GP rows, SNPs without GP, allele-2 reads, pairs with up to 60 reads (class D) and
+    cells cut into several work items, 7-point alpha grid, 20 samples (tiles with idle threads)."""
+    rng = np.random.default_rng(17)
+    s = synth.make_pileup(C=10, nv=20, V=20000, kbar=3000, seed=1717)
+    plp = s.plp
+    nrd = np.diff(plp.pair_read_ptr)
+    deep = rng.random(plp.n_pairs) < 0.02
+    nrd2 = np.where(deep, rng.integers(4, 60, plp.n_pairs), nrd)
+    prp = np.concatenate([[0], np.cumsum(nrd2)]).astype(np.int64)
+    N = int(prp[-1])
+    from popscle_b200 import Pileup
+    p2 = Pileup(plp.n_cells, plp.n_snps, plp.cell_ptr, plp.pair_snp, prp, rng.choice([0, 0, 0, 1, 1, 2], N).astype(np.uint8),
+                rng.integers(13, 41, N).astype(np.uint8), plp.snp_af)
+    s2 = synth.Synth(p2, s.geno, s.af, s.truth_d1, s.truth_d2, 1717)
+    gp = rng.dirichlet([0.5, 0.5, 0.5], size=(plp.n_snps, 20)).astype(np.float32).astype(np.float64)
+    has = (rng.random(plp.n_snps) > 0.2).astype(np.uint8)
+    alphas = [0.0, 0.05, 0.1, 0.2, 0.3, 0.4, 0.5]
+    out, grid, ref, rgrid = _run_both(ctx, s2, gp, has, alphas, "poly")
+    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
+    out, grid, ref, rgrid = _run_both(ctx, s2, gp, has, alphas, "general")
+    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
 
 
 def test_config4_shape_small(ctx):
@@ -59,8 +85,9 @@ def test_config4_shape_small(ctx):
     alphas = [0.025 * i for i in range(21)]
     s = synth.make_pileup(C=12, nv=64, V=3000, kbar=150, seed=404)
     gp = synth.gt_to_gp(s.geno)
-    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas)
-    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.2)
+    for kernel in ("auto", "general"):
+        out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas, kernel)
+        check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.2)
 
 
 def test_missing_genotypes_and_other_alleles(ctx):
@@ -71,7 +98,7 @@ def test_missing_genotypes_and_other_alleles(ctx):
     gp = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 5)).astype(np.float32).astype(np.float64)
     has = (rng.random(s.plp.n_snps) > 0.3).astype(np.uint8)
     s.plp.read_allele[rng.random(s.plp.n_reads) < 0.2] = 2
-    for general in ("cls", "lane", "general"):
+    for general in ("cls", "lane", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, has, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT)
 
@@ -96,7 +123,7 @@ def test_deep_pairs_and_empty_cells(ctx):
     geno = rng.integers(0, 3, (nv, V)).astype(np.int8)
     gp = synth.gt_to_gp(geno)
     s = synth.Synth(plp, geno, plp.snp_af, None, None, 9)
-    for general in ("cls", "lane", "general"):
+    for general in ("cls", "lane", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.3)
 
