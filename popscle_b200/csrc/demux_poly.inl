@@ -29,6 +29,12 @@
 // two block barriers per group.  The pairs of an item are processed in class order S | M | D
 // (records of demux_cls.inl's k_dmx_classify, so R is uniform within a group except M's 2 vs 3).
 
+#ifndef PLY_MINB
+#define PLY_MINB 2         /* CTAs per SM the register allocation aims at (NPL <= 21) */
+#endif
+#ifndef PLY_EXSMEM
+#define PLY_EXSMEM 1       /* 1: exponents of the running products in shared memory (touched once per 16 pairs) */
+#endif
 #define PLY_G 8            /* pairs per group = warps per CTA */
 #define PLY_T 16           /* tile edge */
 #define PLY_MAX_GRID (PSCL_MAX_ALPHA * 9)
@@ -78,12 +84,16 @@ __global__ void k_ply_scatter(const int64_t* __restrict__ cell_ptr, const int32_
 }
 
 template <int NPL>
-__global__ void __launch_bounds__(256, NPL <= 21 ? 2 : 1) k_demux_poly(PolyArgs a) {
+__global__ void __launch_bounds__(256, NPL <= 21 ? PLY_MINB : 1) k_demux_poly(PolyArgs a) {
   // ---- shared memory -----------------------------------------------------------------------------
   __shared__ __align__(16) double s_rowJ[PLY_G][PLY_T][3];  // genotype rows of the tile's 16 j ...
   __shared__ __align__(16) double s_rowK[PLY_G][PLY_T][3];  // ... and 16 k samples, per pair of the group
   __shared__ __align__(16) double s_par[PLY_G][12];         // S: {c0, c1/2, c1}; M: Phi_e[l] at [3e + l]
-  __shared__ int s_kind[PLY_G];                             // -1 skip | 0 S | 2, 3 M (degree) | 4 D (direct)
+  __shared__ int s_kind[PLY_G];                             // 15 skip | 0 S | 2, 3 M (degree) | 4 D (direct)
+#if PLY_EXSMEM
+  extern __shared__ int s_ex_dyn[];  // [NPL][256] exponents of the running products
+  int (*s_ex)[256] = reinterpret_cast<int (*)[256]>(s_ex_dyn);
+#endif
   __shared__ __align__(16) double s_tabS[3 * 64][2];        // per base-call code: {c0, c1} of pG(p) = c0 + c1 p
   __shared__ __align__(16) double s_tabR[3 * 64][2];        // per base-call code: {pR, pA} (:666-667)
   __shared__ __align__(16) double s_dir[PLY_G][PLY_MAX_GRID];  // class D: pG_n[l][m] at [9n + 3l + m]
@@ -110,9 +120,14 @@ __global__ void __launch_bounds__(256, NPL <= 21 ? 2 : 1) k_demux_poly(PolyArgs 
   const bool my_valid = my_sample < nv;
 
   double acc[NPL];
+#if PLY_EXSMEM
+#pragma unroll
+  for (int n = 0; n < NPL; ++n) { acc[n] = 1.0; s_ex[n][tid] = 0; }
+#else
   int ex[NPL];
 #pragma unroll
   for (int n = 0; n < NPL; ++n) { acc[n] = 1.0; ex[n] = 0; }
+#endif
 
   // grid points this lane evaluates when its warp sets up a class-M/D pair: i = lane + 32 t -> (n, l, m)
   constexpr int VPL = (PLY_MAX_GRID + 31) / 32;
@@ -159,7 +174,7 @@ __global__ void __launch_bounds__(256, NPL <= 21 ? 2 : 1) k_demux_poly(PolyArgs 
       double* dst = lane < 16 ? &s_rowJ[warp][lane][0] : &s_rowK[warp][lane - 16][0];
       dst[0] = g0N; dst[1] = g1N; dst[2] = g2N;
       const uint2 rec = recN;
-      int kind = -1;
+      int kind = 15;
       if (hasN) {
         if (cls == 0) {
           kind = 0;
@@ -243,9 +258,12 @@ __global__ void __launch_bounds__(256, NPL <= 21 ? 2 : 1) k_demux_poly(PolyArgs 
     issue(pos_next);  // the next group's loads fly while this one is multiplied
 
     // ---- multiply: every thread updates the NPL planes of its (J,K) -------------------------------------
+    uint32_t kinds = 0;  // the group's 8 kinds, 4 bits each: no shared-memory round trip inside the pair loop
+#pragma unroll
+    for (int s = 0; s < PLY_G; ++s) kinds |= (uint32_t)(s_kind[s] & 15) << (4 * s);
     for (uint32_t s = 0; s < n; ++s) {
-      const int kind = s_kind[s];
-      if (kind < 0) continue;
+      const int kind = (int)((kinds >> (4 * s)) & 15u);
+      if (kind == 15) continue;
       const double gj0 = s_rowJ[s][tj][0], gj1 = s_rowJ[s][tj][1], gj2 = s_rowJ[s][tj][2];
       const double gk0 = s_rowK[s][tk][0], gk1 = s_rowK[s][tk][1], gk2 = s_rowK[s][tk][2];
       const double Sk = gk0 + gk1 + gk2, Mk = fma(2.0, gk2, gk1);
@@ -288,8 +306,13 @@ __global__ void __launch_bounds__(256, NPL <= 21 ? 2 : 1) k_demux_poly(PolyArgs 
     since += (int)n;
     if (since >= 16) {  // keep the running products inside the double range (terms >= ~1e-10 each)
       since = 0;
+#if PLY_EXSMEM
+#pragma unroll
+      for (int nn = 0; nn < NPL; ++nn) { int x = 0; pscl_renorm(acc[nn], x); s_ex[nn][tid] += x; }
+#else
 #pragma unroll
       for (int nn = 0; nn < NPL; ++nn) pscl_renorm(acc[nn], ex[nn]);
+#endif
     }
     pos = pos_next;
     __syncthreads();  // everyone is done with the staged group before it is overwritten
@@ -299,8 +322,13 @@ __global__ void __launch_bounds__(256, NPL <= 21 ? 2 : 1) k_demux_poly(PolyArgs 
 #pragma unroll
     for (int nn = 0; nn < NPL; ++nn) {
       if (nn < na) {
-        pscl_renorm(acc[nn], ex[nn]);
-        out[nn] = pscl_prod_log(acc[nn], ex[nn]);
+#if PLY_EXSMEM
+        int x = s_ex[nn][tid];
+#else
+        int x = ex[nn];
+#endif
+        pscl_renorm(acc[nn], x);
+        out[nn] = pscl_prod_log(acc[nn], x);
       }
     }
   }
@@ -346,12 +374,23 @@ static int ply_build_stream(pscl_ctx* ctx, pscl_plp* p) {
   return PSCL_OK;
 }
 
+template <int NPL>
+static cudaError_t launch_poly_n(pscl_ctx* ctx, const PolyArgs& a, dim3 grid) {
+  const size_t dyn = PLY_EXSMEM ? sizeof(int) * NPL * 256 : 0;
+  static bool attr_set[64] = {false};
+  if (dyn && !attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_demux_poly<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  k_demux_poly<NPL><<<grid, 256, dyn, ctx->stream>>>(a);
+  return cudaGetLastError();
+}
 static cudaError_t launch_poly(pscl_ctx* ctx, const PolyArgs& a, int n_work) {
   dim3 grid((unsigned)(a.tiles * a.tiles), (unsigned)n_work);
-  if (a.na <= 4) k_demux_poly<4><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (a.na <= 8) k_demux_poly<8><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (a.na <= 16) k_demux_poly<16><<<grid, 256, 0, ctx->stream>>>(a);
-  else if (a.na <= 21) k_demux_poly<21><<<grid, 256, 0, ctx->stream>>>(a);
-  else k_demux_poly<32><<<grid, 256, 0, ctx->stream>>>(a);
-  return cudaGetLastError();
+  if (a.na <= 4) return launch_poly_n<4>(ctx, a, grid);
+  if (a.na <= 8) return launch_poly_n<8>(ctx, a, grid);
+  if (a.na <= 16) return launch_poly_n<16>(ctx, a, grid);
+  if (a.na <= 21) return launch_poly_n<21>(ctx, a, grid);
+  return launch_poly_n<32>(ctx, a, grid);
 }
