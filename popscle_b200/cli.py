@@ -101,11 +101,10 @@ def demuxlet(argv, engine=None):
         raise UsageError("--sam (BAM/CRAM pileup on the fly) needs htslib; run `popscle dsc-pileup` first and pass --plp")
     if not o["plp"] or not o["vcf"] or not o["out"]:
         raise UsageError("Missing required option(s) : --plp (or --sam), --vcf, --out")
-    if o["geno-error-coeff"] > 0:
-        raise UsageError("--geno-error-coeff (INFO/R2 scaling, sc_drop_seq.cpp:300-306) is not supported by this host yet")
     sm = list(o["sm"]) + (_read_list(o["sm-list"]) if o["sm-list"] else [])
     _notice(f"Loading pileup information with prefix {o['plp']}")
-    L = plpio.load_plp(o["plp"], o["vcf"], field=o["field"], geno_error_offset=o["geno-error-offset"], sm_list=sm or None,
+    L = plpio.load_plp(o["plp"], o["vcf"], field=o["field"], geno_error_offset=o["geno-error-offset"], geno_error_coeff=o["geno-error-coeff"],
+                       r2_info=o["r2-info"], sm_list=sm or None,
                        min_bq=o["min-BQ"], cap_bq=o["cap-BQ"], min_read=o["min-total"], min_umi=o["min-umi"], min_snp=o["min-snp"],
                        group_list=_read_list(o["group-list"]) if o["group-list"] else None,
                        min_mac=o["min-mac"], min_callrate=o["min-callrate"])

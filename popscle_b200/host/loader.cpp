@@ -35,6 +35,7 @@ struct VcfCursor {
   int rid = -1, pos = 0;
   char ref = 0, alt = 0;
   std::vector<float> gps;             // [nv*3] of the current record
+  std::string info;                   // INFO column of the current record
   std::string line;
   std::vector<std::string> c, alleles, fmt, cell, parts, vals;
 
@@ -87,6 +88,7 @@ struct VcfCursor {
       if (c[4] != ".") { split_char(c[4], ',', parts); alleles.insert(alleles.end(), parts.begin(), parts.end()); }
       const int nal = (int)alleles.size();
       if (nal > o.max_alleles) continue;
+      info = c[7];
       split_char(c[8], ':', fmt);
       int gi = -1, fi = -1;
       for (size_t i = 0; i < fmt.size(); ++i) {
@@ -245,6 +247,24 @@ void load_plp(const LoadOptions& o, Loaded& L) {
       const double sum = avg[0] + avg[1] + avg[2];
       avg[0] /= sum; avg[1] /= sum; avg[2] /= sum;
       double err = o.geno_error_offset;
+      if (o.geno_error_coeff > 0) {  // look for the R2 INFO field: exactly one float (sc_drop_seq.cpp:301-306)
+        bool ok = false;
+        float r2 = 0.f;
+        const std::string key = o.r2_info + "=";
+        size_t b = 0;
+        while (b <= vc->info.size()) {
+          size_t e2 = vc->info.find(';', b);
+          if (e2 == std::string::npos) e2 = vc->info.size();
+          if (vc->info.compare(b, key.size(), key) == 0) {
+            const std::string val = vc->info.substr(b + key.size(), e2 - b - key.size());
+            if (!val.empty() && val != "." && val.find(',') == std::string::npos) { r2 = (float)atof(val.c_str()); ok = true; }
+            break;
+          }
+          b = e2 + 1;
+        }
+        if (!ok) throw host_error("Cannot extract " + o.r2_info + " (1 float value) from INFO field at " + std::string(f[1]) + ":" + std::to_string(pos) + ". Cannot use --geno-error-coeff");
+        err += (1 - o.geno_error_offset) * (1 - r2) * o.geno_error_coeff;
+      }
       if (err > 0.999) err = 0.999;
       if (err < 0) err = 0;
       if (err > 0)

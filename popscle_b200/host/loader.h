@@ -14,6 +14,8 @@ struct LoadOptions {
   std::string plp_prefix, vcf;           // vcf empty = no genotypes (freemuxlet)
   std::string field = "GP";
   double geno_error_offset = 0.1;
+  double geno_error_coeff = 0.0;   // --geno-error-coeff: err = offset + (1-offset)(1-R2)*coeff (sc_drop_seq.cpp:299-306)
+  std::string r2_info = "R2";      // --r2-info
   std::vector<std::string> sm;           // --sm / --sm-list (held in a std::set by the reference: sorted)
   int min_bq = 1, cap_bq = 60;           // library defaults (sc_drop_seq.h:181); the commands pass 13 / 20
   int min_read = 0, min_umi = 0, min_snp = 0;

@@ -114,9 +114,8 @@ int cmd_demuxlet(int argc, char** argv) {
   if (alphas.empty()) { alphas.push_back(0.0); alphas.push_back(0.5); }  // cmd_cram_demuxlet.cpp:85-89
   if (!sam.empty()) throw host_error("--sam (BAM/CRAM pileup on the fly) needs htslib; run `popscle dsc-pileup` first and pass --plp");
   if (plp.empty() || vcf.empty() || out.empty()) throw host_error("Missing required option(s) : --plp (or --sam), --vcf, --out");
-  if (genoErrorCoeff > 0) throw host_error("--geno-error-coeff (INFO/R2 scaling, sc_drop_seq.cpp:300-306) is not supported by this host yet");
   LoadOptions lo;
-  lo.plp_prefix = plp; lo.vcf = vcf; lo.field = field; lo.geno_error_offset = genoErrorOffset; lo.sm = sm;
+  lo.plp_prefix = plp; lo.vcf = vcf; lo.field = field; lo.geno_error_offset = genoErrorOffset; lo.geno_error_coeff = genoErrorCoeff; lo.r2_info = r2Info; lo.sm = sm;
   if (!smList.empty()) for (auto& s : read_first_column(smList)) lo.sm.push_back(s);
   lo.min_bq = minBQ; lo.cap_bq = capBQ; lo.min_read = minTotal; lo.min_umi = minUMI; lo.min_snp = minSNP;
   if (!groupList.empty()) { lo.group_list = read_first_column(groupList); lo.has_group_list = true; }

@@ -87,7 +87,7 @@ def write_plp(prefix: str, plp: Pileup, sites: Sites, barcodes=None):
     return barcodes
 
 
-def write_vcf(path: str, sites: Sites, samples, geno=None, gp=None, pl=None, keep=None):
+def write_vcf(path: str, sites: Sites, samples, geno=None, gp=None, pl=None, keep=None, r2=None):
     """Text VCF with GT (geno int [nv][V], -1 = missing), GP (float [V][nv][3]) and/or PL
     (int [V][nv][3]) FORMAT fields.  keep = mask of SNPs to emit (the rest are absent from the VCF)."""
     V = len(sites.chrom)
@@ -121,7 +121,7 @@ def write_vcf(path: str, sites: Sites, samples, geno=None, gp=None, pl=None, kee
                 if pl is not None:
                     parts.append(",".join(str(int(x)) for x in pl[v, j]))
                 cols.append(":".join(parts))
-            f.write(f"{sites.chrom[v]}\t{int(sites.pos[v])}\t.\t{sites.ref[v]}\t{sites.alt[v]}\t.\tPASS\tAF={sites.af[v]:.5f};R2=0.9\t"
+            f.write(f"{sites.chrom[v]}\t{int(sites.pos[v])}\t.\t{sites.ref[v]}\t{sites.alt[v]}\t.\tPASS\tAF={sites.af[v]:.5f};R2={0.9 if r2 is None else float(r2[v]):.4g}\t"
                     + ":".join(fmt) + "\t" + "\t".join(cols) + "\n")
 
 
@@ -168,7 +168,7 @@ def _parse_vcf(path, field, sm_list=None, min_mac=1, min_callrate=0.5, max_allel
     """Records of a text VCF that pass the demuxlet site filters (cmd_cram_demuxlet.cpp:27-29,
     bcf_filtered_reader.cpp:505-581), with per-sample float32 posteriors
     (bcf_filtered_reader.cpp:367-461, gt_error = 0 as load_from_plp passes).  Yields
-    (contig rid, pos, ref, alt, gp[nv*3] float32)."""
+    (contig rid, pos, ref, alt, gp[nv*3] float32, INFO column)."""
     contigs, samples, cols = {}, None, None
     for line in _lines(path):
         if line.startswith("##"):
@@ -260,7 +260,7 @@ def _parse_vcf(path, field, sm_list=None, min_mac=1, min_callrate=0.5, max_allel
             for g in range(ngen):
                 s = (s + raw[:, g]).astype(np.float32)
             gp = (raw / s[:, None]).astype(np.float32).ravel()
-        yield (rid, pos, alleles[0], alleles[1] if nal > 1 else ".", gp)
+        yield (rid, pos, alleles[0], alleles[1] if nal > 1 else ".", gp, c[7])
 
 
 def _lines(path):
@@ -274,8 +274,19 @@ def _lines(path):
                 yield line
 
 
+def _info_float(info: str, key: str):
+    """One float32 value of an INFO key (bcf_get_info_float; the reference insists on exactly one value)."""
+    for kv in info.split(";"):
+        if kv.startswith(key + "="):
+            vals = kv[len(key) + 1:].split(",")
+            if len(vals) != 1 or vals[0] in (".", ""):
+                return None
+            return float(np.float32(float(vals[0])))
+    return None
+
+
 def load_plp(prefix: str, vcf: str | None = None, field: str = "GP", geno_error_offset: float = 0.1,
-             sm_list=None, min_bq: int = 1, cap_bq: int = 60, min_read: int = 0, min_umi: int = 0, min_snp: int = 0,
+             geno_error_coeff: float = 0.0, r2_info: str = "R2", sm_list=None, min_bq: int = 1, cap_bq: int = 60, min_read: int = 0, min_umi: int = 0, min_snp: int = 0,
              group_list=None, min_mac: int = 1, min_callrate: float = 0.5) -> LoadedPileup:
     """sc_dropseq_lib_t::load_from_plp (sc_drop_seq.cpp:103-384).  Library defaults min_bq=1 /
     cap_bq=60 (sc_drop_seq.h:181); the demuxlet and freemuxlet commands pass 13 / 20."""
@@ -343,7 +354,14 @@ def load_plp(prefix: str, vcf: str | None = None, field: str = "GP", geno_error_
         for i in range(nv * 3):  # :289-291, sample-major accumulation order
             avg[i % 3] += g[i]
         avg = avg / (avg[0] + avg[1] + avg[2])
-        err = min(max(geno_error_offset, 0.0), 0.999)
+        err = geno_error_offset
+        if geno_error_coeff > 0:  # [error] = [offset] + [1-offset]*[1-R2]*[coeff] (sc_drop_seq.cpp:299-306)
+            r2 = _info_float(cur[5], r2_info)
+            if r2 is None:
+                raise ValueError(f"Cannot extract {r2_info} (1 float value) from INFO field at {r[1]}:{p}. Cannot use --geno-error-coeff")
+            # `1 - r2flts[0]` is evaluated in float32 in the reference (int - float), then widened
+            err += (1 - geno_error_offset) * float(np.float32(1.0) - np.float32(r2)) * geno_error_coeff
+        err = min(max(err, 0.0), 0.999)
         if err > 0:
             g = (1 - err) * g + err * np.tile(avg, nv)
         has.append(1); gps.append(g)

@@ -169,7 +169,8 @@ def test_cpp_host_loader_matches_python_loader(case, tmp_path, host_exe):
     os.chdir(work)
     try:
         if argv[0] == "demuxlet":
-            L = plpio.load_plp(o["plp"], o["vcf"], field=o["field"], geno_error_offset=o["geno-error-offset"], sm_list=o["sm"] or None,
+            L = plpio.load_plp(o["plp"], o["vcf"], field=o["field"], geno_error_offset=o["geno-error-offset"],
+                               geno_error_coeff=o["geno-error-coeff"], r2_info=o["r2-info"], sm_list=o["sm"] or None,
                                min_bq=o["min-BQ"], cap_bq=o["cap-BQ"], min_read=o["min-total"], min_umi=o["min-umi"], min_snp=o["min-snp"],
                                group_list=cli._read_list(o["group-list"]) if o["group-list"] else None)
         elif argv[0] == "freemuxlet":
