@@ -571,6 +571,107 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
   a.cells[a.out_base + blockIdx.x] = o;
 }
 
+// Small grids (config 2: 128 entries per cell): one WARP per cell, eight cells per CTA, no block barriers —
+// 10k single-cell CTAs were launch-rate bound (119 us per step against 0.74 ms for the accumulation kernel).
+__global__ void __launch_bounds__(256) k_demux_epilogue_w(EpiArgs a, int n_cells) {
+  const int lane = threadIdx.x & 31, cw = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (cw >= n_cells) return;
+  const int c = a.cell_begin + cw;
+  const int nv = a.nv, na = a.nalpha, G = nv * nv * na;
+  const int ia = a.cell_item_ptr[c], ib = a.cell_item_ptr[c + 1];
+  double* sum_row = a.partial + (size_t)(ia - a.item_base) * G;
+  double* grid_row = a.grid ? a.grid + (size_t)(a.out_base + cw) * G : nullptr;
+  const double lsp = log((1.0 - a.doublet_prior) / nv);                       // :793
+  const double ldp1 = log(a.doublet_prior / nv / (nv - 1.) / (na - 1.));      // :794
+  const double ldp2 = log(a.doublet_prior / nv / (nv - 1.) / (na - 1.) * 2);  // :795
+
+  Top2 sng = {-1e300, -1e300, 0x7fffffff, 0x7fffffff}, dbl = sng;
+  double mx_all = -1e-300, mx_sng = -1e-300;  // the (sic) -1e-300 start of :791 is a term of both sums
+  for (int idx = lane; idx < G; idx += 32) {
+    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    const bool is_s = (n == 0 && k == 0), is_d = (n >= 1 && j != k);
+    double x = __longlong_as_double(0x7ff8000000000000ll);
+    if (is_s || is_d) {
+      x = 0.0;  // memset(llksAB,0) :643 — a cell without items keeps zeros
+      for (int it = ia; it < ib; ++it) x += a.partial[(size_t)(it - a.item_base) * G + idx];
+      if (ib > ia) sum_row[idx] = x;
+      if (is_s) {
+        top2_push(sng, x, j);
+        double t = x + lsp;
+        mx_all = fmax(mx_all, t); mx_sng = fmax(mx_sng, t);
+      } else {
+        top2_push(dbl, x, idx);
+        if (c_alpha[n] == 0.5) { if (k < j) mx_all = fmax(mx_all, x + ldp2); }  // :812-815
+        else mx_all = fmax(mx_all, x + ldp1);
+      }
+    }
+    if (grid_row) grid_row[idx] = x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sng = top2_shfl_merge(sng, o);
+    dbl = top2_shfl_merge(dbl, o);
+    mx_all = fmax(mx_all, __shfl_xor_sync(0xffffffffu, mx_all, o));
+    mx_sng = fmax(mx_sng, __shfl_xor_sync(0xffffffffu, mx_sng, o));
+  }
+  // second pass: sum of exp (the logAdd chains of :804-821 evaluated as max + log(sum exp))
+  double se_all = 0.0, se_sng = 0.0;
+  for (int idx = lane; idx < G; idx += 32) {
+    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    if (n == 0 && k == 0) {
+      double x = (ib > ia) ? sum_row[idx] : 0.0;
+      se_all += exp(x + lsp - mx_all);
+      se_sng += exp(x + lsp - mx_sng);
+    } else if (n >= 1 && j != k) {
+      double x = (ib > ia) ? sum_row[idx] : 0.0;
+      if (c_alpha[n] == 0.5) { if (k < j) se_all += exp(x + ldp2 - mx_all); }
+      else se_all += exp(x + ldp1 - mx_all);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se_all += __shfl_xor_sync(0xffffffffu, se_all, o);
+    se_sng += __shfl_xor_sync(0xffffffffu, se_sng, o);
+  }
+  if (lane != 0) return;
+  se_all += exp(-1e-300 - mx_all);
+  se_sng += exp(-1e-300 - mx_sng);
+  const double sumLLK = mx_all + log(se_all), sngLLK = mx_sng + log(se_sng);
+
+  const int sBest = (sng.i1 == 0x7fffffff) ? -1 : sng.i1, sNext = (sng.i2 == 0x7fffffff) ? -1 : sng.i2;
+  const double sngBestLLK = sng.v1, sngNextLLK = sng.v2, dblBestLLK = dbl.v1, dblNextLLK = dbl.v2;
+  int dBest1 = -1, dBest2 = -1, dBestA = -1, dNext1 = -1, dNext2 = -1, dNextA = -1;
+  if (dbl.i1 != 0x7fffffff) { dBestA = dbl.i1 % na; dBest2 = (dbl.i1 / na) % nv; dBest1 = dbl.i1 / na / nv; }
+  if (dbl.i2 != 0x7fffffff) { dNextA = dbl.i2 % na; dNext2 = (dbl.i2 / na) % nv; dNext1 = dbl.i2 / na / nv; }
+
+  pscl_demux_cell o;
+  memset(&o, 0, sizeof(o));
+  o.n_snps = (int32_t)(a.cell_ptr[c + 1] - a.cell_ptr[c]);
+  if (dblBestLLK > sngBestLLK + 2) {  // :925-946
+    o.type = PSCL_DBL;
+    o.best_pp = exp(dblBestLLK + ((dBestA >= 0 && c_alpha[dBestA] == 0.5) ? ldp2 : ldp1) - sumLLK);
+    o.best_j = dBest1; o.best_k = dBest2; o.best_llk = dblBestLLK; o.best_a = dBestA;
+    if (dblNextLLK > sngBestLLK + 2) { o.next_j = dNext1; o.next_k = dNext2; o.next_llk = dblNextLLK; o.next_a = dNextA; }
+    else { o.next_j = o.next_k = sBest; o.next_llk = sngBestLLK; o.next_a = 0; }
+  } else {
+    o.type = (sngBestLLK > sngNextLLK + 2) ? PSCL_SNG : PSCL_AMB;  // :947 / :968
+    o.best_pp = sngBestLLK + lsp - sumLLK;                         // no exp (:949, :970)
+    o.best_j = o.best_k = sBest; o.best_llk = sngBestLLK; o.best_a = 0;
+    if (dblBestLLK > sngNextLLK + 2) { o.next_j = dBest1; o.next_k = dBest2; o.next_llk = dblBestLLK; o.next_a = dBestA; }
+    else { o.next_j = o.next_k = sNext; o.next_llk = sngNextLLK; o.next_a = 0; }
+  }
+  o.sng_best = sBest; o.sng_next = sNext;
+  o.dbl_best_j = dBest1; o.dbl_best_k = dBest2; o.dbl_best_a = dBestA;
+  o.dbl_next_j = dNext1; o.dbl_next_k = dNext2; o.dbl_next_a = dNextA;
+  o.sng_pp = exp(sngLLK - sumLLK);               // :990
+  o.sng_only_pp = exp(sngBestLLK + lsp - sngLLK);  // :991
+  o.sng_best_llk = sngBestLLK; o.sng_next_llk = sngNextLLK;
+  o.dbl_best_llk = dblBestLLK; o.dbl_next_llk = dblNextLLK;
+  o.sum_llk = sumLLK; o.sng_llk = sngLLK;
+  a.cells[a.out_base + cw] = o;
+}
+
+
 #include "demux_cls.inl"
 #include "demux_poly.inl"
 
@@ -767,7 +868,8 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     ea.cells = (pscl_demux_cell*)ctx->dm_cells; ea.grid = ctx->keep_grid ? ctx->dm_grid : nullptr;
     ea.cell_begin = c0; ea.out_base = c0 - cell_begin; ea.item_base = ib; ea.nv = nv; ea.nalpha = na;
     ea.doublet_prior = opts->doublet_prior;
-    k_demux_epilogue<<<(unsigned)(c1 - c0), 128, 0, ctx->stream>>>(ea);
+    if (G <= 1024) k_demux_epilogue_w<<<(unsigned)((c1 - c0 + 7) / 8), 256, 0, ctx->stream>>>(ea, c1 - c0);
+    else k_demux_epilogue<<<(unsigned)(c1 - c0), 128, 0, ctx->stream>>>(ea);
     ctx->launches++;
     PSCL_CUDA(ctx, cudaGetLastError());
     c0 = c1;
