@@ -8,8 +8,9 @@
 //   k_fmx_seed        greedy sequential cluster seeding (:223-260, sc_drop_seq.cpp:544-578), one
 //                     persistent CTA walking the cells in score order
 //   k_fmx_mstep       cluster pileups rebuilt by ordered merges (:277-288, :590-596,
-//                     sc_drop_seq.h:77-101); one thread per (SNP, cluster) replays the merges of the
-//                     SNP-major pair list in ascending cell id — the clamp makes merge order matter
+//                     sc_drop_seq.h:77-101); one thread per SNP replays the merges of the SNP-major
+//                     pair list in ascending cell id (the clamp makes merge order matter), the nS
+//                     pileups of the SNP in a shared-memory column of the thread
 //   k_fmx_posterior   per (SNP, cluster) genotype posterior u = (1-e) norm(h * gl_diag) + e h (:402-415):
 //                     it does not depend on the cell, so it is built once per iteration, not per pair
 //   k_fmx_estep       cell x cluster-pair LLK partials (:383-456); one lane per (cell,SNP) pair, running
@@ -32,10 +33,14 @@ struct pscl_fmx_state {
   // SNP-major view of the pair list (ascending cell id inside one SNP)
   int64_t* snp_ptr = nullptr;    // [V+1]
   uint32_t* snp_pair = nullptr;  // [P] cell-major pair id of each SNP-major entry
-  int32_t* snp_cell = nullptr;   // [P] cell of each SNP-major entry
-  uint32_t* csc_pos = nullptr;   // [P] SNP-major position of each cell-major pair
+  // warp-grouped SNP-major layout of the M-step: 32 consecutive SNPs form a group; entry t of SNP v sits in
+  // slot grp_base[v/32] + t, lane v%32, so a warp reads entry t of its 32 SNPs as contiguous 32-element rows
+  int64_t* grp_base = nullptr;   // [ceil(V/32)+1] first slot of each group (its length = the longest list in it)
+  int32_t* cell_w = nullptr;     // [slots][32] cell of the entry, -1 = padding
+  uint32_t* csc_pos = nullptr;   // [P] slot of each cell-major pair (stage 1 scatters through it)
+  int64_t n_slots = 0;
   double* gl_soa = nullptr;      // [9][P]  cell-major
-  double* gl_csc = nullptr;      // [P][9]  SNP-major
+  double* gl_csc = nullptr;      // [slots][9][32]  pair GLs in the warp-grouped SNP-major layout
   double* clust_diag = nullptr;  // [V][nS][3]  diagonal GLs of the cluster pileups (all the E-step reads)
   double* u_tab = nullptr;       // [V][US]     per (SNP, cluster) posterior
   double* clust_gl = nullptr;    // [V][nS][9]  full cluster pileups (seeding, final output)
@@ -61,7 +66,7 @@ struct pscl_fmx_state {
 static void fmx_state_free(pscl_ctx* ctx) {
   pscl_fmx_state* s = ctx->fmx;
   if (!s) return;
-  cudaFree(s->snp_ptr); cudaFree(s->snp_pair); cudaFree(s->snp_cell); cudaFree(s->csc_pos);
+  cudaFree(s->snp_ptr); cudaFree(s->snp_pair); cudaFree(s->grp_base); cudaFree(s->cell_w); cudaFree(s->csc_pos);
   cudaFree(s->gl_soa); cudaFree(s->gl_csc); cudaFree(s->clust_diag); cudaFree(s->u_tab);
   cudaFree(s->clust_gl); cudaFree(s->clust_cnt); cudaFree(s->present); cudaFree(s->cells);
   cudaFree(s->member); cudaFree(s->item_s1); cudaFree(s->item_nrd); cudaFree(s->item_llk);
@@ -79,11 +84,8 @@ __global__ void k_fmx_iota(uint32_t* v, int64_t n) {
   if (i < n) v[i] = (uint32_t)i;
 }
 
-// after the stable sort by SNP: segment starts, owning cell of each entry, inverse permutation
-__global__ void k_fmx_csc_fill(const int32_t* __restrict__ key, const uint32_t* __restrict__ val,
-                               const int64_t* __restrict__ cell_ptr, int32_t C, int32_t V, int64_t P,
-                               int64_t* __restrict__ snp_ptr, int32_t* __restrict__ snp_cell,
-                               uint32_t* __restrict__ csc_pos) {
+// after the stable sort by SNP: segment starts
+__global__ void k_fmx_snp_ptr(const int32_t* __restrict__ key, int32_t V, int64_t P, int64_t* __restrict__ snp_ptr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const int32_t k = key[i];
@@ -91,14 +93,32 @@ __global__ void k_fmx_csc_fill(const int32_t* __restrict__ key, const uint32_t* 
   for (int32_t v = prev + 1; v <= k; ++v) snp_ptr[v] = i;
   if (i == P - 1)
     for (int32_t v = k + 1; v <= V; ++v) snp_ptr[v] = P;
+}
+// longest list of each group of 32 SNPs (entry n_groups = 0 so that the exclusive scan ends with the total)
+__global__ void k_fmx_group_len(const int64_t* __restrict__ snp_ptr, int32_t V, int32_t n_groups, int64_t* __restrict__ glen) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_groups) return;
+  int64_t m = 0;
+  if (g < n_groups)
+    for (int v = g * 32; v < min(V, g * 32 + 32); ++v) m = max(m, snp_ptr[v + 1] - snp_ptr[v]);
+  glen[g] = m;
+}
+// owning cell of each entry in the warp-grouped layout, slot of each cell-major pair
+__global__ void k_fmx_csc_fill(const int32_t* __restrict__ key, const uint32_t* __restrict__ val,
+                               const int64_t* __restrict__ cell_ptr, int32_t C, int64_t P, const int64_t* __restrict__ snp_ptr,
+                               const int64_t* __restrict__ grp_base, int32_t* __restrict__ cell_w, uint32_t* __restrict__ csc_pos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int32_t v = key[i];
   const uint32_t p = val[i];
-  csc_pos[p] = (uint32_t)i;
+  const int64_t slot = grp_base[v >> 5] + (i - snp_ptr[v]);
+  csc_pos[p] = (uint32_t)slot;
   int lo = 0, hi = C;  // largest c with cell_ptr[c] <= p
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
     if (cell_ptr[mid] <= (int64_t)p) lo = mid; else hi = mid;
   }
-  snp_cell[i] = lo;
+  cell_w[slot * 32 + (v & 31)] = lo;
 }
 
 __global__ void k_fmx_fill_i64(int64_t* v, int64_t n, int64_t x) {
@@ -164,9 +184,10 @@ __global__ void __launch_bounds__(256) k_fmx_stage1(S1Args a) {
 #pragma unroll
       for (int i = 0; i < 9; ++i) gl[i] /= t;
       const uint32_t q = a.csc_pos[p];
+      const int32_t snp = a.pair_snp[p];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { a.gl_soa[(size_t)i * a.P + p] = gl[i]; a.gl_csc[(size_t)q * 9 + i] = gl[i]; }
-      const double af = a.snp_af[a.pair_snp[p]];
+      for (int i = 0; i < 9; ++i) { a.gl_soa[(size_t)i * a.P + p] = gl[i]; a.gl_csc[((size_t)q * 9 + i) * 32 + (snp & 31)] = gl[i]; }
+      const double af = a.snp_af[snp];
       double h[3];
       h[0] = __dmul_rn(1.0 - af, 1.0 - af); h[1] = __dmul_rn(__dmul_rn(2.0, af), 1.0 - af); h[2] = __dmul_rn(af, af);
       double lk0 = 0.0, lk2 = 0.0;
@@ -346,7 +367,8 @@ __global__ void k_fmx_fill_f64(double* v, size_t n, double x) {
 // ------------------------------------------------------------------------------------------------
 struct MArgs {
   const int64_t* snp_ptr;
-  const int32_t* snp_cell;
+  const int64_t* grp_base;
+  const int32_t* cell_w;
   const uint32_t* snp_pair;
   const double* gl_csc;
   const int32_t* member;
@@ -358,39 +380,82 @@ struct MArgs {
   int32_t V, nS, final_;
 };
 
-__global__ void __launch_bounds__(256) k_fmx_mstep(MArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)a.V * a.nS) return;
-  const int v = (int)(t / a.nS), j = (int)(t - (int64_t)v * a.nS);
-  double gl[9];
+// One thread per SNP (a warp = one group of 32 consecutive SNPs) walks the SNP's cell list once (ascending
+// cell id: the clamp makes the merge order matter) and merges every singlet into the pileup of ITS cluster;
+// the nS pileups of the SNP live in a shared-memory column of the thread ([cluster*9 + g][thread],
+// conflict-free).  Entry t of the 32 lists is one coalesced row of cell ids and nine coalesced rows of GLs
+// (warp-grouped layout, k_fmx_csc_fill); the loads of entry t+1 run ahead of the merge of entry t.
+// History (config 3, per EM iteration): thread per (SNP, cluster) scanning the whole list 1.08 ms; thread
+// per SNP on the [P][9] record layout 1.08 ms (same dependent-load chain), 0.86 ms with the loads run ahead.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fmx_mstep(MArgs a) {
+  extern __shared__ __align__(16) double s_gl[];  // [nS*9][THREADS], then int [nS*3][THREADS] when final
+  int* const s_cnt = reinterpret_cast<int*>(s_gl + (size_t)a.nS * 9 * THREADS);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int v = blockIdx.x * THREADS + tid;
+  const int group = v >> 5;
+  const int nS = a.nS;
+  for (int q = 0; q < nS * 9; ++q) s_gl[q * THREADS + tid] = 1.0;  // default-constructed pileup (sc_drop_seq.h:72-75)
+  if (a.final_)
+    for (int q = 0; q < nS * 3; ++q) s_cnt[q * THREADS + tid] = 0;
+  if (group * 32 >= a.V) return;  // whole warp out of range
+  const int64_t slot0 = a.grp_base[group], L = a.grp_base[group + 1] - slot0;  // the group's longest list
+  const int64_t b = v < a.V ? a.snp_ptr[v] : 0;
+  int cell_n = -1, j_n = -1;
+  double o_n[9];
+  if (L > 0) {
+    cell_n = a.cell_w[slot0 * 32 + lane];
+    j_n = cell_n >= 0 ? a.member[cell_n] : -1;
 #pragma unroll
-  for (int g = 0; g < 9; ++g) gl[g] = 1.0;  // default-constructed pileup (sc_drop_seq.h:72-75)
-  int nreads = 0, nref = 0, nalt = 0;
-  const int64_t b = a.snp_ptr[v], e = a.snp_ptr[v + 1];
-  for (int64_t i = b; i < e; ++i) {  // ascending cell id: the clamp makes the merge order matter
-    if (a.member[a.snp_cell[i]] != j) continue;
+    for (int g = 0; g < 9; ++g) o_n[g] = a.gl_csc[((size_t)slot0 * 9 + g) * 32 + lane];
+  }
+  int cell_n2 = L > 1 ? a.cell_w[(slot0 + 1) * 32 + lane] : -1;
+  for (int64_t t = 0; t < L; ++t) {
+    const int j = j_n;
     double o[9];
-    const double* src = a.gl_csc + (size_t)i * 9;
 #pragma unroll
-    for (int g = 0; g < 9; ++g) o[g] = src[g];
+    for (int g = 0; g < 9; ++g) o[g] = o_n[g];
+    if (t + 1 < L) {
+      j_n = cell_n2 >= 0 ? a.member[cell_n2] : -1;
+      const double* src = a.gl_csc + ((size_t)(slot0 + t + 1) * 9) * 32 + lane;
+#pragma unroll
+      for (int g = 0; g < 9; ++g) o_n[g] = src[g * 32];
+      cell_n2 = (t + 2 < L) ? a.cell_w[(slot0 + t + 2) * 32 + lane] : -1;
+    }
+    if (j < 0) continue;
+    double gl[9];
+    double* col = s_gl + (size_t)j * 9 * THREADS + tid;
+#pragma unroll
+    for (int g = 0; g < 9; ++g) gl[g] = col[g * THREADS];
     fmx_merge(gl, o);
+#pragma unroll
+    for (int g = 0; g < 9; ++g) col[g * THREADS] = gl[g];
     if (a.final_) {
-      const uint32_t p = a.snp_pair[i];
+      const uint32_t p = a.snp_pair[b + t];
+      int nreads = 0, nref = 0, nalt = 0;
       for (uint32_t r = a.pair_rd[p]; r < a.pair_rd[p + 1]; ++r) {
         const uint32_t al = a.rd_aq[r] >> 6;
         ++nreads;
         if (al == 0) ++nref; else if (al == 1) ++nalt;
       }
+      int* cc = s_cnt + (size_t)j * 3 * THREADS + tid;
+      cc[0] += nreads; cc[THREADS] += nref; cc[2 * THREADS] += nalt;
     }
   }
-  double* d = a.clust_diag + (size_t)t * 3;
-  d[0] = gl[0]; d[1] = gl[4]; d[2] = gl[8];
-  if (a.final_) {
-    double* cg = a.clust_gl + (size_t)t * 9;
+  if (v >= a.V) return;
+  for (int j = 0; j < nS; ++j) {
+    const double* col = s_gl + (size_t)j * 9 * THREADS + tid;
+    const size_t e = (size_t)v * nS + j;
+    double* d = a.clust_diag + e * 3;
+    d[0] = col[0]; d[1] = col[4 * THREADS]; d[2] = col[8 * THREADS];
+    if (a.final_) {
+      double* cg = a.clust_gl + e * 9;
 #pragma unroll
-    for (int g = 0; g < 9; ++g) cg[g] = gl[g];
-    int32_t* cc = a.clust_cnt + (size_t)t * 3;
-    cc[0] = nreads; cc[1] = nref; cc[2] = nalt;
+      for (int g = 0; g < 9; ++g) cg[g] = col[g * THREADS];
+      int32_t* cc = a.clust_cnt + e * 3;
+      const int* sc = s_cnt + (size_t)j * 3 * THREADS + tid;
+      cc[0] = sc[0]; cc[1] = sc[THREADS]; cc[2] = sc[2 * THREADS];
+    }
   }
 }
 
@@ -676,38 +741,63 @@ __global__ void __launch_bounds__(128) k_fmx_classify(const double* __restrict__
 static int fmx_build_csc(pscl_ctx* ctx, pscl_fmx_state* s) {
   const pscl_plp* plp = s->plp;
   const int64_t P = s->P;
+  const int32_t NG = (s->V + 31) / 32;
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->snp_ptr, sizeof(int64_t) * ((size_t)s->V + 1)));
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->snp_pair, sizeof(uint32_t) * (size_t)(P ? P : 1)));
-  PSCL_CUDA(ctx, cudaMalloc((void**)&s->snp_cell, sizeof(int32_t) * (size_t)(P ? P : 1)));
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->csc_pos, sizeof(uint32_t) * (size_t)(P ? P : 1)));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->grp_base, sizeof(int64_t) * ((size_t)NG + 1)));
+  s->n_slots = 0;
   if (P == 0) {
     k_fmx_fill_i64<<<FMX_GRID(s->V + 1, 256), 256, 0, ctx->stream>>>(s->snp_ptr, (int64_t)s->V + 1, 0);
-    ctx->launches++;
+    k_fmx_fill_i64<<<FMX_GRID(NG + 1, 256), 256, 0, ctx->stream>>>(s->grp_base, (int64_t)NG + 1, 0);
+    ctx->launches += 2;
     PSCL_CUDA(ctx, cudaGetLastError());
+    PSCL_CUDA(ctx, cudaMalloc((void**)&s->cell_w, 16));
     return PSCL_OK;
   }
   int32_t* key_out = nullptr;
   uint32_t* val_in = nullptr;
-  void* tmp = nullptr;
-  size_t tmp_bytes = 0;
+  int64_t* glen = nullptr;
+  void *tmp = nullptr, *tmp2 = nullptr;
+  size_t tmp_bytes = 0, tmp2_bytes = 0;
   PSCL_CUDA(ctx, cudaMalloc((void**)&key_out, sizeof(int32_t) * (size_t)P));
   PSCL_CUDA(ctx, cudaMalloc((void**)&val_in, sizeof(uint32_t) * (size_t)P));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&glen, sizeof(int64_t) * ((size_t)NG + 1)));
   k_fmx_iota<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(val_in, P);
   ctx->launches++;
   int end_bit = 1;
   while (end_bit < 31 && ((int64_t)1 << end_bit) < (int64_t)s->V) ++end_bit;
   // stable LSD radix sort: equal SNP ids keep their cell-major order = ascending cell id
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int)P, 0, end_bit, ctx->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp2_bytes, glen, s->grp_base, NG + 1, ctx->stream);
   PSCL_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+  PSCL_CUDA(ctx, cudaMalloc(&tmp2, tmp2_bytes ? tmp2_bytes : 16));
   cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int)P, 0, end_bit, ctx->stream);
   ctx->launches += 4;
   if (e == cudaSuccess) {
-    k_fmx_csc_fill<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(key_out, s->snp_pair, plp->cell_ptr, s->C, s->V, P, s->snp_ptr, s->snp_cell, s->csc_pos);
+    k_fmx_snp_ptr<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(key_out, s->V, P, s->snp_ptr);
+    k_fmx_group_len<<<FMX_GRID(NG + 1, 256), 256, 0, ctx->stream>>>(s->snp_ptr, s->V, NG, glen);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp2, tmp2_bytes, glen, s->grp_base, NG + 1, ctx->stream);  // grp_base[NG] = slots
+  ctx->launches += 3;
+  int64_t n_slots = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_slots, s->grp_base + NG, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && n_slots >= ((int64_t)1 << 32)) {
+    cudaFree(key_out); cudaFree(val_in); cudaFree(glen); cudaFree(tmp); cudaFree(tmp2);
+    return pscl_fail(ctx, PSCL_EINVAL, "SNP-major view needs %lld slots (>= 2^32): shard the SNPs", (long long)n_slots);
+  }
+  s->n_slots = n_slots;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->cell_w, sizeof(int32_t) * 32 * (size_t)(n_slots ? n_slots : 1));
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->cell_w, 0xff, sizeof(int32_t) * 32 * (size_t)(n_slots ? n_slots : 1), ctx->stream);  // -1 = padding
+  if (e == cudaSuccess) {
+    k_fmx_csc_fill<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(key_out, s->snp_pair, plp->cell_ptr, s->C, P, s->snp_ptr, s->grp_base, s->cell_w, s->csc_pos);
     ctx->launches++;
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(key_out); cudaFree(val_in); cudaFree(tmp);
+  cudaFree(key_out); cudaFree(val_in); cudaFree(glen); cudaFree(tmp); cudaFree(tmp2);
   if (e != cudaSuccess) return pscl_fail(ctx, PSCL_ECUDA, "SNP-major view build failed: %s", cudaGetErrorString(e));
   return PSCL_OK;
 }
@@ -736,7 +826,7 @@ extern "C" int pscl_fmx_init(pscl_ctx* ctx, const pscl_plp* plp, const pscl_fmx_
   int rc = fmx_build_csc(ctx, s);
   if (rc != PSCL_OK) return rc;
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->gl_soa, sizeof(double) * 9 * P1));
-  PSCL_CUDA(ctx, cudaMalloc((void**)&s->gl_csc, sizeof(double) * 9 * P1));
+  PSCL_CUDA(ctx, cudaMalloc((void**)&s->gl_csc, sizeof(double) * 9 * 32 * (size_t)(s->n_slots ? s->n_slots : 1)));
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->clust_diag, sizeof(double) * 3 * VS));
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->u_tab, sizeof(double) * (size_t)(s->V ? s->V : 1) * s->US));
   PSCL_CUDA(ctx, cudaMalloc((void**)&s->clust_gl, sizeof(double) * 9 * VS));
@@ -847,10 +937,22 @@ static int fmx_mstep_launch(pscl_ctx* ctx, pscl_fmx_state* s, const int32_t* mem
   const int64_t n = (int64_t)s->V * s->nS;
   if (n == 0) return PSCL_OK;
   MArgs a;
-  a.snp_ptr = s->snp_ptr; a.snp_cell = s->snp_cell; a.snp_pair = s->snp_pair; a.gl_csc = s->gl_csc; a.member = member;
+  a.snp_ptr = s->snp_ptr; a.grp_base = s->grp_base; a.cell_w = s->cell_w; a.snp_pair = s->snp_pair; a.gl_csc = s->gl_csc; a.member = member;
   a.pair_rd = s->plp->pair_rd; a.rd_aq = s->plp->rd_aq; a.clust_diag = s->clust_diag; a.clust_gl = s->clust_gl;
   a.clust_cnt = s->clust_cnt; a.V = s->V; a.nS = s->nS; a.final_ = final_;
-  k_fmx_mstep<<<FMX_GRID(n, 256), 256, 0, ctx->stream>>>(a);
+  {
+    const int threads = s->nS <= 16 ? 128 : 64;
+    const size_t smem = (size_t)s->nS * threads * (9 * sizeof(double) + 3 * sizeof(int));
+    static bool attr_set[64] = {false};
+    if (!attr_set[ctx->device & 63]) {
+      PSCL_CUDA(ctx, cudaFuncSetAttribute(k_fmx_mstep<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PSCL_CUDA(ctx, cudaFuncSetAttribute(k_fmx_mstep<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[ctx->device & 63] = true;
+    }
+    const int64_t vpad = ((int64_t)s->V + 31) / 32 * 32;  // whole warps: a group of 32 SNPs is never split
+    if (threads == 128) k_fmx_mstep<128><<<FMX_GRID(vpad, 128), 128, smem, ctx->stream>>>(a);
+    else k_fmx_mstep<64><<<FMX_GRID(vpad, 64), 64, smem, ctx->stream>>>(a);
+  }
   ctx->launches++;
   PSCL_CUDA(ctx, cudaGetLastError());
   s->final_tab = final_ != 0;
