@@ -40,7 +40,7 @@ struct pscl_fmx_state {
   uint32_t* csc_pos = nullptr;   // [P] slot of each cell-major pair (stage 1 scatters through it)
   int64_t n_slots = 0;
   double* gl_soa = nullptr;      // [9][P]  cell-major
-  double* gl_csc = nullptr;      // [slots][9][32]  pair GLs in the warp-grouped SNP-major layout
+  double* gl_csc = nullptr;      // [slots][32][9]  pair GLs in the warp-grouped SNP-major layout
   double* clust_diag = nullptr;  // [V][nS][3]  diagonal GLs of the cluster pileups (all the E-step reads)
   double* u_tab = nullptr;       // [V][US]     per (SNP, cluster) posterior
   double* clust_gl = nullptr;    // [V][nS][9]  full cluster pileups (seeding, final output)
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_fmx_stage1(S1Args a) {
       const uint32_t q = a.csc_pos[p];
       const int32_t snp = a.pair_snp[p];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { a.gl_soa[(size_t)i * a.P + p] = gl[i]; a.gl_csc[((size_t)q * 9 + i) * 32 + (snp & 31)] = gl[i]; }
+      for (int i = 0; i < 9; ++i) { a.gl_soa[(size_t)i * a.P + p] = gl[i]; a.gl_csc[((size_t)q * 32 + (snp & 31)) * 9 + i] = gl[i]; }
       const double af = a.snp_af[snp];
       double h[3];
       h[0] = __dmul_rn(1.0 - af, 1.0 - af); h[1] = __dmul_rn(__dmul_rn(2.0, af), 1.0 - af); h[2] = __dmul_rn(af, af);
@@ -383,8 +383,9 @@ struct MArgs {
 // One thread per SNP (a warp = one group of 32 consecutive SNPs) walks the SNP's cell list once (ascending
 // cell id: the clamp makes the merge order matter) and merges every singlet into the pileup of ITS cluster;
 // the nS pileups of the SNP live in a shared-memory column of the thread ([cluster*9 + g][thread],
-// conflict-free).  Entry t of the 32 lists is one coalesced row of cell ids and nine coalesced rows of GLs
-// (warp-grouped layout, k_fmx_csc_fill); the loads of entry t+1 run ahead of the merge of entry t.
+// conflict-free).  Entry t of the 32 lists is one coalesced row of cell ids and one contiguous 2304-byte block of
+// 32 GL records (warp-grouped layout, k_fmx_csc_fill; records stay whole so that stage 1 writes 72 contiguous
+// bytes per pair); the loads of entry t+1 run ahead of the merge of entry t.
 // History (config 3, per EM iteration): thread per (SNP, cluster) scanning the whole list 1.08 ms; thread
 // per SNP on the [P][9] record layout 1.08 ms (same dependent-load chain), 0.86 ms with the loads run ahead.
 template <int THREADS>
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(THREADS) k_fmx_mstep(MArgs a) {
     cell_n = a.cell_w[slot0 * 32 + lane];
     j_n = cell_n >= 0 ? a.member[cell_n] : -1;
 #pragma unroll
-    for (int g = 0; g < 9; ++g) o_n[g] = a.gl_csc[((size_t)slot0 * 9 + g) * 32 + lane];
+    for (int g = 0; g < 9; ++g) o_n[g] = a.gl_csc[((size_t)slot0 * 32 + lane) * 9 + g];
   }
   int cell_n2 = L > 1 ? a.cell_w[(slot0 + 1) * 32 + lane] : -1;
   for (int64_t t = 0; t < L; ++t) {
@@ -417,9 +418,9 @@ __global__ void __launch_bounds__(THREADS) k_fmx_mstep(MArgs a) {
     for (int g = 0; g < 9; ++g) o[g] = o_n[g];
     if (t + 1 < L) {
       j_n = cell_n2 >= 0 ? a.member[cell_n2] : -1;
-      const double* src = a.gl_csc + ((size_t)(slot0 + t + 1) * 9) * 32 + lane;
+      const double* src = a.gl_csc + ((size_t)(slot0 + t + 1) * 32 + lane) * 9;
 #pragma unroll
-      for (int g = 0; g < 9; ++g) o_n[g] = src[g * 32];
+      for (int g = 0; g < 9; ++g) o_n[g] = src[g];
       cell_n2 = (t + 2 < L) ? a.cell_w[(slot0 + t + 2) * 32 + lane] : -1;
     }
     if (j < 0) continue;
