@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel", default="lane", choices=["lane", "cls", "general"],
+    ap.add_argument("--kernel", default="lane", choices=["lane", "cls", "ab", "general"],
                     help="demuxlet accumulation kernel: k_demux_default (default), k_demux_cls, k_demux_general")
     return ap.parse_args()
 
@@ -401,8 +401,8 @@ def main():
     plp, nv = s.plp, cfg["nv"]
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
-    ctx.demux_select_kernel({"lane": 1, "general": 2, "cls": 3}[args.kernel])
-    kname = {"cls": "k_demux_cls", "lane": "k_demux_default", "general": "k_demux_general"}[args.kernel]
+    ctx.demux_select_kernel({"lane": 1, "general": 2, "cls": 3, "ab": 5}[args.kernel])
+    kname = {"cls": "k_demux_cls", "ab": "k_demux_ab", "lane": "k_demux_default", "general": "k_demux_general"}[args.kernel]
 
     # ---- device-resident arm ("value") ----------------------------------------------------------
     dplp = ctx.upload(plp)

@@ -247,7 +247,7 @@ int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes);
 /* Route every alpha grid through the general demuxlet kernel (parity tests of that kernel). */
 int pscl_demux_force_general(pscl_ctx* ctx, int enable);
 /* Accumulation kernel: 0 = automatic (k_demux_default for the alpha grid {0, 0.5} with <= 8 samples,
- * k_demux_poly otherwise), 1 = k_demux_default (lane per pair; needs that default shape),
+ * k_demux_poly otherwise), 1 = k_demux_default (lane per pair; needs that default shape), 5 = k_demux_ab (k_demux_cls with two warps per batch; default shape),
  * 2 = k_demux_general (9-FMA baseline, any shape), 3 = k_demux_cls (class-split records, TMA packet
  * ring; default shape), 4 = k_demux_poly (polynomial in alpha, any shape).  All are parity-tested
  * against the same oracle. */

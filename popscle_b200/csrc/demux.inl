@@ -673,6 +673,7 @@ __global__ void __launch_bounds__(256) k_demux_epilogue_w(EpiArgs a, int n_cells
 
 
 #include "demux_cls.inl"
+#include "demux_ab.inl"
 #include "demux_poly.inl"
 
 // ------------------------------------------------------------------------------------------------
@@ -715,7 +716,7 @@ extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
   return PSCL_OK;
 }
 extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 4) return PSCL_EINVAL;
+  if (!ctx || which < 0 || which > 5) return PSCL_EINVAL;
   ctx->demux_kernel = which;
   return PSCL_OK;
 }
@@ -772,7 +773,8 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     for (int i = 0; i < na; ++i) h_gamma[i] = 0.5 * h_alpha[i];
     PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gamma, h_gamma, sizeof(h_gamma), 0, cudaMemcpyHostToDevice, ctx->stream));
   }
-  const bool use_ws = use_default && ctx->demux_kernel == 3;
+  const bool use_ws = use_default && (ctx->demux_kernel == 3 || ctx->demux_kernel == 5);
+  const bool use_ab = use_default && ctx->demux_kernel == 5;
   if (use_ws) {
     if ((rc = dmx_build_classes(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
     if ((rc = dmx_build_geno_tables(ctx)) != PSCL_OK) return rc;
@@ -810,14 +812,26 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
         wa.desc = whole ? plp->dmx_desc_sorted : plp->dmx_desc_nat + ib;
         wa.partial = ctx->dm_partial; wa.counter = ctx->dm_counter;
         wa.item_base = ib; wa.n_work = nwork; wa.n_snps = ctx->geno_V;
-        switch (nv) {
-          case 2: e = launch_cls<2>(ctx, wa); break;
-          case 3: e = launch_cls<3>(ctx, wa); break;
-          case 4: e = launch_cls<4>(ctx, wa); break;
-          case 5: e = launch_cls<5>(ctx, wa); break;
-          case 6: e = launch_cls<6>(ctx, wa); break;
-          case 7: e = launch_cls<7>(ctx, wa); break;
-          case 8: e = launch_cls<8>(ctx, wa); break;
+        if (use_ab) {
+          switch (nv) {
+            case 2: e = launch_ab<2>(ctx, wa); break;
+            case 3: e = launch_ab<3>(ctx, wa); break;
+            case 4: e = launch_ab<4>(ctx, wa); break;
+            case 5: e = launch_ab<5>(ctx, wa); break;
+            case 6: e = launch_ab<6>(ctx, wa); break;
+            case 7: e = launch_ab<7>(ctx, wa); break;
+            case 8: e = launch_ab<8>(ctx, wa); break;
+          }
+        } else {
+          switch (nv) {
+            case 2: e = launch_cls<2>(ctx, wa); break;
+            case 3: e = launch_cls<3>(ctx, wa); break;
+            case 4: e = launch_cls<4>(ctx, wa); break;
+            case 5: e = launch_cls<5>(ctx, wa); break;
+            case 6: e = launch_cls<6>(ctx, wa); break;
+            case 7: e = launch_cls<7>(ctx, wa); break;
+            case 8: e = launch_cls<8>(ctx, wa); break;
+          }
         }
       } else if (use_default) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));

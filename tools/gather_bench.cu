@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
@@ -23,6 +24,8 @@ template <int N> __device__ __forceinline__ void waitg() { asm volatile("cp.asyn
 // mode 1: the same with .ca
 // mode 2: every lane loads its own row with LDG.128 into registers (DEPTH ignored: ROWB/16 loads in flight per lane)
 // mode 3: every lane issues one bulk copy for its row, completion on an mbarrier per buffer
+// mode 4: as mode 0, but all source addresses of a batch are computed BEFORE the first LDGSTS, so every copy has
+//         its own address registers (no write-after-read wait on the registers of the copy in front)
 template <int ROWB, int DEPTH, int MODE, int STRIDE_O = 0, int WORK = 0>
 __global__ void __launch_bounds__(256) k_gather(const unsigned char* __restrict__ tab, const int32_t* __restrict__ idx, int64_t n_batches,
                                                 double* __restrict__ sink) {
@@ -42,7 +45,18 @@ __global__ void __launch_bounds__(256) k_gather(const unsigned char* __restrict_
   }
   auto issue = [&](int64_t b, int buf) {
     const int snp = idx[b * 32 + lane];
-    if (MODE == 0 || MODE == 1) {
+    if (MODE == 4) {
+      const unsigned char* src[LPR];
+#pragma unroll
+      for (int i = 0; i < LPR; ++i) {
+        const int s = __shfl_sync(0xffffffffu, snp, i * RPI + rsub);
+        src[i] = tab + (size_t)s * ROWB + piece * 16;
+      }
+#pragma unroll
+      for (int i = 0; i < LPR; ++i)
+        if (piece < NCH) cp16(rows_u32 + buf * 32 * STRIDE + (i * RPI + rsub) * STRIDE + piece * 16, src[i]);
+      commit();
+    } else if (MODE == 0 || MODE == 1) {
 #pragma unroll
       for (int i = 0; i < LPR; ++i) {
         const int s = __shfl_sync(0xffffffffu, snp, i * RPI + rsub);
@@ -121,7 +135,7 @@ static void run(const char* name, const unsigned char* tab, const int32_t* idx, 
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-  printf("%-30s stride=%3d work=%3d rowB=%3d depth=%d ctas/SM=%d smem=%6zu : %.3f ms  %.2f Grows/s  %.2f TB/s\n", name, STRIDE, WORK, ROWB, DEPTH, ctas_per_sm, smem, ms,
+  printf("%-34s stride=%3d work=%3d rowB=%3d depth=%d ctas/SM=%d smem=%6zu : %.3f ms  %.2f Grows/s  %.2f TB/s\n", name, STRIDE, WORK, ROWB, DEPTH, ctas_per_sm, smem, ms,
          nb * 32 / ms / 1e6, (double)nb * 32 * ROWB / ms / 1e9);
 }
 
@@ -135,15 +149,32 @@ int main() {
   for (auto& x : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x = (int32_t)(s % V); }
   CK(cudaMalloc(&idx, h.size() * 4)); CK(cudaMemcpy(idx, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&sink, 8));
-  run<128, 1, 0>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 2, 0>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 2, 0, 208>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 2, 0, 208, 64>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 2, 0, 208, 128>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 2, 0, 208, 256>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 1, 0, 208, 128>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<192, 2, 0, 208, 128>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<192, 2, 0, 208, 256>("LDGSTS.cg cooperative", tab, idx, nb, sink, 1);
-  run<128, 2, 0, 208, 128>("LDGSTS.cg cooperative", tab, idx, nb, sink, 2);
+  run<128, 1, 4>("addresses first", tab, idx, nb, sink, 1);
+  run<128, 2, 4>("addresses first", tab, idx, nb, sink, 1);
+  run<128, 2, 4, 208, 128>("addresses first", tab, idx, nb, sink, 1);
+  run<128, 2, 4, 208, 256>("addresses first", tab, idx, nb, sink, 1);
+  run<192, 2, 4, 208, 128>("addresses first", tab, idx, nb, sink, 1);
+  run<128, 2, 4, 208, 128>("addresses first", tab, idx, nb, sink, 2);
+  run<128, 1, 0>("uniform random rows", tab, idx, nb, sink, 1);
+  run<128, 2, 0, 208, 128>("uniform random rows", tab, idx, nb, sink, 1);
+  {  // the kernels' real pattern: a warp's 32 rows are consecutive entries of ONE cell's ascending SNP list
+    const int K = 2000;  // SNPs per cell
+    std::vector<int32_t> h2(h.size());
+    uint64_t s2 = 0x9E3779B97F4A7C15ull;
+    for (size_t c0 = 0; c0 < h2.size(); c0 += K) {
+      const size_t n = std::min<size_t>(K, h2.size() - c0);
+      for (size_t i = 0; i < n; ++i) { s2 ^= s2 << 13; s2 ^= s2 >> 7; s2 ^= s2 << 17; h2[c0 + i] = (int32_t)(s2 % V); }
+      std::sort(h2.begin() + c0, h2.begin() + c0 + n);
+    }
+    CK(cudaMemcpy(idx, h2.data(), h2.size() * 4, cudaMemcpyHostToDevice));
+    run<128, 1, 0>("sorted per cell (as the kernels)", tab, idx, nb, sink, 1);
+    run<128, 2, 0, 208, 128>("sorted per cell (as the kernels)", tab, idx, nb, sink, 1);
+    run<192, 2, 0, 208, 128>("sorted per cell (as the kernels)", tab, idx, nb, sink, 1);
+    // the same lists with the row index bit-mixed (a table stored in hashed row order)
+    for (auto& x : h2) { uint32_t y = (uint32_t)x * 2654435761u; x = (int32_t)(y % (uint32_t)V); }
+    CK(cudaMemcpy(idx, h2.data(), h2.size() * 4, cudaMemcpyHostToDevice));
+    run<128, 1, 0>("sorted per cell, hashed row order", tab, idx, nb, sink, 1);
+    run<128, 2, 0, 208, 128>("sorted per cell, hashed row order", tab, idx, nb, sink, 1);
+  }
   return 0;
 }
