@@ -120,6 +120,67 @@ __global__ void __launch_bounds__(256) k_gather(const unsigned char* __restrict_
   if (acc == 123.456) sink[0] = acc;
 }
 
+// mode 5: cooperative LDG.128 into registers (same lane mapping as mode 0), stored to shared memory one batch later:
+//         plain loads pipeline inside a warp, LDGSTS does not (one in flight per warp at issue, ~145 cycles each)
+template <int ROWB, int WORK>
+__global__ void __launch_bounds__(256) k_gather_ldg(const unsigned char* __restrict__ tab, const int32_t* __restrict__ idx, int64_t n_batches,
+                                                    double* __restrict__ sink) {
+  constexpr int STRIDE = 208, NCH = ROWB / 16;
+  constexpr int LPR = NCH <= 8 ? 8 : 16, RPI = 32 / LPR;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* rows = smem + (size_t)warp * (32 * STRIDE);
+  const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+  const int piece = lane % LPR, rsub = lane / LPR;
+  double acc = 0.0;
+  uint4 v[LPR];
+  auto issue = [&](int64_t b) {
+    const int snp = idx[b * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < LPR; ++i) {
+      const int s = __shfl_sync(0xffffffffu, snp, i * RPI + rsub);
+      if (piece < NCH) v[i] = *reinterpret_cast<const uint4*>(tab + (size_t)s * ROWB + piece * 16);
+    }
+  };
+  int64_t b = gw;
+  if (b < n_batches) issue(b);
+  for (; b < n_batches; b += nw) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < LPR; ++i)
+      if (piece < NCH) *reinterpret_cast<uint4*>(rows + (i * RPI + rsub) * STRIDE + piece * 16) = v[i];
+    __syncwarp();
+    if (b + nw < n_batches) issue(b + nw);
+    const double2* r = reinterpret_cast<const double2*>(rows + lane * STRIDE);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { double2 x = r[i]; acc += x.x * x.y; }
+    if (WORK) {
+      double w0 = acc, w1 = acc + 1, w2 = acc + 2, w3 = acc + 3;
+#pragma unroll
+      for (int i = 0; i < WORK / 4; ++i) { w0 = fma(w0, 1.0000001, 1e-9); w1 = fma(w1, 1.0000001, 1e-9); w2 = fma(w2, 1.0000001, 1e-9); w3 = fma(w3, 1.0000001, 1e-9); }
+      acc = w0 + w1 + w2 + w3;
+    }
+  }
+  if (acc == 123.456) sink[0] = acc;
+}
+template <int ROWB, int WORK>
+static void run_ldg(const unsigned char* tab, const int32_t* idx, int64_t nb, double* sink, int ctas_per_sm) {
+  size_t smem = 8 * 32 * 208;
+  CK(cudaFuncSetAttribute(k_gather_ldg<ROWB, WORK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int grid = 148 * ctas_per_sm;
+  for (int w = 0; w < 2; ++w) k_gather_ldg<ROWB, WORK><<<grid, 256, smem>>>(tab, idx, nb, sink);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0);
+  for (int w = 0; w < 5; ++w) k_gather_ldg<ROWB, WORK><<<grid, 256, smem>>>(tab, idx, nb, sink);
+  cudaEventRecord(e1);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+  printf("%-34s stride=208 work=%3d rowB=%3d depth=1 ctas/SM=%d smem=%6zu : %.3f ms  %.2f Grows/s\n", "LDG.128 cooperative -> regs -> STS", WORK, ROWB, ctas_per_sm, smem, ms, nb * 32 / ms / 1e6);
+}
+
 template <int ROWB, int DEPTH, int MODE, int STRIDE_O = 0, int WORK = 0>
 static void run(const char* name, const unsigned char* tab, const int32_t* idx, int64_t nb, double* sink, int ctas_per_sm) {
   constexpr int STRIDE = STRIDE_O ? STRIDE_O : ((ROWB / 16) | 1) * 16;
@@ -149,6 +210,12 @@ int main() {
   for (auto& x : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x = (int32_t)(s % V); }
   CK(cudaMalloc(&idx, h.size() * 4)); CK(cudaMemcpy(idx, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&sink, 8));
+  run_ldg<128, 0>(tab, idx, nb, sink, 1);
+  run_ldg<128, 128>(tab, idx, nb, sink, 1);
+  run_ldg<128, 256>(tab, idx, nb, sink, 1);
+  run_ldg<192, 128>(tab, idx, nb, sink, 1);
+  run_ldg<128, 128>(tab, idx, nb, sink, 2);
+  run_ldg<128, 256>(tab, idx, nb, sink, 2);
   run<128, 1, 4>("addresses first", tab, idx, nb, sink, 1);
   run<128, 2, 4>("addresses first", tab, idx, nb, sink, 1);
   run<128, 2, 4, 208, 128>("addresses first", tab, idx, nb, sink, 1);
