@@ -459,8 +459,10 @@ struct EpiArgs {
   int32_t out_base;         // index of cell_begin inside cells[] / grid[]
   int32_t item_base;        // first item of this batch
   int32_t nv, nalpha;
+  unsigned long long inv_nv, inv_na;  // ceil(2^40 / d): idx / d == (idx * inv) >> 40, exact while idx * d < 2^40
   double doublet_prior;
 };
+__device__ __forceinline__ int epi_div(int x, unsigned long long inv) { return (int)(((unsigned long long)(unsigned)x * inv) >> 40); }
 
 __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
   const int c = a.cell_begin + blockIdx.x;
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
   Top2 sng = {-1e300, -1e300, 0x7fffffff, 0x7fffffff}, dbl = sng;
   double mx_all = -1e-300, mx_sng = -1e-300;  // the (sic) -1e-300 start of :791 is a term of both sums
   for (int idx = tid; idx < G; idx += 128) {
-    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    const int jk = epi_div(idx, a.inv_na), n = idx - jk * na, j = epi_div(jk, a.inv_nv), k = jk - j * nv;
     const bool is_s = (n == 0 && k == 0), is_d = (n >= 1 && j != k);
     double x = __longlong_as_double(0x7ff8000000000000ll);
     if (is_s || is_d) {
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(128) k_demux_epilogue(EpiArgs a) {
   // second pass: sum of exp (the logAdd chains of :804-821 evaluated as max + log(sum exp))
   double se_all = 0.0, se_sng = 0.0;
   for (int idx = tid; idx < G; idx += 128) {
-    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    const int jk = epi_div(idx, a.inv_na), n = idx - jk * na, j = epi_div(jk, a.inv_nv), k = jk - j * nv;
     if (n == 0 && k == 0) {
       double x = (ib > ia) ? sum_row[idx] : 0.0;
       se_all += exp(x + lsp - mx_all);
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(256) k_demux_epilogue_w(EpiArgs a, int n_cells
   Top2 sng = {-1e300, -1e300, 0x7fffffff, 0x7fffffff}, dbl = sng;
   double mx_all = -1e-300, mx_sng = -1e-300;  // the (sic) -1e-300 start of :791 is a term of both sums
   for (int idx = lane; idx < G; idx += 32) {
-    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    const int jk = epi_div(idx, a.inv_na), n = idx - jk * na, j = epi_div(jk, a.inv_nv), k = jk - j * nv;
     const bool is_s = (n == 0 && k == 0), is_d = (n >= 1 && j != k);
     double x = __longlong_as_double(0x7ff8000000000000ll);
     if (is_s || is_d) {
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(256) k_demux_epilogue_w(EpiArgs a, int n_cells
   // second pass: sum of exp (the logAdd chains of :804-821 evaluated as max + log(sum exp))
   double se_all = 0.0, se_sng = 0.0;
   for (int idx = lane; idx < G; idx += 32) {
-    const int n = idx % na, jk = idx / na, k = jk % nv, j = jk / nv;
+    const int jk = epi_div(idx, a.inv_na), n = idx - jk * na, j = epi_div(jk, a.inv_nv), k = jk - j * nv;
     if (n == 0 && k == 0) {
       double x = (ib > ia) ? sum_row[idx] : 0.0;
       se_all += exp(x + lsp - mx_all);
@@ -882,6 +884,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     ea.cells = (pscl_demux_cell*)ctx->dm_cells; ea.grid = ctx->keep_grid ? ctx->dm_grid : nullptr;
     ea.cell_begin = c0; ea.out_base = c0 - cell_begin; ea.item_base = ib; ea.nv = nv; ea.nalpha = na;
     ea.doublet_prior = opts->doublet_prior;
+    ea.inv_nv = ((1ull << 40) + nv - 1) / nv; ea.inv_na = ((1ull << 40) + na - 1) / na;
     if (G <= 1024) k_demux_epilogue_w<<<(unsigned)((c1 - c0 + 7) / 8), 256, 0, ctx->stream>>>(ea, c1 - c0);
     else k_demux_epilogue<<<(unsigned)(c1 - c0), 128, 0, ctx->stream>>>(ea);
     ctx->launches++;
