@@ -209,3 +209,37 @@ def test_compact_pileup_inputs_are_equivalent(ctx):
     bad.compact()[1][5] |= 0xC0
     with pytest.raises(PsclError):
         ctx.demux_run(bad, synth.gt_to_gp(synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1).geno), None, DEFAULT, compact=True)
+
+
+@pytest.mark.parametrize("nv,na", [(2, 2), (3, 3), (9, 5), (17, 9), (33, 17), (5, 32)])
+def test_poly_shapes(ctx, nv, na):
+    """every plane-count bucket of k_demux_poly (4/8/16/21/32) and sample counts that leave idle tile threads"""
+    alphas = [0.5 * i / (na - 1) for i in range(na)]
+    s = synth.make_pileup(C=30, nv=nv, V=900, kbar=150, seed=500 + nv)
+    gp = synth.gt_to_gp(s.geno)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas, "poly")
+    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
+
+
+@pytest.mark.parametrize("kernel", ["lane", "cls", "ab", "poly", "general"])
+def test_degenerate_pileups(ctx, kernel):
+    """one cell with one pair; no pair at all; no SNP with genotypes"""
+    from popscle_b200 import Pileup
+    nv, V = 4, 50
+    rng = np.random.default_rng(3)
+    gp = synth.gt_to_gp(rng.integers(0, 3, (nv, V)).astype(np.int8))
+    one = Pileup(1, V, [0, 1], [7], [0, 2], np.array([0, 1], np.uint8), np.array([30, 20], np.uint8), rng.uniform(0.1, 0.5, V))
+    s1 = synth.Synth(one, None, None, None, None, 0)
+    out, grid, ref, rgrid = _run_both(ctx, s1, gp, None, DEFAULT, kernel)
+    check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=1.0)
+    empty = Pileup(3, V, [0, 0, 0, 0], np.zeros(0, np.int32), [0], np.zeros(0, np.uint8), np.zeros(0, np.uint8), rng.uniform(0.1, 0.5, V))
+    ctx.demux_select_kernel(KERNELS[kernel])
+    try:
+        o = ctx.demux_run(empty, gp, None, DEFAULT)
+    finally:
+        ctx.demux_select_kernel(0)
+    assert len(o) == 3 and (o["n_snps"] == 0).all()
+    s = synth.make_pileup(C=20, nv=nv, V=V, kbar=20, seed=5)
+    out, grid, ref, rgrid = _run_both(ctx, s, gp, np.zeros(V, np.uint8), DEFAULT, kernel)
+    assert_close(out["sng_best_llk"], ref["sng_best_llk"], "no genotypes: singlet LLK")
+    assert_close(out["dbl_best_llk"], ref["dbl_best_llk"], "no genotypes: doublet LLK")
