@@ -452,21 +452,25 @@ def main():
     keep = []
     from popscle_b200 import Pileup
     arrs = {}
-    p32, aq = plp.compact()  # ABI 2 compact host arrays: 32-bit read offsets, allele<<6|qual (what the CLI host builds)
-    for name, src in (("cell_ptr", plp.cell_ptr), ("pair_snp", plp.pair_snp), ("pair_read_ptr32", p32), ("read_aq", aq)):
+    # ABI 3 compact host arrays (what the CLI host builds): first SNP per cell + 16-bit SNP gaps + 8-bit base-call
+    # counts for the pairs, allele<<6|qual for the base-calls
+    p32, aq = plp.compact()
+    first, d16, n8 = plp.compact3()
+    for name, src in (("cell_ptr", plp.cell_ptr), ("cell_first_snp", first), ("pair_snp_delta16", d16), ("pair_nreads8", n8), ("read_aq", aq)):
         t_, v_ = pin(src); keep.append(t_); arrs[name] = v_
     gp_t, gp_pin = pin(gp); keep.append(gp_t)
-    hplp = Pileup(plp.n_cells, plp.n_snps, arrs["cell_ptr"], arrs["pair_snp"], plp.pair_read_ptr, plp.read_allele, plp.read_qual, None)
-    hplp._compact = (arrs["pair_read_ptr32"], arrs["read_aq"])  # pinned copies are what crosses the ABI
+    hplp = Pileup(plp.n_cells, plp.n_snps, arrs["cell_ptr"], plp.pair_snp, plp.pair_read_ptr, plp.read_allele, plp.read_qual, None)
+    hplp._compact = (p32, arrs["read_aq"])  # pinned copies are what crosses the ABI
+    hplp._compact3 = (arrs["cell_first_snp"], arrs["pair_snp_delta16"], arrs["pair_nreads8"])
     h2d = sum(v.nbytes for v in arrs.values()) + gp_pin.nbytes
     d2h = 160 * plp.n_cells
     for _ in range(2):
-        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=True)
+        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=True)
+        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
     torch.cuda.synchronize()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -490,7 +494,7 @@ def main():
                            "l2": "flushed between timed steps (256 MiB memset, untimed)"},
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "api": "pscl_demux_run (pinned host buffers in ABI-2 compact form: u32 read offsets, 1 B per base-call; per-cell records out)"},
+                        "steps": e2e_steps, "api": "pscl_demux_run (pinned host buffers in ABI-3 compact form: 3 B per pair, 1 B per base-call; per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_demux(s, gp, nv, args.cpu_seconds, os.cpu_count() or 1)

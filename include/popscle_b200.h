@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSCL_ABI_VERSION 2
+#define PSCL_ABI_VERSION 3
 
 typedef enum pscl_status {
   PSCL_OK = 0,
@@ -65,10 +65,17 @@ typedef struct pscl_pileup {
   const double* snp_af;         /* [V]   AF column of .var.gz (freemuxlet prior); may be NULL
                                          for demuxlet                                          */
   /* Compact alternatives (ABI 2; NULL = not given).  A host that builds them halves the bytes that
-   * cross PCIe per pileup (13 -> 5.3 B per pair + 2 -> 1 B per base-call); when one is given the
+   * cross PCIe per pileup (13 -> 9 B per pair + 2 -> 1 B per base-call); when one is given the
    * wide array it replaces may be NULL. */
   const uint32_t* pair_read_ptr32; /* [P+1] the same offsets as pair_read_ptr (n_reads < 2^32)  */
   const uint8_t* read_aq;          /* [N]   allele << 6 | qual, qual <= 63                      */
+  /* ABI 3: the pair arrays as small deltas (decoded on the device by a per-cell scan and a global
+   * scan): 3 B per pair instead of 8.  pair_snp_delta16[p] = pair_snp[p] - pair_snp[p-1] inside a
+   * cell (0 for the first pair of a cell, whose SNP id is cell_first_snp[cell]); every delta must be
+   * < 65536 and every pair must have < 256 base-calls, else the host keeps the wider arrays. */
+  const int32_t* cell_first_snp;     /* [C]   SNP id of the first pair of each cell (any value for empty cells) */
+  const uint16_t* pair_snp_delta16;  /* [P]                                                      */
+  const uint8_t* pair_nreads8;       /* [P]   base-calls of each pair                            */
 } pscl_pileup;
 
 /* Genotype table (replaces sc_snp_t::gps, sc_drop_seq.h:29-37, filled at

@@ -30,7 +30,8 @@ class CPileup(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("n_snps", C.c_int32), ("n_pairs", C.c_int64), ("n_reads", C.c_int64),
                 ("cell_ptr", C.c_void_p), ("pair_snp", C.c_void_p), ("pair_read_ptr", C.c_void_p),
                 ("read_allele", C.c_void_p), ("read_qual", C.c_void_p), ("snp_af", C.c_void_p),
-                ("pair_read_ptr32", C.c_void_p), ("read_aq", C.c_void_p)]
+                ("pair_read_ptr32", C.c_void_p), ("read_aq", C.c_void_p),
+                ("cell_first_snp", C.c_void_p), ("pair_snp_delta16", C.c_void_p), ("pair_nreads8", C.c_void_p)]
 
 
 class CGeno(C.Structure):
@@ -121,6 +122,27 @@ class Pileup:
             self._compact = c
         return c
 
+    def compact3(self):
+        """(cell_first_snp, pair_snp_delta16, pair_nreads8): the delta-coded pair arrays of ABI 3, or None when a
+        SNP gap >= 65536 or a pair with >= 256 base-calls rules them out."""
+        c = getattr(self, "_compact3", 0)
+        if c == 0:
+            c = None
+            nrd = np.diff(self.pair_read_ptr)
+            P = self.n_pairs
+            first = np.zeros(self.n_cells, dtype=np.int32)
+            starts = self.cell_ptr[:-1]
+            nonempty = self.cell_ptr[1:] > starts
+            delta = np.zeros(P, dtype=np.int64)
+            if P:
+                delta[1:] = np.diff(self.pair_snp.astype(np.int64))
+                delta[starts[nonempty]] = 0
+                first[nonempty] = self.pair_snp[starts[nonempty]]
+            if P == 0 or (delta.min() >= 0 and delta.max() < 65536 and nrd.max() < 256):
+                c = (first, delta.astype(np.uint16), nrd.astype(np.uint8))
+            self._compact3 = c
+        return c
+
     def c_struct(self, cls=CPileup, compact=False):
         s = cls()
         s.n_cells, s.n_snps, s.n_pairs, s.n_reads = self.n_cells, self.n_snps, self.n_pairs, self.n_reads
@@ -134,6 +156,10 @@ class Pileup:
             p32, aq = self.compact()
             s.pair_read_ptr32, s.read_aq = p32.ctypes.data, aq.ctypes.data
             s.pair_read_ptr = s.read_allele = s.read_qual = None
+            c3 = self.compact3() if compact == 3 else None
+            if c3 is not None:  # ABI 3: only deltas and counts for the pair arrays
+                s.cell_first_snp, s.pair_snp_delta16, s.pair_nreads8 = (x.ctypes.data for x in c3)
+                s.pair_snp = s.pair_read_ptr32 = None
         return s
 
     def slice_cells(self, c0: int, c1: int) -> "Pileup":

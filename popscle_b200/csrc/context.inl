@@ -149,6 +149,31 @@ __global__ void k_check_reads(const uint8_t* __restrict__ aq, int64_t n, int* ba
   if (b) atomicExch(bad, 1);
 }
 
+// ABI 3: SNP ids from 16-bit deltas, one warp per cell (inclusive scan of the deltas on top of the cell's first id)
+__global__ void k_decode_snp(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ first, const uint16_t* __restrict__ delta,
+                             int32_t C, int32_t V, int32_t* __restrict__ pair_snp, int* bad) {
+  const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
+  int run = (b < e) ? first[c] : 0;
+  for (int64_t p0 = b; p0 < e; p0 += 32) {
+    const int64_t p = p0 + lane;
+    int v = (p < e && p > b) ? (int)delta[p] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    v += run;
+    if (p < e) { pair_snp[p] = v; if (v < 0 || v >= V) atomicExch(bad, 2); }
+    run = __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+// ABI 3: read offsets from 8-bit counts are an exclusive scan (CUB); this checks that they end at n_reads
+__global__ void k_check_total(const uint32_t* __restrict__ pair_rd, int64_t P, int64_t N, int* bad) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && (int64_t)pair_rd[P] != N) atomicExch(bad, 3);
+}
+struct PsclU8ToU32 {
+  __host__ __device__ uint32_t operator()(uint8_t x) const { return x; }
+};
+
 // int64 read offsets -> uint32 (device images hold < 2^32 reads)
 __global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +201,9 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   const int64_t P = h->n_pairs, N = h->n_reads;
   if (C < 0 || V < 0 || P < 0 || N < 0) return pscl_fail(ctx, PSCL_EINVAL, "negative size in pscl_pileup");
   const bool ptr32 = h->pair_read_ptr32 != nullptr, packed = h->read_aq != nullptr;
-  if (!h->cell_ptr || (P > 0 && (!h->pair_snp || (!h->pair_read_ptr && !ptr32))) || (N > 0 && !packed && (!h->read_allele || !h->read_qual)))
+  const bool dsnp = h->pair_snp_delta16 != nullptr && h->cell_first_snp != nullptr, cnt8 = h->pair_nreads8 != nullptr;
+  if (!h->cell_ptr || (P > 0 && ((!h->pair_snp && !dsnp) || (!h->pair_read_ptr && !ptr32 && !cnt8))) ||
+      (N > 0 && !packed && (!h->read_allele || !h->read_qual)))
     return pscl_fail(ctx, PSCL_EINVAL, "pscl_pileup has a NULL array");
   if (N >= ((int64_t)1 << 32) || P >= ((int64_t)1 << 32))
     return pscl_fail(ctx, PSCL_EINVAL, "a device pileup image holds < 2^32 pairs/reads; shard the barcodes or SNPs");
@@ -184,7 +211,7 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
     return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr must run from 0 to n_pairs");
   for (int32_t c = 0; c < C; ++c)
     if (h->cell_ptr[c + 1] < h->cell_ptr[c]) return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr not monotone at cell %d", c);
-  if (P > 0 && (ptr32 ? (h->pair_read_ptr32[0] != 0 || (int64_t)h->pair_read_ptr32[P] != N) : (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N)))
+  if (P > 0 && !cnt8 && (ptr32 ? (h->pair_read_ptr32[0] != 0 || (int64_t)h->pair_read_ptr32[P] != N) : (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N)))
     return pscl_fail(ctx, PSCL_EINVAL, "pair_read_ptr must run from 0 to n_reads");
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
   pscl_plp* p = new pscl_plp();
@@ -218,11 +245,38 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   cudaError_t e = cudaSuccess;
 #define UP(field, src, bytes) do { if (e == cudaSuccess) e = up((void**)&p->field, src, bytes); } while (0)
   UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
-  UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
-  if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
-  else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
-  uint8_t *d_al = nullptr, *d_q = nullptr;
+  uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr;
+  uint16_t* d_delta = nullptr;
+  int32_t* d_first = nullptr;
+  void* d_scan_tmp = nullptr;
   int* d_bad = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
+  if (dsnp) {  // ABI 3: 16-bit SNP deltas, decoded per cell
+    if (e == cudaSuccess) e = up((void**)&d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P);
+    if (e == cudaSuccess) e = up((void**)&d_first, h->cell_first_snp, sizeof(int32_t) * C);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_snp, sizeof(int32_t) * (P ? P : 1));
+    if (e == cudaSuccess && C > 0) {
+      k_decode_snp<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, d_first, d_delta, C, V, p->pair_snp, d_bad);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+  } else {
+    UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
+  }
+  if (cnt8) {  // ABI 3: 8-bit base-call counts, offsets by an exclusive scan
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_cnt, (size_t)P + 1);  // one zero byte of slack: the scan's last output is the total
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt + P, 0, 1, ctx->stream);
+    if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(d_cnt, h->pair_nreads8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
+    size_t tb = 0;
+    thrust::transform_iterator<PsclU8ToU32, const uint8_t*, uint32_t, uint32_t> it((const uint8_t*)d_cnt, PsclU8ToU32());
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&d_scan_tmp, tb ? tb : 16);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
+    if (e == cudaSuccess) { k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, P, N, d_bad); ctx->launches += 2; e = cudaGetLastError(); }
+  } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
+  else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
   if (packed) {
     UP(rd_aq, h->read_aq, (size_t)N);
   } else {
@@ -230,8 +284,6 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
     if (e == cudaSuccess) e = up((void**)&d_q, h->read_qual, (size_t)N);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
   }
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
   if (e == cudaSuccess && N > 0) {
     if (packed) k_check_reads<<<(unsigned)((N + 4095) / 4096), 256, 0, ctx->stream>>>(p->rd_aq, N, d_bad);
     else k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, d_bad);
@@ -245,8 +297,8 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   UP(item_order, order.data(), sizeof(int32_t) * p->n_items);
   UP(cell_item_ptr, p->h_cell_item_ptr.data(), sizeof(int32_t) * (C + 1));
 #undef UP
-  if (e == cudaSuccess && !ptr32) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
-  if (e == cudaSuccess && P > 0 && !ptr32) {
+  if (e == cudaSuccess && !ptr32 && !cnt8) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
+  if (e == cudaSuccess && P > 0 && !ptr32 && !cnt8) {
     k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1);
     ctx->launches++;
     e = cudaGetLastError();
@@ -255,7 +307,11 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   // the host vectors above are pageable sources of async copies: drain before they go out of scope
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_al); cudaFree(d_q); cudaFree(d_bad);
+  cudaFree(d_al); cudaFree(d_q); cudaFree(d_bad); cudaFree(d_cnt); cudaFree(d_delta); cudaFree(d_first); cudaFree(d_scan_tmp);
+  if (e == cudaSuccess && bad > 1) {
+    pscl_plp_free(ctx, p);
+    return pscl_fail(ctx, PSCL_EINVAL, bad == 2 ? "pair_snp_delta16 decodes to a SNP id outside [0, n_snps)" : "pair_nreads8 does not sum to n_reads");
+  }
   if (e == cudaSuccess && bad) {
     pscl_plp_free(ctx, p);
     return pscl_fail(ctx, PSCL_EINVAL, "read_allele must be 0/1/2 and read_qual <= 63 (dsc-pileup writes phred <= 40, cmd_cram_dsc_pileup.cpp:19-20)");

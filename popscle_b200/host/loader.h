@@ -48,10 +48,16 @@ struct Loaded {
   // compact arrays of ABI 2 (filled by view() on first use): 32-bit read offsets, allele<<6|qual
   mutable std::vector<uint32_t> pair_read_ptr32;
   mutable std::vector<uint8_t> read_aq;
+  // delta-coded pair arrays of ABI 3: first SNP per cell, 16-bit SNP gaps, 8-bit base-call counts
+  mutable std::vector<int32_t> cell_first_snp;
+  mutable std::vector<uint16_t> pair_snp_delta16;
+  mutable std::vector<uint8_t> pair_nreads8;
+  mutable int delta_state = 0;  // 0 not tried, 1 usable, -1 a gap or a count does not fit
 
   pscl_pileup view() const {
     pscl_pileup p;
     p.pair_read_ptr32 = nullptr; p.read_aq = nullptr;
+    p.cell_first_snp = nullptr; p.pair_snp_delta16 = nullptr; p.pair_nreads8 = nullptr;
     if (read_allele.size() < (1ull << 32)) {  // halves the bytes pscl_plp_upload sends over PCIe
       if (pair_read_ptr32.size() != pair_read_ptr.size()) pair_read_ptr32.assign(pair_read_ptr.begin(), pair_read_ptr.end());
       bool ok = true;
@@ -63,6 +69,26 @@ struct Loaded {
         }
       }
       if (ok) { p.pair_read_ptr32 = pair_read_ptr32.data(); p.read_aq = read_aq.data(); }
+      if (ok && delta_state == 0) {  // 3 B per pair instead of 8: SNP ids rise within a cell, counts are small
+        const size_t P = pair_snp.size();
+        cell_first_snp.assign((size_t)n_cells, 0);
+        pair_snp_delta16.assign(P, 0);
+        pair_nreads8.assign(P, 0);
+        bool fits = true;
+        for (int32_t c = 0; c < n_cells && fits; ++c) {
+          const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
+          if (e > b) cell_first_snp[c] = pair_snp[b];
+          for (int64_t i = b; i < e; ++i) {
+            const int64_t d = i > b ? (int64_t)pair_snp[i] - pair_snp[i - 1] : 0, n = pair_read_ptr[i + 1] - pair_read_ptr[i];
+            if (d < 0 || d > 65535 || n < 0 || n > 255) { fits = false; break; }
+            pair_snp_delta16[i] = (uint16_t)d; pair_nreads8[i] = (uint8_t)n;
+          }
+        }
+        delta_state = fits ? 1 : -1;
+      }
+      if (ok && delta_state == 1) {
+        p.cell_first_snp = cell_first_snp.data(); p.pair_snp_delta16 = pair_snp_delta16.data(); p.pair_nreads8 = pair_nreads8.data();
+      }
     }
     p.n_cells = n_cells; p.n_snps = n_snps;
     p.n_pairs = (int64_t)pair_snp.size(); p.n_reads = (int64_t)read_allele.size();

@@ -40,7 +40,7 @@ def test_library_is_sm100a_only(built):
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==88 && offsetof(pscl_pileup, read_aq)==80 ? 0 : 1; }\n')
+    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==112 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
@@ -53,7 +53,7 @@ def test_no_cpu_fallback(built):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = capi.load_library()
-    assert lib.pscl_abi_version() == 2
+    assert lib.pscl_abi_version() == 3
     h = ctypes.c_void_p()
     err = ctypes.create_string_buffer(256)
     rc = lib.pscl_create(0, ctypes.byref(h), err, len(err))
@@ -83,10 +83,11 @@ def test_product_never_imports_the_oracle():
 
 
 def test_pileup_struct_matches_the_ctypes_mirror():
-    """ABI 2: the compact arrays sit behind the wide ones; the ctypes mirror has the same layout."""
+    """ABI 2/3: the compact arrays sit behind the wide ones; the ctypes mirror has the same layout."""
     import ctypes as C
     from popscle_b200 import capi
-    assert C.sizeof(capi.CPileup) == 88
+    assert C.sizeof(capi.CPileup) == 112
+    assert capi.CPileup.cell_first_snp.offset == 88 and capi.CPileup.pair_snp_delta16.offset == 96 and capi.CPileup.pair_nreads8.offset == 104
     assert capi.CPileup.pair_read_ptr32.offset == 72 and capi.CPileup.read_aq.offset == 80
     from popscle_b200 import synth
     s = synth.make_pileup(C=5, nv=2, V=50, kbar=50, seed=3)
@@ -95,3 +96,20 @@ def test_pileup_struct_matches_the_ctypes_mirror():
     assert ((aq >> 6) == s.plp.read_allele).all() and ((aq & 63) == s.plp.read_qual).all()
     cs = s.plp.c_struct(compact=True)
     assert cs.pair_read_ptr is None and cs.read_allele is None and cs.read_aq == aq.ctypes.data
+    # ABI 3: delta-coded pair arrays decode back to pair_snp / pair_read_ptr
+    first, d16, n8 = s.plp.compact3()
+    assert d16.dtype == np.uint16 and n8.dtype == np.uint8 and first.dtype == np.int32
+    snp = np.empty(s.plp.n_pairs, dtype=np.int64)
+    for c in range(s.plp.n_cells):
+        b, e = s.plp.cell_ptr[c], s.plp.cell_ptr[c + 1]
+        snp[b:e] = first[c] + np.cumsum(d16[b:e].astype(np.int64))
+    assert (snp == s.plp.pair_snp).all()
+    assert (np.concatenate([[0], np.cumsum(n8.astype(np.int64))]) == s.plp.pair_read_ptr).all()
+    cs = s.plp.c_struct(compact=3)
+    assert cs.pair_snp is None and cs.pair_read_ptr32 is None and cs.pair_nreads8 == n8.ctypes.data
+    wide = synth.make_pileup(C=3, nv=2, V=50, kbar=10, seed=4).plp
+    wide.n_snps = 200000
+    wide.pair_snp = wide.pair_snp.copy(); wide.pair_snp[wide.cell_ptr[1] - 1] = 199999  # a gap >= 65536: no delta form
+    assert wide.compact3() is None
+    cs = wide.c_struct(compact=3)
+    assert cs.pair_snp is not None and cs.pair_snp_delta16 is None

@@ -211,6 +211,40 @@ def test_compact_pileup_inputs_are_equivalent(ctx):
         ctx.demux_run(bad, synth.gt_to_gp(synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1).geno), None, DEFAULT, compact=True)
 
 
+def test_delta_coded_pileup_inputs_are_equivalent(ctx):
+    """ABI 3 delta-coded pair arrays (first SNP per cell, 16-bit gaps, 8-bit base-call counts) decode on the device to the
+    same image: bit-identical records for demuxlet and freemuxlet, with empty cells and a cell larger than one work
+    item; deltas that leave [0, n_snps) and counts that do not sum to n_reads are rejected."""
+    from popscle_b200 import PsclError
+    s = synth.make_pileup(C=40, nv=6, V=30000, kbar=1500, seed=4243)
+    assert np.diff(s.plp.cell_ptr).max() > 2048
+    q = s.plp
+    cp = np.insert(np.insert(q.cell_ptr, 3, q.cell_ptr[3]), 3, q.cell_ptr[3])  # two empty cells in the middle, one at the end
+    cp = np.append(cp, cp[-1])
+    plp = type(q)(len(cp) - 1, q.n_snps, cp, q.pair_snp, q.pair_read_ptr, q.read_allele, q.read_qual, q.snp_af)
+    assert plp.compact3() is not None
+    gp = synth.gt_to_gp(s.geno)
+    a = ctx.demux_run(plp, gp, None, DEFAULT)
+    b = ctx.demux_run(plp, gp, None, DEFAULT, compact=3)
+    assert a.tobytes() == b.tobytes()
+    fa = ctx.fmx_run(plp, ctx.fmx_opts(3))[0]
+    fb = ctx.fmx_run(plp, ctx.fmx_opts(3), compact=3)[0]
+    assert fa.tobytes() == fb.tobytes()
+    empty = synth.make_pileup(C=4, nv=2, V=50, kbar=20, seed=2)
+    empty.plp.cell_ptr[:] = 0
+    e = type(empty.plp)(4, 50, empty.plp.cell_ptr, empty.plp.pair_snp[:0], np.zeros(1, np.int64), empty.plp.read_allele[:0], empty.plp.read_qual[:0], None)
+    assert ctx.demux_run(e, synth.gt_to_gp(empty.geno), None, DEFAULT, compact=3).tobytes() == ctx.demux_run(e, synth.gt_to_gp(empty.geno), None, DEFAULT).tobytes()
+    for what in ("delta", "count"):
+        bad = synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1)
+        first, d16, n8 = bad.plp.compact3()
+        if what == "delta":
+            d16[bad.plp.cell_ptr[5] + 1] = 60000
+        else:
+            n8[7] += 1
+        with pytest.raises(PsclError):
+            ctx.demux_run(bad.plp, synth.gt_to_gp(bad.geno), None, DEFAULT, compact=3)
+
+
 @pytest.mark.parametrize("nv,na", [(2, 2), (3, 3), (9, 5), (17, 9), (33, 17), (5, 32)])
 def test_poly_shapes(ctx, nv, na):
     """every plane-count bucket of k_demux_poly (4/8/16/21/32) and sample counts that leave idle tile threads"""
