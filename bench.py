@@ -468,9 +468,12 @@ def main():
         out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
+    per_call = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        tc = time.perf_counter()
         out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
+        per_call.append(round((time.perf_counter() - tc) * 1e3, 3))
     torch.cuda.synchronize()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -494,7 +497,7 @@ def main():
                            "l2": "flushed between timed steps (256 MiB memset, untimed)"},
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "api": "pscl_demux_run (pinned host buffers in ABI-3 compact form: 3 B per pair, 1 B per base-call; per-cell records out)"},
+                        "steps": e2e_steps, "ms_per_call": per_call, "api": "pscl_demux_run (pinned host buffers in ABI-3 compact form: 3 B per pair, 1 B per base-call; per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_demux(s, gp, nv, args.cpu_seconds, os.cpu_count() or 1)

@@ -18,6 +18,7 @@
 
 #include "../../include/popscle_b200.h"
 
+#define PSCL_MAX_STAGES 16 /* slices of a staged pscl_demux_run (copy of slice k+1 under the scoring of slice k) */
 #define PSCL_MAX_ALPHA 32 /* pG fold keeps n_alpha*9 values in one warp's registers (<= 9 per lane) */
 
 struct pscl_plp {
@@ -53,6 +54,13 @@ struct pscl_plp {
   double* dmx_deep = nullptr;        // [n_deep][6] folded factors of the pairs with > 3 usable base-calls
   uint4* dmx_desc_nat = nullptr;     // [n_items] {first packet, end packet, item, -}, natural item order
   uint4* dmx_desc_sorted = nullptr;  // [n_items] the same in item_order
+  // ABI-3 delta form: first SNP per cell and 16-bit gaps (kept only while a staged pscl_demux_run decodes them slice
+  // by slice), the upload's validity flag, and the slices themselves (cells [stage_cell[k], stage_cell[k+1]))
+  int32_t* d_first = nullptr;
+  uint16_t* d_delta = nullptr;
+  int* d_bad = nullptr;
+  int n_stages = 0;
+  int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};
 };
 
 struct pscl_fmx_state;
@@ -65,6 +73,10 @@ struct pscl_ctx {
   std::string err;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D slices of a staged pscl_demux_run
+  cudaEvent_t stage_go = nullptr;
+  int* stage_flags = nullptr;          // device [PSCL_MAX_STAGES]: slice k has landed (written by the copy queue)
+  int* h_one = nullptr;                // pinned host word holding 1, the source of those flag writes
   double* fold_tab = nullptr;   // [3][64][6] per-read factors of the default alpha grid (demux.inl)
   double* phred_err = nullptr;  // [256] device copy of PhredHelper's phred2Err (staged to smem by kernels)
   // demuxlet state

@@ -33,6 +33,9 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   cudaEventCreate(&c->ev2);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->stage_go, cudaEventDisableTiming);
+  if (cudaHostAlloc((void**)&c->h_one, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_one = 1;
   {  // keep freed blocks mapped in the device's default pool (see common.cuh: device memory)
     cudaMemPool_t pool = nullptr;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -61,7 +64,7 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
       cudaMemcpyAsync(c->fold_tab, ftab, sizeof(ftab), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
       cudaMalloc((void**)&c->phred_err, sizeof(tab)) != cudaSuccess ||
       cudaMemcpyAsync(c->phred_err, tab, sizeof(tab), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-      cudaMalloc((void**)&c->dm_counter, 64) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      cudaMalloc((void**)&c->dm_counter, 64) != cudaSuccess || cudaMalloc((void**)&c->stage_flags, sizeof(int) * PSCL_MAX_STAGES) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
     delete c;
     return fail(PSCL_ENOMEM, "device allocation failed in pscl_create");
   }
@@ -90,6 +93,10 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev2);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->stage_go) cudaEventDestroy(ctx->stage_go);
+  if (ctx->h_one) cudaFreeHost(ctx->h_one);
+  cudaFree(ctx->stage_flags);
   cudaStreamSynchronize(ctx->stream);
   {  // hand the cached blocks back to the driver
     cudaMemPool_t pool = nullptr;
@@ -149,22 +156,53 @@ __global__ void k_check_reads(const uint8_t* __restrict__ aq, int64_t n, int* ba
   if (b) atomicExch(bad, 1);
 }
 
-// ABI 3: SNP ids from 16-bit deltas, one warp per cell (inclusive scan of the deltas on top of the cell's first id)
+// ABI 3: SNP ids from 16-bit gaps, one warp per cell.  A lane takes 8 consecutive gaps (one 16-byte load, the next
+// batch of 256 already in flight), sums them locally, the warp scans the lane totals on top of the running id.  The
+// first gap of a cell is ignored (its id is cell_first_snp); ids only grow, so every id is range-checked cheaply.
 __global__ void k_decode_snp(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ first, const uint16_t* __restrict__ delta,
-                             int32_t C, int32_t V, int32_t* __restrict__ pair_snp, int* bad) {
-  const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (c >= C) return;
+                             int32_t c_begin, int32_t c_end, int32_t V, int32_t* __restrict__ pair_snp, int* bad) {
+  const int c = c_begin + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (c >= c_end) return;
   const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
-  int run = (b < e) ? first[c] : 0;
-  for (int64_t p0 = b; p0 < e; p0 += 32) {
-    const int64_t p = p0 + lane;
-    int v = (p < e && p > b) ? (int)delta[p] : 0;
+  if (b >= e) return;
+  int run = first[c];
+  bool oob = run < 0 || run >= V;
+  auto fetch = [&](int64_t base) {
+    const int64_t p = base + lane * 8;
+    return (p < e) ? *reinterpret_cast<const uint4*>(delta + p) : make_uint4(0u, 0u, 0u, 0u);  // delta has 16 B of slack
+  };
+  int64_t base = b & ~(int64_t)7;
+  uint4 cur = fetch(base);
+  for (; base < e; base += 256) {
+    const uint4 nxt = fetch(base + 256);
+    const int64_t p = base + lane * 8;
+    const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+    int x[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-    v += run;
-    if (p < e) { pair_snp[p] = v; if (v < 0 || v >= V) atomicExch(bad, 2); }
-    run = __shfl_sync(0xffffffffu, v, 31);
+    for (int i = 0; i < 8; ++i) {
+      const int64_t q = p + i;
+      const int d = (int)((w[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+      x[i] = (q > b && q < e) ? d : 0;
+    }
+#pragma unroll
+    for (int i = 1; i < 8; ++i) x[i] += x[i - 1];
+    int tot = x[7], inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const int off = run + inc - tot;
+    if (p >= b && p + 8 <= e) {
+      int4* dst = reinterpret_cast<int4*>(pair_snp + p);
+      dst[0] = make_int4(off + x[0], off + x[1], off + x[2], off + x[3]);
+      dst[1] = make_int4(off + x[4], off + x[5], off + x[6], off + x[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int64_t q = p + i; if (q >= b && q < e) pair_snp[q] = off + x[i]; }
+    }
+    run = __shfl_sync(0xffffffffu, off + tot, 31);
+    oob |= run < 0 || run >= V;  // ids are non-decreasing: the running maximum is the last one
+    cur = nxt;
   }
+  if (oob && lane == 0) atomicExch(bad, 2);
 }
 // ABI 3: read offsets from 8-bit counts are an exclusive scan (CUB); this checks that they end at n_reads
 __global__ void k_check_total(const uint32_t* __restrict__ pair_rd, int64_t P, int64_t N, int* bad) {
@@ -180,9 +218,20 @@ __global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restric
   if (i < n) out[i] = (uint32_t)in[i];
 }
 
+static const char* pscl_bad_pileup_msg(int bad) {
+  return bad == 2 ? "pair_snp_delta16 decodes to a SNP id outside [0, n_snps)"
+       : bad == 3 ? "pair_nreads8 does not sum to n_reads"
+                  : "read_allele must be 0/1/2 and read_qual <= 63 (dsc-pileup writes phred <= 40, cmd_cram_dsc_pileup.cpp:19-20)";
+}
+
 extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
   if (!p) return;
-  if (ctx) { t_pscl_stream = ctx->stream; cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ctx) {
+    t_pscl_stream = ctx->stream; cudaSetDevice(ctx->device);
+    if (p->n_stages && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // slices still in flight write into d_delta
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_bad);
   cudaFree(p->cell_ptr); cudaFree(p->pair_snp); cudaFree(p->pair_rd); cudaFree(p->rd_aq);
   cudaFree(p->snp_af); cudaFree(p->item_cell); cudaFree(p->item_pbeg);
   cudaFree(p->item_pend); cudaFree(p->item_order); cudaFree(p->cell_item_ptr); cudaFree(p->snp_ptr);
@@ -192,11 +241,16 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
   delete p;
 }
 
-extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out) {
-  if (!ctx) return PSCL_EINVAL;
-  PsclScope scope__(ctx);
+// Host image -> device image.  `stages` > 1 (pscl_demux_run only, ABI-3 delta arrays) leaves the SNP gaps out of the
+// synchronous part: they cross PCIe on ctx->copy_stream in `stages` slices of whole cells, one event per slice, while
+// the caller scores the slices that have arrived (pscl_demux_run); the decode kernel then runs per slice.
+static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages) {
   if (!h || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_plp_upload: NULL argument");
   *out = nullptr;
+  static const bool trace = getenv("PSCL_TRACE") != nullptr;  // wall-clock of the upload's phases on stderr
+  auto tnow = [&](bool drain) { if (trace && drain) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+  auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto tr0 = tnow(false);
   const int32_t C = h->n_cells, V = h->n_snps;
   const int64_t P = h->n_pairs, N = h->n_reads;
   if (C < 0 || V < 0 || P < 0 || N < 0) return pscl_fail(ctx, PSCL_EINVAL, "negative size in pscl_pileup");
@@ -214,28 +268,12 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   if (P > 0 && !cnt8 && (ptr32 ? (h->pair_read_ptr32[0] != 0 || (int64_t)h->pair_read_ptr32[P] != N) : (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N)))
     return pscl_fail(ctx, PSCL_EINVAL, "pair_read_ptr must run from 0 to n_reads");
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!dsnp || P == 0 || C < 2 || !ctx->copy_stream || !ctx->h_one) stages = 1;
+  if (stages > PSCL_MAX_STAGES) stages = PSCL_MAX_STAGES;
   pscl_plp* p = new pscl_plp();
   p->C = C; p->V = V; p->P = P; p->N = N;
-  p->h_cell_ptr.assign(h->cell_ptr, h->cell_ptr + C + 1);
-  // work items
-  std::vector<int32_t> item_cell;
-  std::vector<int64_t> pbeg, pend;
-  p->h_cell_item_ptr.resize(C + 1);
-  for (int32_t c = 0; c < C; ++c) {
-    p->h_cell_item_ptr[c] = (int32_t)item_cell.size();
-    int64_t b = h->cell_ptr[c], e = h->cell_ptr[c + 1], n = e - b;
-    int64_t nch = (n + PSCL_ITEM_PAIRS - 1) / PSCL_ITEM_PAIRS;
-    for (int64_t i = 0; i < nch; ++i) {  // equal split, multiples of 32 pairs
-      int64_t s = b + ((n * i / nch) & ~(int64_t)31), t = (i + 1 == nch) ? e : b + ((n * (i + 1) / nch) & ~(int64_t)31);
-      item_cell.push_back(c); pbeg.push_back(s); pend.push_back(t);
-    }
-  }
-  p->h_cell_item_ptr[C] = (int32_t)item_cell.size();
-  p->n_items = (int32_t)item_cell.size();
-  std::vector<int32_t> order(p->n_items);
-  for (int32_t i = 0; i < p->n_items; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return pend[a] - pbeg[a] > pend[b] - pbeg[b]; });
 
+  // ---- 1. the big arrays first: their copies run while the host builds the work items below -------
   auto up = [&](void** d, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(d, bytes ? bytes : 16);
     if (e != cudaSuccess) return e;
@@ -246,35 +284,14 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
 #define UP(field, src, bytes) do { if (e == cudaSuccess) e = up((void**)&p->field, src, bytes); } while (0)
   UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
   uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr;
-  uint16_t* d_delta = nullptr;
-  int32_t* d_first = nullptr;
   void* d_scan_tmp = nullptr;
-  int* d_bad = nullptr;
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_bad, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
-  if (dsnp) {  // ABI 3: 16-bit SNP deltas, decoded per cell
-    if (e == cudaSuccess) e = up((void**)&d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P);
-    if (e == cudaSuccess) e = up((void**)&d_first, h->cell_first_snp, sizeof(int32_t) * C);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_snp, sizeof(int32_t) * (P ? P : 1));
-    if (e == cudaSuccess && C > 0) {
-      k_decode_snp<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, d_first, d_delta, C, V, p->pair_snp, d_bad);
-      ctx->launches++;
-      e = cudaGetLastError();
-    }
-  } else {
-    UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
-  }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_bad, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_bad, 0, sizeof(int), ctx->stream);
   if (cnt8) {  // ABI 3: 8-bit base-call counts, offsets by an exclusive scan
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_cnt, (size_t)P + 1);  // one zero byte of slack: the scan's last output is the total
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt + P, 0, 1, ctx->stream);
     if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(d_cnt, h->pair_nreads8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
-    size_t tb = 0;
-    thrust::transform_iterator<PsclU8ToU32, const uint8_t*, uint32_t, uint32_t> it((const uint8_t*)d_cnt, PsclU8ToU32());
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&d_scan_tmp, tb ? tb : 16);
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
-    if (e == cudaSuccess) { k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, P, N, d_bad); ctx->launches += 2; e = cudaGetLastError(); }
   } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
   else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
   if (packed) {
@@ -284,37 +301,121 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
     if (e == cudaSuccess) e = up((void**)&d_q, h->read_qual, (size_t)N);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
   }
-  if (e == cudaSuccess && N > 0) {
-    if (packed) k_check_reads<<<(unsigned)((N + 4095) / 4096), 256, 0, ctx->stream>>>(p->rd_aq, N, d_bad);
-    else k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, d_bad);
-    ctx->launches++;
-    e = cudaGetLastError();
+  if (dsnp) {  // ABI 3: 16-bit SNP gaps, decoded per cell
+    if (e == cudaSuccess) e = up((void**)&p->d_first, h->cell_first_snp, sizeof(int32_t) * C);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_delta, sizeof(uint16_t) * (size_t)P + 16);  // k_decode_snp reads whole 16-byte groups
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_snp, sizeof(int32_t) * (P ? P : 1));
+    if (stages > 1) {  // slices of whole cells with about equal pair counts; their copies are queued in step 2b
+      p->n_stages = stages;
+      p->stage_cell[0] = 0;
+      for (int k = 1; k < stages; ++k) {
+        const int64_t want = P * k / stages;
+        int32_t c = (int32_t)(std::lower_bound(h->cell_ptr, h->cell_ptr + C + 1, want) - h->cell_ptr);
+        p->stage_cell[k] = std::max(p->stage_cell[k - 1], std::min(c, C));
+      }
+      p->stage_cell[stages] = C;
+    } else if (e == cudaSuccess && P > 0) {
+      e = cudaMemcpyAsync(p->d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P, cudaMemcpyHostToDevice, ctx->stream);
+    }
+  } else {
+    UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
   }
   if (h->snp_af) UP(snp_af, h->snp_af, sizeof(double) * V);
+  const auto tr1 = tnow(false);
+
+  // ---- 2. work items (host; overlaps the copies) -------------------------------------------------------
+  p->h_cell_ptr.assign(h->cell_ptr, h->cell_ptr + C + 1);
+  std::vector<int32_t> item_cell;
+  std::vector<int64_t> pbeg, pend;
+  item_cell.reserve((size_t)C + (size_t)(P / PSCL_ITEM_PAIRS) + 1);
+  pbeg.reserve(item_cell.capacity()); pend.reserve(item_cell.capacity());
+  p->h_cell_item_ptr.resize(C + 1);
+  for (int32_t c = 0; c < C; ++c) {
+    p->h_cell_item_ptr[c] = (int32_t)item_cell.size();
+    int64_t b = h->cell_ptr[c], e2 = h->cell_ptr[c + 1], n = e2 - b;
+    int64_t nch = (n + PSCL_ITEM_PAIRS - 1) / PSCL_ITEM_PAIRS;
+    for (int64_t i = 0; i < nch; ++i) {  // equal split, multiples of 32 pairs
+      int64_t s0 = b + ((n * i / nch) & ~(int64_t)31), t = (i + 1 == nch) ? e2 : b + ((n * (i + 1) / nch) & ~(int64_t)31);
+      item_cell.push_back(c); pbeg.push_back(s0); pend.push_back(t);
+    }
+  }
+  p->h_cell_item_ptr[C] = (int32_t)item_cell.size();
+  p->n_items = (int32_t)item_cell.size();
+  // items by descending size, ties in natural order: a counting sort (sizes are <= PSCL_ITEM_PAIRS + 31).  A staged
+  // image is ordered slice by slice, so that the kernel's first items are the ones whose gaps land first.
+  std::vector<int32_t> order(p->n_items);
+  {
+    const int NB = PSCL_ITEM_PAIRS + 64;
+    std::vector<int32_t> head(NB + 1);
+    const int nseg = p->n_stages > 1 ? p->n_stages : 1;
+    for (int k = 0; k < nseg; ++k) {
+      const int32_t ib = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k]] : 0;
+      const int32_t ie = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k + 1]] : p->n_items;
+      std::fill(head.begin(), head.end(), 0);
+      for (int32_t i = ib; i < ie; ++i) head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1) + 1]++;
+      for (int b2 = 0; b2 < NB; ++b2) head[b2 + 1] += head[b2];
+      for (int32_t i = ib; i < ie; ++i) order[ib + head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1)]++] = i;
+    }
+  }
+  const auto tr2 = tnow(false);
   UP(item_cell, item_cell.data(), sizeof(int32_t) * p->n_items);
   UP(item_pbeg, pbeg.data(), sizeof(int64_t) * p->n_items);
   UP(item_pend, pend.data(), sizeof(int64_t) * p->n_items);
   UP(item_order, order.data(), sizeof(int32_t) * p->n_items);
   UP(cell_item_ptr, p->h_cell_item_ptr.data(), sizeof(int32_t) * (C + 1));
 #undef UP
-  if (e == cudaSuccess && !ptr32 && !cnt8) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
-  if (e == cudaSuccess && P > 0 && !ptr32 && !cnt8) {
-    k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1);
+  // ---- 2b. staged image: the gaps go last, slice by slice on the copy stream, a flag word behind each slice ----------
+  if (p->n_stages > 1) {
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->stage_flags, 0, sizeof(int) * PSCL_MAX_STAGES, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_go, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_go, 0);
+    for (int k = 0; k < p->n_stages && e == cudaSuccess; ++k) {
+      const int64_t pb = h->cell_ptr[p->stage_cell[k]], pe = h->cell_ptr[p->stage_cell[k + 1]];
+      if (pe > pb) e = cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->stage_flags + k, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream);
+    }
+  }
+
+  // ---- 3. device-side decoding and checks ------------------------------------------------------------
+  if (dsnp && p->n_stages == 0 && e == cudaSuccess && C > 0 && P > 0) {
+    k_decode_snp<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta, 0, C, V, p->pair_snp, p->d_bad);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (cnt8) {
+    size_t tb = 0;
+    thrust::transform_iterator<PsclU8ToU32, const uint8_t*, uint32_t, uint32_t> it((const uint8_t*)d_cnt, PsclU8ToU32());
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&d_scan_tmp, tb ? tb : 16);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
+    if (e == cudaSuccess) { k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, P, N, p->d_bad); ctx->launches += 2; e = cudaGetLastError(); }
+  } else if (!ptr32) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
+    if (e == cudaSuccess) {
+      k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess && N > 0) {
+    if (packed) k_check_reads<<<(unsigned)((N + 4095) / 4096), 256, 0, ctx->stream>>>(p->rd_aq, N, p->d_bad);
+    else k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
   }
   int bad = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, p->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   // the host vectors above are pageable sources of async copies: drain before they go out of scope
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_al); cudaFree(d_q); cudaFree(d_bad); cudaFree(d_cnt); cudaFree(d_delta); cudaFree(d_first); cudaFree(d_scan_tmp);
-  if (e == cudaSuccess && bad > 1) {
-    pscl_plp_free(ctx, p);
-    return pscl_fail(ctx, PSCL_EINVAL, bad == 2 ? "pair_snp_delta16 decodes to a SNP id outside [0, n_snps)" : "pair_nreads8 does not sum to n_reads");
+  cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp);
+  if (p->n_stages == 0) { cudaFree(p->d_delta); cudaFree(p->d_first); p->d_delta = nullptr; p->d_first = nullptr; }
+  if (trace) {
+    const auto tr3 = tnow(false);
+    fprintf(stderr, "[pscl_plp_upload] checks + enqueue %.3f ms | work items (host) %.3f | item arrays, decode, drain %.3f | stages %d\n", tms(tr0, tr1), tms(tr1, tr2), tms(tr2, tr3), p->n_stages);
   }
   if (e == cudaSuccess && bad) {
     pscl_plp_free(ctx, p);
-    return pscl_fail(ctx, PSCL_EINVAL, "read_allele must be 0/1/2 and read_qual <= 63 (dsc-pileup writes phred <= 40, cmd_cram_dsc_pileup.cpp:19-20)");
+    return pscl_fail(ctx, PSCL_EINVAL, "%s", pscl_bad_pileup_msg(bad));
   }
   if (e != cudaSuccess) {
     pscl_plp_free(ctx, p);
@@ -324,4 +425,10 @@ extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** o
   p->scratch_h2d = nullptr;
   *out = p;
   return PSCL_OK;
+}
+
+extern "C" int pscl_plp_upload(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out) {
+  if (!ctx) return PSCL_EINVAL;
+  PsclScope scope__(ctx);
+  return plp_upload_impl(ctx, h, out, 1);
 }

@@ -74,9 +74,19 @@ struct DemuxArgs {
   int* counter;
   int32_t item_base, n_work;
   int32_t nv, nalpha;
+  // staged run (k_demux_default<NV, true>): SNP ids come from the ABI-3 gaps, which are still crossing PCIe in slices of
+  // whole cells when the kernel starts; flags[k] is written behind slice k by the same copy queue
+  const uint16_t* delta = nullptr;     // [P] gap to the previous pair's SNP id (ignored at a cell's first pair)
+  const int32_t* first = nullptr;      // [C] SNP id of each cell's first pair
+  const int64_t* cell_ptr = nullptr;   // [C+1]
+  const int32_t* item_cell = nullptr;  // [n_items]
+  const int* flags = nullptr;          // [n_stages]
+  int* bad = nullptr;                  // 2: SNP id out of range, 4: a slice never arrived
+  int32_t n_snps = 0, n_stages = 0;
+  int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};
 };
 
-template <int NV>
+template <int NV, bool DELTA>
 __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
   constexpr int NE = Cfg::NE, ND = Cfg::ND, SD = Cfg::STRIDE_D;
@@ -101,6 +111,33 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     const int item = a.item_order ? a.item_order[w] : a.item_base + w;
     const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
     const int niter = (int)((pe - pb + 31) >> 5);
+    int snp_run = 0;       // DELTA: SNP id of the pair before the next 32
+    int64_t cell_pb = -1;  // DELTA: first pair of the item's cell
+    if constexpr (DELTA) {
+      const int c = a.item_cell[item];
+      cell_pb = a.cell_ptr[c];
+      int k = 0;
+      for (int i = 1; i < a.n_stages; ++i) k += (c >= a.stage_cell[i]) ? 1 : 0;
+      if (lane == 0) {  // wait for the slice (bounded: a copy that never lands must not hang the device)
+        const long long t_start = clock64();
+        for (;;) {
+          int f;
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(f) : "l"(a.flags + k) : "memory");
+          if (f) break;
+          __nanosleep(200);
+          if (clock64() - t_start > (1ll << 32)) { atomicExch(a.bad, 4); break; }
+        }
+      }
+      __syncwarp();
+      snp_run = a.first[c];
+      if (pb > cell_pb) {  // a later work item of a large cell: id of the pair before it
+        int sum = 0;
+        for (int64_t q = cell_pb + 1 + lane; q < pb; q += 32) sum += (int)a.delta[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        snp_run += sum;
+      }
+    }
 
     double acc[NE];
 #pragma unroll
@@ -116,9 +153,22 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     auto loadA = [&](int it) {
       int64_t p = pb + ((int64_t)it << 5) + lane;
       okA = (it < niter) && (p < pe);
-      if (okA) { snpA = a.pair_snp[p]; r0A = a.pair_rd[p]; r1A = a.pair_rd[p + 1]; }
+      if (okA) {
+        if constexpr (DELTA) snpA = (p == cell_pb) ? 0 : (int32_t)a.delta[p];  // the gap; issueB turns it into the id
+        else snpA = a.pair_snp[p];
+        r0A = a.pair_rd[p]; r1A = a.pair_rd[p + 1];
+      }
     };
     auto issueB = [&](int buf) {  // consumes stage A
+      if constexpr (DELTA) {  // inclusive scan of the 32 gaps on top of the running id
+        int v = okA ? snpA : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        v += snp_run;
+        snp_run = __shfl_sync(0xffffffffu, v, 31);
+        snpA = v;
+        if (okA && (unsigned)v >= (unsigned)a.n_snps) { okA = false; atomicExch(a.bad, 2); }
+      }
       r0B = r0A; r1B = r1A; hasB = 0; b0B = b1B = b2B = PSCL_FOLD_ONES << 6;  // placeholder: "no read"
       if (okA) {
         hasB = 1;
@@ -728,14 +778,16 @@ static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
   using Cfg = DefaultCfg<NV>;
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
   int grid = ctx->sm_count;
   if (grid * 8 > a.n_work) grid = (a.n_work + 7) / 8;
   if (grid < 1) grid = 1;
-  k_demux_default<NV><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
+  if (a.delta) k_demux_default<NV, true><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
+  else k_demux_default<NV, false><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -804,6 +856,13 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
       a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend;
       a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
       a.item_base = ib; a.n_work = nwork; a.nv = nv; a.nalpha = na;
+      if (plp->n_stages > 1) {  // staged pscl_demux_run: ids from the gaps, slice by slice as they land
+        if (!use_default || use_ws || a.item_order == nullptr)
+          return pscl_fail(ctx, PSCL_ESTATE, "a staged pileup image can only be scored whole by k_demux_default");
+        a.delta = plp->d_delta; a.first = plp->d_first; a.cell_ptr = plp->cell_ptr; a.item_cell = plp->item_cell;
+        a.flags = ctx->stage_flags; a.bad = plp->d_bad; a.n_snps = plp->V; a.n_stages = plp->n_stages;
+        for (int k = 0; k <= plp->n_stages; ++k) a.stage_cell[k] = plp->stage_cell[k];
+      }
       cudaError_t e = cudaSuccess;
       if (use_ws) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
@@ -936,25 +995,50 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
   static const bool trace = getenv("PSCL_TRACE") != nullptr;
   auto now = [&]() { if (trace) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  // Staged run: with the ABI-3 delta arrays and the default kernel's shape, the SNP gaps (the largest array) cross PCIe in
+  // slices of whole cells on a second stream, each followed by a 4-byte flag.  The scoring kernel is launched once, as
+  // soon as everything else is on the device; it takes its work items slice by slice, decodes the gaps itself and waits
+  // on a slice's flag before touching it, so the scoring hides under the copy except for the last slice.  Cells are
+  // independent (cmd_cram_demuxlet.cpp:636) and every cell is summed in the same order, so no record changes.
+  // PSCL_STAGES=n overrides the slice count (1 = off).
+  int stages = 1;
+  if (!llk_grid && !ctx->keep_grid && !ctx->force_general && ctx->demux_kernel <= 1 && opts->alphas && opts->n_alpha == 2 &&
+      opts->alphas[0] == 0.0 && opts->alphas[1] == 0.5 && geno->n_samples >= 2 && geno->n_samples <= 8 &&
+      host->pair_snp_delta16 && host->cell_first_snp && host->n_pairs < ((int64_t)1 << 30)) {
+    if (const char* sv = getenv("PSCL_STAGES")) stages = atoi(sv);
+    else if (host->n_pairs >= ((int64_t)1 << 22)) stages = (int)std::min<int64_t>(PSCL_MAX_STAGES, host->n_pairs / 1250000);  // ~2.5 MB of gaps per slice
+    if (stages < 1) stages = 1;
+  }
   const auto t0 = now();
-  pscl_plp* plp = nullptr;
-  int rc = pscl_plp_upload(ctx, host, &plp);
+  int rc = pscl_demux_set_geno(ctx, geno, host->n_snps);  // genotypes first: every slice needs them
   if (rc != PSCL_OK) return rc;
   const auto t1 = now();
-  rc = pscl_demux_set_geno(ctx, geno, host->n_snps);
+  pscl_plp* plp = nullptr;
+  rc = plp_upload_impl(ctx, host, &plp, stages);
+  if (rc != PSCL_OK) return rc;
   const auto t2 = now();
   bool keep = ctx->keep_grid;
-  if (rc == PSCL_OK && llk_grid) ctx->keep_grid = true;
-  if (rc == PSCL_OK) rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);
+  int bad = 0;
+  if (plp->n_stages > 1) {
+    rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);  // one launch; its warps wait on the slice flags
+    if (rc == PSCL_OK && cudaMemcpyAsync(&bad, plp->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      rc = pscl_fail(ctx, PSCL_ECUDA, "staged run: flag read-back failed");
+  } else {
+    if (llk_grid) ctx->keep_grid = true;
+    rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);
+  }
   const auto t3 = now();
   if (rc == PSCL_OK) rc = pscl_demux_fetch(ctx, out, llk_grid);
+  if (rc == PSCL_OK && bad == 4) rc = pscl_fail(ctx, PSCL_ECUDA, "staged run: a slice of pair_snp_delta16 never reached the device");
+  else if (rc == PSCL_OK && bad) rc = pscl_fail(ctx, PSCL_EINVAL, "%s", pscl_bad_pileup_msg(bad));
   const auto t4 = now();
   ctx->keep_grid = keep;
   std::string err = ctx->err;
+  const int n_st = plp->n_stages;
   pscl_plp_free(ctx, plp);
   ctx->err = err;
   if (trace)
-    fprintf(stderr, "[pscl_demux_run] upload %.3f ms | set_geno %.3f | score %.3f | fetch %.3f | free %.3f\n", ms(t0, t1), ms(t1, t2),
-            ms(t2, t3), ms(t3, t4), ms(t4, now()));
+    fprintf(stderr, "[pscl_demux_run] set_geno %.3f ms | upload %.3f | score %.3f (%d slices) | fetch %.3f | free %.3f\n", ms(t0, t1), ms(t1, t2),
+            ms(t2, t3), n_st, ms(t3, t4), ms(t4, now()));
   return rc;
 }

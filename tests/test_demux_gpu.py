@@ -1,4 +1,6 @@
 """GPU parity of the demuxlet path (through the C ABI) against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -230,6 +232,17 @@ def test_delta_coded_pileup_inputs_are_equivalent(ctx):
     fa = ctx.fmx_run(plp, ctx.fmx_opts(3))[0]
     fb = ctx.fmx_run(plp, ctx.fmx_opts(3), compact=3)[0]
     assert fa.tobytes() == fb.tobytes()
+    # staged run: the SNP gaps cross in slices of whole cells on a second stream, each slice decoded and scored as it lands
+    try:
+        for n in ("2", "3", "8", "50"):
+            os.environ["PSCL_STAGES"] = n
+            assert ctx.demux_run(plp, gp, None, DEFAULT, compact=3).tobytes() == a.tobytes(), n
+        bad = synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1)
+        bad.plp.compact3()[1][bad.plp.cell_ptr[15] + 1] = 60000
+        with pytest.raises(PsclError):
+            ctx.demux_run(bad.plp, synth.gt_to_gp(bad.geno), None, DEFAULT, compact=3)
+    finally:
+        os.environ.pop("PSCL_STAGES", None)
     empty = synth.make_pileup(C=4, nv=2, V=50, kbar=20, seed=2)
     empty.plp.cell_ptr[:] = 0
     e = type(empty.plp)(4, 50, empty.plp.cell_ptr, empty.plp.pair_snp[:0], np.zeros(1, np.int64), empty.plp.read_allele[:0], empty.plp.read_qual[:0], None)

@@ -58,6 +58,8 @@ def test_config2_sharding_and_sample_permutation(ctx, cfg2):
     s, gp = cfg2
     plp = s.plp
     full = ctx.demux_run(plp, gp, None, DEFAULT, compact=True)
+    staged = ctx.demux_run(plp, gp, None, DEFAULT, compact=3)  # ABI-3 delta arrays: copied in slices under the scoring
+    assert staged.tobytes() == full.tobytes()
     cuts = [0, 1234, 1235, 6000, plp.n_cells]
     parts = [ctx.demux_run(plp.slice_cells(a, b), gp, None, DEFAULT) for a, b in zip(cuts[:-1], cuts[1:])]
     assert np.concatenate(parts).tobytes() == full.tobytes()  # barcode shards are bit-identical
