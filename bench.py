@@ -42,8 +42,9 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel", default="lane", choices=["lane", "cls", "ab", "general"],
-                    help="demuxlet accumulation kernel: k_demux_default (default), k_demux_cls, k_demux_general")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "lane", "dict", "cls", "ab", "general"],
+                    help="demuxlet accumulation kernel: auto (the library's choice: k_demux_default on dictionary-coded genotypes "
+                         "for this workload), lane (k_demux_default on gathered genotype rows), k_demux_cls, k_demux_ab, k_demux_general")
     return ap.parse_args()
 
 
@@ -401,8 +402,8 @@ def main():
     plp, nv = s.plp, cfg["nv"]
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
-    ctx.demux_select_kernel({"lane": 1, "general": 2, "cls": 3, "ab": 5}[args.kernel])
-    kname = {"cls": "k_demux_cls", "ab": "k_demux_ab", "lane": "k_demux_default", "general": "k_demux_general"}[args.kernel]
+    ctx.demux_select_kernel({"auto": 0, "lane": 1, "general": 2, "cls": 3, "ab": 5, "dict": 6}[args.kernel])
+    kname = None  # named after the first scoring pass, from what the library launched
 
     # ---- device-resident arm ("value") ----------------------------------------------------------
     dplp = ctx.upload(plp)
@@ -433,6 +434,8 @@ def main():
         main_ms.append(ctx.demux_last_kernel_ms()[0])
     barrier()
     launches = ctx.launch_count - l0
+    kname = {1: "k_demux_default", 6: "k_demux_default_dict", 2: "k_demux_general", 3: "k_demux_cls", 4: "k_demux_poly",
+             5: "k_demux_ab"}[ctx.demux_last_kernel()]
     clocks = sampler.stop() if rank == 0 else None
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([t_ms], dtype=torch.float64, device="cuda")

@@ -215,6 +215,7 @@ def load_library() -> C.CDLL:
         "pscl_demux_select_kernel": (C.c_int, [vp, C.c_int]),
         "pscl_demux_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CGeno), C.POINTER(CDemuxOpts), vp, vp]),
         "pscl_demux_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "pscl_demux_last_kernel": (C.c_int, [vp]),
         "pscl_fmx_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult)]),
         "pscl_fmx_init": (C.c_int, [vp, vp, C.POINTER(CFmxOpts)]),
         "pscl_fmx_stage1": (C.c_int, [vp, vp]),
@@ -237,7 +238,7 @@ EXPORTED_SYMBOLS = [
     "pscl_abi_version", "pscl_create", "pscl_destroy", "pscl_last_error", "pscl_stream", "pscl_set_stream",
     "pscl_sync", "pscl_launch_count", "pscl_set_partial_budget", "pscl_plp_upload", "pscl_plp_free",
     "pscl_demux_set_geno", "pscl_demux_score", "pscl_demux_fetch", "pscl_demux_keep_grid",
-    "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_fmx_run", "pscl_fmx_init",
+    "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_demux_last_kernel", "pscl_fmx_run", "pscl_fmx_init",
     "pscl_fmx_stage1", "pscl_fmx_seed", "pscl_fmx_mstep", "pscl_fmx_estep", "pscl_fmx_classify",
     "pscl_fmx_fetch", "pscl_fmx_last_kernel_ms",
 ]
@@ -323,8 +324,13 @@ class Context:
         self._chk(self.lib.pscl_demux_force_general(self.h, int(enable)))
 
     def demux_select_kernel(self, which: int):
-        """0 = auto, 1 = k_demux_default, 2 = k_demux_general, 3 = k_demux_cls, 4 = k_demux_poly (see popscle_b200.h)."""
+        """0 = auto, 1 = k_demux_default on genotype rows, 2 = k_demux_general, 3 = k_demux_cls, 4 = k_demux_poly,
+        5 = k_demux_ab, 6 = k_demux_default on dictionary-coded genotypes when the table allows (see popscle_b200.h)."""
         self._chk(self.lib.pscl_demux_select_kernel(self.h, int(which)))
+
+    def demux_last_kernel(self) -> int:
+        """which accumulation kernel the last demux_score launched (demux_select_kernel's numbering)"""
+        return int(self.lib.pscl_demux_last_kernel(self.h))
 
     def demux_score(self, dplp: "DevicePileup", alphas, doublet_prior: float = 0.5, cell_begin: int = 0,
                     cell_end: int | None = None):

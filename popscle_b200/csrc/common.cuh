@@ -85,7 +85,16 @@ struct pscl_ctx {
   uint8_t* has_gp = nullptr;  // [V] or null (= all)
   double* gpM = nullptr;      // [V][(3nv+1)&~1] 16-B padded genotype rows (k_demux_cls, built lazily)
   double* gpS = nullptr;      // [V][nv][2] (S_j, M_j) moments of the rows
-  int demux_kernel = 0;       // 0 auto, 1 k_demux_default, 2 k_demux_general, 3 k_demux_cls, 4 k_demux_poly
+  // dictionary-coded genotypes (demux.inl, built by pscl_demux_set_geno when nv <= 8): usable when *h_dict_over == 0
+  unsigned long long* gp_code = nullptr;   // [V] 8-bit code per sample
+  double* gp_dict = nullptr;               // [256][3] the distinct triples
+  unsigned long long* gp_dict_key = nullptr;  // [256] hash keys claiming the slots
+  int* gp_dict_over = nullptr;             // device flag: more than 256 distinct triples (or a hash clash)
+  int* h_dict_over = nullptr;              // pinned host copy of the flag
+  cudaEvent_t ev_dict = nullptr;           // the host copy is valid once this has completed
+  bool dict_built = false;
+  int dm_last_kernel = 0;                  // what the last pscl_demux_score launched (pscl_demux_select_kernel's numbering)
+  int demux_kernel = 0;       // 0 auto, 1 k_demux_default (rows), 2 k_demux_general, 3 k_demux_cls, 4 k_demux_poly, 5 ab, 6 default (dictionary)
   bool keep_grid = false, force_general = false, dm_single_batch = true;
   int32_t dm_cell_begin = 0, dm_cell_end = 0, dm_nalpha = 0;
   void* dm_cells = nullptr;   // pscl_demux_cell[cells]

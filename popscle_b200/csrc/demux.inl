@@ -36,6 +36,7 @@
 // the fold is branch-free.  Filled on the host in the reference's own expression order.
 #define PSCL_FOLD_ROW 6  /* 5 factors padded to 48 B */
 #define PSCL_FOLD_ONES (2 * 64)
+#define PSCL_DICT_N 256 /* entries of the genotype dictionary (8-bit codes) */
 
 // max of positive, non-NaN doubles: DSETP + 2 SEL instead of fmax()'s NaN-aware sequence
 __device__ __forceinline__ double dmx_pmax(double x, double y) { return x > y ? x : y; }
@@ -84,9 +85,14 @@ struct DemuxArgs {
   int* bad = nullptr;                  // 2: SNP id out of range, 4: a slice never arrived
   int32_t n_snps = 0, n_stages = 0;
   int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};
+  // dictionary-coded genotypes (k_demux_default<NV, *, true>): when every (SNP, sample) triple of the table is one of
+  // <= 256 distinct triples (hard calls: 3 per combination of genotype counts), a pair needs 8 bytes of codes instead of
+  // a 24*nv-byte row, and the triples themselves sit in shared memory
+  const unsigned long long* gp_code = nullptr;  // [V] 8-bit dictionary index per sample
+  const double* gp_dict = nullptr;              // [256][3]
 };
 
-template <int NV, bool DELTA>
+template <int NV, bool DELTA, bool DICT>
 __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
   constexpr int NE = Cfg::NE, ND = Cfg::ND, SD = Cfg::STRIDE_D;
@@ -97,6 +103,8 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
   int* s_exp = reinterpret_cast<int*>(s_g + 2 * 256 * SD);    // [NE][256]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < 3 * 64 * PSCL_FOLD_ROW; i += 256) s_tab[i] = a.fold_tab[i];
+  double* const s_dict = reinterpret_cast<double*>(s_exp + NE * 256);  // [256][3], DICT only
+  if constexpr (DICT) { for (int i = tid; i < PSCL_DICT_N * 3; i += 256) s_dict[i] = a.gp_dict[i]; }
   __syncthreads();
   double* const g_row0 = s_g + (size_t)tid * SD;              // buffer 1 is 256*SD doubles further
 
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     //                      before use), has_gp, genotype row via cp.async into this lane's smem row
     int32_t snpA = 0; uint32_t r0A = 0, r1A = 0; bool okA = false;
     uint32_t r0B = 0, r1B = 0, b0B = 0, b1B = 0, b2B = 0, hasB = 0;
+    unsigned long long codeB = 0;
     auto loadA = [&](int it) {
       int64_t p = pb + ((int64_t)it << 5) + lane;
       okA = (it < niter) && (p < pe);
@@ -177,7 +186,9 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
         if (n > 0) b0B = a.rd_aq[r0B];
         if (n > 1) b1B = a.rd_aq[r0B + 1];
         if (n > 2) b2B = a.rd_aq[r0B + 2];
+        if constexpr (DICT) codeB = a.gp_code[snpA];
       }
+      if constexpr (DICT) return;  // no genotype rows to fetch
       // Cooperative row gather: the warp's 32 genotype rows are fetched LPR lanes per row, so one
       // LDGSTS instruction touches 32/LPR whole rows (a few 128-B lines) instead of 32 scattered
       // 16-B pieces of 32 different rows (one L1 tag lookup each).  A denser mapping (piece
@@ -204,12 +215,15 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     for (int it = 0; it < niter; ++it) {
       const int buf = it & 1;
       const uint32_t r0 = r0B, r1 = r1B, b0 = b0B, b1 = b1B, b2 = b2B;
+      const unsigned long long code = codeB;
       const bool has = hasB != 0;
-      __syncwarp();  // every lane is done reading buffer buf^1 (iteration it-1) before it is refilled
+      if constexpr (!DICT) __syncwarp();  // every lane is done reading buffer buf^1 (iteration it-1) before it is refilled
       issueB(buf ^ 1);
       loadA(it + 2);
-      __pipeline_wait_prior(1);  // this lane's pieces of iteration `it` have landed ...
-      __syncwarp();              // ... and so have the other lanes' pieces of this lane's row
+      if constexpr (!DICT) {
+        __pipeline_wait_prior(1);  // this lane's pieces of iteration `it` have landed ...
+        __syncwarp();              // ... and so have the other lanes' pieces of this lane's row
+      }
 
       if (has) {
         ++n_has;
@@ -239,7 +253,13 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
 
         // ---- D3: genotype row from this lane's shared-memory row ------------------------------
         double G[NV][3];
-        {
+        if constexpr (DICT) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const double* d = s_dict + (uint32_t)((code >> (8 * j)) & 255ull) * 3;
+            G[j][0] = d[0]; G[j][1] = d[1]; G[j][2] = d[2];
+          }
+        } else {
           const double* row = g_row0 + (size_t)buf * 256 * SD;
           if constexpr (Cfg::V16) {
             const double2* r2 = reinterpret_cast<const double2*>(row);
@@ -274,7 +294,7 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
         for (int e = 0; e < NE; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * 256 + tid] += ex; }
       }
     }
-    __pipeline_wait_prior(0);
+    if constexpr (!DICT) __pipeline_wait_prior(0);
 
     // ---- item epilogue ---------------------------------------------------------------------------
     // Lane products are multiplied across the warp first (mantissas in [1,2) after renorm, so 32 of
@@ -731,6 +751,58 @@ __global__ void __launch_bounds__(256) k_demux_epilogue_w(EpiArgs a, int n_cells
 // ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
+// ---- genotype dictionary ----------------------------------------------------------------------------------------
+// Hard-call genotypes (--field GT: gps = (1-err)*onehot + err*avg with avg from the SNP's genotype counts,
+// sc_drop_seq.cpp:285-315) put few distinct triples into the table: 3 per combination of counts, 135 for 8 samples.
+// Pass 1 lets every triple claim a slot of a 256-entry open-addressing table by a 64-bit hash of its bits; pass 2 writes
+// the slot numbers as 8-bit codes and checks each triple bit for bit against its slot, so a hash clash or a 257th triple
+// only raises the overflow flag and the row-gather kernel is used instead.
+__device__ __forceinline__ unsigned long long dmx_triple_key(const double* t) {
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    h ^= (unsigned long long)__double_as_longlong(t[i]);
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 29;
+  }
+  return h | 1ull;  // 0 means "free slot"
+}
+__global__ void k_geno_dict_claim(const double* __restrict__ gp, int64_t n, unsigned long long* keys, double* dict, int* over) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t[3] = {gp[3 * i], gp[3 * i + 1], gp[3 * i + 2]};
+  const unsigned long long key = dmx_triple_key(t);
+  int s = (int)((key >> 32) & (PSCL_DICT_N - 1));
+  for (int probe = 0; probe < PSCL_DICT_N; ++probe, s = (s + 1) & (PSCL_DICT_N - 1)) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(keys + s);
+    if (k == 0ull) {
+      k = atomicCAS(keys + s, 0ull, key);
+      if (k == 0ull) { dict[3 * s] = t[0]; dict[3 * s + 1] = t[1]; dict[3 * s + 2] = t[2]; return; }
+    }
+    if (k == key) return;
+  }
+  atomicExch(over, 1);
+}
+__global__ void k_geno_dict_codes(const double* __restrict__ gp, int32_t V, int32_t nv, const unsigned long long* __restrict__ keys,
+                                  const double* __restrict__ dict, unsigned long long* __restrict__ code, int* over) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  unsigned long long c = 0;
+  bool bad = false;
+  for (int j = 0; j < nv; ++j) {
+    const double* t = gp + ((size_t)v * nv + j) * 3;
+    const unsigned long long key = dmx_triple_key(t);
+    int s = (int)((key >> 32) & (PSCL_DICT_N - 1)), probe = 0;
+    while (probe < PSCL_DICT_N && keys[s] != key) { s = (s + 1) & (PSCL_DICT_N - 1); ++probe; }
+    if (probe == PSCL_DICT_N) { bad = true; break; }
+    bad |= __double_as_longlong(dict[3 * s]) != __double_as_longlong(t[0]) || __double_as_longlong(dict[3 * s + 1]) != __double_as_longlong(t[1]) ||
+           __double_as_longlong(dict[3 * s + 2]) != __double_as_longlong(t[2]);
+    c |= (unsigned long long)s << (8 * j);
+  }
+  code[v] = c;
+  if (bad) atomicExch(over, 1);
+}
+
 extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t n_snps) {
   if (!ctx) return PSCL_EINVAL;
   PsclScope scope__(ctx);
@@ -752,6 +824,30 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
   }
   ctx->nv = geno->n_samples;
   ctx->geno_V = n_snps;
+  // dictionary form of the table for k_demux_default (2 <= nv <= 8): two small kernels behind the copy, flag to a pinned word
+  cudaFree(ctx->gp_code); ctx->gp_code = nullptr;
+  ctx->dict_built = false;
+  if (geno->n_samples <= 8 && n_snps > 0 && ctx->h_dict_over) {
+    if (!ctx->gp_dict) {
+      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict, sizeof(double) * 3 * PSCL_DICT_N));
+      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_key, sizeof(unsigned long long) * PSCL_DICT_N));
+      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_over, sizeof(int)));
+    }
+    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_code, sizeof(unsigned long long) * (size_t)n_snps));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict, 0, sizeof(double) * 3 * PSCL_DICT_N, ctx->stream));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_key, 0, sizeof(unsigned long long) * PSCL_DICT_N, ctx->stream));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_over, 0, sizeof(int), ctx->stream));
+    const int64_t n = (int64_t)n_snps * geno->n_samples;
+    k_geno_dict_claim<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n, ctx->gp_dict_key, ctx->gp_dict, ctx->gp_dict_over);
+    k_geno_dict_codes<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, geno->n_samples, ctx->gp_dict_key, ctx->gp_dict,
+                                                                                 ctx->gp_code, ctx->gp_dict_over);
+    ctx->launches += 2;
+    PSCL_CUDA(ctx, cudaGetLastError());
+    *ctx->h_dict_over = 1;
+    PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->h_dict_over, ctx->gp_dict_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PSCL_CUDA(ctx, cudaEventRecord(ctx->ev_dict, ctx->stream));
+    ctx->dict_built = true;
+  }
   return PSCL_OK;
 }
 
@@ -767,8 +863,9 @@ extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
   ctx->force_general = enable != 0;
   return PSCL_OK;
 }
+extern "C" int pscl_demux_last_kernel(const pscl_ctx* ctx) { return ctx ? ctx->dm_last_kernel : 0; }
 extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 5) return PSCL_EINVAL;
+  if (!ctx || which < 0 || which > 6) return PSCL_EINVAL;
   ctx->demux_kernel = which;
   return PSCL_OK;
 }
@@ -778,16 +875,25 @@ static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
   using Cfg = DefaultCfg<NV>;
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    const int sm = (int)Cfg::SMEM + PSCL_DICT_N * 24;  // + the genotype dictionary of the DICT variants
+    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
   int grid = ctx->sm_count;
   if (grid * 8 > a.n_work) grid = (a.n_work + 7) / 8;
   if (grid < 1) grid = 1;
-  if (a.delta) k_demux_default<NV, true><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
-  else k_demux_default<NV, false><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
+  const size_t sm = Cfg::SMEM + PSCL_DICT_N * 24;
+  if (a.gp_code) {
+    if (a.delta) k_demux_default<NV, true, true><<<grid, 256, sm, ctx->stream>>>(a);
+    else k_demux_default<NV, false, true><<<grid, 256, sm, ctx->stream>>>(a);
+  } else {
+    if (a.delta) k_demux_default<NV, true, false><<<grid, 256, sm, ctx->stream>>>(a);
+    else k_demux_default<NV, false, false><<<grid, 256, sm, ctx->stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -819,6 +925,11 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
 
   const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && ctx->demux_kernel != 4 && na == 2 && h_alpha[0] == 0.0 &&
                            h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
+  bool use_dict = false;  // dictionary-coded genotypes: auto (0) and 6 take them when the table allows, 1 keeps the row gather
+  if (use_default && ctx->dict_built && (ctx->demux_kernel == 0 || ctx->demux_kernel == 6)) {
+    PSCL_CUDA(ctx, cudaEventSynchronize(ctx->ev_dict));
+    use_dict = *ctx->h_dict_over == 0;
+  }
   // every other shape: the polynomial kernel unless k_demux_general was asked for
   const bool use_poly = !use_default && !ctx->force_general && ctx->demux_kernel != 2;
   if (use_poly) {
@@ -833,6 +944,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     if ((rc = dmx_build_classes(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
     if ((rc = dmx_build_geno_tables(ctx)) != PSCL_OK) return rc;
   }
+  ctx->dm_last_kernel = use_ab ? 5 : use_ws ? 3 : use_default ? (use_dict ? 6 : 1) : use_poly ? 4 : 2;
   const std::vector<int32_t>& cip = plp->h_cell_item_ptr;
   size_t max_items = ctx->partial_budget_bytes / (G * sizeof(double));
   if (max_items < 1) max_items = 1;
@@ -856,6 +968,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
       a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend;
       a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
       a.item_base = ib; a.n_work = nwork; a.nv = nv; a.nalpha = na;
+      if (use_dict) { a.gp_code = ctx->gp_code; a.gp_dict = ctx->gp_dict; }
       if (plp->n_stages > 1) {  // staged pscl_demux_run: ids from the gaps, slice by slice as they land
         if (!use_default || use_ws || a.item_order == nullptr)
           return pscl_fail(ctx, PSCL_ESTATE, "a staged pileup image can only be scored whole by k_demux_default");
@@ -1002,7 +1115,7 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
   // independent (cmd_cram_demuxlet.cpp:636) and every cell is summed in the same order, so no record changes.
   // PSCL_STAGES=n overrides the slice count (1 = off).
   int stages = 1;
-  if (!llk_grid && !ctx->keep_grid && !ctx->force_general && ctx->demux_kernel <= 1 && opts->alphas && opts->n_alpha == 2 &&
+  if (!llk_grid && !ctx->keep_grid && !ctx->force_general && (ctx->demux_kernel <= 1 || ctx->demux_kernel == 6) && opts->alphas && opts->n_alpha == 2 &&
       opts->alphas[0] == 0.0 && opts->alphas[1] == 0.5 && geno->n_samples >= 2 && geno->n_samples <= 8 &&
       host->pair_snp_delta16 && host->cell_first_snp && host->n_pairs < ((int64_t)1 << 30)) {
     if (const char* sv = getenv("PSCL_STAGES")) stages = atoi(sv);

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEFAULT = [0.0, 0.5]
 
 
-KERNELS = {"auto": 0, "lane": 1, "general": 2, "cls": 3, "poly": 4, "ab": 5}
+KERNELS = {"auto": 0, "lane": 1, "general": 2, "cls": 3, "poly": 4, "ab": 5, "dict": 6}
 
 
 def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
@@ -29,7 +29,7 @@ def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
 
 
 @pytest.mark.parametrize("nv", [2, 3, 4, 5, 6, 7, 8])
-@pytest.mark.parametrize("general", ["cls", "ab", "lane", "general", "poly"])
+@pytest.mark.parametrize("general", ["cls", "ab", "lane", "dict", "general", "poly"])
 def test_default_grid_parity(ctx, nv, general):
     s = synth.make_pileup(C=300, nv=nv, V=2000, kbar=250, seed=100 + nv)
     gp = synth.gt_to_gp(s.geno)
@@ -100,7 +100,7 @@ def test_missing_genotypes_and_other_alleles(ctx):
     gp = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 5)).astype(np.float32).astype(np.float64)
     has = (rng.random(s.plp.n_snps) > 0.3).astype(np.uint8)
     s.plp.read_allele[rng.random(s.plp.n_reads) < 0.2] = 2
-    for general in ("cls", "ab", "lane", "general", "poly"):
+    for general in ("cls", "ab", "lane", "dict", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, has, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT)
 
@@ -125,12 +125,12 @@ def test_deep_pairs_and_empty_cells(ctx):
     geno = rng.integers(0, 3, (nv, V)).astype(np.int8)
     gp = synth.gt_to_gp(geno)
     s = synth.Synth(plp, geno, plp.snp_af, None, None, 9)
-    for general in ("cls", "ab", "lane", "general", "poly"):
+    for general in ("cls", "ab", "lane", "dict", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.3)
 
 
-@pytest.mark.parametrize("kernel", ["cls", "ab", "lane"])
+@pytest.mark.parametrize("kernel", ["cls", "ab", "lane", "dict"])
 def test_sharding_is_bit_identical(ctx, kernel):
     """barcode shards reproduce the unsharded records bit for bit; so do partial-grid batches."""
     s = synth.make_pileup(C=400, nv=8, V=3000, kbar=300, seed=77)
@@ -185,7 +185,7 @@ def test_errors(ctx):
         ctx.demux_run(bad, gp, None, DEFAULT)
 
 
-@pytest.mark.parametrize("kernel", ["cls", "ab", "lane"])
+@pytest.mark.parametrize("kernel", ["cls", "ab", "lane", "dict"])
 def test_cells_larger_than_one_work_item(ctx, kernel):
     """cells with > 2048 pairs are cut into several work items whose partial grids are summed in item order."""
     s = synth.make_pileup(C=24, nv=8, V=30000, kbar=5000, seed=88)
@@ -193,6 +193,45 @@ def test_cells_larger_than_one_work_item(ctx, kernel):
     gp = synth.gt_to_gp(s.geno)
     out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, kernel)
     check_demux_parity(out, grid, ref, rgrid, DEFAULT)
+
+
+def test_genotype_dictionary_is_bit_identical_and_falls_back(ctx):
+    """k_demux_default reads 8-bit dictionary codes instead of genotype rows when the table holds <= 256 distinct triples
+    (hard calls: 3 per combination of genotype counts); the records are bit-identical to the row-gather kernel's, SNPs
+    without GP included.  A table with more triples (soft GP, several error rates) silently takes the rows."""
+    s = synth.make_pileup(C=200, nv=7, V=2500, kbar=300, seed=606)
+    rng = np.random.default_rng(6)
+    has = (rng.random(s.plp.n_snps) > 0.2).astype(np.uint8)
+
+    def run(gp, which, has_gp=None):
+        ctx.demux_select_kernel(which)
+        try:
+            return ctx.demux_run(s.plp, gp, has_gp, DEFAULT, want_grid=True)
+        finally:
+            ctx.demux_select_kernel(0)
+
+    gp = synth.gt_to_gp(s.geno)
+    assert 3 < len(np.unique(gp.reshape(-1, 3), axis=0)) <= 256
+    for h in (None, has):
+        lane, lgrid = run(gp, 1, h)
+        for which in (0, 6):
+            rec, grid = run(gp, which, h)
+            assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
+    # exactly 256 distinct triples still fit, 257 do not; either way nothing changes in the output
+    for n_trip in (256, 257):
+        gpe = gp.copy()
+        flat = gpe.reshape(-1, 3)
+        flat[:] = flat[0]
+        extra = rng.dirichlet([1.0, 1.0, 1.0], size=n_trip - 1)
+        flat[rng.permutation(len(flat))[: 40 * (n_trip - 1)].reshape(40, -1)] = extra[None, :, :]
+        assert len(np.unique(flat, axis=0)) == n_trip
+        lane, lgrid = run(gpe, 1)
+        rec, grid = run(gpe, 0)
+        assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
+    soft = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 7))
+    lane, lgrid = run(soft, 1)
+    rec, grid = run(soft, 6)
+    assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
 
 
 def test_compact_pileup_inputs_are_equivalent(ctx):

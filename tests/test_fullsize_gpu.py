@@ -27,7 +27,7 @@ def test_config2_kernels_agree_and_match_the_oracle_sample(ctx, cfg2):
     ctx.demux_set_geno(gp, None, plp.n_snps)
     ctx.demux_keep_grid(True)
     try:
-        for name, k in (("lane", 1), ("cls", 3), ("poly", 4)):
+        for name, k in (("lane", 1), ("dict", 6), ("cls", 3), ("poly", 4)):
             ctx.demux_select_kernel(k)
             ctx.demux_score(d, DEFAULT, 0.5)
             outs[name] = ctx.demux_fetch(want_grid=True)
@@ -36,6 +36,7 @@ def test_config2_kernels_agree_and_match_the_oracle_sample(ctx, cfg2):
         ctx.demux_keep_grid(False)
         d.free()
     rec, grid = outs["lane"]
+    assert outs["dict"][0].tobytes() == rec.tobytes() and np.array_equal(outs["dict"][1], grid, equal_nan=True)  # same sums, coded genotypes
     live = ~np.isnan(grid)
     for name in ("cls", "poly"):  # three independent formulations of the same sums: ~1e-13 apart
         r2, g2 = outs[name]
