@@ -767,21 +767,28 @@ __device__ __forceinline__ unsigned long long dmx_triple_key(const double* t) {
   }
   return h | 1ull;  // 0 means "free slot"
 }
-__global__ void k_geno_dict_claim(const double* __restrict__ gp, int64_t n, unsigned long long* keys, double* dict, int* over) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double t[3] = {gp[3 * i], gp[3 * i + 1], gp[3 * i + 2]};
-  const unsigned long long key = dmx_triple_key(t);
-  int s = (int)((key >> 32) & (PSCL_DICT_N - 1));
-  for (int probe = 0; probe < PSCL_DICT_N; ++probe, s = (s + 1) & (PSCL_DICT_N - 1)) {
-    unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(keys + s);
-    if (k == 0ull) {
-      k = atomicCAS(keys + s, 0ull, key);
-      if (k == 0ull) { dict[3 * s] = t[0]; dict[3 * s + 1] = t[1]; dict[3 * s + 2] = t[2]; return; }
+__global__ void k_geno_dict_claim(const double* __restrict__ gp, int32_t V, int32_t nv, unsigned long long* keys, double* dict, int* over) {
+  // one thread per SNP: its samples share a few triples, so keys this thread has already placed are skipped
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  unsigned long long seen0 = 0ull, seen1 = 0ull, seen2 = 0ull, seen3 = 0ull;
+  for (int j = 0; j < nv; ++j) {
+    const double* tp = gp + ((size_t)v * nv + j) * 3;
+    const double t[3] = {tp[0], tp[1], tp[2]};
+    const unsigned long long key = dmx_triple_key(t);
+    if (key == seen0 || key == seen1 || key == seen2 || key == seen3) continue;
+    seen3 = seen2; seen2 = seen1; seen1 = seen0; seen0 = key;
+    int s = (int)((key >> 32) & (PSCL_DICT_N - 1)), probe = 0;
+    for (; probe < PSCL_DICT_N; ++probe, s = (s + 1) & (PSCL_DICT_N - 1)) {
+      unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(keys + s);
+      if (k == 0ull) {
+        k = atomicCAS(keys + s, 0ull, key);
+        if (k == 0ull) { dict[3 * s] = t[0]; dict[3 * s + 1] = t[1]; dict[3 * s + 2] = t[2]; break; }
+      }
+      if (k == key) break;
     }
-    if (k == key) return;
+    if (probe == PSCL_DICT_N) { atomicExch(over, 1); return; }
   }
-  atomicExch(over, 1);
 }
 __global__ void k_geno_dict_codes(const double* __restrict__ gp, int32_t V, int32_t nv, const unsigned long long* __restrict__ keys,
                                   const double* __restrict__ dict, unsigned long long* __restrict__ code, int* over) {
@@ -837,8 +844,8 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict, 0, sizeof(double) * 3 * PSCL_DICT_N, ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_key, 0, sizeof(unsigned long long) * PSCL_DICT_N, ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_over, 0, sizeof(int), ctx->stream));
-    const int64_t n = (int64_t)n_snps * geno->n_samples;
-    k_geno_dict_claim<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n, ctx->gp_dict_key, ctx->gp_dict, ctx->gp_dict_over);
+    k_geno_dict_claim<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, geno->n_samples, ctx->gp_dict_key, ctx->gp_dict,
+                                                                                 ctx->gp_dict_over);
     k_geno_dict_codes<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, geno->n_samples, ctx->gp_dict_key, ctx->gp_dict,
                                                                                  ctx->gp_code, ctx->gp_dict_over);
     ctx->launches += 2;

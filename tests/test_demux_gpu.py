@@ -203,10 +203,14 @@ def test_genotype_dictionary_is_bit_identical_and_falls_back(ctx):
     rng = np.random.default_rng(6)
     has = (rng.random(s.plp.n_snps) > 0.2).astype(np.uint8)
 
+    ran = []
+
     def run(gp, which, has_gp=None):
         ctx.demux_select_kernel(which)
         try:
-            return ctx.demux_run(s.plp, gp, has_gp, DEFAULT, want_grid=True)
+            out = ctx.demux_run(s.plp, gp, has_gp, DEFAULT, want_grid=True)
+            ran.append(ctx.demux_last_kernel())
+            return out
         finally:
             ctx.demux_select_kernel(0)
 
@@ -216,7 +220,15 @@ def test_genotype_dictionary_is_bit_identical_and_falls_back(ctx):
         lane, lgrid = run(gp, 1, h)
         for which in (0, 6):
             rec, grid = run(gp, which, h)
+            assert ran[-1] == 6 and ran[-2 if which == 6 else -1] == 6
             assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
+    # a missing call replaced by a flat prior adds one triple: still coded
+    gp4 = gp.copy()
+    gp4[rng.random(gp4.shape[:2]) < 0.1] = [0.3, 0.3, 0.4]
+    lane, lgrid = run(gp4, 1)
+    rec, grid = run(gp4, 0)
+    assert ran[-2:] == [1, 6]
+    assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
     # exactly 256 distinct triples still fit, 257 do not; either way nothing changes in the output
     for n_trip in (256, 257):
         gpe = gp.copy()
@@ -227,10 +239,12 @@ def test_genotype_dictionary_is_bit_identical_and_falls_back(ctx):
         assert len(np.unique(flat, axis=0)) == n_trip
         lane, lgrid = run(gpe, 1)
         rec, grid = run(gpe, 0)
+        assert ran[-1] == (6 if n_trip == 256 else 1)
         assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
     soft = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 7))
     lane, lgrid = run(soft, 1)
     rec, grid = run(soft, 6)
+    assert ran[-1] == 1
     assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
 
 
