@@ -37,6 +37,9 @@
 #define PSCL_FOLD_ROW 6  /* 5 factors padded to 48 B */
 #define PSCL_FOLD_ONES (2 * 64)
 #define PSCL_DICT_N 256 /* entries of the genotype dictionary (8-bit codes) */
+#ifndef PSCL_DICT_THREADS
+#define PSCL_DICT_THREADS 256 /* threads per CTA of the dictionary variants of k_demux_default (384 measured: +2%) */
+#endif
 
 // max of positive, non-NaN doubles: DSETP + 2 SEL instead of fmax()'s NaN-aware sequence
 __device__ __forceinline__ double dmx_pmax(double x, double y) { return x > y ? x : y; }
@@ -58,6 +61,9 @@ struct DefaultCfg {
   static constexpr int THREADS = 256;
   static constexpr size_t SMEM = sizeof(double) * 3 * 64 * PSCL_FOLD_ROW +
                                  (size_t)2 * THREADS * STRIDE_D * sizeof(double) + (size_t)NE * THREADS * sizeof(int);
+  // dictionary variants: fold table, [NE][threads] epilogue stash, [NE][threads] exponents, 256 triples x 16 copies
+  static constexpr size_t SMEM_DICT = sizeof(double) * 3 * 64 * PSCL_FOLD_ROW + (size_t)NE * PSCL_DICT_THREADS * (sizeof(double) + sizeof(int)) +
+                                      (size_t)PSCL_DICT_N * 3 * sizeof(double) * 16;
 };
 
 struct DemuxArgs {
@@ -92,19 +98,26 @@ struct DemuxArgs {
   const double* gp_dict = nullptr;              // [256][3]
 };
 
+// threads per CTA: 256 for both kinds of variant (the dictionary variants were also measured with 384 threads at 168
+// registers: 0.650 vs 0.662 ms, not worth the spills; what bounds them is shared-memory bandwidth)
 template <int NV, bool DELTA, bool DICT>
-__global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
+__global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
+  constexpr int NT = DICT ? PSCL_DICT_THREADS : 256;
   constexpr int NE = Cfg::NE, ND = Cfg::ND, SD = Cfg::STRIDE_D;
   constexpr int E_SG0 = NV + ND, E_MX = NV + ND + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_tab = reinterpret_cast<double*>(smem_raw);        // [3*64][PSCL_FOLD_ROW]
-  double* s_g = s_tab + 3 * 64 * PSCL_FOLD_ROW;               // [2][256][SD]
-  int* s_exp = reinterpret_cast<int*>(s_g + 2 * 256 * SD);    // [NE][256]
+  double* s_g = s_tab + 3 * 64 * PSCL_FOLD_ROW;               // [2][256][SD] genotype rows; DICT: [NE][NT] epilogue stash
+  int* s_exp = reinterpret_cast<int*>(s_g + (DICT ? NE * NT : 2 * 256 * SD));  // [NE][NT]
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < 3 * 64 * PSCL_FOLD_ROW; i += 256) s_tab[i] = a.fold_tab[i];
-  double* const s_dict = reinterpret_cast<double*>(s_exp + NE * 256);  // [256][3], DICT only
-  if constexpr (DICT) { for (int i = tid; i < PSCL_DICT_N * 3; i += 256) s_dict[i] = a.gp_dict[i]; }
+  for (int i = tid; i < 3 * 64 * PSCL_FOLD_ROW; i += NT) s_tab[i] = a.fold_tab[i];
+  // DICT: the dictionary, 16 copies interleaved ([256*3][16] doubles): lane l reads copy l%16, which lives in its own
+  // pair of banks, so the 32 lanes' lookups of 32 different triples never collide (a single copy cost ~3x the wavefronts)
+  double* const s_dict = reinterpret_cast<double*>(s_exp + NE * NT);
+  if constexpr (DICT) {
+    for (int i = tid; i < PSCL_DICT_N * 3 * 16; i += NT) s_dict[i] = a.gp_dict[i >> 4];
+  }
   __syncthreads();
   double* const g_row0 = s_g + (size_t)tid * SD;              // buffer 1 is 256*SD doubles further
 
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
 
     double acc[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) { acc[e] = 1.0; s_exp[e * 256 + tid] = 0; }
+    for (int e = 0; e < NE; ++e) { acc[e] = 1.0; s_exp[e * NT + tid] = 0; }
     int n_has = 0;
 
     // ---- software pipeline --------------------------------------------------------------------
@@ -256,8 +269,8 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
         if constexpr (DICT) {
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
-            const double* d = s_dict + (uint32_t)((code >> (8 * j)) & 255ull) * 3;
-            G[j][0] = d[0]; G[j][1] = d[1]; G[j][2] = d[2];
+            const double* d = s_dict + (uint32_t)((code >> (8 * j)) & 255ull) * 48 + (lane & 15);
+            G[j][0] = d[0]; G[j][1] = d[16]; G[j][2] = d[32];
           }
         } else {
           const double* row = g_row0 + (size_t)buf * 256 * SD;
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
       }
       if ((it & 7) == 7) {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * 256 + tid] += ex; }
+        for (int e = 0; e < NE; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * NT + tid] += ex; }
       }
     }
     if constexpr (!DICT) __pipeline_wait_prior(0);
@@ -300,7 +313,10 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     // Lane products are multiplied across the warp first (mantissas in [1,2) after renorm, so 32 of
     // them cannot overflow), then ONE log per accumulator per item, taken by lane e%32.  Rolled
     // through this lane's (now free) genotype rows so it does not bloat the hot loop's I-footprint.
-    {
+    if constexpr (DICT) {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) s_g[e * NT + tid] = acc[e];
+    } else {
       double* st0 = g_row0;
       double* st1 = g_row0 + (size_t)256 * SD;
 #pragma unroll
@@ -310,8 +326,8 @@ __global__ void __launch_bounds__(256, 1) k_demux_default(DemuxArgs a) {
     int keep_e0 = 0, keep_e1 = 0;
 #pragma unroll 1
     for (int e = 0; e < NE; ++e) {
-      double m = (e < SD) ? g_row0[e] : g_row0[(size_t)256 * SD + (e - SD)];
-      int ex = s_exp[e * 256 + tid];
+      double m = DICT ? s_g[e * NT + tid] : (e < SD) ? g_row0[e] : g_row0[(size_t)256 * SD + (e - SD)];
+      int ex = s_exp[e * NT + tid];
       pscl_renorm(m, ex);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -882,24 +898,23 @@ static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
   using Cfg = DefaultCfg<NV>;
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    const int sm = (int)Cfg::SMEM + PSCL_DICT_N * 24;  // + the genotype dictionary of the DICT variants
-    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_DICT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_DICT);
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
+  const int wpc = (a.gp_code ? PSCL_DICT_THREADS : 256) / 32;  // warps (= work items in flight) per CTA
   int grid = ctx->sm_count;
-  if (grid * 8 > a.n_work) grid = (a.n_work + 7) / 8;
+  if (grid * wpc > a.n_work) grid = (a.n_work + wpc - 1) / wpc;
   if (grid < 1) grid = 1;
-  const size_t sm = Cfg::SMEM + PSCL_DICT_N * 24;
   if (a.gp_code) {
-    if (a.delta) k_demux_default<NV, true, true><<<grid, 256, sm, ctx->stream>>>(a);
-    else k_demux_default<NV, false, true><<<grid, 256, sm, ctx->stream>>>(a);
+    if (a.delta) k_demux_default<NV, true, true><<<grid, PSCL_DICT_THREADS, Cfg::SMEM_DICT, ctx->stream>>>(a);
+    else k_demux_default<NV, false, true><<<grid, PSCL_DICT_THREADS, Cfg::SMEM_DICT, ctx->stream>>>(a);
   } else {
-    if (a.delta) k_demux_default<NV, true, false><<<grid, 256, sm, ctx->stream>>>(a);
-    else k_demux_default<NV, false, false><<<grid, 256, sm, ctx->stream>>>(a);
+    if (a.delta) k_demux_default<NV, true, false><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
+    else k_demux_default<NV, false, false><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
   }
   return cudaGetLastError();
 }
