@@ -461,11 +461,15 @@ def main():
     first, d16, n8 = plp.compact3()
     for name, src in (("cell_ptr", plp.cell_ptr), ("cell_first_snp", first), ("pair_snp_delta16", d16), ("pair_nreads8", n8), ("read_aq", aq)):
         t_, v_ = pin(src); keep.append(t_); arrs[name] = v_
-    gp_t, gp_pin = pin(gp); keep.append(gp_t)
+    # genotypes the way the CLI host hands them over for --field GT (ABI 4): one byte per (SNP, sample) hard call and the
+    # genotype error rate; the library builds the mixed table (sc_drop_seq.cpp:287-315) on the device
+    from popscle_b200 import RawGeno
+    gt_t, gt_pin = pin(np.ascontiguousarray(s.geno.T.astype(np.uint8))); keep.append(gt_t)
+    gp_pin = RawGeno(gt8=gt_pin, err=0.1)
     hplp = Pileup(plp.n_cells, plp.n_snps, arrs["cell_ptr"], plp.pair_snp, plp.pair_read_ptr, plp.read_allele, plp.read_qual, None)
     hplp._compact = (p32, arrs["read_aq"])  # pinned copies are what crosses the ABI
     hplp._compact3 = (arrs["cell_first_snp"], arrs["pair_snp_delta16"], arrs["pair_nreads8"])
-    h2d = sum(v.nbytes for v in arrs.values()) + gp_pin.nbytes
+    h2d = sum(v.nbytes for v in arrs.values()) + gt_pin.nbytes
     d2h = 160 * plp.n_cells
     for _ in range(2):
         out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
@@ -500,7 +504,7 @@ def main():
                            "l2": "flushed between timed steps (256 MiB memset, untimed)"},
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "ms_per_call": per_call, "api": "pscl_demux_run (pinned host buffers in ABI-3 compact form: 3 B per pair, 1 B per base-call; per-cell records out)"},
+                        "steps": e2e_steps, "ms_per_call": per_call, "api": "pscl_demux_run (pinned host buffers in compact form: 3 B per pair, 1 B per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_demux(s, gp, nv, args.cpu_seconds, os.cpu_count() or 1)

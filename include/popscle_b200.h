@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSCL_ABI_VERSION 3
+#define PSCL_ABI_VERSION 4
 
 typedef enum pscl_status {
   PSCL_OK = 0,
@@ -83,8 +83,19 @@ typedef struct pscl_pileup {
 typedef struct pscl_geno {
   int32_t n_samples;     /* nv = vr.get_nsamples()                                              */
   const double* gp;      /* [V * nv * 3] P(genotype = 0/1/2) per SNP, sample; rows of SNPs with
-                            has_gp == 0 are ignored                                             */
+                            has_gp == 0 are ignored.  NULL when one of the raw forms below is given */
   const uint8_t* has_gp; /* [V] 1 if snps[v].gps != NULL (cmd_cram_demuxlet.cpp:733); NULL = all 1 */
+  /* ABI 4, optional: the reader's posteriors BEFORE the geno-error mixing, which the library then
+   * does on the device exactly as sc_drop_seq.cpp:287-315 does (per-SNP average started at 1e-10 and
+   * accumulated in sample order, gps = (1-err)*gp + err*avg in double, err clamped to [0, 0.999]).
+   * gp_f32: [V * nv * 3] floats as vr.get_posterior_probability() returns them (any --field), half
+   * the bytes of `gp`.  gt8: [V * nv] hard calls 0/1/2 (--field GT without missing calls: the
+   * one-hot rows of bcf_filtered_reader.cpp:385-409), 1/24 of the bytes.  The error rate is
+   * `geno_err_snp[v]` when that is given (--geno-error-coeff with an R2 INFO field), else `geno_err`. */
+  const float* gp_f32;
+  const uint8_t* gt8;
+  const double* geno_err_snp;
+  double geno_err;
 } pscl_geno;
 
 /* ------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@ shared library is missing, or no sm_100 device is present, the calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 import os
 from dataclasses import dataclass
 
@@ -35,7 +36,19 @@ class CPileup(C.Structure):
 
 
 class CGeno(C.Structure):
-    _fields_ = [("n_samples", C.c_int32), ("gp", C.c_void_p), ("has_gp", C.c_void_p)]
+    _fields_ = [("n_samples", C.c_int32), ("gp", C.c_void_p), ("has_gp", C.c_void_p),
+                ("gp_f32", C.c_void_p), ("gt8", C.c_void_p), ("geno_err_snp", C.c_void_p), ("geno_err", C.c_double)]
+
+
+@dataclasses.dataclass
+class RawGeno:
+    """ABI 4 genotype input: the reader's posteriors before the geno-error mixing (sc_drop_seq.cpp:287-315), mixed on the
+    device.  Give `gt8` (uint8 [V][nv] hard calls 0/1/2) or `gp_f32` (float32 [V][nv][3]); `err` is the error rate
+    (--geno-error-offset), `err_snp` a per-SNP override (--geno-error-coeff with R2)."""
+    gt8: np.ndarray | None = None
+    gp_f32: np.ndarray | None = None
+    err: float = 0.1
+    err_snp: np.ndarray | None = None
 
 
 class CDemuxOpts(C.Structure):
@@ -302,19 +315,46 @@ class Context:
         return DevicePileup(self, out, plp.n_cells, plp.n_snps, plp.n_pairs, plp.n_reads)
 
     # ---- demuxlet ----
-    def demux_set_geno(self, gp: np.ndarray, has_gp: np.ndarray | None, n_snps: int):
-        gp = np.ascontiguousarray(gp, dtype=np.float64)
-        assert gp.ndim == 3 and gp.shape[0] == n_snps and gp.shape[2] == 3, gp.shape
+    @staticmethod
+    def _geno(gp, has_gp):
+        """CGeno + the arrays it points into.  `gp`: float64 [V][nv][3] (the mixed table), or a RawGeno (ABI 4: the
+        reader's float32 posteriors or uint8 hard calls plus the genotype error, mixed on the device)."""
         g = CGeno()
-        g.n_samples = gp.shape[1]
-        g.gp = gp.ctypes.data
-        hg = None
+        keep = []
+        if isinstance(gp, RawGeno):
+            if gp.gt8 is not None:
+                a = np.ascontiguousarray(gp.gt8, dtype=np.uint8)
+                assert a.ndim == 2
+                g.gt8 = a.ctypes.data
+            else:
+                a = np.ascontiguousarray(gp.gp_f32, dtype=np.float32)
+                assert a.ndim == 3 and a.shape[2] == 3, a.shape
+                g.gp_f32 = a.ctypes.data
+            keep.append(a)
+            if gp.err_snp is not None:
+                e = np.ascontiguousarray(gp.err_snp, dtype=np.float64)
+                assert e.shape == (a.shape[0],)
+                g.geno_err_snp = e.ctypes.data
+                keep.append(e)
+            g.geno_err = float(gp.err)
+        else:
+            a = np.ascontiguousarray(gp, dtype=np.float64)
+            assert a.ndim == 3 and a.shape[2] == 3, a.shape
+            g.gp = a.ctypes.data
+            keep.append(a)
+        g.n_samples = a.shape[1]
         if has_gp is not None:
             hg = np.ascontiguousarray(has_gp, dtype=np.uint8)
             g.has_gp = hg.ctypes.data
+            keep.append(hg)
+        return g, keep, a.shape[0], a.shape[1]
+
+    def demux_set_geno(self, gp, has_gp: np.ndarray | None, n_snps: int):
+        g, keep, V, nv = self._geno(gp, has_gp)
+        assert V == n_snps, (V, n_snps)
         self._chk(self.lib.pscl_demux_set_geno(self.h, C.byref(g), n_snps))
-        self.sync()  # gp / hg are pageable numpy buffers
-        self._nv = gp.shape[1]
+        self.sync()  # the sources are pageable numpy buffers
+        self._nv = nv
 
     def demux_keep_grid(self, enable: bool):
         self._chk(self.lib.pscl_demux_keep_grid(self.h, int(enable)))
@@ -355,19 +395,12 @@ class Context:
     def demux_run(self, plp: Pileup, gp: np.ndarray, has_gp, alphas, doublet_prior: float = 0.5,
                   want_grid: bool = False, compact: bool = False):
         """The one-call path of the CLI host: host buffers in, per-cell records out."""
-        gp = np.ascontiguousarray(gp, dtype=np.float64)
         al = np.ascontiguousarray(alphas, dtype=np.float64)
         cs = plp.c_struct(compact=compact)
-        g = CGeno()
-        g.n_samples = gp.shape[1]
-        g.gp = gp.ctypes.data
-        hg = None
-        if has_gp is not None:
-            hg = np.ascontiguousarray(has_gp, dtype=np.uint8)
-            g.has_gp = hg.ctypes.data
+        g, keep, _, nv = self._geno(gp, has_gp)
         o = CDemuxOpts(len(al), al.ctypes.data, doublet_prior)
         out = np.zeros(plp.n_cells, dtype=DEMUX_CELL_DTYPE)
-        grid = np.empty((plp.n_cells, gp.shape[1], gp.shape[1], len(al))) if want_grid else None
+        grid = np.empty((plp.n_cells, nv, nv, len(al))) if want_grid else None
         self._chk(self.lib.pscl_demux_run(self.h, C.byref(cs), C.byref(g), C.byref(o), out.ctypes.data,
                                           grid.ctypes.data if want_grid else None))
         return (out, grid) if want_grid else out

@@ -91,6 +91,7 @@ struct pscl_ctx {
   unsigned long long* gp_dict_key = nullptr;  // [256] hash keys claiming the slots
   int* gp_dict_over = nullptr;             // device flag: more than 256 distinct triples (or a hash clash)
   int* h_dict_over = nullptr;              // pinned host copy of the flag
+  int* h_geno_bad = nullptr;               // pinned: the raw genotype input (ABI 4) held an invalid hard-call code
   cudaEvent_t ev_dict = nullptr;           // the host copy is valid once this has completed
   bool dict_built = false;
   int dm_last_kernel = 0;                  // what the last pscl_demux_score launched (pscl_demux_select_kernel's numbering)

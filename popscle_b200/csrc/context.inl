@@ -37,6 +37,7 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
   cudaEventCreateWithFlags(&c->stage_go, cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&c->h_one, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_one = 1;
   if (cudaHostAlloc((void**)&c->h_dict_over, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_dict_over = 1;
+  if (cudaHostAlloc((void**)&c->h_geno_bad, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_geno_bad = 0;
   cudaEventCreateWithFlags(&c->ev_dict, cudaEventDisableTiming);
   {  // keep freed blocks mapped in the device's default pool (see common.cuh: device memory)
     cudaMemPool_t pool = nullptr;
@@ -99,6 +100,7 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   if (ctx->stage_go) cudaEventDestroy(ctx->stage_go);
   if (ctx->h_one) cudaFreeHost(ctx->h_one);
   if (ctx->h_dict_over) cudaFreeHost(ctx->h_dict_over);
+  if (ctx->h_geno_bad) cudaFreeHost(ctx->h_geno_bad);
   if (ctx->ev_dict) cudaEventDestroy(ctx->ev_dict);
   cudaFree(ctx->gp_code); cudaFree(ctx->gp_dict); cudaFree(ctx->gp_dict_key); cudaFree(ctx->gp_dict_over);
   cudaFree(ctx->stage_flags);

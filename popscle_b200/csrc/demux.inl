@@ -826,10 +826,48 @@ __global__ void k_geno_dict_codes(const double* __restrict__ gp, int32_t V, int3
   if (bad) atomicExch(over, 1);
 }
 
+// ABI 4: genotype table from the reader's raw posteriors, mixed with the genotype error on the device.  One thread per
+// SNP walks its samples in order, as sc_drop_seq.cpp:288-315 does; explicit _rn arithmetic keeps the compiler from
+// contracting (1-err)*gp + err*avg into an FMA, so the table is bit-identical to the host-mixed one.
+__global__ void k_geno_mix(const float* __restrict__ f32, const uint8_t* __restrict__ gt8, const double* __restrict__ err_snp, double err0,
+                           int32_t V, int32_t nv, const uint8_t* __restrict__ has_gp, double* __restrict__ gp, int* bad) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  if (has_gp && !has_gp[v]) return;
+  double avg0 = 1e-10, avg1 = 1e-10, avg2 = 1e-10;
+  double* out = gp + (size_t)v * nv * 3;
+  for (int j = 0; j < nv; ++j) {
+    double g0, g1, g2;
+    if (gt8) {
+      const uint8_t c = gt8[(size_t)v * nv + j];
+      if (c > 2) { atomicExch(bad, 1); return; }
+      g0 = c == 0 ? 1.0 : 0.0; g1 = c == 1 ? 1.0 : 0.0; g2 = c == 2 ? 1.0 : 0.0;
+    } else {
+      const float* f = f32 + ((size_t)v * nv + j) * 3;
+      g0 = (double)f[0]; g1 = (double)f[1]; g2 = (double)f[2];
+    }
+    out[3 * j] = g0; out[3 * j + 1] = g1; out[3 * j + 2] = g2;
+    avg0 = __dadd_rn(avg0, g0); avg1 = __dadd_rn(avg1, g1); avg2 = __dadd_rn(avg2, g2);
+  }
+  const double sum = __dadd_rn(__dadd_rn(avg0, avg1), avg2);
+  avg0 = __ddiv_rn(avg0, sum); avg1 = __ddiv_rn(avg1, sum); avg2 = __ddiv_rn(avg2, sum);
+  double err = err_snp ? err_snp[v] : err0;
+  if (err > 0.999) err = 0.999;
+  if (err < 0) err = 0;
+  if (err > 0) {
+    const double keep = __dsub_rn(1.0, err);
+    for (int j = 0; j < nv; ++j) {
+      out[3 * j] = __dadd_rn(__dmul_rn(keep, out[3 * j]), __dmul_rn(err, avg0));
+      out[3 * j + 1] = __dadd_rn(__dmul_rn(keep, out[3 * j + 1]), __dmul_rn(err, avg1));
+      out[3 * j + 2] = __dadd_rn(__dmul_rn(keep, out[3 * j + 2]), __dmul_rn(err, avg2));
+    }
+  }
+}
+
 extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t n_snps) {
   if (!ctx) return PSCL_EINVAL;
   PsclScope scope__(ctx);
-  if (!geno || !geno->gp || geno->n_samples < 2 || n_snps < 0)
+  if (!geno || (!geno->gp && !geno->gp_f32 && !geno->gt8) || geno->n_samples < 2 || n_snps < 0)
     return pscl_fail(ctx, PSCL_EINVAL,
                      "pscl_demux_set_geno: need gp and n_samples >= 2 (the reference divides by nv-1, "
                      "cmd_cram_demuxlet.cpp:794)");
@@ -840,11 +878,44 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
   cudaFree(ctx->gpS); ctx->gpS = nullptr;
   size_t bytes = sizeof(double) * (size_t)n_snps * geno->n_samples * 3;
   PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp, bytes ? bytes : 16));
-  PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->gp, geno->gp, bytes, cudaMemcpyHostToDevice, ctx->stream));
   if (geno->has_gp) {
     PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->has_gp, n_snps ? n_snps : 16));
     PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->has_gp, geno->has_gp, n_snps, cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (geno->gp) {
+    PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->gp, geno->gp, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  } else if (n_snps > 0) {  // ABI 4 raw posteriors: copy the small form, mix on the device
+    const size_t cells = (size_t)n_snps * geno->n_samples;
+    float* d_f32 = nullptr; uint8_t* d_gt8 = nullptr; double* d_err = nullptr; int* d_bad = nullptr;
+    PSCL_CUDA(ctx, cudaMalloc((void**)&d_bad, sizeof(int)));
+    PSCL_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp, 0, bytes, ctx->stream));  // rows of SNPs without GP stay zero
+    if (geno->gt8) {
+      PSCL_CUDA(ctx, cudaMalloc((void**)&d_gt8, cells));
+      PSCL_CUDA(ctx, cudaMemcpyAsync(d_gt8, geno->gt8, cells, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      PSCL_CUDA(ctx, cudaMalloc((void**)&d_f32, sizeof(float) * cells * 3));
+      PSCL_CUDA(ctx, cudaMemcpyAsync(d_f32, geno->gp_f32, sizeof(float) * cells * 3, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (geno->geno_err_snp) {
+      PSCL_CUDA(ctx, cudaMalloc((void**)&d_err, sizeof(double) * n_snps));
+      PSCL_CUDA(ctx, cudaMemcpyAsync(d_err, geno->geno_err_snp, sizeof(double) * n_snps, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_geno_mix<<<(unsigned)((n_snps + 127) / 128), 128, 0, ctx->stream>>>(d_f32, d_gt8, d_err, geno->geno_err, n_snps, geno->n_samples, ctx->has_gp,
+                                                                           ctx->gp, d_bad);
+    ctx->launches++;
+    PSCL_CUDA(ctx, cudaGetLastError());
+    cudaFree(d_f32); cudaFree(d_gt8); cudaFree(d_err);
+    // codes other than 0/1/2 are an input error; the flag travels to a pinned word and pscl_demux_score reads it
+    if (ctx->h_geno_bad) {
+      *ctx->h_geno_bad = 0;
+      PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->h_geno_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaFree(d_bad);
+  } else if (ctx->h_geno_bad) {
+    *ctx->h_geno_bad = 0;
+  }
+  if (!geno->gp && ctx->h_geno_bad == nullptr) return pscl_fail(ctx, PSCL_ENOMEM, "no pinned flag word for the raw genotype forms");
   ctx->nv = geno->n_samples;
   ctx->geno_V = n_snps;
   // dictionary form of the table for k_demux_default (2 <= nv <= 8): two small kernels behind the copy, flag to a pinned word
@@ -868,9 +939,9 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
     PSCL_CUDA(ctx, cudaGetLastError());
     *ctx->h_dict_over = 1;
     PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->h_dict_over, ctx->gp_dict_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PSCL_CUDA(ctx, cudaEventRecord(ctx->ev_dict, ctx->stream));
     ctx->dict_built = true;
   }
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev_dict, ctx->stream));  // both pinned flag words are valid once this completes
   return PSCL_OK;
 }
 
@@ -947,11 +1018,11 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
 
   const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && ctx->demux_kernel != 4 && na == 2 && h_alpha[0] == 0.0 &&
                            h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
+  PSCL_CUDA(ctx, cudaEventSynchronize(ctx->ev_dict));  // set_geno's flag words (long done by now in every normal flow)
+  if (ctx->h_geno_bad && *ctx->h_geno_bad)
+    return pscl_fail(ctx, PSCL_EINVAL, "pscl_geno.gt8 holds a code other than 0/1/2 (missing calls need gp_f32)");
   bool use_dict = false;  // dictionary-coded genotypes: auto (0) and 6 take them when the table allows, 1 keeps the row gather
-  if (use_default && ctx->dict_built && (ctx->demux_kernel == 0 || ctx->demux_kernel == 6)) {
-    PSCL_CUDA(ctx, cudaEventSynchronize(ctx->ev_dict));
-    use_dict = *ctx->h_dict_over == 0;
-  }
+  if (use_default && ctx->dict_built && (ctx->demux_kernel == 0 || ctx->demux_kernel == 6)) use_dict = *ctx->h_dict_over == 0;
   // every other shape: the polynomial kernel unless k_demux_general was asked for
   const bool use_poly = !use_default && !ctx->force_general && ctx->demux_kernel != 2;
   if (use_poly) {

@@ -240,8 +240,18 @@ void load_plp(const LoadOptions& o, Loaded& L) {
       }
       const size_t base = L.gp.size();
       L.gp.resize(base + (size_t)nv * 3, 0.0);
+      L.gp_f32.resize(base + (size_t)nv * 3, 0.f);
+      L.gt8.resize(L.gt8.size() + (size_t)nv, 0);
+      L.err_snp.push_back(0.0);
       L.has_gp.push_back(found ? 1 : 0);
       if (!found) continue;
+      for (int j = 0; j < nv; ++j) {  // raw forms for the device-side mixing
+        const float* g = &vc->gps[(size_t)j * 3];
+        L.gp_f32[base + 3 * j] = g[0]; L.gp_f32[base + 3 * j + 1] = g[1]; L.gp_f32[base + 3 * j + 2] = g[2];
+        const int code = (g[0] == 1.f && g[1] == 0.f && g[2] == 0.f) ? 0 : (g[0] == 0.f && g[1] == 1.f && g[2] == 0.f) ? 1
+                       : (g[0] == 0.f && g[1] == 0.f && g[2] == 1.f) ? 2 : -1;
+        if (code < 0) L.gt8_ok = false; else L.gt8[base / 3 + j] = (uint8_t)code;
+      }
       double avg[3] = {1e-10, 1e-10, 1e-10};  // :288-292
       for (int i = 0; i < nv * 3; ++i) avg[i % 3] += (L.gp[base + i] = (double)vc->gps[i]);
       const double sum = avg[0] + avg[1] + avg[2];
@@ -265,6 +275,7 @@ void load_plp(const LoadOptions& o, Loaded& L) {
         if (!ok) throw host_error("Cannot extract " + o.r2_info + " (1 float value) from INFO field at " + std::string(f[1]) + ":" + std::to_string(pos) + ". Cannot use --geno-error-coeff");
         err += (1 - o.geno_error_offset) * (1 - r2) * o.geno_error_coeff;
       }
+      L.err_snp.back() = err;  // the library clamps it the same way
       if (err > 0.999) err = 0.999;
       if (err < 0) err = 0;
       if (err > 0)

@@ -42,8 +42,23 @@ struct Loaded {
   std::vector<int64_t> cell_uniq_reads, cell_totl_reads;
   // genotypes (when a VCF was given)
   std::vector<std::string> samples;
-  std::vector<double> gp;       // [V][nv][3]
+  std::vector<double> gp;       // [V][nv][3] after the geno-error mixing (host copy: checksums, debugging)
   std::vector<uint8_t> has_gp;  // [V]
+  // raw forms of ABI 4 (what crosses PCIe; the library mixes on the device): the reader's float posteriors, the per-SNP
+  // error rate, and hard calls when every posterior row is one-hot (--field GT without missing calls)
+  std::vector<float> gp_f32;    // [V][nv][3]
+  std::vector<double> err_snp;  // [V]
+  std::vector<uint8_t> gt8;     // [V][nv], valid while gt8_ok
+  bool gt8_ok = true;
+  pscl_geno geno_view() const {
+    pscl_geno g;
+    g.n_samples = (int32_t)samples.size();
+    g.gp = nullptr; g.has_gp = has_gp.data();
+    g.gp_f32 = gt8_ok ? nullptr : gp_f32.data();
+    g.gt8 = gt8_ok ? gt8.data() : nullptr;
+    g.geno_err_snp = err_snp.data(); g.geno_err = 0.0;
+    return g;
+  }
 
   // compact arrays of ABI 2 (filled by view() on first use): 32-bit read offsets, allele<<6|qual
   mutable std::vector<uint32_t> pair_read_ptr32;

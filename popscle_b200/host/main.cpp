@@ -128,7 +128,7 @@ int cmd_demuxlet(int argc, char** argv) {
   notice("Starting to identify best matching individual IDs");
   Ctx ctx;
   pscl_pileup view = L.view();
-  pscl_geno geno = {(int32_t)L.samples.size(), L.gp.data(), L.has_gp.data()};
+  pscl_geno geno = L.geno_view();  // raw posteriors / hard calls + error rates: the library mixes on the device
   pscl_demux_opts opts = {(int32_t)alphas.size(), alphas.data(), doubletPrior};
   std::vector<pscl_demux_cell> cells((size_t)L.n_cells);
   ctx.chk(pscl_demux_run(ctx.h, &view, &geno, &opts, cells.data(), NULL));

@@ -248,6 +248,48 @@ def test_genotype_dictionary_is_bit_identical_and_falls_back(ctx):
     assert rec.tobytes() == lane.tobytes() and np.array_equal(grid, lgrid, equal_nan=True)
 
 
+def test_raw_genotype_forms_are_mixed_on_the_device_bit_for_bit(ctx):
+    """ABI 4: hard calls (uint8) or the reader's float32 posteriors plus the genotype error rate go in, and the library
+    does the mixing of sc_drop_seq.cpp:287-315 on the device; the records are bit-identical to those from the table the
+    host mixes (synth.gt_to_gp restates those lines).  Per-SNP error rates (--geno-error-coeff), SNPs without GP,
+    clamping at 0.999, err = 0, soft posteriors, and an invalid hard-call code are covered."""
+    from popscle_b200 import PsclError, RawGeno
+    s = synth.make_pileup(C=150, nv=6, V=1500, kbar=200, seed=808)
+    rng = np.random.default_rng(8)
+    V, nv = s.plp.n_snps, 6
+    gt8 = np.ascontiguousarray(s.geno.T.astype(np.uint8))
+    onehot = np.zeros((V, nv, 3), dtype=np.float32)
+    onehot[np.arange(V)[:, None], np.arange(nv)[None, :], s.geno.T.astype(np.int64)] = 1.0
+    has = (rng.random(V) > 0.2).astype(np.uint8)
+    for err in (0.1, 0.0, 0.02, 5.0):
+        want = ctx.demux_run(s.plp, synth.gt_to_gp(s.geno, err), None, DEFAULT, want_grid=True)
+        for raw in (RawGeno(gt8=gt8, err=err), RawGeno(gp_f32=onehot, err=err)):
+            got = ctx.demux_run(s.plp, raw, None, DEFAULT, want_grid=True)
+            assert got[0].tobytes() == want[0].tobytes() and np.array_equal(got[1], want[1], equal_nan=True), err
+    want = ctx.demux_run(s.plp, synth.gt_to_gp(s.geno), has, DEFAULT)
+    assert ctx.demux_run(s.plp, RawGeno(gt8=gt8), has, DEFAULT).tobytes() == want.tobytes()
+    # per-SNP error rates, soft float32 posteriors, a non-default alpha grid (k_demux_poly)
+    err_snp = rng.uniform(-0.05, 1.2, V)
+    soft = rng.dirichlet([0.5, 0.5, 0.5], size=(V, nv)).astype(np.float32)
+    mixed = np.empty((V, nv, 3))
+    for v in range(V):  # sc_drop_seq.cpp:288-315 restated per SNP
+        avg = np.full(3, 1e-10)
+        for j in range(nv):
+            avg = avg + soft[v, j].astype(np.float64)
+        avg = avg / (avg[0] + avg[1] + avg[2])
+        e = min(max(err_snp[v], 0.0), 0.999)
+        mixed[v] = (1 - e) * soft[v].astype(np.float64) + e * avg if e > 0 else soft[v]
+    for alphas in (DEFAULT, [0.0, 0.2, 0.5]):
+        want = ctx.demux_run(s.plp, mixed, None, alphas)
+        got = ctx.demux_run(s.plp, RawGeno(gp_f32=soft, err_snp=err_snp), None, alphas)
+        assert got.tobytes() == want.tobytes()
+    bad = gt8.copy()
+    bad[17, 3] = 3
+    with pytest.raises(PsclError):
+        ctx.demux_run(s.plp, RawGeno(gt8=bad), None, DEFAULT)
+    ctx.demux_run(s.plp, RawGeno(gt8=gt8), None, DEFAULT)  # the context recovers
+
+
 def test_compact_pileup_inputs_are_equivalent(ctx):
     """ABI 2 compact host arrays (u32 read offsets, allele<<6|qual) give bit-identical records, for demuxlet and
     freemuxlet; a byte with allele code 3 is rejected."""
