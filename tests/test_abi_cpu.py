@@ -114,3 +114,18 @@ def test_pileup_struct_matches_the_ctypes_mirror():
     assert wide.compact3() is None
     cs = wide.c_struct(compact=3)
     assert cs.pair_snp is not None and cs.pair_snp_delta16 is None
+
+
+def test_raw_genotype_forms_build_the_right_struct():
+    """ABI 4: RawGeno fills gt8 / gp_f32 / geno_err(_snp) and leaves gp NULL; the plain table fills gp only."""
+    from popscle_b200 import RawGeno
+    from popscle_b200.capi import Context
+    gt8 = np.zeros((7, 3), dtype=np.uint8)
+    g, keep, V, nv = Context._geno(RawGeno(gt8=gt8, err=0.05), None)
+    assert (V, nv) == (7, 3) and g.gp is None and g.gp_f32 is None and g.gt8 == keep[0].ctypes.data and g.geno_err == 0.05
+    f32 = np.zeros((7, 3, 3), dtype=np.float32)
+    es = np.linspace(0, 1, 7)
+    g, keep, V, nv = Context._geno(RawGeno(gp_f32=f32, err_snp=es), np.ones(7, np.uint8))
+    assert g.gt8 is None and g.gp_f32 == keep[0].ctypes.data and g.geno_err_snp == keep[1].ctypes.data and g.has_gp == keep[2].ctypes.data
+    g, keep, V, nv = Context._geno(np.zeros((7, 3, 3)), None)
+    assert g.gp == keep[0].ctypes.data and g.gt8 is None and g.gp_f32 is None and g.geno_err_snp is None
