@@ -259,6 +259,7 @@ EXPORTED_SYMBOLS = [
 
 class Context:
     """One pscl_ctx (one GPU)."""
+    accepts_compact = True  # demux_run takes RawGeno genotypes and compact=2/3 pileup forms (cli.py asks)
 
     def __init__(self, device: int = 0, stream: int | None = None):
         self.lib = load_library()

@@ -88,9 +88,27 @@ int dry_run(const Loaded& L) {
   mix(L.read_qual.data(), L.read_qual.size()); mix(L.af.data(), L.af.size() * 8);
   unsigned long long hg = 1469598103934665603ull;
   std::swap(h, hg); mix(L.gp.data(), L.gp.size() * 8); mix(L.has_gp.data(), L.has_gp.size()); std::swap(h, hg);
-  printf("{\"cells\": %d, \"snps\": %d, \"pairs\": %zu, \"reads\": %zu, \"samples\": %zu, \"has_gp\": %zu, \"pileup_fnv1a\": \"%016llx\", \"geno_fnv1a\": \"%016llx\"}\n",
+  // the compact forms that actually cross the ABI (view(): ABI 2/3 arrays; geno_view(): ABI 4 raw genotypes)
+  unsigned long long hc = 1469598103934665603ull, hr = 1469598103934665603ull;
+  const pscl_pileup v = L.view();
+  const int form = v.pair_snp_delta16 ? 3 : v.pair_read_ptr32 ? 2 : 0;
+  std::swap(h, hc);
+  if (v.pair_read_ptr32) { mix(v.pair_read_ptr32, (size_t)(v.n_pairs + 1) * 4); mix(v.read_aq, (size_t)v.n_reads); }
+  if (v.pair_snp_delta16) { mix(v.cell_first_snp, (size_t)v.n_cells * 4); mix(v.pair_snp_delta16, (size_t)v.n_pairs * 2); mix(v.pair_nreads8, (size_t)v.n_pairs); }
+  std::swap(h, hc);
+  int gt8 = -1;
+  if (!L.samples.empty()) {
+    const pscl_geno g = L.geno_view();
+    gt8 = g.gt8 ? 1 : 0;
+    std::swap(h, hr);
+    if (g.gt8) mix(g.gt8, L.gt8.size()); else mix(g.gp_f32, L.gp_f32.size() * 4);
+    mix(g.geno_err_snp, L.err_snp.size() * 8);
+    std::swap(h, hr);
+  }
+  printf("{\"cells\": %d, \"snps\": %d, \"pairs\": %zu, \"reads\": %zu, \"samples\": %zu, \"has_gp\": %zu, \"pileup_fnv1a\": \"%016llx\", \"geno_fnv1a\": \"%016llx\", "
+         "\"compact_form\": %d, \"compact_fnv1a\": \"%016llx\", \"gt8\": %d, \"raw_geno_fnv1a\": \"%016llx\"}\n",
          L.n_cells, L.n_snps, L.pair_snp.size(), L.read_allele.size(), L.samples.size(),
-         (size_t)std::count(L.has_gp.begin(), L.has_gp.end(), 1), h, hg);
+         (size_t)std::count(L.has_gp.begin(), L.has_gp.end(), 1), h, hg, form, hc, gt8, hr);
   return 0;
 }
 

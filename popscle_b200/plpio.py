@@ -147,6 +147,17 @@ class Genotypes:
     samples: list
     gp: np.ndarray       # float64 [V][nv][3] after the error mixing (what add_snp stores)
     has_gp: np.ndarray   # uint8 [V]
+    # raw forms of ABI 4 (what the hosts hand to the library, which mixes on the device)
+    gp_f32: np.ndarray | None = None   # float32 [V][nv][3] as the reader returned them
+    err_snp: np.ndarray | None = None  # float64 [V] error rate before clamping
+    gt8: np.ndarray | None = None      # uint8 [V][nv] hard calls when every row with GP is one-hot, else None
+
+    def raw(self):
+        """RawGeno for Context.demux_run: hard calls when possible, float posteriors otherwise."""
+        from .capi import RawGeno
+        if self.gt8 is not None:
+            return RawGeno(gt8=self.gt8, err_snp=self.err_snp, err=0.0)
+        return RawGeno(gp_f32=self.gp_f32, err_snp=self.err_snp, err=0.0)
 
 
 @dataclass
@@ -319,7 +330,7 @@ def load_plp(prefix: str, vcf: str | None = None, field: str = "GP", geno_error_
     chr2rid, rid2chr = {}, []
     chrom, pos, ref, alt, af = [], [], [], [], []
     vit = samples = cur = None
-    gps, has = [], []
+    gps, has, raws, errs = [], [], [], []
     if vcf is not None:
         vit = _parse_vcf(vcf, field, sm_list, min_mac, min_callrate)
         _, samples, _ = next(vit)
@@ -348,7 +359,8 @@ def load_plp(prefix: str, vcf: str | None = None, field: str = "GP", geno_error_
                     break
             cur = next(vit, None)
         if not found:
-            has.append(0); gps.append(np.zeros(nv * 3)); continue
+            has.append(0); gps.append(np.zeros(nv * 3)); raws.append(np.zeros(nv * 3, dtype=np.float32)); errs.append(0.0); continue
+        raws.append(np.asarray(cur[4], dtype=np.float32)[:nv * 3])
         g = cur[4].astype(np.float64)  # get_posterior_at widens the float (bcf_filtered_reader.h:166)
         avg = np.full(3, 1e-10)
         for i in range(nv * 3):  # :289-291, sample-major accumulation order
@@ -361,6 +373,7 @@ def load_plp(prefix: str, vcf: str | None = None, field: str = "GP", geno_error_
                 raise ValueError(f"Cannot extract {r2_info} (1 float value) from INFO field at {r[1]}:{p}. Cannot use --geno-error-coeff")
             # `1 - r2flts[0]` is evaluated in float32 in the reference (int - float), then widened
             err += (1 - geno_error_offset) * float(np.float32(1.0) - np.float32(r2)) * geno_error_coeff
+        errs.append(err)
         err = min(max(err, 0.0), 0.999)
         if err > 0:
             g = (1 - err) * g + err * np.tile(avg, nv)
@@ -408,7 +421,14 @@ def load_plp(prefix: str, vcf: str | None = None, field: str = "GP", geno_error_
     totl[agree] = np.asarray(tmp_totl, dtype=np.int64)[agree]
     geno = None
     if vit is not None:
-        geno = Genotypes(list(samples), np.asarray(gps, dtype=np.float64).reshape(V, nv, 3), np.asarray(has, dtype=np.uint8))
+        has8 = np.asarray(has, dtype=np.uint8)
+        f32 = np.asarray(raws, dtype=np.float32).reshape(V, nv, 3)
+        onehot = ((f32 == 1.0).sum(axis=2) == 1) & ((f32 == 0.0).sum(axis=2) == 2)
+        gt8 = None
+        if bool(onehot[has8 != 0].all()):  # --field GT without missing calls: one byte per call crosses PCIe
+            gt8 = np.where(has8[:, None] != 0, f32.argmax(axis=2), 0).astype(np.uint8)
+        geno = Genotypes(list(samples), np.asarray(gps, dtype=np.float64).reshape(V, nv, 3), has8,
+                         np.ascontiguousarray(f32), np.asarray(errs, dtype=np.float64), gt8)
     return LoadedPileup(plp, barcodes, sites, uniq, totl, geno, rid2chr)
 
 

@@ -185,6 +185,14 @@ def test_cpp_host_loader_matches_python_loader(case, tmp_path, host_exe):
     if L.geno is not None:
         assert got["samples"] == len(L.geno.samples) and got["has_gp"] == int(L.geno.has_gp.sum())
         assert got["geno_fnv1a"] == _fnv1a(np.ascontiguousarray(L.geno.gp), L.geno.has_gp)
+        # ABI 4 raw genotype forms, as geno_view() hands them to the library
+        assert got["gt8"] == (1 if L.geno.gt8 is not None else 0) == (1 if o["field"] == "GT" else 0)
+        assert got["raw_geno_fnv1a"] == _fnv1a(L.geno.gt8 if L.geno.gt8 is not None else L.geno.gp_f32, L.geno.err_snp)
+    # ABI 2/3 compact pileup arrays, as view() hands them to the library
+    p32, aq = p.compact()
+    c3 = p.compact3()
+    assert got["compact_form"] == (3 if c3 is not None else 2)
+    assert got["compact_fnv1a"] == _fnv1a(p32, aq, *(c3 if c3 is not None else ()))
 
 
 def test_cpp_host_errors(host_exe, tmp_path):
