@@ -205,7 +205,14 @@ int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* 
 int pscl_demux_fetch(pscl_ctx* ctx, pscl_demux_cell* out, double* llk_grid);
 /* Debug switch: keep the per-cell LLK grid on the device so pscl_demux_fetch can return it. */
 int pscl_demux_keep_grid(pscl_ctx* ctx, int enable);
-/* One-call convenience used by the CLI host: upload (if needed) + score + fetch. */
+/* One-call path used by the CLI hosts: genotype table + pileup upload + score + fetch; returns with the
+ * records in `out` (and the grid in `llk_grid`, if not NULL).  When `host` carries the ABI-3 delta arrays
+ * and the shape is the default kernel's (alpha grid {0, 0.5}, <= 8 samples, no grid requested), the run is
+ * staged: the SNP gaps cross PCIe in slices on a second stream while the one scoring launch already works
+ * on the slices that have landed, so most of the kernel time hides under the copy.  Page-locked host
+ * arrays (cudaHostAlloc / cudaHostRegister) make that overlap real; pageable ones give the same records
+ * without it.  Environment: PSCL_STAGES=n sets the slice count (1 = no staging), PSCL_TRACE=1 prints the
+ * wall-clock of every phase on stderr. */
 int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_geno* geno,
                    const pscl_demux_opts* opts, pscl_demux_cell* out, double* llk_grid);
 /* Device time (ms, CUDA events on pscl_stream) of the kernels of the last pscl_demux_score. */
