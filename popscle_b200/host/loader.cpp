@@ -2,6 +2,7 @@
 #include "loader.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -182,6 +183,15 @@ void expect_header(LineReader& r, const char* const* names, int n, const std::st
 }  // namespace
 
 void load_plp(const LoadOptions& o, Loaded& L) {
+  // PSCL_TRACE=1: wall-clock of the loader's phases on stderr
+  const bool trace = getenv("PSCL_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[load_plp] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   std::string line;
   std::vector<char*> f;
   // ---- CEL (sc_drop_seq.cpp:124-203) ----
@@ -207,6 +217,7 @@ void load_plp(const LoadOptions& o, Loaded& L) {
     }
   }
   const int32_t C = (int32_t)L.barcodes.size();
+  lap("cel.gz");
   // ---- VAR, merge-joined with the VCF cursor (:206-330) ----
   {
     LineReader r(o.plp_prefix + ".var.gz");
@@ -283,6 +294,7 @@ void load_plp(const LoadOptions& o, Loaded& L) {
     }
   }
   const int32_t V = (int32_t)L.chrom.size();
+  lap("var.gz + vcf");
   // ---- PLP (:335-372): rows -> (cell, snp, reads); then cell-major, SNP ascending ----
   std::vector<int32_t> row_cell, row_snp;
   std::vector<int64_t> row_beg;  // into al / bq
@@ -316,33 +328,47 @@ void load_plp(const LoadOptions& o, Loaded& L) {
     row_beg.push_back((int64_t)al.size());
   }
   const size_t R = row_cell.size();
+  lap("plp.gz rows");
   std::vector<uint32_t> order(R);
   std::iota(order.begin(), order.end(), 0u);
   bool sorted = true;
   for (size_t i = 1; i < R && sorted; ++i)
     sorted = row_cell[i - 1] < row_cell[i] || (row_cell[i - 1] == row_cell[i] && row_snp[i - 1] <= row_snp[i]);
-  if (!sorted)  // dsc-pileup writes SNP-major; the std::map of the reference makes it cell-major, SNP ascending
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-      return row_cell[a] != row_cell[b] ? row_cell[a] < row_cell[b] : row_snp[a] < row_snp[b];
-    });
+  if (!sorted) {  // dsc-pileup writes SNP-major; the std::map of the reference makes it cell-major, SNP ascending
+    bool snp_major = true;
+    for (size_t i = 1; i < R && snp_major; ++i) snp_major = row_snp[i - 1] <= row_snp[i];
+    if (snp_major) {  // rows already ascend in SNP id: a stable counting sort by cell is the whole job, O(R)
+      std::vector<size_t> head((size_t)C + 1, 0);
+      for (size_t i = 0; i < R; ++i) ++head[(size_t)row_cell[i] + 1];
+      for (int32_t c = 0; c < C; ++c) head[c + 1] += head[c];
+      for (size_t i = 0; i < R; ++i) order[head[row_cell[i]]++] = (uint32_t)i;
+    } else {
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        return row_cell[a] != row_cell[b] ? row_cell[a] < row_cell[b] : row_snp[a] < row_snp[b];
+      });
+    }
+  }
+  lap("cell-major order");
   L.n_cells = C; L.n_snps = V;
   L.cell_ptr.assign((size_t)C + 1, 0);
   L.pair_read_ptr.assign(1, 0);
-  L.read_allele.reserve(al.size()); L.read_qual.reserve(bq.size());
+  L.read_allele.resize(al.size()); L.read_qual.resize(bq.size());
+  L.pair_snp.reserve(R); L.pair_read_ptr.reserve(R + 1);
   L.cell_uniq_reads.assign(C, 0);
   int prev_c = -1, prev_s = -1;
+  size_t w = 0;  // reads written so far
   for (size_t k = 0; k < R; ++k) {
     const uint32_t i = order[k];
     const bool same = row_cell[i] == prev_c && row_snp[i] == prev_s;  // a (cell,SNP) listed on several rows is one pair
-    L.read_allele.insert(L.read_allele.end(), al.begin() + row_beg[i], al.begin() + row_beg[i + 1]);
-    L.read_qual.insert(L.read_qual.end(), bq.begin() + row_beg[i], bq.begin() + row_beg[i + 1]);
-    if (same) L.pair_read_ptr.back() = (int64_t)L.read_allele.size();
+    const int64_t rb = row_beg[i], re = row_beg[i + 1];
+    for (int64_t r = rb; r < re; ++r, ++w) { L.read_allele[w] = al[r]; L.read_qual[w] = bq[r]; }
+    if (same) L.pair_read_ptr.back() = (int64_t)w;
     else {
       L.pair_snp.push_back(row_snp[i]);
-      L.pair_read_ptr.push_back((int64_t)L.read_allele.size());
+      L.pair_read_ptr.push_back((int64_t)w);
       ++L.cell_ptr[(size_t)row_cell[i] + 1];
     }
-    L.cell_uniq_reads[row_cell[i]] += row_beg[i + 1] - row_beg[i];
+    L.cell_uniq_reads[row_cell[i]] += re - rb;
     prev_c = row_cell[i]; prev_s = row_snp[i];
   }
   for (int32_t c = 0; c < C; ++c) L.cell_ptr[c + 1] += L.cell_ptr[c];
@@ -350,6 +376,7 @@ void load_plp(const LoadOptions& o, Loaded& L) {
   L.cell_totl_reads = L.cell_uniq_reads;
   for (int32_t c = 0; c < C; ++c)
     if (L.cell_uniq_reads[c] == tmp_uniq[c] && tmp_nsnp[c] == L.cell_ptr[c + 1] - L.cell_ptr[c]) L.cell_totl_reads[c] = tmp_totl[c];
+  lap("flat image");
 }
 
 }  // namespace pscl_host
