@@ -39,6 +39,8 @@ struct VcfCursor {
   std::string info;                   // INFO column of the current record
   std::string line;
   std::vector<std::string> c, alleles, fmt, cell, parts, vals;
+  std::vector<int> g1, g2, acs;
+  std::vector<std::vector<std::string>> smp;
 
   VcfCursor(const std::string& path, const LoadOptions& opt) : rd(path), o(opt) {
     bool saw = false;
@@ -98,9 +100,9 @@ struct VcfCursor {
       }
       if (gi < 0) throw host_error("Cannot find the field GT from the VCF file at position " + c[0] + ":" + c[1]);
       // minMAC / minCallRate force GT parsing (bcf_filter_arg.h:110-113)
-      std::vector<int> g1(nv), g2(nv), acs(nal, 0);
+      g1.assign(nv, 0); g2.assign(nv, 0); acs.assign(nal, 0);  // members: no allocation per record
       int an = 0;
-      std::vector<std::vector<std::string>> smp(nv);
+      if ((int)smp.size() != nv) smp.resize(nv);
       for (int i = 0; i < nv; ++i) {
         split_char(c[9 + cols[i]], ':', smp[i]);
         const std::string& gt = gi < (int)smp[i].size() ? smp[i][gi] : std::string(".");
