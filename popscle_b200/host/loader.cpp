@@ -298,23 +298,47 @@ void load_plp(const LoadOptions& o, Loaded& L) {
   const int32_t V = (int32_t)L.chrom.size();
   lap("var.gz + vcf");
   // ---- PLP (:335-372): rows -> (cell, snp, reads); then cell-major, SNP ascending ----
-  std::vector<int32_t> row_cell, row_snp;
-  std::vector<int64_t> row_beg;  // into al / bq
+  struct Row { int32_t cell, snp; int64_t beg; };  // beg: into al / bq; one record so the cell-major pass below
+  std::vector<Row> rows;                            // touches one cache line per row, not four
   std::vector<uint8_t> al, bq;
   {
     LineReader r(o.plp_prefix + ".plp.gz");
     static const char* H[] = {"#DROPLET_ID", "SNP_ID", "ALLELES", "BASEQS"};
     expect_header(r, H, 4, o.plp_prefix + ".plp.gz", "#DROPLET_ID SNP_ID ALLELES BASEQS");
-    while (next_row(r, line, f)) {
-      if (f.size() < 4) throw host_error("Cannot access field at 3 >= " + std::to_string(f.size()));
-      const int drop = atoi(f[0]);
-      if (drop < 0 || drop >= (int)index_bcs.size()) throw host_error("DROPLET_ID " + std::string(f[0]) + " of .plp.gz is not in .cel.gz");
+    // rows are parsed in place from the reader's buffer (whitespace-separated like tsv_reader's ksplit; atoi semantics)
+    const char* lb = nullptr;
+    size_t ln = 0;
+    auto is_ws = [](char ch) { return ch == ' ' || ch == '\t' || ch == '\v' || ch == '\f' || ch == '\r' || ch == '\n'; };
+    while (r.next_span(lb, ln) && ln > 0) {
+      const char* p = lb;
+      const char* const end = lb + ln;
+      const char* fb[4]; const char* fe[4];
+      int nf = 0;
+      while (p < end) {
+        while (p < end && is_ws(*p)) ++p;
+        if (p >= end) break;
+        const char* q = p;
+        while (q < end && !is_ws(*q)) ++q;
+        if (nf < 4) { fb[nf] = p; fe[nf] = q; }
+        ++nf;
+        p = q;
+      }
+      if (nf < 4) throw host_error("Cannot access field at 3 >= " + std::to_string(nf));
+      auto to_int = [](const char* b2, const char* e2) {  // atoi: optional sign, leading digits
+        bool neg = false;
+        if (b2 < e2 && (*b2 == '-' || *b2 == '+')) { neg = *b2 == '-'; ++b2; }
+        long v = 0;
+        while (b2 < e2 && *b2 >= '0' && *b2 <= '9') { v = v * 10 + (*b2 - '0'); ++b2; }
+        return (int)(neg ? -v : v);
+      };
+      const int drop = to_int(fb[0], fe[0]);
+      if (drop < 0 || drop >= (int)index_bcs.size()) throw host_error("DROPLET_ID " + std::string(fb[0], fe[0]) + " of .plp.gz is not in .cel.gz");
       const int ibc = index_bcs[drop];
       if (ibc < 0) continue;
-      const int snp = atoi(f[1]);
-      if (snp < 0 || snp >= V) throw host_error("SNP_ID " + std::string(f[1]) + " of .plp.gz is not in .var.gz");
-      const char *pa = f[2], *pq = f[3];
-      const size_t l = strlen(pq), la = strlen(pa);
+      const int snp = to_int(fb[1], fe[1]);
+      if (snp < 0 || snp >= V) throw host_error("SNP_ID " + std::string(fb[1], fe[1]) + " of .plp.gz is not in .var.gz");
+      const char *pa = fb[2], *pq = fb[3];
+      const size_t l = (size_t)(fe[3] - fb[3]), la = (size_t)(fe[2] - fb[2]);
       const int64_t b0 = (int64_t)al.size();
       for (size_t i = 0; i < l && i < la; ++i) {
         int q = (int)(signed char)(pq[i] - 33);
@@ -325,28 +349,28 @@ void load_plp(const LoadOptions& o, Loaded& L) {
         }
       }
       if ((int64_t)al.size() == b0) continue;
-      row_cell.push_back(ibc); row_snp.push_back(snp); row_beg.push_back(b0);
+      rows.push_back(Row{ibc, snp, b0});
     }
-    row_beg.push_back((int64_t)al.size());
+    rows.push_back(Row{-1, -1, (int64_t)al.size()});  // sentinel: end of the last row's reads
   }
-  const size_t R = row_cell.size();
+  const size_t R = rows.size() - 1;
   lap("plp.gz rows");
   std::vector<uint32_t> order(R);
   std::iota(order.begin(), order.end(), 0u);
   bool sorted = true;
   for (size_t i = 1; i < R && sorted; ++i)
-    sorted = row_cell[i - 1] < row_cell[i] || (row_cell[i - 1] == row_cell[i] && row_snp[i - 1] <= row_snp[i]);
+    sorted = rows[i - 1].cell < rows[i].cell || (rows[i - 1].cell == rows[i].cell && rows[i - 1].snp <= rows[i].snp);
   if (!sorted) {  // dsc-pileup writes SNP-major; the std::map of the reference makes it cell-major, SNP ascending
     bool snp_major = true;
-    for (size_t i = 1; i < R && snp_major; ++i) snp_major = row_snp[i - 1] <= row_snp[i];
+    for (size_t i = 1; i < R && snp_major; ++i) snp_major = rows[i - 1].snp <= rows[i].snp;
     if (snp_major) {  // rows already ascend in SNP id: a stable counting sort by cell is the whole job, O(R)
       std::vector<size_t> head((size_t)C + 1, 0);
-      for (size_t i = 0; i < R; ++i) ++head[(size_t)row_cell[i] + 1];
+      for (size_t i = 0; i < R; ++i) ++head[(size_t)rows[i].cell + 1];
       for (int32_t c = 0; c < C; ++c) head[c + 1] += head[c];
-      for (size_t i = 0; i < R; ++i) order[head[row_cell[i]]++] = (uint32_t)i;
+      for (size_t i = 0; i < R; ++i) order[head[rows[i].cell]++] = (uint32_t)i;
     } else {
       std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        return row_cell[a] != row_cell[b] ? row_cell[a] < row_cell[b] : row_snp[a] < row_snp[b];
+        return rows[a].cell != rows[b].cell ? rows[a].cell < rows[b].cell : rows[a].snp < rows[b].snp;
       });
     }
   }
@@ -361,17 +385,18 @@ void load_plp(const LoadOptions& o, Loaded& L) {
   size_t w = 0;  // reads written so far
   for (size_t k = 0; k < R; ++k) {
     const uint32_t i = order[k];
-    const bool same = row_cell[i] == prev_c && row_snp[i] == prev_s;  // a (cell,SNP) listed on several rows is one pair
-    const int64_t rb = row_beg[i], re = row_beg[i + 1];
+    const Row rw = rows[i];
+    const bool same = rw.cell == prev_c && rw.snp == prev_s;  // a (cell,SNP) listed on several rows is one pair
+    const int64_t rb = rw.beg, re = rows[i + 1].beg;
     for (int64_t r = rb; r < re; ++r, ++w) { L.read_allele[w] = al[r]; L.read_qual[w] = bq[r]; }
     if (same) L.pair_read_ptr.back() = (int64_t)w;
     else {
-      L.pair_snp.push_back(row_snp[i]);
+      L.pair_snp.push_back(rw.snp);
       L.pair_read_ptr.push_back((int64_t)w);
-      ++L.cell_ptr[(size_t)row_cell[i] + 1];
+      ++L.cell_ptr[(size_t)rw.cell + 1];
     }
-    L.cell_uniq_reads[row_cell[i]] += re - rb;
-    prev_c = row_cell[i]; prev_s = row_snp[i];
+    L.cell_uniq_reads[rw.cell] += re - rb;
+    prev_c = rw.cell; prev_s = rw.snp;
   }
   for (int32_t c = 0; c < C; ++c) L.cell_ptr[c + 1] += L.cell_ptr[c];
   // sanity check on the observed counts (:375-381): NUM.READ replaces the pass count where the rest agrees

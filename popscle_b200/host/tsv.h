@@ -51,6 +51,29 @@ class LineReader {
       pos_ = len_;
     }
   }
+  // the same, as a view into the reader's buffer (valid until the next call): no copy per line
+  bool next_span(const char*& b, size_t& n) {
+    for (;;) {
+      const char* s = buf_.data() + pos_;
+      const char* e = pos_ < len_ ? (const char*)memchr(s, '\n', len_ - pos_) : nullptr;
+      if (e) {
+        b = s; n = (size_t)(e - s); pos_ += n + 1;
+        if (n && b[n - 1] == '\r') --n;
+        return true;
+      }
+      if (eof_) {  // last line without a terminator
+        if (pos_ == len_) return false;
+        b = s; n = len_ - pos_; pos_ = len_;
+        return true;
+      }
+      const size_t rem = len_ - pos_;  // a partial line: move it to the front and read on
+      if (rem == buf_.size()) buf_.resize(buf_.size() * 2);
+      if (rem && pos_) memmove(buf_.data(), buf_.data() + pos_, rem);
+      const int got = gzread(gz_, buf_.data() + rem, (unsigned)(buf_.size() - rem));
+      if (got <= 0) eof_ = true;
+      len_ = rem + (got > 0 ? (size_t)got : 0); pos_ = 0;
+    }
+  }
   const std::string& path() const { return path_; }
 
  private:
@@ -58,6 +81,7 @@ class LineReader {
   gzFile gz_ = nullptr;
   std::vector<char> buf_;
   size_t pos_ = 0, len_ = 0;
+  bool eof_ = false;
 };
 
 // whitespace-separated fields of `line` (in place: the line is cut into NUL-terminated tokens)
