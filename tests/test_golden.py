@@ -229,3 +229,41 @@ def test_cpp_host_matches_reference_files(case, tmp_path, host_exe):
         (_compare_vcf if fn.endswith(".vcf") else _compare_table)(ref, txt, f"{case}/{fn} (C++ host)")
         n += 1
     assert n > 0
+
+
+def test_cpp_plp_parser_line_endings(tmp_path, host_exe):
+    """The in-place PLP row parser of the C++ host: a last row without a newline, CRLF line ends and rows that straddle
+    the reader's 1 MiB buffer give the same image; an empty line ends the file as tsv_reader does (tsv_reader.cpp:37-41)."""
+    import gzip
+    import subprocess
+    case = "demux_gt"
+    argv = _host_argv(case, tmp_path)
+
+    def run(mutate):
+        work = tmp_path / mutate.__name__
+        shutil.copytree(os.path.join(GOLD, case), work)
+        plp = work / "p.plp.gz"
+        text = gzip.open(plp, "rt").read()
+        with gzip.open(plp, "wt", newline="") as f:
+            f.write(mutate(text))
+        r = subprocess.run([host_exe] + argv + ["--dry-run"], cwd=work, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout)
+
+    def same(t): return t
+    def no_final_newline(t): return t.rstrip("\n")
+    def crlf(t): return t.replace("\n", "\r\n")
+    def padded(t):  # > 1 MiB of leading whitespace on one row: the row straddles (and outgrows) the read buffer
+        lines = t.split("\n")
+        lines[5] = " " * (3 << 20) + lines[5]
+        return "\n".join(lines)
+    def cut_at_empty_line(t):
+        lines = t.split("\n")
+        return "\n".join(lines[:40] + [""] + lines[40:])
+
+    base = run(same)
+    for m in (no_final_newline, crlf, padded):
+        got = run(m)
+        assert got["pileup_fnv1a"] == base["pileup_fnv1a"] and got["pairs"] == base["pairs"], m.__name__
+    short = run(cut_at_empty_line)
+    assert 0 < short["reads"] < base["reads"]
