@@ -5,11 +5,16 @@
 // the items of a cell in fixed order and restates the prior / logAdd / best-next / SNG-DBL-AMB
 // logic (:788-991).
 //
-//   k_demux_default<NV> : the default alpha grid {0, 0.5} (:85-89) and 2 <= nv <= 8.  One warp per
-//       work item, ONE LANE PER (cell,SNP) PAIR: the nv singlet + nv(nv-1)/2 doublet running
+//   k_demux_default<NV, DELTA, DICT> : the default alpha grid {0, 0.5} (:85-89) and 2 <= nv <= 8.  One warp
+//       per work item, ONE LANE PER (cell,SNP) PAIR: the nv singlet + nv(nv-1)/2 doublet running
 //       products live in that lane's registers.  Inputs are software-pipelined: indices two
 //       iterations ahead (registers), read bytes and the genotype row one iteration ahead
 //       (cp.async into a conflict-free shared-memory row per lane).
+//       DICT : the genotype table is made of <= 256 distinct triples (hard calls): 8 bytes of codes per
+//              pair instead of the row, the triples in 16 conflict-free shared-memory copies (bit-identical).
+//       DELTA: the staged pscl_demux_run: SNP ids come from 16-bit gaps that are still crossing PCIe in
+//              slices when the kernel starts; a warp waits on its slice's flag and scans the gaps itself.
+//   k_demux_poly (demux_poly.inl), k_demux_cls / k_demux_ab (demux_cls.inl, demux_ab.inl): see those files.
 //   k_demux_general<EPT> : any nv / alpha grid.  One CTA per (work item, tile of 256*EPT grid
 //       entries); 8 pairs per round are folded by one warp each, staged in shared memory, and
 //       every thread updates its EPT register accumulators.
