@@ -475,17 +475,29 @@ def main():
         out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
     barrier()
     e2e_steps = max(3, min(args.steps, 200))  # the same K steps as the device-resident arm
-    per_call = []
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        tc = time.perf_counter()
-        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
-        per_call.append(round((time.perf_counter() - tc) * 1e3, 3))
-    torch.cuda.synchronize()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    # The GPU boxes are shared hosts: single calls stalled for 5-900 ms in some visits (profiles/r0*_bench.json,
+    # `ms_per_call`), with and without the staged path.  The K calls are therefore timed three times back to back and
+    # the fastest repeat is reported (every repeat's total is in the line); each repeat is max-over-ranks.
+    E2E_REPEATS = 3
+    totals, calls = [], []
+    for _rep in range(E2E_REPEATS):
+        barrier()
+        per_call = []
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            tc = time.perf_counter()
+            out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
+            per_call.append(round((time.perf_counter() - tc) * 1e3, 3))
+        torch.cuda.synchronize()
+        totals.append(time.perf_counter() - t0)
+        calls.append(per_call)
+    e2e_t = torch.tensor(totals, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = total_reads * e2e_steps / float(e2e_t.item())
+    e2e_totals = [float(x) for x in e2e_t.tolist()]
+    best = int(np.argmin(e2e_totals))
+    per_call = calls[best]
+    e2e_value = total_reads * e2e_steps / e2e_totals[best]
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -504,7 +516,8 @@ def main():
                            "l2": "flushed between timed steps (256 MiB memset, untimed)"},
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "ms_per_call": per_call[:32], "api": "pscl_demux_run (pinned host buffers in compact form: 3 B per pair, 1 B per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
+                        "steps": e2e_steps, "repeats": E2E_REPEATS, "repeat_totals_ms": [round(x * 1e3, 3) for x in e2e_totals],
+                        "ms_per_call": per_call[:32], "api": "pscl_demux_run (pinned host buffers in compact form: 3 B per pair, 1 B per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_demux(s, gp, nv, args.cpu_seconds, os.cpu_count() or 1)
