@@ -355,55 +355,81 @@ void load_plp(const LoadOptions& o, Loaded& L) {
   }
   const size_t R = rows.size() - 1;
   lap("plp.gz rows");
-  std::vector<uint32_t> order(R);
-  std::iota(order.begin(), order.end(), 0u);
-  bool sorted = true;
-  for (size_t i = 1; i < R && sorted; ++i)
-    sorted = rows[i - 1].cell < rows[i].cell || (rows[i - 1].cell == rows[i].cell && rows[i - 1].snp <= rows[i].snp);
-  if (!sorted) {  // dsc-pileup writes SNP-major; the std::map of the reference makes it cell-major, SNP ascending
-    bool snp_major = true;
-    for (size_t i = 1; i < R && snp_major; ++i) snp_major = rows[i - 1].snp <= rows[i].snp;
-    if (snp_major) {  // rows already ascend in SNP id: a stable counting sort by cell is the whole job, O(R)
-      std::vector<size_t> head((size_t)C + 1, 0);
-      for (size_t i = 0; i < R; ++i) ++head[(size_t)rows[i].cell + 1];
-      for (int32_t c = 0; c < C; ++c) head[c + 1] += head[c];
-      for (size_t i = 0; i < R; ++i) order[head[rows[i].cell]++] = (uint32_t)i;
-    } else {
+  bool sorted = true, snp_major = true;
+  for (size_t i = 1; i < R && (sorted || snp_major); ++i) {
+    sorted = sorted && (rows[i - 1].cell < rows[i].cell || (rows[i - 1].cell == rows[i].cell && rows[i - 1].snp <= rows[i].snp));
+    snp_major = snp_major && rows[i - 1].snp <= rows[i].snp;
+  }
+  L.n_cells = C; L.n_snps = V;
+  L.cell_ptr.assign((size_t)C + 1, 0);
+  L.read_allele.resize(al.size()); L.read_qual.resize(bq.size());
+  L.cell_uniq_reads.assign(C, 0);
+  if (snp_major && !sorted) {
+    // dsc-pileup's order (SNP-major; the std::map of the reference makes it cell-major, SNP ascending): every cell's rows
+    // already ascend in SNP id, so the image is two sequential passes over the rows with one write cursor per cell —
+    // no sort, no gather.  A (cell,SNP) listed on several rows is one pair: such rows are neighbours in the cell's stream.
+    std::vector<int32_t> last(C, -1);
+    std::vector<int64_t> npair(C, 0), nread(C, 0);
+    for (size_t i = 0; i < R; ++i) {
+      const Row& rw = rows[i];
+      if (rw.snp != last[rw.cell]) { ++npair[rw.cell]; last[rw.cell] = rw.snp; }
+      nread[rw.cell] += rows[i + 1].beg - rw.beg;
+    }
+    std::vector<int64_t> ppos(C), rpos(C);  // next pair / next read of each cell
+    int64_t pp = 0, rr = 0;
+    for (int32_t c = 0; c < C; ++c) {
+      ppos[c] = pp; rpos[c] = rr; L.cell_ptr[c] = pp;
+      pp += npair[c]; rr += nread[c];
+      L.cell_uniq_reads[c] = nread[c];
+    }
+    L.cell_ptr[C] = pp;
+    L.pair_snp.assign((size_t)pp, 0);
+    L.pair_read_ptr.assign((size_t)pp + 1, 0);
+    std::fill(last.begin(), last.end(), -1);
+    for (size_t i = 0; i < R; ++i) {
+      const Row& rw = rows[i];
+      const int32_t c = rw.cell;
+      if (rw.snp != last[c]) { L.pair_snp[(size_t)ppos[c]++] = rw.snp; last[c] = rw.snp; }
+      int64_t w = rpos[c];
+      for (int64_t r = rw.beg; r < rows[i + 1].beg; ++r, ++w) { L.read_allele[(size_t)w] = al[r]; L.read_qual[(size_t)w] = bq[r]; }
+      rpos[c] = w;
+      L.pair_read_ptr[(size_t)ppos[c]] = w;  // end of the pair the row belongs to (= start of the next one)
+    }
+    lap("flat image (two-pass scatter)");
+  } else {
+    std::vector<uint32_t> order(R);
+    std::iota(order.begin(), order.end(), 0u);
+    if (!sorted)
       std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         return rows[a].cell != rows[b].cell ? rows[a].cell < rows[b].cell : rows[a].snp < rows[b].snp;
       });
+    lap("cell-major order");
+    L.pair_read_ptr.assign(1, 0);
+    L.pair_snp.reserve(R); L.pair_read_ptr.reserve(R + 1);
+    int prev_c = -1, prev_s = -1;
+    size_t w = 0;  // reads written so far
+    for (size_t k = 0; k < R; ++k) {
+      const uint32_t i = order[k];
+      const Row rw = rows[i];
+      const bool same = rw.cell == prev_c && rw.snp == prev_s;  // a (cell,SNP) listed on several rows is one pair
+      const int64_t rb = rw.beg, re = rows[i + 1].beg;
+      for (int64_t r = rb; r < re; ++r, ++w) { L.read_allele[w] = al[r]; L.read_qual[w] = bq[r]; }
+      if (same) L.pair_read_ptr.back() = (int64_t)w;
+      else {
+        L.pair_snp.push_back(rw.snp);
+        L.pair_read_ptr.push_back((int64_t)w);
+        ++L.cell_ptr[(size_t)rw.cell + 1];
+      }
+      L.cell_uniq_reads[rw.cell] += re - rb;
+      prev_c = rw.cell; prev_s = rw.snp;
     }
+    for (int32_t c = 0; c < C; ++c) L.cell_ptr[c + 1] += L.cell_ptr[c];
+    lap("flat image");
   }
-  lap("cell-major order");
-  L.n_cells = C; L.n_snps = V;
-  L.cell_ptr.assign((size_t)C + 1, 0);
-  L.pair_read_ptr.assign(1, 0);
-  L.read_allele.resize(al.size()); L.read_qual.resize(bq.size());
-  L.pair_snp.reserve(R); L.pair_read_ptr.reserve(R + 1);
-  L.cell_uniq_reads.assign(C, 0);
-  int prev_c = -1, prev_s = -1;
-  size_t w = 0;  // reads written so far
-  for (size_t k = 0; k < R; ++k) {
-    const uint32_t i = order[k];
-    const Row rw = rows[i];
-    const bool same = rw.cell == prev_c && rw.snp == prev_s;  // a (cell,SNP) listed on several rows is one pair
-    const int64_t rb = rw.beg, re = rows[i + 1].beg;
-    for (int64_t r = rb; r < re; ++r, ++w) { L.read_allele[w] = al[r]; L.read_qual[w] = bq[r]; }
-    if (same) L.pair_read_ptr.back() = (int64_t)w;
-    else {
-      L.pair_snp.push_back(rw.snp);
-      L.pair_read_ptr.push_back((int64_t)w);
-      ++L.cell_ptr[(size_t)rw.cell + 1];
-    }
-    L.cell_uniq_reads[rw.cell] += re - rb;
-    prev_c = rw.cell; prev_s = rw.snp;
-  }
-  for (int32_t c = 0; c < C; ++c) L.cell_ptr[c + 1] += L.cell_ptr[c];
   // sanity check on the observed counts (:375-381): NUM.READ replaces the pass count where the rest agrees
   L.cell_totl_reads = L.cell_uniq_reads;
   for (int32_t c = 0; c < C; ++c)
     if (L.cell_uniq_reads[c] == tmp_uniq[c] && tmp_nsnp[c] == L.cell_ptr[c + 1] - L.cell_ptr[c]) L.cell_totl_reads[c] = tmp_totl[c];
-  lap("flat image");
 }
 
 }  // namespace pscl_host

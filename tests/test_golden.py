@@ -261,9 +261,26 @@ def test_cpp_plp_parser_line_endings(tmp_path, host_exe):
         lines = t.split("\n")
         return "\n".join(lines[:40] + [""] + lines[40:])
 
+    def cell_major(t):  # already in the image's order: no reordering at all
+        lines = t.rstrip("\n").split("\n")
+        body = sorted(lines[1:], key=lambda r: (int(r.split()[0]), int(r.split()[1])))
+        return "\n".join(lines[:1] + body) + "\n"
+    def reversed_rows(t):  # neither order: the generic stable sort
+        lines = t.rstrip("\n").split("\n")
+        return "\n".join(lines[:1] + lines[1:][::-1]) + "\n"
+
     base = run(same)
-    for m in (no_final_newline, crlf, padded):
+    for m in (no_final_newline, crlf, padded, cell_major, reversed_rows):
         got = run(m)
         assert got["pileup_fnv1a"] == base["pileup_fnv1a"] and got["pairs"] == base["pairs"], m.__name__
     short = run(cut_at_empty_line)
     assert 0 < short["reads"] < base["reads"]
+    # a (cell, SNP) listed on two rows is one pair with the reads of both (std::map semantics); the scatter path (SNP-major
+    # file) and the sorted path (cell-major file) agree on it
+    def dup_snp_major(t):
+        lines = t.rstrip("\n").split("\n")
+        return "\n".join(lines[:8] + [lines[7]] + lines[8:]) + "\n"
+    def dup_cell_major(t): return cell_major(dup_snp_major(t))
+    d1, d2 = run(dup_snp_major), run(dup_cell_major)
+    assert d1["pairs"] == base["pairs"] and d1["reads"] > base["reads"]
+    assert d1["pileup_fnv1a"] == d2["pileup_fnv1a"] != base["pileup_fnv1a"]
