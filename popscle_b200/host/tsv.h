@@ -101,14 +101,18 @@ inline int split_ws(std::string& line, std::vector<char*>& f) {
 }
 
 inline void split_char(const std::string& s, char d, std::vector<std::string>& out) {
-  out.clear();
-  size_t b = 0;
+  // the strings of `out` are reused (assign keeps their capacity): no allocation per field once warmed up
+  size_t n = 0, b = 0;
   for (;;) {
-    size_t e = s.find(d, b);
-    out.emplace_back(s, b, e == std::string::npos ? std::string::npos : e - b);
+    const size_t e = s.find(d, b);
+    const size_t len = e == std::string::npos ? std::string::npos : e - b;
+    if (n < out.size()) out[n].assign(s, b, len);
+    else out.emplace_back(s, b, len);
+    ++n;
     if (e == std::string::npos) break;
     b = e + 1;
   }
+  out.resize(n);
 }
 
 // tsv_reader semantics: a row, or false at EOF *or at the first empty line* (tsv_reader.cpp:37-41)
