@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSCL_ABI_VERSION 4
+#define PSCL_ABI_VERSION 5
 
 typedef enum pscl_status {
   PSCL_OK = 0,
@@ -146,6 +146,11 @@ typedef struct pscl_fmx_opts {
   double frac_init_clust;     /* default 1.0 (:28)                                              */
   double singlet_score_thres; /* default -1e300 (:26)                                           */
   int32_t mode_old;           /* 0 = freemux2 (popscle freemuxlet), 1 = freemuxlet-old EM rules */
+  /* ABI 5: --randomize-singlet-score (cmd_cram_freemux2.cpp:164-181): the singlet scores are shuffled
+   * with libc rand() (Fisher-Yates, j = i + rand() % (n - i)) after srand(seed ? seed : time(0)),
+   * before the droplets are sorted for the greedy seeding.  0 = off.                             */
+  int32_t randomize_singlet_score;
+  int32_t seed;               /* --seed                                                         */
 } pscl_fmx_opts;
 
 typedef struct pscl_fmx_cell {

@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -411,6 +412,13 @@ int orc_fmx_run(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* ini
   }
   if (pair_gl_out) memcpy(pair_gl_out, pair_gl, sizeof(double) * 9 * P);
 
+  if (o->randomize_singlet_score) { /* :164-181: srand(seed or time), Fisher-Yates with libc rand() */
+    srand(o->seed == 0 ? (unsigned)time(NULL) : (unsigned)o->seed);
+    for (int32_t i = 0; i < C - 1; ++i) {
+      int32_t j = i + rand() % (C - i);
+      if (i < j) { double tmp = scores[j]; scores[j] = scores[i]; scores[i] = tmp; }
+    }
+  }
   for (int32_t c = 0; c < C; ++c) { clusts[c] = -1; types[c] = -1; order[c] = c; }
   if (init_clust) { /* :198-216 */
     for (int32_t c = 0; c < C; ++c)

@@ -51,6 +51,7 @@ typedef struct orc_fmx_opts {
   int32_t max_iter, early_stop;
   double frac_init_clust, singlet_score_thres;
   int32_t mode_old;
+  int32_t randomize_singlet_score, seed; /* cmd_cram_freemux2.cpp:164-181 */
 } orc_fmx_opts;
 
 /* layout-identical to pscl_fmx_cell */

@@ -58,7 +58,8 @@ class CDemuxOpts(C.Structure):
 class CFmxOpts(C.Structure):
     _fields_ = [("n_clusters", C.c_int32), ("doublet_prior", C.c_double), ("geno_error", C.c_double),
                 ("max_iter", C.c_int32), ("early_stop", C.c_int32), ("frac_init_clust", C.c_double),
-                ("singlet_score_thres", C.c_double), ("mode_old", C.c_int32)]
+                ("singlet_score_thres", C.c_double), ("mode_old", C.c_int32),
+                ("randomize_singlet_score", C.c_int32), ("seed", C.c_int32)]
 
 
 class CFmxResult(C.Structure):
@@ -409,9 +410,9 @@ class Context:
     # ---- freemuxlet ----
     @staticmethod
     def fmx_opts(n_clusters: int, doublet_prior=0.5, geno_error=0.1, max_iter=10, early_stop=True,
-                 frac_init_clust=1.0, singlet_score_thres=-1e300, mode_old=False) -> CFmxOpts:
+                 frac_init_clust=1.0, singlet_score_thres=-1e300, mode_old=False, randomize_singlet_score=False, seed=0) -> CFmxOpts:
         return CFmxOpts(n_clusters, doublet_prior, geno_error, max_iter, int(early_stop), frac_init_clust,
-                        singlet_score_thres, int(mode_old))
+                        singlet_score_thres, int(mode_old), int(randomize_singlet_score), int(seed))
 
     def fmx_run(self, plp: Pileup, opts: CFmxOpts, init_clust: np.ndarray | None = None, want_clusters=False,
                 compact: bool = False):

@@ -131,8 +131,6 @@ def _freemux(argv, old, engine=None):
     o = _parse(argv, FREEMUXLET_OLD_SPEC if old else FREEMUXLET_SPEC)
     if not o["plp"] or not o["out"] or o["nsample"] == 0:
         raise UsageError("Missing required option(s) : --plp, --out, --nsample")
-    if not old and o["randomize-singlet-score"]:
-        raise UsageError("--randomize-singlet-score consumes the libc rand() stream (cmd_cram_freemux2.cpp:171-181); not supported")
     nS = o["nsample"]
     if old:
         # cmd_cram_freemuxlet.cpp:83 never copies the filter flags into the loader: library defaults apply
@@ -159,7 +157,8 @@ def _freemux(argv, old, engine=None):
     eng = engine or _default_engine()
     try:
         opts = eng.fmx_opts(nS, doublet_prior=o["doublet-prior"], geno_error=o["geno-error"], max_iter=10, early_stop=True,
-                            frac_init_clust=o["frac-init-clust"], singlet_score_thres=-1e300, mode_old=old)
+                            frac_init_clust=o["frac-init-clust"], singlet_score_thres=-1e300, mode_old=old,
+                            randomize_singlet_score=bool(o.get("randomize-singlet-score", False)), seed=int(o.get("seed", 0) or 0))
         cells, res, gl, cnt = eng.fmx_run(L.plp, opts, init, want_clusters=True)
     finally:
         if own:

@@ -905,6 +905,16 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
     std::vector<int32_t> h_order(s->C);
     e = cudaMemcpyAsync(h_score.data(), score, sizeof(double) * s->C, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && s->o.randomize_singlet_score) {
+      // --randomize-singlet-score (cmd_cram_freemux2.cpp:164-181): Fisher-Yates on the scores with the libc rand()
+      // stream the reference uses; the kernel's threshold test (:226) must see the shuffled scores too
+      srand(s->o.seed == 0 ? (unsigned)time(nullptr) : (unsigned)s->o.seed);
+      for (int32_t i = 0; i < s->C - 1; ++i) {
+        const int32_t j = i + rand() % (s->C - i);
+        if (i < j) std::swap(h_score[i], h_score[j]);
+      }
+      e = cudaMemcpyAsync(score, h_score.data(), sizeof(double) * s->C, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) {
       fmx_sort_order(h_score, h_order);
       e = cudaMemcpyAsync(s->order, h_order.data(), sizeof(int32_t) * s->C, cudaMemcpyHostToDevice, ctx->stream);

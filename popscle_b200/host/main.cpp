@@ -170,7 +170,6 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   else { p.add("min-umi", &minUMI); p.add("randomize-singlet-score", &randomize); p.add("seed", &seed); }
   p.read(argc, argv);
   if (plp.empty() || out.empty() || nSamples == 0) throw host_error("Missing required option(s) : --plp, --out, --nsample");
-  if (randomize) throw host_error("--randomize-singlet-score consumes the libc rand() stream (cmd_cram_freemux2.cpp:171-181); not supported");
   if (auxFiles) throw host_error("--aux-files (clust0 / ldist debug outputs) is not supported");
   LoadOptions lo;
   lo.plp_prefix = plp;
@@ -211,7 +210,7 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   if (dry) return dry_run(L);
   Ctx ctx;
   pscl_pileup view = L.view();
-  pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0};
+  pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0, randomize ? 1 : 0, seed};
   std::vector<pscl_fmx_cell> cells((size_t)L.n_cells);
   std::vector<double> gl((size_t)L.n_snps * nSamples * 9);
   std::vector<int32_t> cnt((size_t)L.n_snps * nSamples * 3);
