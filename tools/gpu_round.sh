@@ -13,4 +13,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KRE} -s 3 -c 1 -f -o gpurun_out/${TAG}_prof \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full exit $?"
+# the other bench lines of a full round (skip with FAST=1)
+if [ -z "$FAST" ]; then
+  timeout 120 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/${TAG}_smoke.log
+  timeout 300 python bench.py --workload freemux --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_freemux.json 2> gpurun_out/${TAG}_bench_freemux.err; echo "freemux exit $?"
+  timeout 300 python bench.py --workload demux64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_demux64.json 2> gpurun_out/${TAG}_bench_demux64.err; echo "demux64 exit $?"
+  timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_reference_arm.err; echo "reference arm exit $?"
+fi
 ls -la gpurun_out
