@@ -42,9 +42,9 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=0, help="override the cell count (debug)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "lane", "dict", "cls", "ab", "general"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "lane", "dict", "general", "poly"],
                     help="demuxlet accumulation kernel: auto (the library's choice: k_demux_default on dictionary-coded genotypes "
-                         "for this workload), lane (k_demux_default on gathered genotype rows), k_demux_cls, k_demux_ab, k_demux_general")
+                         "for this workload), lane (k_demux_default on gathered genotype rows), k_demux_general, k_demux_poly")
     return ap.parse_args()
 
 
@@ -402,7 +402,7 @@ def main():
     plp, nv = s.plp, cfg["nv"]
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
-    ctx.demux_select_kernel({"auto": 0, "lane": 1, "general": 2, "cls": 3, "ab": 5, "dict": 6}[args.kernel])
+    ctx.demux_select_kernel({"auto": 0, "lane": 1, "general": 2, "poly": 4, "dict": 6}[args.kernel])
     kname = None  # named after the first scoring pass, from what the library launched
 
     # ---- device-resident arm ("value") ----------------------------------------------------------

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSCL_ABI_VERSION 5
+#define PSCL_ABI_VERSION 6
 
 typedef enum pscl_status {
   PSCL_OK = 0,
@@ -268,6 +268,55 @@ int pscl_fmx_classify(pscl_ctx* ctx, const double* llk_dev, int32_t* clust_dev,
 int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt);
 /* Device time (ms) of the last pscl_fmx_estep or pscl_fmx_mstep (CUDA events on pscl_stream). */
 int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float* ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Several GPUs in one process (ABI 6).  The reference is single-threaded and its only
+ * parallelism advice is "--group-list ... for parallelized run" (cmd_cram_demuxlet.cpp:75): split the
+ * barcodes by hand and run several processes.  pscl_multi does that split inside the library.
+ *   demuxlet   barcodes sharded into contiguous ranges balanced by pair count, genotype table
+ *              replicated, no collective (cells are independent: cmd_cram_demuxlet.cpp:636-1013);
+ *   freemuxlet SNPs sharded into ranges balanced by pair count; stage 1 + greedy seeding
+ *              (cmd_cram_freemux2.cpp:117-261) on the first GPU, then per EM iteration (:373-605) one
+ *              all-reduce of the C x npairs partial LLKs over NVLink peer memory (the library's own
+ *              kernel: fixed rank order, the same bits on every GPU), redundant classification and
+ *              an SNP-local M-step.
+ * One host thread per GPU, bound to the CPUs next to it.  The results equal the single-GPU ones
+ * bit for bit for demuxlet, and up to the summation order of the SNP ranges for freemuxlet.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pscl_multi pscl_multi;
+#define PSCL_MULTI_MAX_GPUS 16
+typedef struct pscl_multi_timing {   /* wall-clock of the last pscl_multi_*_run, per GPU (host clocks) */
+  int32_t n_gpus, iters;             /* EM iterations executed (freemuxlet)                              */
+  double total_ms;                   /* whole call                                                        */
+  double seed_ms;                    /* freemuxlet: whole-pileup stage 1 + greedy seeding on the first GPU */
+  double allreduce_ms;               /* freemuxlet: mean per iteration, measured only with
+                                        PSCL_MULTI_TIME_ALLREDUCE=1 (adds two stream synchronisations)  */
+  int64_t allreduce_bytes;           /* C * npairs * 8                                                    */
+  double upload_ms[PSCL_MULTI_MAX_GPUS];   /* H2D of the shard (freemuxlet: whole pileup + SNP filter)   */
+  double setup_ms[PSCL_MULTI_MAX_GPUS];    /* freemuxlet: SNP-major view, stage 1, initial M-step         */
+  double compute_ms[PSCL_MULTI_MAX_GPUS];  /* demuxlet: score + fetch; freemuxlet: the EM loop + fetch    */
+  double kernel_ms[PSCL_MULTI_MAX_GPUS];   /* demuxlet: device time of the scoring kernels (CUDA events)  */
+  int64_t units[PSCL_MULTI_MAX_GPUS];      /* (cell, SNP) pairs this GPU owned                            */
+} pscl_multi_timing;
+
+/* gpu_ids[n_gpu] = CUDA ordinals (NULL = 0..n_gpu-1; n_gpu <= 0 = every visible GPU).  A device may be
+ * listed more than once (tests). */
+int pscl_multi_create(const int* gpu_ids, int n_gpu, pscl_multi** out, char* err, size_t errlen);
+void pscl_multi_destroy(pscl_multi* m);
+const char* pscl_multi_last_error(const pscl_multi* m);
+int pscl_multi_size(const pscl_multi* m);
+pscl_ctx* pscl_multi_ctx(pscl_multi* m, int i);  /* the per-GPU context (kernel selection, timing) */
+/* Same arguments and results as pscl_demux_run / pscl_fmx_run. */
+int pscl_multi_demux_run(pscl_multi* m, const pscl_pileup* host, const pscl_geno* geno,
+                         const pscl_demux_opts* opts, pscl_demux_cell* out, double* llk_grid);
+int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const pscl_fmx_opts* opts,
+                       const int32_t* init_clust, pscl_fmx_cell* out, double* clust_gl,
+                       int32_t* clust_cnt, pscl_fmx_result* res);
+int pscl_multi_last_timing(const pscl_multi* m, pscl_multi_timing* out);
+/* Runs the calling thread on the CPUs of the NUMA node GPU `device` hangs off
+ * (/sys/bus/pci/devices/<bus id>/local_cpulist), so that its pinned buffers and staging copies are
+ * node-local.  Multi-process hosts (one rank per GPU) call it before allocating. */
+int pscl_bind_thread_to_device(int device);
 
 /* ---- knobs used by tests and the benchmark harness ---- */
 /* Launch on a caller-owned stream (e.g. torch's current stream) instead of the context's own. */

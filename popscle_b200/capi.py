@@ -62,6 +62,13 @@ class CFmxOpts(C.Structure):
                 ("randomize_singlet_score", C.c_int32), ("seed", C.c_int32)]
 
 
+class CMultiTiming(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("iters", C.c_int32), ("total_ms", C.c_double), ("seed_ms", C.c_double),
+                ("allreduce_ms", C.c_double), ("allreduce_bytes", C.c_int64),
+                ("upload_ms", C.c_double * 16), ("setup_ms", C.c_double * 16), ("compute_ms", C.c_double * 16),
+                ("kernel_ms", C.c_double * 16), ("units", C.c_int64 * 16)]
+
+
 class CFmxResult(C.Structure):
     _fields_ = [("n_iter", C.c_int32), ("n_changed", C.c_int32), ("n_singlet", C.c_int32),
                 ("n_doublet", C.c_int32), ("n_ambiguous", C.c_int32)]
@@ -239,6 +246,15 @@ def load_library() -> C.CDLL:
         "pscl_fmx_classify": (C.c_int, [vp, vp, vp, C.POINTER(CFmxResult)]),
         "pscl_fmx_fetch": (C.c_int, [vp, vp, vp, vp]),
         "pscl_fmx_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "pscl_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp), C.c_char_p, C.c_size_t]),
+        "pscl_multi_destroy": (None, [vp]),
+        "pscl_multi_last_error": (C.c_char_p, [vp]),
+        "pscl_multi_size": (C.c_int, [vp]),
+        "pscl_multi_ctx": (vp, [vp, C.c_int]),
+        "pscl_multi_demux_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CGeno), C.POINTER(CDemuxOpts), vp, vp]),
+        "pscl_multi_fmx_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult)]),
+        "pscl_multi_last_timing": (C.c_int, [vp, C.POINTER(CMultiTiming)]),
+        "pscl_bind_thread_to_device": (C.c_int, [C.c_int]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError = the library does not export what the header declares
@@ -255,6 +271,8 @@ EXPORTED_SYMBOLS = [
     "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_demux_last_kernel", "pscl_fmx_run", "pscl_fmx_init",
     "pscl_fmx_stage1", "pscl_fmx_seed", "pscl_fmx_mstep", "pscl_fmx_estep", "pscl_fmx_classify",
     "pscl_fmx_fetch", "pscl_fmx_last_kernel_ms",
+    "pscl_multi_create", "pscl_multi_destroy", "pscl_multi_last_error", "pscl_multi_size", "pscl_multi_ctx",
+    "pscl_multi_demux_run", "pscl_multi_fmx_run", "pscl_multi_last_timing", "pscl_bind_thread_to_device",
 ]
 
 
@@ -467,6 +485,95 @@ class Context:
         a = C.c_float()
         self._chk(self.lib.pscl_fmx_last_kernel_ms(self.h, C.byref(a)))
         return a.value
+
+
+class Multi:
+    """pscl_multi: several GPUs driven from this process (barcode-sharded demuxlet, SNP-sharded freemuxlet)."""
+    accepts_compact = True
+
+    def __init__(self, gpu_ids=None, n_gpu: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        if gpu_ids is not None:
+            ids = (C.c_int * len(gpu_ids))(*gpu_ids)
+            rc = self.lib.pscl_multi_create(ids, len(gpu_ids), C.byref(h), err, len(err))
+        else:
+            rc = self.lib.pscl_multi_create(None, n_gpu, C.byref(h), err, len(err))
+        if rc != PSCL_OK:
+            raise PsclError(rc, err.value.decode())
+        self.h = h
+
+    def _chk(self, rc: int):
+        if rc != PSCL_OK:
+            raise PsclError(rc, self.lib.pscl_multi_last_error(self.h).decode())
+
+    @property
+    def size(self) -> int:
+        return int(self.lib.pscl_multi_size(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pscl_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def select_demux_kernel(self, which: int):
+        for i in range(self.size):
+            rc = self.lib.pscl_demux_select_kernel(C.c_void_p(self.lib.pscl_multi_ctx(self.h, i)), int(which))
+            if rc != PSCL_OK:
+                raise PsclError(rc, "pscl_demux_select_kernel")
+
+    def timing(self) -> dict:
+        t = CMultiTiming()
+        self._chk(self.lib.pscl_multi_last_timing(self.h, C.byref(t)))
+        n = t.n_gpus
+        return {"n_gpus": n, "iters": t.iters, "total_ms": t.total_ms, "seed_ms": t.seed_ms, "allreduce_ms": t.allreduce_ms,
+                "allreduce_bytes": t.allreduce_bytes, "upload_ms": list(t.upload_ms)[:n], "setup_ms": list(t.setup_ms)[:n],
+                "compute_ms": list(t.compute_ms)[:n], "kernel_ms": list(t.kernel_ms)[:n], "units": list(t.units)[:n]}
+
+    def demux_run(self, plp: Pileup, gp, has_gp, alphas, doublet_prior: float = 0.5, want_grid: bool = False, compact=False):
+        al = np.ascontiguousarray(alphas, dtype=np.float64)
+        cs = plp.c_struct(compact=compact)
+        g, keep, _, nv = Context._geno(gp, has_gp)
+        o = CDemuxOpts(len(al), al.ctypes.data, doublet_prior)
+        out = np.zeros(plp.n_cells, dtype=DEMUX_CELL_DTYPE)
+        grid = np.empty((plp.n_cells, nv, nv, len(al))) if want_grid else None
+        self._chk(self.lib.pscl_multi_demux_run(self.h, C.byref(cs), C.byref(g), C.byref(o), out.ctypes.data,
+                                                grid.ctypes.data if want_grid else None))
+        return (out, grid) if want_grid else out
+
+    fmx_opts = staticmethod(Context.fmx_opts)
+
+    def fmx_run(self, plp: Pileup, opts: CFmxOpts, init_clust=None, want_clusters=False, compact=False):
+        cs = plp.c_struct(compact=compact)
+        out = np.zeros(plp.n_cells, dtype=FMX_CELL_DTYPE)
+        res = CFmxResult()
+        ic = np.ascontiguousarray(init_clust, dtype=np.int32) if init_clust is not None else None
+        gl = cnt = None
+        if want_clusters:
+            gl = np.empty((plp.n_snps, opts.n_clusters, 9), dtype=np.float64)
+            cnt = np.empty((plp.n_snps, opts.n_clusters, 3), dtype=np.int32)
+        self._chk(self.lib.pscl_multi_fmx_run(self.h, C.byref(cs), C.byref(opts), ic.ctypes.data if ic is not None else None,
+                                              out.ctypes.data, gl.ctypes.data if gl is not None else None,
+                                              cnt.ctypes.data if cnt is not None else None, C.byref(res)))
+        return out, res, gl, cnt
+
+
+def bind_to_device(device: int) -> bool:
+    """Runs the calling thread on the CPUs of the GPU's NUMA node (pinned buffers allocated afterwards are node-local)."""
+    return load_library().pscl_bind_thread_to_device(int(device)) == PSCL_OK
 
 
 class DevicePileup:

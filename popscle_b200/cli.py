@@ -71,6 +71,7 @@ DEMUXLET_SPEC = {
     "sam-verbose": ("int", 1000000), "vcf-verbose": ("int", 10000),
     "cap-BQ": ("int", 20), "min-BQ": ("int", 13), "min-MQ": ("int", 20), "min-TD": ("int", 0), "excl-flag": ("int", 3844),
     "group-list": ("str", ""), "min-total": ("int", 0), "min-umi": ("int", 0), "min-snp": ("int", 0),
+    "gpus": ("int", 1),  # extension: GPUs of this box to shard the barcodes over (0 = all)
 }
 
 FREEMUX_COMMON = {
@@ -79,6 +80,7 @@ FREEMUX_COMMON = {
     "bf-thres": ("float", 5.41), "frac-init-clust": ("float", 1.0), "iter-init": ("int", 10),
     "keep-init-missing": ("flag", False), "min-BQ": ("int", 13), "group-list": ("str", ""),
     "min-total": ("int", 0), "min-snp": ("int", 0),
+    "gpus": ("int", 1),  # extension: GPUs of this box to shard the SNPs over (0 = all)
 }
 FREEMUXLET_SPEC = dict(FREEMUX_COMMON, **{"geno-error": ("float", 0.1), "cap-BQ": ("int", 20), "min-umi": ("int", 0),
                                          "randomize-singlet-score": ("flag", False), "seed": ("int", 0)})
@@ -89,9 +91,17 @@ def _read_list(path):
     return [r[0] for r in plpio._rows(path)]
 
 
-def _default_engine():
-    from .capi import Context
-    return Context(0)  # raises without libpopscle_b200.so or an sm_100 GPU: no CPU fallback
+def _default_engine(gpus=1):
+    """One GPU (Context), or `--gpus N` / PSCL_GPU_IDS=0,1,... GPUs of this box (Multi: pscl_multi_* of the C ABI).
+    Raises without libpopscle_b200.so or an sm_100 GPU: no CPU fallback."""
+    import os
+    from .capi import Context, Multi
+    ids = [int(x) for x in os.environ.get("PSCL_GPU_IDS", "").split(",") if x != ""]
+    if len(ids) > 1:
+        return Multi(gpu_ids=ids)
+    if not ids and gpus != 1:
+        return Multi(n_gpu=gpus)
+    return Context(ids[0] if ids else 0)
 
 
 def demuxlet(argv, engine=None):
@@ -110,7 +120,7 @@ def demuxlet(argv, engine=None):
                        min_mac=o["min-mac"], min_callrate=o["min-callrate"])
     _notice("Starting to identify best matching individual IDs")
     own = engine is None
-    eng = engine or _default_engine()
+    eng = engine or _default_engine(o["gpus"])
     try:
         # the compact boundary, as the C++ host uses it: delta-coded pair arrays (ABI 3) when they fit, raw posteriors or
         # hard calls + error rates (ABI 4) mixed on the device
@@ -154,7 +164,7 @@ def _freemux(argv, old, engine=None):
                 m[r[0]] = k
         init = np.array([m.get(b, -1) for b in L.barcodes], dtype=np.int32)
     own = engine is None
-    eng = engine or _default_engine()
+    eng = engine or _default_engine(o["gpus"])
     try:
         opts = eng.fmx_opts(nS, doublet_prior=o["doublet-prior"], geno_error=o["geno-error"], max_iter=10, early_stop=True,
                             frac_init_clust=o["frac-init-clust"], singlet_score_thres=-1e300, mode_old=old,

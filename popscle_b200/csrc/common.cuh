@@ -39,8 +39,8 @@ struct pscl_plp {
   int64_t* item_pend = nullptr;    // [n_items]
   int32_t* item_order = nullptr;   // [n_items]
   int32_t* cell_item_ptr = nullptr;  // [C+1]
-  std::vector<int32_t> h_cell_item_ptr;
-  std::vector<int64_t> h_cell_ptr;
+  std::vector<int32_t> h_cell_item_ptr, h_item_cell, h_item_order;
+  std::vector<int64_t> h_cell_ptr, h_item_pbeg, h_item_pend;
   // SNP-major view for the freemuxlet M-step (built lazily)
   int64_t* snp_ptr = nullptr;    // [V+1]
   uint32_t* snp_pair = nullptr;  // [P] pair ids, ascending cell id inside one SNP
@@ -78,6 +78,7 @@ struct pscl_ctx {
   cudaEvent_t stage_go = nullptr;
   int* stage_flags = nullptr;          // device [PSCL_MAX_STAGES]: slice k has landed (written by the copy queue)
   int* h_one = nullptr;                // pinned host word holding 1, the source of those flag writes
+  long long stage_spin_ticks = 1ll << 32;  // how long a warp of the staged kernel waits for a slice (PSCL_STAGE_TIMEOUT_MS, default 2000)
   double* fold_tab = nullptr;   // [3][64][6] per-read factors of the default alpha grid (demux.inl)
   double* phred_err = nullptr;  // [256] device copy of PhredHelper's phred2Err (staged to smem by kernels)
   // demuxlet state
@@ -179,3 +180,27 @@ __device__ __forceinline__ void pscl_renorm(double& m, int& e) {
 __device__ __forceinline__ double pscl_prod_log(double m, int e) {
   return log(m) + (double)e * 0.693147180559945309417232121458;
 }
+
+// Warp transpose-reduce of N (power of two) running products per lane: after the call lane L holds in
+// m[0], x[0] the product over all 32 lanes of element (L * N) / 32.  Recursive halving: at every step a
+// lane keeps one half of its elements, hands the other half to its partner and multiplies what it gets.
+template <int N>
+__device__ __forceinline__ void pscl_transpose_prod(double (&m)[N], int (&x)[N], const int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = N / 2; n >= 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double sm = up ? m[i] : m[i + n], km = up ? m[i + n] : m[i];
+      const int sx = up ? x[i] : x[i + n], kx = up ? x[i + n] : x[i];
+      m[i] = km * __shfl_xor_sync(0xffffffffu, sm, o);
+      x[i] = kx + __shfl_xor_sync(0xffffffffu, sx, o);
+    }
+  }
+  for (; o >= 1; o >>= 1) {  // fewer elements than lanes: finish with a plain butterfly
+    m[0] *= __shfl_xor_sync(0xffffffffu, m[0], o);
+    x[0] += __shfl_xor_sync(0xffffffffu, x[0], o);
+  }
+}
+

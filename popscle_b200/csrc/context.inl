@@ -26,6 +26,11 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
   pscl_ctx* c = new pscl_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  {  // bound of the staged kernel's wait for a slice, in SM clock ticks (prop.clockRate is in kHz = ticks per ms)
+    const char* tv = getenv("PSCL_STAGE_TIMEOUT_MS");
+    const long long ms = tv ? atoll(tv) : 2000;
+    c->stage_spin_ticks = (ms > 0 ? ms : 1) * (long long)(prop.clockRate > 0 ? prop.clockRate : 1900000);
+  }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete c;
     return fail(PSCL_ECUDA, cudaGetErrorString(e));
@@ -220,13 +225,28 @@ struct PsclU8ToU32 {
 };
 
 // int64 read offsets -> uint32 (device images hold < 2^32 reads)
-__global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
+__global__ void k_narrow_ptr(const int64_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int64_t base) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint32_t)in[i];
+  if (i < n) out[i] = (uint32_t)(in[i] - base);
+}
+__global__ void k_rebase_u32(uint32_t* __restrict__ v, int64_t n, uint32_t base) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] -= base;
+}
+
+// wide forms: SNP ids inside [0, V), read offsets non-decreasing and <= N (the delta forms are checked while decoding)
+__global__ void k_check_pairs(const int32_t* __restrict__ pair_snp, const uint32_t* __restrict__ pair_rd, int64_t P, int32_t V, int64_t N,
+                              int check_snp, int* bad) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  if (check_snp && (unsigned)pair_snp[p] >= (unsigned)V) atomicExch(bad, 2);
+  const uint32_t a = pair_rd[p], b = pair_rd[p + 1];
+  if (b < a || (int64_t)b > N) atomicExch(bad, 5);
 }
 
 static const char* pscl_bad_pileup_msg(int bad) {
-  return bad == 2 ? "pair_snp_delta16 decodes to a SNP id outside [0, n_snps)"
+  return bad == 2 ? "pair_snp / pair_snp_delta16 holds a SNP id outside [0, n_snps)"
+       : bad == 5 ? "pair_read_ptr is not non-decreasing inside [0, n_reads]"
        : bad == 3 ? "pair_nreads8 does not sum to n_reads"
                   : "read_allele must be 0/1/2 and read_qual <= 63 (dsc-pileup writes phred <= 40, cmd_cram_dsc_pileup.cpp:19-20)";
 }
@@ -251,7 +271,61 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
 // Host image -> device image.  `stages` > 1 (pscl_demux_run only, ABI-3 delta arrays) leaves the SNP gaps out of the
 // synchronous part: they cross PCIe on ctx->copy_stream in `stages` slices of whole cells, one event per slice, while
 // the caller scores the slices that have arrived (pscl_demux_run); the decode kernel then runs per slice.
-static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages) {
+// Work items of a device image from its (host copy of the) cell_ptr: chunks of <= PSCL_ITEM_PAIRS pairs of one cell, listed
+// by descending size (counting sort; a staged image is ordered slice by slice, so that the kernel's first items are the
+// ones whose gaps land first).  Enqueues the five item arrays on ctx->stream; the host vectors live in *p.
+static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cell_ptr) {
+  const int32_t C = p->C;
+  const int64_t P = p->P;
+  p->h_cell_ptr.assign(cell_ptr, cell_ptr + C + 1);
+  std::vector<int32_t>& item_cell = p->h_item_cell;
+  std::vector<int64_t>&pbeg = p->h_item_pbeg, &pend = p->h_item_pend;
+  item_cell.clear(); pbeg.clear(); pend.clear();
+  item_cell.reserve((size_t)C + (size_t)(P / PSCL_ITEM_PAIRS) + 1);
+  pbeg.reserve(item_cell.capacity()); pend.reserve(item_cell.capacity());
+  p->h_cell_item_ptr.resize(C + 1);
+  for (int32_t c = 0; c < C; ++c) {
+    p->h_cell_item_ptr[c] = (int32_t)item_cell.size();
+    int64_t b = cell_ptr[c], e2 = cell_ptr[c + 1], n = e2 - b;
+    int64_t nch = (n + PSCL_ITEM_PAIRS - 1) / PSCL_ITEM_PAIRS;
+    for (int64_t i = 0; i < nch; ++i) {  // equal split, multiples of 32 pairs
+      int64_t s0 = b + ((n * i / nch) & ~(int64_t)31), t = (i + 1 == nch) ? e2 : b + ((n * (i + 1) / nch) & ~(int64_t)31);
+      item_cell.push_back(c); pbeg.push_back(s0); pend.push_back(t);
+    }
+  }
+  p->h_cell_item_ptr[C] = (int32_t)item_cell.size();
+  p->n_items = (int32_t)item_cell.size();
+  std::vector<int32_t>& order = p->h_item_order;
+  order.resize(p->n_items);
+  {
+    const int NB = PSCL_ITEM_PAIRS + 64;
+    std::vector<int32_t> head(NB + 1);
+    const int nseg = p->n_stages > 1 ? p->n_stages : 1;
+    for (int k = 0; k < nseg; ++k) {
+      const int32_t ib = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k]] : 0;
+      const int32_t ie = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k + 1]] : p->n_items;
+      std::fill(head.begin(), head.end(), 0);
+      for (int32_t i = ib; i < ie; ++i) head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1) + 1]++;
+      for (int b2 = 0; b2 < NB; ++b2) head[b2 + 1] += head[b2];
+      for (int32_t i = ib; i < ie; ++i) order[ib + head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1)]++] = i;
+    }
+  }
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** d, const void* src, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16);
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  up((void**)&p->item_cell, item_cell.data(), sizeof(int32_t) * p->n_items);
+  up((void**)&p->item_pbeg, pbeg.data(), sizeof(int64_t) * p->n_items);
+  up((void**)&p->item_pend, pend.data(), sizeof(int64_t) * p->n_items);
+  up((void**)&p->item_order, order.data(), sizeof(int32_t) * p->n_items);
+  up((void**)&p->cell_item_ptr, p->h_cell_item_ptr.data(), sizeof(int32_t) * (C + 1));
+  return e;
+}
+
+// read_base: the host's read offsets (pair_read_ptr / pair_read_ptr32) and read arrays belong to a longer pileup and
+// this image starts at base-call `read_base` of it (barcode shards of pscl_multi_demux_run point into the caller's arrays).
+static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages, int64_t read_base = 0) {
   if (!h || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_plp_upload: NULL argument");
   *out = nullptr;
   static const bool trace = getenv("PSCL_TRACE") != nullptr;  // wall-clock of the upload's phases on stderr
@@ -272,7 +346,8 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr must run from 0 to n_pairs");
   for (int32_t c = 0; c < C; ++c)
     if (h->cell_ptr[c + 1] < h->cell_ptr[c]) return pscl_fail(ctx, PSCL_EINVAL, "cell_ptr not monotone at cell %d", c);
-  if (P > 0 && !cnt8 && (ptr32 ? (h->pair_read_ptr32[0] != 0 || (int64_t)h->pair_read_ptr32[P] != N) : (h->pair_read_ptr[0] != 0 || h->pair_read_ptr[P] != N)))
+  if (P > 0 && !cnt8 && (ptr32 ? ((int64_t)h->pair_read_ptr32[0] != read_base || (int64_t)h->pair_read_ptr32[P] != read_base + N)
+                               : (h->pair_read_ptr[0] != read_base || h->pair_read_ptr[P] != read_base + N)))
     return pscl_fail(ctx, PSCL_EINVAL, "pair_read_ptr must run from 0 to n_reads");
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!dsnp || P == 0 || C < 2 || !ctx->copy_stream || !ctx->h_one) stages = 1;
@@ -331,45 +406,8 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   const auto tr1 = tnow(false);
 
   // ---- 2. work items (host; overlaps the copies) -------------------------------------------------------
-  p->h_cell_ptr.assign(h->cell_ptr, h->cell_ptr + C + 1);
-  std::vector<int32_t> item_cell;
-  std::vector<int64_t> pbeg, pend;
-  item_cell.reserve((size_t)C + (size_t)(P / PSCL_ITEM_PAIRS) + 1);
-  pbeg.reserve(item_cell.capacity()); pend.reserve(item_cell.capacity());
-  p->h_cell_item_ptr.resize(C + 1);
-  for (int32_t c = 0; c < C; ++c) {
-    p->h_cell_item_ptr[c] = (int32_t)item_cell.size();
-    int64_t b = h->cell_ptr[c], e2 = h->cell_ptr[c + 1], n = e2 - b;
-    int64_t nch = (n + PSCL_ITEM_PAIRS - 1) / PSCL_ITEM_PAIRS;
-    for (int64_t i = 0; i < nch; ++i) {  // equal split, multiples of 32 pairs
-      int64_t s0 = b + ((n * i / nch) & ~(int64_t)31), t = (i + 1 == nch) ? e2 : b + ((n * (i + 1) / nch) & ~(int64_t)31);
-      item_cell.push_back(c); pbeg.push_back(s0); pend.push_back(t);
-    }
-  }
-  p->h_cell_item_ptr[C] = (int32_t)item_cell.size();
-  p->n_items = (int32_t)item_cell.size();
-  // items by descending size, ties in natural order: a counting sort (sizes are <= PSCL_ITEM_PAIRS + 31).  A staged
-  // image is ordered slice by slice, so that the kernel's first items are the ones whose gaps land first.
-  std::vector<int32_t> order(p->n_items);
-  {
-    const int NB = PSCL_ITEM_PAIRS + 64;
-    std::vector<int32_t> head(NB + 1);
-    const int nseg = p->n_stages > 1 ? p->n_stages : 1;
-    for (int k = 0; k < nseg; ++k) {
-      const int32_t ib = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k]] : 0;
-      const int32_t ie = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k + 1]] : p->n_items;
-      std::fill(head.begin(), head.end(), 0);
-      for (int32_t i = ib; i < ie; ++i) head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1) + 1]++;
-      for (int b2 = 0; b2 < NB; ++b2) head[b2 + 1] += head[b2];
-      for (int32_t i = ib; i < ie; ++i) order[ib + head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1)]++] = i;
-    }
-  }
+  if (e == cudaSuccess) e = plp_make_items(ctx, p, h->cell_ptr);
   const auto tr2 = tnow(false);
-  UP(item_cell, item_cell.data(), sizeof(int32_t) * p->n_items);
-  UP(item_pbeg, pbeg.data(), sizeof(int64_t) * p->n_items);
-  UP(item_pend, pend.data(), sizeof(int64_t) * p->n_items);
-  UP(item_order, order.data(), sizeof(int32_t) * p->n_items);
-  UP(cell_item_ptr, p->h_cell_item_ptr.data(), sizeof(int32_t) * (C + 1));
 #undef UP
   // ---- 2b. staged image: the gaps go last, slice by slice on the copy stream, a flag word behind each slice ----------
   if (p->n_stages > 1) {
@@ -379,7 +417,9 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     for (int k = 0; k < p->n_stages && e == cudaSuccess; ++k) {
       const int64_t pb = h->cell_ptr[p->stage_cell[k]], pe = h->cell_ptr[p->stage_cell[k + 1]];
       if (pe > pb) e = cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->stage_flags + k, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream);
+      // PSCL_FAULT=drop_stage_flag (fault-injection test): the last slice's flag never arrives, the kernel must time out
+      const bool drop = k == p->n_stages - 1 && getenv("PSCL_FAULT") && !strcmp(getenv("PSCL_FAULT"), "drop_stage_flag");
+      if (e == cudaSuccess && !drop) e = cudaMemcpyAsync(ctx->stage_flags + k, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream);
     }
   }
 
@@ -392,17 +432,26 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   if (cnt8) {
     size_t tb = 0;
     thrust::transform_iterator<PsclU8ToU32, const uint8_t*, uint32_t, uint32_t> it((const uint8_t*)d_cnt, PsclU8ToU32());
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, p->pair_rd, (int64_t)(P + 1), ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&d_scan_tmp, tb ? tb : 16);
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int)(P + 1), ctx->stream);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int64_t)(P + 1), ctx->stream);
     if (e == cudaSuccess) { k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, P, N, p->d_bad); ctx->launches += 2; e = cudaGetLastError(); }
   } else if (!ptr32) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
     if (e == cudaSuccess) {
-      k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1);
+      k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1, read_base);
       ctx->launches++;
       e = cudaGetLastError();
     }
+  } else if (read_base != 0 && e == cudaSuccess) {
+    k_rebase_u32<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>(p->pair_rd, P + 1, (uint32_t)read_base);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && P > 0 && (!dsnp || !cnt8) && p->n_stages == 0) {
+    k_check_pairs<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(p->pair_snp, p->pair_rd, P, V, N, dsnp ? 0 : 1, p->d_bad);
+    ctx->launches++;
+    e = cudaGetLastError();
   }
   if (e == cudaSuccess && N > 0) {
     if (packed) k_check_reads<<<(unsigned)((N + 4095) / 4096), 256, 0, ctx->stream>>>(p->rd_aq, N, p->d_bad);

@@ -42,8 +42,8 @@
 #define PSCL_FOLD_ROW 6  /* 5 factors padded to 48 B */
 #define PSCL_FOLD_ONES (2 * 64)
 #define PSCL_DICT_N 256 /* entries of the genotype dictionary (8-bit codes) */
-#ifndef PSCL_DICT_THREADS
-#define PSCL_DICT_THREADS 256 /* threads per CTA of the dictionary variants of k_demux_default (384 measured: +2%) */
+#ifndef PSCL_RENORM_EVERY
+#define PSCL_RENORM_EVERY 16 /* pairs between two exponent extractions of the running products (power of two) */
 #endif
 
 // max of positive, non-NaN doubles: DSETP + 2 SEL instead of fmax()'s NaN-aware sequence
@@ -63,12 +63,15 @@ struct DefaultCfg {
   static constexpr int LPR = NCH <= 1 ? 1 : NCH <= 2 ? 2 : NCH <= 4 ? 4 : NCH <= 8 ? 8 : NCH <= 16 ? 16 : 32;
   static constexpr int RPI = 32 / LPR;
   static_assert(NCH <= 32, "genotype row too long for the cooperative gather");
-  static constexpr int THREADS = 256;
-  static constexpr size_t SMEM = sizeof(double) * 3 * 64 * PSCL_FOLD_ROW +
-                                 (size_t)2 * THREADS * STRIDE_D * sizeof(double) + (size_t)NE * THREADS * sizeof(int);
-  // dictionary variants: fold table, [NE][threads] epilogue stash, [NE][threads] exponents, 256 triples x 16 copies
-  static constexpr size_t SMEM_DICT = sizeof(double) * 3 * 64 * PSCL_FOLD_ROW + (size_t)NE * PSCL_DICT_THREADS * (sizeof(double) + sizeof(int)) +
-                                      (size_t)PSCL_DICT_N * 3 * sizeof(double) * 16;
+  static_assert(NE <= 40, "the item epilogue reduces at most 32 + 8 accumulators");
+  // fold table | [2][threads] genotype rows | [NE][threads] exponents
+  __host__ __device__ static constexpr size_t smem_rows(int nt) {
+    return sizeof(double) * 3 * 64 * PSCL_FOLD_ROW + (size_t)2 * nt * STRIDE_D * sizeof(double) + (size_t)NE * nt * sizeof(int);
+  }
+  // dictionary variants: fold table | [NE][threads] exponents | 256 triples x 16 copies
+  __host__ __device__ static constexpr size_t smem_dict(int nt) {
+    return sizeof(double) * 3 * 64 * PSCL_FOLD_ROW + (size_t)NE * nt * sizeof(int) + (size_t)PSCL_DICT_N * 3 * sizeof(double) * 16;
+  }
 };
 
 struct DemuxArgs {
@@ -95,6 +98,7 @@ struct DemuxArgs {
   const int* flags = nullptr;          // [n_stages]
   int* bad = nullptr;                  // 2: SNP id out of range, 4: a slice never arrived
   int32_t n_snps = 0, n_stages = 0;
+  long long spin_limit = 0;            // clock64 ticks a warp waits for a slice before it gives up (bad = 4)
   int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};
   // dictionary-coded genotypes (k_demux_default<NV, *, true>): when every (SNP, sample) triple of the table is one of
   // <= 256 distinct triples (hard calls: 3 per combination of genotype counts), a pair needs 8 bytes of codes instead of
@@ -103,38 +107,37 @@ struct DemuxArgs {
   const double* gp_dict = nullptr;              // [256][3]
 };
 
-// threads per CTA: 256 for both kinds of variant (the dictionary variants were also measured with 384 threads at 168
-// registers: 0.650 vs 0.662 ms, not worth the spills; what bounds them is shared-memory bandwidth)
-template <int NV, bool DELTA, bool DICT>
-__global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_default(DemuxArgs a) {
+// NT threads per CTA, one CTA per SM.  (Splitting a work item's running products between two warps, so that 12 or 16
+// warps fit an SM at 158 / 128 registers, was measured at 0.67 / 0.71 ms against 0.53 ms for this form: the duplicated
+// fold and the extra work items cost more than the added warps hide; profiles/r2a_variants.txt.)
+template <int NV, bool DELTA, bool DICT, int NT>
+__global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
-  constexpr int NT = DICT ? PSCL_DICT_THREADS : 256;
-  constexpr int NE = Cfg::NE, ND = Cfg::ND, SD = Cfg::STRIDE_D;
-  constexpr int E_SG0 = NV + ND, E_MX = NV + ND + 1;
+  constexpr int ND = Cfg::ND, SD = Cfg::STRIDE_D, NAM = Cfg::NE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_tab = reinterpret_cast<double*>(smem_raw);        // [3*64][PSCL_FOLD_ROW]
-  double* s_g = s_tab + 3 * 64 * PSCL_FOLD_ROW;               // [2][256][SD] genotype rows; DICT: [NE][NT] epilogue stash
-  int* s_exp = reinterpret_cast<int*>(s_g + (DICT ? NE * NT : 2 * 256 * SD));  // [NE][NT]
+  double* s_g = s_tab + 3 * 64 * PSCL_FOLD_ROW;               // rows: [2][NT][SD] genotype rows
+  int* s_exp = reinterpret_cast<int*>(s_g + (DICT ? 0 : 2 * NT * SD));  // [NAM][NT]
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < 3 * 64 * PSCL_FOLD_ROW; i += NT) s_tab[i] = a.fold_tab[i];
   // DICT: the dictionary, 16 copies interleaved ([256*3][16] doubles): lane l reads copy l%16, which lives in its own
   // pair of banks, so the 32 lanes' lookups of 32 different triples never collide (a single copy cost ~3x the wavefronts)
-  double* const s_dict = reinterpret_cast<double*>(s_exp + NE * NT);
+  double* const s_dict = reinterpret_cast<double*>(s_exp + NAM * NT);
   if constexpr (DICT) {
     for (int i = tid; i < PSCL_DICT_N * 3 * 16; i += NT) s_dict[i] = a.gp_dict[i >> 4];
   }
   __syncthreads();
-  double* const g_row0 = s_g + (size_t)tid * SD;              // buffer 1 is 256*SD doubles further
+  double* const g_row0 = s_g + (size_t)tid * SD;              // buffer 1 is NT*SD doubles further
 
   // the next work index is fetched while the current item is processed (inline PTX: the compiler would
   // otherwise turn the lane-0 atomicAdd into a warp-aggregated one whose result is needed at once)
   auto grab = [&]() { int w = 0; if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(w) : "l"(a.counter) : "memory"); return w; };
-  int w_next = grab();
-  for (;;) {
-    const int w = __shfl_sync(0xffffffffu, w_next, 0);
-    if (w >= a.n_work) break;
-    w_next = grab();
-    const int item = a.item_order ? a.item_order[w] : a.item_base + w;
+
+  // ---- one work item ------------------------------------------------------------------------------------------------
+  // accumulators: [0, NV) singlets | [NV, NV+ND) doublets (j,k<j) at NV + j(j-1)/2 + k | k=0 column factor | pair normaliser
+  auto run = [&](const int item) {
+    constexpr int NACC = Cfg::NE, E_SG0 = NV + ND, E_MX = NV + ND + 1;
+
     const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
     const int niter = (int)((pe - pb + 31) >> 5);
     int snp_run = 0;       // DELTA: SNP id of the pair before the next 32
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_def
           asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(f) : "l"(a.flags + k) : "memory");
           if (f) break;
           __nanosleep(200);
-          if (clock64() - t_start > (1ll << 32)) { atomicExch(a.bad, 4); break; }
+          if (clock64() - t_start > a.spin_limit) { atomicExch(a.bad, 4); break; }
         }
       }
       __syncwarp();
@@ -165,9 +168,9 @@ __global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_def
       }
     }
 
-    double acc[NE];
+    double acc[NACC];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) { acc[e] = 1.0; s_exp[e * NT + tid] = 0; }
+    for (int e = 0; e < NACC; ++e) { acc[e] = 1.0; s_exp[e * NT + tid] = 0; }
     int n_has = 0;
 
     // ---- software pipeline --------------------------------------------------------------------
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_def
       // f = 32 i + lane: 12 instead of 16 instructions per 192-byte-row batch) was measured and is
       // NOT faster (0.749 vs 0.740 ms): the cost follows the rows touched, not the instructions.
       const unsigned okmask = __ballot_sync(0xffffffffu, okA);
-      double* dst_base = s_g + ((size_t)buf * 256 + (tid & ~31)) * SD;
+      double* dst_base = s_g + ((size_t)buf * NT + (tid & ~31)) * SD;
 #pragma unroll
       for (int i = 0; i < Cfg::LPR; ++i) {
         const int row = i * Cfg::RPI + (lane / Cfg::LPR), piece = lane % Cfg::LPR;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_def
             G[j][0] = d[0]; G[j][1] = d[16]; G[j][2] = d[32];
           }
         } else {
-          const double* row = g_row0 + (size_t)buf * 256 * SD;
+          const double* row = g_row0 + (size_t)buf * NT * SD;
           if constexpr (Cfg::V16) {
             const double2* r2 = reinterpret_cast<const double2*>(row);
             double flat[Cfg::ROW_D];
@@ -307,66 +310,77 @@ __global__ void __launch_bounds__(DICT ? PSCL_DICT_THREADS : 256, 1) k_demux_def
             acc[NV + j * (j - 1) / 2 + k] *= (G[k][0] * v0 + G[k][1] * v1 + G[k][2] * v2);
         }
       }
-      if ((it & 7) == 7) {
+      // Exponents move to shared memory every PSCL_RENORM_EVERY pairs.  A term is >= min h >= 1e-10 * mx (rows sum to one)
+      // and mx >= f(p = 0.5) >= 0.25^3 for the three folded base-calls (deeper pairs are rescaled), i.e. >= 1.5e-12:
+      // 16 of them stay above 1e-190, far inside a double's exponent range.
+      if ((it & (PSCL_RENORM_EVERY - 1)) == PSCL_RENORM_EVERY - 1) {
 #pragma unroll
-        for (int e = 0; e < NE; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * NT + tid] += ex; }
+        for (int e = 0; e < NACC; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * NT + tid] += ex; }
       }
     }
     if constexpr (!DICT) __pipeline_wait_prior(0);
 
     // ---- item epilogue ---------------------------------------------------------------------------
-    // Lane products are multiplied across the warp first (mantissas in [1,2) after renorm, so 32 of
-    // them cannot overflow), then ONE log per accumulator per item, taken by lane e%32.  Rolled
-    // through this lane's (now free) genotype rows so it does not bloat the hot loop's I-footprint.
-    if constexpr (DICT) {
+    // Lane products are multiplied across the warp by a transpose-reduction (recursive halving: 31 + 7 exchanged
+    // values per lane instead of 5 butterfly steps per accumulator; mantissas are in [1,2) after renorm, so 32 of
+    // them cannot overflow), then ONE log per accumulator per item, taken by the lane that ends up holding it.
+    // Two groups: GA in {8, 16, 32} accumulators, then GB in {0, 8} (NACC <= 40); after a transpose of N the product
+    // of element e sits in lane e * 32 / N.
+    constexpr int GA = NACC <= 8 ? 8 : NACC <= 24 ? 16 : 32, GB = NACC > GA ? 8 : 0;
+    static_assert(NACC <= GA + GB, "epilogue groups");
+    double lg1, lg2 = 0.0;
+    {
+      double m1[GA]; int x1[GA];
 #pragma unroll
-      for (int e = 0; e < NE; ++e) s_g[e * NT + tid] = acc[e];
-    } else {
-      double* st0 = g_row0;
-      double* st1 = g_row0 + (size_t)256 * SD;
-#pragma unroll
-      for (int e = 0; e < NE; ++e) { if (e < SD) st0[e] = acc[e]; else st1[e - SD] = acc[e]; }
-    }
-    double corr = 0.0, sg0_log = 0.0, keep_m0 = 1.0, keep_m1 = 1.0;
-    int keep_e0 = 0, keep_e1 = 0;
-#pragma unroll 1
-    for (int e = 0; e < NE; ++e) {
-      double m = DICT ? s_g[e * NT + tid] : (e < SD) ? g_row0[e] : g_row0[(size_t)256 * SD + (e - SD)];
-      int ex = s_exp[e * NT + tid];
-      pscl_renorm(m, ex);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        m *= __shfl_xor_sync(0xffffffffu, m, o);
-        ex += __shfl_xor_sync(0xffffffffu, ex, o);
+      for (int e = 0; e < GA; ++e) {
+        if (e < NACC) { m1[e] = acc[e]; x1[e] = s_exp[e * NT + tid]; pscl_renorm(m1[e], x1[e]); }
+        else { m1[e] = 1.0; x1[e] = 0; }
       }
-      if (e == E_MX) {  // every lane: log(prod mx * (1+1e-10)^n_has), the pair normaliser of :704-725
-        int nh = n_has;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, o);
-        corr = pscl_prod_log(m, ex) + (double)nh * log1p(1e-10);
-      } else if (e == E_SG0) {  // every lane: log prod (sum_m g_0[m]), the k=0 column factor of :806
-        sg0_log = pscl_prod_log(m, ex);
-      } else if ((e & 31) == lane) {
-        if (e < 32) { keep_m0 = m; keep_e0 = ex; } else { keep_m1 = m; keep_e1 = ex; }
-      }
+      pscl_transpose_prod<GA>(m1, x1, lane);
+      pscl_renorm(m1[0], x1[0]);
+      lg1 = pscl_prod_log(m1[0], x1[0]);
     }
+    if constexpr (GB > 0) {
+      double m2[8]; int x2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (GA + e < NACC) { m2[e] = acc[GA + e]; x2[e] = s_exp[(GA + e) * NT + tid]; pscl_renorm(m2[e], x2[e]); }
+        else { m2[e] = 1.0; x2[e] = 0; }
+      }
+      pscl_transpose_prod<8>(m2, x2, lane);
+      pscl_renorm(m2[0], x2[0]);
+      lg2 = pscl_prod_log(m2[0], x2[0]);
+    }
+    auto pick = [&](int e) { return e < GA ? __shfl_sync(0xffffffffu, lg1, e * (32 / GA)) : __shfl_sync(0xffffffffu, lg2, (e - GA) * 4); };
+    int nh = n_has;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nh += __shfl_xor_sync(0xffffffffu, nh, o);
+    // log(prod mx * (1+1e-10)^n_has): the pair normaliser of :704-725
+    const double corr = pick(E_MX) + (double)nh * log1p(1e-10);
+    const double sg0_log = pick(E_SG0);  // log prod (sum_m g_0[m]), the k=0 column factor of :806
     double* out = a.partial + (size_t)(item - a.item_base) * (NV * NV * 2);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int e = lane + 32 * half;
-      if (e < NV + ND) {
-        double x = pscl_prod_log(half ? keep_m1 : keep_m0, half ? keep_e1 : keep_e0) - corr;
-        if (e < NV) out[(e * NV + 0) * 2 + 0] = x + sg0_log;
-        else {
-          int dd = e - NV, j = 1;
-          while ((j + 1) * j / 2 <= dd) ++j;  // dd = j(j-1)/2 + k
-          const int k = dd - j * (j - 1) / 2;
-          out[(j * NV + k) * 2 + 1] = x;
-          out[(k * NV + j) * 2 + 1] = x;
-        }
+    auto store = [&](int e, double lg) {
+      if (e < NV) out[(e * NV + 0) * 2 + 0] = lg - corr + sg0_log;
+      else if (e < NV + ND) {
+        int dd = e - NV, j = 1;
+        while ((j + 1) * j / 2 <= dd) ++j;  // dd = j(j-1)/2 + k
+        const int k = dd - j * (j - 1) / 2;
+        const double x = lg - corr;
+        out[(j * NV + k) * 2 + 1] = x;
+        out[(k * NV + j) * 2 + 1] = x;
       }
-    }
+    };
+    if (lane % (32 / GA) == 0) store(lane / (32 / GA), lg1);
+    if (GB > 0 && (lane & 3) == 0) store(GA + (lane >> 2), lg2);
     __syncwarp();
+  };
+
+  int w_next = grab();
+  for (;;) {
+    const int w = __shfl_sync(0xffffffffu, w_next, 0);
+    if (w >= a.n_work) break;
+    w_next = grab();
+    run(a.item_order ? a.item_order[w] : a.item_base + w);
   }
 }
 
@@ -765,9 +779,11 @@ __global__ void __launch_bounds__(256) k_demux_epilogue_w(EpiArgs a, int n_cells
 }
 
 
-#include "demux_cls.inl"
-#include "demux_ab.inl"
 #include "demux_poly.inl"
+#ifdef PSCL_EXPERIMENTAL  // measured slower than k_demux_default: not part of the product library
+#include "experimental/demux_cls.inl"
+#include "experimental/demux_ab.inl"
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // host API
@@ -869,6 +885,37 @@ __global__ void k_geno_mix(const float* __restrict__ f32, const uint8_t* __restr
   }
 }
 
+// Tail of every way a genotype table gets onto the device (host copy, on-device mixing, NVLink peer copy): the
+// dictionary form of the table for k_demux_default (2 <= nv <= 8) — two small kernels, flag to a pinned word.
+static int demux_geno_finish(pscl_ctx* ctx, int32_t n_samples, int32_t n_snps) {
+  ctx->nv = n_samples;
+  ctx->geno_V = n_snps;
+  cudaFree(ctx->gp_code); ctx->gp_code = nullptr;
+  ctx->dict_built = false;
+  if (n_samples <= 8 && n_snps > 0 && ctx->h_dict_over) {
+    if (!ctx->gp_dict) {
+      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict, sizeof(double) * 3 * PSCL_DICT_N));
+      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_key, sizeof(unsigned long long) * PSCL_DICT_N));
+      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_over, sizeof(int)));
+    }
+    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_code, sizeof(unsigned long long) * (size_t)n_snps));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict, 0, sizeof(double) * 3 * PSCL_DICT_N, ctx->stream));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_key, 0, sizeof(unsigned long long) * PSCL_DICT_N, ctx->stream));
+    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_over, 0, sizeof(int), ctx->stream));
+    k_geno_dict_claim<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, n_samples, ctx->gp_dict_key, ctx->gp_dict,
+                                                                                 ctx->gp_dict_over);
+    k_geno_dict_codes<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, n_samples, ctx->gp_dict_key, ctx->gp_dict,
+                                                                                 ctx->gp_code, ctx->gp_dict_over);
+    ctx->launches += 2;
+    PSCL_CUDA(ctx, cudaGetLastError());
+    *ctx->h_dict_over = 1;
+    PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->h_dict_over, ctx->gp_dict_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->dict_built = true;
+  }
+  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev_dict, ctx->stream));  // both pinned flag words are valid once this completes
+  return PSCL_OK;
+}
+
 extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t n_snps) {
   if (!ctx) return PSCL_EINVAL;
   PsclScope scope__(ctx);
@@ -921,33 +968,7 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
     *ctx->h_geno_bad = 0;
   }
   if (!geno->gp && ctx->h_geno_bad == nullptr) return pscl_fail(ctx, PSCL_ENOMEM, "no pinned flag word for the raw genotype forms");
-  ctx->nv = geno->n_samples;
-  ctx->geno_V = n_snps;
-  // dictionary form of the table for k_demux_default (2 <= nv <= 8): two small kernels behind the copy, flag to a pinned word
-  cudaFree(ctx->gp_code); ctx->gp_code = nullptr;
-  ctx->dict_built = false;
-  if (geno->n_samples <= 8 && n_snps > 0 && ctx->h_dict_over) {
-    if (!ctx->gp_dict) {
-      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict, sizeof(double) * 3 * PSCL_DICT_N));
-      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_key, sizeof(unsigned long long) * PSCL_DICT_N));
-      PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_over, sizeof(int)));
-    }
-    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_code, sizeof(unsigned long long) * (size_t)n_snps));
-    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict, 0, sizeof(double) * 3 * PSCL_DICT_N, ctx->stream));
-    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_key, 0, sizeof(unsigned long long) * PSCL_DICT_N, ctx->stream));
-    PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_over, 0, sizeof(int), ctx->stream));
-    k_geno_dict_claim<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, geno->n_samples, ctx->gp_dict_key, ctx->gp_dict,
-                                                                                 ctx->gp_dict_over);
-    k_geno_dict_codes<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, geno->n_samples, ctx->gp_dict_key, ctx->gp_dict,
-                                                                                 ctx->gp_code, ctx->gp_dict_over);
-    ctx->launches += 2;
-    PSCL_CUDA(ctx, cudaGetLastError());
-    *ctx->h_dict_over = 1;
-    PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->h_dict_over, ctx->gp_dict_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->dict_built = true;
-  }
-  PSCL_CUDA(ctx, cudaEventRecord(ctx->ev_dict, ctx->stream));  // both pinned flag words are valid once this completes
-  return PSCL_OK;
+  return demux_geno_finish(ctx, geno->n_samples, n_snps);
 }
 
 extern "C" int pscl_demux_keep_grid(pscl_ctx* ctx, int enable) {
@@ -965,34 +986,47 @@ extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
 extern "C" int pscl_demux_last_kernel(const pscl_ctx* ctx) { return ctx ? ctx->dm_last_kernel : 0; }
 extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
   if (!ctx || which < 0 || which > 6) return PSCL_EINVAL;
+#ifndef PSCL_EXPERIMENTAL
+  if (which == 3 || which == 5)
+    return pscl_fail(ctx, PSCL_EINVAL, "k_demux_cls / k_demux_ab are experiments (csrc/experimental/), built only with -DPSCL_EXPERIMENTAL");
+#endif
   ctx->demux_kernel = which;
   return PSCL_OK;
 }
 
-template <int NV>
-static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
+// Threads per CTA of k_demux_default (compile-time; overridable for A/B builds, tools/build_variant.sh)
+#ifndef PSCL_DICT_NT
+#define PSCL_DICT_NT 256
+#endif
+#ifndef PSCL_ROWS_NT
+#define PSCL_ROWS_NT 256
+#endif
+
+template <int NV, bool DELTA, bool DICT>
+static cudaError_t launch_default_v(pscl_ctx* ctx, const DemuxArgs& a) {
+  constexpr int NT = DICT ? PSCL_DICT_NT : PSCL_ROWS_NT;
   using Cfg = DefaultCfg<NV>;
+  constexpr size_t SMEM = DICT ? Cfg::smem_dict(NT) : Cfg::smem_rows(NT);
+  static_assert(SMEM <= 227 * 1024, "k_demux_default: shared memory budget");
+  auto kern = k_demux_default<NV, DELTA, DICT, NT>;
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_demux_default<NV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_DICT);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_demux_default<NV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_DICT);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
-  const int wpc = (a.gp_code ? PSCL_DICT_THREADS : 256) / 32;  // warps (= work items in flight) per CTA
+  const int wpc = NT / 32;  // warps (= work items in flight) per CTA
   int grid = ctx->sm_count;
   if (grid * wpc > a.n_work) grid = (a.n_work + wpc - 1) / wpc;
   if (grid < 1) grid = 1;
-  if (a.gp_code) {
-    if (a.delta) k_demux_default<NV, true, true><<<grid, PSCL_DICT_THREADS, Cfg::SMEM_DICT, ctx->stream>>>(a);
-    else k_demux_default<NV, false, true><<<grid, PSCL_DICT_THREADS, Cfg::SMEM_DICT, ctx->stream>>>(a);
-  } else {
-    if (a.delta) k_demux_default<NV, true, false><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
-    else k_demux_default<NV, false, false><<<grid, 256, Cfg::SMEM, ctx->stream>>>(a);
-  }
+  kern<<<grid, NT, SMEM, ctx->stream>>>(a);
   return cudaGetLastError();
+}
+
+template <int NV>
+static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
+  if (a.gp_code) return a.delta ? launch_default_v<NV, true, true>(ctx, a) : launch_default_v<NV, false, true>(ctx, a);
+  return a.delta ? launch_default_v<NV, true, false>(ctx, a) : launch_default_v<NV, false, false>(ctx, a);
 }
 
 extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
@@ -1036,12 +1070,16 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     for (int i = 0; i < na; ++i) h_gamma[i] = 0.5 * h_alpha[i];
     PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_gamma, h_gamma, sizeof(h_gamma), 0, cudaMemcpyHostToDevice, ctx->stream));
   }
+#ifdef PSCL_EXPERIMENTAL
   const bool use_ws = use_default && (ctx->demux_kernel == 3 || ctx->demux_kernel == 5);
   const bool use_ab = use_default && ctx->demux_kernel == 5;
   if (use_ws) {
     if ((rc = dmx_build_classes(ctx, const_cast<pscl_plp*>(plp))) != PSCL_OK) return rc;
     if ((rc = dmx_build_geno_tables(ctx)) != PSCL_OK) return rc;
   }
+#else
+  const bool use_ws = false, use_ab = false;
+#endif
   ctx->dm_last_kernel = use_ab ? 5 : use_ws ? 3 : use_default ? (use_dict ? 6 : 1) : use_poly ? 4 : 2;
   const std::vector<int32_t>& cip = plp->h_cell_item_ptr;
   size_t max_items = ctx->partial_budget_bytes / (G * sizeof(double));
@@ -1072,9 +1110,11 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
           return pscl_fail(ctx, PSCL_ESTATE, "a staged pileup image can only be scored whole by k_demux_default");
         a.delta = plp->d_delta; a.first = plp->d_first; a.cell_ptr = plp->cell_ptr; a.item_cell = plp->item_cell;
         a.flags = ctx->stage_flags; a.bad = plp->d_bad; a.n_snps = plp->V; a.n_stages = plp->n_stages;
+        a.spin_limit = ctx->stage_spin_ticks;
         for (int k = 0; k <= plp->n_stages; ++k) a.stage_cell[k] = plp->stage_cell[k];
       }
       cudaError_t e = cudaSuccess;
+#ifdef PSCL_EXPERIMENTAL
       if (use_ws) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
         ClsArgs wa;
@@ -1105,7 +1145,9 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
             case 8: e = launch_cls<8>(ctx, wa); break;
           }
         }
-      } else if (use_default) {
+      } else
+#endif
+      if (use_default) {
         PSCL_CUDA(ctx, cudaMemsetAsync(ctx->dm_counter, 0, sizeof(int), ctx->stream));
         switch (nv) {
           case 2: e = launch_default<2>(ctx, a); break;
@@ -1219,6 +1261,14 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
     if (const char* sv = getenv("PSCL_STAGES")) stages = atoi(sv);
     else if (host->n_pairs >= ((int64_t)1 << 22)) stages = (int)std::min<int64_t>(PSCL_MAX_STAGES, host->n_pairs / 1250000);  // ~2.5 MB of gaps per slice
     if (stages < 1) stages = 1;
+    if (stages > 1) {
+      // a staged image is scored by ONE launch over all work items: fall back to the plain upload when their partial
+      // grids would not fit the scratch budget (pscl_demux_score would then have to split the cells into batches)
+      size_t items = 0;
+      for (int32_t c = 0; c < host->n_cells; ++c) items += (size_t)((host->cell_ptr[c + 1] - host->cell_ptr[c] + PSCL_ITEM_PAIRS - 1) / PSCL_ITEM_PAIRS);
+      const size_t G = (size_t)geno->n_samples * geno->n_samples * 2;
+      if (items * G * sizeof(double) > ctx->partial_budget_bytes) stages = 1;
+    }
   }
   const auto t0 = now();
   int rc = pscl_demux_set_geno(ctx, geno, host->n_snps);  // genotypes first: every slice needs them

@@ -27,7 +27,7 @@
 // L2.  Pairs are taken 8 at a time (warp w stages pair w: 16 + 16 genotype rows of 24 B, prefetched
 // through registers one group ahead; classes M and D also get their Phi / pG tables from that warp),
 // two block barriers per group.  The pairs of an item are processed in class order S | M | D
-// (records of demux_cls.inl's k_dmx_classify, so R is uniform within a group except M's 2 vs 3).
+// (records of k_dmx_classify below, so R is uniform within a group except M's 2 vs 3).
 
 #ifndef PLY_MINB
 #define PLY_MINB 2         /* CTAs per SM the register allocation aims at (NPL <= 21) */
@@ -54,6 +54,44 @@ struct PolyArgs {
   int32_t item_base, nv, na, tiles;  // tiles per dimension
 };
 
+#define WS_NONE_CODES 0x00808080u /* three "no base-call" codes: allele 2, qual 0 = the all-ones row of both fold tables */
+
+// record of every pair in original order + class key for the scan: low word counts class M
+// (2-3 usable base-calls), high word class D (> 3)
+__global__ void k_dmx_classify(const int32_t* __restrict__ pair_snp, const uint32_t* __restrict__ pair_rd,
+                               const uint8_t* __restrict__ rd_aq, int64_t P, uint2* __restrict__ rec_tmp,
+                               unsigned long long* __restrict__ key) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const uint32_t r0 = pair_rd[p], r1 = pair_rd[p + 1];
+  uint32_t cnt = 0, codes = WS_NONE_CODES;
+  for (uint32_t r = r0; r < r1; ++r) {
+    const uint32_t aq = rd_aq[r];
+    if ((aq >> 6) == 2u) continue;  // cmd_cram_demuxlet.cpp:664
+    if (cnt < 3u) codes = (codes & ~(0xffu << (8 * cnt))) | (aq << (8 * cnt));
+    ++cnt;
+  }
+  rec_tmp[p] = make_uint2((uint32_t)pair_snp[p], codes | (min(cnt, 255u) << 24));
+  key[p] = cnt <= 1u ? 0ull : cnt <= 3u ? 1ull : (1ull << 32);
+}
+
+
+// class ranges of a work item inside the class-ordered record array: the item's records are the
+// contiguous range [ib, ie) of its cell's range, whose classes are S | M | D with boundaries sm, md
+struct DmxItemRanges { uint32_t lo[3], hi[3]; };
+__device__ __forceinline__ DmxItemRanges dmx_item_ranges(const int64_t* cell_ptr, const int32_t* item_cell, const int64_t* item_pbeg,
+                                                         const int64_t* item_pend, const unsigned long long* scan, int item) {
+  const int c = item_cell[item];
+  const int64_t c0 = cell_ptr[c], c1 = cell_ptr[c + 1];
+  const unsigned long long s0 = scan[c0], s1 = scan[c1];
+  const int64_t n_m = (uint32_t)(s1 - s0), n_d = (uint32_t)((s1 >> 32) - (s0 >> 32)), n_s = (c1 - c0) - n_m - n_d;
+  const uint32_t ib = (uint32_t)item_pbeg[item], ie = (uint32_t)item_pend[item], sm = (uint32_t)(c0 + n_s), md = (uint32_t)(c0 + n_s + n_m);
+  DmxItemRanges r;
+  r.lo[0] = ib; r.hi[0] = min(ie, sm);
+  r.lo[1] = max(ib, sm); r.hi[1] = min(ie, md);
+  r.lo[2] = max(ib, md); r.hi[2] = ie;
+  return r;
+}
 // one warp per work item: class-ordered flat records (class D keeps the original pair index) and the
 // item's class boundaries
 __global__ void k_ply_scatter(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ item_cell,

@@ -1,4 +1,4 @@
-// demux_cls.inl — class-split demuxlet kernel for the default alpha grid {0, 0.5}, 2 <= nv <= 8
+// experimental/demux_cls.inl (compiled only with -DPSCL_EXPERIMENTAL; measured slower than k_demux_default, kept as a record) — class-split demuxlet kernel for the default alpha grid {0, 0.5}, 2 <= nv <= 8
 // (part of popscle_b200.cu; replaces cmd_cram_demuxlet.cpp:655-747).  k_demux_default (demux.inl) is
 // the lane-per-pair baseline this kernel is measured against; both are parity-tested.
 //
@@ -54,7 +54,6 @@
 #define CLS_FLAG_END 2u  /* last batch of its work item */
 #define CLS_FLAG_EXIT 4u
 #define CLS_FLAG_D 8u    /* class D: the fold comes from the deep table */
-#define WS_NONE_CODES 0x00808080u /* three "no base-call" codes: allele 2, qual 0 = the all-ones row of both fold tables */
 
 struct ClsArgs {
   const unsigned char* pkt;  // [n_pkt][CLS_PKT_B] batch packets: 16-byte header {flags | n<<8, item, -, -} + 32 records,
@@ -135,28 +134,7 @@ __device__ __forceinline__ void cls_bulk_g2s(uint32_t dst, const void* src, uint
 }
 __device__ __forceinline__ double cls_pmax(double x, double y) { return x > y ? x : y; }  // positive, non-NaN operands
 
-// Warp transpose-reduce of N (power of two) running products per lane: after the call lane L holds in
-// m[0], x[0] the product over all 32 lanes of element (L * N) / 32.  Recursive halving: at every step a
-// lane keeps one half of its elements, hands the other half to its partner and multiplies what it gets.
-template <int N>
-__device__ __forceinline__ void cls_transpose_prod(double (&m)[N], int (&x)[N], const int lane) {
-  int o = 16;
-#pragma unroll
-  for (int n = N / 2; n >= 1; n >>= 1, o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const double sm = up ? m[i] : m[i + n], km = up ? m[i + n] : m[i];
-      const int sx = up ? x[i] : x[i + n], kx = up ? x[i + n] : x[i];
-      m[i] = km * __shfl_xor_sync(0xffffffffu, sm, o);
-      x[i] = kx + __shfl_xor_sync(0xffffffffu, sx, o);
-    }
-  }
-  for (; o >= 1; o >>= 1) {  // fewer elements than lanes: finish with a plain butterfly
-    m[0] *= __shfl_xor_sync(0xffffffffu, m[0], o);
-    x[0] += __shfl_xor_sync(0xffffffffu, x[0], o);
-  }
-}
+#define cls_transpose_prod pscl_transpose_prod  /* common.cuh */
 
 struct ClsBatch {
   uint2 rec;       // this lane's record (a harmless one beyond n)
@@ -442,26 +420,7 @@ __global__ void __launch_bounds__(CLS_THREADS, 1) k_demux_cls(ClsArgs a) {
   cls_cp_async_wait<0>();
 }
 
-// ---- class-stream build (once per pileup image) ------------------------------------------------------
-// record of every pair in original order + class key for the scan: low word counts class M
-// (2-3 usable base-calls), high word class D (> 3)
-__global__ void k_dmx_classify(const int32_t* __restrict__ pair_snp, const uint32_t* __restrict__ pair_rd,
-                               const uint8_t* __restrict__ rd_aq, int64_t P, uint2* __restrict__ rec_tmp,
-                               unsigned long long* __restrict__ key) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const uint32_t r0 = pair_rd[p], r1 = pair_rd[p + 1];
-  uint32_t cnt = 0, codes = WS_NONE_CODES;
-  for (uint32_t r = r0; r < r1; ++r) {
-    const uint32_t aq = rd_aq[r];
-    if ((aq >> 6) == 2u) continue;  // cmd_cram_demuxlet.cpp:664
-    if (cnt < 3u) codes = (codes & ~(0xffu << (8 * cnt))) | (aq << (8 * cnt));
-    ++cnt;
-  }
-  rec_tmp[p] = make_uint2((uint32_t)pair_snp[p], codes | (min(cnt, 255u) << 24));
-  key[p] = cnt <= 1u ? 0ull : cnt <= 3u ? 1ull : (1ull << 32);
-}
-
+// ---- class-stream build (once per pileup image): k_dmx_classify lives in demux_poly.inl (k_demux_poly shares it) ----
 // one warp per work item: records of a cell are written class S first, then M, then D, each in the
 // original (ascending SNP) order; class-D pairs are folded here (cmd_cram_demuxlet.cpp:660-700)
 __global__ void k_dmx_scatter(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ item_cell,
@@ -505,22 +464,7 @@ __global__ void k_dmx_scatter(const int64_t* __restrict__ cell_ptr, const int32_
   }
 }
 
-// class ranges of a work item inside the class-ordered record array: the item's records are the
-// contiguous range [ib, ie) of its cell's range, whose classes are S | M | D with boundaries sm, md
-struct DmxItemRanges { uint32_t lo[3], hi[3]; };
-__device__ __forceinline__ DmxItemRanges dmx_item_ranges(const int64_t* cell_ptr, const int32_t* item_cell, const int64_t* item_pbeg,
-                                                         const int64_t* item_pend, const unsigned long long* scan, int item) {
-  const int c = item_cell[item];
-  const int64_t c0 = cell_ptr[c], c1 = cell_ptr[c + 1];
-  const unsigned long long s0 = scan[c0], s1 = scan[c1];
-  const int64_t n_m = (uint32_t)(s1 - s0), n_d = (uint32_t)((s1 >> 32) - (s0 >> 32)), n_s = (c1 - c0) - n_m - n_d;
-  const uint32_t ib = (uint32_t)item_pbeg[item], ie = (uint32_t)item_pend[item], sm = (uint32_t)(c0 + n_s), md = (uint32_t)(c0 + n_s + n_m);
-  DmxItemRanges r;
-  r.lo[0] = ib; r.hi[0] = min(ie, sm);
-  r.lo[1] = max(ib, sm); r.hi[1] = min(ie, md);
-  r.lo[2] = max(ib, md); r.hi[2] = ie;
-  return r;
-}
+// (dmx_item_ranges lives in demux_poly.inl)
 // number of 32-record packets of every work item (a packet never mixes classes)
 __global__ void k_dmx_count_packets(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ item_cell,
                                     const int64_t* __restrict__ item_pbeg, const int64_t* __restrict__ item_pend, int32_t n_items,

@@ -769,11 +769,11 @@ static int fmx_build_csc(pscl_ctx* ctx, pscl_fmx_state* s) {
   int end_bit = 1;
   while (end_bit < 31 && ((int64_t)1 << end_bit) < (int64_t)s->V) ++end_bit;
   // stable LSD radix sort: equal SNP ids keep their cell-major order = ascending cell id
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int)P, 0, end_bit, ctx->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int64_t)P, 0, end_bit, ctx->stream);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp2_bytes, glen, s->grp_base, NG + 1, ctx->stream);
   PSCL_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
   PSCL_CUDA(ctx, cudaMalloc(&tmp2, tmp2_bytes ? tmp2_bytes : 16));
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int)P, 0, end_bit, ctx->stream);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plp->pair_snp, key_out, val_in, s->snp_pair, (int64_t)P, 0, end_bit, ctx->stream);
   ctx->launches += 4;
   if (e == cudaSuccess) {
     k_fmx_snp_ptr<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(key_out, s->V, P, s->snp_ptr);
@@ -1070,9 +1070,11 @@ extern "C" int pscl_fmx_classify(pscl_ctx* ctx, const double* llk_dev, int32_t* 
   return PSCL_OK;
 }
 
-extern "C" int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt) {
-  FMX_STATE(ctx, s);
-  if (!s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_fetch before pscl_fmx_seed");
+// Per-cell records (nullable) and the cluster pileups of SNPs [v0, v1) of the current membership, written to rows
+// [v0, v1) of the caller's [V][nS][9] / [V][nS][3] arrays (an SNP shard owns exactly its own rows).
+static int fmx_fetch_range(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, int32_t v0, int32_t v1) {
+  pscl_fmx_state* s = ctx->fmx;
+  if (!s || !s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_fetch before pscl_fmx_seed");
   if (out && s->C > 0)
     PSCL_CUDA(ctx, cudaMemcpyAsync(out, s->cells, sizeof(pscl_fmx_cell) * (size_t)s->C, cudaMemcpyDeviceToHost, ctx->stream));
   if (clust_gl || clust_cnt) {
@@ -1080,12 +1082,17 @@ extern "C" int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_g
     // reference writes .clust1.vcf.gz, cmd_cram_freemux2.cpp:608-658)
     int rc = fmx_mstep_launch(ctx, s, s->member, 1);
     if (rc != PSCL_OK) return rc;
-    const size_t VS = (size_t)s->V * s->nS;
-    if (clust_gl && VS) PSCL_CUDA(ctx, cudaMemcpyAsync(clust_gl, s->clust_gl, sizeof(double) * 9 * VS, cudaMemcpyDeviceToHost, ctx->stream));
-    if (clust_cnt && VS) PSCL_CUDA(ctx, cudaMemcpyAsync(clust_cnt, s->clust_cnt, sizeof(int32_t) * 3 * VS, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t off = (size_t)v0 * s->nS, n = (size_t)(v1 > v0 ? v1 - v0 : 0) * s->nS;
+    if (clust_gl && n) PSCL_CUDA(ctx, cudaMemcpyAsync(clust_gl + 9 * off, s->clust_gl + 9 * off, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (clust_cnt && n) PSCL_CUDA(ctx, cudaMemcpyAsync(clust_cnt + 3 * off, s->clust_cnt + 3 * off, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
   }
   PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PSCL_OK;
+}
+
+extern "C" int pscl_fmx_fetch(pscl_ctx* ctx, pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt) {
+  FMX_STATE(ctx, s);
+  return fmx_fetch_range(ctx, out, clust_gl, clust_cnt, 0, s->V);
 }
 
 extern "C" int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float* ms) {

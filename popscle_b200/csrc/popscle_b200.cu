@@ -5,3 +5,4 @@
 #include "context.inl"
 #include "demux.inl"
 #include "freemux.inl"
+#include "multi.inl"

@@ -69,14 +69,32 @@ struct Parser {
   }
 };
 
-struct Ctx {  // pscl_ctx with the reference's error convention
+// The engine behind a command, with the reference's error convention: one GPU (pscl_ctx) or, with `--gpus N`
+// (N > 1; 0 = every visible GPU) or PSCL_GPU_IDS=0,1,..., several GPUs of this box (pscl_multi: barcode-sharded
+// demuxlet, SNP-sharded freemuxlet; the reference's own advice is to split the barcodes by hand with --group-list,
+// cmd_cram_demuxlet.cpp:75).
+struct Engine {
   pscl_ctx* h = nullptr;
-  Ctx() {
+  pscl_multi* m = nullptr;
+  explicit Engine(int gpus) {
     char err[512] = {0};
-    if (pscl_create(0, &h, err, sizeof err) != PSCL_OK) throw host_error(err);
+    std::vector<int> ids;
+    if (const char* e = getenv("PSCL_GPU_IDS")) {
+      for (const char* c = e; *c;) { ids.push_back(atoi(c)); while (*c && *c != ',') ++c; if (*c == ',') ++c; }
+    }
+    if (ids.size() > 1 || (ids.empty() && gpus != 1)) {
+      if (pscl_multi_create(ids.empty() ? NULL : ids.data(), ids.empty() ? gpus : (int)ids.size(), &m, err, sizeof err) != PSCL_OK) throw host_error(err);
+    } else if (pscl_create(ids.empty() ? 0 : ids[0], &h, err, sizeof err) != PSCL_OK) throw host_error(err);
   }
-  ~Ctx() { pscl_destroy(h); }
-  void chk(int rc) { if (rc != PSCL_OK) throw host_error(pscl_last_error(h)); }
+  ~Engine() { pscl_destroy(h); pscl_multi_destroy(m); }
+  int n_gpus() const { return m ? pscl_multi_size(m) : 1; }
+  void chk(int rc) { if (rc != PSCL_OK) throw host_error(m ? pscl_multi_last_error(m) : pscl_last_error(h)); }
+  void demux_run(const pscl_pileup* v, const pscl_geno* g, const pscl_demux_opts* o, pscl_demux_cell* out) {
+    chk(m ? pscl_multi_demux_run(m, v, g, o, out, NULL) : pscl_demux_run(h, v, g, o, out, NULL));
+  }
+  void fmx_run(const pscl_pileup* v, const pscl_fmx_opts* o, const int32_t* init, pscl_fmx_cell* out, double* gl, int32_t* cnt, pscl_fmx_result* res) {
+    chk(m ? pscl_multi_fmx_run(m, v, o, init, out, gl, cnt, res) : pscl_fmx_run(h, v, o, init, out, gl, cnt, res));
+  }
 };
 
 // test hook: what the loader produced, without touching the GPU
@@ -116,7 +134,7 @@ int cmd_demuxlet(int argc, char** argv) {
   std::string sam, tagGroup = "CB", tagUMI = "UB", plp, vcf, field = "GP", r2Info = "R2", smList, out, groupList;
   double genoErrorOffset = 0.1, genoErrorCoeff = 0.0, minCallRate = 0.5, doubletPrior = 0.5;
   int minMAC = 1, samVerbose = 1000000, vcfVerbose = 10000, capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0, exclFlag = 3844;
-  int minTotal = 0, minUMI = 0, minSNP = 0;
+  int minTotal = 0, minUMI = 0, minSNP = 0, gpus = 1;
   std::vector<std::string> sm;
   std::vector<double> alphas;
   bool dry = false;
@@ -128,6 +146,7 @@ int cmd_demuxlet(int argc, char** argv) {
   p.add("sam-verbose", &samVerbose); p.add("vcf-verbose", &vcfVerbose); p.add("cap-BQ", &capBQ); p.add("min-BQ", &minBQ);
   p.add("min-MQ", &minMQ); p.add("min-TD", &minTD); p.add("excl-flag", &exclFlag); p.add("group-list", &groupList);
   p.add("min-total", &minTotal); p.add("min-umi", &minUMI); p.add("min-snp", &minSNP); p.add("dry-run", &dry);
+  p.add("gpus", &gpus);  // extension: GPUs of this box to shard the barcodes over (1; 0 = all)
   p.read(argc, argv);
   if (alphas.empty()) { alphas.push_back(0.0); alphas.push_back(0.5); }  // cmd_cram_demuxlet.cpp:85-89
   if (!sam.empty()) throw host_error("--sam (BAM/CRAM pileup on the fly) needs htslib; run `popscle dsc-pileup` first and pass --plp");
@@ -144,12 +163,13 @@ int cmd_demuxlet(int argc, char** argv) {
   notice("Finished loading %d droplets, %d variants, %zu UMIs in total..", L.n_cells, L.n_snps, L.read_allele.size());
   if (dry) return dry_run(L);
   notice("Starting to identify best matching individual IDs");
-  Ctx ctx;
+  Engine eng(gpus);
   pscl_pileup view = L.view();
   pscl_geno geno = L.geno_view();  // raw posteriors / hard calls + error rates: the library mixes on the device
   pscl_demux_opts opts = {(int32_t)alphas.size(), alphas.data(), doubletPrior};
   std::vector<pscl_demux_cell> cells((size_t)L.n_cells);
-  ctx.chk(pscl_demux_run(ctx.h, &view, &geno, &opts, cells.data(), NULL));
+  if (eng.n_gpus() > 1) notice("Sharding %d droplets over %d GPUs by pair count", L.n_cells, eng.n_gpus());
+  eng.demux_run(&view, &geno, &opts, cells.data());
   write_best(out + ".best", L, cells, alphas, minTotal, minUMI, minSNP);
   notice("Finished writing output files");
   return 0;
@@ -157,7 +177,7 @@ int cmd_demuxlet(int argc, char** argv) {
 
 int cmd_freemux(int argc, char** argv, bool old_mode) {
   std::string plp, initClusterFile, out, groupList;
-  int nSamples = 0, verbose = 100, initIteration = 10, capBQ = old_mode ? 40 : 20, minBQ = 13, minTotal = 0, minUMI = 0, minSNP = 0, seed = 0;
+  int nSamples = 0, verbose = 100, initIteration = 10, capBQ = old_mode ? 40 : 20, minBQ = 13, minTotal = 0, minUMI = 0, minSNP = 0, seed = 0, gpus = 1;
   double doubletPrior = 0.5, genoError = old_mode ? 0.0 : 0.1, bfThres = 5.41, fracInitClust = 1.0;
   bool auxFiles = false, keepInitMissing = false, randomize = false, dry = false;
   Parser p;
@@ -166,6 +186,7 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   p.add("bf-thres", &bfThres); p.add("frac-init-clust", &fracInitClust); p.add("iter-init", &initIteration);
   p.add("keep-init-missing", &keepInitMissing); p.add("cap-BQ", &capBQ); p.add("min-BQ", &minBQ); p.add("group-list", &groupList);
   p.add("min-total", &minTotal); p.add("min-snp", &minSNP); p.add("dry-run", &dry);
+  p.add("gpus", &gpus);  // extension: GPUs of this box to shard the SNPs over (1; 0 = all)
   if (old_mode) p.add("min-uniq", &minUMI);
   else { p.add("min-umi", &minUMI); p.add("randomize-singlet-score", &randomize); p.add("seed", &seed); }
   p.read(argc, argv);
@@ -208,14 +229,15 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
     if (nmiss > 0) fprintf(stderr, "WARNING: %d of %d droplets do not have initial cluster assignment\n", nmiss, L.n_cells);
   }
   if (dry) return dry_run(L);
-  Ctx ctx;
+  Engine eng(gpus);
   pscl_pileup view = L.view();
   pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0, randomize ? 1 : 0, seed};
   std::vector<pscl_fmx_cell> cells((size_t)L.n_cells);
   std::vector<double> gl((size_t)L.n_snps * nSamples * 9);
   std::vector<int32_t> cnt((size_t)L.n_snps * nSamples * 3);
   pscl_fmx_result res;
-  ctx.chk(pscl_fmx_run(ctx.h, &view, &o, init.empty() ? NULL : init.data(), cells.data(), gl.data(), cnt.data(), &res));
+  if (eng.n_gpus() > 1) notice("Sharding %d variants over %d GPUs by pair count", L.n_snps, eng.n_gpus());
+  eng.fmx_run(&view, &o, init.empty() ? NULL : init.data(), cells.data(), gl.data(), cnt.data(), &res);
   notice("Finished %d EM iterations: %d singlets, %d doublets, %d ambiguous, and %d changed", res.n_iter, res.n_singlet, res.n_doublet,
          res.n_ambiguous, res.n_changed);
   write_lmix(out + ".lmix", L, cells, old_mode);

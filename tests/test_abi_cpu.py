@@ -53,7 +53,7 @@ def test_no_cpu_fallback(built):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = capi.load_library()
-    assert lib.pscl_abi_version() == 5
+    assert lib.pscl_abi_version() == 6
     h = ctypes.c_void_p()
     err = ctypes.create_string_buffer(256)
     rc = lib.pscl_create(0, ctypes.byref(h), err, len(err))

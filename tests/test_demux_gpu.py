@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEFAULT = [0.0, 0.5]
 
 
-KERNELS = {"auto": 0, "lane": 1, "general": 2, "cls": 3, "poly": 4, "ab": 5, "dict": 6}
+KERNELS = {"auto": 0, "lane": 1, "general": 2, "poly": 4, "dict": 6}
 
 
 def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
@@ -29,7 +29,7 @@ def _run_both(ctx, s, gp, has_gp, alphas, general=False, dp=0.5):
 
 
 @pytest.mark.parametrize("nv", [2, 3, 4, 5, 6, 7, 8])
-@pytest.mark.parametrize("general", ["cls", "ab", "lane", "dict", "general", "poly"])
+@pytest.mark.parametrize("general", ["lane", "dict", "general", "poly"])
 def test_default_grid_parity(ctx, nv, general):
     s = synth.make_pileup(C=300, nv=nv, V=2000, kbar=250, seed=100 + nv)
     gp = synth.gt_to_gp(s.geno)
@@ -100,7 +100,7 @@ def test_missing_genotypes_and_other_alleles(ctx):
     gp = rng.dirichlet([0.4, 0.4, 0.4], size=(s.plp.n_snps, 5)).astype(np.float32).astype(np.float64)
     has = (rng.random(s.plp.n_snps) > 0.3).astype(np.uint8)
     s.plp.read_allele[rng.random(s.plp.n_reads) < 0.2] = 2
-    for general in ("cls", "ab", "lane", "dict", "general", "poly"):
+    for general in ("lane", "dict", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, has, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT)
 
@@ -125,12 +125,12 @@ def test_deep_pairs_and_empty_cells(ctx):
     geno = rng.integers(0, 3, (nv, V)).astype(np.int8)
     gp = synth.gt_to_gp(geno)
     s = synth.Synth(plp, geno, plp.snp_af, None, None, 9)
-    for general in ("cls", "ab", "lane", "dict", "general", "poly"):
+    for general in ("lane", "dict", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
         check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.3)
 
 
-@pytest.mark.parametrize("kernel", ["cls", "ab", "lane", "dict"])
+@pytest.mark.parametrize("kernel", ["lane", "dict"])
 def test_sharding_is_bit_identical(ctx, kernel):
     """barcode shards reproduce the unsharded records bit for bit; so do partial-grid batches."""
     s = synth.make_pileup(C=400, nv=8, V=3000, kbar=300, seed=77)
@@ -185,7 +185,7 @@ def test_errors(ctx):
         ctx.demux_run(bad, gp, None, DEFAULT)
 
 
-@pytest.mark.parametrize("kernel", ["cls", "ab", "lane", "dict"])
+@pytest.mark.parametrize("kernel", ["lane", "dict"])
 def test_cells_larger_than_one_work_item(ctx, kernel):
     """cells with > 2048 pairs are cut into several work items whose partial grids are summed in item order."""
     s = synth.make_pileup(C=24, nv=8, V=30000, kbar=5000, seed=88)
@@ -363,7 +363,7 @@ def test_poly_shapes(ctx, nv, na):
     check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
 
 
-@pytest.mark.parametrize("kernel", ["lane", "cls", "ab", "poly", "general"])
+@pytest.mark.parametrize("kernel", ["lane", "dict", "poly", "general"])
 def test_degenerate_pileups(ctx, kernel):
     """one cell with one pair; no pair at all; no SNP with genotypes"""
     from popscle_b200 import Pileup
