@@ -321,6 +321,9 @@ int pscl_bind_thread_to_device(int device);
 /* ---- knobs used by tests and the benchmark harness ---- */
 /* Launch on a caller-owned stream (e.g. torch's current stream) instead of the context's own. */
 int pscl_set_stream(pscl_ctx* ctx, void* cuda_stream);
+/* Fault injection for the error-path tests: the nth device allocation from now on (nth >= 1) fails as an exhausted
+ * device would (the call then returns PSCL_ENOMEM and the context stays usable); 0 = off. */
+int pscl_debug_fail_alloc(pscl_ctx* ctx, int nth);
 /* Upper bound of the per-batch partial-grid scratch of pscl_demux_score (default 1 GiB). */
 int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes);
 /* Route every alpha grid through the general demuxlet kernel (parity tests of that kernel). */

@@ -226,6 +226,7 @@ def load_library() -> C.CDLL:
         "pscl_sync": (C.c_int, [vp]),
         "pscl_launch_count": (i64, [vp]),
         "pscl_set_partial_budget": (C.c_int, [vp, C.c_size_t]),
+        "pscl_debug_fail_alloc": (C.c_int, [vp, C.c_int]),
         "pscl_plp_upload": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(vp)]),
         "pscl_plp_free": (None, [vp, vp]),
         "pscl_demux_set_geno": (C.c_int, [vp, C.POINTER(CGeno), i32]),
@@ -266,7 +267,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "pscl_abi_version", "pscl_create", "pscl_destroy", "pscl_last_error", "pscl_stream", "pscl_set_stream",
-    "pscl_sync", "pscl_launch_count", "pscl_set_partial_budget", "pscl_plp_upload", "pscl_plp_free",
+    "pscl_sync", "pscl_launch_count", "pscl_set_partial_budget", "pscl_debug_fail_alloc", "pscl_plp_upload", "pscl_plp_free",
     "pscl_demux_set_geno", "pscl_demux_score", "pscl_demux_fetch", "pscl_demux_keep_grid",
     "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_demux_last_kernel", "pscl_fmx_run", "pscl_fmx_init",
     "pscl_fmx_stage1", "pscl_fmx_seed", "pscl_fmx_mstep", "pscl_fmx_estep", "pscl_fmx_classify",
@@ -323,6 +324,10 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.pscl_launch_count(self.h))
+
+    def debug_fail_alloc(self, nth: int):
+        """test knob: the nth device allocation from now fails (PSCL_ENOMEM)"""
+        self._chk(self.lib.pscl_debug_fail_alloc(self.h, int(nth)))
 
     def set_partial_budget(self, nbytes: int):
         self._chk(self.lib.pscl_set_partial_budget(self.h, nbytes))

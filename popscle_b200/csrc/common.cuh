@@ -111,6 +111,7 @@ struct pscl_ctx {
   float dm_ms_main = 0.f, dm_ms_total = 0.f;
   bool dm_timed = false;
   pscl_fmx_state* fmx = nullptr;
+  int fail_alloc_in = 0;  // pscl_debug_fail_alloc
 };
 
 // ---- device memory: stream-ordered allocation out of the device's default memory pool -------------
@@ -121,12 +122,17 @@ struct pscl_ctx {
 // release threshold so freed blocks stay mapped for the next call.  The two macros below route the
 // (many) existing call sites; PsclScope publishes the current context's stream to them.
 static thread_local cudaStream_t t_pscl_stream = nullptr;
-static inline cudaError_t pscl_pool_alloc(void** p, size_t n) { return cudaMallocAsync(p, n ? n : 16, t_pscl_stream); }
+static thread_local pscl_ctx* t_pscl_ctx = nullptr;
+static inline cudaError_t pscl_pool_alloc(void** p, size_t n) {
+  // fault injection (pscl_debug_fail_alloc): the n-th allocation from now fails the way an exhausted device does
+  if (t_pscl_ctx && t_pscl_ctx->fail_alloc_in > 0 && --t_pscl_ctx->fail_alloc_in == 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  return cudaMallocAsync(p, n ? n : 16, t_pscl_stream);
+}
 static inline cudaError_t pscl_pool_free(void* p) { return p ? cudaFreeAsync(p, t_pscl_stream) : cudaSuccess; }
 #define cudaMalloc(p, n) pscl_pool_alloc((void**)(p), (n))
 #define cudaFree(p) pscl_pool_free((void*)(p))
 struct PsclScope {
-  explicit PsclScope(const pscl_ctx* c) { t_pscl_stream = c->stream; }
+  explicit PsclScope(const pscl_ctx* c) { t_pscl_stream = c->stream; t_pscl_ctx = const_cast<pscl_ctx*>(c); }
 };
 
 static inline int pscl_fail(pscl_ctx* ctx, int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));

@@ -136,6 +136,11 @@ extern "C" int pscl_sync(pscl_ctx* ctx) {
   return PSCL_OK;
 }
 extern "C" int64_t pscl_launch_count(const pscl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int pscl_debug_fail_alloc(pscl_ctx* ctx, int nth) {
+  if (!ctx) return PSCL_EINVAL;
+  ctx->fail_alloc_in = nth > 0 ? nth : 0;
+  return PSCL_OK;
+}
 extern "C" int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes) {
   if (!ctx || bytes < (1u << 20)) return PSCL_EINVAL;
   ctx->partial_budget_bytes = bytes;
@@ -254,7 +259,7 @@ static const char* pscl_bad_pileup_msg(int bad) {
 extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
   if (!p) return;
   if (ctx) {
-    t_pscl_stream = ctx->stream; cudaSetDevice(ctx->device);
+    t_pscl_stream = ctx->stream; t_pscl_ctx = ctx; cudaSetDevice(ctx->device);
     if (p->n_stages && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // slices still in flight write into d_delta
     cudaStreamSynchronize(ctx->stream);
   }

@@ -112,6 +112,9 @@ class _OracleStep:
         self.new_f64 = lambda n: np.zeros(n)
         self.new_i32 = lambda n: np.zeros(n, dtype=np.int32)
 
+    def set_f64(self, buf, values):
+        buf[:] = values
+
     def init(self, plp, opts):
         self.plp, self.o = plp, opts
         self.nS = opts.n_clusters
@@ -186,11 +189,36 @@ def _worker_fmx(rank, world, port, q):
     o = orc.fmx_opts(3, max_iter=4)
     init = s.truth_d1.astype(np.int32)
     (types, member), res = dist.fmx_em_sharded(_OracleStep(), s.plp.slice_snps(v0, v1), o, init, allreduce, 50)
+    # without --init-cluster: greedy seeding over the whole pileup on rank 0 only, clusters broadcast
+    calls = []
+
+    def seed_full():
+        if rank != 0:
+            return None
+        calls.append(1)
+        r = orc.fmx_run(s.plp, orc.fmx_opts(3, max_iter=0))["cells"]
+        st = np.concatenate([r["llk0"], r["llk2"], r["n_snps"].astype(np.float64), r["n_reads"].astype(np.float64)])
+        return st, r["init_clust"]
+
+    def bcast(a):
+        box = [a]
+        td.broadcast_object_list(box, src=0)
+        return box[0]
+    (types2, member2), _ = dist.fmx_em_sharded(_OracleStep(), s.plp.slice_snps(v0, v1), o, None, allreduce, 50, seed_full=seed_full, bcast=bcast)
+    assert len(calls) == (1 if rank == 0 else 0)
     if rank == 0:
         (t1, m1), r1 = dist.fmx_em_sharded(_OracleStep(), s.plp, o, init, lambda b: None, 50)
         ref = orc.fmx_run(s.plp, o, init)["cells"]
-        q.put(bool(np.array_equal(types, t1) and np.array_equal(member, m1) and np.array_equal(types, ref["type"])
-                   and np.array_equal(member, np.where(ref["type"] == 0, ref["best_j"], -1))))
+        ok = bool(np.array_equal(types, t1) and np.array_equal(member, m1) and np.array_equal(types, ref["type"])
+                  and np.array_equal(member, np.where(ref["type"] == 0, ref["best_j"], -1)))
+        ref2 = orc.fmx_run(s.plp, o)["cells"]  # greedy seeding + EM, unsharded
+        ok = ok and bool(np.array_equal(types2, ref2["type"]) and np.array_equal(member2, np.where(ref2["type"] == 0, ref2["best_j"], -1)))
+        try:
+            dist.fmx_em_sharded(_OracleStep(), s.plp, o, None, lambda b: None, 50)
+            ok = False
+        except ValueError:
+            pass
+        q.put(ok)
     td.destroy_process_group()
 
 
