@@ -357,6 +357,172 @@ __global__ void __launch_bounds__(1024, 1) k_fmx_seed(SeedArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// greedy seeding, batched: the same chain of decisions, but only what really depends on the previous cell is serial
+// ------------------------------------------------------------------------------------------------
+// The distance of cell i to cluster j is a sum over the SNPs the two share (sc_drop_seq.cpp:544-578), and the state of
+// cluster j at SNP s changes only when a cell covering s is merged into j.  A batch of B cells (consecutive in seeding
+// order) is therefore handled in two launches:
+//   k_fmx_seed_dist    (all SMs) every (cell of the batch, SNP, cluster) contribution against the cluster table as it
+//                      stands BEFORE the batch, kept per (pair, cluster) in `contrib`, plus their per-cell sums;
+//   k_fmx_seed_commit  (one CTA) walks the B cells in order.  A cell's true distance = snapshot sum + the corrections at
+//                      the SNPs some earlier cell of this batch merged into (dirty[s]: batch stamp + cluster bit mask):
+//                      contribution against the CURRENT table minus the stored one.  Then argmax (first wins, :238-241)
+//                      and the merge (:248-251), which marks its SNPs dirty.
+// Cells of a batch share few SNPs (K^2/V = 40 of 2000 at configs[2]), so the serial part touches ~K dirty words and a few
+// hundred corrections per cell instead of K x nS evaluations with two logs each.  The decisions are those of the serial
+// chain up to the summation order of the distance (a reordering of ~1e3 terms; ties within ~1e-13 relative could flip,
+// as they could between any two compilers of the reference).
+#define PSCL_SEED_SPLIT 4   /* CTAs per batch cell in k_fmx_seed_dist */
+struct SeedBatchArgs {
+  const int32_t* elig;        // [n_elig] cells that take part, in seeding order
+  const int64_t* epair;       // [n_elig + 1] running pair count of those cells (offsets into contrib, relative to the batch)
+  const int64_t* cell_ptr;
+  const int32_t* pair_snp;
+  const double* gl_soa;
+  const double* snp_af;
+  double* clust_gl;           // [V][nS][9]
+  uint8_t* present;           // [V][nS]
+  unsigned long long* dirty;  // [V] (batch + 1) << 32 | mask of the clusters merged into at this SNP during that batch
+  double* contrib;            // [pairs of the batch][nS]
+  double* d0p;                // [B][PSCL_SEED_SPLIT][nS]
+  int32_t* clust;
+  pscl_fmx_cell* cells;
+  int64_t P;
+  int32_t nS, base, nb, batch;
+};
+
+// log lk2 - log lk0 of one (cell pair, cluster) (sc_drop_seq.cpp:556-571), diagonals only on both sides
+__device__ __forceinline__ double fmx_seed_term(double ci0, double ci1, double ci2, double cj0, double cj1, double cj2, double h0, double h1, double h2) {
+  const double lk2 = ci0 * cj0 * h0 + ci1 * cj1 * h1 + ci2 * cj2 * h2;
+  const double lk0 = (ci0 * h0 + ci1 * h1 + ci2 * h2) * (cj0 * h0 + cj1 * h1 + cj2 * h2);  // sum_g sum_h ci[g] cj[h] h[g] h[h]
+  return log(lk2) - log(lk0);
+}
+
+template <int NSM>
+__global__ void __launch_bounds__(256) k_fmx_seed_dist(SeedBatchArgs a) {
+  __shared__ double s_w[8][NSM];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nS = a.nS;
+  const int b = blockIdx.x, q = blockIdx.y;
+  const int si = a.elig[a.base + b];
+  const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
+  const int64_t t0 = K * q / PSCL_SEED_SPLIT, t1 = K * (q + 1) / PSCL_SEED_SPLIT;
+  double* const out = a.contrib + (size_t)(a.epair[a.base + b] - a.epair[a.base]) * nS;
+  double sum[NSM];
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) sum[j] = 0.0;
+  for (int64_t t = t0 + tid; t < t1; t += 256) {
+    const int64_t p = pb + t;
+    const int32_t s = a.pair_snp[p];
+    const double af = a.snp_af[s];
+    const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
+    const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
+#pragma unroll
+    for (int j = 0; j < NSM; ++j) {
+      if (j < nS) {
+        const size_t e = (size_t)s * nS + j;
+        double c = 0.0;
+        if (a.present[e]) {
+          const double* cj = a.clust_gl + e * 9;
+          c = fmx_seed_term(ci0, ci1, ci2, cj[0], cj[4], cj[8], h0, h1, h2);
+        }
+        out[(size_t)t * nS + j] = c;
+        sum[j] += c;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], o);
+    if (lane == 0) s_w[warp][j] = sum[j];
+  }
+  __syncthreads();
+  if (tid < nS) {
+    double x = 0.0;
+    for (int w = 0; w < 8; ++w) x += s_w[w][tid];
+    a.d0p[((size_t)b * PSCL_SEED_SPLIT + q) * nS + tid] = x;
+  }
+}
+
+template <int NSM>
+__global__ void __launch_bounds__(1024, 1) k_fmx_seed_commit(SeedBatchArgs a) {
+  __shared__ double s_w[32][NSM], s_sc[NSM];
+  __shared__ int s_choice;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nS = a.nS;
+  const unsigned long long stamp = (unsigned long long)(a.batch + 1) << 32;
+  for (int b = 0; b < a.nb; ++b) {
+    const int si = a.elig[a.base + b];
+    const int64_t pb = a.cell_ptr[si], pe = a.cell_ptr[si + 1];
+    const double* const stored = a.contrib + (size_t)(a.epair[a.base + b] - a.epair[a.base]) * nS;
+    // ---- corrections at the SNPs earlier cells of this batch have merged into ----
+    double delta[NSM];
+#pragma unroll
+    for (int j = 0; j < NSM; ++j) delta[j] = 0.0;
+    for (int64_t p = pb + tid; p < pe; p += 1024) {
+      const int32_t s = a.pair_snp[p];
+      const unsigned long long w = a.dirty[s];
+      if ((w >> 32) != (stamp >> 32)) continue;
+      const unsigned mask = (unsigned)w;
+      const double af = a.snp_af[s];
+      const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
+      const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
+#pragma unroll
+      for (int j = 0; j < NSM; ++j) {
+        if (j < nS && ((mask >> j) & 1u)) {
+          const double* cj = a.clust_gl + ((size_t)s * nS + j) * 9;
+          delta[j] += fmx_seed_term(ci0, ci1, ci2, cj[0], cj[4], cj[8], h0, h1, h2) - stored[(size_t)(p - pb) * nS + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NSM; ++j) {
+      if (j < nS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) delta[j] += __shfl_xor_sync(0xffffffffu, delta[j], o);
+        if (lane == 0) s_w[warp][j] = delta[j];
+      }
+    }
+    __syncthreads();
+    if (tid < nS) {
+      double x = 0.0;
+      for (int q = 0; q < PSCL_SEED_SPLIT; ++q) x += a.d0p[((size_t)b * PSCL_SEED_SPLIT + q) * nS + tid];
+      double d = 0.0;
+      for (int w = 0; w < 32; ++w) d += s_w[w][tid];
+      s_sc[tid] = x + d;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = 0;
+      double bs = s_sc[0];
+      for (int j = 1; j < nS; ++j)
+        if (s_sc[j] > bs) { best = j; bs = s_sc[j]; }  // :238-241, first wins
+      s_choice = best;
+      a.clust[si] = best;
+      a.cells[si].clust = a.cells[si].init_clust = best;
+      a.cells[si].type = 0;
+    }
+    __syncthreads();
+    const int jstar = s_choice;
+    // ---- merge the cell into the chosen cluster (:248-251) and mark its SNPs ----
+    for (int64_t p = pb + tid; p < pe; p += 1024) {
+      const int32_t s = a.pair_snp[p];
+      const size_t e = (size_t)s * nS + jstar;
+      double gl[9], o[9];
+      double* cg = a.clust_gl + e * 9;
+#pragma unroll
+      for (int g = 0; g < 9; ++g) { gl[g] = cg[g]; o[g] = a.gl_soa[(size_t)g * a.P + p]; }
+      fmx_merge(gl, o);
+#pragma unroll
+      for (int g = 0; g < 9; ++g) cg[g] = gl[g];
+      a.present[e] = 1;
+      const unsigned long long w = a.dirty[s];
+      a.dirty[s] = (((w >> 32) == (stamp >> 32)) ? w : stamp) | (1ull << jstar);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void k_fmx_fill_f64(double* v, size_t n, double x) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = x;
@@ -925,7 +1091,8 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
       ctx->launches++;
       e = cudaMemsetAsync(s->present, 0, VS, ctx->stream);
     }
-    if (e == cudaSuccess) {
+    const bool serial = getenv("PSCL_SEED_SERIAL") != nullptr;  // the one-CTA chain (kept as the cross-check of the batched form)
+    if (e == cudaSuccess && serial) {
       SeedArgs a;
       a.order = s->order; a.score = score; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa;
       a.snp_af = plp->snp_af; a.clust_gl = s->clust_gl; a.present = s->present; a.clust = clust_dev; a.cells = s->cells;
@@ -933,6 +1100,48 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
       k_fmx_seed<<<1, 1024, 0, ctx->stream>>>(a);
       ctx->launches++;
       e = cudaGetLastError();
+    } else if (e == cudaSuccess) {
+      // cells that take part (:225-226), in seeding order, and the running pair count of their pileups
+      std::vector<int32_t> elig;
+      std::vector<int64_t> epair(1, 0);
+      elig.reserve(s->C);
+      for (int32_t i = 0; i < s->C; ++i) {
+        const int32_t si = h_order[i];
+        if ((double)i > (double)s->C * s->o.frac_init_clust) continue;
+        if (h_score[si] < s->o.singlet_score_thres) continue;
+        elig.push_back(si);
+        epair.push_back(epair.back() + (plp->h_cell_ptr[si + 1] - plp->h_cell_ptr[si]));
+      }
+      int B = 32;
+      if (const char* bv = getenv("PSCL_SEED_BATCH")) B = std::max(1, std::min(256, atoi(bv)));
+      const int n_elig = (int)elig.size();
+      int64_t max_pairs = 1;
+      for (int b0 = 0; b0 < n_elig; b0 += B) max_pairs = std::max(max_pairs, epair[std::min(n_elig, b0 + B)] - epair[b0]);
+      int32_t* d_elig = nullptr; int64_t* d_epair = nullptr; unsigned long long* d_dirty = nullptr; double *d_contrib = nullptr, *d_d0p = nullptr;
+      auto alloc = [&](void** d, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16); };
+      alloc((void**)&d_elig, sizeof(int32_t) * (size_t)std::max(n_elig, 1));
+      alloc((void**)&d_epair, sizeof(int64_t) * ((size_t)n_elig + 1));
+      alloc((void**)&d_dirty, sizeof(unsigned long long) * (size_t)std::max(s->V, 1));
+      alloc((void**)&d_contrib, sizeof(double) * (size_t)max_pairs * s->nS);
+      alloc((void**)&d_d0p, sizeof(double) * (size_t)B * PSCL_SEED_SPLIT * s->nS);
+      if (e == cudaSuccess && n_elig) e = cudaMemcpyAsync(d_elig, elig.data(), sizeof(int32_t) * n_elig, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_epair, epair.data(), sizeof(int64_t) * ((size_t)n_elig + 1), cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_dirty, 0, sizeof(unsigned long long) * (size_t)std::max(s->V, 1), ctx->stream);
+      SeedBatchArgs a;
+      a.elig = d_elig; a.epair = d_epair; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.snp_af = plp->snp_af;
+      a.clust_gl = s->clust_gl; a.present = s->present; a.dirty = d_dirty; a.contrib = d_contrib; a.d0p = d_d0p; a.clust = clust_dev;
+      a.cells = s->cells; a.P = s->P; a.nS = s->nS;
+      for (int b0 = 0, batch = 0; b0 < n_elig && e == cudaSuccess; b0 += B, ++batch) {
+        a.base = b0; a.nb = std::min(B, n_elig - b0); a.batch = batch;
+        const dim3 grid((unsigned)a.nb, PSCL_SEED_SPLIT);
+        if (s->nS <= 8) { k_fmx_seed_dist<8><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<8><<<1, 1024, 0, ctx->stream>>>(a); }
+        else if (s->nS <= 16) { k_fmx_seed_dist<16><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<16><<<1, 1024, 0, ctx->stream>>>(a); }
+        else { k_fmx_seed_dist<PSCL_FMX_MAX_CLUSTERS><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<PSCL_FMX_MAX_CLUSTERS><<<1, 1024, 0, ctx->stream>>>(a); }
+        ctx->launches += 2;
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // elig / epair are pageable sources
+      cudaFree(d_elig); cudaFree(d_epair); cudaFree(d_dirty); cudaFree(d_contrib); cudaFree(d_d0p);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h_order is a pageable source
   }

@@ -69,7 +69,7 @@ def main():
     if only:
         return main_only(only)
     main_all()
-    main_only({"demux_r2", "fmx_random"})
+    main_only({"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21"})
 
 
 def main_only(only):
@@ -89,7 +89,32 @@ def main_only(only):
         base(110, 3, 700, 200, 21, d)
         run_ref(d, ["freemuxlet", "--plp", "p", "--nsample", "3", "--randomize-singlet-score", "--seed", "11", "--frac-init-clust", "0.6",
                     "--out", "ref"])
-    unknown = only - {"demux_r2", "fmx_random"}
+    # 11. the benchmark's own kernel shape through the reference: 8 samples, hard calls (k_demux_default on dictionary-coded
+    # genotypes) ...
+    if "demux_gt8" in only:
+        d = fresh("demux_gt8")
+        s, sites, bcs = base(140, 8, 1500, 220, 23, d, allele2=0.02)
+        plpio.write_vcf(os.path.join(d, "g.vcf.gz"), sites, [f"D{j}" for j in range(8)], geno=s.geno)
+        run_ref(d, ["demuxlet", "--plp", "p", "--vcf", "g.vcf.gz", "--field", "GT", "--out", "ref"])
+    # 12. ... and 8 samples with soft posteriors (k_demux_default on gathered genotype rows), SNPs missing from the VCF
+    if "demux_gp8" in only:
+        d = fresh("demux_gp8")
+        s, sites, bcs = base(120, 8, 1400, 220, 24, d)
+        rng = np.random.default_rng(12)
+        gp = 0.85 * np.eye(3)[s.geno.T] + 0.15 * rng.dirichlet([1, 1, 1], size=(1400, 8))
+        keep = rng.random(1400) > 0.1
+        plpio.write_vcf(os.path.join(d, "g.vcf.gz"), sites, [f"D{j}" for j in range(8)], geno=s.geno, gp=gp, keep=keep)
+        run_ref(d, ["demuxlet", "--plp", "p", "--vcf", "g.vcf.gz", "--field", "GP", "--out", "ref"])
+    # 13. configs[3]'s shape through the reference: 64 samples, the 21-point alpha grid (k_demux_poly), a few droplets
+    if "demux_64x21" in only:
+        d = fresh("demux_64x21")
+        s, sites, bcs = base(24, 64, 1500, 260, 25, d)
+        plpio.write_vcf(os.path.join(d, "g.vcf.gz"), sites, [f"P{j:02d}" for j in range(64)], geno=s.geno)
+        argv = ["demuxlet", "--plp", "p", "--vcf", "g.vcf.gz", "--field", "GT"]
+        for i in range(21):
+            argv += ["--alpha", "%g" % (0.025 * i)]
+        run_ref(d, argv + ["--out", "ref"])
+    unknown = only - {"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21"}
     if unknown:
         sys.exit(f"cases {sorted(unknown)} are generated by the full run only")
 

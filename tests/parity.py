@@ -47,8 +47,32 @@ def _pair_key(j, k, a, alphas):
     return j, k, a
 
 
+def _doublet_rank_ties(rgrid, alphas, eps=1e-9):
+    """From the oracle's grid: (tie12, tie23) per cell.  Candidates are the live doublet entries with the two mirror
+    entries of an alpha == 0.5 pair counted ONCE (they are equal up to rounding, and which of the two the reference ranks
+    first is noise).  tie12: best and second-best CANDIDATE within eps (the argmax itself is a toss-up); tie23: the
+    second-best ENTRY (what the reference reports as its next doublet, cmd_cram_demuxlet.cpp:883-906) cannot be told from
+    the third-best entry unless that is its own mirror."""
+    C, nv, _, na = rgrid.shape
+    vals = []
+    for n in range(1, na):
+        g = rgrid[:, :, :, n]
+        if alphas[n] == 0.5:
+            iu = np.triu_indices(nv, 1)
+            vals.append(np.maximum(g[:, iu[0], iu[1]], g[:, iu[1], iu[0]]))  # one candidate per unordered pair
+        else:
+            off = ~np.eye(nv, dtype=bool)
+            vals.append(g[:, off])
+    v = np.sort(np.concatenate(vals, axis=1), axis=1)[:, ::-1]
+    scale = eps * np.maximum(1.0, np.abs(v[:, 0]))
+    tie12 = (v[:, 0] - v[:, 1]) <= scale if v.shape[1] > 1 else np.zeros(C, bool)
+    return tie12, scale
+
+
 def check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.02):
-    """out/ref: DEMUX_CELL_DTYPE arrays; grid/rgrid: [cell][j][k][n] (either may be None)."""
+    """out/ref: DEMUX_CELL_DTYPE arrays; grid/rgrid: [cell][j][k][n] (either may be None).
+    Every field of the record is compared: LLKs and posteriors within RTOL, droplet type and every sample id / alpha index
+    exactly (alpha == 0.5 pairs unordered), for all cells but the numerically tied ones, which are counted and listed."""
     assert len(out) == len(ref)
     nz = ref["n_snps"] > 0
     assert np.array_equal(out["n_snps"], ref["n_snps"])
@@ -60,12 +84,18 @@ def check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.02):
             live[:, :, n] = ~np.eye(nv, dtype=bool)
         assert_close(grid[:, live], rgrid[:, live], "llksAB live entries")
         assert np.all(np.isnan(grid[:, ~live])), "dead grid entries must be NaN"
-    for f in ("best_llk", "next_llk", "sng_best_llk", "sng_next_llk", "dbl_best_llk", "sum_llk", "sng_llk",
+    for f in ("best_llk", "next_llk", "sng_best_llk", "sng_next_llk", "dbl_best_llk", "dbl_next_llk", "sum_llk", "sng_llk",
               "sng_pp", "sng_only_pp", "best_pp"):
         assert_close(out[f][nz], ref[f][nz], f)
-    tied = _tied(ref) | ~nz
-    assert tied.mean() <= allow_tied_frac, f"too many numerically tied cells: {tied.mean()}"
-    ok = ~tied
+    tied = _tied(ref) & nz
+    tie12 = np.zeros(len(ref), bool)
+    if rgrid is not None:
+        tie12, _ = _doublet_rank_ties(rgrid, alphas)
+        tied |= tie12 & nz
+    frac = tied.sum() / max(int(nz.sum()), 1)
+    assert frac <= allow_tied_frac, (f"too many numerically tied cells: {int(tied.sum())} of {int(nz.sum())} "
+                                     f"(cells {np.flatnonzero(tied)[:20].tolist()})")
+    ok = nz & ~tied
     for f in ("type", "sng_best", "sng_next", "best_a", "dbl_best_a"):
         bad = np.flatnonzero(ok & (out[f] != ref[f]))
         assert bad.size == 0, f"{f} differs for cells {bad[:10]}: {out[f][bad[:10]]} vs {ref[f][bad[:10]]}"
@@ -74,8 +104,23 @@ def check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.02):
         rj, rk, _ = _pair_key(ref[pre + "_j"], ref[pre + "_k"], ref[af], alphas)
         bad = np.flatnonzero(ok & ((oj != rj) | (ok_ != rk)))
         assert bad.size == 0, f"{pre} pair differs for cells {bad[:10]}"
-    # NEXT: the second-best doublet is usually the mirror of the best at alpha 0.5; compare its LLK
-    # (checked above) and its ids as an unordered pair where the oracle has no near-tie for 2nd place
+    # NEXT.GUESS and the second-best doublet.  The reference's second-best doublet ENTRY is, at alpha 0.5, normally the
+    # mirror (k,j) of the best one; its LLK was compared above, its ids are compared as an unordered pair wherever the
+    # oracle's second entry is separated from the third (known from the grid).
+    if rgrid is not None:
+        C, nv, _, na = rgrid.shape
+        ent = np.concatenate([rgrid[:, :, :, n][:, ~np.eye(nv, dtype=bool)] for n in range(1, na)], axis=1)
+        ent = np.sort(ent, axis=1)[:, ::-1]
+        scale = 1e-9 * np.maximum(1.0, np.abs(ent[:, 0]))
+        third_close = (ent[:, 1] - ent[:, 2]) <= scale if ent.shape[1] > 2 else np.zeros(C, bool)
+        # the third entry may be the mirror-pair partner only when the best two were NOT mirrors of each other: rare; skip those
+        ok2 = ok & ~third_close
+        for pre, af in (("dbl_next", "dbl_next_a"), ("next", "next_a")):
+            oj, ok_, oa = _pair_key(out[pre + "_j"], out[pre + "_k"], out[af], alphas)
+            rj, rk, ra = _pair_key(ref[pre + "_j"], ref[pre + "_k"], ref[af], alphas)
+            bad = np.flatnonzero(ok2 & ((oj != rj) | (ok_ != rk) | (oa != ra)))
+            assert bad.size == 0, (f"{pre} guess differs for cells {bad[:10]}: ours {list(zip(oj[bad[:5]], ok_[bad[:5]], oa[bad[:5]]))} "
+                                   f"ref {list(zip(rj[bad[:5]], rk[bad[:5]], ra[bad[:5]]))}")
     return int(ok.sum())
 
 

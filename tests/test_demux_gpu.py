@@ -77,9 +77,9 @@ def test_poly_soft_genotypes_deep_pairs_and_big_cells(ctx):
     has = (rng.random(plp.n_snps) > 0.2).astype(np.uint8)
     alphas = [0.0, 0.05, 0.1, 0.2, 0.3, 0.4, 0.5]
     out, grid, ref, rgrid = _run_both(ctx, s2, gp, has, alphas, "poly")
-    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
+    check_demux_parity(out, grid, ref, rgrid, alphas)
     out, grid, ref, rgrid = _run_both(ctx, s2, gp, has, alphas, "general")
-    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
+    check_demux_parity(out, grid, ref, rgrid, alphas)
 
 
 def test_config4_shape_small(ctx):
@@ -89,7 +89,7 @@ def test_config4_shape_small(ctx):
     gp = synth.gt_to_gp(s.geno)
     for kernel in ("auto", "general"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas, kernel)
-        check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.2)
+        check_demux_parity(out, grid, ref, rgrid, alphas)
 
 
 def test_missing_genotypes_and_other_alleles(ctx):
@@ -127,7 +127,7 @@ def test_deep_pairs_and_empty_cells(ctx):
     s = synth.Synth(plp, geno, plp.snp_af, None, None, 9)
     for general in ("lane", "dict", "general", "poly"):
         out, grid, ref, rgrid = _run_both(ctx, s, gp, None, DEFAULT, general)
-        check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.3)
+        check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=0.06)  # 2 of 35: the one-pair cell and one 400-read cell are true ties
 
 
 @pytest.mark.parametrize("kernel", ["lane", "dict"])
@@ -360,7 +360,7 @@ def test_poly_shapes(ctx, nv, na):
     s = synth.make_pileup(C=30, nv=nv, V=900, kbar=150, seed=500 + nv)
     gp = synth.gt_to_gp(s.geno)
     out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas, "poly")
-    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
+    check_demux_parity(out, grid, ref, rgrid, alphas)
 
 
 @pytest.mark.parametrize("kernel", ["lane", "dict", "poly", "general"])
@@ -373,7 +373,7 @@ def test_degenerate_pileups(ctx, kernel):
     one = Pileup(1, V, [0, 1], [7], [0, 2], np.array([0, 1], np.uint8), np.array([30, 20], np.uint8), rng.uniform(0.1, 0.5, V))
     s1 = synth.Synth(one, None, None, None, None, 0)
     out, grid, ref, rgrid = _run_both(ctx, s1, gp, None, DEFAULT, kernel)
-    check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=1.0)
+    check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=1.0)  # ONE cell with ONE pair: everything ties
     empty = Pileup(3, V, [0, 0, 0, 0], np.zeros(0, np.int32), [0], np.zeros(0, np.uint8), np.zeros(0, np.uint8), rng.uniform(0.1, 0.5, V))
     ctx.demux_select_kernel(KERNELS[kernel])
     try:
@@ -428,10 +428,21 @@ def test_a_slice_that_never_arrives_is_reported_and_the_context_survives(built):
         again = c.demux_run(s.plp, gp, None, DEFAULT, compact=3)  # staged, flags intact
         del os.environ["PSCL_STAGES"]
         assert again.tobytes() == good.tobytes()
-        # device memory exhaustion (injected at every allocation of a run in turn) is reported as PSCL_ENOMEM, leaks
-        # nothing that matters and leaves the context usable
+    finally:
+        os.environ.pop("PSCL_STAGES", None)
+        c.close()
+
+
+def test_device_memory_exhaustion_is_reported_and_the_context_survives(built):
+    """Fault injection (pscl_debug_fail_alloc): an allocation failing anywhere inside a run comes back as PSCL_ENOMEM,
+    and the same context then produces the right records again."""
+    from popscle_b200 import Context, PsclError
+    s = synth.make_pileup(C=400, nv=4, V=2000, kbar=200, seed=92)
+    gp = synth.gt_to_gp(s.geno)
+    with Context(0) as c:
+        good = c.demux_run(s.plp, gp, None, DEFAULT, compact=3)
         hit = 0
-        for nth in range(1, 40):
+        for nth in range(1, 60):
             c.debug_fail_alloc(nth)
             try:
                 got = c.demux_run(s.plp, gp, None, DEFAULT, compact=3)
@@ -459,106 +470,3 @@ def test_a_slice_that_never_arrives_is_reported_and_the_context_survives(built):
                 c.debug_fail_alloc(0)
         assert hit >= 5
         assert c.fmx_run(s.plp, o)[0].tobytes() == fgood.tobytes()
-    finally:
-        os.environ.pop("PSCL_STAGES", None)
-    empty = synth.make_pileup(C=4, nv=2, V=50, kbar=20, seed=2)
-    empty.plp.cell_ptr[:] = 0
-    e = type(empty.plp)(4, 50, empty.plp.cell_ptr, empty.plp.pair_snp[:0], np.zeros(1, np.int64), empty.plp.read_allele[:0], empty.plp.read_qual[:0], None)
-    assert ctx.demux_run(e, synth.gt_to_gp(empty.geno), None, DEFAULT, compact=3).tobytes() == ctx.demux_run(e, synth.gt_to_gp(empty.geno), None, DEFAULT).tobytes()
-    for what in ("delta", "count"):
-        bad = synth.make_pileup(C=20, nv=3, V=200, kbar=60, seed=1)
-        first, d16, n8 = bad.plp.compact3()
-        if what == "delta":
-            d16[bad.plp.cell_ptr[5] + 1] = 60000
-        else:
-            n8[7] += 1
-        with pytest.raises(PsclError):
-            ctx.demux_run(bad.plp, synth.gt_to_gp(bad.geno), None, DEFAULT, compact=3)
-
-
-@pytest.mark.parametrize("nv,na", [(2, 2), (3, 3), (9, 5), (17, 9), (33, 17), (5, 32)])
-def test_poly_shapes(ctx, nv, na):
-    """every plane-count bucket of k_demux_poly (4/8/16/21/32) and sample counts that leave idle tile threads"""
-    alphas = [0.5 * i / (na - 1) for i in range(na)]
-    s = synth.make_pileup(C=30, nv=nv, V=900, kbar=150, seed=500 + nv)
-    gp = synth.gt_to_gp(s.geno)
-    out, grid, ref, rgrid = _run_both(ctx, s, gp, None, alphas, "poly")
-    check_demux_parity(out, grid, ref, rgrid, alphas, allow_tied_frac=0.3)
-
-
-@pytest.mark.parametrize("kernel", ["lane", "dict", "poly", "general"])
-def test_degenerate_pileups(ctx, kernel):
-    """one cell with one pair; no pair at all; no SNP with genotypes"""
-    from popscle_b200 import Pileup
-    nv, V = 4, 50
-    rng = np.random.default_rng(3)
-    gp = synth.gt_to_gp(rng.integers(0, 3, (nv, V)).astype(np.int8))
-    one = Pileup(1, V, [0, 1], [7], [0, 2], np.array([0, 1], np.uint8), np.array([30, 20], np.uint8), rng.uniform(0.1, 0.5, V))
-    s1 = synth.Synth(one, None, None, None, None, 0)
-    out, grid, ref, rgrid = _run_both(ctx, s1, gp, None, DEFAULT, kernel)
-    check_demux_parity(out, grid, ref, rgrid, DEFAULT, allow_tied_frac=1.0)
-    empty = Pileup(3, V, [0, 0, 0, 0], np.zeros(0, np.int32), [0], np.zeros(0, np.uint8), np.zeros(0, np.uint8), rng.uniform(0.1, 0.5, V))
-    ctx.demux_select_kernel(KERNELS[kernel])
-    try:
-        o = ctx.demux_run(empty, gp, None, DEFAULT)
-    finally:
-        ctx.demux_select_kernel(0)
-    assert len(o) == 3 and (o["n_snps"] == 0).all()
-    s = synth.make_pileup(C=20, nv=nv, V=V, kbar=20, seed=5)
-    out, grid, ref, rgrid = _run_both(ctx, s, gp, np.zeros(V, np.uint8), DEFAULT, kernel)
-    assert_close(out["sng_best_llk"], ref["sng_best_llk"], "no genotypes: singlet LLK")
-    assert_close(out["dbl_best_llk"], ref["dbl_best_llk"], "no genotypes: doublet LLK")
-
-
-def test_staged_run_falls_back_when_the_partial_grids_do_not_fit(ctx):
-    """a staged image can only be scored in one batch; with a small scratch budget pscl_demux_run must take
-    the plain upload instead of failing with PSCL_ESTATE."""
-    s = synth.make_pileup(C=3000, nv=8, V=4000, kbar=300, seed=91)
-    raw_gp = synth.gt_to_gp(s.geno)
-    ref = ctx.demux_run(s.plp, raw_gp, None, DEFAULT, compact=3)
-    os.environ["PSCL_STAGES"] = "3"
-    try:
-        staged = ctx.demux_run(s.plp, raw_gp, None, DEFAULT, compact=3)
-        ctx.set_partial_budget(1 << 20)  # 1 MiB: 1024 work items per batch, the pileup has 3000
-        small = ctx.demux_run(s.plp, raw_gp, None, DEFAULT, compact=3)
-    finally:
-        del os.environ["PSCL_STAGES"]
-        ctx.set_partial_budget(1 << 30)
-    assert staged.tobytes() == ref.tobytes() and small.tobytes() == ref.tobytes()
-
-
-def test_a_slice_that_never_arrives_is_reported_and_the_context_survives(built):
-    """Fault injection: the last slice's flag is withheld (PSCL_FAULT=drop_stage_flag); the staged kernel gives up after
-    PSCL_STAGE_TIMEOUT_MS, pscl_demux_run returns PSCL_ECUDA, and the same context scores the next call correctly."""
-    from popscle_b200 import Context, PsclError
-    s = synth.make_pileup(C=400, nv=4, V=2000, kbar=200, seed=92)
-    gp = synth.gt_to_gp(s.geno)
-    os.environ["PSCL_STAGE_TIMEOUT_MS"] = "50"
-    try:
-        c = Context(0)
-    finally:
-        del os.environ["PSCL_STAGE_TIMEOUT_MS"]
-    try:
-        good = c.demux_run(s.plp, gp, None, DEFAULT, compact=3)
-        os.environ["PSCL_STAGES"] = "3"
-        os.environ["PSCL_FAULT"] = "drop_stage_flag"
-        try:
-            with pytest.raises(PsclError) as ei:
-                c.demux_run(s.plp, gp, None, DEFAULT, compact=3)
-            assert ei.value.code == -3 and "never reached the device" in str(ei.value)
-        finally:
-            del os.environ["PSCL_FAULT"]
-        again = c.demux_run(s.plp, gp, None, DEFAULT, compact=3)  # staged, flags intact
-        del os.environ["PSCL_STAGES"]
-        assert again.tobytes() == good.tobytes()
-        # device memory exhaustion is reported as PSCL_ENOMEM and leaves the context usable
-        with pytest.raises(PsclError) as ei:
-            c.demux_set_geno(np.zeros((1, 2, 3)), None, 1) or c.lib.pscl_set_partial_budget(c.h, 1 << 62) or c.demux_keep_grid(True) or \
-                c.demux_run(synth.make_pileup(C=20000, nv=64, V=2000, kbar=60, seed=93).plp, np.full((2000, 64, 3), 1 / 3.), None,
-                            [i / 40 for i in range(21)], want_grid=True)
-        assert ei.value.code in (-4, -3)
-        c.demux_keep_grid(False)
-        assert c.demux_run(s.plp, gp, None, DEFAULT, compact=3).tobytes() == good.tobytes()
-    finally:
-        os.environ.pop("PSCL_STAGES", None)
-        c.close()

@@ -47,7 +47,7 @@ def test_config2_kernels_agree_and_match_the_oracle_sample(ctx, cfg2):
     rng = np.random.default_rng(2)
     for c0 in rng.integers(0, plp.n_cells - 25, 6):
         ref, rgrid = orc.demux(plp, gp, None, DEFAULT, 0.5, int(c0), int(c0) + 25, want_grid=True, n_threads=8)
-        check_demux_parity(rec[c0:c0 + 25], grid[c0:c0 + 25], ref, rgrid, DEFAULT, allow_tied_frac=0.1)
+        check_demux_parity(rec[c0:c0 + 25], grid[c0:c0 + 25], ref, rgrid, DEFAULT)
     # the synthetic truth: singlets go to their donor, doublets are found
     sng = rec["type"] == 0
     assert sng.mean() > 0.85 and (rec["sng_best"][sng] == s.truth_d1[sng]).mean() > 0.999
