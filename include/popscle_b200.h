@@ -134,8 +134,7 @@ typedef struct pscl_demux_cell {
  * freemuxlet — replaces cmd_cram_freemux2.cpp:117-163 (stage 1), :184-261 (sort + greedy
  * seeding), :277-288 (cluster pileup build), :373-605 (EM) ; `mode_old` selects the EM variant
  * of cmd_cram_freemuxlet.cpp:456-653 (geno_error only on the last iteration, no early stop,
- * cluster ids not reset) — its pairwise/vote seeding (:184-346) is NOT implemented, so old
- * mode needs init_clust.
+ * cluster ids not reset) and its pairwise/vote seeding (:165-346; see bf_thres / iter_init below).
  * ------------------------------------------------------------------------------------------ */
 typedef struct pscl_fmx_opts {
   int32_t n_clusters;         /* --nsample                                                      */
@@ -151,6 +150,13 @@ typedef struct pscl_fmx_opts {
    * before the droplets are sorted for the greedy seeding.  0 = off.                             */
   int32_t randomize_singlet_score;
   int32_t seed;               /* --seed                                                         */
+  /* ABI 6: freemuxlet-old's own seeding (cmd_cram_freemuxlet.cpp:165-346), used when mode_old is set and there is no
+   * init_clust or iter_init > 0: the pairwise Bayes-factor matrix over the shared SNPs of every two droplets (on the
+   * device), votes of the already clustered droplets (:245-296) and, when iter_init > 0, ten refinement sweeps in
+   * std::random_shuffle order (:300-346) — on the un-seeded libc rand() stream, as the reference.                   */
+  double bf_thres;            /* --bf-thres, default 5.41 (cmd_cram_freemuxlet.cpp:22)          */
+  int32_t iter_init;          /* --iter-init, default 10; 0 skips the sweeps                    */
+  int32_t keep_init_missing;  /* --keep-init-missing (:336)                                     */
 } pscl_fmx_opts;
 
 typedef struct pscl_fmx_cell {

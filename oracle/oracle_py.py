@@ -48,7 +48,8 @@ class OFmxOpts(C.Structure):
     _fields_ = [("n_clusters", C.c_int32), ("doublet_prior", C.c_double), ("geno_error", C.c_double),
                 ("max_iter", C.c_int32), ("early_stop", C.c_int32), ("frac_init_clust", C.c_double),
                 ("singlet_score_thres", C.c_double), ("mode_old", C.c_int32),
-                ("randomize_singlet_score", C.c_int32), ("seed", C.c_int32)]
+                ("randomize_singlet_score", C.c_int32), ("seed", C.c_int32),
+                ("bf_thres", C.c_double), ("iter_init", C.c_int32), ("keep_init_missing", C.c_int32)]
 
 
 class OFmxResult(C.Structure):
@@ -146,9 +147,12 @@ def fmx_merge(gls_a, cnt_a, ld_a, gls_b, cnt_b, ld_b):
 
 
 def fmx_opts(n_clusters, doublet_prior=0.5, geno_error=0.1, max_iter=10, early_stop=True, frac_init_clust=1.0,
-             singlet_score_thres=-1e300, mode_old=False, randomize_singlet_score=False, seed=0):
+             singlet_score_thres=-1e300, mode_old=False, randomize_singlet_score=False, seed=0, bf_thres=5.41, iter_init=0,
+             keep_init_missing=False):
+    """iter_init > 0 (the reference's default is 10) together with mode_old runs freemuxlet-old's own vote seeding."""
     return OFmxOpts(n_clusters, doublet_prior, geno_error, max_iter, int(early_stop), frac_init_clust,
-                    singlet_score_thres, int(mode_old), int(randomize_singlet_score), int(seed))
+                    singlet_score_thres, int(mode_old), int(randomize_singlet_score), int(seed), bf_thres, int(iter_init),
+                    int(keep_init_missing))
 
 
 def fmx_run(plp, opts, init_clust=None, want_clusters=False, want_pair_gl=False, want_llk=False, n_threads=1):

@@ -420,7 +420,101 @@ int orc_fmx_run(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* ini
     }
   }
   for (int32_t c = 0; c < C; ++c) { clusts[c] = -1; types[c] = -1; order[c] = c; }
-  if (init_clust) { /* :198-216 */
+  if (o->mode_old && (!init_clust || o->iter_init > 0)) {
+    /* freemuxlet-old: pairwise Bayes factors + votes (cmd_cram_freemuxlet.cpp:165-346).  The reference never seeds
+     * rand(): glibc's default stream (seed 1), consumed nS values per visited droplet (:259, :312) and n-1 per
+     * std::random_shuffle (:304; libstdc++: j = rand() % (i + 1) for i = 1..n-1, swap if i != j). */
+    srand(1); /* what a fresh process starts with: every reference run draws the same numbers */
+    g_sort_scores = scores;
+    qsort(order, C, sizeof(int32_t), cmp_drop); /* :166-171 */
+    /* SNP-major lists (snp_cell_plps, :113: std::map keyed by cell id -> ascending cell id) */
+    int64_t* sptr = (int64_t*)calloc((size_t)V + 1, sizeof(int64_t));
+    int64_t* spair = (int64_t*)malloc(sizeof(int64_t) * (P > 0 ? P : 1));
+    int32_t* pcell = (int32_t*)malloc(sizeof(int32_t) * (P > 0 ? P : 1));
+    for (int64_t p = 0; p < P; ++p) sptr[plp->pair_snp[p] + 1]++;
+    for (int32_t v = 0; v < V; ++v) sptr[v + 1] += sptr[v];
+    {
+      int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * ((size_t)V + 1));
+      memcpy(fill, sptr, sizeof(int64_t) * ((size_t)V + 1));
+      for (int32_t c = 0; c < C; ++c)
+        for (int64_t p = plp->cell_ptr[c]; p < plp->cell_ptr[c + 1]; ++p) { pcell[p] = c; spair[fill[plp->pair_snp[p]]++] = p; }
+      free(fill);
+    }
+    /* dropDs[i][j], j < i (:174, :187-189): llk0 / llk2 only (nsnps / nread1 / nread2 feed --aux-files alone) */
+    double* d0 = (double*)calloc((size_t)C * C, sizeof(double));
+    double* d2 = (double*)calloc((size_t)C * C, sizeof(double));
+    for (int32_t v = 0; v < V; ++v) { /* :190-222 */
+      double af = plp->snp_af[v], gps[3];
+      gps[0] = (1.0 - af) * (1.0 - af); gps[1] = 2.0 * af * (1.0 - af); gps[2] = af * af;
+      for (int64_t a = sptr[v]; a < sptr[v + 1]; ++a) {
+        const double* glis = pair_gl + spair[a] * 9;
+        for (int64_t b = sptr[v]; b < a; ++b) {
+          const double* gljs = pair_gl + spair[b] * 9;
+          double lk0 = 0, lk2 = 0;
+          for (int gi = 0; gi < 3; ++gi) {
+            lk2 += (glis[gi * 3 + gi] * gljs[gi * 3 + gi] * gps[gi]);
+            for (int gj = 0; gj < 3; ++gj) lk0 += (glis[gi * 3 + gi] * gljs[gj * 3 + gj] * gps[gi] * gps[gj]);
+          }
+          size_t e = (size_t)pcell[spair[a]] * C + pcell[spair[b]];
+          d2[e] += log(lk2); d0[e] += log(lk0);
+        }
+      }
+    }
+#define DD(i, j) ((i) > (j) ? (size_t)(i) * C + (j) : (size_t)(j) * C + (i))
+    double* votes = (double*)malloc(sizeof(double) * nS);
+    if (init_clust) { /* :227-243 */
+      for (int32_t c = 0; c < C; ++c) clusts[c] = init_clust[c] >= 0 ? init_clust[c] : -1;
+    } else { /* :245-296 */
+      for (int32_t i = 0; i < C; ++i) {
+        int32_t si = order[i];
+        if (i > C * o->frac_init_clust) continue; /* :248 */
+        for (int j = 0; j < nS; ++j) votes[j] = rand() / (RAND_MAX + 1.) / 1000.; /* :258-260 */
+        for (int32_t j = 0; j < i; ++j) {
+          int32_t sj = order[j];
+          size_t e = DD(si, sj);
+          if (d0[e] - d2[e] > o->bf_thres) votes[clusts[sj]] -= 1.0;      /* :275-277 */
+          else if (d2[e] - d0[e] > o->bf_thres) votes[clusts[sj]] += 1.0; /* :278-280 */
+        }
+        int elected = 0;
+        double maxvote = votes[0];
+        for (int j = 1; j < nS; ++j)
+          if (maxvote < votes[j]) { elected = j; maxvote = votes[j]; } /* :282-289 */
+        clusts[si] = elected;
+      }
+    }
+    if (o->iter_init > 0) { /* :300-346: always ten sweeps */
+      int32_t* orand = (int32_t*)malloc(sizeof(int32_t) * (C > 0 ? C : 1));
+      for (int sweep = 0; sweep < 10; ++sweep) {
+        for (int32_t i = 0; i < C; ++i) orand[i] = i;
+        for (int32_t i = 1; i < C; ++i) { /* std::random_shuffle (libstdc++) */
+          int32_t j = rand() % (i + 1);
+          if (i != j) { int32_t t = orand[i]; orand[i] = orand[j]; orand[j] = t; }
+        }
+        for (int32_t i = 0; i < C; ++i) {
+          int32_t si = orand[i];
+          for (int j = 0; j < nS; ++j) votes[j] = rand() / (RAND_MAX + 1.) / 1000.;
+          for (int32_t j = 0; j < C; ++j) {
+            if (si != j) {
+              size_t e = DD(si, j);
+              double bf = d2[e] - d0[e];
+              if (clusts[j] >= 0) {
+                if (bf > o->bf_thres) ++votes[clusts[j]];
+                else if (bf < 0 - o->bf_thres) --votes[clusts[j]];
+              }
+            }
+          }
+          int elected = 0;
+          double maxvote = votes[0];
+          for (int j = 1; j < nS; ++j)
+            if (maxvote < votes[j]) { elected = j; maxvote = votes[j]; }
+          if ((clusts[si] >= 0) || (o->keep_init_missing == 0)) clusts[si] = elected; /* :336-340 */
+        }
+      }
+      free(orand);
+    }
+#undef DD
+    free(votes); free(d0); free(d2); free(sptr); free(spair); free(pcell);
+  } else if (init_clust) { /* :198-216 */
     for (int32_t c = 0; c < C; ++c)
       if (init_clust[c] >= 0) { clusts[c] = init_clust[c]; types[c] = 0; }
   } else { /* :184-189, :217-261 */

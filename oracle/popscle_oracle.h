@@ -52,6 +52,10 @@ typedef struct orc_fmx_opts {
   double frac_init_clust, singlet_score_thres;
   int32_t mode_old;
   int32_t randomize_singlet_score, seed; /* cmd_cram_freemux2.cpp:164-181 */
+  /* freemuxlet-old's own seeding (cmd_cram_freemuxlet.cpp:184-346), used when mode_old and (no init_clust or iter_init > 0) */
+  double bf_thres;            /* --bf-thres, default 5.41 (:22) */
+  int32_t iter_init;          /* --iter-init, default 10: > 0 runs the ten vote-refinement sweeps (:300) */
+  int32_t keep_init_missing;  /* --keep-init-missing (:336) */
 } orc_fmx_opts;
 
 /* layout-identical to pscl_fmx_cell */

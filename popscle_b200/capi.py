@@ -59,7 +59,8 @@ class CFmxOpts(C.Structure):
     _fields_ = [("n_clusters", C.c_int32), ("doublet_prior", C.c_double), ("geno_error", C.c_double),
                 ("max_iter", C.c_int32), ("early_stop", C.c_int32), ("frac_init_clust", C.c_double),
                 ("singlet_score_thres", C.c_double), ("mode_old", C.c_int32),
-                ("randomize_singlet_score", C.c_int32), ("seed", C.c_int32)]
+                ("randomize_singlet_score", C.c_int32), ("seed", C.c_int32),
+                ("bf_thres", C.c_double), ("iter_init", C.c_int32), ("keep_init_missing", C.c_int32)]
 
 
 class CMultiTiming(C.Structure):
@@ -433,9 +434,13 @@ class Context:
     # ---- freemuxlet ----
     @staticmethod
     def fmx_opts(n_clusters: int, doublet_prior=0.5, geno_error=0.1, max_iter=10, early_stop=True,
-                 frac_init_clust=1.0, singlet_score_thres=-1e300, mode_old=False, randomize_singlet_score=False, seed=0) -> CFmxOpts:
+                 frac_init_clust=1.0, singlet_score_thres=-1e300, mode_old=False, randomize_singlet_score=False, seed=0,
+                 bf_thres=5.41, iter_init=0, keep_init_missing=False) -> CFmxOpts:
+        """iter_init > 0 (the reference's default is 10) or a missing init_clust, together with mode_old, runs
+        freemuxlet-old's own pairwise / vote seeding."""
         return CFmxOpts(n_clusters, doublet_prior, geno_error, max_iter, int(early_stop), frac_init_clust,
-                        singlet_score_thres, int(mode_old), int(randomize_singlet_score), int(seed))
+                        singlet_score_thres, int(mode_old), int(randomize_singlet_score), int(seed), bf_thres, int(iter_init),
+                        int(keep_init_missing))
 
     def fmx_run(self, plp: Pileup, opts: CFmxOpts, init_clust: np.ndarray | None = None, want_clusters=False,
                 compact: bool = False):

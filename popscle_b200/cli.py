@@ -145,9 +145,6 @@ def _freemux(argv, old, engine=None):
     if old:
         # cmd_cram_freemuxlet.cpp:83 never copies the filter flags into the loader: library defaults apply
         L = plpio.load_plp(o["plp"], None)
-        if not o["init-cluster"] or o["iter-init"] != 0:
-            raise UsageError("freemuxlet-old: the pairwise-distance vote seeding (cmd_cram_freemuxlet.cpp:184-346, libc rand()) "
-                             "is not implemented; pass --init-cluster FILE --iter-init 0")
     else:
         L = plpio.load_plp(o["plp"], None, min_bq=o["min-BQ"], cap_bq=o["cap-BQ"], min_read=o["min-total"], min_umi=o["min-umi"],
                            min_snp=o["min-snp"], group_list=_read_list(o["group-list"]) if o["group-list"] else None)
@@ -168,7 +165,8 @@ def _freemux(argv, old, engine=None):
     try:
         opts = eng.fmx_opts(nS, doublet_prior=o["doublet-prior"], geno_error=o["geno-error"], max_iter=10, early_stop=True,
                             frac_init_clust=o["frac-init-clust"], singlet_score_thres=-1e300, mode_old=old,
-                            randomize_singlet_score=bool(o.get("randomize-singlet-score", False)), seed=int(o.get("seed", 0) or 0))
+                            randomize_singlet_score=bool(o.get("randomize-singlet-score", False)), seed=int(o.get("seed", 0) or 0),
+                            **(dict(bf_thres=o["bf-thres"], iter_init=o["iter-init"], keep_init_missing=o["keep-init-missing"]) if old else {}))
         cells, res, gl, cnt = eng.fmx_run(L.plp, opts, init, want_clusters=True)
     finally:
         if own:

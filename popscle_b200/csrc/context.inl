@@ -368,7 +368,9 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     return e;
   };
   cudaError_t e = cudaSuccess;
-#define UP(field, src, bytes) do { if (e == cudaSuccess) e = up((void**)&p->field, src, bytes); } while (0)
+  const char* where = "";  // the first step that failed (named in the error message)
+#define UP(field, src, bytes) do { if (e == cudaSuccess) { e = up((void**)&p->field, src, bytes); if (e != cudaSuccess) where = #field; } } while (0)
+#define STEP(name) do { if (e != cudaSuccess && !*where) where = name; } while (0)
   UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
   uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr;
   void* d_scan_tmp = nullptr;
@@ -379,6 +381,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt + P, 0, 1, ctx->stream);
     if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(d_cnt, h->pair_nreads8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
+    STEP("pair_nreads8 / pair_rd");
   } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
   else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
   if (packed) {
@@ -387,6 +390,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     if (e == cudaSuccess) e = up((void**)&d_al, h->read_allele, (size_t)N);
     if (e == cudaSuccess) e = up((void**)&d_q, h->read_qual, (size_t)N);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
+    STEP("read_allele / read_qual");
   }
   if (dsnp) {  // ABI 3: 16-bit SNP gaps, decoded per cell
     if (e == cudaSuccess) e = up((void**)&p->d_first, h->cell_first_snp, sizeof(int32_t) * C);
@@ -407,11 +411,13 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   } else {
     UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
   }
+  STEP("pair_snp_delta16 / pair_snp");
   if (h->snp_af) UP(snp_af, h->snp_af, sizeof(double) * V);
   const auto tr1 = tnow(false);
 
   // ---- 2. work items (host; overlaps the copies) -------------------------------------------------------
   if (e == cudaSuccess) e = plp_make_items(ctx, p, h->cell_ptr);
+  STEP("work items");
   const auto tr2 = tnow(false);
 #undef UP
   // ---- 2b. staged image: the gaps go last, slice by slice on the copy stream, a flag word behind each slice ----------
@@ -464,10 +470,12 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
+  STEP("decode / scan / checks (launch)");
   int bad = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, p->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   // the host vectors above are pageable sources of async copies: drain before they go out of scope
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  STEP("drain (a copy or kernel of the upload failed on the device)");
   cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp);
   if (p->n_stages == 0) { cudaFree(p->d_delta); cudaFree(p->d_first); p->d_delta = nullptr; p->d_first = nullptr; }
   if (trace) {
@@ -480,7 +488,10 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   }
   if (e != cudaSuccess) {
     pscl_plp_free(ctx, p);
-    return pscl_fail(ctx, e == cudaErrorMemoryAllocation ? PSCL_ENOMEM : PSCL_ECUDA, "pileup upload failed: %s", cudaGetErrorString(e));
+    size_t mf = 0, mt = 0;
+    cudaMemGetInfo(&mf, &mt);
+    return pscl_fail(ctx, e == cudaErrorMemoryAllocation ? PSCL_ENOMEM : PSCL_ECUDA, "pileup upload failed at %s: %s (P=%lld N=%lld, device memory %zu of %zu MiB free)",
+                     where, cudaGetErrorString(e), (long long)P, (long long)N, mf >> 20, mt >> 20);
   }
   cudaFree(p->scratch_h2d);
   p->scratch_h2d = nullptr;

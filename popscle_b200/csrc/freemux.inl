@@ -523,6 +523,119 @@ __global__ void __launch_bounds__(1024, 1) k_fmx_seed_commit(SeedBatchArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// freemuxlet-old seeding: pairwise Bayes factors (cmd_cram_freemuxlet.cpp:174-222) on the device
+// ------------------------------------------------------------------------------------------------
+// dropDs[i][j] (j < i) accumulates, over the SNPs both droplets cover in ascending SNP order, log lk2 and log lk0 of the
+// two droplets' diagonal GLs.  The votes (:245-346) only ever compare llk2 - llk0 with +-bf_thres, so the device keeps two
+// bits per pair: 1 = "same donor" (llk2 - llk0 > thres), 2 = "different" (llk0 - llk2 > thres), 0 = undecided.
+// One WARP per droplet i walks i's SNPs in ascending order; the 32 lanes take the other droplets of that SNP's list
+// (SNP-major view), so every dropDs[i][j] receives its terms in the reference's order; the row's running sums live in a
+// per-warp scratch row in global memory (L2).  No C x C matrix of doubles exists anywhere: C^2/4 bytes of trits.
+struct PairwiseArgs {
+  const int64_t* cell_ptr;
+  const int32_t* pair_snp;
+  const double* gl_soa;
+  const double* snp_af;
+  const int64_t* snp_ptr;
+  const uint32_t* snp_pair;
+  const int32_t* pair_cell;
+  double* scratch;   // [warps][2][C]
+  uint32_t* trit;    // [C][W] 16 two-bit entries per word; row i holds j < i after this kernel
+  int* counter;
+  int64_t P;
+  int32_t C, W;
+  double thres;
+};
+__global__ void __launch_bounds__(512) k_fmx_pairwise(PairwiseArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  double* const acc2 = a.scratch + (size_t)gw * 2 * a.C;
+  double* const acc0 = acc2 + a.C;
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(a.counter, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= a.C) break;
+    const int i = a.C - 1 - w;  // long rows first
+    for (int j = lane; j < i; j += 32) { acc2[j] = 0.0; acc0[j] = 0.0; }
+    __syncwarp();
+    for (int64_t p = a.cell_ptr[i]; p < a.cell_ptr[i + 1]; ++p) {
+      const int32_t s = a.pair_snp[p];
+      const double af = a.snp_af[s];
+      double gps[3];
+      gps[0] = __dmul_rn(1.0 - af, 1.0 - af); gps[1] = __dmul_rn(__dmul_rn(2.0, af), 1.0 - af); gps[2] = __dmul_rn(af, af);
+      const double gi[3] = {a.gl_soa[p], a.gl_soa[(size_t)4 * a.P + p], a.gl_soa[(size_t)8 * a.P + p]};
+      const int64_t e = a.snp_ptr[s + 1];
+      for (int64_t t = a.snp_ptr[s] + lane; t < e; t += 32) {
+        const uint32_t q = a.snp_pair[t];
+        const int j = a.pair_cell[q];
+        if (j >= i) break;  // the list is in ascending droplet order (:196 `jt != it`)
+        const double gj[3] = {a.gl_soa[q], a.gl_soa[(size_t)4 * a.P + q], a.gl_soa[(size_t)8 * a.P + q]};
+        double lk0 = 0.0, lk2 = 0.0;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {  // :204-209, the reference's order of operations, no contraction
+          lk2 = __dadd_rn(lk2, __dmul_rn(__dmul_rn(gi[g], gj[g]), gps[g]));
+#pragma unroll
+          for (int h = 0; h < 3; ++h) lk0 = __dadd_rn(lk0, __dmul_rn(__dmul_rn(__dmul_rn(gi[g], gj[h]), gps[g]), gps[h]));
+        }
+        acc2[j] += log(lk2);
+        acc0[j] += log(lk0);
+      }
+      __syncwarp();  // the next SNP may hand droplet j to another lane
+    }
+    uint32_t* row = a.trit + (size_t)i * a.W;
+    for (int wd = lane; wd * 16 < i; wd += 32) {
+      uint32_t bits = 0;
+      for (int k = 0; k < 16; ++k) {
+        const int j = wd * 16 + k;
+        if (j < i) {
+          const double l2 = acc2[j], l0 = acc0[j];
+          const uint32_t t = (l0 - l2 > a.thres) ? 2u : (l2 - l0 > a.thres) ? 1u : 0u;  // :275-280
+          bits |= t << (2 * k);
+        }
+      }
+      row[wd] = bits;
+    }
+    __syncwarp();
+  }
+}
+// fills the upper triangle from the lower one (row i, j > i  <-  row j, column i)
+__global__ void k_fmx_trit_symmetrize(uint32_t* trit, int32_t C, int32_t W) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)C * W) return;
+  const int i = (int)(idx / W), wd = (int)(idx - (int64_t)i * W);
+  if (wd * 16 + 15 <= i) return;  // entirely in the lower triangle
+  uint32_t bits = trit[idx];
+  for (int k = 0; k < 16; ++k) {
+    const int j = wd * 16 + k;
+    if (j > i && j < C) {
+      const uint32_t t = (trit[(size_t)j * W + (i >> 4)] >> (2 * (i & 15))) & 3u;
+      bits = (bits & ~(3u << (2 * k))) | (t << (2 * k));
+    } else if (j >= i) bits &= ~(3u << (2 * k));
+  }
+  trit[idx] = bits;
+}
+__global__ void k_fmx_pair_cell(const int64_t* __restrict__ cell_ptr, int32_t C, int64_t P, int32_t* __restrict__ pair_cell) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int lo = 0, hi = C;  // largest c with cell_ptr[c] <= p
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cell_ptr[mid] <= p) lo = mid; else hi = mid;
+  }
+  pair_cell[p] = lo;
+}
+// clusters decided on the host -> cell records, clust[]
+__global__ void k_fmx_set_clusters(const int32_t* __restrict__ cl, int32_t C, pscl_fmx_cell* __restrict__ cells, int32_t* __restrict__ clust) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int v = cl[c];
+  cells[c].clust = cells[c].init_clust = v;
+  cells[c].type = v >= 0 ? 0 : -1;
+  clust[c] = v;
+}
+
 __global__ void k_fmx_fill_f64(double* v, size_t n, double x) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = x;
@@ -1054,6 +1167,106 @@ static void fmx_sort_order(const std::vector<double>& score, std::vector<int32_t
   });
 }
 
+// freemuxlet-old's seeding (cmd_cram_freemuxlet.cpp:165-346): the Bayes-factor trits on the device, the votes on the host
+// in the reference's own order and on its own random numbers (glibc rand() from its default seed; std::random_shuffle of
+// libstdc++ draws rand() % (i + 1) for i = 1..n-1) — the vote loops are a Gauss-Seidel sweep over the droplets and cost
+// C^2 two-bit look-ups each, which is minutes on the host only beyond ~50k droplets (the reference's own matrix of
+// doubles would need 40 GB there).
+static int fmx_seed_old(pscl_ctx* ctx, pscl_fmx_state* s, const double* score_dev, const int32_t* init_clust_dev, int32_t* clust_dev) {
+  const pscl_plp* plp = s->plp;
+  const int32_t C = s->C, nS = s->nS, W = (C + 15) / 16;
+  const int64_t P = s->P;
+  std::vector<double> h_score(C);
+  std::vector<int32_t> order(C), clusts(C, -1);
+  PSCL_CUDA(ctx, cudaMemcpyAsync(h_score.data(), score_dev, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (init_clust_dev) PSCL_CUDA(ctx, cudaMemcpyAsync(clusts.data(), init_clust_dev, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, ctx->stream));
+  // ---- pairwise trits ----
+  int32_t* d_pair_cell = nullptr; uint32_t* d_trit = nullptr; double* d_scratch = nullptr; int* d_counter = nullptr; int32_t* d_cl = nullptr;
+  const int warps_per_cta = 16, ctas = ctx->sm_count * 2, n_warps = warps_per_cta * ctas;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** d, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16); };
+  alloc((void**)&d_pair_cell, sizeof(int32_t) * (size_t)(P ? P : 1));
+  alloc((void**)&d_trit, sizeof(uint32_t) * (size_t)C * W);
+  alloc((void**)&d_scratch, sizeof(double) * 2 * (size_t)C * n_warps);
+  alloc((void**)&d_counter, sizeof(int));
+  alloc((void**)&d_cl, sizeof(int32_t) * (size_t)C);
+  std::vector<uint32_t> trit((size_t)C * W);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_trit, 0, sizeof(uint32_t) * (size_t)C * W, ctx->stream);
+  if (e == cudaSuccess) {
+    if (P > 0) k_fmx_pair_cell<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(plp->cell_ptr, C, P, d_pair_cell);
+    PairwiseArgs a;
+    a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.snp_af = plp->snp_af; a.snp_ptr = s->snp_ptr;
+    a.snp_pair = s->snp_pair; a.pair_cell = d_pair_cell; a.scratch = d_scratch; a.trit = d_trit; a.counter = d_counter;
+    a.P = P; a.C = C; a.W = W; a.thres = s->o.bf_thres;
+    k_fmx_pairwise<<<ctas, warps_per_cta * 32, 0, ctx->stream>>>(a);
+    k_fmx_trit_symmetrize<<<FMX_GRID((int64_t)C * W, 256), 256, 0, ctx->stream>>>(d_trit, C, W);
+    ctx->launches += 3;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(trit.data(), d_trit, sizeof(uint32_t) * (size_t)C * W, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) {
+    auto tr = [&](int32_t i, int32_t j) { return (trit[(size_t)i * W + (j >> 4)] >> (2 * (j & 15))) & 3u; };
+    fmx_sort_order(h_score, order);  // :166-171
+    srand(1);  // the reference never seeds: every run of it draws glibc's default stream
+    std::vector<double> votes(nS);
+    if (!init_clust_dev) {  // :245-296
+      for (int32_t i = 0; i < C; ++i) {
+        const int32_t si = order[i];
+        if ((double)i > (double)C * s->o.frac_init_clust) continue;  // :248
+        for (int j = 0; j < nS; ++j) votes[j] = rand() / (RAND_MAX + 1.) / 1000.;
+        for (int32_t j = 0; j < i; ++j) {
+          const int32_t sj = order[j];
+          const uint32_t t = tr(si, sj);
+          if (t == 2u) votes[clusts[sj]] -= 1.0;
+          else if (t == 1u) votes[clusts[sj]] += 1.0;
+        }
+        int elected = 0;
+        double maxvote = votes[0];
+        for (int j = 1; j < nS; ++j)
+          if (maxvote < votes[j]) { elected = j; maxvote = votes[j]; }
+        clusts[si] = elected;
+      }
+    }
+    if (s->o.iter_init > 0) {  // :300-346, always ten sweeps
+      std::vector<int32_t> orand(C);
+      for (int sweep = 0; sweep < 10; ++sweep) {
+        for (int32_t i = 0; i < C; ++i) orand[i] = i;
+        for (int32_t i = 1; i < C; ++i) {  // std::random_shuffle (libstdc++)
+          const int32_t j = rand() % (i + 1);
+          if (i != j) std::swap(orand[i], orand[j]);
+        }
+        for (int32_t i = 0; i < C; ++i) {
+          const int32_t si = orand[i];
+          for (int j = 0; j < nS; ++j) votes[j] = rand() / (RAND_MAX + 1.) / 1000.;
+          const uint32_t* row = trit.data() + (size_t)si * W;
+          for (int32_t j = 0; j < C; ++j) {
+            const uint32_t t = (row[j >> 4] >> (2 * (j & 15))) & 3u;  // the diagonal entry is 0
+            if (t && clusts[j] >= 0) { if (t == 1u) ++votes[clusts[j]]; else --votes[clusts[j]]; }
+          }
+          int elected = 0;
+          double maxvote = votes[0];
+          for (int j = 1; j < nS; ++j)
+            if (maxvote < votes[j]) { elected = j; maxvote = votes[j]; }
+          if (clusts[si] >= 0 || !s->o.keep_init_missing) clusts[si] = elected;  // :336-340
+        }
+      }
+    }
+    e = cudaMemcpyAsync(d_cl, clusts.data(), sizeof(int32_t) * C, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      k_fmx_set_clusters<<<FMX_GRID(C, 128), 128, 0, ctx->stream>>>(d_cl, C, s->cells, clust_dev);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_pair_cell); cudaFree(d_trit); cudaFree(d_scratch); cudaFree(d_counter); cudaFree(d_cl);
+  if (e != cudaSuccess)
+    return pscl_fail(ctx, e == cudaErrorMemoryAllocation ? PSCL_ENOMEM : PSCL_ECUDA, "freemuxlet-old seeding failed: %s", cudaGetErrorString(e));
+  return PSCL_OK;
+}
+
 extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int32_t* init_clust_dev, int32_t* clust_dev) {
   FMX_STATE(ctx, s);
   if (!s->stage1_done) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_seed before pscl_fmx_stage1");
@@ -1066,6 +1279,14 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
     ctx->launches++;
   }
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && s->o.mode_old && s->C > 0 && (!init_clust_dev || s->o.iter_init > 0)) {
+    const int rc_old = fmx_seed_old(ctx, s, score, init_clust_dev, clust_dev);
+    cudaFree(score);
+    if (rc_old != PSCL_OK) return rc_old;
+    s->begun = true;
+    s->iters = 0;
+    return PSCL_OK;
+  }
   if (e == cudaSuccess && !init_clust_dev && s->C > 0) {
     std::vector<double> h_score(s->C);
     std::vector<int32_t> h_order(s->C);

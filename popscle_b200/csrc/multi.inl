@@ -111,11 +111,10 @@ extern "C" int pscl_multi_create(const int* gpu_ids, int n_gpu, pscl_multi** out
       return fail(rc, std::string("GPU ") + std::to_string(gpu_ids ? gpu_ids[i] : i) + ": " + e2);
     }
   }
-  // peer access: the runtime's mapping for plain allocations and the stream-ordered pool's own access list
+  // peer access for plain allocations: the buffers of the all-reduce are cudaMalloc'ed outside the stream-ordered pool
+  // (pool memory would need its own access list, cudaMemPoolSetAccess)
   for (int i = 0; i < n_gpu; ++i) {
     cudaSetDevice(m->dev[i]);
-    cudaMemPool_t pool = nullptr;
-    cudaDeviceGetDefaultMemPool(&pool, m->dev[i]);
     for (int k = 0; k < n_gpu; ++k) {
       if (m->dev[k] == m->dev[i]) continue;
       int can = 0;
@@ -124,14 +123,6 @@ extern "C" int pscl_multi_create(const int* gpu_ids, int n_gpu, pscl_multi** out
       const cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[k], 0);
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->peer_ok = false;
       cudaGetLastError();
-      if (pool) {  // device k may read and write what device i allocates with cudaMallocAsync
-        cudaMemAccessDesc d;
-        memset(&d, 0, sizeof d);
-        d.location.type = cudaMemLocationTypeDevice;
-        d.location.id = m->dev[k];
-        d.flags = cudaMemAccessFlagsProtReadWrite;
-        if (cudaMemPoolSetAccess(pool, &d, 1) != cudaSuccess) { m->peer_ok = false; cudaGetLastError(); }
-      }
     }
     cudaEventCreateWithFlags(&m->ev_in[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&m->ev_out[i], cudaEventDisableTiming);
@@ -511,6 +502,10 @@ extern "C" int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const 
   red_llk.n = C1 * npairs; red_s1.n = 4 * C1;
   pscl_fmx_result results[PSCL_MULTI_MAX];
   memset(results, 0, sizeof results);
+  // seeding needs every SNP of a cell: one GPU does it over the whole pileup, the shards then start from its clusters
+  const bool seed_whole = N > 1 && (!init_clust || (opts->mode_old && opts->iter_init > 0));
+  pscl_fmx_opts shard_opts = *opts;
+  shard_opts.iter_init = 0;
   m->tm = pscl_multi_timing{};
   m->tm.n_gpus = N;
   const double t_begin = multi_now_ms();
@@ -525,21 +520,24 @@ extern "C" int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const 
       const double t0 = multi_now_ms();
       int rr = pscl_plp_upload(ctx, host, &full);  // every GPU takes the whole (compact) pileup over its own PCIe link
       if (rr != PSCL_OK) return rr;
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_s1, sizeof(double) * 4 * C1));
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_s1_sum, sizeof(double) * 4 * C1));
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_llk, sizeof(double) * C1 * npairs));
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_llk_sum, sizeof(double) * C1 * npairs));
+      // the four buffers other GPUs read or write: plain (peer-mapped) device memory, not the pool
+      PSCL_CUDA(ctx, (cudaMalloc)((void**)&d_s1, sizeof(double) * 4 * C1));
+      PSCL_CUDA(ctx, (cudaMalloc)((void**)&d_s1_sum, sizeof(double) * 4 * C1));
+      PSCL_CUDA(ctx, (cudaMalloc)((void**)&d_llk, sizeof(double) * C1 * npairs));
+      PSCL_CUDA(ctx, (cudaMalloc)((void**)&d_llk_sum, sizeof(double) * C1 * npairs));
       PSCL_CUDA(ctx, cudaMalloc((void**)&d_clust, sizeof(int32_t) * C1));
       PSCL_CUDA(ctx, cudaMalloc((void**)&d_init, sizeof(int32_t) * C1));
       red_s1.in.p[r] = d_s1; red_s1.out.p[r] = d_s1_sum; red_llk.in.p[r] = d_llk; red_llk.out.p[r] = d_llk_sum;
       if (r == 0) {
         if ((rr = plp_snp_cuts(ctx, full, N, vcut)) != PSCL_OK) return rr;
-        if (!init_clust && N > 1) {
-          // stage 1 + greedy seeding over ALL SNPs on this GPU (a sequential chain over the cells, cmd_cram_freemux2.cpp:223-260)
+        if (seed_whole) {
+          // stage 1 + seeding over ALL SNPs on this GPU: the greedy chain over the cells (cmd_cram_freemux2.cpp:223-260),
+          // or freemuxlet-old's pairwise matrix and votes (cmd_cram_freemuxlet.cpp:165-346, also refining a given init_clust)
           const double ts = multi_now_ms();
           if ((rr = pscl_fmx_init(ctx, full, opts)) != PSCL_OK) return rr;
           if ((rr = pscl_fmx_stage1(ctx, d_s1)) != PSCL_OK) return rr;
-          if ((rr = pscl_fmx_seed(ctx, d_s1, nullptr, d_clust)) != PSCL_OK) return rr;
+          if (init_clust) PSCL_CUDA(ctx, cudaMemcpyAsync(d_init, h_clust.data(), sizeof(int32_t) * C1, cudaMemcpyHostToDevice, ctx->stream));
+          if ((rr = pscl_fmx_seed(ctx, d_s1, init_clust ? d_init : nullptr, d_clust)) != PSCL_OK) return rr;
           PSCL_CUDA(ctx, cudaMemcpyAsync(h_stage1.data(), d_s1, sizeof(double) * 4 * C1, cudaMemcpyDeviceToHost, ctx->stream));
           PSCL_CUDA(ctx, cudaMemcpyAsync(h_clust.data(), d_clust, sizeof(int32_t) * C1, cudaMemcpyDeviceToHost, ctx->stream));
           PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -548,7 +546,7 @@ extern "C" int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const 
         }
       }
       if (!m->bar.wait()) return PSCL_ECUDA;  // cuts, seeds and the buffer addresses of every GPU are published
-      const bool seeded = !init_clust && N > 1;
+      const bool seeded = seed_whole;
       if (N > 1) {
         if ((rr = plp_filter_snps(ctx, full, (int32_t)vcut[r], (int32_t)vcut[r + 1], &shard)) != PSCL_OK) return rr;
         pscl_plp_free(ctx, full);
@@ -558,7 +556,7 @@ extern "C" int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const 
         full = nullptr;
       }
       const double t1 = multi_now_ms();
-      if ((rr = pscl_fmx_init(ctx, shard, opts)) != PSCL_OK) return rr;
+      if ((rr = pscl_fmx_init(ctx, shard, seeded ? &shard_opts : opts)) != PSCL_OK) return rr;
       pscl_fmx_state* s = ctx->fmx;
       if ((rr = pscl_fmx_stage1(ctx, d_s1)) != PSCL_OK) return rr;
       const double* s1_use = d_s1;
@@ -608,7 +606,7 @@ extern "C" int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const 
     const std::string e = ctx->err;
     // nobody frees a buffer another GPU may still be reading
     if (rc2 == PSCL_OK) { cudaStreamSynchronize(ctx->stream); m->bar.wait(); }
-    cudaFree(d_s1); cudaFree(d_s1_sum); cudaFree(d_llk); cudaFree(d_llk_sum); cudaFree(d_clust); cudaFree(d_init);
+    (cudaFree)(d_s1); (cudaFree)(d_s1_sum); (cudaFree)(d_llk); (cudaFree)(d_llk_sum); cudaFree(d_clust); cudaFree(d_init);
     fmx_state_free(ctx);
     if (shard) pscl_plp_free(ctx, shard);
     if (full) pscl_plp_free(ctx, full);

@@ -196,9 +196,6 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   lo.plp_prefix = plp;
   if (old_mode) {
     // cmd_cram_freemuxlet.cpp:83 never copies the filter flags into the loader: library defaults apply
-    if (initClusterFile.empty() || initIteration != 0)
-      throw host_error("freemuxlet-old: the pairwise-distance vote seeding (cmd_cram_freemuxlet.cpp:184-346, libc rand()) is not implemented; "
-                       "pass --init-cluster FILE --iter-init 0");
   } else {
     lo.min_bq = minBQ; lo.cap_bq = capBQ; lo.min_read = minTotal; lo.min_umi = minUMI; lo.min_snp = minSNP;
     if (!groupList.empty()) { lo.group_list = read_first_column(groupList); lo.has_group_list = true; }
@@ -231,7 +228,8 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   if (dry) return dry_run(L);
   Engine eng(gpus);
   pscl_pileup view = L.view();
-  pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0, randomize ? 1 : 0, seed};
+  pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0, randomize ? 1 : 0, seed,
+                     bfThres, old_mode ? initIteration : 0, keepInitMissing ? 1 : 0};
   std::vector<pscl_fmx_cell> cells((size_t)L.n_cells);
   std::vector<double> gl((size_t)L.n_snps * nSamples * 9);
   std::vector<int32_t> cnt((size_t)L.n_snps * nSamples * 3);

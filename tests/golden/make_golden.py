@@ -69,7 +69,7 @@ def main():
     if only:
         return main_only(only)
     main_all()
-    main_only({"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21"})
+    main_only({"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21", "fmx_old_seed", "fmx_old_refine", "fmx_old_frac"})
 
 
 def main_only(only):
@@ -114,7 +114,29 @@ def main_only(only):
         for i in range(21):
             argv += ["--alpha", "%g" % (0.025 * i)]
         run_ref(d, argv + ["--out", "ref"])
-    unknown = only - {"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21"}
+    # 14. freemuxlet-old with ITS OWN seeding: pairwise Bayes-factor matrix, votes on the un-seeded libc rand() stream, ten
+    # refinement sweeps in std::random_shuffle order (cmd_cram_freemuxlet.cpp:165-346)
+    if "fmx_old_seed" in only:
+        d = fresh("fmx_old_seed")
+        base(110, 3, 700, 200, 26, d)
+        run_ref(d, ["freemuxlet-old", "--plp", "p", "--nsample", "3", "--geno-error", "0.05", "--out", "ref"])
+    # 15. ... the refinement sweeps alone, from a partial --init-cluster file, missing droplets kept missing, a looser
+    # Bayes-factor threshold, half of the droplets in the first round
+    if "fmx_old_refine" in only:
+        d = fresh("fmx_old_refine")
+        s, sites, bcs = base(100, 4, 700, 200, 27, d)
+        rng = np.random.default_rng(15)
+        with open(os.path.join(d, "init.tsv"), "w") as f:
+            for c in range(100):
+                if rng.random() < 0.7:
+                    f.write(f"{bcs[c]}\t{int(rng.integers(0, 4) if rng.random() < 0.3 else s.truth_d1[c])}\n")
+        run_ref(d, ["freemuxlet-old", "--plp", "p", "--nsample", "4", "--init-cluster", "init.tsv", "--keep-init-missing", "--bf-thres", "3.0",
+                    "--out", "ref"])
+    if "fmx_old_frac" in only:
+        d = fresh("fmx_old_frac")
+        base(90, 3, 600, 180, 28, d)
+        run_ref(d, ["freemuxlet-old", "--plp", "p", "--nsample", "3", "--frac-init-clust", "0.5", "--iter-init", "0", "--out", "ref"])
+    unknown = only - {"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21", "fmx_old_seed", "fmx_old_refine", "fmx_old_frac"}
     if unknown:
         sys.exit(f"cases {sorted(unknown)} are generated by the full run only")
 

@@ -40,7 +40,7 @@ def test_library_is_sm100a_only(built):
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==112 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 && sizeof(pscl_geno)==56 && offsetof(pscl_geno, geno_err)==48 && sizeof(pscl_fmx_opts)==64 && offsetof(pscl_fmx_opts, seed)==56 ? 0 : 1; }\n')
+    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==112 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 && sizeof(pscl_geno)==56 && offsetof(pscl_geno, geno_err)==48 && sizeof(pscl_fmx_opts)==80 && offsetof(pscl_fmx_opts, seed)==56 && offsetof(pscl_fmx_opts, bf_thres)==64 && offsetof(pscl_fmx_opts, keep_init_missing)==76 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
@@ -89,7 +89,7 @@ def test_pileup_struct_matches_the_ctypes_mirror():
     assert C.sizeof(capi.CPileup) == 112
     assert capi.CPileup.cell_first_snp.offset == 88 and capi.CPileup.pair_snp_delta16.offset == 96 and capi.CPileup.pair_nreads8.offset == 104
     assert capi.CPileup.pair_read_ptr32.offset == 72 and capi.CPileup.read_aq.offset == 80
-    assert C.sizeof(capi.CFmxOpts) == 64 and capi.CFmxOpts.randomize_singlet_score.offset == 52 and capi.CFmxOpts.seed.offset == 56
+    assert C.sizeof(capi.CFmxOpts) == 80 and capi.CFmxOpts.bf_thres.offset == 64 and capi.CFmxOpts.keep_init_missing.offset == 76 and capi.CFmxOpts.randomize_singlet_score.offset == 52 and capi.CFmxOpts.seed.offset == 56
     assert C.sizeof(capi.CGeno) == 56 and capi.CGeno.gp_f32.offset == 24 and capi.CGeno.geno_err.offset == 48
     from popscle_b200 import synth
     s = synth.make_pileup(C=5, nv=2, V=50, kbar=50, seed=3)

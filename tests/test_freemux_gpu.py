@@ -190,3 +190,42 @@ def test_batched_seeding_vs_oracle_at_2000_cells(ctx):
         r = orc.fmx_run(s.plp, orc.fmx_opts(nS))
         check_fmx_parity(cells, r["cells"])
         assert res.n_iter == r["res"].n_iter and res.n_singlet == r["res"].n_singlet
+
+
+@pytest.mark.parametrize("case", ["seed", "seed_frac_nosweeps", "refine_partial_init", "refine_keep_missing"])
+def test_old_mode_pairwise_vote_seeding(ctx, case):
+    """N3: freemuxlet-old's own seeding (cmd_cram_freemuxlet.cpp:165-346) — Bayes-factor trits on the device, votes on
+    glibc's default rand() stream — against the oracle's restatement (which reproduces the reference's files, test_golden)."""
+    nS = 4
+    s = synth.make_pileup(C=260, nv=nS, V=1500, kbar=260, seed=880)
+    init = None
+    kw = dict(mode_old=True, geno_error=0.05, early_stop=False)
+    if case == "seed":
+        kw.update(iter_init=10)
+    elif case == "seed_frac_nosweeps":
+        kw.update(iter_init=0, frac_init_clust=0.5, bf_thres=4.0)
+    else:
+        rng = np.random.default_rng(3)
+        init = np.where(rng.random(260) < 0.6, s.truth_d1, -1).astype(np.int32)
+        init[rng.random(260) < 0.1] = 2
+        kw.update(iter_init=10, keep_init_missing=(case == "refine_keep_missing"))
+    cells, res, gl, cnt = ctx.fmx_run(s.plp, ctx.fmx_opts(nS, **kw), init, want_clusters=True)
+    r = orc.fmx_run(s.plp, orc.fmx_opts(nS, **kw), init, want_clusters=True, n_threads=8)
+    assert np.array_equal(cells["init_clust"], r["cells"]["init_clust"])
+    if case == "seed_frac_nosweeps":
+        assert (cells["init_clust"] < 0).sum() > 100  # the droplets beyond --frac-init-clust stay unassigned
+    if case == "refine_keep_missing":
+        assert np.array_equal(cells["init_clust"] < 0, init < 0)
+    _check(cells, res, gl, cnt, r)
+
+
+def test_old_mode_seeding_sharded(ctx):
+    """pscl_multi: the pairwise seeding needs every SNP of a droplet, so it runs over the whole pileup on one GPU."""
+    from popscle_b200 import Multi
+    s = synth.make_pileup(C=200, nv=3, V=1200, kbar=240, seed=881)
+    o = ctx.fmx_opts(3, mode_old=True, geno_error=0.05, iter_init=10, early_stop=False)
+    one = ctx.fmx_run(s.plp, o)[0]
+    with Multi(gpu_ids=[int(x) for x in os.environ.get("PSCL_TEST_GPUS", "0,0").split(",")] * 2) as m:
+        many = m.fmx_run(s.plp, o)[0]
+    assert np.array_equal(many["init_clust"], one["init_clust"])
+    check_fmx_parity(many, one)

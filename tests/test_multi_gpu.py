@@ -14,9 +14,15 @@ pytestmark = pytest.mark.gpu
 DEFAULT = [0.0, 0.5]
 
 
+def _ids(n):
+    """device list of n entries: the same GPU n times on a one-GPU box, or PSCL_TEST_GPUS=0,1,... cycled on a real multi-GPU box"""
+    have = [int(x) for x in os.environ.get("PSCL_TEST_GPUS", "0").split(",")]
+    return [have[i % len(have)] for i in range(n)]
+
+
 @pytest.fixture(scope="module")
 def multi3(built):
-    m = Multi(gpu_ids=[0, 0, 0])
+    m = Multi(gpu_ids=_ids(3))
     yield m
     m.close()
 
@@ -57,7 +63,7 @@ def test_wide_genotype_table_travels_gpu_to_gpu(ctx, built):
     gp = synth.gt_to_gp(s.geno)
     assert gp.nbytes >= 32 << 20
     one = ctx.demux_run(s.plp, gp, None, DEFAULT)
-    with Multi(gpu_ids=[0, 0, 0, 0, 0]) as m:
+    with Multi(gpu_ids=_ids(5)) as m:
         many = m.demux_run(s.plp, gp, None, DEFAULT)
         assert many.tobytes() == one.tobytes()
         os.environ["PSCL_NO_GENO_TREE"] = "1"
@@ -108,13 +114,13 @@ def test_cli_hosts_take_gpus(ctx, tmp_path):
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demux_gt")
     exe = _build.build_host()
     outs = {}
-    for tag, env in (("one", {}), ("two", {"PSCL_GPU_IDS": "0,0"})):
+    for tag, env in (("one", {}), ("two", {"PSCL_GPU_IDS": ",".join(map(str, _ids(2)))})):
         o = str(tmp_path / tag)
         subprocess.check_call([exe, "demuxlet", "--plp", "p", "--vcf", "g.vcf.gz", "--field", "GT", "--out", o], cwd=gold,
                               env=dict(os.environ, **env), stderr=subprocess.DEVNULL)
         outs[tag] = open(o + ".best").read()
     assert outs["one"] == outs["two"]
-    os.environ["PSCL_GPU_IDS"] = "0,0"
+    os.environ["PSCL_GPU_IDS"] = ",".join(map(str, _ids(2)))
     cwd = os.getcwd()
     os.chdir(gold)
     try:
@@ -126,7 +132,7 @@ def test_cli_hosts_take_gpus(ctx, tmp_path):
     gold = os.path.join(os.path.dirname(gold), "fmx_default")
     import gzip
     res = {}
-    for tag, env in (("one", {}), ("two", {"PSCL_GPU_IDS": "0,0"})):
+    for tag, env in (("one", {}), ("two", {"PSCL_GPU_IDS": ",".join(map(str, _ids(2)))})):
         o = str(tmp_path / ("f" + tag))
         subprocess.check_call([exe, "freemuxlet", "--plp", "p", "--nsample", "4", "--out", o, "--seed", "1"], cwd=gold,
                               env=dict(os.environ, **env), stderr=subprocess.DEVNULL)
