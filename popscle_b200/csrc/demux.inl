@@ -999,7 +999,7 @@ extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
 #define PSCL_DICT_NT 256
 #endif
 #ifndef PSCL_ROWS_NT
-#define PSCL_ROWS_NT 256
+#define PSCL_ROWS_NT 384
 #endif
 
 template <int NV, bool DELTA, bool DICT>

@@ -362,18 +362,21 @@ __global__ void __launch_bounds__(1024, 1) k_fmx_seed(SeedArgs a) {
 // ------------------------------------------------------------------------------------------------
 // The distance of cell i to cluster j is a sum over the SNPs the two share (sc_drop_seq.cpp:544-578), and the state of
 // cluster j at SNP s changes only when a cell covering s is merged into j.  A batch of B cells (consecutive in seeding
-// order) is therefore handled in two launches:
+// order) is therefore handled in three launches:
 //   k_fmx_seed_dist    (all SMs) every (cell of the batch, SNP, cluster) contribution against the cluster table as it
-//                      stands BEFORE the batch, kept per (pair, cluster) in `contrib`, plus their per-cell sums;
-//   k_fmx_seed_commit  (one CTA) walks the B cells in order.  A cell's true distance = snapshot sum + the corrections at
-//                      the SNPs some earlier cell of this batch merged into (dirty[s]: batch stamp + cluster bit mask):
-//                      contribution against the CURRENT table minus the stored one.  Then argmax (first wins, :238-241)
-//                      and the merge (:248-251), which marks its SNPs dirty.
-// Cells of a batch share few SNPs (K^2/V = 40 of 2000 at configs[2]), so the serial part touches ~K dirty words and a few
-// hundred corrections per cell instead of K x nS evaluations with two logs each.  The decisions are those of the serial
-// chain up to the summation order of the distance (a reordering of ~1e3 terms; ties within ~1e-13 relative could flip,
-// as they could between any two compilers of the reference).
-#define PSCL_SEED_SPLIT 4   /* CTAs per batch cell in k_fmx_seed_dist */
+//                      stands BEFORE the batch, kept per (pair, cluster) in `contrib`, plus their per-cell sums; and a
+//                      count, per SNP, of the batch's cells that cover it (mark[s]).
+//   k_fmx_seed_commit  (one CTA) walks the B cells in order, looking only at the pairs whose SNP another cell of the batch
+//                      covers too (compacted into a dense list: cells share few SNPs, K^2/V = 40 of 2000 at configs[2]).
+//                      A cell's true distance = snapshot sum + the corrections at the SNPs an EARLIER cell of the batch
+//                      merged into (cluster bit mask in mark[s]): contribution against the CURRENT table minus the
+//                      stored one.  Then argmax (first wins, :238-241) and the merge (:248-251) at those shared SNPs.
+//   k_fmx_seed_merge   (all SMs) the merges at the SNPs only one cell of the batch covers: nobody else in the batch can
+//                      see them, so they run in parallel once the clusters are decided.
+// The decisions are those of the serial chain up to the summation order of the distance (a reordering of ~1e3 terms; ties
+// within ~1e-13 relative could flip, as they could between any two compilers of the reference).
+#define PSCL_SEED_SPLIT 4      /* CTAs per batch cell in k_fmx_seed_dist / k_fmx_seed_merge */
+#define PSCL_SEED_LIST 8192    /* shared pairs of one cell the commit kernel lists at a time */
 struct SeedBatchArgs {
   const int32_t* elig;        // [n_elig] cells that take part, in seeding order
   const int64_t* epair;       // [n_elig + 1] running pair count of those cells (offsets into contrib, relative to the batch)
@@ -383,7 +386,8 @@ struct SeedBatchArgs {
   const double* snp_af;
   double* clust_gl;           // [V][nS][9]
   uint8_t* present;           // [V][nS]
-  unsigned long long* dirty;  // [V] (batch + 1) << 32 | mask of the clusters merged into at this SNP during that batch
+  unsigned long long* mark;   // [V] (batch + 1) << 32 | cells of the batch covering the SNP (saturating) << 24 | mask of the
+                              //     clusters merged into at this SNP by the commit kernel during that batch
   double* contrib;            // [pairs of the batch][nS]
   double* d0p;                // [B][PSCL_SEED_SPLIT][nS]
   int32_t* clust;
@@ -398,6 +402,17 @@ __device__ __forceinline__ double fmx_seed_term(double ci0, double ci1, double c
   const double lk0 = (ci0 * h0 + ci1 * h1 + ci2 * h2) * (cj0 * h0 + cj1 * h1 + cj2 * h2);  // sum_g sum_h ci[g] cj[h] h[g] h[h]
   return log(lk2) - log(lk0);
 }
+__device__ __forceinline__ void fmx_seed_merge_pair(const SeedBatchArgs& a, int64_t p, int32_t s, int j) {
+  const size_t e = (size_t)s * a.nS + j;
+  double gl[9], o[9];
+  double* cg = a.clust_gl + e * 9;
+#pragma unroll
+  for (int g = 0; g < 9; ++g) { gl[g] = cg[g]; o[g] = a.gl_soa[(size_t)g * a.P + p]; }
+  fmx_merge(gl, o);
+#pragma unroll
+  for (int g = 0; g < 9; ++g) cg[g] = gl[g];
+  a.present[e] = 1;
+}
 
 template <int NSM>
 __global__ void __launch_bounds__(256) k_fmx_seed_dist(SeedBatchArgs a) {
@@ -408,12 +423,22 @@ __global__ void __launch_bounds__(256) k_fmx_seed_dist(SeedBatchArgs a) {
   const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
   const int64_t t0 = K * q / PSCL_SEED_SPLIT, t1 = K * (q + 1) / PSCL_SEED_SPLIT;
   double* const out = a.contrib + (size_t)(a.epair[a.base + b] - a.epair[a.base]) * nS;
+  const unsigned long long stamp = (unsigned long long)(a.batch + 1) << 32;
   double sum[NSM];
 #pragma unroll
   for (int j = 0; j < NSM; ++j) sum[j] = 0.0;
   for (int64_t t = t0 + tid; t < t1; t += 256) {
     const int64_t p = pb + t;
     const int32_t s = a.pair_snp[p];
+    {  // one more cell of this batch covers SNP s
+      unsigned long long old = a.mark[s], want;
+      do {
+        const unsigned long long cur = old;
+        want = ((cur >> 32) != (stamp >> 32)) ? (stamp | (1ull << 24)) : (((cur >> 24) & 0xffull) < 0xffull ? cur + (1ull << 24) : cur);
+        old = atomicCAS(a.mark + s, cur, want);
+        if (old == cur) break;
+      } while (true);
+    }
     const double af = a.snp_af[s];
     const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
     const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
@@ -448,78 +473,114 @@ __global__ void __launch_bounds__(256) k_fmx_seed_dist(SeedBatchArgs a) {
 template <int NSM>
 __global__ void __launch_bounds__(1024, 1) k_fmx_seed_commit(SeedBatchArgs a) {
   __shared__ double s_w[32][NSM], s_sc[NSM];
-  __shared__ int s_choice;
+  __shared__ int s_choice, s_wcnt[32], s_n;
+  __shared__ int s_list[PSCL_SEED_LIST];  // pair offsets (inside the cell) whose SNP another cell of the batch covers too
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nS = a.nS;
   const unsigned long long stamp = (unsigned long long)(a.batch + 1) << 32;
   for (int b = 0; b < a.nb; ++b) {
     const int si = a.elig[a.base + b];
-    const int64_t pb = a.cell_ptr[si], pe = a.cell_ptr[si + 1];
+    const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
     const double* const stored = a.contrib + (size_t)(a.epair[a.base + b] - a.epair[a.base]) * nS;
-    // ---- corrections at the SNPs earlier cells of this batch have merged into ----
     double delta[NSM];
 #pragma unroll
     for (int j = 0; j < NSM; ++j) delta[j] = 0.0;
-    for (int64_t p = pb + tid; p < pe; p += 1024) {
-      const int32_t s = a.pair_snp[p];
-      const unsigned long long w = a.dirty[s];
-      if ((w >> 32) != (stamp >> 32)) continue;
-      const unsigned mask = (unsigned)w;
-      const double af = a.snp_af[s];
-      const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
-      const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
-#pragma unroll
-      for (int j = 0; j < NSM; ++j) {
-        if (j < nS && ((mask >> j) & 1u)) {
-          const double* cj = a.clust_gl + ((size_t)s * nS + j) * 9;
-          delta[j] += fmx_seed_term(ci0, ci1, ci2, cj[0], cj[4], cj[8], h0, h1, h2) - stored[(size_t)(p - pb) * nS + j];
+    int jstar = -1;
+    // two passes over the cell's pairs, PSCL_SEED_LIST at a time: pass 0 lists the shared pairs and sums the corrections
+    // (the decision follows it), pass 1 lists them again and merges
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int64_t c0 = 0; c0 < K; c0 += PSCL_SEED_LIST) {
+        const int64_t c1 = c0 + PSCL_SEED_LIST < K ? c0 + PSCL_SEED_LIST : K;
+        // ---- deterministic compaction: position = (iteration, warp, lane) order ----
+        // (a cell of <= PSCL_SEED_LIST pairs keeps pass 0's list for pass 1: the per-SNP cover counts do not change
+        // inside the commit kernel)
+        int n_list = (pass == 1 && K <= PSCL_SEED_LIST) ? s_n : 0;
+        for (int64_t t = c0 + tid; t < c0 + (((c1 - c0) + 1023) & ~(int64_t)1023) && !(pass == 1 && K <= PSCL_SEED_LIST); t += 1024) {
+          bool sh = false;
+          if (t < c1) sh = ((a.mark[a.pair_snp[pb + t]] >> 24) & 0xffull) >= 2ull;
+          const unsigned bal = __ballot_sync(0xffffffffu, sh);
+          if (lane == 0) s_wcnt[warp] = __popc(bal);
+          __syncthreads();
+          int before = 0, total = 0;
+          for (int w = 0; w < 32; ++w) { const int c = s_wcnt[w]; before += w < warp ? c : 0; total += c; }
+          if (sh) s_list[n_list + before + __popc(bal & ((1u << lane) - 1u))] = (int)(t - c0);
+          n_list += total;
+          __syncthreads();
         }
+        if (pass == 0 && tid == 0) s_n = n_list;
+        // ---- the listed pairs, one per thread ----
+        for (int q = tid; q < n_list; q += 1024) {
+          const int64_t t = c0 + s_list[q];
+          const int64_t p = pb + t;
+          const int32_t s = a.pair_snp[p];
+          if (pass == 0) {
+            unsigned mask = (unsigned)a.mark[s] & 0xffffffu;  // clusters an earlier cell of this batch merged into at s
+            if (mask) {
+              const double af = a.snp_af[s];
+              const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
+              const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
+              while (mask) {  // usually one bit: the lanes loop together whatever cluster each one corrects
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double* cj = a.clust_gl + ((size_t)s * nS + j) * 9;
+                const double v = fmx_seed_term(ci0, ci1, ci2, cj[0], cj[4], cj[8], h0, h1, h2) - stored[(size_t)t * nS + j];
+#pragma unroll
+                for (int jj = 0; jj < NSM; ++jj) delta[jj] += (jj == j) ? v : 0.0;
+              }
+            }
+          } else {
+            fmx_seed_merge_pair(a, p, s, jstar);
+            a.mark[s] |= 1ull << jstar;  // the stamp is this batch's (the SNP is covered by >= 2 of its cells)
+          }
+        }
+        __syncthreads();
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int j = 0; j < NSM; ++j) {
+          if (j < nS) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) delta[j] += __shfl_xor_sync(0xffffffffu, delta[j], o);
+            if (lane == 0) s_w[warp][j] = delta[j];
+          }
+        }
+        __syncthreads();
+        if (tid < nS) {
+          double x = 0.0;
+          for (int q = 0; q < PSCL_SEED_SPLIT; ++q) x += a.d0p[((size_t)b * PSCL_SEED_SPLIT + q) * nS + tid];
+          double d = 0.0;
+          for (int w = 0; w < 32; ++w) d += s_w[w][tid];
+          s_sc[tid] = x + d;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int best = 0;
+          double bs = s_sc[0];
+          for (int j = 1; j < nS; ++j)
+            if (s_sc[j] > bs) { best = j; bs = s_sc[j]; }  // :238-241, first wins
+          s_choice = best;
+          a.clust[si] = best;
+          a.cells[si].clust = a.cells[si].init_clust = best;
+          a.cells[si].type = 0;
+        }
+        __syncthreads();
+        jstar = s_choice;
       }
     }
-#pragma unroll
-    for (int j = 0; j < NSM; ++j) {
-      if (j < nS) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) delta[j] += __shfl_xor_sync(0xffffffffu, delta[j], o);
-        if (lane == 0) s_w[warp][j] = delta[j];
-      }
-    }
+    (void)stamp;
     __syncthreads();
-    if (tid < nS) {
-      double x = 0.0;
-      for (int q = 0; q < PSCL_SEED_SPLIT; ++q) x += a.d0p[((size_t)b * PSCL_SEED_SPLIT + q) * nS + tid];
-      double d = 0.0;
-      for (int w = 0; w < 32; ++w) d += s_w[w][tid];
-      s_sc[tid] = x + d;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int best = 0;
-      double bs = s_sc[0];
-      for (int j = 1; j < nS; ++j)
-        if (s_sc[j] > bs) { best = j; bs = s_sc[j]; }  // :238-241, first wins
-      s_choice = best;
-      a.clust[si] = best;
-      a.cells[si].clust = a.cells[si].init_clust = best;
-      a.cells[si].type = 0;
-    }
-    __syncthreads();
-    const int jstar = s_choice;
-    // ---- merge the cell into the chosen cluster (:248-251) and mark its SNPs ----
-    for (int64_t p = pb + tid; p < pe; p += 1024) {
-      const int32_t s = a.pair_snp[p];
-      const size_t e = (size_t)s * nS + jstar;
-      double gl[9], o[9];
-      double* cg = a.clust_gl + e * 9;
-#pragma unroll
-      for (int g = 0; g < 9; ++g) { gl[g] = cg[g]; o[g] = a.gl_soa[(size_t)g * a.P + p]; }
-      fmx_merge(gl, o);
-#pragma unroll
-      for (int g = 0; g < 9; ++g) cg[g] = gl[g];
-      a.present[e] = 1;
-      const unsigned long long w = a.dirty[s];
-      a.dirty[s] = (((w >> 32) == (stamp >> 32)) ? w : stamp) | (1ull << jstar);
-    }
-    __syncthreads();
+  }
+}
+
+// the merges nobody else in the batch can see: SNPs covered by exactly one of its cells
+__global__ void __launch_bounds__(256) k_fmx_seed_merge(SeedBatchArgs a) {
+  const int b = blockIdx.x, q = blockIdx.y;
+  const int si = a.elig[a.base + b];
+  const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
+  const int64_t t0 = K * q / PSCL_SEED_SPLIT, t1 = K * (q + 1) / PSCL_SEED_SPLIT;
+  const int j = a.clust[si];
+  for (int64_t t = t0 + threadIdx.x; t < t1; t += 256) {
+    const int32_t s = a.pair_snp[pb + t];
+    if (((a.mark[s] >> 24) & 0xffull) < 2ull) fmx_seed_merge_pair(a, pb + t, s, j);
   }
 }
 
@@ -790,8 +851,11 @@ __global__ void __launch_bounds__(THREADS) k_fmx_estep(EArgs a) {
   constexpr int EBASE = J0 * (J0 + 1) / 2;
   const int nS = NS > 0 ? NS : a.nS;
   const int US = NS > 0 ? ((NS * 3 + 1) & ~1) : a.US;
-  const int SD = NS > 0 ? ((((US / 2) & 1) == 0) ? US + 2 : US) : a.SD;
-  const int NCH = US / 2;                       // 16-byte pieces per posterior row
+  // a kernel instance with compile-time NS only needs the posteriors of clusters [0, J1): it gathers and stages that
+  // head of the row (RD doubles), which shrinks both the L2 traffic and the shared-memory footprint of the early tiles
+  const int RD = NS > 0 ? ((J1 * 3 + 1) & ~1) : US;
+  const int SD = NS > 0 ? ((((RD / 2) & 1) == 0) ? RD + 2 : RD) : a.SD;
+  const int NCH = RD / 2;                       // 16-byte pieces per (head of a) posterior row
   int lg = 0;
   while ((1 << lg) < NCH && lg < 5) ++lg;       // lanes per row (power of two, <= 32)
   const int LPR = 1 << lg, RPI = 32 >> lg;
@@ -1333,24 +1397,24 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
         elig.push_back(si);
         epair.push_back(epair.back() + (plp->h_cell_ptr[si + 1] - plp->h_cell_ptr[si]));
       }
-      int B = 32;
+      int B = 8;
       if (const char* bv = getenv("PSCL_SEED_BATCH")) B = std::max(1, std::min(256, atoi(bv)));
       const int n_elig = (int)elig.size();
       int64_t max_pairs = 1;
       for (int b0 = 0; b0 < n_elig; b0 += B) max_pairs = std::max(max_pairs, epair[std::min(n_elig, b0 + B)] - epair[b0]);
-      int32_t* d_elig = nullptr; int64_t* d_epair = nullptr; unsigned long long* d_dirty = nullptr; double *d_contrib = nullptr, *d_d0p = nullptr;
+      int32_t* d_elig = nullptr; int64_t* d_epair = nullptr; unsigned long long* d_mark = nullptr; double *d_contrib = nullptr, *d_d0p = nullptr;
       auto alloc = [&](void** d, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16); };
       alloc((void**)&d_elig, sizeof(int32_t) * (size_t)std::max(n_elig, 1));
       alloc((void**)&d_epair, sizeof(int64_t) * ((size_t)n_elig + 1));
-      alloc((void**)&d_dirty, sizeof(unsigned long long) * (size_t)std::max(s->V, 1));
+      alloc((void**)&d_mark, sizeof(unsigned long long) * (size_t)std::max(s->V, 1));
       alloc((void**)&d_contrib, sizeof(double) * (size_t)max_pairs * s->nS);
       alloc((void**)&d_d0p, sizeof(double) * (size_t)B * PSCL_SEED_SPLIT * s->nS);
       if (e == cudaSuccess && n_elig) e = cudaMemcpyAsync(d_elig, elig.data(), sizeof(int32_t) * n_elig, cudaMemcpyHostToDevice, ctx->stream);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_epair, epair.data(), sizeof(int64_t) * ((size_t)n_elig + 1), cudaMemcpyHostToDevice, ctx->stream);
-      if (e == cudaSuccess) e = cudaMemsetAsync(d_dirty, 0, sizeof(unsigned long long) * (size_t)std::max(s->V, 1), ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(d_mark, 0, sizeof(unsigned long long) * (size_t)std::max(s->V, 1), ctx->stream);
       SeedBatchArgs a;
       a.elig = d_elig; a.epair = d_epair; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.snp_af = plp->snp_af;
-      a.clust_gl = s->clust_gl; a.present = s->present; a.dirty = d_dirty; a.contrib = d_contrib; a.d0p = d_d0p; a.clust = clust_dev;
+      a.clust_gl = s->clust_gl; a.present = s->present; a.mark = d_mark; a.contrib = d_contrib; a.d0p = d_d0p; a.clust = clust_dev;
       a.cells = s->cells; a.P = s->P; a.nS = s->nS;
       for (int b0 = 0, batch = 0; b0 < n_elig && e == cudaSuccess; b0 += B, ++batch) {
         a.base = b0; a.nb = std::min(B, n_elig - b0); a.batch = batch;
@@ -1358,11 +1422,12 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
         if (s->nS <= 8) { k_fmx_seed_dist<8><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<8><<<1, 1024, 0, ctx->stream>>>(a); }
         else if (s->nS <= 16) { k_fmx_seed_dist<16><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<16><<<1, 1024, 0, ctx->stream>>>(a); }
         else { k_fmx_seed_dist<PSCL_FMX_MAX_CLUSTERS><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<PSCL_FMX_MAX_CLUSTERS><<<1, 1024, 0, ctx->stream>>>(a); }
-        ctx->launches += 2;
+        k_fmx_seed_merge<<<grid, 256, 0, ctx->stream>>>(a);
+        ctx->launches += 3;
         e = cudaGetLastError();
       }
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // elig / epair are pageable sources
-      cudaFree(d_elig); cudaFree(d_epair); cudaFree(d_dirty); cudaFree(d_contrib); cudaFree(d_d0p);
+      cudaFree(d_elig); cudaFree(d_epair); cudaFree(d_mark); cudaFree(d_contrib); cudaFree(d_d0p);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h_order is a pageable source
   }
@@ -1413,8 +1478,10 @@ extern "C" int pscl_fmx_mstep(pscl_ctx* ctx, const int32_t* clust_dev) {
 template <int NS, int J0, int J1, int THREADS>
 static int fmx_estep_launch(pscl_ctx* ctx, pscl_fmx_state* s, const EArgs& a) {
   constexpr int NA = J1 * (J1 + 1) / 2 - J0 * (J0 + 1) / 2;
-  if (2 * s->SD < NA) return pscl_fail(ctx, PSCL_EINVAL, "internal: E-step staging rows too short (SD=%d, NA=%d)", s->SD, NA);
-  const size_t smem = sizeof(double) * 2 * THREADS * (size_t)s->SD + sizeof(int) * (size_t)NA * THREADS;
+  constexpr int RD = (J1 * 3 + 1) & ~1;
+  const int SD = NS > 0 ? ((((RD / 2) & 1) == 0) ? RD + 2 : RD) : s->SD;  // as in the kernel
+  if (2 * SD < NA) return pscl_fail(ctx, PSCL_EINVAL, "internal: E-step staging rows too short (SD=%d, NA=%d)", SD, NA);
+  const size_t smem = sizeof(double) * 2 * THREADS * (size_t)SD + sizeof(int) * (size_t)NA * THREADS;
   auto kern = k_fmx_estep<NS, J0, J1, THREADS>;
   PSCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -1459,6 +1526,12 @@ extern "C" int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev) {
       case 6: rc = fmx_estep_launch<6, 0, 6, 128>(ctx, s, a); break;
       case 7: rc = fmx_estep_launch<7, 0, 7, 128>(ctx, s, a); break;
       case 8: rc = fmx_estep_launch<8, 0, 8, 128>(ctx, s, a); break;
+      case 16:  // configs[4]'s cluster count: compile-time tiles (each gathers only the row head it needs)
+        rc = fmx_estep_launch<16, 0, 8, 64>(ctx, s, a);
+        if (rc == PSCL_OK) rc = fmx_estep_launch<16, 8, 11, 64>(ctx, s, a);
+        if (rc == PSCL_OK) rc = fmx_estep_launch<16, 11, 14, 64>(ctx, s, a);
+        if (rc == PSCL_OK) rc = fmx_estep_launch<16, 14, 16, 64>(ctx, s, a);
+        break;
       default:
         rc = fmx_estep_launch<0, 0, 8, 64>(ctx, s, a);
         if (rc == PSCL_OK && nS > 8) rc = fmx_estep_launch<0, 8, 11, 64>(ctx, s, a);

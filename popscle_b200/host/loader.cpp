@@ -98,24 +98,31 @@ struct VcfCursor {
         if (fmt[i] == "GT") gi = (int)i;
         if (fmt[i] == o.field) fi = (int)i;
       }
-      if (gi < 0) throw host_error("Cannot find the field GT from the VCF file at position " + c[0] + ":" + c[1]);
-      // minMAC / minCallRate force GT parsing (bcf_filter_arg.h:110-113)
-      g1.assign(nv, 0); g2.assign(nv, 0); acs.assign(nal, 0);  // members: no allocation per record
+      // GT is parsed (and required) only when something reads it: the site filters minMAC / minCallRate
+      // (require_GT, bcf_filter_arg.h:110-113) or --field GT itself
+      const bool need_gt = o.min_mac > 0 || o.min_callrate > 0 || o.field == "GT";
+      if (gi < 0 && need_gt) throw host_error("Cannot find the field GT from the VCF file at position " + c[0] + ":" + c[1]);
+      g1.assign(nv, -1); g2.assign(nv, -1); acs.assign(nal, 0);  // members: no allocation per record
       int an = 0;
       if ((int)smp.size() != nv) smp.resize(nv);
       for (int i = 0; i < nv; ++i) {
         split_char(c[9 + cols[i]], ':', smp[i]);
+        if (gi < 0) continue;
         const std::string& gt = gi < (int)smp[i].size() ? smp[i][gi] : std::string(".");
         size_t sep = gt.find_first_of("/|");
         std::string a = gt.substr(0, sep), b = sep == std::string::npos ? std::string(".") : gt.substr(sep + 1);
         g1[i] = (a == "." || a.empty()) ? -1 : atoi(a.c_str());
         g2[i] = (b == "." || b.empty()) ? -1 : atoi(b.c_str());
+        if (g1[i] >= nal || g2[i] >= nal)  // an allele number the record does not define ("0/3" at a biallelic site)
+          throw host_error("GT " + gt + " names an allele beyond the ALT list at position " + c[0] + ":" + c[1]);
         if (g1[i] >= 0) { ++an; ++acs[g1[i]]; }
         if (g2[i] >= 0) { ++an; ++acs[g2[i]]; }
       }
-      if (nv > 0 && o.min_callrate > (double)an / (2.0 * nv)) continue;
-      const int ac = an - acs[0];
-      if (ac < o.min_mac || an - ac < o.min_mac) continue;
+      if (need_gt) {
+        if (nv > 0 && o.min_callrate > (double)an / (2.0 * nv)) continue;
+        const int ac = an - acs[0];
+        if (ac < o.min_mac || an - ac < o.min_mac) continue;
+      }
       // ---- posteriors with gt_error = 0 (load_from_plp passes 0, sc_drop_seq.cpp:113,285) ----
       const int ngen = nal * (nal + 1) / 2;
       gps.assign((size_t)nv * ngen, 0.f);

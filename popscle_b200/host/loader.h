@@ -68,6 +68,7 @@ struct Loaded {
   mutable std::vector<uint16_t> pair_snp_delta16;
   mutable std::vector<uint8_t> pair_nreads8;
   mutable int delta_state = 0;  // 0 not tried, 1 usable, -1 a gap or a count does not fit
+  mutable int compact_state = 0;  // the same for read_aq (an allele code > 2 or a quality > 63 rules the packed form out)
 
   pscl_pileup view() const {
     pscl_pileup p;
@@ -75,14 +76,16 @@ struct Loaded {
     p.cell_first_snp = nullptr; p.pair_snp_delta16 = nullptr; p.pair_nreads8 = nullptr;
     if (read_allele.size() < (1ull << 32)) {  // halves the bytes pscl_plp_upload sends over PCIe
       if (pair_read_ptr32.size() != pair_read_ptr.size()) pair_read_ptr32.assign(pair_read_ptr.begin(), pair_read_ptr.end());
-      bool ok = true;
-      if (read_aq.size() != read_allele.size()) {
+      if (compact_state == 0) {  // decided once per loaded pileup (a later call must not forget a failed check)
+        bool fits = true;
         read_aq.resize(read_allele.size());
         for (size_t i = 0; i < read_aq.size(); ++i) {
-          ok = ok && read_allele[i] <= 2 && read_qual[i] <= 63;
+          fits = fits && read_allele[i] <= 2 && read_qual[i] <= 63;  // e.g. --cap-BQ above 63
           read_aq[i] = (uint8_t)((read_allele[i] << 6) | (read_qual[i] & 63));
         }
+        compact_state = fits ? 1 : -1;
       }
+      const bool ok = compact_state == 1;
       if (ok) { p.pair_read_ptr32 = pair_read_ptr32.data(); p.read_aq = read_aq.data(); }
       if (ok && delta_state == 0) {  // 3 B per pair instead of 8: SNP ids rise within a cell, counts are small
         const size_t P = pair_snp.size();

@@ -207,26 +207,33 @@ def _parse_vcf(path, field, sm_list=None, min_mac=1, min_callrate=0.5, max_allel
         smp = [x.split(":") for x in c[9:]]
         if nal > max_alleles:
             continue
-        # minMAC / minCallRate force GT parsing (bcf_filter_arg.h:110-113)
-        if "GT" not in fmt:
+        # GT is parsed (and required) only when something reads it: the site filters minMAC / minCallRate
+        # (require_GT, bcf_filter_arg.h:110-113) or --field GT itself
+        need_gt = min_mac > 0 or min_callrate > 0 or field == "GT"
+        if "GT" not in fmt and need_gt:
             raise ValueError(f"Cannot find the field GT from the VCF file at position {c[0]}:{pos}")
-        gi = fmt.index("GT")
-        gts = []
-        for j in cols:
-            a = smp[j][gi].replace("|", "/").split("/")
-            a = [(-1 if x in (".", "") else int(x)) for x in a] + [-1]
-            gts.append((a[0], a[1]))
+        gts = [(-1, -1)] * len(cols)
+        if "GT" in fmt:
+            gi = fmt.index("GT")
+            gts = []
+            for j in cols:
+                a = smp[j][gi].replace("|", "/").split("/")
+                a = [(-1 if x in (".", "") else int(x)) for x in a] + [-1]
+                if a[0] >= nal or a[1] >= nal:
+                    raise ValueError(f"GT {smp[j][gi]} names an allele beyond the ALT list at position {c[0]}:{pos}")
+                gts.append((a[0], a[1]))
         an = sum((x >= 0) + (y >= 0) for x, y in gts)
         acs = [0] * nal
         for x, y in gts:
             if x >= 0: acs[x] += 1
             if y >= 0: acs[y] += 1
         nv = len(cols)
-        if nv and min_callrate > an / (2.0 * nv):
-            continue
-        ac = an - acs[0]
-        if ac < min_mac or an - ac < min_mac:
-            continue
+        if need_gt:
+            if nv and min_callrate > an / (2.0 * nv):
+                continue
+            ac = an - acs[0]
+            if ac < min_mac or an - ac < min_mac:
+                continue
         ngen = nal * (nal + 1) // 2
         gp = np.zeros(nv * ngen, dtype=np.float32)
         if field == "GT":

@@ -242,3 +242,41 @@ def test_gloo_barcode_sharded_demuxlet(built):
 
 def test_gloo_snp_sharded_freemuxlet(built):
     assert _spawn(_worker_fmx, 29612)
+
+
+def test_vcf_without_gt_and_bad_allele_numbers(tmp_path, built):
+    """GT is only required when a site filter or --field GT reads it (bcf_filter_arg.h:110-113), and an
+    allele number beyond the ALT list is an input error, not an out-of-bounds write — in both hosts."""
+    import gzip
+    import subprocess
+    from popscle_b200 import _build, plpio
+    s = synth.make_pileup(C=12, nv=2, V=40, kbar=20, seed=4)
+    sites = plpio.default_sites(40, s.af, seed=4)
+    plpio.write_plp(str(tmp_path / "p"), s.plp, sites)
+    head = "##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\n"
+
+    def vcf(name, fmt, cell):
+        with gzip.open(tmp_path / name, "wt") as f:
+            f.write(head)
+            for v in range(40):
+                f.write(f"{sites.chrom[v]}\t{int(sites.pos[v])}\t.\t{sites.ref[v]}\t{sites.alt[v]}\t.\tPASS\t.\t{fmt}\t{cell(v, 0)}\t{cell(v, 1)}\n")
+    vcf("gp_only.vcf.gz", "GP", lambda v, j: "0.8,0.15,0.05" if (v + j) % 2 else "0.1,0.2,0.7")
+    vcf("bad_gt.vcf.gz", "GT", lambda v, j: "0/3" if v == 7 else "0/1")
+    exe = _build.build_host()
+    # no GT column: fine once nothing needs it ...
+    L = plpio.load_plp(str(tmp_path / "p"), str(tmp_path / "gp_only.vcf.gz"), field="GP", min_mac=0, min_callrate=0.0)
+    assert L.geno.has_gp.sum() == 40 and L.geno.gp.shape == (40, 2, 3)
+    r = subprocess.run([exe, "demuxlet", "--plp", "p", "--vcf", "gp_only.vcf.gz", "--field", "GP", "--min-mac", "0", "--min-callrate", "0",
+                        "--out", "o", "--dry-run"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and '"has_gp": 40' in r.stdout, r.stderr
+    # ... and the reference's error while the default filters are on
+    with pytest.raises(ValueError, match="Cannot find the field GT"):
+        plpio.load_plp(str(tmp_path / "p"), str(tmp_path / "gp_only.vcf.gz"), field="GP")
+    r = subprocess.run([exe, "demuxlet", "--plp", "p", "--vcf", "gp_only.vcf.gz", "--field", "GP", "--out", "o", "--dry-run"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 134 and "Cannot find the field GT" in r.stderr
+    with pytest.raises(ValueError, match="beyond the ALT list"):
+        plpio.load_plp(str(tmp_path / "p"), str(tmp_path / "bad_gt.vcf.gz"), field="GT")
+    r = subprocess.run([exe, "demuxlet", "--plp", "p", "--vcf", "bad_gt.vcf.gz", "--field", "GT", "--out", "o", "--dry-run"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 134 and "beyond the ALT list" in r.stderr

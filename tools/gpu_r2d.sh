@@ -1,0 +1,26 @@
+#!/bin/bash
+# round-2 visit D: all GPU tests, bench line, seeding batch-size sweep
+TAG=${1:-r2d}
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -12 gpurun_out/${TAG}_pytest.log
+for B in 8 16 32 64; do
+  echo "== PSCL_SEED_BATCH=$B"; PSCL_SEED_BATCH=$B timeout 300 python tools/time_seed.py 10000 8 100000 2000 2>&1 | grep -E "seed \(greedy\)|cluster sizes"
+done
+echo "== 20k x nS16"; PSCL_SEED_BATCH=16 timeout 300 python tools/time_seed.py 20000 16 500000 4000 2>&1 | grep -E "seed \(greedy\)|estep 1|cluster sizes"
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"; tail -3 gpurun_out/${TAG}_bench.err
+python - <<PY
+import json
+try:
+    j = json.loads(open("gpurun_out/${TAG}_bench.json").read())
+    print("value %.3g ms_per_step %.4f kernel_ms %.4f frac %.3f e2e %.3g" % (j["value"], j["ms_per_step"], j["roofline"]["kernel_ms"], j["roofline"]["frac"], j["e2e"]["value"]))
+    print("e2e totals", j["e2e"]["repeat_totals_ms"])
+    for k, v in (j.get("strong") or {}).items():
+        print(k, {a: v.get(a) for a in ("ms", "balance", "ms_per_iter", "estep_ms", "allreduce_ms", "seed_ms", "error")})
+    print(json.dumps(j.get("extra"), indent=1)[:1500])
+except Exception as e:
+    print("bench parse failed", e)
+PY
+PSCL_TRACE=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras 2>&1 >/dev/null | grep pscl_demux_run | tail -4
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --kernel lane | python -c "
+import sys,json
+j=json.loads(sys.stdin.read()); print('lane kernel_ms', round(j['roofline']['kernel_ms'],4), 'frac', round(j['roofline']['frac'],3))"
