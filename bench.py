@@ -459,11 +459,12 @@ def main():
     keep = []
     from popscle_b200 import Pileup
     arrs = {}
-    # ABI 3 compact host arrays (what the CLI host builds): first SNP per cell + 16-bit SNP gaps + 8-bit base-call
-    # counts for the pairs, allele<<6|qual for the base-calls
+    # the compact host arrays the CLI hosts build (ABI 6): first SNP per cell, 8-bit SNP gaps and 2-bit base-call counts with
+    # the rare large values on the side (1.25 B per pair), allele<<6|qual for the base-calls (1 B each)
     p32, aq = plp.compact()
-    first, d16, n8 = plp.compact3()
-    for name, src in (("cell_ptr", plp.cell_ptr), ("cell_first_snp", first), ("pair_snp_delta16", d16), ("pair_nreads8", n8), ("read_aq", aq)):
+    first, d8, gbig, cbp, n2, nbig, nbp = plp.compact4()
+    for name, src in (("cell_ptr", plp.cell_ptr), ("cell_first_snp", first), ("pair_snp_delta8", d8), ("snp_gap_big", gbig), ("cell_gap_big_ptr", cbp),
+                      ("pair_nreads2", n2), ("nreads_big", nbig), ("nreads_big_ptr", nbp), ("read_aq", aq)):
         t_, v_ = pin(src); keep.append(t_); arrs[name] = v_
     # genotypes the way the CLI host hands them over for --field GT (ABI 4): one byte per (SNP, sample) hard call and the
     # genotype error rate; the library builds the mixed table (sc_drop_seq.cpp:287-315) on the device
@@ -472,11 +473,11 @@ def main():
     gp_pin = RawGeno(gt8=gt_pin, err=0.1)
     hplp = Pileup(plp.n_cells, plp.n_snps, arrs["cell_ptr"], plp.pair_snp, plp.pair_read_ptr, plp.read_allele, plp.read_qual, None)
     hplp._compact = (p32, arrs["read_aq"])  # pinned copies are what crosses the ABI
-    hplp._compact3 = (arrs["cell_first_snp"], arrs["pair_snp_delta16"], arrs["pair_nreads8"])
+    hplp._compact4 = tuple(arrs[k] for k in ("cell_first_snp", "pair_snp_delta8", "snp_gap_big", "cell_gap_big_ptr", "pair_nreads2", "nreads_big", "nreads_big_ptr"))
     h2d = sum(v.nbytes for v in arrs.values()) + gt_pin.nbytes
     d2h = 160 * plp.n_cells
     for _ in range(2):
-        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
+        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=4)
     barrier()
     e2e_steps = max(3, min(args.steps, 200))  # the same K steps as the device-resident arm
     # The GPU boxes are shared hosts: single calls stalled for 5-900 ms in some visits (profiles/r0*_bench.json,
@@ -490,7 +491,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             tc = time.perf_counter()
-            out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=3)
+            out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=4)
             per_call.append(round((time.perf_counter() - tc) * 1e3, 3))
         torch.cuda.synchronize()
         totals.append(time.perf_counter() - t0)
@@ -543,7 +544,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "repeats": E2E_REPEATS, "repeat_totals_ms": [round(x * 1e3, 3) for x in e2e_totals],
                         "reported": "median repeat", "numa_bound": bool(numa_bound),
-                        "ms_per_call": per_call[:32], "api": "pscl_demux_run (pinned host buffers in compact form: 3 B per pair, 1 B per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
+                        "ms_per_call": per_call[:32], "api": "pscl_demux_run (pinned host buffers in compact form: 1.25 B per pair + the rare large gaps / counts, 1 B per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if strong is not None:
             line["strong"] = strong

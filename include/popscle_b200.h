@@ -76,6 +76,23 @@ typedef struct pscl_pileup {
   const int32_t* cell_first_snp;     /* [C]   SNP id of the first pair of each cell (any value for empty cells) */
   const uint16_t* pair_snp_delta16;  /* [P]                                                      */
   const uint8_t* pair_nreads8;       /* [P]   base-calls of each pair                            */
+  /* ABI 6: the same two pair arrays in 1.25 B per pair (5 B per pair over PCIe became 1.3).  SNP gaps are small
+   * (a cell covers ~2 % of the SNPs in ascending order) and so are the counts (1.3 base-calls per pair on average), so both
+   * are stored short with the rare large values on the side, in pair order:
+   *   pair_snp_delta8[p]  = the gap to the previous pair's SNP id if it is < 255, else 255 and the gap itself is the next
+   *                         unread entry of snp_gap_big; 0 (ignored) at a cell's first pair;
+   *   cell_gap_big_ptr[c] = how many entries of snp_gap_big belong to the cells before c;
+   *   pair_nreads2        = two bits per pair, pair p in bits 2*(p%4).. of byte p/4: 1..3 base-calls, or 0 and the count
+   *                         (4..255) is the next unread entry of nreads_big;
+   *   nreads_big_ptr[k]   = how many entries of nreads_big belong to the pairs before 1024*k.
+   * Given together with cell_first_snp (ABI 3); pair_snp_delta8 + pair_nreads2 replace pair_snp_delta16 + pair_nreads8. */
+  const uint8_t* pair_snp_delta8;    /* [P]                                                      */
+  const uint32_t* snp_gap_big;       /* [n_gap_big]                                              */
+  const int64_t* cell_gap_big_ptr;   /* [C+1]                                                    */
+  const uint8_t* pair_nreads2;       /* [(P+3)/4]                                                */
+  const uint8_t* nreads_big;         /* [n_nreads_big]                                           */
+  const int64_t* nreads_big_ptr;     /* [P/1024 + 2]                                             */
+  int64_t n_gap_big, n_nreads_big;
 } pscl_pileup;
 
 /* Genotype table (replaces sc_snp_t::gps, sc_drop_seq.h:29-37, filled at

@@ -32,7 +32,10 @@ class CPileup(C.Structure):
                 ("cell_ptr", C.c_void_p), ("pair_snp", C.c_void_p), ("pair_read_ptr", C.c_void_p),
                 ("read_allele", C.c_void_p), ("read_qual", C.c_void_p), ("snp_af", C.c_void_p),
                 ("pair_read_ptr32", C.c_void_p), ("read_aq", C.c_void_p),
-                ("cell_first_snp", C.c_void_p), ("pair_snp_delta16", C.c_void_p), ("pair_nreads8", C.c_void_p)]
+                ("cell_first_snp", C.c_void_p), ("pair_snp_delta16", C.c_void_p), ("pair_nreads8", C.c_void_p),
+                ("pair_snp_delta8", C.c_void_p), ("snp_gap_big", C.c_void_p), ("cell_gap_big_ptr", C.c_void_p),
+                ("pair_nreads2", C.c_void_p), ("nreads_big", C.c_void_p), ("nreads_big_ptr", C.c_void_p),
+                ("n_gap_big", C.c_int64), ("n_nreads_big", C.c_int64)]
 
 
 class CGeno(C.Structure):
@@ -165,7 +168,45 @@ class Pileup:
             self._compact3 = c
         return c
 
+    def compact4(self):
+        """The ABI-6 pair arrays (1.25 B per pair): (cell_first_snp, pair_snp_delta8, snp_gap_big, cell_gap_big_ptr,
+        pair_nreads2, nreads_big, nreads_big_ptr), or None when a pair has no or >= 256 base-calls."""
+        c = getattr(self, "_compact4", 0)
+        if c == 0:
+            c = None
+            P, Cn = self.n_pairs, self.n_cells
+            nrd = np.diff(self.pair_read_ptr)
+            starts = self.cell_ptr[:-1]
+            nonempty = self.cell_ptr[1:] > starts
+            first = np.zeros(Cn, dtype=np.int32)
+            gap = np.zeros(P, dtype=np.int64)
+            if P:
+                gap[1:] = np.diff(self.pair_snp.astype(np.int64))
+                gap[starts[nonempty]] = 0
+                first[nonempty] = self.pair_snp[starts[nonempty]]
+            if P == 0 or (gap.min() >= 0 and gap.max() < (1 << 32) and nrd.min() >= 1 and nrd.max() < 256):
+                big = gap >= 255
+                d8 = np.where(big, 255, gap).astype(np.uint8)
+                gap_big = gap[big].astype(np.uint32)
+                cum_big = np.concatenate([[0], np.cumsum(big)]).astype(np.int64)
+                cell_big_ptr = np.ascontiguousarray(cum_big[self.cell_ptr])
+                esc = nrd >= 4
+                f2 = np.where(esc, 0, nrd).astype(np.uint8)
+                pad = (-P) % 4
+                f2p = np.concatenate([f2, np.zeros(pad, np.uint8)]).reshape(-1, 4)
+                n2 = (f2p[:, 0] | (f2p[:, 1] << 2) | (f2p[:, 2] << 4) | (f2p[:, 3] << 6)).astype(np.uint8)
+                nbig = nrd[esc].astype(np.uint8)
+                cum_esc = np.concatenate([[0], np.cumsum(esc)]).astype(np.int64)
+                blocks = np.minimum(np.arange(P // 1024 + 2, dtype=np.int64) * 1024, P)
+                nbig_ptr = np.ascontiguousarray(cum_esc[blocks])
+                c = (first, d8, gap_big, cell_big_ptr, np.ascontiguousarray(n2), nbig, nbig_ptr)
+            self._compact4 = c
+        return c
+
     def c_struct(self, cls=CPileup, compact=False):
+        """compact: False = wide arrays; True / 2 = ABI 2 (32-bit offsets, packed reads); 3 = ABI 3 (16-bit SNP gaps, 8-bit
+        counts); 4 = ABI 6 (8-bit gaps, 2-bit counts, exceptions on the side) — each falls back to the previous form when
+        the pileup does not fit it."""
         s = cls()
         s.n_cells, s.n_snps, s.n_pairs, s.n_reads = self.n_cells, self.n_snps, self.n_pairs, self.n_reads
         s.cell_ptr = self.cell_ptr.ctypes.data
@@ -178,8 +219,17 @@ class Pileup:
             p32, aq = self.compact()
             s.pair_read_ptr32, s.read_aq = p32.ctypes.data, aq.ctypes.data
             s.pair_read_ptr = s.read_allele = s.read_qual = None
-            c3 = self.compact3() if compact == 3 else None
-            if c3 is not None:  # ABI 3: only deltas and counts for the pair arrays
+            c4 = self.compact4() if compact == 4 else None
+            c3 = self.compact3() if compact == 3 or (compact == 4 and c4 is None) else None
+            if c4 is not None:
+                first, d8, gbig, cbp, n2, nbig, nbp = c4
+                s.cell_first_snp, s.pair_snp_delta8, s.cell_gap_big_ptr = first.ctypes.data, d8.ctypes.data, cbp.ctypes.data
+                s.snp_gap_big = gbig.ctypes.data if len(gbig) else None
+                s.pair_nreads2, s.nreads_big_ptr = n2.ctypes.data, nbp.ctypes.data
+                s.nreads_big = nbig.ctypes.data if len(nbig) else None
+                s.n_gap_big, s.n_nreads_big = len(gbig), len(nbig)
+                s.pair_snp = s.pair_read_ptr32 = None
+            elif c3 is not None:  # ABI 3: only deltas and counts for the pair arrays
                 s.cell_first_snp, s.pair_snp_delta16, s.pair_nreads8 = (x.ctypes.data for x in c3)
                 s.pair_snp = s.pair_read_ptr32 = None
         return s

@@ -122,10 +122,10 @@ def demuxlet(argv, engine=None):
     own = engine is None
     eng = engine or _default_engine(o["gpus"])
     try:
-        # the compact boundary, as the C++ host uses it: delta-coded pair arrays (ABI 3) when they fit, raw posteriors or
+        # the compact boundary, as the C++ host uses it: 8-bit SNP gaps / 2-bit counts (ABI 6) when they fit, raw posteriors or
         # hard calls + error rates (ABI 4) mixed on the device
         if getattr(eng, "accepts_compact", False):
-            cells = eng.demux_run(L.plp, L.geno.raw(), L.geno.has_gp, alphas, o["doublet-prior"], compact=3)
+            cells = eng.demux_run(L.plp, L.geno.raw(), L.geno.has_gp, alphas, o["doublet-prior"], compact=4)
         else:  # an engine with the plain interface (the tests' CPU stand-in)
             cells = eng.demux_run(L.plp, L.geno.gp, L.geno.has_gp, alphas, o["doublet-prior"])
     finally:

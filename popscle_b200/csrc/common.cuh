@@ -40,7 +40,7 @@ struct pscl_plp {
   int32_t* item_order = nullptr;   // [n_items]
   int32_t* cell_item_ptr = nullptr;  // [C+1]
   std::vector<int32_t> h_cell_item_ptr, h_item_cell, h_item_order;
-  std::vector<int64_t> h_cell_ptr, h_item_pbeg, h_item_pend;
+  std::vector<int64_t> h_cell_ptr, h_item_pbeg, h_item_pend, h_cell_gap_ptr;
   // SNP-major view for the freemuxlet M-step (built lazily)
   int64_t* snp_ptr = nullptr;    // [V+1]
   uint32_t* snp_pair = nullptr;  // [P] pair ids, ascending cell id inside one SNP
@@ -59,6 +59,11 @@ struct pscl_plp {
   // by slice), the upload's validity flag, and the slices themselves (cells [stage_cell[k], stage_cell[k+1]))
   int32_t* d_first = nullptr;
   uint16_t* d_delta = nullptr;
+  // ABI-6 form of the same: 8-bit gaps (255 = the next entry of d_gap_big), first big gap of every cell
+  uint8_t* d_delta8 = nullptr;
+  uint32_t* d_gap_big = nullptr;
+  int64_t* d_cell_gap_ptr = nullptr;
+  int64_t n_gap_big = 0;
   int* d_bad = nullptr;
   int n_stages = 0;
   int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};

@@ -221,6 +221,64 @@ __global__ void k_decode_snp(const int64_t* __restrict__ cell_ptr, const int32_t
   }
   if (oob && lane == 0) atomicExch(bad, 2);
 }
+// ABI 6: SNP ids from 8-bit gaps with the large ones on the side, one warp per cell, 32 gaps per step.  gap_big is indexed
+// from the cell's own first large gap (cell_gap_ptr) plus the rank of the marker inside the cell.
+__global__ void k_decode_snp8(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ first, const uint8_t* __restrict__ delta8,
+                              const uint32_t* __restrict__ gap_big, const int64_t* __restrict__ cell_gap_ptr, int64_t n_gap_big, int32_t C, int32_t V,
+                              int32_t* __restrict__ pair_snp, int* bad) {
+  const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
+  if (b >= e) return;
+  int run = first[c];
+  int64_t big = cell_gap_ptr[c];
+  bool oob = run < 0 || run >= V;
+  for (int64_t base = b; base < e; base += 32) {
+    const int64_t p = base + lane;
+    int d = (p < e && p > b) ? (int)delta8[p] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, d == 255);
+    if (d == 255) {
+      const int64_t k = big + __popc(m & ((1u << lane) - 1u));
+      if (k < n_gap_big) d = (int)gap_big[k]; else { d = 0; oob = true; }
+    }
+    big += __popc(m);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, d, o); if (lane >= o) d += t; }
+    const int id = run + d;
+    if (p < e) { pair_snp[p] = id; oob |= id < 0 || id >= V; }
+    run = __shfl_sync(0xffffffffu, id, 31);
+  }
+  if (big != cell_gap_ptr[c + 1]) oob = true;  // the cell used more or fewer large gaps than the host says it owns
+  if (__any_sync(0xffffffffu, oob) && lane == 0) atomicExch(bad, 2);
+}
+// ABI 6: base-call counts from two bits per pair with the counts >= 4 on the side; one warp per block of 1024 GLOBAL pair
+// indices (blk_ptr[k] = large counts before pair 1024*k); the image holds pairs [pair_base, pair_base + P) of the host's
+// arrays (pair_base != 0 for the barcode shards of pscl_multi_demux_run).  n2 starts at the byte of pair g_first,
+// big at entry blk_ptr[0] of the host's array.
+__global__ void k_expand_counts2(const uint8_t* __restrict__ n2, const uint8_t* __restrict__ big, const int64_t* __restrict__ blk_ptr,
+                                 int64_t g_first, int64_t pair_base, int64_t P, int64_t n_big, uint8_t* __restrict__ cnt8, int* bad) {
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t g0 = g_first + gw * 1024, end = pair_base + P;
+  if (g0 >= end) return;
+  int64_t run = blk_ptr[gw] - blk_ptr[0];
+  bool wrong = false;
+  for (int step = 0; step < 32; ++step) {
+    const int64_t g = g0 + step * 32 + lane;
+    unsigned f = 1;
+    if (g < end) f = (n2[(g - g_first) >> 2] >> (2 * (int)(g & 3))) & 3u;
+    const unsigned m = __ballot_sync(0xffffffffu, f == 0u);
+    if (f == 0u) {
+      const int64_t k = run + __popc(m & ((1u << lane) - 1u));
+      if (k < n_big) f = big[k]; else wrong = true;
+      if (f == 0u) wrong = true;  // a pair has at least one base-call
+    }
+    run += __popc(m);
+    if (g >= pair_base && g < end) cnt8[g - pair_base] = (uint8_t)f;
+  }
+  if (__any_sync(0xffffffffu, wrong) && lane == 0) atomicExch(bad, 3);
+}
+
 // ABI 3: read offsets from 8-bit counts are an exclusive scan (CUB); this checks that they end at n_reads
 __global__ void k_check_total(const uint32_t* __restrict__ pair_rd, int64_t P, int64_t N, int* bad) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && (int64_t)pair_rd[P] != N) atomicExch(bad, 3);
@@ -250,9 +308,9 @@ __global__ void k_check_pairs(const int32_t* __restrict__ pair_snp, const uint32
 }
 
 static const char* pscl_bad_pileup_msg(int bad) {
-  return bad == 2 ? "pair_snp / pair_snp_delta16 holds a SNP id outside [0, n_snps)"
+  return bad == 2 ? "pair_snp / pair_snp_delta16 / pair_snp_delta8 holds a SNP id outside [0, n_snps) (or the large-gap list does not match its markers)"
        : bad == 5 ? "pair_read_ptr is not non-decreasing inside [0, n_reads]"
-       : bad == 3 ? "pair_nreads8 does not sum to n_reads"
+       : bad == 3 ? "pair_nreads8 / pair_nreads2 does not sum to n_reads (or the large-count list does not match its markers)"
                   : "read_allele must be 0/1/2 and read_qual <= 63 (dsc-pileup writes phred <= 40, cmd_cram_dsc_pileup.cpp:19-20)";
 }
 
@@ -263,7 +321,7 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
     if (p->n_stages && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // slices still in flight write into d_delta
     cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_bad);
+  cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_bad); cudaFree(p->d_delta8); cudaFree(p->d_gap_big); cudaFree(p->d_cell_gap_ptr);
   cudaFree(p->cell_ptr); cudaFree(p->pair_snp); cudaFree(p->pair_rd); cudaFree(p->rd_aq);
   cudaFree(p->snp_af); cudaFree(p->item_cell); cudaFree(p->item_pbeg);
   cudaFree(p->item_pend); cudaFree(p->item_order); cudaFree(p->cell_item_ptr); cudaFree(p->snp_ptr);
@@ -330,7 +388,9 @@ static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cel
 
 // read_base: the host's read offsets (pair_read_ptr / pair_read_ptr32) and read arrays belong to a longer pileup and
 // this image starts at base-call `read_base` of it (barcode shards of pscl_multi_demux_run point into the caller's arrays).
-static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages, int64_t read_base = 0) {
+// pair_base: the same for the ABI-6 count arrays (pair_nreads2 / nreads_big / nreads_big_ptr are indexed by the caller's
+// global pair numbers; every other array of a shard view is already offset).
+static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages, int64_t read_base = 0, int64_t pair_base = 0) {
   if (!h || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_plp_upload: NULL argument");
   *out = nullptr;
   static const bool trace = getenv("PSCL_TRACE") != nullptr;  // wall-clock of the upload's phases on stderr
@@ -341,8 +401,12 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   const int64_t P = h->n_pairs, N = h->n_reads;
   if (C < 0 || V < 0 || P < 0 || N < 0) return pscl_fail(ctx, PSCL_EINVAL, "negative size in pscl_pileup");
   const bool ptr32 = h->pair_read_ptr32 != nullptr, packed = h->read_aq != nullptr;
-  const bool dsnp = h->pair_snp_delta16 != nullptr && h->cell_first_snp != nullptr, cnt8 = h->pair_nreads8 != nullptr;
-  if (!h->cell_ptr || (P > 0 && ((!h->pair_snp && !dsnp) || (!h->pair_read_ptr && !ptr32 && !cnt8))) ||
+  // ABI 6 forms win over ABI 3 ones when both are given
+  const bool dsnp8 = h->pair_snp_delta8 != nullptr && h->cell_first_snp != nullptr && h->cell_gap_big_ptr != nullptr && (h->n_gap_big == 0 || h->snp_gap_big);
+  const bool cnt2 = h->pair_nreads2 != nullptr && h->nreads_big_ptr != nullptr && (h->n_nreads_big == 0 || h->nreads_big);
+  const bool dsnp = !dsnp8 && h->pair_snp_delta16 != nullptr && h->cell_first_snp != nullptr;
+  const bool cnt8 = cnt2 || h->pair_nreads8 != nullptr;  // cnt2 is expanded to 8-bit counts on the device first
+  if (!h->cell_ptr || (P > 0 && ((!h->pair_snp && !dsnp && !dsnp8) || (!h->pair_read_ptr && !ptr32 && !cnt8))) ||
       (N > 0 && !packed && (!h->read_allele || !h->read_qual)))
     return pscl_fail(ctx, PSCL_EINVAL, "pscl_pileup has a NULL array");
   if (N >= ((int64_t)1 << 32) || P >= ((int64_t)1 << 32))
@@ -355,7 +419,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
                                : (h->pair_read_ptr[0] != read_base || h->pair_read_ptr[P] != read_base + N)))
     return pscl_fail(ctx, PSCL_EINVAL, "pair_read_ptr must run from 0 to n_reads");
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!dsnp || P == 0 || C < 2 || !ctx->copy_stream || !ctx->h_one) stages = 1;
+  if ((!dsnp && !dsnp8) || P == 0 || C < 2 || !ctx->copy_stream || !ctx->h_one) stages = 1;
   if (stages > PSCL_MAX_STAGES) stages = PSCL_MAX_STAGES;
   pscl_plp* p = new pscl_plp();
   p->C = C; p->V = V; p->P = P; p->N = N;
@@ -369,17 +433,29 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   };
   cudaError_t e = cudaSuccess;
   const char* where = "";  // the first step that failed (named in the error message)
+  int64_t n_gap_local = 0;
 #define UP(field, src, bytes) do { if (e == cudaSuccess) { e = up((void**)&p->field, src, bytes); if (e != cudaSuccess) where = #field; } } while (0)
 #define STEP(name) do { if (e != cudaSuccess && !*where) where = name; } while (0)
   UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
-  uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr;
+  uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr, *d_n2 = nullptr, *d_nbig = nullptr;
+  int64_t* d_nblk = nullptr;
+  int64_t n_big_local = 0, n2_first = 0;
   void* d_scan_tmp = nullptr;
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_bad, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_bad, 0, sizeof(int), ctx->stream);
   if (cnt8) {  // ABI 3: 8-bit base-call counts, offsets by an exclusive scan
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_cnt, (size_t)P + 1);  // one zero byte of slack: the scan's last output is the total
     if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt + P, 0, 1, ctx->stream);
-    if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(d_cnt, h->pair_nreads8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
+    if (cnt2 && P > 0) {  // ABI 6: two bits per pair + the large counts, expanded by k_expand_counts2
+      const int64_t k0 = pair_base / 1024, k1 = (pair_base + P + 1023) / 1024, g_first = k0 * 1024;
+      const int64_t byte0 = g_first / 4, byte1 = (pair_base + P + 3) / 4, big0 = h->nreads_big_ptr[k0], big1 = h->nreads_big_ptr[k1];
+      if (big0 < 0 || big1 < big0 || big1 > h->n_nreads_big) { pscl_plp_free(ctx, p); return pscl_fail(ctx, PSCL_EINVAL, "nreads_big_ptr does not index nreads_big"); }
+      n_big_local = big1 - big0;
+      if (e == cudaSuccess) e = up((void**)&d_n2, h->pair_nreads2 + byte0, (size_t)(byte1 - byte0));
+      if (e == cudaSuccess) e = up((void**)&d_nbig, h->nreads_big ? h->nreads_big + big0 : nullptr, (size_t)n_big_local);
+      if (e == cudaSuccess) e = up((void**)&d_nblk, h->nreads_big_ptr + k0, sizeof(int64_t) * (size_t)(k1 - k0 + 1));
+      n2_first = g_first;
+    } else if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(d_cnt, h->pair_nreads8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
     STEP("pair_nreads8 / pair_rd");
   } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
@@ -392,9 +468,22 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
     STEP("read_allele / read_qual");
   }
-  if (dsnp) {  // ABI 3: 16-bit SNP gaps, decoded per cell
+  if (dsnp || dsnp8) {  // ABI 3 / 6: 16-bit or 8-bit SNP gaps, decoded per cell
     if (e == cudaSuccess) e = up((void**)&p->d_first, h->cell_first_snp, sizeof(int32_t) * C);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_delta, sizeof(uint16_t) * (size_t)P + 16);  // k_decode_snp reads whole 16-byte groups
+    if (dsnp) {
+      if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_delta, sizeof(uint16_t) * (size_t)P + 16);  // k_decode_snp reads whole 16-byte groups
+    } else {
+      const int64_t g0 = h->cell_gap_big_ptr[0], g1 = h->cell_gap_big_ptr[C];
+      if (g0 < 0 || g1 < g0 || g1 > h->n_gap_big) { pscl_plp_free(ctx, p); return pscl_fail(ctx, PSCL_EINVAL, "cell_gap_big_ptr does not index snp_gap_big"); }
+      n_gap_local = g1 - g0;
+      p->n_gap_big = n_gap_local;
+      std::vector<int64_t>& cg = p->h_cell_gap_ptr;  // rebased to this image's first large gap
+      cg.resize((size_t)C + 1);
+      for (int32_t c = 0; c <= C; ++c) cg[c] = h->cell_gap_big_ptr[c] - g0;
+      if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_delta8, (size_t)P + 16);
+      if (e == cudaSuccess) e = up((void**)&p->d_gap_big, h->snp_gap_big ? h->snp_gap_big + g0 : nullptr, sizeof(uint32_t) * (size_t)n_gap_local);
+      if (e == cudaSuccess) e = up((void**)&p->d_cell_gap_ptr, cg.data(), sizeof(int64_t) * ((size_t)C + 1));
+    }
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_snp, sizeof(int32_t) * (P ? P : 1));
     if (stages > 1) {  // slices of whole cells with about equal pair counts; their copies are queued in step 2b
       p->n_stages = stages;
@@ -406,7 +495,8 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       }
       p->stage_cell[stages] = C;
     } else if (e == cudaSuccess && P > 0) {
-      e = cudaMemcpyAsync(p->d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P, cudaMemcpyHostToDevice, ctx->stream);
+      e = dsnp ? cudaMemcpyAsync(p->d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P, cudaMemcpyHostToDevice, ctx->stream)
+               : cudaMemcpyAsync(p->d_delta8, h->pair_snp_delta8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
     }
   } else {
     UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
@@ -427,7 +517,9 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_go, 0);
     for (int k = 0; k < p->n_stages && e == cudaSuccess; ++k) {
       const int64_t pb = h->cell_ptr[p->stage_cell[k]], pe = h->cell_ptr[p->stage_cell[k + 1]];
-      if (pe > pb) e = cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (pe > pb)
+        e = dsnp ? cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream)
+                 : cudaMemcpyAsync(p->d_delta8 + pb, h->pair_snp_delta8 + pb, (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
       // PSCL_FAULT=drop_stage_flag (fault-injection test): the last slice's flag never arrives, the kernel must time out
       const bool drop = k == p->n_stages - 1 && getenv("PSCL_FAULT") && !strcmp(getenv("PSCL_FAULT"), "drop_stage_flag");
       if (e == cudaSuccess && !drop) e = cudaMemcpyAsync(ctx->stage_flags + k, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream);
@@ -435,8 +527,16 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   }
 
   // ---- 3. device-side decoding and checks ------------------------------------------------------------
-  if (dsnp && p->n_stages == 0 && e == cudaSuccess && C > 0 && P > 0) {
-    k_decode_snp<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta, 0, C, V, p->pair_snp, p->d_bad);
+  if ((dsnp || dsnp8) && p->n_stages == 0 && e == cudaSuccess && C > 0 && P > 0) {
+    if (dsnp) k_decode_snp<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta, 0, C, V, p->pair_snp, p->d_bad);
+    else k_decode_snp8<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta8, p->d_gap_big, p->d_cell_gap_ptr,
+                                                                                       n_gap_local, C, V, p->pair_snp, p->d_bad);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (cnt2 && P > 0 && e == cudaSuccess) {
+    const int64_t warps = (pair_base + P - n2_first + 1023) / 1024;
+    k_expand_counts2<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_n2, d_nbig, d_nblk, n2_first, pair_base, P, n_big_local, d_cnt, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
   }
@@ -459,8 +559,8 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess && P > 0 && (!dsnp || !cnt8) && p->n_stages == 0) {
-    k_check_pairs<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(p->pair_snp, p->pair_rd, P, V, N, dsnp ? 0 : 1, p->d_bad);
+  if (e == cudaSuccess && P > 0 && ((!dsnp && !dsnp8) || !cnt8) && p->n_stages == 0) {
+    k_check_pairs<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(p->pair_snp, p->pair_rd, P, V, N, (dsnp || dsnp8) ? 0 : 1, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
   }
@@ -476,8 +576,11 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   // the host vectors above are pageable sources of async copies: drain before they go out of scope
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   STEP("drain (a copy or kernel of the upload failed on the device)");
-  cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp);
-  if (p->n_stages == 0) { cudaFree(p->d_delta); cudaFree(p->d_first); p->d_delta = nullptr; p->d_first = nullptr; }
+  cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp); cudaFree(d_n2); cudaFree(d_nbig); cudaFree(d_nblk);
+  if (p->n_stages == 0) {
+    cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_delta8); cudaFree(p->d_gap_big); cudaFree(p->d_cell_gap_ptr);
+    p->d_delta = nullptr; p->d_first = nullptr; p->d_delta8 = nullptr; p->d_gap_big = nullptr; p->d_cell_gap_ptr = nullptr;
+  }
   if (trace) {
     const auto tr3 = tnow(false);
     fprintf(stderr, "[pscl_plp_upload] checks + enqueue %.3f ms | work items (host) %.3f | item arrays, decode, drain %.3f | stages %d\n", tms(tr0, tr1), tms(tr1, tr2), tms(tr2, tr3), p->n_stages);

@@ -92,6 +92,10 @@ struct DemuxArgs {
   // staged run (k_demux_default<NV, true>): SNP ids come from the ABI-3 gaps, which are still crossing PCIe in slices of
   // whole cells when the kernel starts; flags[k] is written behind slice k by the same copy queue
   const uint16_t* delta = nullptr;     // [P] gap to the previous pair's SNP id (ignored at a cell's first pair)
+  const uint8_t* delta8 = nullptr;     // ABI 6 (DELTA == 2): the same in 8 bits, 255 = the next entry of gap_big
+  const uint32_t* gap_big = nullptr;
+  const int64_t* cell_gap_ptr = nullptr;  // [C+1] first large gap of every cell
+  int64_t n_gap_big = 0;
   const int32_t* first = nullptr;      // [C] SNP id of each cell's first pair
   const int64_t* cell_ptr = nullptr;   // [C+1]
   const int32_t* item_cell = nullptr;  // [n_items]
@@ -110,7 +114,7 @@ struct DemuxArgs {
 // NT threads per CTA, one CTA per SM.  (Splitting a work item's running products between two warps, so that 12 or 16
 // warps fit an SM at 158 / 128 registers, was measured at 0.67 / 0.71 ms against 0.53 ms for this form: the duplicated
 // fold and the extra work items cost more than the added warps hide; profiles/r2a_variants.txt.)
-template <int NV, bool DELTA, bool DICT, int NT>
+template <int NV, int DELTA, bool DICT, int NT>
 __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
   constexpr int ND = Cfg::ND, SD = Cfg::STRIDE_D, NAM = Cfg::NE;
@@ -142,7 +146,8 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
     const int niter = (int)((pe - pb + 31) >> 5);
     int snp_run = 0;       // DELTA: SNP id of the pair before the next 32
     int64_t cell_pb = -1;  // DELTA: first pair of the item's cell
-    if constexpr (DELTA) {
+    int64_t big_run = 0;   // DELTA == 2: next unread entry of gap_big
+    if constexpr (DELTA != 0) {
       const int c = a.item_cell[item];
       cell_pb = a.cell_ptr[c];
       int k = 0;
@@ -159,9 +164,21 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
       }
       __syncwarp();
       snp_run = a.first[c];
+      if constexpr (DELTA == 2) big_run = a.cell_gap_ptr[c];
       if (pb > cell_pb) {  // a later work item of a large cell: id of the pair before it
         int sum = 0;
-        for (int64_t q = cell_pb + 1 + lane; q < pb; q += 32) sum += (int)a.delta[q];
+        if constexpr (DELTA == 2) {  // 8-bit gaps: the markers take the large gaps in order
+          for (int64_t q0 = cell_pb + 1; q0 < pb; q0 += 32) {
+            const int64_t q = q0 + lane;
+            int d = q < pb ? (int)a.delta8[q] : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, d == 255);
+            if (d == 255) { const int64_t k = big_run + __popc(m & ((1u << lane) - 1u)); d = k < a.n_gap_big ? (int)a.gap_big[k] : 0; }
+            big_run += __popc(m);
+            sum += d;
+          }
+        } else {
+          for (int64_t q = cell_pb + 1 + lane; q < pb; q += 32) sum += (int)a.delta[q];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         snp_run += sum;
@@ -184,13 +201,24 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
       int64_t p = pb + ((int64_t)it << 5) + lane;
       okA = (it < niter) && (p < pe);
       if (okA) {
-        if constexpr (DELTA) snpA = (p == cell_pb) ? 0 : (int32_t)a.delta[p];  // the gap; issueB turns it into the id
+        if constexpr (DELTA == 1) snpA = (p == cell_pb) ? 0 : (int32_t)a.delta[p];  // the gap; issueB turns it into the id
+        else if constexpr (DELTA == 2) snpA = (p == cell_pb) ? 0 : (int32_t)a.delta8[p];
         else snpA = a.pair_snp[p];
         r0A = a.pair_rd[p]; r1A = a.pair_rd[p + 1];
       }
+      if constexpr (DELTA == 2) {  // a marker stands for the next large gap (rare: ~0.5 % of the pairs at configs[1])
+        const bool mk = okA && snpA == 255;
+        const unsigned m = __ballot_sync(0xffffffffu, mk);
+        if (mk) {
+          const int64_t k = big_run + __popc(m & ((1u << lane) - 1u));
+          if (k < a.n_gap_big) snpA = (int32_t)a.gap_big[k];
+          else { snpA = 0; atomicExch(a.bad, 2); }  // more markers than large gaps: malformed input
+        }
+        big_run += __popc(m);
+      }
     };
     auto issueB = [&](int buf) {  // consumes stage A
-      if constexpr (DELTA) {  // inclusive scan of the 32 gaps on top of the running id
+      if constexpr (DELTA != 0) {  // inclusive scan of the 32 gaps on top of the running id
         int v = okA ? snpA : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
@@ -1002,7 +1030,7 @@ extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
 #define PSCL_ROWS_NT 384
 #endif
 
-template <int NV, bool DELTA, bool DICT>
+template <int NV, int DELTA, bool DICT>
 static cudaError_t launch_default_v(pscl_ctx* ctx, const DemuxArgs& a) {
   constexpr int NT = DICT ? PSCL_DICT_NT : PSCL_ROWS_NT;
   using Cfg = DefaultCfg<NV>;
@@ -1025,8 +1053,9 @@ static cudaError_t launch_default_v(pscl_ctx* ctx, const DemuxArgs& a) {
 
 template <int NV>
 static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
-  if (a.gp_code) return a.delta ? launch_default_v<NV, true, true>(ctx, a) : launch_default_v<NV, false, true>(ctx, a);
-  return a.delta ? launch_default_v<NV, true, false>(ctx, a) : launch_default_v<NV, false, false>(ctx, a);
+  const int delta = a.delta8 ? 2 : a.delta ? 1 : 0;  // staged run on 8-bit (ABI 6) / 16-bit (ABI 3) SNP gaps, or plain SNP ids
+  if (a.gp_code) return delta == 2 ? launch_default_v<NV, 2, true>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, true>(ctx, a) : launch_default_v<NV, 0, true>(ctx, a);
+  return delta == 2 ? launch_default_v<NV, 2, false>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, false>(ctx, a) : launch_default_v<NV, 0, false>(ctx, a);
 }
 
 extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
@@ -1108,7 +1137,9 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
       if (plp->n_stages > 1) {  // staged pscl_demux_run: ids from the gaps, slice by slice as they land
         if (!use_default || use_ws || a.item_order == nullptr)
           return pscl_fail(ctx, PSCL_ESTATE, "a staged pileup image can only be scored whole by k_demux_default");
-        a.delta = plp->d_delta; a.first = plp->d_first; a.cell_ptr = plp->cell_ptr; a.item_cell = plp->item_cell;
+        a.delta = plp->d_delta; a.delta8 = plp->d_delta8; a.gap_big = plp->d_gap_big; a.cell_gap_ptr = plp->d_cell_gap_ptr;
+        a.n_gap_big = plp->n_gap_big;
+        a.first = plp->d_first; a.cell_ptr = plp->cell_ptr; a.item_cell = plp->item_cell;
         a.flags = ctx->stage_flags; a.bad = plp->d_bad; a.n_snps = plp->V; a.n_stages = plp->n_stages;
         a.spin_limit = ctx->stage_spin_ticks;
         for (int k = 0; k <= plp->n_stages; ++k) a.stage_cell[k] = plp->stage_cell[k];
@@ -1257,7 +1288,7 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
   int stages = 1;
   if (!llk_grid && !ctx->keep_grid && !ctx->force_general && (ctx->demux_kernel <= 1 || ctx->demux_kernel == 6) && opts->alphas && opts->n_alpha == 2 &&
       opts->alphas[0] == 0.0 && opts->alphas[1] == 0.5 && geno->n_samples >= 2 && geno->n_samples <= 8 &&
-      host->pair_snp_delta16 && host->cell_first_snp && host->n_pairs < ((int64_t)1 << 30)) {
+      (host->pair_snp_delta16 || host->pair_snp_delta8) && host->cell_first_snp && host->n_pairs < ((int64_t)1 << 30)) {
     if (const char* sv = getenv("PSCL_STAGES")) stages = atoi(sv);
     else if (host->n_pairs >= ((int64_t)1 << 22)) stages = (int)std::min<int64_t>(PSCL_MAX_STAGES, host->n_pairs / 1250000);  // ~2.5 MB of gaps per slice
     if (stages < 1) stages = 1;

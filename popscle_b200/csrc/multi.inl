@@ -226,7 +226,17 @@ extern "C" int pscl_multi_demux_run(pscl_multi* m, const pscl_pileup* host, cons
     const int64_t p = host->cell_ptr[cut[r]];
     if (host->pair_read_ptr) rcut[r] = host->pair_read_ptr[p];
     else if (host->pair_read_ptr32) rcut[r] = (int64_t)host->pair_read_ptr32[p];
-    else if (host->pair_nreads8) {  // counts only: sum them up to the cut (continuing from the previous cut)
+    else if (host->pair_nreads2 && host->nreads_big_ptr) {  // ABI 6 counts: two-bit fields + the large counts on the side
+      int64_t s = r ? rcut[r - 1] : 0;
+      const int64_t q0 = r ? host->cell_ptr[cut[r - 1]] : 0;
+      int64_t big = host->nreads_big_ptr[q0 / 1024];  // rank of the first marker at or after q0
+      for (int64_t q = (q0 / 1024) * 1024; q < q0; ++q) big += ((host->pair_nreads2[q >> 2] >> (2 * (q & 3))) & 3) == 0;
+      for (int64_t q = q0; q < p; ++q) {
+        const int f = (host->pair_nreads2[q >> 2] >> (2 * (q & 3))) & 3;
+        s += f ? f : (big < host->n_nreads_big ? host->nreads_big[big++] : 0);
+      }
+      rcut[r] = s;
+    } else if (host->pair_nreads8) {  // counts only: sum them up to the cut (continuing from the previous cut)
       int64_t s = r ? rcut[r - 1] : 0;
       for (int64_t q = r ? host->cell_ptr[cut[r - 1]] : 0; q < p; ++q) s += host->pair_nreads8[q];
       rcut[r] = s;
@@ -276,9 +286,13 @@ extern "C" int pscl_multi_demux_run(pscl_multi* m, const pscl_pileup* host, cons
     if (host->cell_first_snp) sh.cell_first_snp = host->cell_first_snp + c0;
     if (host->pair_snp_delta16) sh.pair_snp_delta16 = host->pair_snp_delta16 + p0;
     if (host->pair_nreads8) sh.pair_nreads8 = host->pair_nreads8 + p0;
+    // ABI 6: the gaps and each cell's first large gap are offset; the count arrays stay the caller's (they are indexed by
+    // global pair numbers, plp_upload_impl gets pair_base = p0)
+    if (host->pair_snp_delta8) sh.pair_snp_delta8 = host->pair_snp_delta8 + p0;
+    if (host->cell_gap_big_ptr) sh.cell_gap_big_ptr = host->cell_gap_big_ptr + c0;
     PsclScope scope__(ctx);
     pscl_plp* plp = nullptr;
-    rc2 = plp_upload_impl(ctx, &sh, &plp, 1, rcut[r]);
+    rc2 = plp_upload_impl(ctx, &sh, &plp, 1, rcut[r], p0);
     if (rc2 != PSCL_OK) return rc2;
     const double t1 = multi_now_ms();
     const bool keep = ctx->keep_grid;

@@ -67,6 +67,11 @@ struct Loaded {
   mutable std::vector<int32_t> cell_first_snp;
   mutable std::vector<uint16_t> pair_snp_delta16;
   mutable std::vector<uint8_t> pair_nreads8;
+  // ABI 6: 8-bit gaps / 2-bit counts with the large values on the side (1.25 B per pair)
+  mutable std::vector<uint8_t> pair_snp_delta8, pair_nreads2, nreads_big;
+  mutable std::vector<uint32_t> snp_gap_big;
+  mutable std::vector<int64_t> cell_gap_big_ptr, nreads_big_ptr;
+  mutable int tiny_state = 0;   // 0 not tried, 1 usable, -1 a pair without base-calls or with >= 256 of them
   mutable int delta_state = 0;  // 0 not tried, 1 usable, -1 a gap or a count does not fit
   mutable int compact_state = 0;  // the same for read_aq (an allele code > 2 or a quality > 63 rules the packed form out)
 
@@ -74,6 +79,8 @@ struct Loaded {
     pscl_pileup p;
     p.pair_read_ptr32 = nullptr; p.read_aq = nullptr;
     p.cell_first_snp = nullptr; p.pair_snp_delta16 = nullptr; p.pair_nreads8 = nullptr;
+    p.pair_snp_delta8 = nullptr; p.snp_gap_big = nullptr; p.cell_gap_big_ptr = nullptr;
+    p.pair_nreads2 = nullptr; p.nreads_big = nullptr; p.nreads_big_ptr = nullptr; p.n_gap_big = p.n_nreads_big = 0;
     if (read_allele.size() < (1ull << 32)) {  // halves the bytes pscl_plp_upload sends over PCIe
       if (pair_read_ptr32.size() != pair_read_ptr.size()) pair_read_ptr32.assign(pair_read_ptr.begin(), pair_read_ptr.end());
       if (compact_state == 0) {  // decided once per loaded pileup (a later call must not forget a failed check)
@@ -106,6 +113,36 @@ struct Loaded {
       }
       if (ok && delta_state == 1) {
         p.cell_first_snp = cell_first_snp.data(); p.pair_snp_delta16 = pair_snp_delta16.data(); p.pair_nreads8 = pair_nreads8.data();
+      }
+      if (ok && tiny_state == 0) {  // ABI 6 (the library prefers it): one byte per gap, two bits per count
+        const size_t P = pair_snp.size();
+        if (cell_first_snp.size() != (size_t)n_cells) cell_first_snp.assign((size_t)n_cells, 0);
+        pair_snp_delta8.assign(P, 0); pair_nreads2.assign((P + 3) / 4, 0);
+        snp_gap_big.clear(); nreads_big.clear();
+        cell_gap_big_ptr.assign((size_t)n_cells + 1, 0); nreads_big_ptr.assign(P / 1024 + 2, 0);
+        bool fits = true;
+        for (int32_t c = 0; c < n_cells && fits; ++c) {
+          const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
+          cell_gap_big_ptr[c] = (int64_t)snp_gap_big.size();
+          if (e > b) cell_first_snp[c] = pair_snp[b];
+          for (int64_t i = b; i < e; ++i) {
+            const int64_t d = i > b ? (int64_t)pair_snp[i] - pair_snp[i - 1] : 0, n = pair_read_ptr[i + 1] - pair_read_ptr[i];
+            if (d < 0 || n < 1 || n > 255) { fits = false; break; }
+            if (i % 1024 == 0) nreads_big_ptr[(size_t)(i / 1024)] = (int64_t)nreads_big.size();
+            if (d >= 255) { pair_snp_delta8[i] = 255; snp_gap_big.push_back((uint32_t)d); } else pair_snp_delta8[i] = (uint8_t)d;
+            if (n >= 4) nreads_big.push_back((uint8_t)n); else pair_nreads2[(size_t)(i >> 2)] |= (uint8_t)(n << (2 * (i & 3)));
+          }
+        }
+        cell_gap_big_ptr[(size_t)n_cells] = (int64_t)snp_gap_big.size();
+        for (size_t k = P / 1024 + (P % 1024 ? 1 : 0); k < nreads_big_ptr.size(); ++k) nreads_big_ptr[k] = (int64_t)nreads_big.size();
+        if (P % 1024 == 0 && P > 0) nreads_big_ptr[P / 1024] = (int64_t)nreads_big.size();
+        tiny_state = fits ? 1 : -1;
+      }
+      if (ok && tiny_state == 1) {
+        p.cell_first_snp = cell_first_snp.data(); p.pair_snp_delta8 = pair_snp_delta8.data(); p.cell_gap_big_ptr = cell_gap_big_ptr.data();
+        p.snp_gap_big = snp_gap_big.empty() ? nullptr : snp_gap_big.data(); p.n_gap_big = (int64_t)snp_gap_big.size();
+        p.pair_nreads2 = pair_nreads2.data(); p.nreads_big_ptr = nreads_big_ptr.data();
+        p.nreads_big = nreads_big.empty() ? nullptr : nreads_big.data(); p.n_nreads_big = (int64_t)nreads_big.size();
       }
     }
     p.n_cells = n_cells; p.n_snps = n_snps;

@@ -40,7 +40,7 @@ def test_library_is_sm100a_only(built):
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==112 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 && sizeof(pscl_geno)==56 && offsetof(pscl_geno, geno_err)==48 && sizeof(pscl_fmx_opts)==80 && offsetof(pscl_fmx_opts, seed)==56 && offsetof(pscl_fmx_opts, bf_thres)==64 && offsetof(pscl_fmx_opts, keep_init_missing)==76 ? 0 : 1; }\n')
+    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==176 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 && offsetof(pscl_pileup, pair_snp_delta8)==112 && offsetof(pscl_pileup, nreads_big_ptr)==152 && offsetof(pscl_pileup, n_nreads_big)==168 && sizeof(pscl_geno)==56 && offsetof(pscl_geno, geno_err)==48 && sizeof(pscl_fmx_opts)==80 && offsetof(pscl_fmx_opts, seed)==56 && offsetof(pscl_fmx_opts, bf_thres)==64 && offsetof(pscl_fmx_opts, keep_init_missing)==76 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
@@ -86,7 +86,7 @@ def test_pileup_struct_matches_the_ctypes_mirror():
     """ABI 2/3: the compact arrays sit behind the wide ones; the ctypes mirror has the same layout."""
     import ctypes as C
     from popscle_b200 import capi
-    assert C.sizeof(capi.CPileup) == 112
+    assert C.sizeof(capi.CPileup) == 176 and capi.CPileup.pair_snp_delta8.offset == 112 and capi.CPileup.nreads_big_ptr.offset == 152 and capi.CPileup.n_nreads_big.offset == 168
     assert capi.CPileup.cell_first_snp.offset == 88 and capi.CPileup.pair_snp_delta16.offset == 96 and capi.CPileup.pair_nreads8.offset == 104
     assert capi.CPileup.pair_read_ptr32.offset == 72 and capi.CPileup.read_aq.offset == 80
     assert C.sizeof(capi.CFmxOpts) == 80 and capi.CFmxOpts.bf_thres.offset == 64 and capi.CFmxOpts.keep_init_missing.offset == 76 and capi.CFmxOpts.randomize_singlet_score.offset == 52 and capi.CFmxOpts.seed.offset == 56
@@ -109,6 +109,24 @@ def test_pileup_struct_matches_the_ctypes_mirror():
     assert (np.concatenate([[0], np.cumsum(n8.astype(np.int64))]) == s.plp.pair_read_ptr).all()
     cs = s.plp.c_struct(compact=3)
     assert cs.pair_snp is None and cs.pair_read_ptr32 is None and cs.pair_nreads8 == n8.ctypes.data
+    # ABI 6: 8-bit gaps / 2-bit counts with the large values on the side decode back to the same arrays
+    big = synth.make_pileup(C=40, nv=2, V=60000, kbar=120, seed=6).plp  # mean gap 500: many markers
+    nrd = np.diff(big.pair_read_ptr); nrd[::7] = 9; nrd[5] = 255
+    big.pair_read_ptr = np.concatenate([[0], np.cumsum(nrd)]).astype(np.int64)
+    big.read_allele = np.zeros(int(big.pair_read_ptr[-1]), np.uint8); big.read_qual = np.full(int(big.pair_read_ptr[-1]), 30, np.uint8)
+    first4, d8, gbig, cbp, n2, nbig, nbp = big.compact4()
+    assert d8.dtype == np.uint8 and gbig.dtype == np.uint32 and (d8 == 255).sum() == len(gbig) > 100 and cbp[-1] == len(gbig)
+    gap = d8.astype(np.int64); gap[d8 == 255] = gbig
+    for c in range(big.n_cells):
+        b, e = big.cell_ptr[c], big.cell_ptr[c + 1]
+        assert (first4[c] + np.cumsum(gap[b:e]) == big.pair_snp[b:e]).all() and cbp[c] == (d8[:b] == 255).sum()
+    f = np.stack([(n2 >> k) & 3 for k in (0, 2, 4, 6)], 1).ravel()[:big.n_pairs].astype(np.int64)
+    assert (f == 0).sum() == len(nbig) and nbp[-1] == len(nbig) and all(nbp[k] == (f[:1024 * k] == 0).sum() for k in range(len(nbp) - 1))
+    f[f == 0] = nbig
+    assert (f == nrd).all()
+    cs = big.c_struct(compact=4)
+    assert cs.pair_snp is None and cs.pair_snp_delta16 is None and cs.pair_nreads8 is None and cs.pair_snp_delta8 == d8.ctypes.data
+    assert cs.n_gap_big == len(gbig) and cs.n_nreads_big == len(nbig) and cs.nreads_big_ptr == nbp.ctypes.data
     wide = synth.make_pileup(C=3, nv=2, V=50, kbar=10, seed=4).plp
     wide.n_snps = 200000
     wide.pair_snp = wide.pair_snp.copy(); wide.pair_snp[wide.cell_ptr[1] - 1] = 199999  # a gap >= 65536: no delta form

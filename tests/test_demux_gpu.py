@@ -470,3 +470,58 @@ def test_device_memory_exhaustion_is_reported_and_the_context_survives(built):
                 c.debug_fail_alloc(0)
         assert hit >= 5
         assert c.fmx_run(s.plp, o)[0].tobytes() == fgood.tobytes()
+
+
+def test_tiny_pileup_form_abi6_is_equivalent(ctx):
+    """ABI 6: 8-bit SNP gaps and 2-bit base-call counts with the large values on the side (1.25 B per pair) — decoded on the
+    device (k_decode_snp8 / k_expand_counts2) or, staged, inside the scoring kernel — give the records of the wide arrays bit
+    for bit: sparse SNPs (many large gaps), deep pairs (large counts), cells cut into several work items, freemuxlet."""
+    from popscle_b200 import PsclError
+    s = synth.make_pileup(C=260, nv=8, V=120000, kbar=700, seed=96)  # mean gap 170: a third of the gaps are markers
+    plp = s.plp
+    rng = np.random.default_rng(4)
+    nrd = np.diff(plp.pair_read_ptr)
+    nrd = np.where(rng.random(plp.n_pairs) < 0.03, rng.integers(4, 200, plp.n_pairs), nrd)
+    prp = np.concatenate([[0], np.cumsum(nrd)]).astype(np.int64)
+    N = int(prp[-1])
+    from popscle_b200 import Pileup
+    p2 = Pileup(plp.n_cells, plp.n_snps, plp.cell_ptr, plp.pair_snp, prp, rng.choice([0, 0, 1, 2], N).astype(np.uint8),
+                rng.integers(13, 41, N).astype(np.uint8), plp.snp_af)
+    first, d8, gbig, cbp, n2, nbig, nbp = p2.compact4()
+    assert len(gbig) > 1000 and len(nbig) > 1000
+    gp = synth.gt_to_gp(s.geno)
+    wide = ctx.demux_run(p2, gp, None, DEFAULT)
+    assert ctx.demux_run(p2, gp, None, DEFAULT, compact=4).tobytes() == wide.tobytes()
+    for stages in ("1", "2", "5", "16"):
+        os.environ["PSCL_STAGES"] = stages
+        try:
+            assert ctx.demux_run(p2, gp, None, DEFAULT, compact=4).tobytes() == wide.tobytes(), stages
+        finally:
+            del os.environ["PSCL_STAGES"]
+    # a cell of 7000 pairs: later work items start inside the cell and count the markers before them
+    s3 = synth.make_pileup(C=6, nv=5, V=200000, kbar=7000, seed=97)
+    gp3 = synth.gt_to_gp(s3.geno)
+    w3 = ctx.demux_run(s3.plp, gp3, None, DEFAULT)
+    os.environ["PSCL_STAGES"] = "3"
+    try:
+        assert ctx.demux_run(s3.plp, gp3, None, DEFAULT, compact=4).tobytes() == w3.tobytes()
+    finally:
+        del os.environ["PSCL_STAGES"]
+    # other kernels and freemuxlet decode it on upload
+    al = [0.0, 0.25, 0.5]
+    assert ctx.demux_run(p2, gp, None, al, compact=4).tobytes() == ctx.demux_run(p2, gp, None, al).tobytes()
+    fa = ctx.fmx_run(p2, ctx.fmx_opts(4, max_iter=2, early_stop=False))[0]
+    fb = ctx.fmx_run(p2, ctx.fmx_opts(4, max_iter=2, early_stop=False), compact=4)[0]
+    assert fa.tobytes() == fb.tobytes()
+    # malformed side lists are input errors, not crashes
+    for what in ("gap", "count", "short"):
+        bad = synth.make_pileup(C=30, nv=3, V=50000, kbar=80, seed=98)
+        first, d8, gbig, cbp, n2, nbig, nbp = bad.plp.compact4()
+        if what == "gap":
+            gbig[3] = 60000
+        elif what == "count":
+            n2[2] ^= 0x03
+        else:
+            cbp[-1] -= 1
+        with pytest.raises(PsclError):
+            ctx.demux_run(bad.plp, synth.gt_to_gp(bad.geno), None, DEFAULT, compact=4)

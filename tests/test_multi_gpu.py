@@ -140,3 +140,22 @@ def test_cli_hosts_take_gpus(ctx, tmp_path):
     a = [l.split("\t") for l in res["one"].splitlines()]
     b = [l.split("\t") for l in res["two"].splitlines()]
     assert len(a) == len(b) > 100 and all(x[:6] == y[:6] for x, y in zip(a, b))  # ids, counts, types, best guesses
+
+
+def test_sharded_demuxlet_on_the_tiny_pileup_form(ctx, multi3):
+    """ABI 6 arrays through pscl_multi_demux_run: the shards point into the caller's arrays at pair offsets that are not
+    multiples of 4 (two-bit counts) or 1024 (the large-count index)."""
+    s = synth.make_pileup(C=333, nv=8, V=90000, kbar=401, seed=64)
+    nrd = np.diff(s.plp.pair_read_ptr)
+    nrd[::11] = 6
+    from popscle_b200 import Pileup
+    prp = np.concatenate([[0], np.cumsum(nrd)]).astype(np.int64)
+    N = int(prp[-1])
+    rng = np.random.default_rng(1)
+    p2 = Pileup(s.plp.n_cells, s.plp.n_snps, s.plp.cell_ptr, s.plp.pair_snp, prp, rng.choice([0, 1, 2], N).astype(np.uint8),
+                rng.integers(13, 41, N).astype(np.uint8), s.plp.snp_af)
+    gp = synth.gt_to_gp(s.geno)
+    one = ctx.demux_run(p2, gp, None, DEFAULT)
+    assert multi3.demux_run(p2, gp, None, DEFAULT, compact=4).tobytes() == one.tobytes()
+    assert multi3.fmx_run(p2, ctx.fmx_opts(3, max_iter=1, early_stop=False), compact=4)[0]["n_reads"].tolist() == \
+        ctx.fmx_run(p2, ctx.fmx_opts(3, max_iter=1, early_stop=False))[0]["n_reads"].tolist()

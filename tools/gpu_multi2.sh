@@ -4,8 +4,8 @@ N=${1:-2}; TAG=${2:-r2m$N}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/${TAG}_topo.txt 2>&1
 IDS=$(seq -s, 0 $((N-1)))
-PSCL_TEST_GPUS=$IDS timeout 900 python -m pytest tests/test_multi_gpu.py -x -q -m gpu > gpurun_out/${TAG}_pytest_multi.log 2>&1; echo "pytest multi exit $?"; tail -5 gpurun_out/${TAG}_pytest_multi.log
-for G in 1 $N; do
+PSCL_TEST_GPUS=$IDS timeout 900 python -m pytest tests/test_multi_gpu.py tests/test_freemux_gpu.py -x -q -m gpu -k "multi or sharded or old_mode_seeding_sharded" > gpurun_out/${TAG}_pytest_multi.log 2>&1; echo "pytest multi exit $?"; tail -5 gpurun_out/${TAG}_pytest_multi.log
+for G in $N; do
   timeout 600 python tools/multi_bench.py $G > gpurun_out/${TAG}_multi_api_$G.json 2> gpurun_out/${TAG}_multi_api_$G.err; echo "multi_bench $G exit $?"; cat gpurun_out/${TAG}_multi_api_$G.json | cut -c1-1500
 done
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline \

@@ -29,14 +29,16 @@ with Multi(n_gpu=n) as m:
     c5 = synth.CONFIGS[5]
     s = synth.make_pileup(fc, c5["nv"], c5["V"], c5["kbar"], 20260106)
     s.plp.compact(); s.plp.compact3()
-    os.environ["PSCL_MULTI_TIME_ALLREDUCE"] = "1"
     o = m.fmx_opts(c5["nv"], early_stop=False, max_iter=bs.FREEMUX16_ITERS)
-    t0 = time.perf_counter()
-    cells, res, _, _ = m.fmx_run(s.plp, o, compact=3)
-    wall = 1e3 * (time.perf_counter() - t0)
-    t = m.timing()
-    out["freemux16"] = {"cells": fc, "pairs": s.plp.n_pairs, "wall_ms": wall, "iters": t["iters"], "seed_ms": t["seed_ms"],
-                        "em_ms_per_iter_max": max(t["compute_ms"]) / max(t["iters"], 1), "allreduce_ms": t["allreduce_ms"],
-                        "allreduce_bytes": t["allreduce_bytes"], "upload_ms": t["upload_ms"], "setup_ms": t["setup_ms"], "units": t["units"],
-                        "singlets": int((cells["type"] == 0).sum())}
+    for tag, timed in (("freemux16", False), ("freemux16_allreduce_isolated", True)):
+        if timed:
+            os.environ["PSCL_MULTI_TIME_ALLREDUCE"] = "1"  # two extra stream synchronisations per iteration around the collective
+        t0 = time.perf_counter()
+        cells, res, _, _ = m.fmx_run(s.plp, o, compact=3)
+        wall = 1e3 * (time.perf_counter() - t0)
+        t = m.timing()
+        out[tag] = {"cells": fc, "pairs": s.plp.n_pairs, "wall_ms": wall, "iters": t["iters"], "seed_ms": t["seed_ms"],
+                    "em_ms_per_iter_max": max(t["compute_ms"]) / max(t["iters"], 1), "allreduce_ms": t["allreduce_ms"],
+                    "allreduce_bytes": t["allreduce_bytes"], "upload_ms": t["upload_ms"], "setup_ms": t["setup_ms"], "units": t["units"],
+                    "singlets": int((cells["type"] == 0).sum())}
 print(json.dumps(out), flush=True)
