@@ -464,15 +464,22 @@ def main():
     p32, aq = plp.compact()
     first, d8, gbig, cbp, n2, nbig, nbp = plp.compact4()
     for name, src in (("cell_ptr", plp.cell_ptr), ("cell_first_snp", first), ("pair_snp_delta8", d8), ("snp_gap_big", gbig), ("cell_gap_big_ptr", cbp),
-                      ("pair_nreads2", n2), ("nreads_big", nbig), ("nreads_big_ptr", nbp), ("read_aq", aq)):
+                      ("pair_nreads2", n2), ("nreads_big", nbig), ("nreads_big_ptr", nbp)):
         t_, v_ = pin(src); keep.append(t_); arrs[name] = v_
+    pr = plp.packed_reads()  # 4-6 bits per base-call (palette of the distinct allele<<6|qual bytes) when <= 64 of them
+    if pr is not None:
+        for name, src in (("read_packed", pr[0]), ("read_palette", pr[1])):
+            t_, v_ = pin(src); keep.append(t_); arrs[name] = v_
+    else:
+        t_, v_ = pin(aq); keep.append(t_); arrs["read_aq"] = v_
     # genotypes the way the CLI host hands them over for --field GT (ABI 4): one byte per (SNP, sample) hard call and the
     # genotype error rate; the library builds the mixed table (sc_drop_seq.cpp:287-315) on the device
     from popscle_b200 import RawGeno
     gt_t, gt_pin = pin(np.ascontiguousarray(s.geno.T.astype(np.uint8))); keep.append(gt_t)
     gp_pin = RawGeno(gt8=gt_pin, err=0.1)
     hplp = Pileup(plp.n_cells, plp.n_snps, arrs["cell_ptr"], plp.pair_snp, plp.pair_read_ptr, plp.read_allele, plp.read_qual, None)
-    hplp._compact = (p32, arrs["read_aq"])  # pinned copies are what crosses the ABI
+    hplp._compact = (p32, arrs.get("read_aq", aq))  # pinned copies are what crosses the ABI
+    hplp._packed_reads = (arrs["read_packed"], arrs["read_palette"], pr[2]) if pr is not None else None
     hplp._compact4 = tuple(arrs[k] for k in ("cell_first_snp", "pair_snp_delta8", "snp_gap_big", "cell_gap_big_ptr", "pair_nreads2", "nreads_big", "nreads_big_ptr"))
     h2d = sum(v.nbytes for v in arrs.values()) + gt_pin.nbytes
     d2h = 160 * plp.n_cells
@@ -544,7 +551,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "repeats": E2E_REPEATS, "repeat_totals_ms": [round(x * 1e3, 3) for x in e2e_totals],
                         "reported": "median repeat", "numa_bound": bool(numa_bound),
-                        "ms_per_call": per_call[:32], "api": "pscl_demux_run (pinned host buffers in compact form: 1.25 B per pair + the rare large gaps / counts, 1 B per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
+                        "ms_per_call": per_call[:32], "api": "pscl_demux_run (pinned host buffers in the ABI-6 compact form: 1.25 B per pair + the rare large gaps / counts, 4-6 bits per base-call, 1 B per (SNP, sample) hard call; per-cell records out)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if strong is not None:
             line["strong"] = strong

@@ -93,6 +93,13 @@ typedef struct pscl_pileup {
   const uint8_t* nreads_big;         /* [n_nreads_big]                                           */
   const int64_t* nreads_big_ptr;     /* [P/1024 + 2]                                             */
   int64_t n_gap_big, n_nreads_big;
+  /* ABI 6: the base-calls as indices into a palette of the distinct allele<<6|qual bytes — after --min-BQ / --cap-BQ there
+   * are few of them (24 with the commands' defaults 13 / 20: 5 bits per base-call instead of 8).  read_bits in {4, 5, 6};
+   * base-call r occupies bits [r*read_bits, (r+1)*read_bits) of the little-endian bit string read_packed; replaces read_aq. */
+  const uint8_t* read_packed;        /* [(N*read_bits + 7)/8 + 1] (one byte of slack)            */
+  const uint8_t* read_palette;       /* [1 << read_bits] allele<<6|qual of each index            */
+  int32_t read_bits;                 /* 0 = not given                                            */
+  int32_t reserved_;
 } pscl_pileup;
 
 /* Genotype table (replaces sc_snp_t::gps, sc_drop_seq.h:29-37, filled at
@@ -317,7 +324,7 @@ typedef struct pscl_multi_timing {   /* wall-clock of the last pscl_multi_*_run,
   int64_t allreduce_bytes;           /* C * npairs * 8                                                    */
   double upload_ms[PSCL_MULTI_MAX_GPUS];   /* H2D of the shard (freemuxlet: whole pileup + SNP filter)   */
   double setup_ms[PSCL_MULTI_MAX_GPUS];    /* freemuxlet: SNP-major view, stage 1, initial M-step         */
-  double compute_ms[PSCL_MULTI_MAX_GPUS];  /* demuxlet: score + fetch; freemuxlet: the EM loop + fetch    */
+  double compute_ms[PSCL_MULTI_MAX_GPUS];  /* demuxlet: score + fetch; freemuxlet: the EM loop             */
   double kernel_ms[PSCL_MULTI_MAX_GPUS];   /* demuxlet: device time of the scoring kernels (CUDA events)  */
   int64_t units[PSCL_MULTI_MAX_GPUS];      /* (cell, SNP) pairs this GPU owned                            */
 } pscl_multi_timing;

@@ -35,7 +35,8 @@ class CPileup(C.Structure):
                 ("cell_first_snp", C.c_void_p), ("pair_snp_delta16", C.c_void_p), ("pair_nreads8", C.c_void_p),
                 ("pair_snp_delta8", C.c_void_p), ("snp_gap_big", C.c_void_p), ("cell_gap_big_ptr", C.c_void_p),
                 ("pair_nreads2", C.c_void_p), ("nreads_big", C.c_void_p), ("nreads_big_ptr", C.c_void_p),
-                ("n_gap_big", C.c_int64), ("n_nreads_big", C.c_int64)]
+                ("n_gap_big", C.c_int64), ("n_nreads_big", C.c_int64),
+                ("read_packed", C.c_void_p), ("read_palette", C.c_void_p), ("read_bits", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class CGeno(C.Structure):
@@ -203,6 +204,27 @@ class Pileup:
             self._compact4 = c
         return c
 
+    def packed_reads(self):
+        """(read_packed, read_palette, bits): the base-calls as 4/5/6-bit indices into the palette of distinct
+        allele<<6|qual bytes (ABI 6), or None when there are more than 64 distinct values."""
+        c = getattr(self, "_packed_reads", 0)
+        if c == 0:
+            c = None
+            _, aq = self.compact()
+            pal, idx = np.unique(aq, return_inverse=True)
+            if len(pal) <= 64:
+                bits = 4 if len(pal) <= 16 else 5 if len(pal) <= 32 else 6
+                n = len(aq)
+                b = ((idx.astype(np.uint8)[:, None] >> np.arange(bits, dtype=np.uint8)) & 1).astype(np.uint8).ravel()  # little-endian bit string
+                b = np.concatenate([b, np.zeros((-len(b)) % 8 + 8, np.uint8)])
+                packed = np.packbits(b, bitorder="little")
+                palette = np.zeros(1 << bits, dtype=np.uint8)
+                palette[:len(pal)] = pal
+                assert len(packed) >= (n * bits + 7) // 8 + 1
+                c = (np.ascontiguousarray(packed), palette, bits)
+            self._packed_reads = c
+        return c
+
     def c_struct(self, cls=CPileup, compact=False):
         """compact: False = wide arrays; True / 2 = ABI 2 (32-bit offsets, packed reads); 3 = ABI 3 (16-bit SNP gaps, 8-bit
         counts); 4 = ABI 6 (8-bit gaps, 2-bit counts, exceptions on the side) — each falls back to the previous form when
@@ -229,6 +251,10 @@ class Pileup:
                 s.nreads_big = nbig.ctypes.data if len(nbig) else None
                 s.n_gap_big, s.n_nreads_big = len(gbig), len(nbig)
                 s.pair_snp = s.pair_read_ptr32 = None
+                pr = self.packed_reads()
+                if pr is not None:  # 4-6 bits per base-call instead of 8
+                    s.read_packed, s.read_palette, s.read_bits = pr[0].ctypes.data, pr[1].ctypes.data, pr[2]
+                    s.read_aq = None
             elif c3 is not None:  # ABI 3: only deltas and counts for the pair arrays
                 s.cell_first_snp, s.pair_snp_delta16, s.pair_nreads8 = (x.ctypes.data for x in c3)
                 s.pair_snp = s.pair_read_ptr32 = None

@@ -157,6 +157,20 @@ __global__ void k_pack_reads(const uint8_t* __restrict__ al, const uint8_t* __re
   aq[i] = (uint8_t)((a << 6) | (b & 63));
 }
 
+// ABI 6: base-calls as read_bits-wide indices into a palette of allele<<6|qual bytes -> one byte per base-call
+__global__ void k_unpack_reads(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ palette, int bits, int64_t n, uint8_t* __restrict__ aq, int* bad) {
+  __shared__ uint8_t s_pal[64];
+  if (threadIdx.x < (1u << bits)) s_pal[threadIdx.x] = palette[threadIdx.x];
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t o = r * bits;
+  const unsigned w = (unsigned)packed[o >> 3] | ((unsigned)packed[(o >> 3) + 1] << 8);  // one byte of slack behind the string
+  const uint8_t v = s_pal[(w >> (int)(o & 7)) & ((1u << bits) - 1u)];
+  if ((v >> 6) == 3) atomicExch(bad, 1);
+  aq[r] = v;
+}
+
 // already packed reads: only the validity check (allele code 3 does not exist)
 __global__ void k_check_reads(const uint8_t* __restrict__ aq, int64_t n, int* bad) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
@@ -400,7 +414,9 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   const int32_t C = h->n_cells, V = h->n_snps;
   const int64_t P = h->n_pairs, N = h->n_reads;
   if (C < 0 || V < 0 || P < 0 || N < 0) return pscl_fail(ctx, PSCL_EINVAL, "negative size in pscl_pileup");
-  const bool ptr32 = h->pair_read_ptr32 != nullptr, packed = h->read_aq != nullptr;
+  const bool pal = h->read_packed != nullptr && h->read_palette != nullptr && h->read_bits >= 4 && h->read_bits <= 6;  // ABI 6
+  const bool ptr32 = h->pair_read_ptr32 != nullptr, packed = pal || h->read_aq != nullptr;
+  if (pal && read_base != 0) return pscl_fail(ctx, PSCL_EINVAL, "a shard view cannot point into read_packed (bit string): pass read_aq");
   // ABI 6 forms win over ABI 3 ones when both are given
   const bool dsnp8 = h->pair_snp_delta8 != nullptr && h->cell_first_snp != nullptr && h->cell_gap_big_ptr != nullptr && (h->n_gap_big == 0 || h->snp_gap_big);
   const bool cnt2 = h->pair_nreads2 != nullptr && h->nreads_big_ptr != nullptr && (h->n_nreads_big == 0 || h->nreads_big);
@@ -437,7 +453,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
 #define UP(field, src, bytes) do { if (e == cudaSuccess) { e = up((void**)&p->field, src, bytes); if (e != cudaSuccess) where = #field; } } while (0)
 #define STEP(name) do { if (e != cudaSuccess && !*where) where = name; } while (0)
   UP(cell_ptr, h->cell_ptr, sizeof(int64_t) * (C + 1));
-  uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr, *d_n2 = nullptr, *d_nbig = nullptr;
+  uint8_t *d_al = nullptr, *d_q = nullptr, *d_cnt = nullptr, *d_n2 = nullptr, *d_nbig = nullptr, *d_rpk = nullptr, *d_rpal = nullptr;
   int64_t* d_nblk = nullptr;
   int64_t n_big_local = 0, n2_first = 0;
   void* d_scan_tmp = nullptr;
@@ -460,7 +476,12 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     STEP("pair_nreads8 / pair_rd");
   } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
   else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
-  if (packed) {
+  if (pal) {  // unpacked by k_unpack_reads
+    if (e == cudaSuccess) e = up((void**)&d_rpk, h->read_packed, (size_t)((N * h->read_bits + 7) / 8 + 1));
+    if (e == cudaSuccess) e = up((void**)&d_rpal, h->read_palette, (size_t)1 << h->read_bits);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
+    STEP("read_packed");
+  } else if (packed) {
     UP(rd_aq, h->read_aq, (size_t)N);
   } else {
     if (e == cudaSuccess) e = up((void**)&d_al, h->read_allele, (size_t)N);
@@ -564,7 +585,11 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess && N > 0) {
+  if (e == cudaSuccess && N > 0 && pal) {
+    k_unpack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_rpk, d_rpal, h->read_bits, N, p->rd_aq, p->d_bad);
+    ctx->launches++;
+    e = cudaGetLastError();
+  } else if (e == cudaSuccess && N > 0) {
     if (packed) k_check_reads<<<(unsigned)((N + 4095) / 4096), 256, 0, ctx->stream>>>(p->rd_aq, N, p->d_bad);
     else k_pack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_al, d_q, p->rd_aq, N, p->d_bad);
     ctx->launches++;
@@ -576,7 +601,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   // the host vectors above are pageable sources of async copies: drain before they go out of scope
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   STEP("drain (a copy or kernel of the upload failed on the device)");
-  cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp); cudaFree(d_n2); cudaFree(d_nbig); cudaFree(d_nblk);
+  cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp); cudaFree(d_n2); cudaFree(d_nbig); cudaFree(d_nblk); cudaFree(d_rpk); cudaFree(d_rpal);
   if (p->n_stages == 0) {
     cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_delta8); cudaFree(p->d_gap_big); cudaFree(p->d_cell_gap_ptr);
     p->d_delta = nullptr; p->d_first = nullptr; p->d_delta8 = nullptr; p->d_gap_big = nullptr; p->d_cell_gap_ptr = nullptr;

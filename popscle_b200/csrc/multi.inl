@@ -246,6 +246,7 @@ extern "C" int pscl_multi_demux_run(pscl_multi* m, const pscl_pileup* host, cons
   const size_t gp_bytes = geno->gp ? sizeof(double) * (size_t)host->n_snps * geno->n_samples * 3 : 0;
   const bool tree = N > 1 && m->peer_ok && gp_bytes >= ((size_t)32 << 20) && getenv("PSCL_NO_GENO_TREE") == nullptr;
   std::vector<std::vector<int64_t>> cp(N);
+  std::vector<std::vector<uint8_t>> aqs(N);
   m->tm = pscl_multi_timing{};
   m->tm.n_gpus = N;
   const size_t G = (size_t)geno->n_samples * geno->n_samples * opts->n_alpha;
@@ -283,6 +284,20 @@ extern "C" int pscl_multi_demux_run(pscl_multi* m, const pscl_pileup* host, cons
     if (host->read_allele) sh.read_allele = host->read_allele + rcut[r];
     if (host->read_qual) sh.read_qual = host->read_qual + rcut[r];
     if (host->read_aq) sh.read_aq = host->read_aq + rcut[r];
+    if (host->read_packed) {  // a bit string cannot be entered at a base-call offset: this shard's bytes are unpacked on the host
+      if (!host->read_aq && host->read_palette && host->read_bits >= 4 && host->read_bits <= 6) {
+        std::vector<uint8_t>& aq = aqs[r];
+        aq.resize((size_t)sh.n_reads);
+        const int bits = host->read_bits;
+        for (int64_t i = 0; i < sh.n_reads; ++i) {
+          const int64_t o = (rcut[r] + i) * bits;
+          const unsigned w = (unsigned)host->read_packed[o >> 3] | ((unsigned)host->read_packed[(o >> 3) + 1] << 8);
+          aq[(size_t)i] = host->read_palette[(w >> (int)(o & 7)) & ((1u << bits) - 1u)];
+        }
+        sh.read_aq = aq.data();
+      }
+      sh.read_packed = nullptr; sh.read_palette = nullptr; sh.read_bits = 0;
+    }
     if (host->cell_first_snp) sh.cell_first_snp = host->cell_first_snp + c0;
     if (host->pair_snp_delta16) sh.pair_snp_delta16 = host->pair_snp_delta16 + p0;
     if (host->pair_nreads8) sh.pair_nreads8 = host->pair_nreads8 + p0;
@@ -608,10 +623,11 @@ extern "C" int pscl_multi_fmx_run(pscl_multi* m, const pscl_pileup* host, const 
         if (!s->o.mode_old && s->o.early_stop && rres.n_changed == 0) break;  // :601-604 — the same decision on every GPU
       }
       results[r] = rres;
+      PSCL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      const double t3 = multi_now_ms();  // the EM loop; the read-back below (cluster pileups: V x nS x 84 B) only shows in total_ms
       // records from GPU 0; every GPU holds the cluster pileups of its own SNP range
       const int32_t w0 = N > 1 ? (int32_t)vcut[r] : 0, w1 = N > 1 ? (int32_t)vcut[r + 1] : V;
       if ((rr = fmx_fetch_range(ctx, r == 0 ? out : nullptr, clust_gl, clust_cnt, w0, w1)) != PSCL_OK) return rr;
-      const double t3 = multi_now_ms();
       m->tm.upload_ms[r] = t1 - t0; m->tm.setup_ms[r] = t2 - t1; m->tm.compute_ms[r] = t3 - t2; m->tm.units[r] = shard->P;
       if (r == 0) { m->tm.iters = iters; m->tm.allreduce_ms = iters ? ar_ms / iters : 0.0; m->tm.allreduce_bytes = (int64_t)(red_llk.n * sizeof(double)); }
       return PSCL_OK;

@@ -71,6 +71,8 @@ struct Loaded {
   mutable std::vector<uint8_t> pair_snp_delta8, pair_nreads2, nreads_big;
   mutable std::vector<uint32_t> snp_gap_big;
   mutable std::vector<int64_t> cell_gap_big_ptr, nreads_big_ptr;
+  mutable std::vector<uint8_t> read_packed, read_palette;  // ABI 6: base-calls as 4/5/6-bit palette indices
+  mutable int read_bits = 0, packed_state = 0;             // packed_state: 0 not tried, 1 usable, -1 more than 64 distinct bytes
   mutable int tiny_state = 0;   // 0 not tried, 1 usable, -1 a pair without base-calls or with >= 256 of them
   mutable int delta_state = 0;  // 0 not tried, 1 usable, -1 a gap or a count does not fit
   mutable int compact_state = 0;  // the same for read_aq (an allele code > 2 or a quality > 63 rules the packed form out)
@@ -81,6 +83,7 @@ struct Loaded {
     p.cell_first_snp = nullptr; p.pair_snp_delta16 = nullptr; p.pair_nreads8 = nullptr;
     p.pair_snp_delta8 = nullptr; p.snp_gap_big = nullptr; p.cell_gap_big_ptr = nullptr;
     p.pair_nreads2 = nullptr; p.nreads_big = nullptr; p.nreads_big_ptr = nullptr; p.n_gap_big = p.n_nreads_big = 0;
+    p.read_packed = nullptr; p.read_palette = nullptr; p.read_bits = 0; p.reserved_ = 0;
     if (read_allele.size() < (1ull << 32)) {  // halves the bytes pscl_plp_upload sends over PCIe
       if (pair_read_ptr32.size() != pair_read_ptr.size()) pair_read_ptr32.assign(pair_read_ptr.begin(), pair_read_ptr.end());
       if (compact_state == 0) {  // decided once per loaded pileup (a later call must not forget a failed check)
@@ -138,6 +141,26 @@ struct Loaded {
         if (P % 1024 == 0 && P > 0) nreads_big_ptr[P / 1024] = (int64_t)nreads_big.size();
         tiny_state = fits ? 1 : -1;
       }
+      if (ok && packed_state == 0) {  // few distinct allele<<6|qual bytes survive --min-BQ / --cap-BQ: index them
+        int slot[256];
+        for (int i = 0; i < 256; ++i) slot[i] = -1;
+        bool seen[256] = {false};
+        for (uint8_t b : read_aq) seen[b] = true;
+        read_palette.clear();
+        for (int i = 0; i < 256; ++i) if (seen[i]) { slot[i] = (int)read_palette.size(); read_palette.push_back((uint8_t)i); }  // ascending, as np.unique
+        if (read_palette.size() <= 64) {
+          read_bits = read_palette.size() <= 16 ? 4 : read_palette.size() <= 32 ? 5 : 6;
+          read_palette.resize((size_t)1 << read_bits, 0);
+          read_packed.assign((read_aq.size() * read_bits + 7) / 8 + 1, 0);
+          for (size_t r = 0; r < read_aq.size(); ++r) {
+            const size_t o = r * read_bits;
+            const unsigned v = (unsigned)slot[read_aq[r]] << (o & 7);
+            read_packed[o >> 3] |= (uint8_t)v; read_packed[(o >> 3) + 1] |= (uint8_t)(v >> 8);
+          }
+          packed_state = 1;
+        } else packed_state = -1;
+      }
+      if (ok && tiny_state == 1 && packed_state == 1) { p.read_packed = read_packed.data(); p.read_palette = read_palette.data(); p.read_bits = read_bits; }
       if (ok && tiny_state == 1) {
         p.cell_first_snp = cell_first_snp.data(); p.pair_snp_delta8 = pair_snp_delta8.data(); p.cell_gap_big_ptr = cell_gap_big_ptr.data();
         p.snp_gap_big = snp_gap_big.empty() ? nullptr : snp_gap_big.data(); p.n_gap_big = (int64_t)snp_gap_big.size();

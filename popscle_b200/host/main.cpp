@@ -114,6 +114,17 @@ int dry_run(const Loaded& L) {
   if (v.pair_read_ptr32) { mix(v.pair_read_ptr32, (size_t)(v.n_pairs + 1) * 4); mix(v.read_aq, (size_t)v.n_reads); }
   if (v.pair_snp_delta16) { mix(v.cell_first_snp, (size_t)v.n_cells * 4); mix(v.pair_snp_delta16, (size_t)v.n_pairs * 2); mix(v.pair_nreads8, (size_t)v.n_pairs); }
   std::swap(h, hc);
+  // ABI 6 forms (8-bit gaps, 2-bit counts, palette-indexed base-calls), when the pileup fits them
+  unsigned long long ht = 1469598103934665603ull;
+  const int tiny = v.pair_snp_delta8 ? 1 : 0, rbits = v.read_bits;
+  std::swap(h, ht);
+  if (v.pair_snp_delta8) {
+    mix(v.cell_first_snp, (size_t)v.n_cells * 4); mix(v.pair_snp_delta8, (size_t)v.n_pairs); mix(v.snp_gap_big, (size_t)v.n_gap_big * 4);
+    mix(v.cell_gap_big_ptr, ((size_t)v.n_cells + 1) * 8); mix(v.pair_nreads2, (size_t)(v.n_pairs + 3) / 4); mix(v.nreads_big, (size_t)v.n_nreads_big);
+    mix(v.nreads_big_ptr, ((size_t)v.n_pairs / 1024 + 2) * 8);
+  }
+  if (v.read_packed) { mix(v.read_packed, ((size_t)v.n_reads * v.read_bits + 7) / 8 + 1); mix(v.read_palette, (size_t)1 << v.read_bits); }
+  std::swap(h, ht);
   int gt8 = -1;
   if (!L.samples.empty()) {
     const pscl_geno g = L.geno_view();
@@ -124,9 +135,10 @@ int dry_run(const Loaded& L) {
     std::swap(h, hr);
   }
   printf("{\"cells\": %d, \"snps\": %d, \"pairs\": %zu, \"reads\": %zu, \"samples\": %zu, \"has_gp\": %zu, \"pileup_fnv1a\": \"%016llx\", \"geno_fnv1a\": \"%016llx\", "
-         "\"compact_form\": %d, \"compact_fnv1a\": \"%016llx\", \"gt8\": %d, \"raw_geno_fnv1a\": \"%016llx\"}\n",
+         "\"compact_form\": %d, \"compact_fnv1a\": \"%016llx\", \"gt8\": %d, \"raw_geno_fnv1a\": \"%016llx\", "
+         "\"tiny_form\": %d, \"read_bits\": %d, \"tiny_fnv1a\": \"%016llx\"}\n",
          L.n_cells, L.n_snps, L.pair_snp.size(), L.read_allele.size(), L.samples.size(),
-         (size_t)std::count(L.has_gp.begin(), L.has_gp.end(), 1), h, hg, form, hc, gt8, hr);
+         (size_t)std::count(L.has_gp.begin(), L.has_gp.end(), 1), h, hg, form, hc, gt8, hr, tiny, rbits, ht);
   return 0;
 }
 

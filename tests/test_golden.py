@@ -193,6 +193,11 @@ def test_cpp_host_loader_matches_python_loader(case, tmp_path, host_exe):
     c3 = p.compact3()
     assert got["compact_form"] == (3 if c3 is not None else 2)
     assert got["compact_fnv1a"] == _fnv1a(p32, aq, *(c3 if c3 is not None else ()))
+    # ABI 6 forms: 8-bit gaps / 2-bit counts with the large values on the side, palette-indexed base-calls
+    c4, pr = p.compact4(), p.packed_reads()
+    assert got["tiny_form"] == (1 if c4 is not None else 0) and got["read_bits"] == (pr[2] if pr is not None and c4 is not None else 0)
+    if c4 is not None:
+        assert got["tiny_fnv1a"] == _fnv1a(*c4, *((pr[0][:(p.n_reads * pr[2] + 7) // 8 + 1], pr[1]) if pr is not None else ()))
 
 
 def test_cpp_host_errors(host_exe, tmp_path):
