@@ -379,8 +379,8 @@ static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cel
     std::vector<int32_t> head(NB + 1);
     const int nseg = p->n_stages > 1 ? p->n_stages : 1;
     for (int k = 0; k < nseg; ++k) {
-      const int32_t ib = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k]] : 0;
-      const int32_t ie = p->n_stages > 1 ? p->h_cell_item_ptr[p->stage_cell[k + 1]] : p->n_items;
+      const int32_t ib = nseg > 1 ? p->h_cell_item_ptr[p->stage_cell[k]] : 0;
+      const int32_t ie = nseg > 1 ? p->h_cell_item_ptr[p->stage_cell[k + 1]] : p->n_items;
       std::fill(head.begin(), head.end(), 0);
       for (int32_t i = ib; i < ie; ++i) head[NB - 1 - (int)std::min<int64_t>(pend[i] - pbeg[i], NB - 1) + 1]++;
       for (int b2 = 0; b2 < NB; ++b2) head[b2 + 1] += head[b2];

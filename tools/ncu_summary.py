@@ -8,13 +8,20 @@ import subprocess
 import sys
 
 
+SKIP = 0
+
+
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    """one kernel of the report (the SKIP-th captured launch)"""
+    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv", "--launch-skip", str(SKIP), "--launch-count", "1"],
+                         capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
+    global SKIP
     rep = sys.argv[1]
+    SKIP = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     raw = page(rep, "raw")
     hdr, units, vals = raw[0], raw[1], raw[2]
     want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
