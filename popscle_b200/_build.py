@@ -58,6 +58,6 @@ def build_host(force: bool = False) -> str | None:
         return exe
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe] + srcs + [
-        "-L", HERE, "-lpopscle_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+        "-L", HERE, "-lpopscle_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"]
     subprocess.check_call(cmd, cwd=ROOT)
     return exe

@@ -189,45 +189,94 @@ void expect_header(LineReader& r, const char* const* names, int n, const std::st
   if (!ok) throw host_error("The header line of " + what + " is malformed or outdated. Expecting " + expecting);
 }
 
-}  // namespace
 
-void load_plp(const LoadOptions& o, Loaded& L) {
-  // PSCL_TRACE=1: wall-clock of the loader's phases on stderr
-  const bool trace = getenv("PSCL_TRACE") != nullptr;
-  auto t_prev = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!trace) return;
-    const auto t = std::chrono::steady_clock::now();
-    fprintf(stderr, "[load_plp] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
-    t_prev = t;
-  };
+// ---- whole-file ingest for the big table (.plp.gz): inflate and parse on several host threads ---------------------------
+// The text of a gzip / BGZF / plain file.  dsc-pileup writes its tables through htslib's BGZF layer: gzip members of at most
+// 64 KB that carry their own compressed size in a 'BC' extra field, so every block inflates independently — on `threads`
+// host threads here.  Any other gzip stream is inflated by one thread; a file without the gzip magic is returned as is.
+std::vector<char> slurp_text(const std::string& path, int threads, bool* was_bgzf) {
+  if (was_bgzf) *was_bgzf = false;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw host_error("Cannot open file " + path + " for reading");
+  std::vector<unsigned char> raw;
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  raw.resize(sz > 0 ? (size_t)sz : 0);
+  if (sz > 0 && fread(raw.data(), 1, raw.size(), f) != raw.size()) { fclose(f); throw host_error("Cannot read file " + path); }
+  fclose(f);
+  if (raw.size() < 18 || raw[0] != 0x1f || raw[1] != 0x8b) return std::vector<char>(raw.begin(), raw.end());
+  // BGZF? walk the members by their BSIZE fields
+  struct Blk { size_t in, in_len, out, out_len; };
+  std::vector<Blk> blk;
+  bool bgzf = true;
+  size_t o = 0, total = 0;
+  while (o < raw.size()) {
+    if (o + 18 > raw.size() || raw[o] != 0x1f || raw[o + 1] != 0x8b || raw[o + 2] != 8 || !(raw[o + 3] & 4)) { bgzf = false; break; }
+    const size_t xlen = raw[o + 10] | (raw[o + 11] << 8);
+    size_t x = o + 12, bsize = 0;
+    const size_t xend = x + xlen;
+    if (xend > raw.size()) { bgzf = false; break; }
+    while (x + 4 <= xend) {
+      const size_t slen = raw[x + 2] | (raw[x + 3] << 8);
+      if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = (size_t)(raw[x + 4] | (raw[x + 5] << 8)) + 1;
+      x += 4 + slen;
+    }
+    if (!bsize || o + bsize > raw.size() || bsize < xlen + 12 + 8) { bgzf = false; break; }
+    const size_t isize = raw[o + bsize - 4] | (raw[o + bsize - 3] << 8) | (raw[o + bsize - 2] << 16) | ((size_t)raw[o + bsize - 1] << 24);
+    blk.push_back(Blk{xend, o + bsize - 8 - xend, total, isize});
+    total += isize;
+    o += bsize;
+  }
+  std::vector<char> text;
+  if (bgzf && !blk.empty()) {
+    if (was_bgzf) *was_bgzf = true;
+    text.resize(total);
+    parallel_for((int)blk.size(), threads, [&](int i) {
+      const Blk& b = blk[i];
+      if (b.out_len == 0) return;
+      z_stream z;
+      memset(&z, 0, sizeof z);
+      if (inflateInit2(&z, -15) != Z_OK) throw host_error("zlib: inflateInit2 failed");
+      z.next_in = raw.data() + b.in; z.avail_in = (uInt)b.in_len;
+      z.next_out = (Bytef*)text.data() + b.out; z.avail_out = (uInt)b.out_len;
+      const int rc = inflate(&z, Z_FINISH);
+      inflateEnd(&z);
+      if (rc != Z_STREAM_END || z.avail_out != 0) throw host_error("Corrupt BGZF block in " + path);
+    });
+    return text;
+  }
+  // one gzip stream (possibly several concatenated members): a single inflater
+  z_stream z;
+  memset(&z, 0, sizeof z);
+  if (inflateInit2(&z, 15 + 32) != Z_OK) throw host_error("zlib: inflateInit2 failed");
+  z.next_in = raw.data(); z.avail_in = (uInt)std::min<size_t>(raw.size(), 1u << 30);
+  size_t in_done = 0, out_done = 0;
+  text.resize(std::max<size_t>(raw.size() * 4, 1 << 16));
+  for (;;) {
+    if (out_done == text.size()) text.resize(text.size() * 2);
+    z.next_out = (Bytef*)text.data() + out_done;
+    z.avail_out = (uInt)std::min<size_t>(text.size() - out_done, 1u << 30);
+    const uInt before_out = z.avail_out, before_in = z.avail_in;
+    const int rc = inflate(&z, Z_NO_FLUSH);
+    out_done += before_out - z.avail_out;
+    in_done += before_in - z.avail_in;
+    if (rc == Z_STREAM_END) {
+      if (in_done >= raw.size()) break;
+      inflateReset(&z);  // the next member
+    } else if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&z); throw host_error("Corrupt gzip stream in " + path); }
+    else if (rc == Z_BUF_ERROR && z.avail_in == 0 && in_done >= raw.size()) break;  // truncated input: keep what there is
+    if (z.avail_in == 0 && in_done < raw.size()) { z.next_in = raw.data() + in_done; z.avail_in = (uInt)std::min<size_t>(raw.size() - in_done, 1u << 30); }
+  }
+  inflateEnd(&z);
+  text.resize(out_done);
+  return text;
+}
+
+// ---- VAR, merge-joined with the VCF cursor (sc_drop_seq.cpp:206-330) ----
+void load_var_vcf(const LoadOptions& o, Loaded& L) {
   std::string line;
   std::vector<char*> f;
-  // ---- CEL (sc_drop_seq.cpp:124-203) ----
-  std::vector<int32_t> index_bcs;
-  std::vector<int64_t> tmp_totl, tmp_uniq, tmp_nsnp;
-  {
-    LineReader r(o.plp_prefix + ".cel.gz");
-    static const char* H[] = {"#DROPLET_ID", "BARCODE", "NUM.READ", "NUM.UMI", "NUM.UMIwSNP", "NUM.SNP"};
-    expect_header(r, H, 6, o.plp_prefix + ".cel.gz", "#DROPLET_ID BARCODE NUM.READ NUM.UMI NUM.UMIwSNP NUM.SNP");
-    std::set<std::string> valid(o.group_list.begin(), o.group_list.end());
-    int nskip = 0;
-    while (next_row(r, line, f)) {
-      if (f.size() < 6) throw host_error("Cannot access field at 5 >= " + std::to_string(f.size()));
-      if (o.has_group_list && !valid.count(f[1])) { ++nskip; index_bcs.push_back(-1); continue; }
-      const int n_reads = atoi(f[2]), n_umis = atoi(f[3]), n_uws = atoi(f[4]), n_snps = atoi(f[5]);
-      if (n_reads < o.min_read || n_umis < o.min_umi || n_snps < o.min_snp) { index_bcs.push_back(-1); ++nskip; continue; }
-      const int new_id = (int)L.barcodes.size();
-      if (new_id + nskip != atoi(f[0]))
-        throw host_error("Observed DROPLET_ID " + std::string(f[0]) + " is different from expected DROPLET_ID. Did you modify the digital pileup files by yourself?");
-      L.barcodes.emplace_back(f[1]);
-      index_bcs.push_back(new_id);
-      tmp_totl.push_back(n_reads); tmp_uniq.push_back(n_uws); tmp_nsnp.push_back(n_snps);
-    }
-  }
-  const int32_t C = (int32_t)L.barcodes.size();
-  lap("cel.gz");
-  // ---- VAR, merge-joined with the VCF cursor (:206-330) ----
   {
     LineReader r(o.plp_prefix + ".var.gz");
     static const char* H[] = {"#SNP_ID", "CHROM", "POS", "REF", "ALT", "AF"};
@@ -302,87 +351,198 @@ void load_plp(const LoadOptions& o, Loaded& L) {
         for (int i = 0; i < nv * 3; ++i) L.gp[base + i] = (1 - err) * L.gp[base + i] + err * avg[i % 3];
     }
   }
-  const int32_t V = (int32_t)L.chrom.size();
-  lap("var.gz + vcf");
-  // ---- PLP (:335-372): rows -> (cell, snp, reads); then cell-major, SNP ascending ----
-  struct Row { int32_t cell, snp; int64_t beg; };  // beg: into al / bq; one record so the cell-major pass below
-  std::vector<Row> rows;                            // touches one cache line per row, not four
-  std::vector<uint8_t> al, bq;
+}
+
+}  // namespace
+
+void load_plp(const LoadOptions& o, Loaded& L) {
+  // PSCL_TRACE=1: wall-clock of the loader's phases on stderr
+  const bool trace = getenv("PSCL_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[load_plp] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
+  std::string line;
+  std::vector<char*> f;
+  // ---- CEL (sc_drop_seq.cpp:124-203) ----
+  std::vector<int32_t> index_bcs;
+  std::vector<int64_t> tmp_totl, tmp_uniq, tmp_nsnp;
   {
-    LineReader r(o.plp_prefix + ".plp.gz");
-    static const char* H[] = {"#DROPLET_ID", "SNP_ID", "ALLELES", "BASEQS"};
-    expect_header(r, H, 4, o.plp_prefix + ".plp.gz", "#DROPLET_ID SNP_ID ALLELES BASEQS");
-    // rows are parsed in place from the reader's buffer (whitespace-separated like tsv_reader's ksplit; atoi semantics)
-    const char* lb = nullptr;
-    size_t ln = 0;
-    auto is_ws = [](char ch) { return ch == ' ' || ch == '\t' || ch == '\v' || ch == '\f' || ch == '\r' || ch == '\n'; };
-    while (r.next_span(lb, ln) && ln > 0) {
-      const char* p = lb;
-      const char* const end = lb + ln;
-      const char* fb[4]; const char* fe[4];
-      int nf = 0;
-      while (p < end) {
-        while (p < end && is_ws(*p)) ++p;
-        if (p >= end) break;
-        const char* q = p;
-        while (q < end && !is_ws(*q)) ++q;
-        if (nf < 4) { fb[nf] = p; fe[nf] = q; }
-        ++nf;
-        p = q;
-      }
-      if (nf < 4) throw host_error("Cannot access field at 3 >= " + std::to_string(nf));
-      auto to_int = [](const char* b2, const char* e2) {  // atoi: optional sign, leading digits
-        bool neg = false;
-        if (b2 < e2 && (*b2 == '-' || *b2 == '+')) { neg = *b2 == '-'; ++b2; }
-        long v = 0;
-        while (b2 < e2 && *b2 >= '0' && *b2 <= '9') { v = v * 10 + (*b2 - '0'); ++b2; }
-        return (int)(neg ? -v : v);
-      };
-      const int drop = to_int(fb[0], fe[0]);
-      if (drop < 0 || drop >= (int)index_bcs.size()) throw host_error("DROPLET_ID " + std::string(fb[0], fe[0]) + " of .plp.gz is not in .cel.gz");
-      const int ibc = index_bcs[drop];
-      if (ibc < 0) continue;
-      const int snp = to_int(fb[1], fe[1]);
-      if (snp < 0 || snp >= V) throw host_error("SNP_ID " + std::string(fb[1], fe[1]) + " of .plp.gz is not in .var.gz");
-      const char *pa = fb[2], *pq = fb[3];
-      const size_t l = (size_t)(fe[3] - fb[3]), la = (size_t)(fe[2] - fb[2]);
-      const int64_t b0 = (int64_t)al.size();
-      for (size_t i = 0; i < l && i < la; ++i) {
-        int q = (int)(signed char)(pq[i] - 33);
-        if (q >= o.min_bq) {
-          if (q > o.cap_bq) q = o.cap_bq;
-          al.push_back((uint8_t)(pa[i] - '0'));
-          bq.push_back((uint8_t)q);
-        }
-      }
-      if ((int64_t)al.size() == b0) continue;
-      rows.push_back(Row{ibc, snp, b0});
+    LineReader r(o.plp_prefix + ".cel.gz");
+    static const char* H[] = {"#DROPLET_ID", "BARCODE", "NUM.READ", "NUM.UMI", "NUM.UMIwSNP", "NUM.SNP"};
+    expect_header(r, H, 6, o.plp_prefix + ".cel.gz", "#DROPLET_ID BARCODE NUM.READ NUM.UMI NUM.UMIwSNP NUM.SNP");
+    std::set<std::string> valid(o.group_list.begin(), o.group_list.end());
+    int nskip = 0;
+    while (next_row(r, line, f)) {
+      if (f.size() < 6) throw host_error("Cannot access field at 5 >= " + std::to_string(f.size()));
+      if (o.has_group_list && !valid.count(f[1])) { ++nskip; index_bcs.push_back(-1); continue; }
+      const int n_reads = atoi(f[2]), n_umis = atoi(f[3]), n_uws = atoi(f[4]), n_snps = atoi(f[5]);
+      if (n_reads < o.min_read || n_umis < o.min_umi || n_snps < o.min_snp) { index_bcs.push_back(-1); ++nskip; continue; }
+      const int new_id = (int)L.barcodes.size();
+      if (new_id + nskip != atoi(f[0]))
+        throw host_error("Observed DROPLET_ID " + std::string(f[0]) + " is different from expected DROPLET_ID. Did you modify the digital pileup files by yourself?");
+      L.barcodes.emplace_back(f[1]);
+      index_bcs.push_back(new_id);
+      tmp_totl.push_back(n_reads); tmp_uniq.push_back(n_uws); tmp_nsnp.push_back(n_snps);
     }
-    rows.push_back(Row{-1, -1, (int64_t)al.size()});  // sentinel: end of the last row's reads
   }
-  const size_t R = rows.size() - 1;
-  lap("plp.gz rows");
-  bool sorted = true, snp_major = true;
-  for (size_t i = 1; i < R && (sorted || snp_major); ++i) {
-    sorted = sorted && (rows[i - 1].cell < rows[i].cell || (rows[i - 1].cell == rows[i].cell && rows[i - 1].snp <= rows[i].snp));
-    snp_major = snp_major && rows[i - 1].snp <= rows[i].snp;
-  }
+  const int32_t C = (int32_t)L.barcodes.size();
+  lap("cel.gz");
+  // ---- VAR + VCF (:206-330) on a thread of its own, beside the PLP table ----
+  std::exception_ptr var_err, plp_err;
+  std::thread var_thread([&] {
+    try {
+      const auto t0 = std::chrono::steady_clock::now();
+      load_var_vcf(o, L);
+      if (trace) fprintf(stderr, "[load_plp] %-28s %8.1f ms (own thread)\n", "var.gz + vcf", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    } catch (...) { var_err = std::current_exception(); }
+  });
+  // ---- PLP (:335-372): rows -> (cell, snp, reads); then cell-major, SNP ascending ----
+  // The table is inflated whole (BGZF blocks on several threads) and cut at line ends into pieces that are parsed in
+  // parallel.  A piece files its rows under the block of droplets they belong to; afterwards one thread per droplet block
+  // walks the pieces in file order — so it sees every droplet's rows in file order — first counting, then writing the
+  // cell-major image through one cursor per droplet.  dsc-pileup writes SNP-major, the reference's std::map makes it
+  // cell-major with SNPs ascending: a droplet's rows already ascend in SNP id in either order, so there is no sort.
+  // (Rows are whitespace-separated like tsv_reader's ksplit, numbers read with atoi's rules, and the table ends at the
+  // first empty line, tsv_reader.cpp:37-41.  A (cell,SNP) listed on several rows is one pair.)
+  struct Row { int32_t cell, snp; uint32_t beg, n; };  // beg: into the piece's al / bq
+  struct Piece { std::vector<std::vector<Row>> bk; std::vector<uint8_t> al, bq; int32_t max_snp = -1; };
+  const int T = loader_threads();
+  const int NB = (int)std::max<int64_t>(1, std::min<int64_t>(T > 1 ? 4 * (int64_t)T : 1, C));  // droplet blocks
+  const int32_t cpb = std::max<int32_t>(1, (C + NB - 1) / NB);                                   // droplets per block
+  std::vector<Piece> pc;
+  std::vector<int64_t> npair((size_t)C, 0), nread((size_t)C, 0);
+  std::vector<int32_t> last((size_t)C, -1);
+  std::atomic<bool> unsorted(false);
+  try {
+    bool bg = false;
+    const std::vector<char> text = slurp_text(o.plp_prefix + ".plp.gz", T, &bg);
+    lap(bg ? "plp.gz inflate (BGZF, parallel)" : "plp.gz inflate");
+    const char* const tb = text.data();
+    const char* te = tb + text.size();
+    auto is_ws = [](char ch) { return ch == ' ' || ch == '\t' || ch == '\v' || ch == '\f' || ch == '\r' || ch == '\n'; };
+    // header line
+    const char* hl = (const char*)memchr(tb, '\n', text.size());
+    if (text.empty()) throw host_error("Cannot read the first line of " + o.plp_prefix + ".plp.gz");
+    {
+      std::string head(tb, hl ? hl : te);
+      std::vector<char*> hf;
+      split_ws(head, hf);
+      static const char* H[] = {"#DROPLET_ID", "SNP_ID", "ALLELES", "BASEQS"};
+      bool ok = hf.size() == 4;
+      for (int i = 0; ok && i < 4; ++i) ok = strcmp(hf[i], H[i]) == 0;
+      if (head.empty()) throw host_error("Cannot read the first line of " + o.plp_prefix + ".plp.gz");
+      if (!ok) throw host_error("The header line of " + o.plp_prefix + ".plp.gz is malformed or outdated. Expecting #DROPLET_ID SNP_ID ALLELES BASEQS");
+    }
+    const char* body = hl ? hl + 1 : te;
+    // the first empty line ends the table
+    for (const char* p = body; p < te;) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(te - p));
+      const char* le = nl ? nl : te;
+      if (le == p || (le == p + 1 && *p == '\r')) { te = p; break; }
+      if (!nl) break;
+      // only line starts matter: jump to the next "\n\n" / "\n\r\n" candidate
+      const char* dbl = (const char*)memmem(nl, (size_t)(te - nl), "\n\n", 2);
+      const char* dbr = (const char*)memmem(nl, (size_t)(te - nl), "\n\r\n", 3);
+      const char* cand = dbl && dbr ? std::min(dbl, dbr) : dbl ? dbl : dbr;
+      if (!cand) break;
+      p = cand + 1;
+    }
+    const size_t len = (size_t)(te - body);
+    const int NP = (int)std::max<size_t>(1, std::min<size_t>((size_t)T * 4, len / (1 << 20) + 1));
+    std::vector<const char*> cut(NP + 1);
+    cut[0] = body; cut[NP] = te;
+    for (int i = 1; i < NP; ++i) {
+      const char* p = body + len * (size_t)i / NP;
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(te - p));
+      cut[i] = nl ? nl + 1 : te;
+      if (cut[i] < cut[i - 1]) cut[i] = cut[i - 1];
+    }
+    pc.resize(NP);
+    const int n_index = (int)index_bcs.size();
+    parallel_for(NP, T, [&](int pi) {
+      Piece P;  // on this thread's stack while it grows: neighbours in pc[] would share cache lines
+      P.bk.resize(NB);
+      const size_t guess = (size_t)(cut[pi + 1] - cut[pi]) / 12 + 16;
+      for (auto& v : P.bk) v.reserve(guess / NB + guess / (4 * NB) + 16);
+      P.al.reserve(guess * 2); P.bq.reserve(guess * 2);
+      const char* lb = cut[pi];
+      while (lb < cut[pi + 1]) {
+        const char* nl = (const char*)memchr(lb, '\n', (size_t)(cut[pi + 1] - lb));
+        const char* const end = nl ? nl : cut[pi + 1];
+        const char* p = lb;
+        lb = nl ? nl + 1 : cut[pi + 1];
+        const char* fb[4]; const char* fe[4];
+        int nf = 0;
+        while (p < end) {
+          while (p < end && is_ws(*p)) ++p;
+          if (p >= end) break;
+          const char* q = p;
+          while (q < end && !is_ws(*q)) ++q;
+          if (nf < 4) { fb[nf] = p; fe[nf] = q; }
+          ++nf;
+          p = q;
+        }
+        if (nf < 4) throw host_error("Cannot access field at 3 >= " + std::to_string(nf));
+        auto to_int = [](const char* b2, const char* e2) {  // atoi: optional sign, leading digits
+          bool neg = false;
+          if (b2 < e2 && (*b2 == '-' || *b2 == '+')) { neg = *b2 == '-'; ++b2; }
+          long v = 0;
+          while (b2 < e2 && *b2 >= '0' && *b2 <= '9') { v = v * 10 + (*b2 - '0'); ++b2; }
+          return (int)(neg ? -v : v);
+        };
+        const int drop = to_int(fb[0], fe[0]);
+        if (drop < 0 || drop >= n_index) throw host_error("DROPLET_ID " + std::string(fb[0], fe[0]) + " of .plp.gz is not in .cel.gz");
+        const int ibc = index_bcs[drop];
+        if (ibc < 0) continue;
+        const int snp = to_int(fb[1], fe[1]);
+        if (snp < 0) throw host_error("SNP_ID " + std::string(fb[1], fe[1]) + " of .plp.gz is not in .var.gz");
+        if (snp > P.max_snp) P.max_snp = snp;  // checked against the VAR table once that thread is done
+        const char *pa = fb[2], *pq = fb[3];
+        const size_t l = (size_t)(fe[3] - fb[3]), la = (size_t)(fe[2] - fb[2]);
+        const size_t b0 = P.al.size();
+        for (size_t i = 0; i < l && i < la; ++i) {
+          int q = (int)(signed char)(pq[i] - 33);
+          if (q >= o.min_bq) {
+            if (q > o.cap_bq) q = o.cap_bq;
+            P.al.push_back((uint8_t)(pa[i] - '0'));
+            P.bq.push_back((uint8_t)q);
+          }
+        }
+        if (P.al.size() == b0) continue;
+        if (P.al.size() >= (1ull << 32)) throw host_error("a piece of .plp.gz holds 2^32 base-calls or more");
+        P.bk[ibc / cpb].push_back(Row{ibc, snp, (uint32_t)b0, (uint32_t)(P.al.size() - b0)});
+      }
+      pc[pi] = std::move(P);
+    });
+    lap("plp.gz parse (parallel)");
+    // pass 1: pairs and base-calls per droplet; is every droplet's stream ascending in SNP id?
+    parallel_for(NB, T, [&](int b) {
+      bool uns = false;
+      for (const Piece& P : pc)
+        for (const Row& rw : P.bk[b]) {
+          if (rw.snp != last[rw.cell]) { uns = uns || rw.snp < last[rw.cell]; ++npair[rw.cell]; last[rw.cell] = rw.snp; }
+          nread[rw.cell] += rw.n;
+        }
+      if (uns) unsorted = true;
+    });
+    lap("plp.gz count (parallel)");
+  } catch (...) { plp_err = std::current_exception(); }
+  var_thread.join();
+  if (var_err) std::rethrow_exception(var_err);  // the reference reads the VAR / VCF tables first: their errors win
+  if (plp_err) std::rethrow_exception(plp_err);
+  const int32_t V = (int32_t)L.chrom.size();
+  for (const Piece& P : pc)
+    if (P.max_snp >= V) throw host_error("SNP_ID " + std::to_string(P.max_snp) + " of .plp.gz is not in .var.gz");
+  lap("var.gz + vcf (wait)");
   L.n_cells = C; L.n_snps = V;
   L.cell_ptr.assign((size_t)C + 1, 0);
-  L.read_allele.resize(al.size()); L.read_qual.resize(bq.size());
   L.cell_uniq_reads.assign(C, 0);
-  if (snp_major && !sorted) {
-    // dsc-pileup's order (SNP-major; the std::map of the reference makes it cell-major, SNP ascending): every cell's rows
-    // already ascend in SNP id, so the image is two sequential passes over the rows with one write cursor per cell —
-    // no sort, no gather.  A (cell,SNP) listed on several rows is one pair: such rows are neighbours in the cell's stream.
-    std::vector<int32_t> last(C, -1);
-    std::vector<int64_t> npair(C, 0), nread(C, 0);
-    for (size_t i = 0; i < R; ++i) {
-      const Row& rw = rows[i];
-      if (rw.snp != last[rw.cell]) { ++npair[rw.cell]; last[rw.cell] = rw.snp; }
-      nread[rw.cell] += rows[i + 1].beg - rw.beg;
-    }
-    std::vector<int64_t> ppos(C), rpos(C);  // next pair / next read of each cell
+  if (!unsorted) {
+    std::vector<int64_t> ppos(C), rpos(C);  // next pair / next base-call of each droplet
     int64_t pp = 0, rr = 0;
     for (int32_t c = 0; c < C; ++c) {
       ppos[c] = pp; rpos[c] = rr; L.cell_ptr[c] = pp;
@@ -390,26 +550,44 @@ void load_plp(const LoadOptions& o, Loaded& L) {
       L.cell_uniq_reads[c] = nread[c];
     }
     L.cell_ptr[C] = pp;
-    L.pair_snp.assign((size_t)pp, 0);
-    L.pair_read_ptr.assign((size_t)pp + 1, 0);
+    L.pair_snp.resize((size_t)pp);
+    L.pair_read_ptr.resize((size_t)pp + 1);
+    L.pair_read_ptr[0] = 0;
+    L.read_allele.resize((size_t)rr); L.read_qual.resize((size_t)rr);
     std::fill(last.begin(), last.end(), -1);
-    for (size_t i = 0; i < R; ++i) {
-      const Row& rw = rows[i];
-      const int32_t c = rw.cell;
-      if (rw.snp != last[c]) { L.pair_snp[(size_t)ppos[c]++] = rw.snp; last[c] = rw.snp; }
-      int64_t w = rpos[c];
-      for (int64_t r = rw.beg; r < rows[i + 1].beg; ++r, ++w) { L.read_allele[(size_t)w] = al[r]; L.read_qual[(size_t)w] = bq[r]; }
-      rpos[c] = w;
-      L.pair_read_ptr[(size_t)ppos[c]] = w;  // end of the pair the row belongs to (= start of the next one)
-    }
-    lap("flat image (two-pass scatter)");
+    parallel_for(NB, T, [&](int b) {
+      for (const Piece& P : pc)
+        for (const Row& rw : P.bk[b]) {
+          const int32_t c = rw.cell;
+          if (rw.snp != last[c]) { L.pair_snp[(size_t)ppos[c]++] = rw.snp; last[c] = rw.snp; }
+          const int64_t w = rpos[c];
+          memcpy(&L.read_allele[(size_t)w], &P.al[rw.beg], rw.n);
+          memcpy(&L.read_qual[(size_t)w], &P.bq[rw.beg], rw.n);
+          rpos[c] = w + rw.n;
+          L.pair_read_ptr[(size_t)ppos[c]] = w + rw.n;  // end of the pair the row belongs to (= start of the next one)
+        }
+    });
+    lap("flat image (parallel scatter)");
   } else {
+    // some droplet's rows do not ascend in SNP id (not a dsc-pileup file): all rows in one list, stable sort by (cell, SNP)
+    struct GRow { int32_t cell, snp; int64_t beg; };
+    std::vector<GRow> rows;
+    std::vector<uint8_t> al, bq;
+    for (int b = 0; b < NB; ++b)      // block by block, pieces in file order: a droplet's rows keep their file order
+      for (const Piece& P : pc)
+        for (const Row& rw : P.bk[b]) {
+          rows.push_back(GRow{rw.cell, rw.snp, (int64_t)al.size()});
+          al.insert(al.end(), P.al.begin() + rw.beg, P.al.begin() + rw.beg + rw.n);
+          bq.insert(bq.end(), P.bq.begin() + rw.beg, P.bq.begin() + rw.beg + rw.n);
+        }
+    rows.push_back(GRow{-1, -1, (int64_t)al.size()});  // sentinel: end of the last row's reads
+    const size_t R = rows.size() - 1;
+    L.read_allele.resize(al.size()); L.read_qual.resize(bq.size());
     std::vector<uint32_t> order(R);
     std::iota(order.begin(), order.end(), 0u);
-    if (!sorted)
-      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        return rows[a].cell != rows[b].cell ? rows[a].cell < rows[b].cell : rows[a].snp < rows[b].snp;
-      });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return rows[a].cell != rows[b].cell ? rows[a].cell < rows[b].cell : rows[a].snp < rows[b].snp;
+    });
     lap("cell-major order");
     L.pair_read_ptr.assign(1, 0);
     L.pair_snp.reserve(R); L.pair_read_ptr.reserve(R + 1);
@@ -417,7 +595,7 @@ void load_plp(const LoadOptions& o, Loaded& L) {
     size_t w = 0;  // reads written so far
     for (size_t k = 0; k < R; ++k) {
       const uint32_t i = order[k];
-      const Row rw = rows[i];
+      const GRow rw = rows[i];
       const bool same = rw.cell == prev_c && rw.snp == prev_s;  // a (cell,SNP) listed on several rows is one pair
       const int64_t rb = rw.beg, re = rows[i + 1].beg;
       for (int64_t r = rb; r < re; ++r, ++w) { L.read_allele[w] = al[r]; L.read_qual[w] = bq[r]; }

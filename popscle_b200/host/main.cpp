@@ -9,6 +9,7 @@
 #include <cstring>
 #include <ctime>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -97,6 +98,21 @@ struct Engine {
   }
 };
 
+// The CUDA context(s) take a few hundred milliseconds to come up: they are created on a thread of their own while the
+// loader reads the files.
+struct EngineStart {
+  std::unique_ptr<Engine> eng;
+  std::exception_ptr err;
+  std::thread th;
+  explicit EngineStart(int gpus) : th([this, gpus] { try { eng.reset(new Engine(gpus)); } catch (...) { err = std::current_exception(); } }) {}
+  ~EngineStart() { if (th.joinable()) th.join(); }
+  Engine& get() {
+    if (th.joinable()) th.join();
+    if (err) std::rethrow_exception(err);
+    return *eng;
+  }
+};
+
 // test hook: what the loader produced, without touching the GPU
 int dry_run(const Loaded& L) {
   unsigned long long h = 1469598103934665603ull;
@@ -108,7 +124,7 @@ int dry_run(const Loaded& L) {
   std::swap(h, hg); mix(L.gp.data(), L.gp.size() * 8); mix(L.has_gp.data(), L.has_gp.size()); std::swap(h, hg);
   // the compact forms that actually cross the ABI (view(): ABI 2/3 arrays; geno_view(): ABI 4 raw genotypes)
   unsigned long long hc = 1469598103934665603ull, hr = 1469598103934665603ull;
-  const pscl_pileup v = L.view();
+  const pscl_pileup v = L.view(true);
   const int form = v.pair_snp_delta16 ? 3 : v.pair_read_ptr32 ? 2 : 0;
   std::swap(h, hc);
   if (v.pair_read_ptr32) { mix(v.pair_read_ptr32, (size_t)(v.n_pairs + 1) * 4); mix(v.read_aq, (size_t)v.n_reads); }
@@ -170,19 +186,26 @@ int cmd_demuxlet(int argc, char** argv) {
   if (!groupList.empty()) { lo.group_list = read_first_column(groupList); lo.has_group_list = true; }
   lo.min_mac = minMAC; lo.min_callrate = minCallRate;
   notice("Loading pileup information with prefix %s", plp.c_str());
+  std::unique_ptr<EngineStart> start(dry ? nullptr : new EngineStart(gpus));
+  trace_lap("popscle", nullptr);
   Loaded L;
   load_plp(lo, L);
+  trace_lap("popscle", "load_plp");
   notice("Finished loading %d droplets, %d variants, %zu UMIs in total..", L.n_cells, L.n_snps, L.read_allele.size());
   if (dry) return dry_run(L);
   notice("Starting to identify best matching individual IDs");
-  Engine eng(gpus);
   pscl_pileup view = L.view();
   pscl_geno geno = L.geno_view();  // raw posteriors / hard calls + error rates: the library mixes on the device
+  trace_lap("popscle", "compact forms");
+  Engine& eng = start->get();
+  trace_lap("popscle", "engine (wait)");
   pscl_demux_opts opts = {(int32_t)alphas.size(), alphas.data(), doubletPrior};
   std::vector<pscl_demux_cell> cells((size_t)L.n_cells);
   if (eng.n_gpus() > 1) notice("Sharding %d droplets over %d GPUs by pair count", L.n_cells, eng.n_gpus());
   eng.demux_run(&view, &geno, &opts, cells.data());
+  trace_lap("popscle", "demux_run");
   write_best(out + ".best", L, cells, alphas, minTotal, minUMI, minSNP);
+  trace_lap("popscle", "write_best");
   notice("Finished writing output files");
   return 0;
 }
@@ -212,8 +235,11 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
     lo.min_bq = minBQ; lo.cap_bq = capBQ; lo.min_read = minTotal; lo.min_umi = minUMI; lo.min_snp = minSNP;
     if (!groupList.empty()) { lo.group_list = read_first_column(groupList); lo.has_group_list = true; }
   }
+  std::unique_ptr<EngineStart> start(dry ? nullptr : new EngineStart(gpus));
+  trace_lap("popscle", nullptr);
   Loaded L;
   load_plp(lo, L);
+  trace_lap("popscle", "load_plp");
   notice("Finished loading %d droplets, %d variants, %zu UMIs in total..", L.n_cells, L.n_snps, L.read_allele.size());
   std::vector<int32_t> init;
   if (!initClusterFile.empty()) {  // cmd_cram_freemux2.cpp:92-104, :198-216
@@ -238,8 +264,10 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
     if (nmiss > 0) fprintf(stderr, "WARNING: %d of %d droplets do not have initial cluster assignment\n", nmiss, L.n_cells);
   }
   if (dry) return dry_run(L);
-  Engine eng(gpus);
   pscl_pileup view = L.view();
+  trace_lap("popscle", "compact forms");
+  Engine& eng = start->get();
+  trace_lap("popscle", "engine (wait)");
   pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0, randomize ? 1 : 0, seed,
                      bfThres, old_mode ? initIteration : 0, keepInitMissing ? 1 : 0};
   std::vector<pscl_fmx_cell> cells((size_t)L.n_cells);
@@ -248,11 +276,13 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   pscl_fmx_result res;
   if (eng.n_gpus() > 1) notice("Sharding %d variants over %d GPUs by pair count", L.n_snps, eng.n_gpus());
   eng.fmx_run(&view, &o, init.empty() ? NULL : init.data(), cells.data(), gl.data(), cnt.data(), &res);
+  trace_lap("popscle", "fmx_run");
   notice("Finished %d EM iterations: %d singlets, %d doublets, %d ambiguous, and %d changed", res.n_iter, res.n_singlet, res.n_doublet,
          res.n_ambiguous, res.n_changed);
   write_lmix(out + ".lmix", L, cells, old_mode);
   write_clust_vcf(out + ".clust1.vcf.gz", L, nSamples, gl, cnt);
   write_clust_samples(out + ".clust1.samples.gz", L, cells);
+  trace_lap("popscle", "writers");
   return 0;
 }
 

@@ -55,9 +55,68 @@ def _open_w(path):
     return gzip.open(path, "wt", compresslevel=1) if str(path).endswith(".gz") else open(path, "w")
 
 
-def write_plp(prefix: str, plp: Pileup, sites: Sites, barcodes=None):
+def write_bgzf(path: str, data: bytes, level: int = 1) -> None:
+    """Writes `data` the way htslib's BGZF layer does (and so the way dsc-pileup writes its tables): independent gzip members of
+    at most 0xff00 input bytes, each carrying its compressed size in a 'BC' extra field, closed by the 28-byte empty block."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        for o in range(0, len(data), 0xff00):
+            chunk = data[o:o + 0xff00]
+            z = zlib.compressobj(level, zlib.DEFLATED, -15)
+            body = z.compress(chunk) + z.flush()
+            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(body) + 25)
+                    + body + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def _digits(x: np.ndarray) -> np.ndarray:
+    nd = np.ones(len(x), dtype=np.int64)
+    t = 10
+    while len(x) and t <= int(x.max()):
+        nd += x >= t
+        t *= 10
+    return nd
+
+
+def plp_text(plp: Pileup) -> bytes:
+    """The text of prefix.plp.gz for a pileup image (header + one row per pair, SNP-major, droplet id ascending inside a SNP),
+    assembled with array operations: 20 M rows take seconds instead of a minute of per-row formatting."""
+    C = plp.n_cells
+    npair = np.diff(plp.cell_ptr)
+    pair_cell = np.repeat(np.arange(C, dtype=np.int64), npair)
+    order = np.lexsort((pair_cell, plp.pair_snp))
+    prp = np.asarray(plp.pair_read_ptr, dtype=np.int64)
+    cell, snp = pair_cell[order], np.asarray(plp.pair_snp, dtype=np.int64)[order]
+    n = (prp[1:] - prp[:-1])[order]
+    dc, ds = _digits(cell), _digits(snp)
+    rl = dc + ds + 2 * n + 4
+    off = np.concatenate(([0], np.cumsum(rl)))
+    buf = np.empty(int(off[-1]), dtype=np.uint8)
+    for x, nd, base in ((cell, dc, off[:-1]), (snp, ds, off[:-1] + dc + 1)):
+        t = x.copy()
+        for k in range(int(nd.max()) if len(nd) else 0):
+            m = nd > k
+            buf[(base + nd - 1 - k)[m]] = (48 + t % 10)[m].astype(np.uint8)
+            t //= 10
+    buf[off[:-1] + dc] = 9
+    buf[off[:-1] + dc + 1 + ds] = 9
+    buf[off[:-1] + dc + ds + 2 + n] = 9
+    buf[off[1:] - 1] = 10
+    tot = int(n.sum())
+    rstart = np.concatenate(([0], np.cumsum(n)))[:-1]
+    within = np.arange(tot, dtype=np.int64) - np.repeat(rstart, n)
+    src = np.repeat(prp[:-1][order], n) + within
+    dst = np.repeat(off[:-1] + dc + ds + 2, n) + within
+    buf[dst] = np.asarray(plp.read_allele, dtype=np.uint8)[src] + 48
+    buf[dst + np.repeat(n, n) + 1] = np.asarray(plp.read_qual, dtype=np.uint8)[src] + 33
+    return (PLP_HEADER + "\n").encode() + buf.tobytes()
+
+
+def write_plp(prefix: str, plp: Pileup, sites: Sites, barcodes=None, bgzf: bool = False):
     """Writes prefix.cel.gz / .var.gz / .plp.gz the way dsc-pileup does: PLP rows SNP-major, droplet id
-    ascending inside a SNP; ALLELES '0'/'1'/'2'; BASEQS phred+33 (cmd_cram_dsc_pileup.cpp:497-518)."""
+    ascending inside a SNP; ALLELES '0'/'1'/'2'; BASEQS phred+33 (cmd_cram_dsc_pileup.cpp:497-518).  bgzf = as BGZF blocks
+    (what htslib's writer produces) instead of one gzip stream."""
     C, V = plp.n_cells, plp.n_snps
     if barcodes is None:
         barcodes = [f"BC{c:07d}-1" for c in range(C)]
@@ -65,25 +124,19 @@ def write_plp(prefix: str, plp: Pileup, sites: Sites, barcodes=None):
     nrd = np.diff(plp.pair_read_ptr)
     pair_cell = np.repeat(np.arange(C, dtype=np.int64), npair)
     cell_reads = np.bincount(pair_cell, weights=nrd, minlength=C).astype(np.int64)
-    with _open_w(prefix + ".cel.gz") as f:
-        f.write(CEL_HEADER + "\n")
-        for c in range(C):
-            f.write(f"{c}\t{barcodes[c]}\t{int(cell_reads[c])}\t{int(cell_reads[c])}\t{int(cell_reads[c])}\t{int(npair[c])}\n")
-    with _open_w(prefix + ".var.gz") as f:
-        f.write(VAR_HEADER + "\n")
-        for v in range(V):
-            f.write(f"{v}\t{sites.chrom[v]}\t{int(sites.pos[v])}\t{sites.ref[v]}\t{sites.alt[v]}\t{sites.af[v]:.5f}\n")
-    order = np.lexsort((pair_cell, plp.pair_snp))  # SNP-major, droplet ascending
-    al = (plp.read_allele + ord("0")).astype(np.uint8).tobytes()
-    bq = (plp.read_qual + 33).astype(np.uint8).tobytes()
-    prp = plp.pair_read_ptr
-    with _open_w(prefix + ".plp.gz") as f:
-        f.write(PLP_HEADER + "\n")
-        buf = io.StringIO()
-        for p in order:
-            a, b = int(prp[p]), int(prp[p + 1])
-            buf.write(f"{int(pair_cell[p])}\t{int(plp.pair_snp[p])}\t{al[a:b].decode()}\t{bq[a:b].decode()}\n")
-        f.write(buf.getvalue())
+
+    def emit(path, text: bytes):
+        if bgzf:
+            write_bgzf(path, text)
+        else:
+            with gzip.open(path, "wb", compresslevel=1) as f:
+                f.write(text)
+
+    emit(prefix + ".cel.gz", (CEL_HEADER + "\n" + "".join(
+        f"{c}\t{barcodes[c]}\t{int(cell_reads[c])}\t{int(cell_reads[c])}\t{int(cell_reads[c])}\t{int(npair[c])}\n" for c in range(C))).encode())
+    emit(prefix + ".var.gz", (VAR_HEADER + "\n" + "".join(
+        f"{v}\t{sites.chrom[v]}\t{int(sites.pos[v])}\t{sites.ref[v]}\t{sites.alt[v]}\t{sites.af[v]:.5f}\n" for v in range(V))).encode())
+    emit(prefix + ".plp.gz", plp_text(plp))
     return barcodes
 
 

@@ -280,3 +280,50 @@ def test_vcf_without_gt_and_bad_allele_numbers(tmp_path, built):
     r = subprocess.run([exe, "demuxlet", "--plp", "p", "--vcf", "bad_gt.vcf.gz", "--field", "GT", "--out", "o", "--dry-run"], cwd=tmp_path,
                        capture_output=True, text=True)
     assert r.returncode == 134 and "beyond the ALT list" in r.stderr
+
+
+def test_parallel_ingest_bgzf_gzip_and_thread_counts_agree(tmp_path, built):
+    """N1: the C++ loader inflates BGZF blocks and parses the PLP table on several threads.  The flat image and every compact
+    form must not depend on the container (BGZF as dsc-pileup writes it / one gzip stream / plain text), on the thread count,
+    or on the row order of the table (SNP-major, cell-major, shuffled), and a corrupt block is an error, not garbage."""
+    import gzip
+    import json
+    import subprocess
+    from popscle_b200 import _build, plpio
+    s = synth.make_pileup(C=150, nv=3, V=900, kbar=260, seed=11)
+    sites = plpio.default_sites(900, s.af, seed=11)
+    exe = _build.build_host()
+    for sub in ("bg", "gz", "txt", "cellmajor", "shuffled"):
+        (tmp_path / sub).mkdir()
+    plpio.write_plp(str(tmp_path / "bg" / "p"), s.plp, sites, bgzf=True)
+    plpio.write_plp(str(tmp_path / "gz" / "p"), s.plp, sites)
+    plpio.write_vcf(str(tmp_path / "ref.vcf.gz"), sites, ["A", "B", "C"], geno=s.geno)
+    text = plpio.plp_text(s.plp)
+    assert gzip.open(tmp_path / "bg" / "p.plp.gz").read() == text and len(text) > 3 * 0xff00  # several BGZF blocks
+    rows = text.decode().splitlines()
+    head, body = rows[0], rows[1:]
+    rng = np.random.default_rng(5)
+    variants = {"txt": body, "cellmajor": sorted(body, key=lambda r: (int(r.split("\t")[0]), int(r.split("\t")[1]))),
+                "shuffled": [body[i] for i in rng.permutation(len(body))]}
+    for sub, lines in variants.items():
+        for ext in ("cel", "var"):
+            (tmp_path / sub / f"p.{ext}.gz").write_bytes((tmp_path / "gz" / f"p.{ext}.gz").read_bytes())
+        (tmp_path / sub / "p.plp.gz").write_bytes(("\n".join([head] + lines) + "\n").encode())  # plain text under the .gz name
+
+    def run(sub, threads):
+        r = subprocess.run([exe, "demuxlet", "--plp", str(tmp_path / sub / "p"), "--vcf", str(tmp_path / "ref.vcf.gz"), "--field", "GT", "--out", "o",
+                            "--dry-run"], cwd=tmp_path, capture_output=True, text=True, env=dict(os.environ, PSCL_LOADER_THREADS=str(threads)))
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    want = run("gz", 1)
+    assert want["pairs"] == s.plp.n_pairs and want["tiny_form"] == 1 and want["compact_form"] == 3
+    for sub in ("bg", "gz", "txt", "cellmajor", "shuffled"):
+        for threads in (1, 3, 16):
+            assert run(sub, threads) == want, (sub, threads)
+    # a flipped byte inside a BGZF block's deflate stream
+    raw = bytearray((tmp_path / "bg" / "p.plp.gz").read_bytes())
+    raw[len(raw) // 2] ^= 0x5a
+    (tmp_path / "bg" / "p.plp.gz").write_bytes(bytes(raw))
+    r = subprocess.run([exe, "demuxlet", "--plp", str(tmp_path / "bg" / "p"), "--vcf", str(tmp_path / "ref.vcf.gz"), "--field", "GT", "--out", "o",
+                        "--dry-run"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 134 and ("Corrupt" in r.stderr or "not in" in r.stderr or "Cannot access" in r.stderr), r.stderr
