@@ -585,6 +585,366 @@ __global__ void __launch_bounds__(256) k_fmx_seed_merge(SeedBatchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// greedy seeding, speculative batches (the default): every cell of a batch decided at once, then proven
+// ------------------------------------------------------------------------------------------------
+// The chain "cell r joins the cluster it is closest to, given the merges of cells 0..r-1" (cmd_cram_freemux2.cpp:223-260)
+// is serial only on paper: once the clusters have some weight, the few merges of the cells just ahead of r almost never
+// change r's decision.  A batch of B consecutive cells (in seeding order) is therefore handled like this:
+//   E0  every cell, in parallel, against the cluster table as it stands before the batch              -> guess A
+//   E1  every cell again, its clusters now being the table PLUS the merges of the batch's earlier cells at the SNPs it
+//       shares with them, those cells placed as guess A says (folded in seeding order, per cluster)     -> B
+//       Cell 0 of the batch has no predecessor, so B[0] is the chain's decision; if A[0..m) == B[0..m) then B[m] saw exactly
+//       the chain's table, so B is the chain's decision up to and including the first index m where A and B differ.
+//   E2  (only if they differ somewhere) the cells after m once more, with B as the placement of their predecessors -> C,
+//       right up to and including the first index where B and C differ.
+//   C   commits the proven prefix: cluster ids out, merges folded into the table per (SNP, cluster) in seeding order, and
+//       the next batch (start, size: doubled after a clean batch, shrunk to what was proven otherwise) written to ctrl[k+1].
+// Every decision is proven against exactly the table the serial chain would have seen; what differs from the chain is only
+// the summation order of a distance (as in the batched form above).  All SMs work on every step: a cell is one CTA.
+// The lists of a SNP's cells in seeding order (rk_*) come from one radix sort of (SNP, rank) keys.
+struct Seed3Ctrl { int32_t r0, nb; };
+struct Seed3Args {
+  const int32_t* elig;        // [n_elig] cells that take part, in seeding order (rank -> cell)
+  const int64_t* cell_ptr;
+  const int32_t* pair_snp;
+  const double* gl_soa;
+  const double* gl_rk;        // [P][9] the pair GLs as 72-byte records in the order of rk: the earlier cells of a batch at a
+                              //        SNP are the records just before a pair's own
+  const double* snp_af;
+  const int64_t* snp_ptr;     // [V+1] SNP-major lists ...
+  const uint32_t* rk;         // [P]   ... rank of each entry's cell; one SNP's entries in ascending rank (cells outside elig
+                              //       last, with rank n_elig)
+  const uint32_t* pos;        // [P]   entry of each cell-major pair
+  double* clust_gl;           // [V][nS][9]
+  uint8_t* present;           // [V][nS]
+  double* diag;               // [V][nS][3] diagonal of clust_gl, -1 while the cluster has no pileup at the SNP
+  double* sc0;                // [bmax][NSM] E0's distances
+  double* part;               // [bmax][Q][NSM] partial sums of the CTAs of one cell (a cell's pairs are split over Q CTAs)
+  int32_t* arrived;           // [bmax] CTAs of the cell that have delivered their part (the last one adds them up)
+  int32_t *dA, *dB, *dC;      // [bmax] decisions of the three evaluation rounds
+  Seed3Ctrl* ctrl;            // [batches + 1]
+  int32_t* stats;             // [4] batches, batches that needed E2, cells proven by E2, smallest batch
+  int32_t* clust;
+  pscl_fmx_cell* cells;
+  int64_t P;
+  int32_t nS, n_elig, bmin, bmax, Q;
+};
+
+// first index in [0, n) where x and y differ (n if none), the same value in every thread of the CTA
+__device__ __forceinline__ int seed3_first_mismatch(const int32_t* x, const int32_t* y, int n, int* s_m) {
+  if (threadIdx.x == 0) *s_m = n;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (x[i] != y[i]) { atomicMin(s_m, i); break; }
+  __syncthreads();
+  const int m = *s_m;
+  __syncthreads();
+  return m;
+}
+
+// lk2 and lk0 of one (cell pair, cluster) (sc_drop_seq.cpp:556-571), diagonals only on both sides
+__device__ __forceinline__ void fmx_seed_lks(double ci0, double ci1, double ci2, double cj0, double cj1, double cj2, double h0, double h1, double h2,
+                                             double& lk2, double& lk0) {
+  lk2 = ci0 * cj0 * h0 + ci1 * cj1 * h1 + ci2 * cj2 * h2;
+  lk0 = (ci0 * h0 + ci1 * h1 + ci2 * h2) * (cj0 * h0 + cj1 * h1 + cj2 * h2);
+}
+// A distance is sum_s log lk2 - log lk0.  The seeding kernels keep it as a running quotient prod lk2 / prod lk0 per thread
+// (mantissa, binary exponent pulled out every few terms) and take the logs per thread and cluster at the end instead of two
+// per term: the terms are >= ~1e-13 (normalised GLs clamped at 1e-6, genotype priors that sum to one), so a handful of them
+// cannot underflow.  In log space this is at least as exact as the chain's own sum of logs.
+__device__ __forceinline__ void seed3_renorm(double& m, int& ex) {
+  int k;
+  m = frexp(m, &k);
+  ex += k;
+}
+// Sums v[j] over the Q CTAs that share cell b: every CTA reduces its own threads and stores the part; the CTA that arrives
+// last adds the Q parts in their fixed order (so the sum does not depend on who was last) into dst[j] (shared memory) and
+// returns true, in every one of its threads.
+template <int NSM, int NT>
+__device__ __forceinline__ bool seed3_cell_sum(const Seed3Args& a, int b, int q, double (&v)[NSM], int nS, double (*s_w)[NSM], double* dst, int* s_last) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    if (lane == 0) s_w[warp][j] = v[j];
+  }
+  __syncthreads();
+  if (tid < nS) {
+    double x = 0.0;
+    for (int w = 0; w < NT / 32; ++w) x += s_w[w][tid];
+    a.part[((size_t)b * a.Q + q) * NSM + tid] = x;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int last = atomicAdd(a.arrived + b, 1) == a.Q - 1;
+    if (last) a.arrived[b] = 0;  // ready for the next round (kernels of one stream do not overlap)
+    *s_last = last;
+  }
+  __syncthreads();
+  if (!*s_last) return false;
+  __threadfence();
+  if (tid < nS) {
+    double x = 0.0;
+    for (int qq = 0; qq < a.Q; ++qq) x += __ldcg(a.part + ((size_t)b * a.Q + qq) * NSM + tid);
+    dst[tid] = x;
+  }
+  __syncthreads();
+  return true;
+}
+
+// E0: every cell of the batch against the cluster table as it stands before the batch
+template <int NSM, int NT>
+__global__ void __launch_bounds__(NT, NSM <= 8 ? 3 : 2) k_fmx_seed3_eval0(Seed3Args a, int k) {
+  __shared__ double s_w[NT / 32][NSM], s_sc[NSM];
+  __shared__ int s_last;
+  const Seed3Ctrl c = a.ctrl[k];
+  const int b = blockIdx.x, q = blockIdx.y, tid = threadIdx.x, nS = a.nS;
+  if (b >= c.nb) return;
+  const int si = a.elig[c.r0 + b];
+  const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
+  double num[NSM], den[NSM];
+  int en[NSM], ed[NSM];
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) { num[j] = 1.0; den[j] = 1.0; en[j] = 0; ed[j] = 0; }
+  int it = 0;
+  for (int64_t t = (int64_t)q * NT + tid; t < K; t += (int64_t)a.Q * NT, ++it) {
+    const int64_t p = pb + t;
+    const int32_t s = a.pair_snp[p];
+    const double af = a.snp_af[s];
+    const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
+    const double ci0 = a.gl_soa[p], ci1 = a.gl_soa[(size_t)4 * a.P + p], ci2 = a.gl_soa[(size_t)8 * a.P + p];
+    const double* dg = a.diag + (size_t)s * nS * 3;
+#pragma unroll
+    for (int j = 0; j < NSM; ++j) {
+      if (j < nS) {
+        const double cj0 = dg[3 * j];
+        if (cj0 >= 0.0) {  // the cluster has a pileup at this SNP (-1 otherwise)
+          double lk2, lk0;
+          fmx_seed_lks(ci0, ci1, ci2, cj0, dg[3 * j + 1], dg[3 * j + 2], h0, h1, h2, lk2, lk0);
+          num[j] *= lk2; den[j] *= lk0;
+        }
+      }
+    }
+    if ((it & 7) == 7) {
+#pragma unroll
+      for (int j = 0; j < NSM; ++j) { seed3_renorm(num[j], en[j]); seed3_renorm(den[j], ed[j]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NSM; ++j)
+    num[j] = (j < nS && it > 0) ? (log(num[j]) - log(den[j])) + (double)(en[j] - ed[j]) * 0.69314718055994530942 : 0.0;
+  if (!seed3_cell_sum<NSM, NT>(a, b, q, num, nS, s_w, s_sc, &s_last)) return;
+  if (tid < nS) a.sc0[(size_t)b * NSM + tid] = s_sc[tid];
+  if (tid == 0) {
+    int best = 0;
+    double bs = s_sc[0];
+    for (int j = 1; j < nS; ++j)
+      if (s_sc[j] > bs) { best = j; bs = s_sc[j]; }  // :238-241, first wins
+    a.dA[b] = best;
+  }
+}
+
+// E1 / E2: the same cells with the merges of the batch's earlier cells folded in.  Only the (SNP, cluster) entries such a
+// merge touches differ from E0, so this kernel computes the change of each distance — (new lk2 / new lk0) over (old lk2 /
+// old lk0) per touched entry, as a running product per (cluster, thread) in shared memory — and adds its log to E0's score.
+// A thread walks back from its pair's entry in the SNP's rank-ordered list over the batch's earlier cells (adjacent
+// entries), then takes the clusters they are placed in one at a time: cluster pileup (72 B), the earlier cells' GL records
+// (72 B each, adjacent entries) folded in seeding order, one quotient.
+template <int NSM, int ROUND, int NT>
+__global__ void __launch_bounds__(NT) k_fmx_seed3_delta(Seed3Args a, int k) {
+  extern __shared__ double s_dyn[];
+  __shared__ double s_w[NT / 32][NSM], s_sc[NSM];
+  __shared__ int s_m, s_last;
+  const Seed3Ctrl c = a.ctrl[k];
+  const int b = blockIdx.x, q = blockIdx.y, tid = threadIdx.x, nS = a.nS;
+  if (b >= c.nb) return;
+  const int32_t* specg = ROUND == 1 ? a.dA : a.dB;   // where the batch's earlier cells are assumed to go
+  int32_t* const out = ROUND == 1 ? a.dB : a.dC;
+  if (ROUND == 2) {
+    const int m1 = seed3_first_mismatch(a.dA, a.dB, c.nb, &s_m);
+    if (m1 >= c.nb) return;                          // E1 proved the whole batch
+    if (b <= m1) { if (tid == 0 && q == 0) out[b] = a.dB[b]; return; }
+  }
+  if (b == 0) { if (tid == 0 && q == 0) out[0] = a.dA[0]; return; }  // no earlier cell in the batch: E0 is the chain's decision
+  double* const acc = s_dyn;                              // [NSM][NT] running quotient of each cluster, this thread's column
+  uint8_t* const spec = (uint8_t*)(s_dyn + (size_t)NSM * NT);  // [b] placements of the earlier cells
+  for (int i = tid; i < b; i += NT) spec[i] = (uint8_t)specg[i];
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) acc[j * NT + tid] = 1.0;
+  __syncthreads();
+  const uint32_t r0 = (uint32_t)c.r0;
+  const int si = a.elig[c.r0 + b];
+  const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
+  int ex[NSM];
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) ex[j] = 0;
+  int it = 0;
+  for (int64_t t = (int64_t)q * NT + tid; t < K; t += (int64_t)a.Q * NT, ++it) {
+    const int64_t p = pb + t;
+    const int32_t s = a.pair_snp[p];
+    const int64_t qe = (int64_t)a.pos[p], lo = a.snp_ptr[s];
+    unsigned mask = 0;     // clusters an earlier cell of the batch is (assumed to be) merged into at this SNP
+    int64_t q0 = qe;
+    for (; q0 > lo; --q0) {
+      const uint32_t r = __ldg(a.rk + q0 - 1);
+      if (r < r0) break;
+      mask |= 1u << spec[r - r0];
+    }
+    if (mask) {
+      const double af = a.snp_af[s];
+      const double h0 = (1.0 - af) * (1.0 - af), h1 = 2.0 * af * (1.0 - af), h2 = af * af;
+      const double ci0 = __ldg(a.gl_rk + (size_t)qe * 9), ci1 = __ldg(a.gl_rk + (size_t)qe * 9 + 4), ci2 = __ldg(a.gl_rk + (size_t)qe * 9 + 8);
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const size_t e = (size_t)s * nS + j;
+        const double* cj = a.clust_gl + e * 9;
+        double gl[9], o[9], lk2, lk0, up = 1.0, dn = 1.0;
+#pragma unroll
+        for (int g = 0; g < 9; ++g) gl[g] = cj[g];  // 1.0 everywhere while the cluster has nothing at this SNP
+        if (a.present[e]) {  // the old term leaves the distance
+          fmx_seed_lks(ci0, ci1, ci2, gl[0], gl[4], gl[8], h0, h1, h2, lk2, lk0);
+          up = lk0; dn = lk2;
+        }
+        for (int64_t tt = q0; tt < qe; ++tt) {
+          if (spec[__ldg(a.rk + tt) - r0] != j) continue;
+          const double* src = a.gl_rk + (size_t)tt * 9;
+#pragma unroll
+          for (int g = 0; g < 9; ++g) o[g] = __ldg(src + g);
+          fmx_merge(gl, o);
+        }
+        fmx_seed_lks(ci0, ci1, ci2, gl[0], gl[4], gl[8], h0, h1, h2, lk2, lk0);
+        acc[j * NT + tid] *= (lk2 * up) / (lk0 * dn);
+      }
+    }
+    if ((it & 3) == 3) {
+#pragma unroll
+      for (int j = 0; j < NSM; ++j) {
+        double m = acc[j * NT + tid];
+        if (m != 1.0) { seed3_renorm(m, ex[j]); acc[j * NT + tid] = m; }
+      }
+    }
+  }
+  double v[NSM];
+#pragma unroll
+  for (int j = 0; j < NSM; ++j) {
+    const double m = acc[j * NT + tid];
+    v[j] = (m == 1.0 && ex[j] == 0) ? 0.0 : log(m) + (double)ex[j] * 0.69314718055994530942;
+  }
+  if (!seed3_cell_sum<NSM, NT>(a, b, q, v, nS, s_w, s_sc, &s_last)) return;
+  if (tid == 0) {
+    int best = 0;
+    double bs = 0.0;
+    for (int j = 0; j < nS; ++j) {
+      const double x = a.sc0[(size_t)b * NSM + j] + s_sc[j];
+      if (j == 0 || x > bs) { best = j; bs = x; }  // :238-241, first wins
+    }
+    out[b] = best;
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_fmx_seed3_commit(Seed3Args a, int k) {
+  extern __shared__ double s_dyn[];
+  __shared__ int s_m;
+  const Seed3Ctrl c = a.ctrl[k];
+  const int b = blockIdx.x, qc = blockIdx.y, tid = threadIdx.x, nS = a.nS;
+  if (c.nb <= 0) {
+    if (b == 0 && qc == 0 && tid == 0) a.ctrl[k + 1] = c;
+    return;
+  }
+  const int m1 = seed3_first_mismatch(a.dA, a.dB, c.nb, &s_m);
+  const int32_t* fing = a.dB;
+  int ncommit = c.nb;
+  if (m1 < c.nb) {
+    const int m2 = seed3_first_mismatch(a.dB, a.dC, c.nb, &s_m);
+    fing = a.dC;
+    ncommit = m2 + 1 < c.nb ? m2 + 1 : c.nb;
+  }
+  if (b == 0 && qc == 0 && tid == 0) {
+    Seed3Ctrl n;
+    n.r0 = c.r0 + ncommit;
+    int nb = ncommit == c.nb ? 2 * c.nb : ncommit;   // a clean batch doubles; otherwise as many as were proven
+    nb = nb < a.bmin ? a.bmin : nb;
+    nb = nb > a.bmax ? a.bmax : nb;
+    n.nb = nb < a.n_elig - n.r0 ? nb : a.n_elig - n.r0;
+    a.ctrl[k + 1] = n;
+    a.stats[0] += 1;
+    if (m1 < c.nb) { a.stats[1] += 1; a.stats[2] += ncommit - (m1 + 1); }
+    if (a.stats[3] == 0 || c.nb < a.stats[3]) a.stats[3] = c.nb;
+  }
+  if (b >= ncommit) return;
+  uint8_t* const fin = (uint8_t*)s_dyn;  // [ncommit] proven placements
+  for (int i = tid; i < ncommit; i += NT) fin[i] = (uint8_t)fing[i];
+  __syncthreads();
+  const uint32_t r0 = (uint32_t)c.r0, r1 = (uint32_t)(c.r0 + ncommit);
+  const int si = a.elig[c.r0 + b];
+  const int j = fin[b];
+  if (tid == 0 && qc == 0) {
+    a.clust[si] = j;
+    a.cells[si].clust = a.cells[si].init_clust = j;
+    a.cells[si].type = 0;
+  }
+  const int64_t pb = a.cell_ptr[si], K = a.cell_ptr[si + 1] - pb;
+  for (int64_t t = (int64_t)qc * NT + tid; t < K; t += (int64_t)a.Q * NT) {
+    const int64_t p = pb + t;
+    const int32_t s = a.pair_snp[p];
+    const int64_t q = (int64_t)a.pos[p], lo = a.snp_ptr[s], hi = a.snp_ptr[s + 1];
+    bool first = true;  // the first of the proven cells that goes into cluster j at this SNP folds all of them, in order
+    for (int64_t tt = q; tt > lo; --tt) {
+      const uint32_t r = __ldg(a.rk + tt - 1);
+      if (r < r0) break;
+      if (fin[r - r0] == j) { first = false; break; }
+    }
+    if (!first) continue;
+    const size_t e = (size_t)s * nS + j;
+    double* cg = a.clust_gl + e * 9;
+    double gl[9], o[9];
+#pragma unroll
+    for (int g = 0; g < 9; ++g) gl[g] = cg[g];
+    for (int64_t tt = q; tt < hi; ++tt) {
+      if (tt != q) {
+        const uint32_t r = __ldg(a.rk + tt);
+        if (r >= r1) break;
+        if (fin[r - r0] != j) continue;
+      }
+      const double* src = a.gl_rk + (size_t)tt * 9;
+#pragma unroll
+      for (int g = 0; g < 9; ++g) o[g] = __ldg(src + g);
+      fmx_merge(gl, o);
+    }
+#pragma unroll
+    for (int g = 0; g < 9; ++g) cg[g] = gl[g];
+    a.diag[e * 3] = gl[0]; a.diag[e * 3 + 1] = gl[4]; a.diag[e * 3 + 2] = gl[8];
+    a.present[e] = 1;
+  }
+}
+
+// (SNP, rank) keys of the cell-major pairs, and the sorted list unpacked
+__global__ void k_fmx_seed3_keys(const int32_t* __restrict__ pair_snp, const int32_t* __restrict__ pair_cell, const uint32_t* __restrict__ rank_of,
+                                 int64_t P, int rank_bits, unsigned long long* __restrict__ key, uint32_t* __restrict__ val) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  key[p] = ((unsigned long long)(uint32_t)pair_snp[p] << rank_bits) | rank_of[pair_cell[p]];
+  val[p] = (uint32_t)p;
+}
+__global__ void k_fmx_seed3_unpack(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ val, const uint32_t* __restrict__ csc_pos,
+                                   const double* __restrict__ gl_csc, int64_t P, int rank_bits, uint32_t* __restrict__ rk, uint32_t* __restrict__ pos,
+                                   double* __restrict__ gl_rk) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P) return;
+  const unsigned long long kk = key[t];
+  const uint32_t pp = val[t];
+  rk[t] = (uint32_t)(kk & ((1ull << rank_bits) - 1ull));
+  pos[pp] = (uint32_t)t;
+  const double* src = gl_csc + ((size_t)csc_pos[pp] * 32 + ((size_t)(kk >> rank_bits) & 31)) * 9;  // the M-step's 72-byte record of the pair
+#pragma unroll
+  for (int g = 0; g < 9; ++g) gl_rk[(size_t)t * 9 + g] = src[g];
+}
+
+// ------------------------------------------------------------------------------------------------
 // freemuxlet-old seeding: pairwise Bayes factors (cmd_cram_freemuxlet.cpp:174-222) on the device
 // ------------------------------------------------------------------------------------------------
 // dropDs[i][j] (j < i) accumulates, over the SNPs both droplets cover in ascending SNP order, log lk2 and log lk0 of the
@@ -1215,8 +1575,6 @@ extern "C" int pscl_fmx_stage1(pscl_ctx* ctx, double* stage1_dev) {
     ctx->launches++;
     PSCL_CUDA(ctx, cudaGetLastError());
   }
-  cudaFree(s->csc_pos);  // only stage 1 scatters through it
-  s->csc_pos = nullptr;
   s->stage1_done = true;
   return PSCL_OK;
 }
@@ -1331,6 +1689,130 @@ static int fmx_seed_old(pscl_ctx* ctx, pscl_fmx_state* s, const double* score_de
   return PSCL_OK;
 }
 
+// the four launches of one batch; dynamic shared memory = the quotient columns [NSM][NT] + one byte per cell of the batch
+template <int NSM, int NT>
+static void seed3_batch_t(const Seed3Args& a, int k, cudaStream_t st) {
+  const size_t sm_delta = sizeof(double) * NSM * NT + (size_t)a.bmax, sm_commit = ((size_t)a.bmax + 7) & ~(size_t)7;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_dev != dev) {
+    cudaFuncSetAttribute(k_fmx_seed3_delta<NSM, 1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * NSM * NT + 2048));
+    cudaFuncSetAttribute(k_fmx_seed3_delta<NSM, 2, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * NSM * NT + 2048));
+    attr_dev = dev;
+  }
+  const dim3 grid((unsigned)a.bmax, (unsigned)a.Q);
+  k_fmx_seed3_eval0<NSM, NT><<<grid, NT, 0, st>>>(a, k);
+  k_fmx_seed3_delta<NSM, 1, NT><<<grid, NT, sm_delta, st>>>(a, k);
+  k_fmx_seed3_delta<NSM, 2, NT><<<grid, NT, sm_delta, st>>>(a, k);
+  k_fmx_seed3_commit<NT><<<grid, NT, sm_commit, st>>>(a, k);
+}
+static void seed3_batch(const Seed3Args& a, int k, cudaStream_t st) {
+  if (a.nS <= 8) seed3_batch_t<8, 256>(a, k, st);
+  else if (a.nS <= 16) seed3_batch_t<16, 256>(a, k, st);
+  else seed3_batch_t<PSCL_FMX_MAX_CLUSTERS, 256>(a, k, st);
+}
+
+// greedy seeding in speculative batches (k_fmx_seed3_*): the rank-ordered SNP lists, then E0 / E1 / E2 / commit per batch;
+// the batch sequence lives on the device (ctrl[]), the host reads it back every few batches to see whether it is done
+static cudaError_t fmx_seed_speculative(pscl_ctx* ctx, pscl_fmx_state* s, const std::vector<int32_t>& elig, int32_t* clust_dev) {
+  const pscl_plp* plp = s->plp;
+  const int64_t P = s->P;
+  const int n_elig = (int)elig.size();
+  int bmax = 128;
+  if (const char* bv = getenv("PSCL_SEED_BATCH")) bmax = std::max(1, std::min(2048, atoi(bv)));
+  const int bmin = std::min(8, bmax);
+  const int NCH = 8;  // batches launched between two looks at the cursor
+  const auto t_begin = std::chrono::steady_clock::now();
+  int rank_bits = 1;
+  while ((1ll << rank_bits) <= (long long)n_elig) ++rank_bits;
+  int snp_bits = 1;
+  while ((1ll << snp_bits) < (long long)s->V) ++snp_bits;
+  std::vector<uint32_t> h_rank((size_t)s->C, (uint32_t)n_elig);
+  for (int r = 0; r < n_elig; ++r) h_rank[elig[r]] = (uint32_t)r;
+  cudaError_t e = cudaSuccess;
+  int32_t *d_elig = nullptr, *d_pair_cell = nullptr, *d_dec = nullptr, *d_stats = nullptr;
+  double *d_diag = nullptr, *d_sc0 = nullptr, *d_part = nullptr;
+  int32_t* d_arrived = nullptr;
+  // a cell's pairs are split over Q CTAs of 256 threads: about one pair per thread, so a kernel lasts one chain of dependent loads
+  int Q = (int)std::max<int64_t>(1, std::min<int64_t>(16, (P / std::max(s->C, 1) + 255) / 256));
+  if (const char* qv = getenv("PSCL_SEED_SPLIT")) Q = std::max(1, std::min(64, atoi(qv)));
+  uint32_t *d_rank_of = nullptr, *d_val = nullptr, *d_val2 = nullptr, *d_pos = nullptr;
+  uint32_t* d_rk = nullptr;
+  double* d_gl_rk = nullptr;
+  unsigned long long *d_key = nullptr, *d_key2 = nullptr;
+  Seed3Ctrl* d_ctrl = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  const size_t n_ctrl = (size_t)n_elig + NCH + 2;
+  auto alloc = [&](void** d, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16); };
+  alloc((void**)&d_elig, sizeof(int32_t) * (size_t)n_elig);
+  alloc((void**)&d_rank_of, sizeof(uint32_t) * (size_t)s->C);
+  alloc((void**)&d_pair_cell, sizeof(int32_t) * (size_t)P);
+  alloc((void**)&d_key, sizeof(unsigned long long) * (size_t)P);
+  alloc((void**)&d_key2, sizeof(unsigned long long) * (size_t)P);
+  alloc((void**)&d_val, sizeof(uint32_t) * (size_t)P);
+  alloc((void**)&d_val2, sizeof(uint32_t) * (size_t)P);
+  alloc((void**)&d_rk, sizeof(uint32_t) * (size_t)P);
+  alloc((void**)&d_gl_rk, sizeof(double) * 9 * (size_t)P);
+  alloc((void**)&d_pos, sizeof(uint32_t) * (size_t)P);
+  alloc((void**)&d_dec, sizeof(int32_t) * 3 * (size_t)bmax);
+  alloc((void**)&d_diag, sizeof(double) * 3 * (size_t)s->V * s->nS);
+  alloc((void**)&d_sc0, sizeof(double) * (size_t)bmax * PSCL_FMX_MAX_CLUSTERS);
+  alloc((void**)&d_part, sizeof(double) * (size_t)bmax * Q * PSCL_FMX_MAX_CLUSTERS);
+  alloc((void**)&d_arrived, sizeof(int32_t) * (size_t)bmax);
+  alloc((void**)&d_stats, sizeof(int32_t) * 4);
+  alloc((void**)&d_ctrl, sizeof(Seed3Ctrl) * n_ctrl);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_val, d_val2, (int64_t)P, 0, rank_bits + snp_bits, ctx->stream);
+  alloc(&d_tmp, tmp_bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_elig, elig.data(), sizeof(int32_t) * (size_t)n_elig, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rank_of, h_rank.data(), sizeof(uint32_t) * (size_t)s->C, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, sizeof(int32_t) * 4, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_arrived, 0, sizeof(int32_t) * (size_t)bmax, ctx->stream);
+  const Seed3Ctrl first = {0, std::min(bmin, n_elig)};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ctrl, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && P > 0) {
+    k_fmx_fill_f64<<<FMX_GRID((int64_t)3 * s->V * s->nS, 256), 256, 0, ctx->stream>>>(d_diag, (size_t)3 * s->V * s->nS, -1.0);
+    k_fmx_pair_cell<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(plp->cell_ptr, s->C, P, d_pair_cell);
+    k_fmx_seed3_keys<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(plp->pair_snp, d_pair_cell, d_rank_of, P, rank_bits, d_key, d_val);
+    e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_val, d_val2, (int64_t)P, 0, rank_bits + snp_bits, ctx->stream);
+    k_fmx_seed3_unpack<<<FMX_GRID(P, 256), 256, 0, ctx->stream>>>(d_key2, d_val2, s->csc_pos, s->gl_csc, P, rank_bits, d_rk, d_pos, d_gl_rk);
+    ctx->launches += 5;
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  Seed3Args a;
+  a.elig = d_elig; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.gl_rk = d_gl_rk; a.snp_af = plp->snp_af; a.snp_ptr = s->snp_ptr;
+  a.rk = d_rk; a.pos = d_pos; a.clust_gl = s->clust_gl; a.present = s->present;
+  a.diag = d_diag; a.sc0 = d_sc0; a.part = d_part; a.arrived = d_arrived; a.Q = Q; a.dA = d_dec; a.dB = d_dec + bmax; a.dC = d_dec + 2 * (size_t)bmax; a.ctrl = d_ctrl; a.stats = d_stats; a.clust = clust_dev; a.cells = s->cells;
+  a.P = P; a.nS = s->nS; a.n_elig = n_elig; a.bmin = bmin; a.bmax = bmax;
+  const bool trace = getenv("PSCL_TRACE") != nullptr;
+  if (trace && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  const auto t_lists = std::chrono::steady_clock::now();
+  Seed3Ctrl cur = first;
+  for (int k = 0; e == cudaSuccess && cur.r0 < n_elig;) {
+    if ((size_t)k + NCH + 1 > n_ctrl) { e = cudaErrorUnknown; break; }  // cannot happen: every batch proves at least one cell
+    for (int i = 0; i < NCH; ++i, ++k) {
+      seed3_batch(a, k, ctx->stream);
+      ctx->launches += 4;
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cur, d_ctrl + k, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e == cudaSuccess && trace) {
+    int32_t st[4] = {0, 0, 0, 0};
+    cudaMemcpy(st, d_stats, sizeof st, cudaMemcpyDeviceToHost);
+    const auto t_end = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pscl_fmx_seed] %d cells in %d batches of <= %d (%d needed a third round, which proved %d more cells; smallest batch %d); "
+            "%d CTAs per cell; rank-ordered SNP lists %.2f ms, batches %.2f ms\n", n_elig, st[0], bmax, st[1], st[2], st[3], Q,
+            std::chrono::duration<double, std::milli>(t_lists - t_begin).count(), std::chrono::duration<double, std::milli>(t_end - t_lists).count());
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_elig); cudaFree(d_rank_of); cudaFree(d_pair_cell); cudaFree(d_key); cudaFree(d_key2); cudaFree(d_val); cudaFree(d_val2);
+  cudaFree(d_rk); cudaFree(d_gl_rk); cudaFree(d_pos); cudaFree(d_dec); cudaFree(d_stats); cudaFree(d_ctrl); cudaFree(d_tmp); cudaFree(d_diag); cudaFree(d_sc0); cudaFree(d_part); cudaFree(d_arrived);
+  return e;
+}
+
 extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int32_t* init_clust_dev, int32_t* clust_dev) {
   FMX_STATE(ctx, s);
   if (!s->stage1_done) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_seed before pscl_fmx_stage1");
@@ -1346,6 +1828,7 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
   if (e == cudaSuccess && s->o.mode_old && s->C > 0 && (!init_clust_dev || s->o.iter_init > 0)) {
     const int rc_old = fmx_seed_old(ctx, s, score, init_clust_dev, clust_dev);
     cudaFree(score);
+    cudaFree(s->csc_pos); s->csc_pos = nullptr;
     if (rc_old != PSCL_OK) return rc_old;
     s->begun = true;
     s->iters = 0;
@@ -1397,42 +1880,49 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
         elig.push_back(si);
         epair.push_back(epair.back() + (plp->h_cell_ptr[si + 1] - plp->h_cell_ptr[si]));
       }
-      int B = 8;
-      if (const char* bv = getenv("PSCL_SEED_BATCH")) B = std::max(1, std::min(256, atoi(bv)));
       const int n_elig = (int)elig.size();
-      int64_t max_pairs = 1;
-      for (int b0 = 0; b0 < n_elig; b0 += B) max_pairs = std::max(max_pairs, epair[std::min(n_elig, b0 + B)] - epair[b0]);
-      int32_t* d_elig = nullptr; int64_t* d_epair = nullptr; unsigned long long* d_mark = nullptr; double *d_contrib = nullptr, *d_d0p = nullptr;
-      auto alloc = [&](void** d, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16); };
-      alloc((void**)&d_elig, sizeof(int32_t) * (size_t)std::max(n_elig, 1));
-      alloc((void**)&d_epair, sizeof(int64_t) * ((size_t)n_elig + 1));
-      alloc((void**)&d_mark, sizeof(unsigned long long) * (size_t)std::max(s->V, 1));
-      alloc((void**)&d_contrib, sizeof(double) * (size_t)max_pairs * s->nS);
-      alloc((void**)&d_d0p, sizeof(double) * (size_t)B * PSCL_SEED_SPLIT * s->nS);
-      if (e == cudaSuccess && n_elig) e = cudaMemcpyAsync(d_elig, elig.data(), sizeof(int32_t) * n_elig, cudaMemcpyHostToDevice, ctx->stream);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(d_epair, epair.data(), sizeof(int64_t) * ((size_t)n_elig + 1), cudaMemcpyHostToDevice, ctx->stream);
-      if (e == cudaSuccess) e = cudaMemsetAsync(d_mark, 0, sizeof(unsigned long long) * (size_t)std::max(s->V, 1), ctx->stream);
-      SeedBatchArgs a;
-      a.elig = d_elig; a.epair = d_epair; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.snp_af = plp->snp_af;
-      a.clust_gl = s->clust_gl; a.present = s->present; a.mark = d_mark; a.contrib = d_contrib; a.d0p = d_d0p; a.clust = clust_dev;
-      a.cells = s->cells; a.P = s->P; a.nS = s->nS;
-      for (int b0 = 0, batch = 0; b0 < n_elig && e == cudaSuccess; b0 += B, ++batch) {
-        a.base = b0; a.nb = std::min(B, n_elig - b0); a.batch = batch;
-        const dim3 grid((unsigned)a.nb, PSCL_SEED_SPLIT);
-        if (s->nS <= 8) { k_fmx_seed_dist<8><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<8><<<1, 1024, 0, ctx->stream>>>(a); }
-        else if (s->nS <= 16) { k_fmx_seed_dist<16><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<16><<<1, 1024, 0, ctx->stream>>>(a); }
-        else { k_fmx_seed_dist<PSCL_FMX_MAX_CLUSTERS><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<PSCL_FMX_MAX_CLUSTERS><<<1, 1024, 0, ctx->stream>>>(a); }
-        k_fmx_seed_merge<<<grid, 256, 0, ctx->stream>>>(a);
-        ctx->launches += 3;
-        e = cudaGetLastError();
+      // the batched form above (8 cells per batch, serial corrections) is kept as a cross-check, and takes over when a state is
+      // seeded a second time (csc_pos is gone)
+      if (getenv("PSCL_SEED_V2") || !s->csc_pos || false) {
+        int B = 8;
+        if (const char* bv = getenv("PSCL_SEED_BATCH")) B = std::max(1, std::min(256, atoi(bv)));
+        int64_t max_pairs = 1;
+        for (int b0 = 0; b0 < n_elig; b0 += B) max_pairs = std::max(max_pairs, epair[std::min(n_elig, b0 + B)] - epair[b0]);
+        int32_t* d_elig = nullptr; int64_t* d_epair = nullptr; unsigned long long* d_mark = nullptr; double *d_contrib = nullptr, *d_d0p = nullptr;
+        auto alloc = [&](void** d, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16); };
+        alloc((void**)&d_elig, sizeof(int32_t) * (size_t)std::max(n_elig, 1));
+        alloc((void**)&d_epair, sizeof(int64_t) * ((size_t)n_elig + 1));
+        alloc((void**)&d_mark, sizeof(unsigned long long) * (size_t)std::max(s->V, 1));
+        alloc((void**)&d_contrib, sizeof(double) * (size_t)max_pairs * s->nS);
+        alloc((void**)&d_d0p, sizeof(double) * (size_t)B * PSCL_SEED_SPLIT * s->nS);
+        if (e == cudaSuccess && n_elig) e = cudaMemcpyAsync(d_elig, elig.data(), sizeof(int32_t) * n_elig, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_epair, epair.data(), sizeof(int64_t) * ((size_t)n_elig + 1), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_mark, 0, sizeof(unsigned long long) * (size_t)std::max(s->V, 1), ctx->stream);
+        SeedBatchArgs a;
+        a.elig = d_elig; a.epair = d_epair; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa; a.snp_af = plp->snp_af;
+        a.clust_gl = s->clust_gl; a.present = s->present; a.mark = d_mark; a.contrib = d_contrib; a.d0p = d_d0p; a.clust = clust_dev;
+        a.cells = s->cells; a.P = s->P; a.nS = s->nS;
+        for (int b0 = 0, batch = 0; b0 < n_elig && e == cudaSuccess; b0 += B, ++batch) {
+          a.base = b0; a.nb = std::min(B, n_elig - b0); a.batch = batch;
+          const dim3 grid((unsigned)a.nb, PSCL_SEED_SPLIT);
+          if (s->nS <= 8) { k_fmx_seed_dist<8><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<8><<<1, 1024, 0, ctx->stream>>>(a); }
+          else if (s->nS <= 16) { k_fmx_seed_dist<16><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<16><<<1, 1024, 0, ctx->stream>>>(a); }
+          else { k_fmx_seed_dist<PSCL_FMX_MAX_CLUSTERS><<<grid, 256, 0, ctx->stream>>>(a); k_fmx_seed_commit<PSCL_FMX_MAX_CLUSTERS><<<1, 1024, 0, ctx->stream>>>(a); }
+          k_fmx_seed_merge<<<grid, 256, 0, ctx->stream>>>(a);
+          ctx->launches += 3;
+          e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // elig / epair are pageable sources
+        cudaFree(d_elig); cudaFree(d_epair); cudaFree(d_mark); cudaFree(d_contrib); cudaFree(d_d0p);
+      } else if (n_elig > 0) {
+        e = fmx_seed_speculative(ctx, s, elig, clust_dev);
       }
-      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // elig / epair are pageable sources
-      cudaFree(d_elig); cudaFree(d_epair); cudaFree(d_mark); cudaFree(d_contrib); cudaFree(d_d0p);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h_order is a pageable source
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(score);
+  cudaFree(s->csc_pos); s->csc_pos = nullptr;  // stage 1 scatters through it, the speculative seeding finds the GL records with it
   if (e != cudaSuccess) return pscl_fail(ctx, PSCL_ECUDA, "freemuxlet seeding failed: %s", cudaGetErrorString(e));
   s->begun = true;
   s->iters = 0;

@@ -161,10 +161,12 @@ def test_fmx_errors(ctx):
 
 
 @pytest.mark.parametrize("shape", [(3000, 8, 20000, 600), (600, 5, 500, 200), (900, 16, 6000, 500), (300, 20, 3000, 300)])
-@pytest.mark.parametrize("batch", [1, 7, 32, 256])
+@pytest.mark.parametrize("batch", [1, 7, 32, 256, 1024])
 def test_batched_seeding_takes_the_serial_chains_decisions(ctx, shape, batch):
-    """k_fmx_seed_dist + k_fmx_seed_commit (snapshot distances + corrections at the SNPs dirtied inside the batch) against
-    the one-CTA serial chain k_fmx_seed, from sparse (few shared SNPs) to dense (every SNP shared) pileups."""
+    """The speculative batches (k_fmx_seed3_*: every cell of a batch decided at once against the table before the batch, then
+    proven against the merges of the batch's earlier cells) and the older batched form (k_fmx_seed_dist + k_fmx_seed_commit:
+    snapshot distances + serial corrections) against the one-CTA serial chain k_fmx_seed, from sparse (few shared SNPs) to
+    dense (every SNP shared) pileups, whatever the batch size."""
     C, nS, V, kbar = shape
     s = synth.make_pileup(C=C, nv=nS, V=V, kbar=kbar, seed=500 + nS)
     o = ctx.fmx_opts(nS, max_iter=0)
@@ -176,10 +178,32 @@ def test_batched_seeding_takes_the_serial_chains_decisions(ctx, shape, batch):
     os.environ["PSCL_SEED_BATCH"] = str(batch)
     try:
         batched, _, gl, cnt = ctx.fmx_run(s.plp, o, want_clusters=True)
+        if batch <= 256:
+            os.environ["PSCL_SEED_V2"] = "1"
+            try:
+                v2 = ctx.fmx_run(s.plp, o)[0]
+            finally:
+                del os.environ["PSCL_SEED_V2"]
+            assert np.array_equal(v2["init_clust"], serial["init_clust"])
     finally:
         del os.environ["PSCL_SEED_BATCH"]
     assert np.array_equal(batched["init_clust"], serial["init_clust"])
     assert (np.bincount(batched["init_clust"], minlength=nS) > 0).all()
+
+
+def test_speculative_seeding_with_threshold_and_fraction(ctx):
+    """cells below --frac-init-clust / the singlet-score threshold take no part (:225-226): they stay unassigned and their
+    pileups never enter a cluster, in the speculative batches as in the serial chain."""
+    s = synth.make_pileup(C=700, nv=6, V=4000, kbar=400, seed=321)
+    o = ctx.fmx_opts(6, max_iter=0, frac_init_clust=0.6)
+    os.environ["PSCL_SEED_SERIAL"] = "1"
+    try:
+        serial = ctx.fmx_run(s.plp, o)[0]
+    finally:
+        del os.environ["PSCL_SEED_SERIAL"]
+    spec = ctx.fmx_run(s.plp, o)[0]
+    assert np.array_equal(spec["init_clust"], serial["init_clust"])
+    assert 250 < (spec["init_clust"] < 0).sum() < 300
 
 
 def test_batched_seeding_vs_oracle_at_2000_cells(ctx):
