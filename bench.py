@@ -483,14 +483,17 @@ def main():
     hplp._compact4 = tuple(arrs[k] for k in ("cell_first_snp", "pair_snp_delta8", "snp_gap_big", "cell_gap_big_ptr", "pair_nreads2", "nreads_big", "nreads_big_ptr"))
     h2d = sum(v.nbytes for v in arrs.values()) + gt_pin.nbytes
     d2h = 160 * plp.n_cells
+    from popscle_b200.capi import DEMUX_CELL_DTYPE
+    out_t = torch.empty(plp.n_cells * DEMUX_CELL_DTYPE.itemsize, dtype=torch.uint8).pin_memory(); keep.append(out_t)
+    out_pin = out_t.numpy().view(DEMUX_CELL_DTYPE)  # the records land in pinned memory too
     for _ in range(2):
-        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=4)
+        out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=4, out=out_pin)
     barrier()
     e2e_steps = max(3, min(args.steps, 200))  # the same K steps as the device-resident arm
     # The GPU boxes are shared hosts: single calls stalled for 5-900 ms in some visits (profiles/r0*_bench.json,
     # `ms_per_call`), with and without the staged path.  The K calls are therefore timed five times back to back and
     # the MEDIAN repeat is reported (every repeat's total is in the line); each repeat is max-over-ranks.
-    E2E_REPEATS = 5
+    E2E_REPEATS = 7
     totals, calls = [], []
     for _rep in range(E2E_REPEATS):
         barrier()
@@ -498,7 +501,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             tc = time.perf_counter()
-            out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=4)
+            out = ctx.demux_run(hplp, gp_pin, None, ALPHAS, 0.5, compact=4, out=out_pin)
             per_call.append(round((time.perf_counter() - tc) * 1e3, 3))
         torch.cuda.synchronize()
         totals.append(time.perf_counter() - t0)

@@ -495,13 +495,17 @@ class Context:
         return a.value, b.value
 
     def demux_run(self, plp: Pileup, gp: np.ndarray, has_gp, alphas, doublet_prior: float = 0.5,
-                  want_grid: bool = False, compact: bool = False):
-        """The one-call path of the CLI host: host buffers in, per-cell records out."""
+                  want_grid: bool = False, compact: bool = False, out: np.ndarray | None = None):
+        """The one-call path of the CLI host: host buffers in, per-cell records out (into `out` when given: a caller that
+        repeats the call keeps one — pinned — record array instead of a fresh pageable one per call)."""
         al = np.ascontiguousarray(alphas, dtype=np.float64)
         cs = plp.c_struct(compact=compact)
         g, keep, _, nv = self._geno(gp, has_gp)
         o = CDemuxOpts(len(al), al.ctypes.data, doublet_prior)
-        out = np.zeros(plp.n_cells, dtype=DEMUX_CELL_DTYPE)
+        if out is None:
+            out = np.zeros(plp.n_cells, dtype=DEMUX_CELL_DTYPE)
+        elif out.dtype != DEMUX_CELL_DTYPE or out.shape != (plp.n_cells,) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous array of n_cells DEMUX_CELL_DTYPE records")
         grid = np.empty((plp.n_cells, nv, nv, len(al))) if want_grid else None
         self._chk(self.lib.pscl_demux_run(self.h, C.byref(cs), C.byref(g), C.byref(o), out.ctypes.data,
                                           grid.ctypes.data if want_grid else None))

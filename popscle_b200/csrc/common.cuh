@@ -66,6 +66,8 @@ struct pscl_plp {
   int64_t n_gap_big = 0;
   int* d_bad = nullptr;
   int n_stages = 0;
+  int n_slices = 0;  // pipelined pscl_demux_run: the gaps land slice by slice (one event each) and every slice is decoded and
+                     // scored by its own launches; stage_cell[] holds the cuts of either form
   int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};
 };
 
@@ -81,6 +83,16 @@ struct pscl_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D slices of a staged pscl_demux_run
   cudaEvent_t stage_go = nullptr;
+  cudaEvent_t ev_up = nullptr;         // a run's non-sliced arrays have landed (recorded on copy_stream)
+  cudaEvent_t ev_counts = nullptr;     // ... its base-call counts have (they come first: their scan runs under the other copies)
+  cudaEvent_t slice_ev[PSCL_MAX_STAGES] = {nullptr};  // ... slice k of the gaps has
+  // deferred H2D copies of a run: queued on copy_stream once every destination buffer exists (see plp_upload_impl)
+  struct PendingCopy { void* dst; const void* src; size_t bytes; };
+  std::vector<PendingCopy> pend;
+  bool pend_on = false;
+  // PSCL_TIMELINE=1: device-time stamps of a run (ms after its first enqueue), printed by pscl_demux_run
+  cudaEvent_t tl[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool tl_on = false;
   int* stage_flags = nullptr;          // device [PSCL_MAX_STAGES]: slice k has landed (written by the copy queue)
   int* h_one = nullptr;                // pinned host word holding 1, the source of those flag writes
   long long stage_spin_ticks = 1ll << 32;  // how long a warp of the staged kernel waits for a slice (PSCL_STAGE_TIMEOUT_MS, default 2000)
@@ -99,6 +111,11 @@ struct pscl_ctx {
   int* gp_dict_over = nullptr;             // device flag: more than 256 distinct triples (or a hash clash)
   int* h_dict_over = nullptr;              // pinned host copy of the flag
   int* h_geno_bad = nullptr;               // pinned: the raw genotype input (ABI 4) held an invalid hard-call code
+  int* h_bad = nullptr;                    // pinned: the pileup image's validity flag, read back at the end of a run
+  // pinned staging for the small host-built arrays of a run (work items, rebased offsets): copies out of pageable vectors
+  // would stall the host behind the big copies already queued on the stream
+  char* h_stage = nullptr;
+  size_t h_stage_cap = 0, h_stage_used = 0;
   cudaEvent_t ev_dict = nullptr;           // the host copy is valid once this has completed
   bool dict_built = false;
   int dm_last_kernel = 0;                  // what the last pscl_demux_score launched (pscl_demux_select_kernel's numbering)

@@ -40,9 +40,13 @@ extern "C" int pscl_create(int device, pscl_ctx** out, char* err, size_t errlen)
   cudaEventCreate(&c->ev2);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->stage_go, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming);
+  for (auto& ev : c->slice_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   if (cudaHostAlloc((void**)&c->h_one, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_one = 1;
   if (cudaHostAlloc((void**)&c->h_dict_over, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_dict_over = 1;
   if (cudaHostAlloc((void**)&c->h_geno_bad, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_geno_bad = 0;
+  if (cudaHostAlloc((void**)&c->h_bad, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *c->h_bad = 0;
   cudaEventCreateWithFlags(&c->ev_dict, cudaEventDisableTiming);
   {  // keep freed blocks mapped in the device's default pool (see common.cuh: device memory)
     cudaMemPool_t pool = nullptr;
@@ -103,9 +107,14 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   cudaEventDestroy(ctx->ev2);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->stage_go) cudaEventDestroy(ctx->stage_go);
+  if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
+  if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
+  for (auto& ev : ctx->slice_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->h_one) cudaFreeHost(ctx->h_one);
   if (ctx->h_dict_over) cudaFreeHost(ctx->h_dict_over);
   if (ctx->h_geno_bad) cudaFreeHost(ctx->h_geno_bad);
+  if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev_dict) cudaEventDestroy(ctx->ev_dict);
   cudaFree(ctx->gp_code); cudaFree(ctx->gp_dict); cudaFree(ctx->gp_dict_key); cudaFree(ctx->gp_dict_over);
   cudaFree(ctx->stage_flags);
@@ -235,35 +244,76 @@ __global__ void k_decode_snp(const int64_t* __restrict__ cell_ptr, const int32_t
   }
   if (oob && lane == 0) atomicExch(bad, 2);
 }
-// ABI 6: SNP ids from 8-bit gaps with the large ones on the side, one warp per cell, 32 gaps per step.  gap_big is indexed
-// from the cell's own first large gap (cell_gap_ptr) plus the rank of the marker inside the cell.
-__global__ void k_decode_snp8(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ first, const uint8_t* __restrict__ delta8,
-                              const uint32_t* __restrict__ gap_big, const int64_t* __restrict__ cell_gap_ptr, int64_t n_gap_big, int32_t C, int32_t V,
-                              int32_t* __restrict__ pair_snp, int* bad) {
-  const int c = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+// ABI 6: SNP ids from 8-bit gaps with the large ones on the side.  One CTA per cell, tiles of 2048 gaps (8 per thread): a
+// block scan of the marker counts places every 255 in gap_big (indexed from the cell's own first large gap, cell_gap_ptr),
+// a second one of the resolved gaps gives the ids — a cell is a couple of microseconds of dependent work instead of a warp
+// walking its 60 steps of 32 gaps one after the other, which made every launch last ~70 us however few cells it had (the
+// pipelined pscl_demux_run decodes slice by slice).
+#define PSCL_DEC8_NT 256
+#define PSCL_DEC8_PER 8
+__device__ __forceinline__ int dec8_block_exscan(int v, int* s_warp, int& total) {  // exclusive scan over the CTA's 256 threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  int before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < PSCL_DEC8_NT / 32; ++w) { const int t = s_warp[w]; before += w < warp ? t : 0; all += t; }
+  __syncthreads();
+  total = all;
+  return before + x - v;
+}
+__global__ void __launch_bounds__(PSCL_DEC8_NT) k_decode_snp8(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ first,
+                              const uint8_t* __restrict__ delta8, const uint32_t* __restrict__ gap_big, const int64_t* __restrict__ cell_gap_ptr,
+                              int64_t n_gap_big, int32_t C, int32_t V, int32_t* __restrict__ pair_snp, int* bad) {
+  __shared__ int s_warp[PSCL_DEC8_NT / 32];
+  __shared__ int s_oob;
+  const int c = blockIdx.x, tid = threadIdx.x;
   if (c >= C) return;
   const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
   if (b >= e) return;
+  if (tid == 0) s_oob = 0;
   int run = first[c];
   int64_t big = cell_gap_ptr[c];
   bool oob = run < 0 || run >= V;
-  for (int64_t base = b; base < e; base += 32) {
-    const int64_t p = base + lane;
-    int d = (p < e && p > b) ? (int)delta8[p] : 0;
-    const unsigned m = __ballot_sync(0xffffffffu, d == 255);
-    if (d == 255) {
-      const int64_t k = big + __popc(m & ((1u << lane) - 1u));
-      if (k < n_gap_big) d = (int)gap_big[k]; else { d = 0; oob = true; }
-    }
-    big += __popc(m);
+  for (int64_t base = b; base < e; base += PSCL_DEC8_NT * PSCL_DEC8_PER) {
+    const int64_t p0 = base + (int64_t)tid * PSCL_DEC8_PER;
+    int d[PSCL_DEC8_PER];
+    int nmark = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, d, o); if (lane >= o) d += t; }
-    const int id = run + d;
-    if (p < e) { pair_snp[p] = id; oob |= id < 0 || id >= V; }
-    run = __shfl_sync(0xffffffffu, id, 31);
+    for (int i = 0; i < PSCL_DEC8_PER; ++i) {
+      const int64_t p = p0 + i;
+      d[i] = (p < e && p > b) ? (int)delta8[p] : 0;
+      nmark += d[i] == 255;
+    }
+    int tot_mark;
+    int64_t k = big + dec8_block_exscan(nmark, s_warp, tot_mark);
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < PSCL_DEC8_PER; ++i) {
+      if (d[i] == 255) {
+        if (k < n_gap_big) d[i] = (int)gap_big[k]; else { d[i] = 0; oob = true; }
+        ++k;
+      }
+      sum += d[i];
+    }
+    big += tot_mark;
+    int tot_sum;
+    int id = run + dec8_block_exscan(sum, s_warp, tot_sum);
+#pragma unroll
+    for (int i = 0; i < PSCL_DEC8_PER; ++i) {
+      const int64_t p = p0 + i;
+      id += d[i];
+      if (p < e) { pair_snp[p] = id; oob |= id < 0 || id >= V; }
+    }
+    run += tot_sum;
   }
   if (big != cell_gap_ptr[c + 1]) oob = true;  // the cell used more or fewer large gaps than the host says it owns
-  if (__any_sync(0xffffffffu, oob) && lane == 0) atomicExch(bad, 2);
+  if (oob) s_oob = 1;
+  __syncthreads();
+  if (tid == 0 && s_oob) atomicExch(bad, 2);
 }
 // ABI 6: base-call counts from two bits per pair with the counts >= 4 on the side; one warp per block of 1024 GLOBAL pair
 // indices (blk_ptr[k] = large counts before pair 1024*k); the image holds pairs [pair_base, pair_base + P) of the host's
@@ -332,7 +382,7 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
   if (!p) return;
   if (ctx) {
     t_pscl_stream = ctx->stream; t_pscl_ctx = ctx; cudaSetDevice(ctx->device);
-    if (p->n_stages && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // slices still in flight write into d_delta
+    if ((p->n_stages || p->n_slices) && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // slices still in flight write into d_delta
     cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_bad); cudaFree(p->d_delta8); cudaFree(p->d_gap_big); cudaFree(p->d_cell_gap_ptr);
@@ -351,7 +401,40 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
 // Work items of a device image from its (host copy of the) cell_ptr: chunks of <= PSCL_ITEM_PAIRS pairs of one cell, listed
 // by descending size (counting sort; a staged image is ordered slice by slice, so that the kernel's first items are the
 // ones whose gaps land first).  Enqueues the five item arrays on ctx->stream; the host vectors live in *p.
-static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cell_ptr) {
+// Pinned staging of a run's small host-built arrays.  pscl_stage_begin sizes the buffer (false: too large or no pinned
+// memory, the caller copies from its pageable vectors and drains); pscl_stage_copy places `bytes` in it and queues the
+// copy.  The buffer is reused by the next upload of the context, which starts after the previous run's final drain.
+static bool pscl_stage_begin(pscl_ctx* ctx, size_t need) {
+  ctx->h_stage_used = 0;
+  if (need > ((size_t)256 << 20)) return false;
+  if (need > ctx->h_stage_cap) {
+    if (ctx->h_stage) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_cap = 0; }
+    const size_t cap = std::max<size_t>(need + need / 2, (size_t)1 << 20);
+    if (cudaHostAlloc((void**)&ctx->h_stage, cap, cudaHostAllocDefault) != cudaSuccess) { ctx->h_stage = nullptr; cudaGetLastError(); return false; }
+    ctx->h_stage_cap = cap;
+  }
+  return true;
+}
+static cudaError_t pscl_stage_copy(pscl_ctx* ctx, void* dst, const void* src, size_t bytes, bool staged) {
+  if (!bytes) return cudaSuccess;
+  if (staged && ctx->h_stage_used + bytes + 16 <= ctx->h_stage_cap) {
+    char* at = ctx->h_stage + ctx->h_stage_used;
+    memcpy(at, src, bytes);
+    ctx->h_stage_used += (bytes + 15) & ~(size_t)15;
+    src = at;
+  }
+  if (ctx->pend_on) { ctx->pend.push_back({dst, src, bytes}); return cudaSuccess; }
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+}
+// an H2D copy of one of the caller's arrays: at once on the context's stream, or (a run's deferred upload) listed for the
+// copy stream
+static cudaError_t pscl_h2d(pscl_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return cudaSuccess;
+  if (ctx->pend_on) { ctx->pend.push_back({dst, src, bytes}); return cudaSuccess; }
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+}
+
+static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cell_ptr, bool staged) {
   const int32_t C = p->C;
   const int64_t P = p->P;
   p->h_cell_ptr.assign(cell_ptr, cell_ptr + C + 1);
@@ -377,7 +460,7 @@ static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cel
   {
     const int NB = PSCL_ITEM_PAIRS + 64;
     std::vector<int32_t> head(NB + 1);
-    const int nseg = p->n_stages > 1 ? p->n_stages : 1;
+    const int nseg = p->n_stages > 1 ? p->n_stages : p->n_slices > 1 ? p->n_slices : 1;
     for (int k = 0; k < nseg; ++k) {
       const int32_t ib = nseg > 1 ? p->h_cell_item_ptr[p->stage_cell[k]] : 0;
       const int32_t ie = nseg > 1 ? p->h_cell_item_ptr[p->stage_cell[k + 1]] : p->n_items;
@@ -390,7 +473,7 @@ static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cel
   cudaError_t e = cudaSuccess;
   auto up = [&](void** d, const void* src, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(d, bytes ? bytes : 16);
-    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && bytes) e = pscl_stage_copy(ctx, *d, src, bytes, staged);
   };
   up((void**)&p->item_cell, item_cell.data(), sizeof(int32_t) * p->n_items);
   up((void**)&p->item_pbeg, pbeg.data(), sizeof(int64_t) * p->n_items);
@@ -404,7 +487,10 @@ static cudaError_t plp_make_items(pscl_ctx* ctx, pscl_plp* p, const int64_t* cel
 // this image starts at base-call `read_base` of it (barcode shards of pscl_multi_demux_run point into the caller's arrays).
 // pair_base: the same for the ABI-6 count arrays (pair_nreads2 / nreads_big / nreads_big_ptr are indexed by the caller's
 // global pair numbers; every other array of a shard view is already offset).
-static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages, int64_t read_base = 0, int64_t pair_base = 0) {
+// deferred: the caller (pscl_demux_run) reads the validity flag itself at the end of its run and drains there, so nothing
+// here waits for the device (the small host-built arrays go through the context's pinned staging buffer).
+static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, int stages, int64_t read_base = 0, int64_t pair_base = 0, bool deferred = false,
+                           const pscl_geno* geno_hook = nullptr, int slices = 1) {
   if (!h || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_plp_upload: NULL argument");
   *out = nullptr;
   static const bool trace = getenv("PSCL_TRACE") != nullptr;  // wall-clock of the upload's phases on stderr
@@ -439,12 +525,20 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   if (stages > PSCL_MAX_STAGES) stages = PSCL_MAX_STAGES;
   pscl_plp* p = new pscl_plp();
   p->C = C; p->V = V; p->P = P; p->N = N;
+  // staging need: work items (<= C + P / PSCL_ITEM_PAIRS + 1 of them, 24 B each) + cell_item_ptr + rebased gap offsets
+  if (deferred) deferred = ctx->copy_stream && ctx->ev_up && pscl_stage_begin(ctx, ((size_t)C + (size_t)(P / PSCL_ITEM_PAIRS) + 2) * 24 + ((size_t)C + 1) * 12 + 4096);
+  // A deferred upload lists its H2D copies instead of queueing them: once every destination exists they all go to the copy
+  // stream in one run (small arrays, counts, base-calls, then the gap slices), so the PCIe link is busy from the first
+  // microsecond while the context's stream builds the genotype tables and then decodes what has landed.
+  ctx->pend.clear();
+  ctx->pend_on = deferred;
+  struct PendOff { pscl_ctx* c; ~PendOff() { c->pend_on = false; } } pend_off__{ctx};
 
   // ---- 1. the big arrays first: their copies run while the host builds the work items below -------
   auto up = [&](void** d, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(d, bytes ? bytes : 16);
     if (e != cudaSuccess) return e;
-    if (bytes) e = cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (bytes) e = pscl_h2d(ctx, *d, src, bytes);
     return e;
   };
   cudaError_t e = cudaSuccess;
@@ -471,9 +565,10 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       if (e == cudaSuccess) e = up((void**)&d_nbig, h->nreads_big ? h->nreads_big + big0 : nullptr, (size_t)n_big_local);
       if (e == cudaSuccess) e = up((void**)&d_nblk, h->nreads_big_ptr + k0, sizeof(int64_t) * (size_t)(k1 - k0 + 1));
       n2_first = g_first;
-    } else if (e == cudaSuccess && P > 0) e = cudaMemcpyAsync(d_cnt, h->pair_nreads8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
+    } else if (e == cudaSuccess && P > 0) e = pscl_h2d(ctx, d_cnt, h->pair_nreads8, (size_t)P);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
     STEP("pair_nreads8 / pair_rd");
+    if (ctx->pend_on) ctx->pend.push_back({nullptr, (const void*)1, 0});  // marker: the counts are complete up to here
   } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
   else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
   if (pal) {  // unpacked by k_unpack_reads
@@ -503,11 +598,14 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       for (int32_t c = 0; c <= C; ++c) cg[c] = h->cell_gap_big_ptr[c] - g0;
       if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_delta8, (size_t)P + 16);
       if (e == cudaSuccess) e = up((void**)&p->d_gap_big, h->snp_gap_big ? h->snp_gap_big + g0 : nullptr, sizeof(uint32_t) * (size_t)n_gap_local);
-      if (e == cudaSuccess) e = up((void**)&p->d_cell_gap_ptr, cg.data(), sizeof(int64_t) * ((size_t)C + 1));
+      if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_cell_gap_ptr, sizeof(int64_t) * ((size_t)C + 1));
+      if (e == cudaSuccess) e = pscl_stage_copy(ctx, p->d_cell_gap_ptr, cg.data(), sizeof(int64_t) * ((size_t)C + 1), deferred);
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_snp, sizeof(int32_t) * (P ? P : 1));
-    if (stages > 1) {  // slices of whole cells with about equal pair counts; their copies are queued in step 2b
-      p->n_stages = stages;
+    if (!deferred || !cnt8 || C < 2 * slices) slices = 1;
+    if (slices > PSCL_MAX_STAGES) slices = PSCL_MAX_STAGES;
+    if (stages > 1 || slices > 1) {  // slices of whole cells with about equal pair counts; their copies are queued in step 2b
+      if (stages > 1) p->n_stages = stages; else { p->n_slices = slices; stages = slices; }
       p->stage_cell[0] = 0;
       for (int k = 1; k < stages; ++k) {
         const int64_t want = P * k / stages;
@@ -516,41 +614,83 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       }
       p->stage_cell[stages] = C;
     } else if (e == cudaSuccess && P > 0) {
-      e = dsnp ? cudaMemcpyAsync(p->d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P, cudaMemcpyHostToDevice, ctx->stream)
-               : cudaMemcpyAsync(p->d_delta8, h->pair_snp_delta8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream);
+      e = dsnp ? pscl_h2d(ctx, p->d_delta, h->pair_snp_delta16, sizeof(uint16_t) * P) : pscl_h2d(ctx, p->d_delta8, h->pair_snp_delta8, (size_t)P);
     }
   } else {
     UP(pair_snp, h->pair_snp, sizeof(int32_t) * P);
   }
   STEP("pair_snp_delta16 / pair_snp");
   if (h->snp_af) UP(snp_af, h->snp_af, sizeof(double) * V);
+
+  // deferred upload: the copies listed so far go to the copy stream (once the context's stream has reached the point where
+  // their destinations exist: stream-ordered allocation); called after the big arrays and again after the work items
+  bool counts_marked = false;
+  auto flush = [&]() {
+    if (!deferred || e != cudaSuccess) return;
+    e = cudaEventRecord(ctx->stage_go, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_go, 0);
+    for (size_t i = 0; i < ctx->pend.size() && e == cudaSuccess; ++i) {
+      if (!ctx->pend[i].dst) { e = cudaEventRecord(ctx->ev_counts, ctx->copy_stream); counts_marked = true; continue; }
+      e = cudaMemcpyAsync(ctx->pend[i].dst, ctx->pend[i].src, ctx->pend[i].bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    }
+    ctx->pend.clear();
+  };
+  flush();  // the big arrays are on their way while the host builds the work items
   const auto tr1 = tnow(false);
 
   // ---- 2. work items (host; overlaps the copies) -------------------------------------------------------
-  if (e == cudaSuccess) e = plp_make_items(ctx, p, h->cell_ptr);
+  if (e == cudaSuccess) e = plp_make_items(ctx, p, h->cell_ptr, deferred);
   STEP("work items");
   const auto tr2 = tnow(false);
 #undef UP
-  // ---- 2b. staged image: the gaps go last, slice by slice on the copy stream, a flag word behind each slice ----------
-  if (p->n_stages > 1) {
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->stage_flags, 0, sizeof(int) * PSCL_MAX_STAGES, ctx->stream);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->stage_go, ctx->stream);
+  // ---- 2b. deferred upload: the rest of the list; staged / sliced image: the gaps go last, slice by slice on the copy
+  //          stream, a flag word (staged) or an event (sliced) behind each slice -----------------------------------------
+  if (p->n_stages > 1 && e == cudaSuccess) e = cudaMemsetAsync(ctx->stage_flags, 0, sizeof(int) * PSCL_MAX_STAGES, ctx->stream);
+  if (deferred) {
+    flush();
+    ctx->pend_on = false;
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_up, ctx->copy_stream);
+    if (ctx->tl_on) cudaEventRecord(ctx->tl[1], ctx->copy_stream);
+  } else if (p->n_stages > 1 && e == cudaSuccess) {
+    e = cudaEventRecord(ctx->stage_go, ctx->stream);  // the buffers exist (stream-ordered allocation) and the flags are cleared
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_go, 0);
-    for (int k = 0; k < p->n_stages && e == cudaSuccess; ++k) {
+  }
+  if (p->n_stages > 1 || p->n_slices > 1) {
+    const int ns = p->n_stages > 1 ? p->n_stages : p->n_slices;
+    for (int k = 0; k < ns && e == cudaSuccess; ++k) {
       const int64_t pb = h->cell_ptr[p->stage_cell[k]], pe = h->cell_ptr[p->stage_cell[k + 1]];
       if (pe > pb)
         e = dsnp ? cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream)
                  : cudaMemcpyAsync(p->d_delta8 + pb, h->pair_snp_delta8 + pb, (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
+      if (p->n_slices > 1) {  // pipelined run: the host queues the slice's decoding and scoring behind this event
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->slice_ev[k], ctx->copy_stream);
+        continue;
+      }
       // PSCL_FAULT=drop_stage_flag (fault-injection test): the last slice's flag never arrives, the kernel must time out
       const bool drop = k == p->n_stages - 1 && getenv("PSCL_FAULT") && !strcmp(getenv("PSCL_FAULT"), "drop_stage_flag");
       if (e == cudaSuccess && !drop) e = cudaMemcpyAsync(ctx->stage_flags + k, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream);
     }
   }
+  STEP("copy queue");
+  if (ctx->tl_on) cudaEventRecord(ctx->tl[2], ctx->copy_stream);
+  int hook_rc = PSCL_OK;
+  if (geno_hook && e == cudaSuccess) hook_rc = pscl_demux_set_geno(ctx, geno_hook, V);  // on the context's stream, under the copies
+  if (ctx->tl_on) cudaEventRecord(ctx->tl[3], ctx->stream);
+  if (deferred && e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, counts_marked ? ctx->ev_counts : ctx->ev_up, 0);
+  if (hook_rc != PSCL_OK) {
+    cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream);
+    const std::string msg = ctx->err;
+    cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_n2); cudaFree(d_nbig); cudaFree(d_nblk); cudaFree(d_rpk); cudaFree(d_rpal);
+    pscl_plp_free(ctx, p);
+    ctx->err = msg;
+    return hook_rc;
+  }
 
   // ---- 3. device-side decoding and checks ------------------------------------------------------------
-  if ((dsnp || dsnp8) && p->n_stages == 0 && e == cudaSuccess && C > 0 && P > 0) {
+  if ((dsnp || dsnp8) && p->n_stages == 0 && p->n_slices <= 1 && e == cudaSuccess && C > 0 && P > 0) {
+    if (deferred && counts_marked) { e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0); counts_marked = false; }
     if (dsnp) k_decode_snp<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta, 0, C, V, p->pair_snp, p->d_bad);
-    else k_decode_snp8<<<(unsigned)(((int64_t)C * 32 + 255) / 256), 256, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta8, p->d_gap_big, p->d_cell_gap_ptr,
+    else k_decode_snp8<<<(unsigned)C, PSCL_DEC8_NT, 0, ctx->stream>>>(p->cell_ptr, p->d_first, p->d_delta8, p->d_gap_big, p->d_cell_gap_ptr,
                                                                                        n_gap_local, C, V, p->pair_snp, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
@@ -569,6 +709,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int64_t)(P + 1), ctx->stream);
     if (e == cudaSuccess) { k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, P, N, p->d_bad); ctx->launches += 2; e = cudaGetLastError(); }
   } else if (!ptr32) {
+    if (deferred && counts_marked && e == cudaSuccess) { e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0); counts_marked = false; }
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
     if (e == cudaSuccess) {
       k_narrow_ptr<<<(unsigned)((P + 1 + 255) / 256), 256, 0, ctx->stream>>>((const int64_t*)p->scratch_h2d, p->pair_rd, P + 1, read_base);
@@ -580,7 +721,8 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess && P > 0 && ((!dsnp && !dsnp8) || !cnt8) && p->n_stages == 0) {
+  if (deferred && counts_marked && e == cudaSuccess) { e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0); counts_marked = false; }  // the scan is queued
+  if (e == cudaSuccess && P > 0 && ((!dsnp && !dsnp8) || !cnt8) && p->n_stages == 0 && p->n_slices <= 1) {
     k_check_pairs<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(p->pair_snp, p->pair_rd, P, V, N, (dsnp || dsnp8) ? 0 : 1, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
@@ -596,13 +738,16 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     e = cudaGetLastError();
   }
   STEP("decode / scan / checks (launch)");
+  if (ctx->tl_on) cudaEventRecord(ctx->tl[4], ctx->stream);
   int bad = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, p->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  // the host vectors above are pageable sources of async copies: drain before they go out of scope
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  STEP("drain (a copy or kernel of the upload failed on the device)");
+  if (!deferred) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, p->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    // the host vectors above are pageable sources of async copies: drain before they go out of scope
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    STEP("drain (a copy or kernel of the upload failed on the device)");
+  }
   cudaFree(d_al); cudaFree(d_q); cudaFree(d_cnt); cudaFree(d_scan_tmp); cudaFree(d_n2); cudaFree(d_nbig); cudaFree(d_nblk); cudaFree(d_rpk); cudaFree(d_rpal);
-  if (p->n_stages == 0) {
+  if (p->n_stages == 0 && p->n_slices <= 1) {
     cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_delta8); cudaFree(p->d_gap_big); cudaFree(p->d_cell_gap_ptr);
     p->d_delta = nullptr; p->d_first = nullptr; p->d_delta8 = nullptr; p->d_gap_big = nullptr; p->d_cell_gap_ptr = nullptr;
   }
@@ -615,6 +760,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     return pscl_fail(ctx, PSCL_EINVAL, "%s", pscl_bad_pileup_msg(bad));
   }
   if (e != cudaSuccess) {
+    if (deferred) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); }  // queued copies still read the caller's arrays
     pscl_plp_free(ctx, p);
     size_t mf = 0, mt = 0;
     cudaMemGetInfo(&mf, &mt);

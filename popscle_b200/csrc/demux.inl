@@ -1086,9 +1086,11 @@ static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
   return delta == 2 ? launch_default_v<NV, 2, false>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, false>(ctx, a) : launch_default_v<NV, 0, false>(ctx, a);
 }
 
-extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
-                                int32_t cell_begin, int32_t cell_end) {
-  if (!ctx) return PSCL_EINVAL;
+// out_origin: the cell whose record is dm_cells[0]; total_cells: how many records the output holds.  pscl_demux_score
+// passes (cell_begin, cell_end - cell_begin); the pipelined pscl_demux_run scores slice after slice into one array
+// (0, n_cells), each slice in its own item order (slice_order).
+static int demux_score_impl(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts, int32_t cell_begin, int32_t cell_end,
+                            int32_t out_origin, int32_t total_cells, bool slice_order, bool alpha_set = false) {
   PsclScope scope__(ctx);
   if (!plp || !opts || !opts->alphas) return pscl_fail(ctx, PSCL_EINVAL, "pscl_demux_score: NULL argument");
   if (!ctx->gp) return pscl_fail(ctx, PSCL_ESTATE, "pscl_demux_score: call pscl_demux_set_geno first");
@@ -1103,14 +1105,15 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
   double h_alpha[PSCL_MAX_ALPHA] = {0};
   for (int i = 0; i < na; ++i) h_alpha[i] = opts->alphas[i];
-  PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_alpha, h_alpha, sizeof(h_alpha), 0, cudaMemcpyHostToDevice, ctx->stream));
+  // (a run has queued this copy ahead of its bulk copies: behind them it would hold the first kernel back until they are through)
+  if (!alpha_set) PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_alpha, h_alpha, sizeof(h_alpha), 0, cudaMemcpyHostToDevice, ctx->stream));
 
-  const int ncell = cell_end - cell_begin;
+  const int ncell = total_cells;
   const size_t G = (size_t)nv * nv * na;
   int rc;
   if ((rc = pscl_reserve(ctx, (pscl_demux_cell**)&ctx->dm_cells, &ctx->dm_cells_cap, sizeof(pscl_demux_cell) * (size_t)ncell)) != PSCL_OK) return rc;
   if (ctx->keep_grid && (rc = pscl_reserve(ctx, &ctx->dm_grid, &ctx->dm_grid_cap, sizeof(double) * G * ncell)) != PSCL_OK) return rc;
-  ctx->dm_cell_begin = cell_begin; ctx->dm_cell_end = cell_end; ctx->dm_nalpha = na;
+  ctx->dm_cell_begin = out_origin; ctx->dm_cell_end = out_origin + total_cells; ctx->dm_nalpha = na;
 
   const bool use_default = !ctx->force_general && ctx->demux_kernel != 2 && ctx->demux_kernel != 4 && na == 2 && h_alpha[0] == 0.0 &&
                            h_alpha[1] == 0.5 && nv >= 2 && nv <= 8;
@@ -1157,7 +1160,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
       DemuxArgs a;
       a.pair_snp = plp->pair_snp; a.pair_rd = plp->pair_rd; a.rd_aq = plp->rd_aq;
       a.gp = ctx->gp; a.has_gp = ctx->has_gp; a.phred_err = ctx->phred_err; a.fold_tab = ctx->fold_tab;
-      a.item_order = (ib == 0 && ie == plp->n_items) ? plp->item_order : nullptr;
+      a.item_order = (ib == 0 && ie == plp->n_items) ? plp->item_order : (slice_order && c0 == cell_begin && c1 == cell_end) ? plp->item_order + ib : nullptr;
       a.item_pbeg = plp->item_pbeg; a.item_pend = plp->item_pend;
       a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
       a.item_base = ib; a.n_work = nwork; a.nv = nv; a.nalpha = na;
@@ -1253,7 +1256,7 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
     EpiArgs ea;
     ea.cell_ptr = plp->cell_ptr; ea.cell_item_ptr = plp->cell_item_ptr; ea.partial = ctx->dm_partial;
     ea.cells = (pscl_demux_cell*)ctx->dm_cells; ea.grid = ctx->keep_grid ? ctx->dm_grid : nullptr;
-    ea.cell_begin = c0; ea.out_base = c0 - cell_begin; ea.item_base = ib; ea.nv = nv; ea.nalpha = na;
+    ea.cell_begin = c0; ea.out_base = c0 - out_origin; ea.item_base = ib; ea.nv = nv; ea.nalpha = na;
     ea.doublet_prior = opts->doublet_prior;
     ea.inv_nv = ((1ull << 40) + nv - 1) / nv; ea.inv_na = ((1ull << 40) + na - 1) / na;
     if (G <= 1024) k_demux_epilogue_w<<<(unsigned)((c1 - c0 + 7) / 8), 256, 0, ctx->stream>>>(ea, c1 - c0);
@@ -1267,6 +1270,12 @@ extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_d
   ctx->dm_single_batch = single_batch;
   (void)main_ms_known;
   return PSCL_OK;
+}
+
+extern "C" int pscl_demux_score(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux_opts* opts,
+                                int32_t cell_begin, int32_t cell_end) {
+  if (!ctx) return PSCL_EINVAL;
+  return demux_score_impl(ctx, plp, opts, cell_begin, cell_end, cell_begin, cell_end - cell_begin, false);
 }
 
 extern "C" int pscl_demux_last_kernel_ms(pscl_ctx* ctx, float* ms_main, float* ms_total) {
@@ -1318,6 +1327,7 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
       opts->alphas[0] == 0.0 && opts->alphas[1] == 0.5 && geno->n_samples >= 2 && geno->n_samples <= 8 &&
       (host->pair_snp_delta16 || host->pair_snp_delta8) && host->cell_first_snp && host->n_pairs < ((int64_t)1 << 30)) {
     if (const char* sv = getenv("PSCL_STAGES")) stages = atoi(sv);
+    else if (const char* sl = getenv("PSCL_SLICES")) stages = atoi(sl);  // the pipelined form, whatever the size
     else if (host->n_pairs >= ((int64_t)1 << 22)) stages = (int)std::min<int64_t>(PSCL_MAX_STAGES, host->n_pairs / 1250000);  // ~2.5 MB of gaps per slice
     if (stages < 1) stages = 1;
     if (stages > 1) {
@@ -1329,26 +1339,95 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
       if (items * G * sizeof(double) > ctx->partial_budget_bytes) stages = 1;
     }
   }
+  static const bool timeline = getenv("PSCL_TIMELINE") != nullptr;
+  ctx->tl_on = timeline;
+  if (timeline) {
+    for (auto& ev : ctx->tl) if (!ev) cudaEventCreate(&ev);
+    cudaEventRecord(ctx->tl[0], ctx->stream);
+  }
+  const auto th0 = std::chrono::steady_clock::now();
+  // Pipelined run (the default for that shape): every copy of the call goes to the copy stream in one queue — small arrays,
+  // base-call counts, base-calls, then the SNP gaps in `slices` slices of whole cells, an event behind each — while the
+  // context's stream builds the genotype tables, scans the counts as soon as they have landed, unpacks the base-calls, and
+  // then takes slice after slice: decode its gaps, score its cells (the plain kernel), finish their records.  What is left
+  // after the last byte has crossed PCIe is one slice's worth of work.  PSCL_SLICES=n overrides the count (1 = off);
+  // PSCL_STAGES selects the older form (one launch whose warps wait on flag words) instead.
+  int slices = 1;
+  if (stages > 1 && !getenv("PSCL_STAGES")) {
+    slices = getenv("PSCL_SLICES") ? stages : std::min(6, stages);
+    stages = 1;
+  }
   const auto t0 = now();
-  int rc = pscl_demux_set_geno(ctx, geno, host->n_snps);  // genotypes first: every slice needs them
+  const bool deferred = ctx->h_bad != nullptr && ctx->copy_stream != nullptr;
+  if (!deferred) slices = 1;
+  int rc = pscl_demux_set_geno(ctx, geno, host->n_snps);  // genotypes first: their (small) copies lead the queue
   if (rc != PSCL_OK) return rc;
+  bool alpha_set = false;
+  if (opts->alphas && opts->n_alpha >= 2 && opts->n_alpha <= PSCL_MAX_ALPHA) {  // ... and the alpha grid (validated by the scoring call)
+    double h_alpha[PSCL_MAX_ALPHA] = {0};
+    for (int i = 0; i < opts->n_alpha; ++i) h_alpha[i] = opts->alphas[i];
+    PSCL_CUDA(ctx, cudaMemcpyToSymbolAsync(c_alpha, h_alpha, sizeof(h_alpha), 0, cudaMemcpyHostToDevice, ctx->stream));
+    alpha_set = true;
+  }
+  if (timeline) cudaEventRecord(ctx->tl[3], ctx->stream);
   const auto t1 = now();
   pscl_plp* plp = nullptr;
-  rc = plp_upload_impl(ctx, host, &plp, stages);
+  rc = plp_upload_impl(ctx, host, &plp, stages, 0, 0, deferred, nullptr, slices);  // validity flag read below, with the records
   if (rc != PSCL_OK) return rc;
   const auto t2 = now();
   bool keep = ctx->keep_grid;
   int bad = 0;
-  if (plp->n_stages > 1) {
-    rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);  // one launch; its warps wait on the slice flags
-    if (rc == PSCL_OK && cudaMemcpyAsync(&bad, plp->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-      rc = pscl_fail(ctx, PSCL_ECUDA, "staged run: flag read-back failed");
+  if (plp->n_slices > 1) {
+    // the gaps of slice k are decoded as soon as they have landed; the cells are scored in `groups` launches (a launch per
+    // slice would leave the persistent kernel's 1184 warps with two or three work items each)
+    int groups = 3;
+    if (const char* gv = getenv("PSCL_GROUPS")) groups = std::max(1, atoi(gv));
+    groups = std::min(groups, plp->n_slices);
+    int32_t g0 = 0;  // first cell not scored yet
+    for (int k = 0; k < plp->n_slices && rc == PSCL_OK; ++k) {
+      const int32_t c0 = plp->stage_cell[k], c1 = plp->stage_cell[k + 1];
+      cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->slice_ev[k], 0);
+      if (e == cudaSuccess && c1 > c0) {
+        const unsigned grid = (unsigned)(((int64_t)(c1 - c0) * 32 + 255) / 256);
+        if (plp->d_delta8) k_decode_snp8<<<(unsigned)(c1 - c0), PSCL_DEC8_NT, 0, ctx->stream>>>(plp->cell_ptr + c0, plp->d_first + c0, plp->d_delta8, plp->d_gap_big, plp->d_cell_gap_ptr + c0,
+                                                                        plp->n_gap_big, c1 - c0, plp->V, plp->pair_snp, plp->d_bad);
+        else k_decode_snp<<<grid, 256, 0, ctx->stream>>>(plp->cell_ptr + c0, plp->d_first + c0, plp->d_delta, 0, c1 - c0, plp->V, plp->pair_snp, plp->d_bad);
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
+      if (e != cudaSuccess) { rc = pscl_fail(ctx, PSCL_ECUDA, "pipelined run: slice %d: %s", k, cudaGetErrorString(e)); break; }
+      const bool group_end = (k + 1) * groups / plp->n_slices != k * groups / plp->n_slices || k + 1 == plp->n_slices;
+      if (group_end && c1 > g0) {
+        if (timeline && k + 1 == plp->n_slices) cudaEventRecord(ctx->tl[6], ctx->stream);
+        rc = demux_score_impl(ctx, plp, opts, g0, c1, 0, host->n_cells, true, alpha_set);
+        g0 = c1;
+      }
+    }
+    ctx->dm_single_batch = false;
+  } else if (plp->n_stages > 1) {
+    rc = demux_score_impl(ctx, plp, opts, 0, host->n_cells, 0, host->n_cells, false, alpha_set);  // one launch; its warps wait on the slice flags
   } else {
     if (llk_grid) ctx->keep_grid = true;
-    rc = pscl_demux_score(ctx, plp, opts, 0, host->n_cells);
+    rc = demux_score_impl(ctx, plp, opts, 0, host->n_cells, 0, host->n_cells, false, alpha_set);
   }
+  // the image's validity flag (malformed arrays, a slice that never arrived) comes back with the records: one drain per run
+  int* const bad_dst = ctx->h_bad ? ctx->h_bad : &bad;
+  if (rc == PSCL_OK && cudaMemcpyAsync(bad_dst, plp->d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = pscl_fail(ctx, PSCL_ECUDA, "run: flag read-back failed");
   const auto t3 = now();
+  const auto th1 = std::chrono::steady_clock::now();
   if (rc == PSCL_OK) rc = pscl_demux_fetch(ctx, out, llk_grid);
+  if (timeline && rc == PSCL_OK) {
+    cudaEventRecord(ctx->tl[5], ctx->stream);
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->copy_stream);
+    float v[8] = {0};
+    cudaEvent_t evs[8] = {ctx->tl[1], ctx->tl[2], ctx->tl[3], ctx->tl[4], ctx->ev1, ctx->ev2, ctx->tl[5], ctx->tl[6]};
+    for (int i = 0; i < 8; ++i) if (cudaEventElapsedTime(&v[i], ctx->tl[0], evs[i]) != cudaSuccess) { v[i] = -1.f; cudaGetLastError(); }
+    fprintf(stderr, "[timeline ms] arrays landed %.3f | gaps landed %.3f | geno tables %.3f | decoded %.3f | scored %.3f | epilogue %.3f | fetched %.3f | last group starts %.3f | host: enqueue %.3f, whole call %.3f\n",
+            v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], ms(th0, th1), ms(th0, std::chrono::steady_clock::now()));
+  }
+  else cudaStreamSynchronize(ctx->stream);  // the staging buffer and the caller's arrays are sources of queued copies
+  bad = *bad_dst;
   if (rc == PSCL_OK && bad == 4) rc = pscl_fail(ctx, PSCL_ECUDA, "staged run: a slice of pair_snp_delta16 never reached the device");
   else if (rc == PSCL_OK && bad) rc = pscl_fail(ctx, PSCL_EINVAL, "%s", pscl_bad_pileup_msg(bad));
   const auto t4 = now();

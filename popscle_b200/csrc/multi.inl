@@ -476,7 +476,7 @@ static int plp_filter_snps(pscl_ctx* ctx, const pscl_plp* full, int32_t v0, int3
   std::vector<int64_t> h_cp((size_t)C + 1);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_cp.data(), p->cell_ptr, sizeof(int64_t) * ((size_t)C + 1), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess) e = plp_make_items(ctx, p, h_cp.data());
+  if (e == cudaSuccess) e = plp_make_items(ctx, p, h_cp.data(), false);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(pos); cudaFree(rpos); cudaFree(tmp);
   if (e != cudaSuccess) {

@@ -33,9 +33,12 @@ class Synth:
 
 
 def make_pileup(C: int, nv: int, V: int, kbar: float, seed: int, cap_bq: int = 20, min_bq: int = 13,
-                doublet_frac: float = 0.1, cell_scale: float = 1.0, snp_seed: int | None = None) -> Synth:
+                doublet_frac: float = 0.1, cell_scale: float = 1.0, snp_seed: int | None = None,
+                cell_seed: int | None = None) -> Synth:
     """SURVEY.md §8(d) generator.  cap_bq/min_bq are applied the way the loader does
-    (sc_drop_seq.cpp:361-369), so `read_qual` is what add_read receives."""
+    (sc_drop_seq.cpp:361-369), so `read_qual` is what add_read receives.
+    cell_seed: independent cell-level draws against the SAME SNP-level truth (AF, donor genotypes): block `cell_seed` of a
+    larger problem's cells, so that a barcode-sharded run can generate each block where it is scored."""
     rng = np.random.Generator(np.random.PCG64(seed))
     # snp_seed: independent SNP-level draws (AF, genotypes) with the SAME cell-level truth, used to give
     # every rank of an SNP-sharded run its own SNP range of the same cells
@@ -44,6 +47,8 @@ def make_pileup(C: int, nv: int, V: int, kbar: float, seed: int, cap_bq: int = 2
     geno = rng_snp.binomial(2, np.broadcast_to(af, (nv, V))).astype(np.int8)
     if snp_seed is not None:
         rng.uniform(0.05, 0.5, 1)  # keep the cell-level stream independent of V
+    if cell_seed is not None:
+        rng = np.random.Generator(np.random.PCG64([seed, 7919, cell_seed]))
     is_dbl = rng.random(C) < doublet_frac
     d1 = rng.integers(0, nv, C).astype(np.int32)
     d2 = ((d1 + rng.integers(1, max(nv, 2), C)) % nv).astype(np.int32)

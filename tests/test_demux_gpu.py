@@ -387,6 +387,42 @@ def test_degenerate_pileups(ctx, kernel):
     assert_close(out["dbl_best_llk"], ref["dbl_best_llk"], "no genotypes: doublet LLK")
 
 
+@pytest.mark.parametrize("slices,groups", [(2, 1), (3, 3), (6, 2), (7, 3), (40, 5)])
+def test_pipelined_run_is_bit_identical(ctx, slices, groups):
+    """The default form of pscl_demux_run at size: every copy on the copy stream (counts, base-calls, then the SNP gaps in
+    slices of whole cells with an event behind each), gaps decoded slice by slice, cells scored in groups of slices.  Cells
+    are independent (cmd_cram_demuxlet.cpp:636) and a cell's pairs are summed in the same order: the records must be the
+    bytes of the one-shot run, for hard calls (dictionary kernel) and soft posteriors (row gather), whatever the cuts;
+    malformed gaps are still an error, and the context survives."""
+    from popscle_b200 import PsclError, RawGeno
+    s = synth.make_pileup(C=700, nv=8, V=6000, kbar=900, seed=1234 + slices)
+    hard = RawGeno(gt8=np.ascontiguousarray(s.geno.T.astype(np.uint8)), err=0.1)
+    rng = np.random.default_rng(slices)
+    soft = rng.dirichlet([0.3, 0.3, 0.3], size=(6000, 8))
+    for gp in (hard, soft):
+        for compact in (3, 4):
+            ref = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=compact)
+            os.environ["PSCL_SLICES"], os.environ["PSCL_GROUPS"] = str(slices), str(groups)
+            try:
+                got = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=compact)
+            finally:
+                del os.environ["PSCL_SLICES"], os.environ["PSCL_GROUPS"]
+            assert got.tobytes() == ref.tobytes(), (type(gp).__name__, compact)
+    bad = synth.make_pileup(C=60, nv=3, V=400, kbar=90, seed=1)
+    first, d8, gbig, cbp, n2, nbig, nbp = bad.plp.compact4()
+    os.environ["PSCL_SLICES"] = "3"
+    try:
+        d8[bad.plp.cell_ptr[45] + 1] = 254  # a gap that walks the SNP id past n_snps
+        d8[bad.plp.cell_ptr[45] + 2] = 254
+        with pytest.raises(PsclError):
+            ctx.demux_run(bad.plp, synth.gt_to_gp(bad.geno), None, DEFAULT, compact=4)
+        ok = synth.make_pileup(C=60, nv=3, V=400, kbar=90, seed=2)
+        assert ctx.demux_run(ok.plp, synth.gt_to_gp(ok.geno), None, DEFAULT, compact=4).tobytes() == \
+            ctx.demux_run(ok.plp, synth.gt_to_gp(ok.geno), None, DEFAULT).tobytes()
+    finally:
+        del os.environ["PSCL_SLICES"]
+
+
 def test_staged_run_falls_back_when_the_partial_grids_do_not_fit(ctx):
     """a staged image can only be scored in one batch; with a small scratch budget pscl_demux_run must take
     the plain upload instead of failing with PSCL_ESTATE."""
