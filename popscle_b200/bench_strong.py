@@ -21,6 +21,16 @@ FREEMUX16_CELLS = 12000
 FREEMUX16_ITERS = 5
 
 
+def _ncu_traffic(key):
+    import json
+    import os
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 def _max_over_ranks(x, world, dev):
     import torch
     import torch.distributed as dist
@@ -174,10 +184,10 @@ def freemux16(ctx, rank, world, dev, cells=FREEMUX16_CELLS, iters=FREEMUX16_ITER
             "ms_per_iter": it_ms, "estep_ms": es_ms, "allreduce_ms": ar_ms, "classify_mstep_ms": cm_ms,
             "estep_balance": (es_sum / world) / es_ms if es_ms > 0 else None,
             "allreduce_bytes": int(C * npairs * 8), "collective": "NCCL all-reduce (torch.distributed) of C x npairs FP64 per EM iteration" if world > 1 else None,
-            "seed_ms": seed_ms, "seed_wall_ms_incl_broadcast": seed_wall_ms, "setup_ms": setup_max,
+            "seed_ms": seed_ms, "seed_call_ms": getattr(step, "last_seed_ms", None), "seed_wall_ms_incl_broadcast": seed_wall_ms, "setup_ms": setup_max,
             "base_calls_per_s": plp.n_reads / (it_ms * 1e-3), "singlets": int(sng.sum()), "singlet_cluster_purity": purity,
             "n_changed_last": int(res.n_changed) if res is not None else None,
-            "limited_by": "k_fmx_estep (the nS = 16 row tiles) inside an iteration; k_fmx_seed (one sequential chain over the cells, rank 0 only) for the whole run",
+            "limited_by": "k_fmx_estep (the nS = 16 row tiles) inside an iteration; for the whole run rank 0's set-up over the whole pileup (upload, SNP-major view, stage 1; seed_ms) of which the speculative-batch seeding itself is seed_call_ms",
             "timing": "CUDA events per phase on each rank, mean over iterations 2.., max over ranks", "generate_s": gen_s}
 
 
@@ -232,5 +242,6 @@ def freemux_cfg3(ctx, plp, truth, dev, iters=10):
             "seed_over_em": seed_ms / em_ms if em_ms > 0 else None,
             "base_calls_per_s_em": plp.n_reads * iters / (em_ms * 1e-3),
             "estep_algorithmic_gbs": None if not es else abytes / (float(np.mean(es)) * 1e-3) / 1e9,
+            "estep_dram_traffic_bytes": _ncu_traffic("k_fmx_estep"),  # dram read + write of one E-step from the committed ncu capture
             "e2e_ms": 1e3 * e2e_s, "e2e_base_calls_per_s": plp.n_reads * iters / e2e_s, "gpu_launches": int(launches),
             "singlets": int(sng.sum()), "singlet_cluster_purity": float(tab.max(axis=1).sum() / max(tab.sum(), 1))}

@@ -406,14 +406,14 @@ static int ply_build_stream(pscl_ctx* ctx, pscl_plp* p) {
   alloc((void**)&scan, sizeof(unsigned long long) * (P + 2));
   alloc((void**)&p->ply_rec, sizeof(uint2) * P);
   alloc((void**)&p->ply_rng, sizeof(uint4) * NI);
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, key, scan, (int)(P + 1), ctx->stream);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, key, scan, (int64_t)(P + 1), ctx->stream);
   alloc(&tmp, tmp_bytes);
   if (e == cudaSuccess) e = cudaMemsetAsync(key, 0, sizeof(unsigned long long) * (P + 1), ctx->stream);
   if (e == cudaSuccess && P > 0) {
     k_dmx_classify<<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(p->pair_snp, p->pair_rd, p->rd_aq, P, rec_tmp, key);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, key, scan, (int)(P + 1), ctx->stream);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, key, scan, (int64_t)(P + 1), ctx->stream);
   if (e == cudaSuccess && NI > 0) {
     k_ply_scatter<<<(unsigned)(((int64_t)NI * 32 + 255) / 256), 256, 0, ctx->stream>>>(
         p->cell_ptr, p->item_cell, p->item_pbeg, p->item_pend, NI, rec_tmp, scan, p->ply_rec, p->ply_rng);

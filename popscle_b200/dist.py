@@ -143,8 +143,12 @@ class CudaStep:
             self.ctx.fmx_init(d, opts)
             st, cl = self.new_f64(4 * plp.n_cells), self.new_i32(plp.n_cells)
             self.ctx.fmx_stage1(st.data_ptr())
+            self.ctx.sync()
+            import time
+            t0 = time.perf_counter()
             self.ctx.fmx_seed(st.data_ptr(), None, cl.data_ptr())
             self.ctx.sync()
+            self.last_seed_ms = 1e3 * (time.perf_counter() - t0)  # the seeding call alone (the rest is upload, views, stage 1)
             return st.cpu().numpy(), cl.cpu().numpy()
         finally:
             d.free()
