@@ -1351,6 +1351,170 @@ __global__ void __launch_bounds__(THREADS) k_fmx_estep(EArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// E-step at nS = 16, one pass: a team of four warps per work item, one warp per row tile
+// ------------------------------------------------------------------------------------------------
+// The four row tiles [0,8) [8,11) [11,14) [14,16) used to be four launches, each gathering (the head of) the posterior row of
+// every pair again: 1.2 KB per pair, and at 500 k SNPs the 192 MB table does not fit L2, so that was DRAM traffic (48.6 GB
+// per iteration at 4.8e7 pairs, profiles/r2j_k_fmx_estep16_tile*_ncu.txt).  Here the four warps of a CTA take the SAME 32
+// pairs per step: the 32 rows (384 B each) are gathered once into shared memory, 8 rows per warp with cp.async, double
+// buffered; every warp then runs its own tile's products out of those rows (warp-uniform code, the tile is chosen by the
+// warp's index) — the same arithmetic on the same doubles in the same order as the tile kernels, so the same bits.
+template <int J0, int J1>
+__device__ __forceinline__ void estep16_tile(const double* __restrict__ row, const double (&gl)[9], double (&acc)[40]) {
+  constexpr int NR = J1 - J0;
+  constexpr int EBASE = J0 * (J0 + 1) / 2;
+  double uj[NR][3];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { uj[r][0] = row[(J0 + r) * 3]; uj[r][1] = row[(J0 + r) * 3 + 1]; uj[r][2] = row[(J0 + r) * 3 + 2]; }
+#pragma unroll
+  for (int k = 0; k < J1; ++k) {
+    double k0, k1, k2;
+    if (k >= J0) { k0 = uj[k - J0 < 0 ? 0 : k - J0][0]; k1 = uj[k - J0 < 0 ? 0 : k - J0][1]; k2 = uj[k - J0 < 0 ? 0 : k - J0][2]; }
+    else { k0 = row[k * 3]; k1 = row[k * 3 + 1]; k2 = row[k * 3 + 2]; }
+    const double v0 = gl[0] * k0 + gl[1] * k1 + gl[2] * k2;
+    const double v1 = gl[3] * k0 + gl[4] * k1 + gl[5] * k2;
+    const double v2 = gl[6] * k0 + gl[7] * k1 + gl[8] * k2;
+#pragma unroll
+    for (int j = (k + 1 > J0 ? k + 1 : J0); j < J1; ++j)
+      acc[j * (j + 1) / 2 + k - EBASE] *= (uj[j - J0][0] * v0 + uj[j - J0][1] * v1 + uj[j - J0][2] * v2);
+    if (k >= J0) acc[k * (k + 1) / 2 + k - EBASE] *= (gl[0] * k0 + gl[4] * k1 + gl[8] * k2);
+  }
+}
+template <int J0, int J1>
+__device__ __forceinline__ void estep16_renorm(double (&acc)[40], int* s_exp, int tid) {
+  constexpr int NA = J1 * (J1 + 1) / 2 - J0 * (J0 + 1) / 2;
+#pragma unroll
+  for (int e = 0; e < NA; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * 128 + tid] += ex; }
+}
+// product across the warp of every accumulator of the tile (transpose-reduction from registers, as k_demux_default's item
+// epilogue), one log per accumulator, stored by the lane that ends up holding it
+template <int J0, int J1>
+__device__ __forceinline__ void estep16_store(const double (&acc)[40], const int* s_exp, int tid, double* __restrict__ out, int npairs) {
+  constexpr int NA = J1 * (J1 + 1) / 2 - J0 * (J0 + 1) / 2;
+  constexpr int EBASE = J0 * (J0 + 1) / 2;
+  static_assert(NA <= 40, "tile too large for the two epilogue groups");
+  const int lane = tid & 31;
+  double m1[32]; int x1[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    if (e < NA) { m1[e] = acc[e]; x1[e] = s_exp[e * 128 + tid]; pscl_renorm(m1[e], x1[e]); } else { m1[e] = 1.0; x1[e] = 0; }
+  }
+  pscl_transpose_prod<32>(m1, x1, lane);
+  pscl_renorm(m1[0], x1[0]);
+  if (lane < NA && lane + EBASE < npairs) out[lane + EBASE] = pscl_prod_log(m1[0], x1[0]);
+  if (NA > 32) {
+    double m2[8]; int x2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (32 + e < NA) { m2[e] = acc[32 + e]; x2[e] = s_exp[(32 + e) * 128 + tid]; pscl_renorm(m2[e], x2[e]); } else { m2[e] = 1.0; x2[e] = 0; }
+    }
+    pscl_transpose_prod<8>(m2, x2, lane);
+    pscl_renorm(m2[0], x2[0]);
+    const int e = 32 + (lane >> 2);  // element 32 + i sits in lane 4 * i
+    if ((lane & 3) == 0 && e < NA && e + EBASE < npairs) out[e + EBASE] = pscl_prod_log(m2[0], x2[0]);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2) k_fmx_estep16_team(EArgs a) {
+  constexpr int US = 48, SD = 50, NCH = 24;  // posterior row: 16 clusters x 3 doubles = 24 pieces of 16 bytes; odd 16-byte stride
+  constexpr int NBUF = 3;                    // row buffers: the gathers run two steps ahead of the products
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_u = reinterpret_cast<double*>(smem_raw);                    // [NBUF][32][SD] rows of a step's 32 pairs
+  int* s_exp = reinterpret_cast<int*>(s_u + (size_t)NBUF * 32 * SD);    // [40][128]
+  int* s_snp = s_exp + 40 * 128;                                        // [2][1024] SNP ids of 32 steps, two chunks
+  __shared__ int s_item;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int w = s_item;
+    __syncthreads();
+    if (w >= a.n_items) break;
+    const int item = a.item_order[w];
+    const int64_t pb = a.item_pbeg[item], pe = a.item_pend[item];
+    const int niter = (int)((pe - pb + 31) >> 5);
+    double acc[40];
+#pragma unroll
+    for (int e = 0; e < 40; ++e) { acc[e] = 1.0; s_exp[e * 128 + tid] = 0; }
+    // SNP ids: 32 steps (1024 pairs) per chunk, loaded by the whole team a chunk ahead (-1 = past the item's end)
+    auto load_chunk = [&](int c) {
+      int* dst = s_snp + (c & 1) * 1024;
+      const int64_t base = pb + (int64_t)c * 1024;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t p = base + tid + 128 * q;
+        dst[tid + 128 * q] = p < pe ? a.pair_snp[p] : -1;
+      }
+    };
+    auto snp_at = [&](int step, int ln) { return s_snp[((step >> 5) & 1) * 1024 + (step & 31) * 32 + ln]; };
+    auto issue_rows = [&](int step, int buf) {  // this warp's 8 rows of the step's 32
+      if (step < niter) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = warp * 8 + i;
+          const int snp_r = snp_at(step, r);
+          if (snp_r >= 0 && lane < NCH)
+            __pipeline_memcpy_async(reinterpret_cast<char*>(s_u + ((size_t)buf * 32 + r) * SD) + lane * 16,
+                                    reinterpret_cast<const char*>(a.u_tab + (size_t)snp_r * US) + lane * 16, 16);
+        }
+      }
+      __pipeline_commit();
+    };
+    double glB[9]; bool okB = false;
+    auto load_gl = [&](int step) {
+      const int64_t p = pb + ((int64_t)step << 5) + lane;
+      okB = step < niter && p < pe;
+      if (okB) {
+#pragma unroll
+        for (int g = 0; g < 9; ++g) glB[g] = a.gl_soa[(size_t)g * a.P + p];
+      }
+    };
+    load_chunk(0);
+    __syncthreads();
+    issue_rows(0, 0);
+    issue_rows(1, 1);
+    load_gl(0);
+    for (int it = 0; it < niter; ++it) {
+      const bool ok = okB;
+      double gl[9];
+#pragma unroll
+      for (int g = 0; g < 9; ++g) gl[g] = glB[g];
+      __syncthreads();  // every warp is done with the buffer of step it-1 (refilled now) and with the SNP chunk before this one
+      if ((it & 31) == 0) load_chunk((it >> 5) + 1);
+      issue_rows(it + 2, (it + 2) % NBUF);
+      load_gl(it + 1);
+      __pipeline_wait_prior(2);
+      __syncthreads();  // ... and every warp's share of this step's rows has landed (and the new SNP chunk is visible)
+      if (ok) {
+        const double* row = s_u + ((size_t)(it % NBUF) * 32 + lane) * SD;
+        switch (warp) {
+          case 0: estep16_tile<0, 8>(row, gl, acc); break;
+          case 1: estep16_tile<8, 11>(row, gl, acc); break;
+          case 2: estep16_tile<11, 14>(row, gl, acc); break;
+          default: estep16_tile<14, 16>(row, gl, acc); break;
+        }
+      }
+      if ((it & 31) == 31) {  // every factor is >= ~1e-6 (clamped GLs), so 32 of them stay far above underflow
+        switch (warp) {
+          case 0: estep16_renorm<0, 8>(acc, s_exp, tid); break;
+          case 1: estep16_renorm<8, 11>(acc, s_exp, tid); break;
+          case 2: estep16_renorm<11, 14>(acc, s_exp, tid); break;
+          default: estep16_renorm<14, 16>(acc, s_exp, tid); break;
+        }
+      }
+    }
+    __pipeline_wait_prior(0);
+    double* out = a.item_llk + (size_t)item * a.npairs;
+    switch (warp) {
+      case 0: estep16_store<0, 8>(acc, s_exp, tid, out, a.npairs); break;
+      case 1: estep16_store<8, 11>(acc, s_exp, tid, out, a.npairs); break;
+      case 2: estep16_store<11, 14>(acc, s_exp, tid, out, a.npairs); break;
+      default: estep16_store<14, 16>(acc, s_exp, tid, out, a.npairs); break;
+    }
+  }
+}
+
 // llk[c][pair] = sum over the cell's items, in item order (a cell without pairs keeps 0, :385 init)
 __global__ void k_fmx_llk_reduce(const int32_t* __restrict__ cell_item_ptr, const double* __restrict__ item_llk,
                                  int32_t C, int32_t npairs, double* __restrict__ llk) {
@@ -1987,6 +2151,22 @@ static int fmx_estep_launch(pscl_ctx* ctx, pscl_fmx_state* s, const EArgs& a) {
   return PSCL_OK;
 }
 
+static int fmx_estep16_team_launch(pscl_ctx* ctx, pscl_fmx_state* s, const EArgs& a) {
+  const size_t smem = sizeof(double) * 3 * 32 * 50 + sizeof(int) * 40 * 128 + sizeof(int) * 2 * 1024;
+  auto kern = k_fmx_estep16_team;
+  PSCL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  PSCL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) return pscl_fail(ctx, PSCL_EINVAL, "E-step team kernel does not fit one SM (smem %zu B)", smem);
+  int grid = ctx->sm_count * per_sm;
+  if (grid > a.n_items) grid = a.n_items;
+  PSCL_CUDA(ctx, cudaMemsetAsync(s->work_counter, 0, sizeof(int), ctx->stream));
+  kern<<<grid, 128, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  PSCL_CUDA(ctx, cudaGetLastError());
+  return PSCL_OK;
+}
+
 extern "C" int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev) {
   FMX_STATE(ctx, s);
   if (!s->begun) return pscl_fail(ctx, PSCL_ESTATE, "pscl_fmx_estep before pscl_fmx_seed / pscl_fmx_mstep");
@@ -2016,7 +2196,9 @@ extern "C" int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev) {
       case 6: rc = fmx_estep_launch<6, 0, 6, 128>(ctx, s, a); break;
       case 7: rc = fmx_estep_launch<7, 0, 7, 128>(ctx, s, a); break;
       case 8: rc = fmx_estep_launch<8, 0, 8, 128>(ctx, s, a); break;
-      case 16:  // configs[4]'s cluster count: compile-time tiles (each gathers only the row head it needs)
+      case 16:  // configs[4]'s cluster count: one pass, a team of four warps per work item (PSCL_ESTEP_TILES=1: the four
+                // compile-time tile launches it replaces, kept as its cross-check)
+        if (!getenv("PSCL_ESTEP_TILES")) { rc = fmx_estep16_team_launch(ctx, s, a); break; }
         rc = fmx_estep_launch<16, 0, 8, 64>(ctx, s, a);
         if (rc == PSCL_OK) rc = fmx_estep_launch<16, 8, 11, 64>(ctx, s, a);
         if (rc == PSCL_OK) rc = fmx_estep_launch<16, 11, 14, 64>(ctx, s, a);

@@ -50,6 +50,27 @@ def test_many_clusters(ctx, nS):
     _check(*_both(ctx, s.plp, nS, max_iter=3), tied=0.05)
 
 
+def test_team_estep_at_16_clusters_gives_the_tile_kernels_bits(ctx):
+    """nS = 16 (configs[4]'s cluster count): the one-pass team kernel (four warps per work item, one per row tile, the posterior
+    rows gathered once) against the four tile launches it replaces (PSCL_ESTEP_TILES=1): the same per-pair products; only the
+    order in which a work item's 32 lane products are multiplied differs (transpose-reduction instead of butterflies), so every
+    id and type is the same and the LLKs agree to rounding; cells of several work items and of a few pairs included."""
+    s = synth.make_pileup(C=400, nv=16, V=9000, kbar=1500, seed=616)
+    o = ctx.fmx_opts(16, early_stop=False, max_iter=4)
+    team = ctx.fmx_run(s.plp, o)[0]
+    os.environ["PSCL_ESTEP_TILES"] = "1"
+    try:
+        tiles = ctx.fmx_run(s.plp, o)[0]
+    finally:
+        del os.environ["PSCL_ESTEP_TILES"]
+    for f in team.dtype.names:
+        if team.dtype[f].kind == "f":
+            assert_close(team[f], tiles[f], f, rtol=1e-12)
+        else:
+            assert np.array_equal(team[f], tiles[f]), f
+    assert (np.bincount(team["clust"][team["clust"] >= 0], minlength=16) > 0).all()
+
+
 def test_init_cluster_and_forced_iterations(ctx):
     """--init-cluster path (:198-216) with unassigned cells; no early stop (benchmark mode)."""
     s = synth.make_pileup(C=300, nv=4, V=2000, kbar=250, seed=42)
