@@ -145,12 +145,29 @@ struct pscl_ctx {
 // (many) existing call sites; PsclScope publishes the current context's stream to them.
 static thread_local cudaStream_t t_pscl_stream = nullptr;
 static thread_local pscl_ctx* t_pscl_ctx = nullptr;
+static thread_local double t_pscl_alloc_ms = 0.0;  // PSCL_TIMELINE: host time inside the allocator calls of the current run
+static thread_local int t_pscl_alloc_n = 0;
 static inline cudaError_t pscl_pool_alloc(void** p, size_t n) {
   // fault injection (pscl_debug_fail_alloc): the n-th allocation from now fails the way an exhausted device does
   if (t_pscl_ctx && t_pscl_ctx->fail_alloc_in > 0 && --t_pscl_ctx->fail_alloc_in == 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  if (t_pscl_ctx && t_pscl_ctx->tl_on) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaMallocAsync(p, n ? n : 16, t_pscl_stream);
+    t_pscl_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++t_pscl_alloc_n;
+    return e;
+  }
   return cudaMallocAsync(p, n ? n : 16, t_pscl_stream);
 }
-static inline cudaError_t pscl_pool_free(void* p) { return p ? cudaFreeAsync(p, t_pscl_stream) : cudaSuccess; }
+static inline cudaError_t pscl_pool_free(void* p) {
+  if (!p) return cudaSuccess;
+  if (t_pscl_ctx && t_pscl_ctx->tl_on) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaFreeAsync(p, t_pscl_stream);
+    t_pscl_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++t_pscl_alloc_n;
+    return e;
+  }
+  return cudaFreeAsync(p, t_pscl_stream);
+}
 #define cudaMalloc(p, n) pscl_pool_alloc((void**)(p), (n))
 #define cudaFree(p) pscl_pool_free((void*)(p))
 struct PsclScope {

@@ -1344,6 +1344,7 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
   if (timeline) {
     for (auto& ev : ctx->tl) if (!ev) cudaEventCreate(&ev);
     cudaEventRecord(ctx->tl[0], ctx->stream);
+    t_pscl_alloc_ms = 0.0; t_pscl_alloc_n = 0;
   }
   const auto th0 = std::chrono::steady_clock::now();
   // Pipelined run (the default for that shape): every copy of the call goes to the copy stream in one queue — small arrays,
@@ -1423,8 +1424,8 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
     float v[8] = {0};
     cudaEvent_t evs[8] = {ctx->tl[1], ctx->tl[2], ctx->tl[3], ctx->tl[4], ctx->ev1, ctx->ev2, ctx->tl[5], ctx->tl[6]};
     for (int i = 0; i < 8; ++i) if (cudaEventElapsedTime(&v[i], ctx->tl[0], evs[i]) != cudaSuccess) { v[i] = -1.f; cudaGetLastError(); }
-    fprintf(stderr, "[timeline ms] arrays landed %.3f | gaps landed %.3f | geno tables %.3f | decoded %.3f | scored %.3f | epilogue %.3f | fetched %.3f | last group starts %.3f | host: enqueue %.3f, whole call %.3f\n",
-            v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], ms(th0, th1), ms(th0, std::chrono::steady_clock::now()));
+    fprintf(stderr, "[timeline ms] arrays landed %.3f | gaps landed %.3f | geno tables %.3f | decoded %.3f | scored %.3f | epilogue %.3f | fetched %.3f | last group starts %.3f | host: %d allocator calls %.3f, enqueue %.3f, whole call %.3f\n",
+            v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], t_pscl_alloc_n, t_pscl_alloc_ms, ms(th0, th1), ms(th0, std::chrono::steady_clock::now()));
   }
   else cudaStreamSynchronize(ctx->stream);  // the staging buffer and the caller's arrays are sources of queued copies
   bad = *bad_dst;

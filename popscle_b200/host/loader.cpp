@@ -25,31 +25,176 @@ std::vector<std::string> read_first_column(const std::string& path) {
 
 namespace {
 
-// ---- text VCF cursor: records that pass the demuxlet site filters, with float posteriors ----------
-struct VcfCursor {
-  LineReader rd;
-  const LoadOptions& o;
-  std::map<std::string, int> contig;  // header order, then first appearance
+std::vector<char> slurp_text(const std::string& path, int threads, bool* was_bgzf);
+
+// ---- text VCF: records that pass the demuxlet site filters, with float posteriors ------------------------------------------
+// The file is inflated whole (BGZF blocks on several threads: what bgzip / bcftools write), its header read, and the data
+// lines cut into line-aligned pieces that are parsed in parallel (GT decoding, the site filters, GT / GP / PL to posteriors
+// are all per record).  The cursor then hands the records out in file order; a record's error (or a contig the header does
+// not list) is kept with it and only raised / numbered when the merge-join with the VAR table reaches it, as the reference's
+// record-at-a-time reader would (bcf_filtered_reader.cpp:505-581, :748-762).
+struct VcfHeader {
+  std::map<std::string, int> contig;  // header order
   std::vector<std::string> samples;   // selected sample names, in reference order
   std::vector<int> cols;              // their VCF columns
+};
+struct VcfRec {
+  int rid = -1;        // >= 0: contig id; < 0: -1 - index into the piece's `names` (not in the header)
+  int pos = 0;
+  char ref = 0, alt = 0;
+  uint8_t state = 0;   // 0 record, 1 dropped by a site filter, 2 error (message in text)
+  size_t gps_off = 0;  // into the piece's gps
+  std::string text;    // INFO column (kept when --geno-error-coeff reads it) or the error message
+};
+struct VcfPiece {
+  std::vector<VcfRec> recs;
+  std::vector<float> gps;            // nv * 3 floats per record of state 0
+  std::vector<std::string> names;    // contigs the header does not list, in order of first appearance in the piece
+};
+struct VcfLineParser {  // one per thread: the scratch vectors keep their capacity from record to record
+  const LoadOptions& o;
+  const VcfHeader& H;
+  const std::string& path;
+  std::vector<std::string> c, alleles, fmt, parts, vals;
+  std::vector<int> g1, g2, acs;
+  std::vector<std::vector<std::string>> smp;
+  std::vector<float> gps;
+  VcfLineParser(const LoadOptions& opt, const VcfHeader& h, const std::string& p) : o(opt), H(h), path(p) {}
+
+  // 0 = record (fields in r, posteriors in this->gps), 1 = dropped by a site filter; throws host_error on a malformed line
+  int parse(const std::string& line, VcfRec& r) {
+    const std::vector<int>& cols = H.cols;
+    const int nv = (int)cols.size();
+    split_char(line, '\t', c);
+    if (c.size() < 10) throw host_error("VCF data line with fewer than 10 columns in " + path);
+    alleles.clear();
+    alleles.push_back(c[3]);
+    if (c[4] != ".") { split_char(c[4], ',', parts); alleles.insert(alleles.end(), parts.begin(), parts.end()); }
+    const int nal = (int)alleles.size();
+    if (nal > o.max_alleles) return 1;
+    split_char(c[8], ':', fmt);
+    int gi = -1, fi = -1;
+    for (size_t i = 0; i < fmt.size(); ++i) {
+      if (fmt[i] == "GT") gi = (int)i;
+      if (fmt[i] == o.field) fi = (int)i;
+    }
+    // GT is parsed (and required) only when something reads it: the site filters minMAC / minCallRate
+    // (require_GT, bcf_filter_arg.h:110-113) or --field GT itself
+    const bool need_gt = o.min_mac > 0 || o.min_callrate > 0 || o.field == "GT";
+    if (gi < 0 && need_gt) throw host_error("Cannot find the field GT from the VCF file at position " + c[0] + ":" + c[1]);
+    g1.assign(nv, -1); g2.assign(nv, -1); acs.assign(nal, 0);  // members: no allocation per record
+    int an = 0;
+    if ((int)smp.size() != nv) smp.resize(nv);
+    for (int i = 0; i < nv; ++i) {
+      split_char(c[9 + cols[i]], ':', smp[i]);
+      if (gi < 0) continue;
+      const std::string& gt = gi < (int)smp[i].size() ? smp[i][gi] : std::string(".");
+      size_t sep = gt.find_first_of("/|");
+      std::string a = gt.substr(0, sep), b = sep == std::string::npos ? std::string(".") : gt.substr(sep + 1);
+      g1[i] = (a == "." || a.empty()) ? -1 : atoi(a.c_str());
+      g2[i] = (b == "." || b.empty()) ? -1 : atoi(b.c_str());
+      if (g1[i] >= nal || g2[i] >= nal)  // an allele number the record does not define ("0/3" at a biallelic site)
+        throw host_error("GT " + gt + " names an allele beyond the ALT list at position " + c[0] + ":" + c[1]);
+      if (g1[i] >= 0) { ++an; ++acs[g1[i]]; }
+      if (g2[i] >= 0) { ++an; ++acs[g2[i]]; }
+    }
+    if (need_gt) {
+      if (nv > 0 && o.min_callrate > (double)an / (2.0 * nv)) return 1;
+      const int ac = an - acs[0];
+      if (ac < o.min_mac || an - ac < o.min_mac) return 1;
+    }
+    // ---- posteriors with gt_error = 0 (load_from_plp passes 0, sc_drop_seq.cpp:113,285) ----
+    const int ngen = nal * (nal + 1) / 2;
+    gps.assign((size_t)nv * ngen, 0.f);
+    if (o.field == "GT") {  // :379-412
+      for (int i = 0; i < nv; ++i) {
+        if (g1[i] < 0 || g2[i] < 0) {
+          int l = 0;
+          for (int j = 0; j < nal; ++j)
+            for (int k = 0; k <= j; ++k, ++l)
+              gps[(size_t)i * ngen + l] = (float)((j == k ? 1.0 : 2.0) * (acs[j] + 1.0 / nal) / (an + 1.0) * (acs[k] + 1.0 / nal) / (an + 1.0));
+        } else {
+          const int a = std::max(g1[i], g2[i]), b = std::min(g1[i], g2[i]);
+          gps[(size_t)i * ngen + a * (a + 1) / 2 + b] = 1.0f;
+        }
+      }
+    } else if (o.field == "PL") {  // :250-327, ploidy 2
+      if (fi < 0) throw host_error("Cannot parse posterior probability at " + c[0] + ":" + c[1]);
+      std::vector<double> pls((size_t)nv * ngen), af(nal, 1.0 / nal), gp(ngen), post((size_t)nv * ngen);
+      for (int i = 0; i < nv; ++i) {
+        split_char(fi < (int)smp[i].size() ? smp[i][fi] : std::string("."), ',', vals);
+        for (int l = 0; l < ngen; ++l) pls[(size_t)i * ngen + l] = l < (int)vals.size() ? atoi(vals[l].c_str()) : 0;
+      }
+      for (int iter = 0; iter < 10; ++iter) {
+        std::vector<double> nw(nal, 0.0);
+        for (int i = 0; i < nv; ++i) {
+          double sum = 0;
+          int l = 0;
+          for (int j = 0; j < nal; ++j)
+            for (int k = 0; k <= j; ++k, ++l) sum += (gp[l] = (j == k ? 1 : 2) * af[j] * af[k] * std::pow(0.1, pls[(size_t)i * ngen + l] / 10.0));
+          l = 0;
+          for (int j = 0; j < nal; ++j)
+            for (int k = 0; k <= j; ++k, ++l) { gp[l] /= sum; nw[j] += gp[l]; nw[k] += gp[l]; post[(size_t)i * ngen + l] = gp[l]; }
+        }
+        for (int j = 0; j < nal; ++j) af[j] = nw[j] / (2.0 * nv);
+      }
+      for (size_t i = 0; i < post.size(); ++i) gps[i] = (float)post[i];
+    } else {  // GP-like float field, :434-458 with gt_error = 0
+      if (fi < 0) throw host_error("Cannot parse posterior probability at " + c[0] + ":" + c[1]);
+      for (int i = 0; i < nv; ++i) {
+        split_char(fi < (int)smp[i].size() ? smp[i][fi] : std::string("."), ',', vals);
+        float sum = 0.f;
+        for (int l = 0; l < ngen; ++l) { float x = l < (int)vals.size() ? (float)atof(vals[l].c_str()) : 0.f; gps[(size_t)i * ngen + l] = x; sum += x; }
+        for (int l = 0; l < ngen; ++l) gps[(size_t)i * ngen + l] /= sum;
+      }
+    }
+    r.pos = atoi(c[1].c_str());
+    r.ref = alleles[0][0];
+    r.alt = nal > 1 ? alleles[1][0] : '.';
+    if (nal != 2) gps.resize((size_t)nv * 3, 0.f);
+    if (o.geno_error_coeff > 0) r.text = c[7];
+    return 0;
+  }
+};
+
+struct VcfCursor {
+  const LoadOptions& o;
+  VcfHeader H;
+  std::vector<std::string>& samples = H.samples;
+  std::map<std::string, int> contig;  // header order, then first appearance (numbered as the cursor reaches them)
+  std::vector<VcfPiece> pieces;
+  size_t pi = 0, ri = 0;
   bool eof = false;
   int rid = -1, pos = 0;
   char ref = 0, alt = 0;
-  std::vector<float> gps;             // [nv*3] of the current record
+  const float* gps = nullptr;         // [nv*3] of the current record
   std::string info;                   // INFO column of the current record
-  std::string line;
-  std::vector<std::string> c, alleles, fmt, cell, parts, vals;
-  std::vector<int> g1, g2, acs;
-  std::vector<std::vector<std::string>> smp;
+  std::string path;
 
-  VcfCursor(const std::string& path, const LoadOptions& opt) : rd(path), o(opt) {
+  VcfCursor(const std::string& p, const LoadOptions& opt) : o(opt), path(p) {
+    const int T = loader_threads();
+    const bool trace = getenv("PSCL_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    const std::vector<char> text = slurp_text(path, T, nullptr);
+    const auto t1 = std::chrono::steady_clock::now();
+    const char* tb = text.data();
+    const char* const te = tb + text.size();
+    // ---- header ----
     bool saw = false;
-    while (rd.next(line)) {
+    const char* lb = tb;
+    std::string line;
+    std::vector<std::string> c;
+    while (lb < te) {
+      const char* nl = (const char*)memchr(lb, '\n', (size_t)(te - lb));
+      const char* le = nl ? nl : te;
+      line.assign(lb, le);
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      lb = nl ? nl + 1 : te;
       if (line.compare(0, 2, "##") == 0) {
         if (line.compare(0, 13, "##contig=<ID=") == 0) {
           size_t e = line.find_first_of(",>", 13);
           std::string id = line.substr(13, e == std::string::npos ? std::string::npos : e - 13);
-          if (!contig.count(id)) { int k = (int)contig.size(); contig[id] = k; }
+          if (!H.contig.count(id)) { int k = (int)H.contig.size(); H.contig[id] = k; }
         }
         continue;
       }
@@ -61,122 +206,101 @@ struct VcfCursor {
           for (const auto& s : want) {
             auto it = std::find(all.begin(), all.end(), s);
             if (it == all.end()) throw host_error("Cannot find sample ID " + s + " from the BCF file");
-            samples.push_back(s);
-            cols.push_back((int)(it - all.begin()));
+            H.samples.push_back(s);
+            H.cols.push_back((int)(it - all.begin()));
           }
         } else {
-          samples = all;
-          cols.resize(all.size());
-          std::iota(cols.begin(), cols.end(), 0);
+          H.samples = all;
+          H.cols.resize(all.size());
+          std::iota(H.cols.begin(), H.cols.end(), 0);
         }
         saw = true;
-        break;
       }
       break;
     }
     if (!saw) throw host_error("Failed reading the BCF/VCF header from " + path + " (text VCF, plain or gzip, is supported)");
+    contig = H.contig;
+    // ---- data lines, in line-aligned pieces ----
+    const char* body = lb;
+    const size_t len = (size_t)(te - body);
+    const int NP = (int)std::max<size_t>(1, std::min<size_t>((size_t)T * 4, len / (1 << 18) + 1));
+    std::vector<const char*> cut(NP + 1);
+    cut[0] = body; cut[NP] = te;
+    for (int i = 1; i < NP; ++i) {
+      const char* q = body + len * (size_t)i / NP;
+      const char* nl = (const char*)memchr(q, '\n', (size_t)(te - q));
+      cut[i] = nl ? nl + 1 : te;
+      if (cut[i] < cut[i - 1]) cut[i] = cut[i - 1];
+    }
+    pieces.resize(NP);
+    const size_t nv3 = H.cols.size() * 3;
+    parallel_for(NP, T, [&](int k) {
+      VcfPiece P;  // on this thread's stack while it grows
+      VcfLineParser ps(o, H, path);
+      std::string ln;
+      auto name_of = [&](const std::string& nm) {  // -1 - index of a contig the header does not list
+        size_t j = 0;
+        while (j < P.names.size() && P.names[j] != nm) ++j;
+        if (j == P.names.size()) P.names.push_back(nm);
+        return -1 - (int)j;
+      };
+      const char* b = cut[k];
+      while (b < cut[k + 1]) {
+        const char* nl = (const char*)memchr(b, '\n', (size_t)(cut[k + 1] - b));
+        const char* e = nl ? nl : cut[k + 1];
+        ln.assign(b, e);
+        b = nl ? nl + 1 : cut[k + 1];
+        if (!ln.empty() && ln.back() == '\r') ln.pop_back();
+        if (ln.empty()) continue;
+        VcfRec r;
+        try {
+          r.state = (uint8_t)ps.parse(ln, r);
+          // the reference's reader looks the contig up before it filters: a dropped record numbers its contig too
+          auto it = H.contig.find(ps.c[0]);
+          r.rid = it != H.contig.end() ? it->second : name_of(ps.c[0]);
+          if (r.state == 0) {
+            r.gps_off = P.gps.size();
+            P.gps.insert(P.gps.end(), ps.gps.begin(), ps.gps.begin() + nv3);
+          }
+        } catch (const host_error& err) {
+          r.state = 2;
+          r.text = err.what();
+          r.rid = 0;
+          if (ps.c.size() >= 10) {  // the line was split: its contig is known (and numbered, as above) before anything fails
+            auto it = H.contig.find(ps.c[0]);
+            r.rid = it != H.contig.end() ? it->second : name_of(ps.c[0]);
+          }
+        }
+        P.recs.push_back(std::move(r));
+      }
+      pieces[k] = std::move(P);
+    });
+    if (trace)
+      fprintf(stderr, "[load_plp] vcf: inflate %.1f ms, records parsed on %d threads %.1f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(), T,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   }
 
   // advance to the next record passing the site filters (bcf_filtered_reader.cpp:505-581, :748-762)
   bool read() {
-    const int nv = (int)cols.size();
-    while (rd.next(line)) {
-      if (line.empty()) continue;
-      split_char(line, '\t', c);
-      if (c.size() < 10) throw host_error("VCF data line with fewer than 10 columns in " + rd.path());
-      auto it = contig.find(c[0]);
-      if (it == contig.end()) { int k = (int)contig.size(); it = contig.emplace(c[0], k).first; }
-      alleles.clear();
-      alleles.push_back(c[3]);
-      if (c[4] != ".") { split_char(c[4], ',', parts); alleles.insert(alleles.end(), parts.begin(), parts.end()); }
-      const int nal = (int)alleles.size();
-      if (nal > o.max_alleles) continue;
-      info = c[7];
-      split_char(c[8], ':', fmt);
-      int gi = -1, fi = -1;
-      for (size_t i = 0; i < fmt.size(); ++i) {
-        if (fmt[i] == "GT") gi = (int)i;
-        if (fmt[i] == o.field) fi = (int)i;
+    for (;;) {
+      while (pi < pieces.size() && ri >= pieces[pi].recs.size()) { ++pi; ri = 0; }
+      if (pi >= pieces.size()) { eof = true; return false; }
+      const VcfPiece& P = pieces[pi];
+      const VcfRec& r = P.recs[ri++];
+      int id = r.rid;
+      if (id < 0) {  // a contig the header does not list: numbered at its first appearance
+        const std::string& name = P.names[(size_t)(-1 - id)];
+        auto it = contig.find(name);
+        if (it == contig.end()) { int k = (int)contig.size(); it = contig.emplace(name, k).first; }
+        id = it->second;
       }
-      // GT is parsed (and required) only when something reads it: the site filters minMAC / minCallRate
-      // (require_GT, bcf_filter_arg.h:110-113) or --field GT itself
-      const bool need_gt = o.min_mac > 0 || o.min_callrate > 0 || o.field == "GT";
-      if (gi < 0 && need_gt) throw host_error("Cannot find the field GT from the VCF file at position " + c[0] + ":" + c[1]);
-      g1.assign(nv, -1); g2.assign(nv, -1); acs.assign(nal, 0);  // members: no allocation per record
-      int an = 0;
-      if ((int)smp.size() != nv) smp.resize(nv);
-      for (int i = 0; i < nv; ++i) {
-        split_char(c[9 + cols[i]], ':', smp[i]);
-        if (gi < 0) continue;
-        const std::string& gt = gi < (int)smp[i].size() ? smp[i][gi] : std::string(".");
-        size_t sep = gt.find_first_of("/|");
-        std::string a = gt.substr(0, sep), b = sep == std::string::npos ? std::string(".") : gt.substr(sep + 1);
-        g1[i] = (a == "." || a.empty()) ? -1 : atoi(a.c_str());
-        g2[i] = (b == "." || b.empty()) ? -1 : atoi(b.c_str());
-        if (g1[i] >= nal || g2[i] >= nal)  // an allele number the record does not define ("0/3" at a biallelic site)
-          throw host_error("GT " + gt + " names an allele beyond the ALT list at position " + c[0] + ":" + c[1]);
-        if (g1[i] >= 0) { ++an; ++acs[g1[i]]; }
-        if (g2[i] >= 0) { ++an; ++acs[g2[i]]; }
-      }
-      if (need_gt) {
-        if (nv > 0 && o.min_callrate > (double)an / (2.0 * nv)) continue;
-        const int ac = an - acs[0];
-        if (ac < o.min_mac || an - ac < o.min_mac) continue;
-      }
-      // ---- posteriors with gt_error = 0 (load_from_plp passes 0, sc_drop_seq.cpp:113,285) ----
-      const int ngen = nal * (nal + 1) / 2;
-      gps.assign((size_t)nv * ngen, 0.f);
-      if (o.field == "GT") {  // :379-412
-        for (int i = 0; i < nv; ++i) {
-          if (g1[i] < 0 || g2[i] < 0) {
-            int l = 0;
-            for (int j = 0; j < nal; ++j)
-              for (int k = 0; k <= j; ++k, ++l)
-                gps[(size_t)i * ngen + l] = (float)((j == k ? 1.0 : 2.0) * (acs[j] + 1.0 / nal) / (an + 1.0) * (acs[k] + 1.0 / nal) / (an + 1.0));
-          } else {
-            const int a = std::max(g1[i], g2[i]), b = std::min(g1[i], g2[i]);
-            gps[(size_t)i * ngen + a * (a + 1) / 2 + b] = 1.0f;
-          }
-        }
-      } else if (o.field == "PL") {  // :250-327, ploidy 2
-        if (fi < 0) throw host_error("Cannot parse posterior probability at " + c[0] + ":" + c[1]);
-        std::vector<double> pls((size_t)nv * ngen), af(nal, 1.0 / nal), gp(ngen), post((size_t)nv * ngen);
-        for (int i = 0; i < nv; ++i) {
-          split_char(fi < (int)smp[i].size() ? smp[i][fi] : std::string("."), ',', vals);
-          for (int l = 0; l < ngen; ++l) pls[(size_t)i * ngen + l] = l < (int)vals.size() ? atoi(vals[l].c_str()) : 0;
-        }
-        for (int iter = 0; iter < 10; ++iter) {
-          std::vector<double> nw(nal, 0.0);
-          for (int i = 0; i < nv; ++i) {
-            double sum = 0;
-            int l = 0;
-            for (int j = 0; j < nal; ++j)
-              for (int k = 0; k <= j; ++k, ++l) sum += (gp[l] = (j == k ? 1 : 2) * af[j] * af[k] * std::pow(0.1, pls[(size_t)i * ngen + l] / 10.0));
-            l = 0;
-            for (int j = 0; j < nal; ++j)
-              for (int k = 0; k <= j; ++k, ++l) { gp[l] /= sum; nw[j] += gp[l]; nw[k] += gp[l]; post[(size_t)i * ngen + l] = gp[l]; }
-          }
-          for (int j = 0; j < nal; ++j) af[j] = nw[j] / (2.0 * nv);
-        }
-        for (size_t i = 0; i < post.size(); ++i) gps[i] = (float)post[i];
-      } else {  // GP-like float field, :434-458 with gt_error = 0
-        if (fi < 0) throw host_error("Cannot parse posterior probability at " + c[0] + ":" + c[1]);
-        for (int i = 0; i < nv; ++i) {
-          split_char(fi < (int)smp[i].size() ? smp[i][fi] : std::string("."), ',', vals);
-          float sum = 0.f;
-          for (int l = 0; l < ngen; ++l) { float x = l < (int)vals.size() ? (float)atof(vals[l].c_str()) : 0.f; gps[(size_t)i * ngen + l] = x; sum += x; }
-          for (int l = 0; l < ngen; ++l) gps[(size_t)i * ngen + l] /= sum;
-        }
-      }
-      rid = it->second;
-      pos = atoi(c[1].c_str());
-      ref = alleles[0][0];
-      alt = nal > 1 ? alleles[1][0] : '.';
-      if (nal != 2) gps.resize((size_t)nv * 3, 0.f);
+      if (r.state == 2) throw host_error(r.text);
+      if (r.state == 1) continue;
+      rid = id; pos = r.pos; ref = r.ref; alt = r.alt;
+      gps = P.gps.data() + r.gps_off;
+      info = r.text;
       return true;
     }
-    eof = true;
-    return false;
   }
 };
 
@@ -290,6 +414,8 @@ void load_var_vcf(const LoadOptions& o, Loaded& L) {
       nv = (int)L.samples.size();
     }
     std::map<std::string, int> chr2rid;
+    std::vector<const float*> hit;       // per VAR row: the posteriors of its VCF record (inside vc->pieces), or null
+    std::vector<std::string> hit_info;   // ... and its INFO column, when --geno-error-coeff reads it
     while (next_row(r, line, f)) {
       if (f.size() < 6) throw host_error("Cannot access field at 5 >= " + std::to_string(f.size()));
       auto it = chr2rid.find(f[1]);
@@ -307,48 +433,70 @@ void load_var_vcf(const LoadOptions& o, Loaded& L) {
         }
         vc->read();
       }
-      const size_t base = L.gp.size();
-      L.gp.resize(base + (size_t)nv * 3, 0.0);
-      L.gp_f32.resize(base + (size_t)nv * 3, 0.f);
-      L.gt8.resize(L.gt8.size() + (size_t)nv, 0);
-      L.err_snp.push_back(0.0);
       L.has_gp.push_back(found ? 1 : 0);
-      if (!found) continue;
-      for (int j = 0; j < nv; ++j) {  // raw forms for the device-side mixing
-        const float* g = &vc->gps[(size_t)j * 3];
-        L.gp_f32[base + 3 * j] = g[0]; L.gp_f32[base + 3 * j + 1] = g[1]; L.gp_f32[base + 3 * j + 2] = g[2];
-        const int code = (g[0] == 1.f && g[1] == 0.f && g[2] == 0.f) ? 0 : (g[0] == 0.f && g[1] == 1.f && g[2] == 0.f) ? 1
-                       : (g[0] == 0.f && g[1] == 0.f && g[2] == 1.f) ? 2 : -1;
-        if (code < 0) L.gt8_ok = false; else L.gt8[base / 3 + j] = (uint8_t)code;
-      }
-      double avg[3] = {1e-10, 1e-10, 1e-10};  // :288-292
-      for (int i = 0; i < nv * 3; ++i) avg[i % 3] += (L.gp[base + i] = (double)vc->gps[i]);
-      const double sum = avg[0] + avg[1] + avg[2];
-      avg[0] /= sum; avg[1] /= sum; avg[2] /= sum;
-      double err = o.geno_error_offset;
-      if (o.geno_error_coeff > 0) {  // look for the R2 INFO field: exactly one float (sc_drop_seq.cpp:301-306)
-        bool ok = false;
-        float r2 = 0.f;
-        const std::string key = o.r2_info + "=";
-        size_t b = 0;
-        while (b <= vc->info.size()) {
-          size_t e2 = vc->info.find(';', b);
-          if (e2 == std::string::npos) e2 = vc->info.size();
-          if (vc->info.compare(b, key.size(), key) == 0) {
-            const std::string val = vc->info.substr(b + key.size(), e2 - b - key.size());
-            if (!val.empty() && val != "." && val.find(',') == std::string::npos) { r2 = (float)atof(val.c_str()); ok = true; }
-            break;
+      hit.push_back(found ? vc->gps : nullptr);
+      if (o.geno_error_coeff > 0) hit_info.push_back(found ? vc->info : std::string());
+    }
+    // ---- the genotype tables of the matched SNPs, filled in parallel (the join above only recorded where each SNP's record is) ----
+    const size_t V = L.chrom.size();
+    if (vc) {
+      L.gp.assign(V * (size_t)nv * 3, 0.0);
+      L.gp_f32.assign(V * (size_t)nv * 3, 0.f);
+      L.gt8.assign(V * (size_t)nv, 0);
+      L.err_snp.assign(V, 0.0);
+      const int T = loader_threads();
+      const int NC = (int)std::max<size_t>(1, std::min<size_t>((size_t)T * 4, V / 2048 + 1));
+      std::atomic<bool> all_hard(true);
+      std::mutex mu;
+      size_t bad_v = V;  // the first SNP whose INFO field cannot be used: its error is the one a serial reader would raise
+      parallel_for(NC, T, [&](int k) {
+        bool hard = true;
+        for (size_t v = V * (size_t)k / NC; v < V * (size_t)(k + 1) / NC; ++v) {
+          const float* g0 = hit[v];
+          if (!g0) continue;
+          const size_t base = v * (size_t)nv * 3;
+          for (int j = 0; j < nv; ++j) {  // raw forms for the device-side mixing
+            const float* g = g0 + (size_t)j * 3;
+            L.gp_f32[base + 3 * j] = g[0]; L.gp_f32[base + 3 * j + 1] = g[1]; L.gp_f32[base + 3 * j + 2] = g[2];
+            const int code = (g[0] == 1.f && g[1] == 0.f && g[2] == 0.f) ? 0 : (g[0] == 0.f && g[1] == 1.f && g[2] == 0.f) ? 1
+                           : (g[0] == 0.f && g[1] == 0.f && g[2] == 1.f) ? 2 : -1;
+            if (code < 0) hard = false; else L.gt8[base / 3 + j] = (uint8_t)code;
           }
-          b = e2 + 1;
+          double avg[3] = {1e-10, 1e-10, 1e-10};  // :288-292
+          for (int i = 0; i < nv * 3; ++i) avg[i % 3] += (L.gp[base + i] = (double)g0[i]);
+          const double sum = avg[0] + avg[1] + avg[2];
+          avg[0] /= sum; avg[1] /= sum; avg[2] /= sum;
+          double err = o.geno_error_offset;
+          if (o.geno_error_coeff > 0) {  // look for the R2 INFO field: exactly one float (sc_drop_seq.cpp:301-306)
+            const std::string& info = hit_info[v];
+            bool ok = false;
+            float r2 = 0.f;
+            const std::string key = o.r2_info + "=";
+            size_t b2 = 0;
+            while (b2 <= info.size()) {
+              size_t e2 = info.find(';', b2);
+              if (e2 == std::string::npos) e2 = info.size();
+              if (info.compare(b2, key.size(), key) == 0) {
+                const std::string val = info.substr(b2 + key.size(), e2 - b2 - key.size());
+                if (!val.empty() && val != "." && val.find(',') == std::string::npos) { r2 = (float)atof(val.c_str()); ok = true; }
+                break;
+              }
+              b2 = e2 + 1;
+            }
+            if (!ok) { std::lock_guard<std::mutex> lk(mu); if (v < bad_v) bad_v = v; break; }
+            err += (1 - o.geno_error_offset) * (1 - r2) * o.geno_error_coeff;
+          }
+          L.err_snp[v] = err;  // the library clamps it the same way
+          if (err > 0.999) err = 0.999;
+          if (err < 0) err = 0;
+          if (err > 0)
+            for (int i = 0; i < nv * 3; ++i) L.gp[base + i] = (1 - err) * L.gp[base + i] + err * avg[i % 3];
         }
-        if (!ok) throw host_error("Cannot extract " + o.r2_info + " (1 float value) from INFO field at " + std::string(f[1]) + ":" + std::to_string(pos) + ". Cannot use --geno-error-coeff");
-        err += (1 - o.geno_error_offset) * (1 - r2) * o.geno_error_coeff;
-      }
-      L.err_snp.back() = err;  // the library clamps it the same way
-      if (err > 0.999) err = 0.999;
-      if (err < 0) err = 0;
-      if (err > 0)
-        for (int i = 0; i < nv * 3; ++i) L.gp[base + i] = (1 - err) * L.gp[base + i] + err * avg[i % 3];
+        if (!hard) all_hard = false;
+      });
+      if (bad_v < V)
+        throw host_error("Cannot extract " + o.r2_info + " (1 float value) from INFO field at " + L.chrom[bad_v] + ":" + std::to_string(L.pos[bad_v]) + ". Cannot use --geno-error-coeff");
+      if (!all_hard) L.gt8_ok = false;
     }
   }
 }
