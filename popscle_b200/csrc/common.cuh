@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -90,6 +92,12 @@ struct pscl_ctx {
   struct PendingCopy { void* dst; const void* src; size_t bytes; };
   std::vector<PendingCopy> pend;
   bool pend_on = false;
+  // Blocks this context has freed, kept by exact size for its next allocation of that size (pscl_pool_alloc / _free below):
+  // a run allocates the same three dozen sizes every call, and although cudaMallocAsync / cudaFreeAsync are cheap on average
+  // (0.6 us), a third of the calls of a 1.7 ms run stalled 1-4 ms inside them (profiles/r3r_allocator_jitter.txt)
+  std::unordered_map<void*, size_t> blk_live;
+  std::multimap<size_t, void*> blk_free;
+  size_t blk_free_bytes = 0;
   // PSCL_TIMELINE=1: device-time stamps of a run (ms after its first enqueue), printed by pscl_demux_run
   cudaEvent_t tl[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool tl_on = false;
@@ -147,19 +155,18 @@ static thread_local cudaStream_t t_pscl_stream = nullptr;
 static thread_local pscl_ctx* t_pscl_ctx = nullptr;
 static thread_local double t_pscl_alloc_ms = 0.0;  // PSCL_TIMELINE: host time inside the allocator calls of the current run
 static thread_local int t_pscl_alloc_n = 0;
-static inline cudaError_t pscl_pool_alloc(void** p, size_t n) {
-  // fault injection (pscl_debug_fail_alloc): the n-th allocation from now fails the way an exhausted device does
-  if (t_pscl_ctx && t_pscl_ctx->fail_alloc_in > 0 && --t_pscl_ctx->fail_alloc_in == 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+static const size_t PSCL_BLK_CACHE_BYTES = (size_t)16 << 30;  // what a context keeps at most (the pool would keep it mapped anyway)
+static const size_t PSCL_BLK_CACHE_N = 512;
+static inline cudaError_t pscl_raw_alloc(void** p, size_t n) {
   if (t_pscl_ctx && t_pscl_ctx->tl_on) {
     const auto t0 = std::chrono::steady_clock::now();
-    const cudaError_t e = cudaMallocAsync(p, n ? n : 16, t_pscl_stream);
+    const cudaError_t e = cudaMallocAsync(p, n, t_pscl_stream);
     t_pscl_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++t_pscl_alloc_n;
     return e;
   }
-  return cudaMallocAsync(p, n ? n : 16, t_pscl_stream);
+  return cudaMallocAsync(p, n, t_pscl_stream);
 }
-static inline cudaError_t pscl_pool_free(void* p) {
-  if (!p) return cudaSuccess;
+static inline cudaError_t pscl_raw_free(void* p) {
   if (t_pscl_ctx && t_pscl_ctx->tl_on) {
     const auto t0 = std::chrono::steady_clock::now();
     const cudaError_t e = cudaFreeAsync(p, t_pscl_stream);
@@ -167,6 +174,58 @@ static inline cudaError_t pscl_pool_free(void* p) {
     return e;
   }
   return cudaFreeAsync(p, t_pscl_stream);
+}
+static inline void pscl_blk_cache_flush(pscl_ctx* c) {  // hand every kept block back to the pool (out of memory, destroy)
+  for (auto& kv : c->blk_free) pscl_raw_free(kv.second);
+  c->blk_free.clear();
+  c->blk_free_bytes = 0;
+}
+// Stream-ordered allocation with a per-context cache of freed blocks.  A kept block was "freed" in the order of the context's
+// stream and is handed out again in that order, so work queued before the free is done before work queued after the reuse
+// (copies a run puts on its copy stream are queued, and waited for, before the run frees anything).
+static inline cudaError_t pscl_pool_alloc(void** p, size_t n) {
+  pscl_ctx* const c = t_pscl_ctx;
+  // fault injection (pscl_debug_fail_alloc): the n-th allocation from now fails the way an exhausted device does
+  if (c && c->fail_alloc_in > 0 && --c->fail_alloc_in == 0) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  if (!n) n = 16;
+  if (c) {
+    auto it = c->blk_free.find(n);
+    if (it != c->blk_free.end()) {
+      *p = it->second;
+      c->blk_free.erase(it);
+      c->blk_free_bytes -= n;
+      c->blk_live[*p] = n;
+      return cudaSuccess;
+    }
+  }
+  // a large request the kept blocks could cover between them: the workload has changed, so they go back to the pool first
+  // (it then reuses their memory instead of mapping more)
+  if (c && n >= ((size_t)64 << 20) && c->blk_free_bytes >= n) pscl_blk_cache_flush(c);
+  cudaError_t e = pscl_raw_alloc(p, n);
+  if (e == cudaErrorMemoryAllocation && c && !c->blk_free.empty()) {  // give the kept blocks back and try once more
+    cudaGetLastError();
+    pscl_blk_cache_flush(c);
+    e = pscl_raw_alloc(p, n);
+  }
+  if (e == cudaSuccess && c) c->blk_live[*p] = n;
+  return e;
+}
+static inline cudaError_t pscl_pool_free(void* p) {
+  if (!p) return cudaSuccess;
+  pscl_ctx* const c = t_pscl_ctx;
+  if (c) {
+    auto it = c->blk_live.find(p);
+    if (it != c->blk_live.end()) {
+      const size_t n = it->second;
+      c->blk_live.erase(it);
+      if (c->blk_free_bytes + n <= PSCL_BLK_CACHE_BYTES && c->blk_free.size() < PSCL_BLK_CACHE_N) {
+        c->blk_free.emplace(n, p);
+        c->blk_free_bytes += n;
+        return cudaSuccess;
+      }
+    }
+  }
+  return pscl_raw_free(p);
 }
 #define cudaMalloc(p, n) pscl_pool_alloc((void**)(p), (n))
 #define cudaFree(p) pscl_pool_free((void*)(p))
