@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PSCL_ABI_VERSION 6
+#define PSCL_ABI_VERSION 7
 
 typedef enum pscl_status {
   PSCL_OK = 0,
@@ -100,6 +100,11 @@ typedef struct pscl_pileup {
   const uint8_t* read_palette;       /* [1 << read_bits] allele<<6|qual of each index            */
   int32_t read_bits;                 /* 0 = not given                                            */
   int32_t reserved_;
+  /* ABI 7 (optional, NULL = not given): the first base-call of every cell, cell_read_ptr[c] = pair_read_ptr[cell_ptr[c]]
+   * (cell_read_ptr[C] = n_reads).  A host that sends base-call COUNTS (ABI 3 / 6) instead of offsets loses nothing by adding
+   * these 8 bytes per cell, and they let pscl_demux_run cut the counts and base-calls at the same cells as the SNP gaps:
+   * every slice of the pileup then lands whole and is decoded and scored while the next one crosses PCIe. */
+  const int64_t* cell_read_ptr;      /* [C+1]                                                    */
 } pscl_pileup;
 
 /* Genotype table (replaces sc_snp_t::gps, sc_drop_seq.h:29-37, filled at

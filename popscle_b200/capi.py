@@ -36,7 +36,8 @@ class CPileup(C.Structure):
                 ("pair_snp_delta8", C.c_void_p), ("snp_gap_big", C.c_void_p), ("cell_gap_big_ptr", C.c_void_p),
                 ("pair_nreads2", C.c_void_p), ("nreads_big", C.c_void_p), ("nreads_big_ptr", C.c_void_p),
                 ("n_gap_big", C.c_int64), ("n_nreads_big", C.c_int64),
-                ("read_packed", C.c_void_p), ("read_palette", C.c_void_p), ("read_bits", C.c_int32), ("reserved_", C.c_int32)]
+                ("read_packed", C.c_void_p), ("read_palette", C.c_void_p), ("read_bits", C.c_int32), ("reserved_", C.c_int32),
+                ("cell_read_ptr", C.c_void_p)]
 
 
 class CGeno(C.Structure):
@@ -169,6 +170,14 @@ class Pileup:
             self._compact3 = c
         return c
 
+    def cell_read_ptr(self):
+        """ABI 7: first base-call of every cell, [C+1] int64 (cached; a caller may pin its own copy in `_cell_read_ptr`)."""
+        c = getattr(self, "_cell_read_ptr", None)
+        if c is None:
+            c = np.ascontiguousarray(np.asarray(self.pair_read_ptr, dtype=np.int64)[np.asarray(self.cell_ptr, dtype=np.int64)])
+            self._cell_read_ptr = c
+        return c
+
     def compact4(self):
         """The ABI-6 pair arrays (1.25 B per pair): (cell_first_snp, pair_snp_delta8, snp_gap_big, cell_gap_big_ptr,
         pair_nreads2, nreads_big, nreads_big_ptr), or None when a pair has no or >= 256 base-calls."""
@@ -251,6 +260,8 @@ class Pileup:
                 s.nreads_big = nbig.ctypes.data if len(nbig) else None
                 s.n_gap_big, s.n_nreads_big = len(gbig), len(nbig)
                 s.pair_snp = s.pair_read_ptr32 = None
+                crp = self.cell_read_ptr()  # ABI 7: lets the run slice counts and base-calls with the gaps
+                s.cell_read_ptr = crp.ctypes.data
                 pr = self.packed_reads()
                 if pr is not None:  # 4-6 bits per base-call instead of 8
                     s.read_packed, s.read_palette, s.read_bits = pr[0].ctypes.data, pr[1].ctypes.data, pr[2]

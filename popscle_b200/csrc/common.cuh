@@ -68,6 +68,18 @@ struct pscl_plp {
   int64_t n_gap_big = 0;
   int* d_bad = nullptr;
   int n_stages = 0;
+  // fully sliced run: counts, base-calls and gaps of a slice land together and are decoded by per-slice launches, so these
+  // upload temporaries live as long as the image (sl_full); sl_rb[k] = first base-call of slice k (from the host's offsets)
+  bool sl_full = false;
+  uint8_t *sl_cnt = nullptr, *sl_n2 = nullptr, *sl_nbig = nullptr, *sl_rpk = nullptr, *sl_rpal = nullptr;
+  int64_t* sl_nblk = nullptr;
+  int64_t* sl_cell_rd = nullptr;  // [C+1] device copy of cell_read_ptr
+  void* sl_scan_tmp = nullptr;
+  size_t sl_scan_bytes = 0;
+  int64_t sl_rb[PSCL_MAX_STAGES + 1] = {0};
+  std::vector<int64_t> sl_nbp;  // host copy of nreads_big_ptr (per 1024 pairs)
+  int64_t sl_n_big = 0;
+  int sl_read_bits = 0;
   int n_slices = 0;  // pipelined pscl_demux_run: the gaps land slice by slice (one event each) and every slice is decoded and
                      // scored by its own launches; stage_cell[] holds the cuts of either form
   int32_t stage_cell[PSCL_MAX_STAGES + 1] = {0};

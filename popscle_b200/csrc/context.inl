@@ -168,11 +168,11 @@ __global__ void k_pack_reads(const uint8_t* __restrict__ al, const uint8_t* __re
 }
 
 // ABI 6: base-calls as read_bits-wide indices into a palette of allele<<6|qual bytes -> one byte per base-call
-__global__ void k_unpack_reads(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ palette, int bits, int64_t n, uint8_t* __restrict__ aq, int* bad) {
+__global__ void k_unpack_reads(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ palette, int bits, int64_t r0, int64_t n, uint8_t* __restrict__ aq, int* bad) {
   __shared__ uint8_t s_pal[64];
   if (threadIdx.x < (1u << bits)) s_pal[threadIdx.x] = palette[threadIdx.x];
   __syncthreads();
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // base-calls [r0, n) of the bit string
   if (r >= n) return;
   const int64_t o = r * bits;
   const unsigned w = (unsigned)packed[o >> 3] | ((unsigned)packed[(o >> 3) + 1] << 8);  // one byte of slack behind the string
@@ -316,6 +316,125 @@ __global__ void __launch_bounds__(PSCL_DEC8_NT) k_decode_snp8(const int64_t* __r
   __syncthreads();
   if (tid == 0 && s_oob) atomicExch(bad, 2);
 }
+// ABI 6 + 7, everything of a cell in one CTA: SNP ids from the 8-bit gaps, read offsets from the 2-bit counts (seeded with the
+// cell's first base-call, cell_read_ptr), and the cell's base-calls unpacked from the palette bit string.  With the offsets
+// of the cells given, nothing in the decoding reaches across cells: a slice of whole cells is ONE launch that lasts about one
+// cell (~10 us), instead of an expand kernel, a device-wide scan and an unpack kernel over the slice.
+// Per tile of 2048 pairs (8 per thread): one block scan of the two marker counts (gaps = 255 / counts = 0, packed 16 + 16
+// bits) places the large values in their side lists, one block scan of the resolved (gap, count) pairs (packed 32 + 32 bits)
+// gives ids and offsets.  The rank of the cell's first large count inside its 1024-pair block of nreads_big_ptr is counted
+// from the 2-bit fields in front of it.
+__device__ __forceinline__ unsigned long long dec_block_exscan64(unsigned long long v, unsigned long long* s_warp, unsigned long long& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  unsigned long long before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < PSCL_DEC8_NT / 32; ++w) { const unsigned long long t = s_warp[w]; before += w < warp ? t : 0; all += t; }
+  __syncthreads();
+  total = all;
+  return before + x - v;
+}
+__global__ void __launch_bounds__(PSCL_DEC8_NT, 4) k_decode_cells(const int64_t* __restrict__ cell_ptr, const int32_t* __restrict__ first,
+                               const uint8_t* __restrict__ delta8, const uint32_t* __restrict__ gap_big, const int64_t* __restrict__ cell_gap_ptr,
+                               int64_t n_gap_big, const uint8_t* __restrict__ n2, const uint8_t* __restrict__ nbig,
+                               const int64_t* __restrict__ nblk, int64_t n_big, const int64_t* __restrict__ cell_rd,
+                               const uint8_t* __restrict__ rpk, const uint8_t* __restrict__ rpal, int bits, int64_t n_reads,
+                               int32_t C, int32_t V, int32_t* __restrict__ pair_snp, uint32_t* __restrict__ pair_rd,
+                               uint8_t* __restrict__ aq, int* bad) {
+  __shared__ unsigned long long s_warp[PSCL_DEC8_NT / 32];
+  __shared__ uint8_t s_pal[64];
+  __shared__ int s_flag;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  if (c >= C) return;
+  const int64_t b = cell_ptr[c], e = cell_ptr[c + 1], rb = cell_rd[c], re = cell_rd[c + 1];
+  if (tid == 0) s_flag = 0;
+  if (tid < (1 << bits)) s_pal[tid] = rpal[tid];
+  int flag = 0;  // 2 = SNP ids / large gaps, 3 = counts, 1 = base-calls
+  if (rb < 0 || re < rb || re > n_reads) flag = 3;
+  if (b < e && !flag) {
+    // rank of the cell's first large count: the block's start in nreads_big + the zero fields between the block's first pair and b
+    const int64_t blk0 = (b >> 10) << 10;
+    unsigned long long zeros = 0, tot;
+    for (int64_t g = blk0 + tid; g < b; g += PSCL_DEC8_NT) zeros += ((n2[g >> 2] >> (2 * (int)(g & 3))) & 3u) == 0u;
+    dec_block_exscan64(zeros, s_warp, tot);
+    int64_t big_cnt = nblk[b >> 10] - nblk[0] + (int64_t)tot;
+    int64_t big_gap = cell_gap_ptr[c];
+    int run_snp = first[c];
+    int64_t run_rd = rb;
+    if (run_snp < 0 || run_snp >= V) flag = 2;
+    for (int64_t base = b; base < e; base += PSCL_DEC8_NT * PSCL_DEC8_PER) {
+      const int64_t p0 = base + (int64_t)tid * PSCL_DEC8_PER;
+      int d[PSCL_DEC8_PER], f[PSCL_DEC8_PER];
+      unsigned marks = 0;  // low 16 bits: gaps of 255, high 16 bits: counts of 0
+#pragma unroll
+      for (int i = 0; i < PSCL_DEC8_PER; ++i) {
+        const int64_t p = p0 + i;
+        d[i] = (p < e && p > b) ? (int)delta8[p] : 0;
+        f[i] = p < e ? (int)((n2[p >> 2] >> (2 * (int)(p & 3))) & 3u) : 1;
+        marks += (d[i] == 255 ? 1u : 0u) + (f[i] == 0 ? 0x10000u : 0u);
+        if (p >= e) f[i] = 0;  // past the cell: contributes no base-call (it was counted as "not a marker" above)
+      }
+      unsigned long long tm;
+      const unsigned long long em = dec_block_exscan64(marks, s_warp, tm);
+      int64_t kg = big_gap + (int64_t)(em & 0xffffu), kc = big_cnt + (int64_t)((em >> 16) & 0xffffu);
+      unsigned long long sums = 0;  // low 32 bits: gap sum, high 32 bits: base-call count sum
+#pragma unroll
+      for (int i = 0; i < PSCL_DEC8_PER; ++i) {
+        const int64_t p = p0 + i;
+        if (d[i] == 255) { if (kg < n_gap_big) d[i] = (int)gap_big[kg]; else { d[i] = 0; flag = 2; } ++kg; }
+        if (p < e && f[i] == 0) { if (kc < n_big) { f[i] = (int)nbig[kc]; if (f[i] == 0) flag = 3; } else flag = 3; ++kc; }
+        sums += (unsigned long long)(unsigned)d[i] + ((unsigned long long)(unsigned)f[i] << 32);
+      }
+      big_gap += (int64_t)(tm & 0xffffu);
+      big_cnt += (int64_t)((tm >> 16) & 0xffffu);
+      unsigned long long ts;
+      const unsigned long long es = dec_block_exscan64(sums, s_warp, ts);
+      int id = run_snp + (int)(unsigned)(es & 0xffffffffu);
+      int64_t rd = run_rd + (int64_t)(es >> 32);
+#pragma unroll
+      for (int i = 0; i < PSCL_DEC8_PER; ++i) {
+        const int64_t p = p0 + i;
+        id += d[i];
+        if (p < e) { pair_snp[p] = id; pair_rd[p] = (uint32_t)rd; if (id < 0 || id >= V) flag = 2; }
+        rd += f[i];
+      }
+      run_snp += (int)(unsigned)(ts & 0xffffffffu);
+      run_rd += (int64_t)(ts >> 32);
+    }
+    if (big_gap != cell_gap_ptr[c + 1]) flag = 2;  // the cell used more or fewer large gaps than the host says it owns
+    if (run_rd != re) flag = 3;                    // its counts do not add up to its base-calls
+  } else if (b >= e && re != rb && !flag) flag = 3;
+  if (tid == 0) pair_rd[e] = (uint32_t)re;  // the next cell writes the same value; the last cell closes the array
+  __syncthreads();  // (s_pal)
+  // base-calls: 8 per thread and step (their 4-6 bits sit in at most 7 consecutive bytes), so a cell of a few thousand
+  // base-calls is one or two steps of independent loads
+  if (flag != 3) {
+    for (int64_t r0 = rb + (int64_t)tid * 8; r0 < re; r0 += (int64_t)PSCL_DEC8_NT * 8) {
+      const int64_t o = r0 * bits;
+      const int64_t by = o >> 3;
+      unsigned long long w = 0;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) w |= (unsigned long long)rpk[by + k] << (8 * k);  // (the bit string has slack bytes behind it)
+      w >>= (int)(o & 7);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (r0 + k < re) {
+          const uint8_t v = s_pal[(unsigned)(w >> (k * bits)) & ((1u << bits) - 1u)];
+          if ((v >> 6) == 3) flag = flag ? flag : 1;
+          aq[r0 + k] = v;
+        }
+      }
+    }
+  }
+  if (flag) atomicMax(&s_flag, flag);
+  __syncthreads();
+  if (tid == 0 && s_flag) atomicExch(bad, s_flag);
+}
+
 // ABI 6: base-call counts from two bits per pair with the counts >= 4 on the side; one warp per block of 1024 GLOBAL pair
 // indices (blk_ptr[k] = large counts before pair 1024*k); the image holds pairs [pair_base, pair_base + P) of the host's
 // arrays (pair_base != 0 for the barcode shards of pscl_multi_demux_run).  n2 starts at the byte of pair g_first,
@@ -387,6 +506,7 @@ extern "C" void pscl_plp_free(pscl_ctx* ctx, pscl_plp* p) {
     cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(p->d_delta); cudaFree(p->d_first); cudaFree(p->d_bad); cudaFree(p->d_delta8); cudaFree(p->d_gap_big); cudaFree(p->d_cell_gap_ptr);
+  cudaFree(p->sl_cnt); cudaFree(p->sl_n2); cudaFree(p->sl_nbig); cudaFree(p->sl_nblk); cudaFree(p->sl_cell_rd); cudaFree(p->sl_rpk); cudaFree(p->sl_rpal); cudaFree(p->sl_scan_tmp);
   cudaFree(p->cell_ptr); cudaFree(p->pair_snp); cudaFree(p->pair_rd); cudaFree(p->rd_aq);
   cudaFree(p->snp_af); cudaFree(p->item_cell); cudaFree(p->item_pbeg);
   cudaFree(p->item_pend); cudaFree(p->item_order); cudaFree(p->cell_item_ptr); cudaFree(p->snp_ptr);
@@ -527,7 +647,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   pscl_plp* p = new pscl_plp();
   p->C = C; p->V = V; p->P = P; p->N = N;
   // staging need: work items (<= C + P / PSCL_ITEM_PAIRS + 1 of them, 24 B each) + cell_item_ptr + rebased gap offsets
-  if (deferred) deferred = ctx->copy_stream && ctx->ev_up && pscl_stage_begin(ctx, ((size_t)C + (size_t)(P / PSCL_ITEM_PAIRS) + 2) * 24 + ((size_t)C + 1) * 12 + 4096);
+  if (deferred) deferred = ctx->copy_stream && ctx->ev_up && pscl_stage_begin(ctx, ((size_t)C + (size_t)(P / PSCL_ITEM_PAIRS) + 2) * 24 + ((size_t)C + 1) * 20 + 4096);
   // A deferred upload lists its H2D copies instead of queueing them: once every destination exists they all go to the copy
   // stream in one run (small arrays, counts, base-calls, then the gap slices), so the PCIe link is busy from the first
   // microsecond while the context's stream builds the genotype tables and then decodes what has landed.
@@ -552,6 +672,13 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   int64_t* d_nblk = nullptr;
   int64_t n_big_local = 0, n2_first = 0;
   void* d_scan_tmp = nullptr;
+  // Fully sliced run (PSCL_SLICE_FULL=1; measured equal to slicing the gaps alone at configs[1], 1.72 against 1.71 ms per call:
+  // four copies per slice instead of one cost the link 0.1 ms, and a slice's decoding cannot run under the previous group's
+  // scoring, whose persistent CTAs hold every register file): the counts and base-calls are not copied whole ahead of the gaps but slice by slice with them, and
+  // decoded by per-slice launches of the caller (pscl_demux_run).  Needs the ABI-6 forms and the host's read offsets at the
+  // cuts (ABI 7's cell_read_ptr, or pair_read_ptr / pair_read_ptr32 when the host passes them beside the counts).
+  const bool full = deferred && slices > 1 && cnt2 && pal && dsnp8 && (h->cell_read_ptr || h->pair_read_ptr || ptr32) && read_base == 0 && pair_base == 0 &&
+                    P > 0 && C >= 2 * slices && ctx->copy_stream && ctx->ev_up && getenv("PSCL_SLICE_FULL");
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_bad, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_bad, 0, sizeof(int), ctx->stream);
   if (cnt8) {  // ABI 3: 8-bit base-call counts, offsets by an exclusive scan
@@ -562,18 +689,35 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       const int64_t byte0 = g_first / 4, byte1 = (pair_base + P + 3) / 4, big0 = h->nreads_big_ptr[k0], big1 = h->nreads_big_ptr[k1];
       if (big0 < 0 || big1 < big0 || big1 > h->n_nreads_big) { pscl_plp_free(ctx, p); return pscl_fail(ctx, PSCL_EINVAL, "nreads_big_ptr does not index nreads_big"); }
       n_big_local = big1 - big0;
-      if (e == cudaSuccess) e = up((void**)&d_n2, h->pair_nreads2 + byte0, (size_t)(byte1 - byte0));
-      if (e == cudaSuccess) e = up((void**)&d_nbig, h->nreads_big ? h->nreads_big + big0 : nullptr, (size_t)n_big_local);
+      if (full) {  // buffers now, contents slice by slice (step 2b)
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_n2, (size_t)(byte1 - byte0) + 16);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_nbig, (size_t)n_big_local + 16);
+      } else {
+        if (e == cudaSuccess) e = up((void**)&d_n2, h->pair_nreads2 + byte0, (size_t)(byte1 - byte0));
+        if (e == cudaSuccess) e = up((void**)&d_nbig, h->nreads_big ? h->nreads_big + big0 : nullptr, (size_t)n_big_local);
+      }
       if (e == cudaSuccess) e = up((void**)&d_nblk, h->nreads_big_ptr + k0, sizeof(int64_t) * (size_t)(k1 - k0 + 1));
       n2_first = g_first;
     } else if (e == cudaSuccess && P > 0) e = pscl_h2d(ctx, d_cnt, h->pair_nreads8, (size_t)P);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
     STEP("pair_nreads8 / pair_rd");
-    if (ctx->pend_on) ctx->pend.push_back({nullptr, (const void*)1, 0});  // marker: the counts are complete up to here
+    if (ctx->pend_on && !full) ctx->pend.push_back({nullptr, (const void*)1, 0});  // marker: the counts are complete up to here
   } else if (ptr32) { UP(pair_rd, h->pair_read_ptr32, sizeof(uint32_t) * (P + 1)); }
   else { UP(scratch_h2d, h->pair_read_ptr, sizeof(int64_t) * (P + 1)); }
   if (pal) {  // unpacked by k_unpack_reads
-    if (e == cudaSuccess) e = up((void**)&d_rpk, h->read_packed, (size_t)((N * h->read_bits + 7) / 8 + 1));
+    if (full) {
+      if (e == cudaSuccess) e = cudaMalloc((void**)&d_rpk, (size_t)((N * h->read_bits + 7) / 8 + 16));  // k_decode_cells reads 7 bytes at a time
+      std::vector<int64_t> crd;  // the cells' first base-calls: given (ABI 7), or looked up in the host's offsets
+      const int64_t* src = h->cell_read_ptr;
+      if (!src) {
+        crd.resize((size_t)C + 1);
+        for (int32_t c = 0; c <= C; ++c) crd[(size_t)c] = ptr32 ? (int64_t)h->pair_read_ptr32[h->cell_ptr[c]] : h->pair_read_ptr[h->cell_ptr[c]];
+        src = crd.data();
+      }
+      if (e == cudaSuccess) e = cudaMalloc((void**)&p->sl_cell_rd, sizeof(int64_t) * ((size_t)C + 1));
+      if (e == cudaSuccess) e = pscl_stage_copy(ctx, p->sl_cell_rd, src, sizeof(int64_t) * ((size_t)C + 1), true);  // staged: `crd` is a local
+    }
+    else if (e == cudaSuccess) e = up((void**)&d_rpk, h->read_packed, (size_t)((N * h->read_bits + 7) / 8 + 1));
     if (e == cudaSuccess) e = up((void**)&d_rpal, h->read_palette, (size_t)1 << h->read_bits);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
     STEP("read_packed");
@@ -603,7 +747,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       if (e == cudaSuccess) e = pscl_stage_copy(ctx, p->d_cell_gap_ptr, cg.data(), sizeof(int64_t) * ((size_t)C + 1), deferred);
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_snp, sizeof(int32_t) * (P ? P : 1));
-    if (!deferred || !cnt8 || C < 2 * slices) slices = 1;
+    if (!deferred || !cnt8 || C < 2 * slices) slices = 1;  // (`full` implies none of these)
     if (slices > PSCL_MAX_STAGES) slices = PSCL_MAX_STAGES;
     if (stages > 1 || slices > 1) {  // slices of whole cells with about equal pair counts; their copies are queued in step 2b
       if (stages > 1) p->n_stages = stages; else { p->n_slices = slices; stages = slices; }
@@ -660,7 +804,23 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     const int ns = p->n_stages > 1 ? p->n_stages : p->n_slices;
     for (int k = 0; k < ns && e == cudaSuccess; ++k) {
       const int64_t pb = h->cell_ptr[p->stage_cell[k]], pe = h->cell_ptr[p->stage_cell[k + 1]];
-      if (pe > pb)
+      if (full) {  // the slice's counts (2-bit bytes from its first 1024-pair block on, its share of the large counts) and base-calls
+        const int32_t ca = p->stage_cell[k], cb = p->stage_cell[k + 1];
+        const int64_t rb = h->cell_read_ptr ? h->cell_read_ptr[ca] : ptr32 ? (int64_t)h->pair_read_ptr32[pb] : h->pair_read_ptr[pb];
+        const int64_t re = h->cell_read_ptr ? h->cell_read_ptr[cb] : ptr32 ? (int64_t)h->pair_read_ptr32[pe] : h->pair_read_ptr[pe];
+        p->sl_rb[k] = rb; p->sl_rb[k + 1] = re;
+        if (rb < 0 || re < rb || re > N) { e = cudaErrorInvalidValue; where = "pair_read_ptr at a slice boundary"; break; }
+        if (pe > pb) {
+          const int64_t kb0 = pb / 1024, kb1 = (pe + 1023) / 1024, by0 = kb0 * 256, by1 = (pe + 3) / 4;
+          const int64_t bg0 = h->nreads_big_ptr[kb0] - h->nreads_big_ptr[0], bg1 = h->nreads_big_ptr[kb1] - h->nreads_big_ptr[0];
+          if (bg0 < 0 || bg1 < bg0 || bg1 > n_big_local) { e = cudaErrorInvalidValue; where = "nreads_big_ptr at a slice boundary"; break; }
+          e = cudaMemcpyAsync(d_n2 + by0, h->pair_nreads2 + by0, (size_t)(by1 - by0), cudaMemcpyHostToDevice, ctx->copy_stream);
+          if (e == cudaSuccess && bg1 > bg0) e = cudaMemcpyAsync(d_nbig + bg0, h->nreads_big + h->nreads_big_ptr[0] + bg0, (size_t)(bg1 - bg0), cudaMemcpyHostToDevice, ctx->copy_stream);
+          const int64_t q0 = rb * h->read_bits / 8, q1 = (re * h->read_bits + 7) / 8 + 1;
+          if (e == cudaSuccess && re > rb) e = cudaMemcpyAsync(d_rpk + q0, h->read_packed + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->copy_stream);
+        }
+      }
+      if (pe > pb && e == cudaSuccess)
         e = dsnp ? cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream)
                  : cudaMemcpyAsync(p->d_delta8 + pb, h->pair_snp_delta8 + pb, (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
       if (p->n_slices > 1) {  // pipelined run: the host queues the slice's decoding and scoring behind this event
@@ -696,19 +856,29 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (cnt2 && P > 0 && e == cudaSuccess) {
+  if (full && e == cudaSuccess) {
+    // the caller decodes slice by slice (k_decode_cells): hand it the packed inputs
+    p->sl_full = true;
+    p->sl_cnt = d_cnt; p->sl_n2 = d_n2; p->sl_nbig = d_nbig; p->sl_nblk = d_nblk; p->sl_rpk = d_rpk; p->sl_rpal = d_rpal;
+    p->sl_n_big = n_big_local; p->sl_read_bits = h->read_bits;
+    p->sl_nbp.assign(h->nreads_big_ptr, h->nreads_big_ptr + (P + 1023) / 1024 + 1);
+    d_cnt = d_n2 = d_nbig = d_rpk = d_rpal = nullptr; d_nblk = nullptr; d_scan_tmp = nullptr;  // owned by the image from here on
+  }
+  if (cnt2 && P > 0 && e == cudaSuccess && !p->sl_full) {
     const int64_t warps = (pair_base + P - n2_first + 1023) / 1024;
     k_expand_counts2<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_n2, d_nbig, d_nblk, n2_first, pair_base, P, n_big_local, d_cnt, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (cnt8) {
+  if (cnt8 && !p->sl_full) {
     size_t tb = 0;
     thrust::transform_iterator<PsclU8ToU32, const uint8_t*, uint32_t, uint32_t> it((const uint8_t*)d_cnt, PsclU8ToU32());
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, it, p->pair_rd, (int64_t)(P + 1), ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&d_scan_tmp, tb ? tb : 16);
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_scan_tmp, tb, it, p->pair_rd, (int64_t)(P + 1), ctx->stream);
     if (e == cudaSuccess) { k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, P, N, p->d_bad); ctx->launches += 2; e = cudaGetLastError(); }
+  } else if (cnt8) {
+    // fully sliced: scanned per slice by the caller
   } else if (!ptr32) {
     if (deferred && counts_marked && e == cudaSuccess) { e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0); counts_marked = false; }
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->pair_rd, sizeof(uint32_t) * (P + 1));
@@ -728,8 +898,10 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess && N > 0 && pal) {
-    k_unpack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_rpk, d_rpal, h->read_bits, N, p->rd_aq, p->d_bad);
+  if (p->sl_full) {
+    // unpacked per slice by the caller
+  } else if (e == cudaSuccess && N > 0 && pal) {
+    k_unpack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_rpk, d_rpal, h->read_bits, 0, N, p->rd_aq, p->d_bad);
     ctx->launches++;
     e = cudaGetLastError();
   } else if (e == cudaSuccess && N > 0) {

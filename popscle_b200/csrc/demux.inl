@@ -1378,6 +1378,7 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
   const auto t2 = now();
   bool keep = ctx->keep_grid;
   int bad = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tl_groups;  // PSCL_TIMELINE: start / end of every group's scoring
   if (plp->n_slices > 1) {
     // the gaps of slice k are decoded as soon as they have landed; the cells are scored in `groups` launches (a launch per
     // slice would leave the persistent kernel's 1184 warps with two or three work items each)
@@ -1388,7 +1389,14 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
     for (int k = 0; k < plp->n_slices && rc == PSCL_OK; ++k) {
       const int32_t c0 = plp->stage_cell[k], c1 = plp->stage_cell[k + 1];
       cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->slice_ev[k], 0);
-      if (e == cudaSuccess && c1 > c0) {
+      if (e == cudaSuccess && c1 > c0 && plp->sl_full) {  // everything of the slice's cells in one launch: ids, offsets, base-calls
+        k_decode_cells<<<(unsigned)(c1 - c0), PSCL_DEC8_NT, 0, ctx->stream>>>(plp->cell_ptr + c0, plp->d_first + c0, plp->d_delta8, plp->d_gap_big, plp->d_cell_gap_ptr + c0,
+                                                                         plp->n_gap_big, plp->sl_n2, plp->sl_nbig, plp->sl_nblk, plp->sl_n_big, plp->sl_cell_rd + c0,
+                                                                         plp->sl_rpk, plp->sl_rpal, plp->sl_read_bits, plp->N, c1 - c0, plp->V, plp->pair_snp, plp->pair_rd,
+                                                                         plp->rd_aq, plp->d_bad);
+        ctx->launches++;
+        e = cudaGetLastError();
+      } else if (e == cudaSuccess && c1 > c0) {
         const unsigned grid = (unsigned)(((int64_t)(c1 - c0) * 32 + 255) / 256);
         if (plp->d_delta8) k_decode_snp8<<<(unsigned)(c1 - c0), PSCL_DEC8_NT, 0, ctx->stream>>>(plp->cell_ptr + c0, plp->d_first + c0, plp->d_delta8, plp->d_gap_big, plp->d_cell_gap_ptr + c0,
                                                                         plp->n_gap_big, c1 - c0, plp->V, plp->pair_snp, plp->d_bad);
@@ -1400,7 +1408,10 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
       const bool group_end = (k + 1) * groups / plp->n_slices != k * groups / plp->n_slices || k + 1 == plp->n_slices;
       if (group_end && c1 > g0) {
         if (timeline && k + 1 == plp->n_slices) cudaEventRecord(ctx->tl[6], ctx->stream);
+        cudaEvent_t ga = nullptr, gb = nullptr;
+        if (timeline && tl_groups.size() < 32) { cudaEventCreate(&ga); cudaEventCreate(&gb); cudaEventRecord(ga, ctx->stream); }
         rc = demux_score_impl(ctx, plp, opts, g0, c1, 0, host->n_cells, true, alpha_set);
+        if (ga) { cudaEventRecord(gb, ctx->stream); tl_groups.push_back({ga, gb}); }
         g0 = c1;
       }
     }
@@ -1424,6 +1435,12 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
     float v[8] = {0};
     cudaEvent_t evs[8] = {ctx->tl[1], ctx->tl[2], ctx->tl[3], ctx->tl[4], ctx->ev1, ctx->ev2, ctx->tl[5], ctx->tl[6]};
     for (int i = 0; i < 8; ++i) if (cudaEventElapsedTime(&v[i], ctx->tl[0], evs[i]) != cudaSuccess) { v[i] = -1.f; cudaGetLastError(); }
+    for (auto& g : tl_groups) {
+      float a0 = 0.f, a1 = 0.f;
+      cudaEventElapsedTime(&a0, ctx->tl[0], g.first); cudaEventElapsedTime(&a1, ctx->tl[0], g.second);
+      fprintf(stderr, "[timeline ms] group scored %.3f -> %.3f\n", a0, a1);
+      cudaEventDestroy(g.first); cudaEventDestroy(g.second);
+    }
     fprintf(stderr, "[timeline ms] arrays landed %.3f | gaps landed %.3f | geno tables %.3f | decoded %.3f | scored %.3f | epilogue %.3f | fetched %.3f | last group starts %.3f | host: %d allocator calls %.3f, enqueue %.3f, whole call %.3f\n",
             v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], t_pscl_alloc_n, t_pscl_alloc_ms, ms(th0, th1), ms(th0, std::chrono::steady_clock::now()));
   }

@@ -276,6 +276,7 @@ extern "C" int pscl_multi_demux_run(pscl_multi* m, const pscl_pileup* host, cons
     mine.resize((size_t)(c1 - c0) + 1);
     for (int64_t c = c0; c <= c1; ++c) mine[(size_t)(c - c0)] = host->cell_ptr[c] - p0;
     pscl_pileup sh = *host;
+    sh.cell_read_ptr = nullptr;  // (global offsets: a shard view is uploaded whole)
     sh.n_cells = (int32_t)(c1 - c0); sh.n_pairs = p1 - p0; sh.n_reads = rcut[r + 1] - rcut[r];
     sh.cell_ptr = mine.data();
     if (host->pair_snp) sh.pair_snp = host->pair_snp + p0;

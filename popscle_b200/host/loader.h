@@ -114,6 +114,7 @@ struct Loaded {
   mutable std::vector<uint32_t> snp_gap_big;
   mutable std::vector<int64_t> cell_gap_big_ptr, nreads_big_ptr;
   mutable std::vector<uint8_t> read_packed, read_palette;  // ABI 6: base-calls as 4/5/6-bit palette indices
+  mutable std::vector<int64_t> cell_read_ptr;              // ABI 7: first base-call of every cell
   mutable int read_bits = 0, packed_state = 0;             // packed_state: 0 not tried, 1 usable, -1 more than 64 distinct bytes
   mutable int tiny_state = 0;   // 0 not tried, 1 usable, -1 a pair without base-calls or with >= 256 of them
   mutable int delta_state = 0;  // 0 not tried, 1 usable, -1 a gap or a count does not fit
@@ -128,7 +129,7 @@ struct Loaded {
     p.cell_first_snp = nullptr; p.pair_snp_delta16 = nullptr; p.pair_nreads8 = nullptr;
     p.pair_snp_delta8 = nullptr; p.snp_gap_big = nullptr; p.cell_gap_big_ptr = nullptr;
     p.pair_nreads2 = nullptr; p.nreads_big = nullptr; p.nreads_big_ptr = nullptr; p.n_gap_big = p.n_nreads_big = 0;
-    p.read_packed = nullptr; p.read_palette = nullptr; p.read_bits = 0; p.reserved_ = 0;
+    p.read_packed = nullptr; p.read_palette = nullptr; p.read_bits = 0; p.reserved_ = 0; p.cell_read_ptr = nullptr;
     const int T = loader_threads();
     const size_t P = pair_snp.size(), N = read_allele.size();
     auto chunks = [&](size_t n, size_t align, auto fn) {  // fn(begin, end) over [0, n) in pieces whose starts are multiples of `align`
@@ -282,6 +283,11 @@ struct Loaded {
         p.nreads_big = nreads_big.empty() ? nullptr : nreads_big.data(); p.n_nreads_big = (int64_t)nreads_big.size();
       }
     }
+    if (cell_read_ptr.size() != (size_t)n_cells + 1) {
+      cell_read_ptr.resize((size_t)n_cells + 1);
+      for (int32_t c = 0; c <= n_cells; ++c) cell_read_ptr[(size_t)c] = pair_read_ptr[(size_t)cell_ptr[(size_t)c]];
+    }
+    p.cell_read_ptr = cell_read_ptr.data();
     p.n_cells = n_cells; p.n_snps = n_snps;
     p.n_pairs = (int64_t)P; p.n_reads = (int64_t)N;
     p.cell_ptr = cell_ptr.data(); p.pair_snp = pair_snp.data(); p.pair_read_ptr = pair_read_ptr.data();

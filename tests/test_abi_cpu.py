@@ -40,7 +40,7 @@ def test_library_is_sm100a_only(built):
 
 def test_header_compiles_as_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==200 && offsetof(pscl_pileup, read_packed)==176 && offsetof(pscl_pileup, read_bits)==192 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 && offsetof(pscl_pileup, pair_snp_delta8)==112 && offsetof(pscl_pileup, nreads_big_ptr)==152 && offsetof(pscl_pileup, n_nreads_big)==168 && sizeof(pscl_geno)==56 && offsetof(pscl_geno, geno_err)==48 && sizeof(pscl_fmx_opts)==80 && offsetof(pscl_fmx_opts, seed)==56 && offsetof(pscl_fmx_opts, bf_thres)==64 && offsetof(pscl_fmx_opts, keep_init_missing)==76 ? 0 : 1; }\n')
+    src.write_text('#include "popscle_b200.h"\n#include <stddef.h>\nint main(void){ pscl_demux_cell c; pscl_fmx_cell f; return sizeof(c)==160 && sizeof(f)==160 && sizeof(pscl_pileup)==208 && offsetof(pscl_pileup, cell_read_ptr)==200 && offsetof(pscl_pileup, read_packed)==176 && offsetof(pscl_pileup, read_bits)==192 && offsetof(pscl_pileup, read_aq)==80 && offsetof(pscl_pileup, pair_nreads8)==104 && offsetof(pscl_pileup, pair_snp_delta8)==112 && offsetof(pscl_pileup, nreads_big_ptr)==152 && offsetof(pscl_pileup, n_nreads_big)==168 && sizeof(pscl_geno)==56 && offsetof(pscl_geno, geno_err)==48 && sizeof(pscl_fmx_opts)==80 && offsetof(pscl_fmx_opts, seed)==56 && offsetof(pscl_fmx_opts, bf_thres)==64 && offsetof(pscl_fmx_opts, keep_init_missing)==76 ? 0 : 1; }\n')
     exe = tmp_path / "t"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     assert subprocess.call([str(exe)]) == 0
@@ -53,7 +53,7 @@ def test_no_cpu_fallback(built):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     lib = capi.load_library()
-    assert lib.pscl_abi_version() == 6
+    assert lib.pscl_abi_version() == 7
     h = ctypes.c_void_p()
     err = ctypes.create_string_buffer(256)
     rc = lib.pscl_create(0, ctypes.byref(h), err, len(err))
@@ -86,7 +86,7 @@ def test_pileup_struct_matches_the_ctypes_mirror():
     """ABI 2/3: the compact arrays sit behind the wide ones; the ctypes mirror has the same layout."""
     import ctypes as C
     from popscle_b200 import capi
-    assert C.sizeof(capi.CPileup) == 200 and capi.CPileup.read_packed.offset == 176 and capi.CPileup.read_bits.offset == 192 and capi.CPileup.pair_snp_delta8.offset == 112 and capi.CPileup.nreads_big_ptr.offset == 152 and capi.CPileup.n_nreads_big.offset == 168
+    assert C.sizeof(capi.CPileup) == 208 and capi.CPileup.cell_read_ptr.offset == 200 and capi.CPileup.read_packed.offset == 176 and capi.CPileup.read_bits.offset == 192 and capi.CPileup.pair_snp_delta8.offset == 112 and capi.CPileup.nreads_big_ptr.offset == 152 and capi.CPileup.n_nreads_big.offset == 168
     assert capi.CPileup.cell_first_snp.offset == 88 and capi.CPileup.pair_snp_delta16.offset == 96 and capi.CPileup.pair_nreads8.offset == 104
     assert capi.CPileup.pair_read_ptr32.offset == 72 and capi.CPileup.read_aq.offset == 80
     assert C.sizeof(capi.CFmxOpts) == 80 and capi.CFmxOpts.bf_thres.offset == 64 and capi.CFmxOpts.keep_init_missing.offset == 76 and capi.CFmxOpts.randomize_singlet_score.offset == 52 and capi.CFmxOpts.seed.offset == 56

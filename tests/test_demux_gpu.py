@@ -405,13 +405,26 @@ def test_pipelined_run_is_bit_identical(ctx, slices, groups):
             os.environ["PSCL_SLICES"], os.environ["PSCL_GROUPS"] = str(slices), str(groups)
             try:
                 got = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=compact)
+                # ... and with the counts and base-calls sliced too (ABI 7's cell_read_ptr; one k_decode_cells launch per slice)
+                os.environ["PSCL_SLICE_FULL"] = "1"
+                full = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=compact)
             finally:
                 del os.environ["PSCL_SLICES"], os.environ["PSCL_GROUPS"]
+                os.environ.pop("PSCL_SLICE_FULL", None)
             assert got.tobytes() == ref.tobytes(), (type(gp).__name__, compact)
+            assert full.tobytes() == ref.tobytes(), (type(gp).__name__, compact, "full")
     bad = synth.make_pileup(C=60, nv=3, V=400, kbar=90, seed=1)
     first, d8, gbig, cbp, n2, nbig, nbp = bad.plp.compact4()
     os.environ["PSCL_SLICES"] = "3"
     try:
+        os.environ["PSCL_SLICE_FULL"] = "1"
+        try:  # a count that disagrees with the cells' base-call offsets
+            n2[bad.plp.cell_ptr[30] // 4] ^= 0x3 << (2 * (bad.plp.cell_ptr[30] % 4))
+            with pytest.raises(PsclError):
+                ctx.demux_run(bad.plp, synth.gt_to_gp(bad.geno), None, DEFAULT, compact=4)
+            n2[bad.plp.cell_ptr[30] // 4] ^= 0x3 << (2 * (bad.plp.cell_ptr[30] % 4))
+        finally:
+            del os.environ["PSCL_SLICE_FULL"]
         d8[bad.plp.cell_ptr[45] + 1] = 254  # a gap that walks the SNP id past n_snps
         d8[bad.plp.cell_ptr[45] + 2] = 254
         with pytest.raises(PsclError):
