@@ -246,13 +246,19 @@ int pscl_demux_fetch(pscl_ctx* ctx, pscl_demux_cell* out, double* llk_grid);
 /* Debug switch: keep the per-cell LLK grid on the device so pscl_demux_fetch can return it. */
 int pscl_demux_keep_grid(pscl_ctx* ctx, int enable);
 /* One-call path used by the CLI hosts: genotype table + pileup upload + score + fetch; returns with the
- * records in `out` (and the grid in `llk_grid`, if not NULL).  When `host` carries the ABI-3 delta arrays
- * and the shape is the default kernel's (alpha grid {0, 0.5}, <= 8 samples, no grid requested), the run is
- * staged: the SNP gaps cross PCIe in slices on a second stream while the one scoring launch already works
- * on the slices that have landed, so most of the kernel time hides under the copy.  Page-locked host
- * arrays (cudaHostAlloc / cudaHostRegister) make that overlap real; pageable ones give the same records
- * without it.  Environment: PSCL_STAGES=n sets the slice count (1 = no staging), PSCL_TRACE=1 prints the
- * wall-clock of every phase on stderr. */
+ * records in `out` (and the grid in `llk_grid`, if not NULL).  When `host` carries the compact arrays (ABI 3 / 6)
+ * and the shape is the default kernel's (alpha grid {0, 0.5}, <= 8 samples, no grid requested), a pileup of
+ * >= 4 M pairs is run PIPELINED: every copy of the call is queued on a second stream at once (small arrays,
+ * counts, base-calls, then the SNP gaps in slices of whole cells), the genotype tables are built and the
+ * counts / base-calls decoded under the copies, every slice's gaps are decoded as they land and the cells
+ * scored in groups of slices, and the records come back with the image's validity flag in one read (one host
+ * drain per call).  Page-locked host arrays (cudaHostAlloc / cudaHostRegister), `out` included, make the
+ * overlap real; pageable ones give the same records without it.  The records are the bytes of the one-shot
+ * run whatever the slicing.  Environment (none needed): PSCL_SLICES=n / PSCL_GROUPS=g force and shape the
+ * pipeline at any size (1 = off), PSCL_SLICE_FULL=1 slices counts and base-calls too (needs ABI 7's
+ * cell_read_ptr or the offsets), PSCL_STAGES=n selects the older form instead (one scoring launch whose warps
+ * decode the gaps and wait on a flag word per slice), PSCL_TRACE=1 prints the wall-clock of every phase and
+ * PSCL_TIMELINE=1 the device time stamps of the call on stderr. */
 int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_geno* geno,
                    const pscl_demux_opts* opts, pscl_demux_cell* out, double* llk_grid);
 /* Device time (ms, CUDA events on pscl_stream) of the kernels of the last pscl_demux_score. */
