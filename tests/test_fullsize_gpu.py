@@ -120,3 +120,18 @@ def test_config3_freemuxlet_sharded_equals_unsharded_and_recovers_donors(ctx):
         check_fmx_parity(a, full, allow_tied_frac=0.05)
     finally:
         ctxs[1].close()
+
+
+def test_config3_greedy_seeding_and_em_match_the_oracle_at_full_size(ctx):
+    """configs[2] the way the default command runs it — stage 1, greedy seeding over all 10 k cells (speculative batches on the
+    device, the serial chain in the oracle), two EM iterations — against the CPU oracle on all host threads: the same initial
+    cluster of every cell, the same types and ids, LLKs within tolerance (full size, not 400 cells)."""
+    import os
+    s = synth.make_config(3)
+    kw = dict(early_stop=False, max_iter=2)
+    cells, res, _, _ = ctx.fmx_run(s.plp, ctx.fmx_opts(8, **kw), compact=4)
+    r = orc.fmx_run(s.plp, orc.fmx_opts(8, **kw), n_threads=max(1, os.cpu_count() or 1))
+    assert np.array_equal(cells["init_clust"], r["cells"]["init_clust"])
+    check_fmx_parity(cells, r["cells"])
+    assert res.n_iter == r["res"].n_iter and res.n_singlet == r["res"].n_singlet
+    assert (np.bincount(cells["init_clust"], minlength=8) > 1000).all()
