@@ -274,6 +274,13 @@ int64_t pscl_launch_count(const pscl_ctx* ctx);
 int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts,
                  const int32_t* init_clust, pscl_fmx_cell* out, double* clust_gl,
                  int32_t* clust_cnt, pscl_fmx_result* res);
+/* ABI 7: the same run, which also hands back the cluster pileups of the INITIAL assignment (after the seeding, before the
+ * first E-step) in `clust_gl0` / `clust_cnt0` (nullable, shaped like clust_gl / clust_cnt): what `--aux-files` writes to
+ * <out>.clust0.vcf.gz (cmd_cram_freemux2.cpp:277-347); the initial clusters of <out>.clust0.samples.gz (:265-274) are
+ * pscl_fmx_cell.init_clust. */
+int pscl_fmx_run_aux(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts,
+                     const int32_t* init_clust, pscl_fmx_cell* out, double* clust_gl,
+                     int32_t* clust_cnt, pscl_fmx_result* res, double* clust_gl0, int32_t* clust_cnt0);
 
 /* Step-level API for SNP-sharded multi-GPU EM: each rank uploads the pairs of its
  * SNP range (cells keep global ids), and the caller all-reduces the per-cell partial sums between

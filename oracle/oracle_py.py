@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
         L.orc_fmx_merge.argtypes = [vp, vp, vp, vp, vp, C.c_double]
         L.orc_fmx_run.restype = C.c_int
         L.orc_fmx_run.argtypes = [C.POINTER(OPileup), C.POINTER(OFmxOpts), vp, vp, vp, vp, C.POINTER(OFmxResult), vp, vp, C.c_int]
+        L.orc_fmx_run_aux.restype = C.c_int
+        L.orc_fmx_run_aux.argtypes = [C.POINTER(OPileup), C.POINTER(OFmxOpts), vp, vp, vp, vp, C.POINTER(OFmxResult), C.c_int, vp, vp]
         L.orc_fmx_estep.restype = C.c_int
         L.orc_fmx_estep.argtypes = [C.POINTER(OPileup), vp, vp, C.c_int, C.c_double, C.c_int, C.c_int, vp, C.c_int]
         _lib = L
@@ -169,6 +171,21 @@ def fmx_run(plp, opts, init_clust=None, want_clusters=False, want_pair_gl=False,
     rc = L.orc_fmx_run(C.byref(cs), C.byref(opts), _p(ic), _p(out), _p(gl), _p(cnt), C.byref(res), _p(pgl), _p(llk), n_threads)
     assert rc == 0, rc
     return dict(cells=out, res=res, clust_gl=gl, clust_cnt=cnt, pair_gl=pgl, llk=llk)
+
+
+def fmx_run_aux(plp, opts, init_clust=None, n_threads=1):
+    """orc_fmx_run_aux: the run + the cluster pileups of the initial assignment (--aux-files)."""
+    L = lib()
+    out = np.zeros(plp.n_cells, dtype=FMX_CELL_DTYPE)
+    res = OFmxResult()
+    ic = np.ascontiguousarray(init_clust, dtype=np.int32) if init_clust is not None else None
+    nS = opts.n_clusters
+    gl, gl0 = np.empty((plp.n_snps, nS, 9)), np.empty((plp.n_snps, nS, 9))
+    cnt, cnt0 = np.empty((plp.n_snps, nS, 3), dtype=np.int32), np.empty((plp.n_snps, nS, 3), dtype=np.int32)
+    cs = plp.c_struct(OPileup)
+    rc = L.orc_fmx_run_aux(C.byref(cs), C.byref(opts), _p(ic), _p(out), _p(gl), _p(cnt), C.byref(res), n_threads, _p(gl0), _p(cnt0))
+    assert rc == 0, rc
+    return out, res, gl, cnt, gl0, cnt0
 
 
 def fmx_estep(plp, pair_gl, clust_gl, nS, geno_error, cell_begin=0, cell_end=None, n_threads=1):

@@ -368,9 +368,24 @@ static int cmp_drop(const void* a, const void* b) {
   return lhs > rhs ? -1 : (lhs < rhs ? 1 : 0);
 }
 
+static int fmx_run_impl(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* init_clust, orc_fmx_cell* out,
+                        double* clust_gl_out, int32_t* clust_cnt_out, orc_fmx_result* res, double* pair_gl_out,
+                        double* llk_last, int n_threads, double* clust_gl0, int32_t* clust_cnt0);
 int orc_fmx_run(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* init_clust, orc_fmx_cell* out,
                 double* clust_gl_out, int32_t* clust_cnt_out, orc_fmx_result* res, double* pair_gl_out,
                 double* llk_last, int n_threads) {
+  return fmx_run_impl(plp, o, init_clust, out, clust_gl_out, clust_cnt_out, res, pair_gl_out, llk_last, n_threads, NULL, NULL);
+}
+/* the same run; clust_gl0 / clust_cnt0 (nullable) receive the cluster pileups of the initial assignment — what --aux-files
+ * writes to <out>.clust0.vcf.gz (cmd_cram_freemux2.cpp:277-347) */
+int orc_fmx_run_aux(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* init_clust, orc_fmx_cell* out,
+                    double* clust_gl_out, int32_t* clust_cnt_out, orc_fmx_result* res, int n_threads,
+                    double* clust_gl0, int32_t* clust_cnt0) {
+  return fmx_run_impl(plp, o, init_clust, out, clust_gl_out, clust_cnt_out, res, NULL, NULL, n_threads, clust_gl0, clust_cnt0);
+}
+static int fmx_run_impl(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* init_clust, orc_fmx_cell* out,
+                        double* clust_gl_out, int32_t* clust_cnt_out, orc_fmx_result* res, double* pair_gl_out,
+                        double* llk_last, int n_threads, double* clust_gl0, int32_t* clust_cnt0) {
   if (!plp || !o || !out || o->n_clusters < 1) return -1;
   phred_init();
   const int C = plp->n_cells, V = plp->n_snps, nS = o->n_clusters;
@@ -556,6 +571,8 @@ int orc_fmx_run(const orc_pileup* plp, const orc_fmx_opts* o, const int32_t* ini
   tab_clear(&tab);
   for (int32_t c = 0; c < C; ++c)
     if (clusts[c] >= 0) tab_merge_cell(&tab, clusts[c], plp, c, pair_gl, pair_cnt, pair_ld);
+  if (clust_gl0) memcpy(clust_gl0, tab.gls, sizeof(double) * (size_t)V * nS * 9);   /* --aux-files, :291-347 */
+  if (clust_cnt0) memcpy(clust_cnt0, tab.cnt, sizeof(int32_t) * (size_t)V * nS * 3);
 
   for (int32_t c = 0; c < C; ++c) { /* :350-370 */
     orc_fmx_cell* r = &out[c];

@@ -103,6 +103,10 @@ void orc_fmx_merge(double* gls_a, int32_t* cnt_a, double* logdenom_a, const doub
 int orc_fmx_run(const orc_pileup* plp, const orc_fmx_opts* opts, const int32_t* init_clust,
                 orc_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, orc_fmx_result* res,
                 double* pair_gl, double* llk_last, int n_threads);
+/* the same run + the cluster pileups of the initial assignment (--aux-files, cmd_cram_freemux2.cpp:277-347) */
+int orc_fmx_run_aux(const orc_pileup* plp, const orc_fmx_opts* opts, const int32_t* init_clust,
+                    orc_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, orc_fmx_result* res, int n_threads,
+                    double* clust_gl0, int32_t* clust_cnt0);
 
 /* one E-step over cells [cell_begin,cell_end) given a dense cluster table [V][nS][9]
  * (cmd_cram_freemux2.cpp:383-456) — used as the timed CPU baseline unit for freemuxlet */

@@ -327,6 +327,7 @@ def load_library() -> C.CDLL:
         "pscl_demux_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "pscl_demux_last_kernel": (C.c_int, [vp]),
         "pscl_fmx_run": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult)]),
+        "pscl_fmx_run_aux": (C.c_int, [vp, C.POINTER(CPileup), C.POINTER(CFmxOpts), vp, vp, vp, vp, C.POINTER(CFmxResult), vp, vp]),
         "pscl_fmx_init": (C.c_int, [vp, vp, C.POINTER(CFmxOpts)]),
         "pscl_fmx_stage1": (C.c_int, [vp, vp]),
         "pscl_fmx_seed": (C.c_int, [vp, vp, vp, vp]),
@@ -357,7 +358,7 @@ EXPORTED_SYMBOLS = [
     "pscl_abi_version", "pscl_create", "pscl_destroy", "pscl_last_error", "pscl_stream", "pscl_set_stream",
     "pscl_sync", "pscl_launch_count", "pscl_set_partial_budget", "pscl_debug_fail_alloc", "pscl_plp_upload", "pscl_plp_free",
     "pscl_demux_set_geno", "pscl_demux_score", "pscl_demux_fetch", "pscl_demux_keep_grid",
-    "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_demux_last_kernel", "pscl_fmx_run", "pscl_fmx_init",
+    "pscl_demux_force_general", "pscl_demux_select_kernel", "pscl_demux_run", "pscl_demux_last_kernel_ms", "pscl_demux_last_kernel", "pscl_fmx_run", "pscl_fmx_run_aux", "pscl_fmx_init",
     "pscl_fmx_stage1", "pscl_fmx_seed", "pscl_fmx_mstep", "pscl_fmx_estep", "pscl_fmx_classify",
     "pscl_fmx_fetch", "pscl_fmx_last_kernel_ms",
     "pscl_multi_create", "pscl_multi_destroy", "pscl_multi_last_error", "pscl_multi_size", "pscl_multi_ctx",
@@ -549,6 +550,20 @@ class Context:
                                         out.ctypes.data, gl.ctypes.data if gl is not None else None,
                                         cnt.ctypes.data if cnt is not None else None, C.byref(res)))
         return out, res, gl, cnt
+
+    def fmx_run_aux(self, plp: Pileup, opts: CFmxOpts, init_clust: np.ndarray | None = None, compact: bool = False):
+        """pscl_fmx_run_aux: the whole run + the cluster pileups of the initial assignment (--aux-files):
+        (cells, result, clust_gl, clust_cnt, clust_gl0, clust_cnt0)."""
+        cs = plp.c_struct(compact=compact)
+        out = np.zeros(plp.n_cells, dtype=FMX_CELL_DTYPE)
+        res = CFmxResult()
+        ic = np.ascontiguousarray(init_clust, dtype=np.int32) if init_clust is not None else None
+        shape = (plp.n_snps, opts.n_clusters)
+        gl, gl0 = np.empty(shape + (9,), dtype=np.float64), np.empty(shape + (9,), dtype=np.float64)
+        cnt, cnt0 = np.empty(shape + (3,), dtype=np.int32), np.empty(shape + (3,), dtype=np.int32)
+        self._chk(self.lib.pscl_fmx_run_aux(self.h, C.byref(cs), C.byref(opts), ic.ctypes.data if ic is not None else None, out.ctypes.data,
+                                            gl.ctypes.data, cnt.ctypes.data, C.byref(res), gl0.ctypes.data, cnt0.ctypes.data))
+        return out, res, gl, cnt, gl0, cnt0
 
     # step-level freemuxlet API (SNP-sharded EM): *_dev arguments are raw device pointers (ints)
     def fmx_init(self, dplp: "DevicePileup", opts: CFmxOpts):

@@ -167,10 +167,24 @@ def _freemux(argv, old, engine=None):
                             frac_init_clust=o["frac-init-clust"], singlet_score_thres=-1e300, mode_old=old,
                             randomize_singlet_score=bool(o.get("randomize-singlet-score", False)), seed=int(o.get("seed", 0) or 0),
                             **(dict(bf_thres=o["bf-thres"], iter_init=o["iter-init"], keep_init_missing=o["keep-init-missing"]) if old else {}))
-        cells, res, gl, cnt = eng.fmx_run(L.plp, opts, init, want_clusters=True)
+        gl0 = cnt0 = None
+        if o["aux-files"]:
+            # .clust0.samples.gz / .clust0.vcf.gz (cmd_cram_freemux2.cpp:265-347).  freemuxlet-old's aux files are dumps of its
+            # pairwise distance matrix (.ldist.gz, cmd_cram_freemuxlet.cpp:176-181, :348-430), which this engine never
+            # materialises (two bits per droplet pair on the device)
+            if old:
+                raise UsageError("--aux-files is not supported by freemuxlet-old here (its .ldist dumps need the pairwise distance matrix)")
+            if not hasattr(eng, "fmx_run_aux"):
+                raise UsageError("--aux-files needs a single GPU (--gpus 1)")
+            cells, res, gl, cnt, gl0, cnt0 = eng.fmx_run_aux(L.plp, opts, init)
+        else:
+            cells, res, gl, cnt = eng.fmx_run(L.plp, opts, init, want_clusters=True)
     finally:
         if own:
             eng.close()
+    if gl0 is not None:
+        report.write_clust0_samples(o["out"] + ".clust0.samples.gz", cells, L.barcodes)
+        report.write_clust_vcf(o["out"] + ".clust0.vcf.gz", L.sites, L.rid2chr, gl0, cnt0, report.observed_snps(L.plp), initial=True)
     report.write_lmix(o["out"] + ".lmix", cells, L.barcodes, old=old)
     report.write_clust_samples(o["out"] + ".clust1.samples.gz", cells, L.barcodes)
     report.write_clust_vcf(o["out"] + ".clust1.vcf.gz", L.sites, L.rid2chr, gl, cnt, report.observed_snps(L.plp))

@@ -2280,8 +2280,17 @@ extern "C" int pscl_fmx_last_kernel_ms(pscl_ctx* ctx, float* ms) {
   return PSCL_OK;
 }
 
+extern "C" int pscl_fmx_run_aux(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts, const int32_t* init_clust,
+                                pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, pscl_fmx_result* res,
+                                double* clust_gl0, int32_t* clust_cnt0);
 extern "C" int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts, const int32_t* init_clust,
                             pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, pscl_fmx_result* res) {
+  return pscl_fmx_run_aux(ctx, host, opts, init_clust, out, clust_gl, clust_cnt, res, nullptr, nullptr);
+}
+
+extern "C" int pscl_fmx_run_aux(pscl_ctx* ctx, const pscl_pileup* host, const pscl_fmx_opts* opts, const int32_t* init_clust,
+                                pscl_fmx_cell* out, double* clust_gl, int32_t* clust_cnt, pscl_fmx_result* res,
+                                double* clust_gl0, int32_t* clust_cnt0) {
   if (!ctx) return PSCL_EINVAL;
   PsclScope scope__(ctx);
   if (!host || !opts || !out) return pscl_fail(ctx, PSCL_EINVAL, "pscl_fmx_run: NULL argument");
@@ -2306,6 +2315,8 @@ extern "C" int pscl_fmx_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl_f
     if ((r = pscl_fmx_stage1(ctx, s->own_stage1)) != PSCL_OK) return r;
     if ((r = pscl_fmx_seed(ctx, s->own_stage1, d_init, s->own_clust)) != PSCL_OK) return r;
     if ((r = pscl_fmx_mstep(ctx, s->own_clust)) != PSCL_OK) return r;  // :277-288
+    // --aux-files: the cluster pileups of the initial assignment, as the reference writes them to .clust0.vcf.gz (:291-347)
+    if ((clust_gl0 || clust_cnt0) && (r = pscl_fmx_fetch(ctx, nullptr, clust_gl0, clust_cnt0)) != PSCL_OK) return r;
     pscl_fmx_result rr;
     memset(&rr, 0, sizeof(rr));
     for (int iter = 0; iter < s->o.max_iter; ++iter) {

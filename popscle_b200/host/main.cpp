@@ -93,8 +93,10 @@ struct Engine {
   void demux_run(const pscl_pileup* v, const pscl_geno* g, const pscl_demux_opts* o, pscl_demux_cell* out) {
     chk(m ? pscl_multi_demux_run(m, v, g, o, out, NULL) : pscl_demux_run(h, v, g, o, out, NULL));
   }
-  void fmx_run(const pscl_pileup* v, const pscl_fmx_opts* o, const int32_t* init, pscl_fmx_cell* out, double* gl, int32_t* cnt, pscl_fmx_result* res) {
-    chk(m ? pscl_multi_fmx_run(m, v, o, init, out, gl, cnt, res) : pscl_fmx_run(h, v, o, init, out, gl, cnt, res));
+  void fmx_run(const pscl_pileup* v, const pscl_fmx_opts* o, const int32_t* init, pscl_fmx_cell* out, double* gl, int32_t* cnt, pscl_fmx_result* res,
+               double* gl0 = nullptr, int32_t* cnt0 = nullptr) {
+    if (m && (gl0 || cnt0)) throw host_error("--aux-files needs a single GPU (--gpus 1)");
+    chk(m ? pscl_multi_fmx_run(m, v, o, init, out, gl, cnt, res) : pscl_fmx_run_aux(h, v, o, init, out, gl, cnt, res, gl0, cnt0));
   }
 };
 
@@ -226,7 +228,9 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   else { p.add("min-umi", &minUMI); p.add("randomize-singlet-score", &randomize); p.add("seed", &seed); }
   p.read(argc, argv);
   if (plp.empty() || out.empty() || nSamples == 0) throw host_error("Missing required option(s) : --plp, --out, --nsample");
-  if (auxFiles) throw host_error("--aux-files (clust0 / ldist debug outputs) is not supported");
+  // --aux-files: .clust0.samples.gz / .clust0.vcf.gz (cmd_cram_freemux2.cpp:265-347).  freemuxlet-old's aux files are dumps of its
+  // pairwise distance matrix (.ldist.gz, cmd_cram_freemuxlet.cpp:176-181, :348-430), which this engine never materialises
+  if (auxFiles && old_mode) throw host_error("--aux-files is not supported by freemuxlet-old here (its .ldist dumps need the pairwise distance matrix)");
   LoadOptions lo;
   lo.plp_prefix = plp;
   if (old_mode) {
@@ -271,12 +275,17 @@ int cmd_freemux(int argc, char** argv, bool old_mode) {
   pscl_fmx_opts o = {nSamples, doubletPrior, genoError, 10, 1, fracInitClust, -1e300, old_mode ? 1 : 0, randomize ? 1 : 0, seed,
                      bfThres, old_mode ? initIteration : 0, keepInitMissing ? 1 : 0};
   std::vector<pscl_fmx_cell> cells((size_t)L.n_cells);
-  std::vector<double> gl((size_t)L.n_snps * nSamples * 9);
-  std::vector<int32_t> cnt((size_t)L.n_snps * nSamples * 3);
+  std::vector<double> gl((size_t)L.n_snps * nSamples * 9), gl0(auxFiles ? gl.size() : 0);
+  std::vector<int32_t> cnt((size_t)L.n_snps * nSamples * 3), cnt0(auxFiles ? cnt.size() : 0);
   pscl_fmx_result res;
   if (eng.n_gpus() > 1) notice("Sharding %d variants over %d GPUs by pair count", L.n_snps, eng.n_gpus());
-  eng.fmx_run(&view, &o, init.empty() ? NULL : init.data(), cells.data(), gl.data(), cnt.data(), &res);
+  eng.fmx_run(&view, &o, init.empty() ? NULL : init.data(), cells.data(), gl.data(), cnt.data(), &res, auxFiles ? gl0.data() : NULL,
+              auxFiles ? cnt0.data() : NULL);
   trace_lap("popscle", "fmx_run");
+  if (auxFiles) {
+    write_clust0_samples(out + ".clust0.samples.gz", L, cells);
+    write_clust_vcf(out + ".clust0.vcf.gz", L, nSamples, gl0, cnt0, true);
+  }
   notice("Finished %d EM iterations: %d singlets, %d doublets, %d ambiguous, and %d changed", res.n_iter, res.n_singlet, res.n_doublet,
          res.n_ambiguous, res.n_changed);
   write_lmix(out + ".lmix", L, cells, old_mode);

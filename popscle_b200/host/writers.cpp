@@ -99,8 +99,14 @@ void write_clust_samples(const std::string& path, const Loaded& L, const std::ve
   }
 }
 
+void write_clust0_samples(const std::string& path, const Loaded& L, const std::vector<pscl_fmx_cell>& cells) {
+  Out w(path, true);
+  w.printf("INT_ID\tBARCODE\tCLUST0\n");
+  for (int32_t i = 0; i < L.n_cells; ++i) w.printf("%d\t%s\t%d\n", i, L.barcodes[i].c_str(), cells[i].init_clust);
+}
+
 void write_clust_vcf(const std::string& path, const Loaded& L, int nS, const std::vector<double>& clust_gl,
-                     const std::vector<int32_t>& clust_cnt) {
+                     const std::vector<int32_t>& clust_cnt, bool initial) {
   Out w(path, true);
   time_t now = std::time(NULL);
   tm* ltm = localtime(&now);
@@ -133,10 +139,11 @@ void write_clust_vcf(const std::string& path, const Loaded& L, int nS, const std
       if (maxGL < gl[8]) maxGL = gl[8];
       int32_t pls[3] = {(int32_t)(-10.0 * log10(gl[0] / maxGL)), (int32_t)(-10.0 * log10(gl[4] / maxGL)), (int32_t)(-10.0 * log10(gl[8] / maxGL))};
       double pps[3] = {gps[0] * (gl[0] / maxGL) + 1e-100, gps[1] * (gl[4] / maxGL) + 1e-100, gps[2] * (gl[8] / maxGL) + 1e-100};
+      if (initial) { pps[0] = gps[0] * gl[0] / maxGL + 1e-100; pps[1] = gps[1] * gl[4] / maxGL + 1e-100; pps[2] = gps[2] * gl[8] / maxGL + 1e-100; }  // :327-329
       const double sumPP = pps[0] + pps[1] + pps[2];
       pps[0] /= sumPP; pps[1] /= sumPP; pps[2] /= sumPP;
       const int bestG = (pps[0] > pps[1]) ? (pps[0] > pps[2] ? 0 : 2) : (pps[1] > pps[2] ? 1 : 2);
-      int gq = (int32_t)(-10 * log10(1.0 - pps[bestG] + 1e-100));
+      int gq = initial ? (int)(-0.1 * log10(1 - pps[bestG] + 1e-100)) : (int32_t)(-10 * log10(1.0 - pps[bestG] + 1e-100));  // :341 (sic) / :652
       if (gq > 255) gq = 255;
       w.printf("\t%d/%d:%d:%d:%d,%d:%d,%d,%d:%.3lg,%.3lg,%.3lg", bestG == 2 ? 1 : 0, bestG > 0 ? 1 : 0, gq, n[0], n[1], n[2], pls[0], pls[1],
                pls[2], pps[0], pps[1], pps[2]);

@@ -95,8 +95,10 @@ def write_clust_samples(path, cells, barcodes):
             f.write(row)
 
 
-def clust_vcf_rows(sites, clust_gl, clust_cnt, observed):
-    """Per-cluster GT:GQ:DP:AD:PL:GP from the diagonal cluster GLs (cmd_cram_freemux2.cpp:623-656)."""
+def clust_vcf_rows(sites, clust_gl, clust_cnt, observed, initial=False):
+    """Per-cluster GT:GQ:DP:AD:PL:GP from the diagonal cluster GLs (cmd_cram_freemux2.cpp:623-656).  initial = the rows of
+    --aux-files' .clust0.vcf.gz (:316-344), which differ in two details: the posterior is (prior * GL) / maxGL rather than
+    prior * (GL / maxGL), and GQ is -0.1 * log10 (sic) rather than -10 * log10."""
     V, nS = clust_gl.shape[0], clust_gl.shape[1]
     for v in range(V):
         if not observed[v]:
@@ -108,18 +110,18 @@ def clust_vcf_rows(sites, clust_gl, clust_cnt, observed):
             g = (float(clust_gl[v, i, 0]), float(clust_gl[v, i, 4]), float(clust_gl[v, i, 8]))
             mx = max(g)
             pls = [int(-10.0 * math.log10(x / mx)) for x in g]
-            pps = [gps[k] * (g[k] / mx) + 1e-100 for k in range(3)]
+            pps = [(gps[k] * g[k] / mx if initial else gps[k] * (g[k] / mx)) + 1e-100 for k in range(3)]
             s = pps[0] + pps[1] + pps[2]
             pps = [x / s for x in pps]
             best = (0 if pps[0] > pps[2] else 2) if pps[0] > pps[1] else (1 if pps[1] > pps[2] else 2)
-            gq = min(int(-10 * math.log10(1.0 - pps[best] + 1e-100)), 255)
+            gq = min(int((-0.1 if initial else -10) * math.log10(1.0 - pps[best] + 1e-100)), 255)
             n = clust_cnt[v, i]
             out.append("\t%d/%d:%d:%d:%d,%d:%d,%d,%d:%.3g,%.3g,%.3g" % (1 if best == 2 else 0, 1 if best > 0 else 0, gq, n[0], n[1], n[2],
                                                                         pls[0], pls[1], pls[2], pps[0], pps[1], pps[2]))
         yield "".join(out) + "\n"
 
 
-def write_clust_vcf(path, sites, rid2chr, clust_gl, clust_cnt, observed, now=None):
+def write_clust_vcf(path, sites, rid2chr, clust_gl, clust_cnt, observed, now=None, initial=False):
     nS = clust_gl.shape[1]
     ltm = time.localtime(now)
     with gzip.open(path, "wt") as f:
@@ -137,8 +139,16 @@ def write_clust_vcf(path, sites, rid2chr, clust_gl, clust_cnt, observed, now=Non
         f.write('##FORMAT=<ID=PL,Number=G,Type=Integer,Description="Phred-scale genotype likelihood">\n')
         f.write('##FORMAT=<ID=GP,Number=G,Type=Float,Description="Posterior probability using pooled allele frequencies">\n')
         f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT" + "".join("\tCLUST%d" % i for i in range(nS)) + "\n")
-        for row in clust_vcf_rows(sites, clust_gl, clust_cnt, observed):
+        for row in clust_vcf_rows(sites, clust_gl, clust_cnt, observed, initial=initial):
             f.write(row)
+
+
+def write_clust0_samples(path, cells, barcodes):
+    """--aux-files: the initial cluster of every droplet, -1 = none (cmd_cram_freemux2.cpp:265-274)"""
+    with gzip.open(path, "wt") as f:
+        f.write("INT_ID\tBARCODE\tCLUST0\n")
+        for i, b in enumerate(barcodes):
+            f.write("%d\t%s\t%d\n" % (i, b, int(cells["init_clust"][i])))
 
 
 def observed_snps(plp) -> np.ndarray:

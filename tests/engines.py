@@ -18,5 +18,8 @@ class OracleEngine:
         r = orc.fmx_run(plp, opts, init_clust, want_clusters=want_clusters, n_threads=self.n_threads)
         return r["cells"], r["res"], r["clust_gl"], r["clust_cnt"]
 
+    def fmx_run_aux(self, plp, opts, init_clust=None, compact=False):
+        return orc.fmx_run_aux(plp, opts, init_clust, n_threads=self.n_threads)
+
     def close(self):
         pass

@@ -69,10 +69,16 @@ def main():
     if only:
         return main_only(only)
     main_all()
-    main_only({"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21", "fmx_old_seed", "fmx_old_refine", "fmx_old_frac"})
+    main_only({"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21", "fmx_old_seed", "fmx_old_refine", "fmx_old_frac", "fmx_aux"})
 
 
 def main_only(only):
+    # 17. freemuxlet --aux-files: the initial clusters (.clust0.samples.gz, -1 for the droplets beyond --frac-init-clust) and the
+    # cluster pileups built from them (.clust0.vcf.gz) beside the usual outputs (cmd_cram_freemux2.cpp:265-347)
+    if "fmx_aux" in only:
+        d = fresh("fmx_aux")
+        base(130, 4, 800, 210, 23, d, allele2=0.02)
+        run_ref(d, ["freemuxlet", "--plp", "p", "--nsample", "4", "--aux-files", "--frac-init-clust", "0.7", "--out", "ref"])
     # 9. demuxlet with --geno-error-coeff: per-site INFO/R2 scales the genotype error (sc_drop_seq.cpp:299-306)
     if "demux_r2" in only:
         d = fresh("demux_r2")
@@ -136,7 +142,7 @@ def main_only(only):
         d = fresh("fmx_old_frac")
         base(90, 3, 600, 180, 28, d)
         run_ref(d, ["freemuxlet-old", "--plp", "p", "--nsample", "3", "--frac-init-clust", "0.5", "--iter-init", "0", "--out", "ref"])
-    unknown = only - {"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21", "fmx_old_seed", "fmx_old_refine", "fmx_old_frac"}
+    unknown = only - {"demux_r2", "fmx_random", "demux_gt8", "demux_gp8", "demux_64x21", "fmx_old_seed", "fmx_old_refine", "fmx_old_frac", "fmx_aux"}
     if unknown:
         sys.exit(f"cases {sorted(unknown)} are generated by the full run only")
 
