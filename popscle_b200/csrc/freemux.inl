@@ -21,7 +21,7 @@
 // per pair kernels read 9 coalesced streams) and record-major [P][9] in SNP-major order (the M-step
 // walks one SNP's cells as one contiguous block).
 
-#define PSCL_FMX_MAX_CLUSTERS 24
+#define PSCL_FMX_MAX_CLUSTERS 32  /* the 32-bit cluster masks of the speculative seeding; the reference has no cap */
 #define PSCL_MIN_NORM_GL 1e-6 /* sc_drop_seq.h:14 */
 
 struct pscl_fmx_state {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(1024, 1) k_fmx_seed(SeedArgs a) {
   __shared__ int s_choice;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nS = a.nS;
-  const int wpc = 32 / nS;            // warps per cluster (nS <= 24 < 32)
+  const int wpc = 32 / nS;            // warps per cluster (nS <= 32)
   const int my_j = warp / wpc, my_w = warp % wpc;
   const bool active = my_j < nS;
   for (int i = 0; i < a.C; ++i) {
@@ -2023,7 +2023,9 @@ extern "C" int pscl_fmx_seed(pscl_ctx* ctx, const double* stage1_dev, const int3
       ctx->launches++;
       e = cudaMemsetAsync(s->present, 0, VS, ctx->stream);
     }
-    const bool serial = getenv("PSCL_SEED_SERIAL") != nullptr;  // the one-CTA chain (kept as the cross-check of the batched form)
+    // the one-CTA chain (kept as the cross-check of the batched forms; also what a state seeded a second time takes beyond 24
+    // clusters, where the older batched form's 24-bit cluster mask ends)
+    const bool serial = getenv("PSCL_SEED_SERIAL") != nullptr || (s->nS > 24 && (getenv("PSCL_SEED_V2") || !s->csc_pos));
     if (e == cudaSuccess && serial) {
       SeedArgs a;
       a.order = s->order; a.score = score; a.cell_ptr = plp->cell_ptr; a.pair_snp = plp->pair_snp; a.gl_soa = s->gl_soa;
@@ -2213,6 +2215,14 @@ extern "C" int pscl_fmx_estep(pscl_ctx* ctx, int32_t iter, double* llk_dev) {
         if (rc == PSCL_OK && nS > 18) rc = fmx_estep_launch<0, 18, 20, 64>(ctx, s, a);
         if (rc == PSCL_OK && nS > 20) rc = fmx_estep_launch<0, 20, 22, 64>(ctx, s, a);
         if (rc == PSCL_OK && nS > 22) rc = fmx_estep_launch<0, 22, 24, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 24) rc = fmx_estep_launch<0, 24, 25, 64>(ctx, s, a);  // one row per launch from here: 25..32 accumulators
+        if (rc == PSCL_OK && nS > 25) rc = fmx_estep_launch<0, 25, 26, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 26) rc = fmx_estep_launch<0, 26, 27, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 27) rc = fmx_estep_launch<0, 27, 28, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 28) rc = fmx_estep_launch<0, 28, 29, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 29) rc = fmx_estep_launch<0, 29, 30, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 30) rc = fmx_estep_launch<0, 30, 31, 64>(ctx, s, a);
+        if (rc == PSCL_OK && nS > 31) rc = fmx_estep_launch<0, 31, 32, 64>(ctx, s, a);
     }
     if (rc != PSCL_OK) return rc;
   }

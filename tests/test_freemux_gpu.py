@@ -43,9 +43,9 @@ def test_greedy_seeding_and_em(ctx, nS):
     assert tab.max(axis=1).sum() > 0.9 * sng.sum()
 
 
-@pytest.mark.parametrize("nS", [9, 12, 16, 20, 24])
+@pytest.mark.parametrize("nS", [9, 12, 16, 20, 24, 27, 32])
 def test_many_clusters(ctx, nS):
-    """runtime-nS tile kernels (more than 8 clusters)."""
+    """runtime-nS tile kernels (more than 8 clusters; one row per launch past 24), up to the cap of 32."""
     s = synth.make_pileup(C=160, nv=nS, V=1500, kbar=250, seed=600 + nS)
     _check(*_both(ctx, s.plp, nS, max_iter=3), tied=0.05)
 
@@ -173,7 +173,7 @@ def test_fmx_errors(ctx):
     with pytest.raises(PsclError):
         ctx.fmx_run(s.plp, ctx.fmx_opts(1))    # nSamples-1 == 0 in the doublet prior (:380)
     with pytest.raises(PsclError):
-        ctx.fmx_run(s.plp, ctx.fmx_opts(25))
+        ctx.fmx_run(s.plp, ctx.fmx_opts(33))
     with pytest.raises(PsclError):
         ctx.fmx_run(s.plp, ctx.fmx_opts(3), np.full(20, 3, dtype=np.int32))  # cluster id >= nsample (:99-100)
     s.plp.snp_af = None
@@ -181,7 +181,7 @@ def test_fmx_errors(ctx):
         ctx.fmx_run(s.plp, ctx.fmx_opts(3))
 
 
-@pytest.mark.parametrize("shape", [(3000, 8, 20000, 600), (600, 5, 500, 200), (900, 16, 6000, 500), (300, 20, 3000, 300)])
+@pytest.mark.parametrize("shape", [(3000, 8, 20000, 600), (600, 5, 500, 200), (900, 16, 6000, 500), (300, 20, 3000, 300), (400, 30, 3000, 300)])
 @pytest.mark.parametrize("batch", [1, 7, 32, 256, 1024])
 def test_batched_seeding_takes_the_serial_chains_decisions(ctx, shape, batch):
     """The speculative batches (k_fmx_seed3_*: every cell of a batch decided at once against the table before the batch, then
