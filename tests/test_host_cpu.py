@@ -327,3 +327,21 @@ def test_parallel_ingest_bgzf_gzip_and_thread_counts_agree(tmp_path, built):
     r = subprocess.run([exe, "demuxlet", "--plp", str(tmp_path / "bg" / "p"), "--vcf", str(tmp_path / "ref.vcf.gz"), "--field", "GT", "--out", "o",
                         "--dry-run"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 134 and ("Corrupt" in r.stderr or "not in" in r.stderr or "Cannot access" in r.stderr), r.stderr
+
+
+def test_vectorised_plp_text_equals_row_formatting():
+    """plpio.plp_text assembles the .plp.gz table with array operations; it must be the text per-row formatting gives
+    (multi-digit ids, pairs of 1..8 base-calls, empty cells, SNP-major order with droplet ids ascending inside a SNP)."""
+    s = synth.make_pileup(C=230, nv=3, V=12000, kbar=150, seed=77)
+    plp = s.plp
+    C = plp.n_cells
+    pair_cell = np.repeat(np.arange(C), np.diff(plp.cell_ptr))
+    order = np.lexsort((pair_cell, plp.pair_snp))
+    al = (plp.read_allele + ord("0")).astype(np.uint8).tobytes()
+    bq = (plp.read_qual + 33).astype(np.uint8).tobytes()
+    prp = plp.pair_read_ptr
+    rows = [plpio.PLP_HEADER]
+    for p in order:
+        a, b = int(prp[p]), int(prp[p + 1])
+        rows.append(f"{int(pair_cell[p])}\t{int(plp.pair_snp[p])}\t{al[a:b].decode()}\t{bq[a:b].decode()}")
+    assert plpio.plp_text(plp) == ("\n".join(rows) + "\n").encode()
