@@ -255,7 +255,7 @@ int pscl_demux_keep_grid(pscl_ctx* ctx, int enable);
  * drain per call).  Page-locked host arrays (cudaHostAlloc / cudaHostRegister), `out` included, make the
  * overlap real; pageable ones give the same records without it.  The records are the bytes of the one-shot
  * run whatever the slicing.  Environment (none needed): PSCL_SLICES=n / PSCL_GROUPS=g force and shape the
- * pipeline at any size (1 = off), PSCL_SLICE_FULL=1 slices counts and base-calls too (needs ABI 7's
+ * pipeline at any size (1 = off), PSCL_SLICE_READS=1 / PSCL_SLICE_FULL=1 slice the base-calls / counts and base-calls too (need ABI 7's
  * cell_read_ptr or the offsets), PSCL_STAGES=n selects the older form instead (one scoring launch whose warps
  * decode the gaps and wait on a flag word per slice), PSCL_TRACE=1 prints the wall-clock of every phase and
  * PSCL_TIMELINE=1 the device time stamps of the call on stderr. */

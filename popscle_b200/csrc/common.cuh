@@ -71,6 +71,7 @@ struct pscl_plp {
   // fully sliced run: counts, base-calls and gaps of a slice land together and are decoded by per-slice launches, so these
   // upload temporaries live as long as the image (sl_full); sl_rb[k] = first base-call of slice k (from the host's offsets)
   bool sl_full = false;
+  bool sl_reads = false;  // only the base-calls are sliced with the gaps (counts whole and early): unpacked per slice by k_unpack_reads
   uint8_t *sl_cnt = nullptr, *sl_n2 = nullptr, *sl_nbig = nullptr, *sl_rpk = nullptr, *sl_rpal = nullptr;
   int64_t* sl_nblk = nullptr;
   int64_t* sl_cell_rd = nullptr;  // [C+1] device copy of cell_read_ptr

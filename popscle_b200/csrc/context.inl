@@ -679,6 +679,14 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
   // cuts (ABI 7's cell_read_ptr, or pair_read_ptr / pair_read_ptr32 when the host passes them beside the counts).
   const bool full = deferred && slices > 1 && cnt2 && pal && dsnp8 && (h->cell_read_ptr || h->pair_read_ptr || ptr32) && read_base == 0 && pair_base == 0 &&
                     P > 0 && C >= 2 * slices && ctx->copy_stream && ctx->ev_up && getenv("PSCL_SLICE_FULL");
+  // Base-calls sliced with the gaps (PSCL_SLICE_READS=1; measured equal to slicing the gaps alone, 1.74 ms per call either way
+  // under PSCL_TIMELINE: the first group starts 0.15 ms earlier, but every slice's unpacking then sits in the scoring stream's
+  // chain instead of under the copies — profiles/r5e_slice_reads_timeline.txt): the counts still go whole and first
+  // (5 MB at configs[1]; expanded and scanned under the other copies), then every slice brings its gaps AND its base-calls,
+  // and the caller unpacks and decodes it with the ordinary kernels (k_unpack_reads on the slice's range, k_decode_snp8 on
+  // its cells).  Scoring can start after the counts and two slices instead of after the counts and all the base-calls.
+  const bool rsl = !full && deferred && slices > 1 && cnt8 && pal && (dsnp8 || dsnp) && (h->cell_read_ptr || h->pair_read_ptr || ptr32) &&
+                   read_base == 0 && pair_base == 0 && P > 0 && C >= 2 * slices && ctx->copy_stream && ctx->ev_up && getenv("PSCL_SLICE_READS");
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_bad, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_bad, 0, sizeof(int), ctx->stream);
   if (cnt8) {  // ABI 3: 8-bit base-call counts, offsets by an exclusive scan
@@ -717,6 +725,7 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
       if (e == cudaSuccess) e = cudaMalloc((void**)&p->sl_cell_rd, sizeof(int64_t) * ((size_t)C + 1));
       if (e == cudaSuccess) e = pscl_stage_copy(ctx, p->sl_cell_rd, src, sizeof(int64_t) * ((size_t)C + 1), true);  // staged: `crd` is a local
     }
+    else if (rsl) { if (e == cudaSuccess) e = cudaMalloc((void**)&d_rpk, (size_t)((N * h->read_bits + 7) / 8 + 16)); }  // filled slice by slice
     else if (e == cudaSuccess) e = up((void**)&d_rpk, h->read_packed, (size_t)((N * h->read_bits + 7) / 8 + 1));
     if (e == cudaSuccess) e = up((void**)&d_rpal, h->read_palette, (size_t)1 << h->read_bits);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->rd_aq, N ? (size_t)N : 16);
@@ -820,6 +829,15 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
           if (e == cudaSuccess && re > rb) e = cudaMemcpyAsync(d_rpk + q0, h->read_packed + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->copy_stream);
         }
       }
+      if (rsl) {  // the slice's base-calls (whole bytes of the bit string around its range)
+        const int32_t ca = p->stage_cell[k], cb = p->stage_cell[k + 1];
+        const int64_t rb = h->cell_read_ptr ? h->cell_read_ptr[ca] : ptr32 ? (int64_t)h->pair_read_ptr32[pb] : h->pair_read_ptr[pb];
+        const int64_t re = h->cell_read_ptr ? h->cell_read_ptr[cb] : ptr32 ? (int64_t)h->pair_read_ptr32[pe] : h->pair_read_ptr[pe];
+        p->sl_rb[k] = rb; p->sl_rb[k + 1] = re;
+        if (rb < 0 || re < rb || re > N) { e = cudaErrorInvalidValue; where = "read offsets at a slice boundary"; break; }
+        const int64_t q0 = rb * h->read_bits / 8, q1 = (re * h->read_bits + 7) / 8 + 1;
+        if (re > rb) e = cudaMemcpyAsync(d_rpk + q0, h->read_packed + q0, (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->copy_stream);
+      }
       if (pe > pb && e == cudaSuccess)
         e = dsnp ? cudaMemcpyAsync(p->d_delta + pb, h->pair_snp_delta16 + pb, sizeof(uint16_t) * (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream)
                  : cudaMemcpyAsync(p->d_delta8 + pb, h->pair_snp_delta8 + pb, (size_t)(pe - pb), cudaMemcpyHostToDevice, ctx->copy_stream);
@@ -898,7 +916,17 @@ static int plp_upload_impl(pscl_ctx* ctx, const pscl_pileup* h, pscl_plp** out, 
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (p->sl_full) {
+  if (rsl && e == cudaSuccess) {  // unpacked per slice by the caller
+    p->sl_reads = true;
+    p->sl_rpk = d_rpk; p->sl_rpal = d_rpal; p->sl_read_bits = h->read_bits;
+    d_rpk = d_rpal = nullptr;  // owned by the image from here on
+    // the host's offsets at the cuts must be the scanned counts' (a cut in the wrong place would unpack the wrong base-calls)
+    for (int k = 1; k < p->n_slices && e == cudaSuccess; ++k) {
+      k_check_total<<<1, 32, 0, ctx->stream>>>(p->pair_rd, h->cell_ptr[p->stage_cell[k]], p->sl_rb[k], p->d_bad);
+      e = cudaGetLastError();
+    }
+  }
+  if (p->sl_full || p->sl_reads) {
     // unpacked per slice by the caller
   } else if (e == cudaSuccess && N > 0 && pal) {
     k_unpack_reads<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_rpk, d_rpal, h->read_bits, 0, N, p->rd_aq, p->d_bad);

@@ -1397,6 +1397,11 @@ extern "C" int pscl_demux_run(pscl_ctx* ctx, const pscl_pileup* host, const pscl
         ctx->launches++;
         e = cudaGetLastError();
       } else if (e == cudaSuccess && c1 > c0) {
+        if (plp->sl_reads && plp->sl_rb[k + 1] > plp->sl_rb[k]) {  // the slice's base-calls
+          k_unpack_reads<<<(unsigned)((plp->sl_rb[k + 1] - plp->sl_rb[k] + 255) / 256), 256, 0, ctx->stream>>>(plp->sl_rpk, plp->sl_rpal, plp->sl_read_bits, plp->sl_rb[k],
+                                                                                                          plp->sl_rb[k + 1], plp->rd_aq, plp->d_bad);
+          ctx->launches++;
+        }
         const unsigned grid = (unsigned)(((int64_t)(c1 - c0) * 32 + 255) / 256);
         if (plp->d_delta8) k_decode_snp8<<<(unsigned)(c1 - c0), PSCL_DEC8_NT, 0, ctx->stream>>>(plp->cell_ptr + c0, plp->d_first + c0, plp->d_delta8, plp->d_gap_big, plp->d_cell_gap_ptr + c0,
                                                                         plp->n_gap_big, c1 - c0, plp->V, plp->pair_snp, plp->d_bad);

@@ -408,11 +408,17 @@ def test_pipelined_run_is_bit_identical(ctx, slices, groups):
                 # ... and with the counts and base-calls sliced too (ABI 7's cell_read_ptr; one k_decode_cells launch per slice)
                 os.environ["PSCL_SLICE_FULL"] = "1"
                 full = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=compact)
+                del os.environ["PSCL_SLICE_FULL"]
+                # ... and with only the base-calls sliced beside the gaps (ordinary decoders on a slice's ranges)
+                os.environ["PSCL_SLICE_READS"] = "1"
+                reads = ctx.demux_run(s.plp, gp, None, DEFAULT, compact=compact)
             finally:
                 del os.environ["PSCL_SLICES"], os.environ["PSCL_GROUPS"]
                 os.environ.pop("PSCL_SLICE_FULL", None)
+                os.environ.pop("PSCL_SLICE_READS", None)
             assert got.tobytes() == ref.tobytes(), (type(gp).__name__, compact)
             assert full.tobytes() == ref.tobytes(), (type(gp).__name__, compact, "full")
+            assert reads.tobytes() == ref.tobytes(), (type(gp).__name__, compact, "reads")
     bad = synth.make_pileup(C=60, nv=3, V=400, kbar=90, seed=1)
     first, d8, gbig, cbp, n2, nbig, nbp = bad.plp.compact4()
     os.environ["PSCL_SLICES"] = "3"
