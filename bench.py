@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the `strong` (one sharded problem per workload) and `extra` measurements")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "lane", "dict", "general", "poly"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "lane", "dict", "cls", "general", "poly"],
                     help="demuxlet accumulation kernel: auto (the library's choice: k_demux_default on dictionary-coded genotypes "
                          "for this workload), lane (k_demux_default on gathered genotype rows), k_demux_general, k_demux_poly")
     return ap.parse_args()
@@ -406,7 +406,7 @@ def main():
     plp, nv = s.plp, cfg["nv"]
     stream = torch.cuda.current_stream()
     ctx = Context(local_rank, stream=stream.cuda_stream)
-    ctx.demux_select_kernel({"auto": 0, "lane": 1, "general": 2, "poly": 4, "dict": 6}[args.kernel])
+    ctx.demux_select_kernel({"auto": 0, "lane": 1, "general": 2, "poly": 4, "dict": 6, "cls": 7}[args.kernel])
     kname = None  # named after the first scoring pass, from what the library launched
 
     # ---- device-resident arm ("value") ----------------------------------------------------------
@@ -439,7 +439,7 @@ def main():
     barrier()
     launches = ctx.launch_count - l0
     kname = {1: "k_demux_default", 6: "k_demux_default_dict", 2: "k_demux_general", 3: "k_demux_cls", 4: "k_demux_poly",
-             5: "k_demux_ab"}[ctx.demux_last_kernel()]
+             5: "k_demux_ab", 7: "k_demux_default_classes"}[ctx.demux_last_kernel()]
     clocks = sampler.stop() if rank == 0 else None
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([t_ms], dtype=torch.float64, device="cuda")

@@ -379,13 +379,17 @@ int pscl_demux_force_general(pscl_ctx* ctx, int enable);
 /* Accumulation kernel: 0 = automatic (k_demux_default for the alpha grid {0, 0.5} with <= 8 samples,
  * k_demux_poly otherwise), 1 = k_demux_default on gathered genotype rows (lane per pair; needs that default shape),
  * 6 = k_demux_default on dictionary-coded genotypes (a table of <= 256 distinct triples, i.e. hard calls as --field GT
- * produces them, is read as 8-bit codes; any other table falls back to the rows; 0 does the same),
+ * produces them, is read as 8-bit codes; any other table falls back to the rows),
+ * 7 = the same on genotype classes (when, besides, no SNP holds more than three distinct triples — one per genotype —
+ * a pair's factors are computed once per class and picked per accumulator; same expressions, bit-identical records; a
+ * table with a fourth triple on some SNP falls back to 6; 0 chooses 7, then 6, then 1 — PSCL_NO_CLS=1 in the
+ * environment skips 7),
  * 5 = k_demux_ab (k_demux_cls with two warps per batch; default shape),
  * 2 = k_demux_general (9-FMA baseline, any shape), 3 = k_demux_cls (class-split records, TMA packet
  * ring; default shape), 4 = k_demux_poly (polynomial in alpha, any shape).  All are parity-tested
  * against the same oracle. */
 int pscl_demux_select_kernel(pscl_ctx* ctx, int which);
-/* Which of the above the last pscl_demux_score actually launched (1..6), 0 before the first one. */
+/* Which of the above the last pscl_demux_score actually launched (1..7), 0 before the first one. */
 int pscl_demux_last_kernel(const pscl_ctx* ctx);
 
 #ifdef __cplusplus

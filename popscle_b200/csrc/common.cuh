@@ -127,9 +127,10 @@ struct pscl_ctx {
   double* gpS = nullptr;      // [V][nv][2] (S_j, M_j) moments of the rows
   // dictionary-coded genotypes (demux.inl, built by pscl_demux_set_geno when nv <= 8): usable when *h_dict_over == 0
   unsigned long long* gp_code = nullptr;   // [V] 8-bit code per sample
+  unsigned long long* gp_cls = nullptr;    // [V] the SNP's <= 3 distinct codes + 2-bit class per sample (usable when *h_dict_over == 0)
   double* gp_dict = nullptr;               // [256][3] the distinct triples
   unsigned long long* gp_dict_key = nullptr;  // [256] hash keys claiming the slots
-  int* gp_dict_over = nullptr;             // device flag: more than 256 distinct triples (or a hash clash)
+  int* gp_dict_over = nullptr;             // device flag: bit 0 more than 256 distinct triples (or a hash clash), bit 1 a SNP with a fourth triple
   int* h_dict_over = nullptr;              // pinned host copy of the flag
   int* h_geno_bad = nullptr;               // pinned: the raw genotype input (ABI 4) held an invalid hard-call code
   int* h_bad = nullptr;                    // pinned: the pileup image's validity flag, read back at the end of a run

@@ -116,7 +116,7 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   if (ctx->h_bad) cudaFreeHost(ctx->h_bad);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev_dict) cudaEventDestroy(ctx->ev_dict);
-  cudaFree(ctx->gp_code); cudaFree(ctx->gp_dict); cudaFree(ctx->gp_dict_key); cudaFree(ctx->gp_dict_over);
+  cudaFree(ctx->gp_code); cudaFree(ctx->gp_cls); cudaFree(ctx->gp_dict); cudaFree(ctx->gp_dict_key); cudaFree(ctx->gp_dict_over);
   cudaFree(ctx->stage_flags);
   pscl_blk_cache_flush(ctx);  // the blocks this context kept for reuse go back to the pool
   cudaStreamSynchronize(ctx->stream);

@@ -42,6 +42,7 @@
 #define PSCL_FOLD_ROW 6  /* 5 factors padded to 48 B */
 #define PSCL_FOLD_ONES (2 * 64)
 #define PSCL_DICT_N 256 /* entries of the genotype dictionary (8-bit codes) */
+#define PSCL_CLS_SLOTS 12 /* genotype-class variant: 9 doublet + 3 singlet products per pair */
 #ifndef PSCL_RENORM_EVERY
 #define PSCL_RENORM_EVERY 16 /* pairs between two exponent extractions of the running products (power of two) */
 #endif
@@ -72,6 +73,8 @@ struct DefaultCfg {
   __host__ __device__ static constexpr size_t smem_dict(int nt) {
     return sizeof(double) * 3 * 64 * PSCL_FOLD_ROW + (size_t)NE * nt * sizeof(int) + (size_t)PSCL_DICT_N * 3 * sizeof(double) * 16;
   }
+  // genotype-class variant: the same + [12][threads] per-pair products of the SNP's (at most three) distinct triples
+  __host__ __device__ static constexpr size_t smem_cls(int nt) { return smem_dict(nt) + (size_t)PSCL_CLS_SLOTS * nt * sizeof(double); }
 };
 
 struct DemuxArgs {
@@ -109,12 +112,16 @@ struct DemuxArgs {
   // a 24*nv-byte row, and the triples themselves sit in shared memory
   const unsigned long long* gp_code = nullptr;  // [V] 8-bit dictionary index per sample
   const double* gp_dict = nullptr;              // [256][3]
+  // genotype classes (k_demux_default<NV, 0, 2>): a SNP of a hard-call table holds at most three distinct triples (one per
+  // genotype: (1-err) onehot + err avg with avg common to the SNP's samples), so gp_code then points at, per SNP, the
+  // dictionary indices of those triples in order of first appearance (bytes 0-2) and each sample's class, 2 bits from bit 32
+  int32_t cls = 0;
 };
 
 // NT threads per CTA, one CTA per SM.  (Splitting a work item's running products between two warps, so that 12 or 16
 // warps fit an SM at 158 / 128 registers, was measured at 0.67 / 0.71 ms against 0.53 ms for this form: the duplicated
 // fold and the extra work items cost more than the added warps hide; profiles/r2a_variants.txt.)
-template <int NV, int DELTA, bool DICT, int NT>
+template <int NV, int DELTA, int DICT, int NT>
 __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
   using Cfg = DefaultCfg<NV>;
   constexpr int ND = Cfg::ND, SD = Cfg::STRIDE_D, NAM = Cfg::NE;
@@ -127,9 +134,10 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
   // DICT: the dictionary, 16 copies interleaved ([256*3][16] doubles): lane l reads copy l%16, which lives in its own
   // pair of banks, so the 32 lanes' lookups of 32 different triples never collide (a single copy cost ~3x the wavefronts)
   double* const s_dict = reinterpret_cast<double*>(s_exp + NAM * NT);
-  if constexpr (DICT) {
+  if constexpr (DICT != 0) {
     for (int i = tid; i < PSCL_DICT_N * 3 * 16; i += NT) s_dict[i] = a.gp_dict[i >> 4];
   }
+  double* const s_cls = s_dict + PSCL_DICT_N * 3 * 16;        // DICT == 2: [PSCL_CLS_SLOTS][NT], column tid is this lane's
   __syncthreads();
   double* const g_row0 = s_g + (size_t)tid * SD;              // buffer 1 is NT*SD doubles further
 
@@ -259,9 +267,9 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
         if (n > 0) b0B = a.rd_aq[r0B];
         if (n > 1) b1B = a.rd_aq[r0B + 1];
         if (n > 2) b2B = a.rd_aq[r0B + 2];
-        if constexpr (DICT) codeB = a.gp_code[snpA];
+        if constexpr (DICT != 0) codeB = a.gp_code[snpA];
       }
-      if constexpr (DICT) return;  // no genotype rows to fetch
+      if constexpr (DICT != 0) return;  // no genotype rows to fetch
       // Cooperative row gather: the warp's 32 genotype rows are fetched LPR lanes per row, so one
       // LDGSTS instruction touches 32/LPR whole rows (a few 128-B lines) instead of 32 scattered
       // 16-B pieces of 32 different rows (one L1 tag lookup each).  A denser mapping (piece
@@ -294,10 +302,10 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
       const uint32_t r0 = r0B, r1 = r1B, b0 = b0B, b1 = b1B, b2 = b2B;
       const unsigned long long code = codeB;
       const bool has = hasB != 0;
-      if constexpr (!DICT) __syncwarp();  // every lane is done reading buffer buf^1 (iteration it-1) before it is refilled
+      if constexpr (DICT == 0) __syncwarp();  // every lane is done reading buffer buf^1 (iteration it-1) before it is refilled
       issueB(buf ^ 1);
       loadA(it + 2);
-      if constexpr (!DICT) {
+      if constexpr (DICT == 0) {
         __pipeline_wait_prior(1);  // this lane's pieces of iteration `it` have landed ...
         __syncwarp();              // ... and so have the other lanes' pieces of this lane's row
       }
@@ -329,8 +337,52 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
         acc[E_MX] *= mx;
 
         // ---- D3: genotype row from this lane's shared-memory row ------------------------------
+        if constexpr (DICT == 2) {
+          // Genotype classes: the SNP's samples share at most three triples T[c], so the pair's singlet factor takes three
+          // values S[c] = T[c].(h0,h2,h4) and its doublet factor nine, D[cj][ck] = T[ck].(H T[cj]) — 63 FP64 operations
+          // instead of 171, the same expressions on the same doubles as below (bit-identical records).  They go to this
+          // lane's column of s_cls and every accumulator picks its factor by its samples' classes: one add and one 64-bit
+          // shared-memory load per accumulator in place of three FP64 operations.
+          double T[3][3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double* d = s_dict + (uint32_t)((code >> (8 * c)) & 255ull) * 48 + (lane & 15);
+            T[c][0] = d[0]; T[c][1] = d[16]; T[c][2] = d[32];
+          }
+          acc[E_SG0] *= (T[0][0] + T[0][1] + T[0][2]);  // sample 0 opens class 0
+          double* const sc = s_cls + tid;
+          double S0 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double S = (T[c][0] * h0 + T[c][1] * h2 + T[c][2] * h4);
+            if (c == 0) S0 = S;
+            sc[(9 + c) * NT] = S;
+          }
+#pragma unroll
+          for (int cj = 0; cj < 3; ++cj) {
+            const double v0 = h0 * T[cj][0] + h1 * T[cj][1] + h2 * T[cj][2];
+            const double v1 = h1 * T[cj][0] + h2 * T[cj][1] + h3 * T[cj][2];
+            const double v2 = h2 * T[cj][0] + h3 * T[cj][1] + h4 * T[cj][2];
+#pragma unroll
+            for (int ck = 0; ck < 3; ++ck) sc[(cj * 3 + ck) * NT] = (T[ck][0] * v0 + T[ck][1] * v1 + T[ck][2] * v2);
+          }
+          const uint32_t cb = (uint32_t)(code >> 32);
+          uint32_t off[NV];  // byte offset of sample j's class between two slots of s_cls
+#pragma unroll
+          for (int j = 0; j < NV; ++j) off[j] = ((cb >> (2 * j)) & 3u) * (uint32_t)(NT * sizeof(double));
+          const char* const scb = reinterpret_cast<const char*>(sc);
+          acc[0] *= S0;
+#pragma unroll
+          for (int j = 1; j < NV; ++j) acc[j] *= *reinterpret_cast<const double*>(scb + 9 * NT * sizeof(double) + off[j]);
+#pragma unroll
+          for (int j = 1; j < NV; ++j) {
+            const char* const rowb = scb + 3 * off[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) acc[NV + j * (j - 1) / 2 + k] *= *reinterpret_cast<const double*>(rowb + off[k]);
+          }
+        } else {
         double G[NV][3];
-        if constexpr (DICT) {
+        if constexpr (DICT != 0) {
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
             const double* d = s_dict + (uint32_t)((code >> (8 * j)) & 255ull) * 48 + (lane & 15);
@@ -365,6 +417,7 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
           for (int k = 0; k < j; ++k)
             acc[NV + j * (j - 1) / 2 + k] *= (G[k][0] * v0 + G[k][1] * v1 + G[k][2] * v2);
         }
+        }
       }
       // Exponents move to shared memory every PSCL_RENORM_EVERY pairs.  A term is >= min h >= 1e-10 * mx (rows sum to one)
       // and mx >= f(p = 0.5) >= 0.25^3 for the three folded base-calls (deeper pairs are rescaled), i.e. >= 1.5e-12:
@@ -374,7 +427,7 @@ __global__ void __launch_bounds__(NT, 1) k_demux_default(DemuxArgs a) {
         for (int e = 0; e < NACC; ++e) { int ex = 0; pscl_renorm(acc[e], ex); s_exp[e * NT + tid] += ex; }
       }
     }
-    if constexpr (!DICT) __pipeline_wait_prior(0);
+    if constexpr (DICT == 0) __pipeline_wait_prior(0);
 
     // ---- item epilogue ---------------------------------------------------------------------------
     // Lane products are multiplied across the warp by a transpose-reduction (recursive halving: 31 + 7 exchanged
@@ -880,11 +933,12 @@ __global__ void k_geno_dict_claim(const double* __restrict__ gp, int32_t V, int3
       }
       if (k == key) break;
     }
-    if (probe == PSCL_DICT_N) { atomicExch(over, 1); return; }
+    if (probe == PSCL_DICT_N) { atomicOr(over, 1); return; }
   }
 }
 __global__ void k_geno_dict_codes(const double* __restrict__ gp, int32_t V, int32_t nv, const unsigned long long* __restrict__ keys,
-                                  const double* __restrict__ dict, unsigned long long* __restrict__ code, int* over) {
+                                  const double* __restrict__ dict, unsigned long long* __restrict__ code,
+                                  unsigned long long* __restrict__ cls, int* over) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   unsigned long long c = 0;
@@ -900,7 +954,24 @@ __global__ void k_geno_dict_codes(const double* __restrict__ gp, int32_t V, int3
     c |= (unsigned long long)s << (8 * j);
   }
   code[v] = c;
-  if (bad) atomicExch(over, 1);
+  if (bad) atomicOr(over, 1);
+  // genotype classes: distinct codes in order of first appearance (a fourth — a missing call among hard ones — only raises
+  // bit 1 of the flag: the dictionary kernel takes that table)
+  unsigned long long w = 0;
+  int d0 = -1, d1 = -1, d2 = -1;
+  bool many = false;
+  for (int j = 0; j < nv; ++j) {
+    const int s = (int)((c >> (8 * j)) & 255ull);
+    int k;
+    if (s == d0 || d0 < 0) { d0 = s; k = 0; }
+    else if (s == d1 || d1 < 0) { d1 = s; k = 1; }
+    else if (s == d2 || d2 < 0) { d2 = s; k = 2; }
+    else { many = true; k = 0; }
+    w |= (unsigned long long)k << (32 + 2 * j);
+  }
+  w |= (unsigned long long)(d0 < 0 ? 0 : d0) | (unsigned long long)(d1 < 0 ? 0 : d1) << 8 | (unsigned long long)(d2 < 0 ? 0 : d2) << 16;
+  cls[v] = w;
+  if (many && !bad) atomicOr(over, 2);
 }
 
 // ABI 4: genotype table from the reader's raw posteriors, mixed with the genotype error on the device.  One thread per
@@ -947,6 +1018,7 @@ static int demux_geno_finish(pscl_ctx* ctx, int32_t n_samples, int32_t n_snps) {
   ctx->nv = n_samples;
   ctx->geno_V = n_snps;
   cudaFree(ctx->gp_code); ctx->gp_code = nullptr;
+  cudaFree(ctx->gp_cls); ctx->gp_cls = nullptr;
   ctx->dict_built = false;
   if (n_samples <= 8 && n_snps > 0 && ctx->h_dict_over) {
     if (!ctx->gp_dict) {
@@ -955,13 +1027,14 @@ static int demux_geno_finish(pscl_ctx* ctx, int32_t n_samples, int32_t n_snps) {
       PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_over, sizeof(int)));
     }
     PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_code, sizeof(unsigned long long) * (size_t)n_snps));
+    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_cls, sizeof(unsigned long long) * (size_t)n_snps));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict, 0, sizeof(double) * 3 * PSCL_DICT_N, ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_key, 0, sizeof(unsigned long long) * PSCL_DICT_N, ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_over, 0, sizeof(int), ctx->stream));
     k_geno_dict_claim<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, n_samples, ctx->gp_dict_key, ctx->gp_dict,
                                                                                  ctx->gp_dict_over);
     k_geno_dict_codes<<<(unsigned)((n_snps + 255) / 256), 256, 0, ctx->stream>>>(ctx->gp, n_snps, n_samples, ctx->gp_dict_key, ctx->gp_dict,
-                                                                                 ctx->gp_code, ctx->gp_dict_over);
+                                                                                 ctx->gp_code, ctx->gp_cls, ctx->gp_dict_over);
     ctx->launches += 2;
     PSCL_CUDA(ctx, cudaGetLastError());
     *ctx->h_dict_over = 1;
@@ -1041,7 +1114,7 @@ extern "C" int pscl_demux_force_general(pscl_ctx* ctx, int enable) {
 }
 extern "C" int pscl_demux_last_kernel(const pscl_ctx* ctx) { return ctx ? ctx->dm_last_kernel : 0; }
 extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
-  if (!ctx || which < 0 || which > 6) return PSCL_EINVAL;
+  if (!ctx || which < 0 || which > 7) return PSCL_EINVAL;
 #ifndef PSCL_EXPERIMENTAL
   if (which == 3 || which == 5)
     return pscl_fail(ctx, PSCL_EINVAL, "k_demux_cls / k_demux_ab are experiments (csrc/experimental/), built only with -DPSCL_EXPERIMENTAL");
@@ -1057,12 +1130,19 @@ extern "C" int pscl_demux_select_kernel(pscl_ctx* ctx, int which) {
 #ifndef PSCL_ROWS_NT
 #define PSCL_ROWS_NT 384
 #endif
+#ifndef PSCL_CLS_NT
+#define PSCL_CLS_NT 256
+#endif
+// whether the automatic choice takes the genotype-class variant of the dictionary kernel when the table allows it
+#ifndef PSCL_CLS_DEFAULT
+#define PSCL_CLS_DEFAULT 1
+#endif
 
-template <int NV, int DELTA, bool DICT>
+template <int NV, int DELTA, int DICT>
 static cudaError_t launch_default_v(pscl_ctx* ctx, const DemuxArgs& a) {
-  constexpr int NT = DICT ? PSCL_DICT_NT : PSCL_ROWS_NT;
+  constexpr int NT = DICT == 2 ? PSCL_CLS_NT : DICT ? PSCL_DICT_NT : PSCL_ROWS_NT;
   using Cfg = DefaultCfg<NV>;
-  constexpr size_t SMEM = DICT ? Cfg::smem_dict(NT) : Cfg::smem_rows(NT);
+  constexpr size_t SMEM = DICT == 2 ? Cfg::smem_cls(NT) : DICT ? Cfg::smem_dict(NT) : Cfg::smem_rows(NT);
   static_assert(SMEM <= 227 * 1024, "k_demux_default: shared memory budget");
   auto kern = k_demux_default<NV, DELTA, DICT, NT>;
   static bool attr_set[64] = {false};
@@ -1082,8 +1162,9 @@ static cudaError_t launch_default_v(pscl_ctx* ctx, const DemuxArgs& a) {
 template <int NV>
 static cudaError_t launch_default(pscl_ctx* ctx, const DemuxArgs& a) {
   const int delta = a.delta8 ? 2 : a.delta ? 1 : 0;  // staged run on 8-bit (ABI 6) / 16-bit (ABI 3) SNP gaps, or plain SNP ids
-  if (a.gp_code) return delta == 2 ? launch_default_v<NV, 2, true>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, true>(ctx, a) : launch_default_v<NV, 0, true>(ctx, a);
-  return delta == 2 ? launch_default_v<NV, 2, false>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, false>(ctx, a) : launch_default_v<NV, 0, false>(ctx, a);
+  if (a.gp_code && a.cls && delta == 0) return launch_default_v<NV, 0, 2>(ctx, a);
+  if (a.gp_code) return delta == 2 ? launch_default_v<NV, 2, 1>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, 1>(ctx, a) : launch_default_v<NV, 0, 1>(ctx, a);
+  return delta == 2 ? launch_default_v<NV, 2, 0>(ctx, a) : delta == 1 ? launch_default_v<NV, 1, 0>(ctx, a) : launch_default_v<NV, 0, 0>(ctx, a);
 }
 
 // out_origin: the cell whose record is dm_cells[0]; total_cells: how many records the output holds.  pscl_demux_score
@@ -1121,7 +1202,11 @@ static int demux_score_impl(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux
   if (ctx->h_geno_bad && *ctx->h_geno_bad)
     return pscl_fail(ctx, PSCL_EINVAL, "pscl_geno.gt8 holds a code other than 0/1/2 (missing calls need gp_f32)");
   bool use_dict = false;  // dictionary-coded genotypes: auto (0) and 6 take them when the table allows, 1 keeps the row gather
-  if (use_default && ctx->dict_built && (ctx->demux_kernel == 0 || ctx->demux_kernel == 6)) use_dict = *ctx->h_dict_over == 0;
+  if (use_default && ctx->dict_built && (ctx->demux_kernel == 0 || ctx->demux_kernel == 6 || ctx->demux_kernel == 7)) use_dict = (*ctx->h_dict_over & 1) == 0;
+  // ... and by genotype classes (7; auto when PSCL_CLS_DEFAULT) when no SNP holds more than three distinct triples and the
+  // SNP ids are plain (the staged in-kernel gap decoding keeps the dictionary form)
+  const bool use_cls = use_dict && *ctx->h_dict_over == 0 && plp->n_stages <= 1 && ctx->gp_cls != nullptr &&
+                       (ctx->demux_kernel == 7 || (ctx->demux_kernel == 0 && PSCL_CLS_DEFAULT && !getenv("PSCL_NO_CLS")));
   // every other shape: the polynomial kernel unless k_demux_general was asked for
   const bool use_poly = !use_default && !ctx->force_general && ctx->demux_kernel != 2;
   if (use_poly) {
@@ -1140,7 +1225,7 @@ static int demux_score_impl(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux
 #else
   const bool use_ws = false, use_ab = false;
 #endif
-  ctx->dm_last_kernel = use_ab ? 5 : use_ws ? 3 : use_default ? (use_dict ? 6 : 1) : use_poly ? 4 : 2;
+  ctx->dm_last_kernel = use_ab ? 5 : use_ws ? 3 : use_default ? (use_cls ? 7 : use_dict ? 6 : 1) : use_poly ? 4 : 2;
   const std::vector<int32_t>& cip = plp->h_cell_item_ptr;
   size_t max_items = ctx->partial_budget_bytes / (G * sizeof(double));
   if (max_items < 1) max_items = 1;
@@ -1165,6 +1250,7 @@ static int demux_score_impl(pscl_ctx* ctx, const pscl_plp* plp, const pscl_demux
       a.partial = ctx->dm_partial; a.counter = ctx->dm_counter;
       a.item_base = ib; a.n_work = nwork; a.nv = nv; a.nalpha = na;
       if (use_dict) { a.gp_code = ctx->gp_code; a.gp_dict = ctx->gp_dict; }
+      if (use_cls) { a.gp_code = ctx->gp_cls; a.cls = 1; }
       if (plp->n_stages > 1) {  // staged pscl_demux_run: ids from the gaps, slice by slice as they land
         if (!use_default || use_ws || a.item_order == nullptr)
           return pscl_fail(ctx, PSCL_ESTATE, "a staged pileup image can only be scored whole by k_demux_default");
