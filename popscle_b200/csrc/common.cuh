@@ -122,7 +122,11 @@ struct pscl_ctx {
   // demuxlet state
   int32_t nv = 0, geno_V = 0;
   double* gp = nullptr;       // [V][nv][3]
-  uint8_t* has_gp = nullptr;  // [V] or null (= all)
+  uint8_t* has_gp = nullptr;  // [V] or null (= all); points at has_gp_buf
+  uint8_t* has_gp_buf = nullptr;
+  size_t gp_cap = 0, has_gp_cap = 0, gp_code_cap = 0, gp_cls_cap = 0;  // set_geno keeps its buffers from call to call
+  uint8_t* geno_raw = nullptr; double* geno_err = nullptr; int* geno_bad = nullptr;  // ABI 4: the raw form before mixing
+  size_t geno_raw_cap = 0, geno_err_cap = 0, geno_bad_cap = 0;
   double* gpM = nullptr;      // [V][(3nv+1)&~1] 16-B padded genotype rows (k_demux_cls, built lazily)
   double* gpS = nullptr;      // [V][nv][2] (S_j, M_j) moments of the rows
   // dictionary-coded genotypes (demux.inl, built by pscl_demux_set_geno when nv <= 8): usable when *h_dict_over == 0

@@ -93,7 +93,8 @@ extern "C" void pscl_destroy(pscl_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   fmx_state_free(ctx);
   cudaFree(ctx->gp);
-  cudaFree(ctx->has_gp);
+  cudaFree(ctx->has_gp_buf);
+  cudaFree(ctx->geno_raw); cudaFree(ctx->geno_err); cudaFree(ctx->geno_bad);
   cudaFree(ctx->gpM);
   cudaFree(ctx->gpS);
   cudaFree(ctx->dm_cells);
@@ -156,6 +157,9 @@ extern "C" int pscl_set_partial_budget(pscl_ctx* ctx, size_t bytes) {
   ctx->partial_budget_bytes = bytes;
   return PSCL_OK;
 }
+
+// SNP id as stored: inside [0, V) whatever the input says (a malformed id raises the pileup's flag where it is found)
+__device__ __forceinline__ int pscl_clamp_snp(int id, int V) { return (unsigned)id < (unsigned)V ? id : 0; }
 
 // allele (0/1/2) and phred quality (<= 63) of one base-call packed into one byte
 __global__ void k_pack_reads(const uint8_t* __restrict__ al, const uint8_t* __restrict__ q,
@@ -231,13 +235,18 @@ __global__ void k_decode_snp(const int64_t* __restrict__ cell_ptr, const int32_t
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     const int off = run + inc - tot;
+    // (an id outside [0, V) raises the flag below; what is stored is clamped, because a pipelined run scores before it reads
+    // the flag and the kernels index their tables with these ids)
+    int y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = pscl_clamp_snp(off + x[i], V);
     if (p >= b && p + 8 <= e) {
       int4* dst = reinterpret_cast<int4*>(pair_snp + p);
-      dst[0] = make_int4(off + x[0], off + x[1], off + x[2], off + x[3]);
-      dst[1] = make_int4(off + x[4], off + x[5], off + x[6], off + x[7]);
+      dst[0] = make_int4(y[0], y[1], y[2], y[3]);
+      dst[1] = make_int4(y[4], y[5], y[6], y[7]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const int64_t q = p + i; if (q >= b && q < e) pair_snp[q] = off + x[i]; }
+      for (int i = 0; i < 8; ++i) { const int64_t q = p + i; if (q >= b && q < e) pair_snp[q] = y[i]; }
     }
     run = __shfl_sync(0xffffffffu, off + tot, 31);
     oob |= run < 0 || run >= V;  // ids are non-decreasing: the running maximum is the last one
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(PSCL_DEC8_NT) k_decode_snp8(const int64_t* __r
     for (int i = 0; i < PSCL_DEC8_PER; ++i) {
       const int64_t p = p0 + i;
       id += d[i];
-      if (p < e) { pair_snp[p] = id; oob |= id < 0 || id >= V; }
+      if (p < e) { pair_snp[p] = pscl_clamp_snp(id, V); oob |= id < 0 || id >= V; }
     }
     run += tot_sum;
   }
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(PSCL_DEC8_NT, 4) k_decode_cells(const int64_t*
       for (int i = 0; i < PSCL_DEC8_PER; ++i) {
         const int64_t p = p0 + i;
         id += d[i];
-        if (p < e) { pair_snp[p] = id; pair_rd[p] = (uint32_t)rd; if (id < 0 || id >= V) flag = 2; }
+        if (p < e) { pair_snp[p] = pscl_clamp_snp(id, V); pair_rd[p] = (uint32_t)rd; if (id < 0 || id >= V) flag = 2; }
         rd += f[i];
       }
       run_snp += (int)(unsigned)(ts & 0xffffffffu);
@@ -482,11 +491,11 @@ __global__ void k_rebase_u32(uint32_t* __restrict__ v, int64_t n, uint32_t base)
 }
 
 // wide forms: SNP ids inside [0, V), read offsets non-decreasing and <= N (the delta forms are checked while decoding)
-__global__ void k_check_pairs(const int32_t* __restrict__ pair_snp, const uint32_t* __restrict__ pair_rd, int64_t P, int32_t V, int64_t N,
+__global__ void k_check_pairs(int32_t* __restrict__ pair_snp, const uint32_t* __restrict__ pair_rd, int64_t P, int32_t V, int64_t N,
                               int check_snp, int* bad) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  if (check_snp && (unsigned)pair_snp[p] >= (unsigned)V) atomicExch(bad, 2);
+  if (check_snp && (unsigned)pair_snp[p] >= (unsigned)V) { atomicExch(bad, 2); pair_snp[p] = 0; }  // flagged; never used as an index
   const uint32_t a = pair_rd[p], b = pair_rd[p + 1];
   if (b < a || (int64_t)b > N) atomicExch(bad, 5);
 }

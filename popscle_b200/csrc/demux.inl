@@ -1012,13 +1012,23 @@ __global__ void k_geno_mix(const float* __restrict__ f32, const uint8_t* __restr
   }
 }
 
+// Device room for a genotype table (and its has_gp bytes): kept from one table to the next, grown when needed.
+static int demux_geno_reserve(pscl_ctx* ctx, size_t gp_bytes, size_t has_gp_bytes) {
+  int rc;
+  if ((rc = pscl_reserve(ctx, &ctx->gp, &ctx->gp_cap, gp_bytes)) != PSCL_OK) return rc;
+  ctx->has_gp = nullptr;
+  if (has_gp_bytes) {
+    if ((rc = pscl_reserve(ctx, &ctx->has_gp_buf, &ctx->has_gp_cap, has_gp_bytes)) != PSCL_OK) return rc;
+    ctx->has_gp = ctx->has_gp_buf;
+  }
+  return PSCL_OK;
+}
+
 // Tail of every way a genotype table gets onto the device (host copy, on-device mixing, NVLink peer copy): the
 // dictionary form of the table for k_demux_default (2 <= nv <= 8) — two small kernels, flag to a pinned word.
 static int demux_geno_finish(pscl_ctx* ctx, int32_t n_samples, int32_t n_snps) {
   ctx->nv = n_samples;
   ctx->geno_V = n_snps;
-  cudaFree(ctx->gp_code); ctx->gp_code = nullptr;
-  cudaFree(ctx->gp_cls); ctx->gp_cls = nullptr;
   ctx->dict_built = false;
   if (n_samples <= 8 && n_snps > 0 && ctx->h_dict_over) {
     if (!ctx->gp_dict) {
@@ -1026,8 +1036,11 @@ static int demux_geno_finish(pscl_ctx* ctx, int32_t n_samples, int32_t n_snps) {
       PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_key, sizeof(unsigned long long) * PSCL_DICT_N));
       PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_dict_over, sizeof(int)));
     }
-    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_code, sizeof(unsigned long long) * (size_t)n_snps));
-    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp_cls, sizeof(unsigned long long) * (size_t)n_snps));
+    // (buffers of a context are kept from one table to the next: a run per call must not pay cudaMalloc / cudaFree, which
+    // also synchronise the device)
+    int rc;
+    if ((rc = pscl_reserve(ctx, &ctx->gp_code, &ctx->gp_code_cap, sizeof(unsigned long long) * (size_t)n_snps)) != PSCL_OK) return rc;
+    if ((rc = pscl_reserve(ctx, &ctx->gp_cls, &ctx->gp_cls_cap, sizeof(unsigned long long) * (size_t)n_snps)) != PSCL_OK) return rc;
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict, 0, sizeof(double) * 3 * PSCL_DICT_N, ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_key, 0, sizeof(unsigned long long) * PSCL_DICT_N, ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp_dict_over, 0, sizeof(int), ctx->stream));
@@ -1053,46 +1066,46 @@ extern "C" int pscl_demux_set_geno(pscl_ctx* ctx, const pscl_geno* geno, int32_t
                      "pscl_demux_set_geno: need gp and n_samples >= 2 (the reference divides by nv-1, "
                      "cmd_cram_demuxlet.cpp:794)");
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaFree(ctx->gp); ctx->gp = nullptr;
-  cudaFree(ctx->has_gp); ctx->has_gp = nullptr;
-  cudaFree(ctx->gpM); ctx->gpM = nullptr;
-  cudaFree(ctx->gpS); ctx->gpS = nullptr;
+  if (ctx->gpM) { cudaFree(ctx->gpM); ctx->gpM = nullptr; }
+  if (ctx->gpS) { cudaFree(ctx->gpS); ctx->gpS = nullptr; }
   size_t bytes = sizeof(double) * (size_t)n_snps * geno->n_samples * 3;
-  PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp, bytes ? bytes : 16));
-  if (geno->has_gp) {
-    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->has_gp, n_snps ? n_snps : 16));
-    PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->has_gp, geno->has_gp, n_snps, cudaMemcpyHostToDevice, ctx->stream));
-  }
+  int rc;
+  if ((rc = demux_geno_reserve(ctx, bytes, geno->has_gp ? (size_t)n_snps : 0)) != PSCL_OK) return rc;
+  if (geno->has_gp) PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->has_gp, geno->has_gp, n_snps, cudaMemcpyHostToDevice, ctx->stream));
   if (geno->gp) {
     PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->gp, geno->gp, bytes, cudaMemcpyHostToDevice, ctx->stream));
   } else if (n_snps > 0) {  // ABI 4 raw posteriors: copy the small form, mix on the device
     const size_t cells = (size_t)n_snps * geno->n_samples;
-    float* d_f32 = nullptr; uint8_t* d_gt8 = nullptr; double* d_err = nullptr; int* d_bad = nullptr;
-    PSCL_CUDA(ctx, cudaMalloc((void**)&d_bad, sizeof(int)));
+    // scratch for the small form: the context's own, kept from call to call (not the block cache: a block handed back there
+    // could be given out again, in this same call, to an array the copy stream fills while k_geno_mix still reads it)
+    float* d_f32 = nullptr; uint8_t* d_gt8 = nullptr; double* d_err = nullptr;
+    int rc2;
+    if ((rc2 = pscl_reserve(ctx, &ctx->geno_bad, &ctx->geno_bad_cap, sizeof(int))) != PSCL_OK) return rc2;
+    int* const d_bad = ctx->geno_bad;
     PSCL_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
     PSCL_CUDA(ctx, cudaMemsetAsync(ctx->gp, 0, bytes, ctx->stream));  // rows of SNPs without GP stay zero
+    if ((rc2 = pscl_reserve(ctx, &ctx->geno_raw, &ctx->geno_raw_cap, geno->gt8 ? cells : sizeof(float) * cells * 3)) != PSCL_OK) return rc2;
     if (geno->gt8) {
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_gt8, cells));
+      d_gt8 = ctx->geno_raw;
       PSCL_CUDA(ctx, cudaMemcpyAsync(d_gt8, geno->gt8, cells, cudaMemcpyHostToDevice, ctx->stream));
     } else {
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_f32, sizeof(float) * cells * 3));
+      d_f32 = reinterpret_cast<float*>(ctx->geno_raw);
       PSCL_CUDA(ctx, cudaMemcpyAsync(d_f32, geno->gp_f32, sizeof(float) * cells * 3, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (geno->geno_err_snp) {
-      PSCL_CUDA(ctx, cudaMalloc((void**)&d_err, sizeof(double) * n_snps));
+      if ((rc2 = pscl_reserve(ctx, &ctx->geno_err, &ctx->geno_err_cap, sizeof(double) * n_snps)) != PSCL_OK) return rc2;
+      d_err = ctx->geno_err;
       PSCL_CUDA(ctx, cudaMemcpyAsync(d_err, geno->geno_err_snp, sizeof(double) * n_snps, cudaMemcpyHostToDevice, ctx->stream));
     }
     k_geno_mix<<<(unsigned)((n_snps + 127) / 128), 128, 0, ctx->stream>>>(d_f32, d_gt8, d_err, geno->geno_err, n_snps, geno->n_samples, ctx->has_gp,
                                                                            ctx->gp, d_bad);
     ctx->launches++;
     PSCL_CUDA(ctx, cudaGetLastError());
-    cudaFree(d_f32); cudaFree(d_gt8); cudaFree(d_err);
     // codes other than 0/1/2 are an input error; the flag travels to a pinned word and pscl_demux_score reads it
     if (ctx->h_geno_bad) {
       *ctx->h_geno_bad = 0;
       PSCL_CUDA(ctx, cudaMemcpyAsync(ctx->h_geno_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    cudaFree(d_bad);
   } else if (ctx->h_geno_bad) {
     *ctx->h_geno_bad = 0;
   }

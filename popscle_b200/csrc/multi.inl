@@ -197,14 +197,12 @@ static void multi_balanced_cuts(const int64_t* ptr, int64_t n, int parts, int64_
 static int demux_set_geno_peer(pscl_ctx* ctx, const pscl_ctx* src, cudaEvent_t src_ready) {
   PsclScope scope__(ctx);
   PSCL_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaFree(ctx->gp); ctx->gp = nullptr;
-  cudaFree(ctx->has_gp); ctx->has_gp = nullptr;
   const size_t bytes = sizeof(double) * (size_t)src->geno_V * src->nv * 3;
-  PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->gp, bytes ? bytes : 16));
+  int rc;
+  if ((rc = demux_geno_reserve(ctx, bytes, src->has_gp ? (size_t)src->geno_V : 0)) != PSCL_OK) return rc;
   PSCL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, src_ready, 0));
   PSCL_CUDA(ctx, cudaMemcpyPeerAsync(ctx->gp, ctx->device, src->gp, src->device, bytes, ctx->stream));
   if (src->has_gp) {
-    PSCL_CUDA(ctx, cudaMalloc((void**)&ctx->has_gp, src->geno_V ? src->geno_V : 16));
     PSCL_CUDA(ctx, cudaMemcpyPeerAsync(ctx->has_gp, ctx->device, src->has_gp, src->device, (size_t)src->geno_V, ctx->stream));
   }
   if (ctx->h_geno_bad) *ctx->h_geno_bad = 0;
