@@ -148,3 +148,18 @@ def test_raw_genotype_forms_build_the_right_struct():
     assert g.gt8 is None and g.gp_f32 == keep[0].ctypes.data and g.geno_err_snp == keep[1].ctypes.data and g.has_gp == keep[2].ctypes.data
     g, keep, V, nv = Context._geno(np.zeros((7, 3, 3)), None)
     assert g.gp == keep[0].ctypes.data and g.gt8 is None and g.gp_f32 is None and g.geno_err_snp is None
+
+
+def test_every_environment_switch_is_documented():
+    """each getenv("PSCL_...") of the library and the C++ host is named in INTEGRATION.md, the header or DESIGN.md"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "popscle_b200", "csrc", "*")) + glob.glob(os.path.join(root, "popscle_b200", "host", "*")):
+        if os.path.isfile(f):
+            names |= set(re.findall(r'getenv\("(PSCL_[A-Z0-9_]+)"\)', open(f, errors="ignore").read()))
+    assert len(names) >= 15
+    docs = "".join(open(os.path.join(root, f)).read() for f in ("INTEGRATION.md", "DESIGN.md", os.path.join("include", "popscle_b200.h")))
+    missing = sorted(n for n in names if n not in docs)
+    assert not missing, missing
